@@ -1,0 +1,139 @@
+/*
+ * mktfhe_b200.h -- C ABI of libmktfhe_b200.so, the B200 (sm_100a) engine for the
+ * bootstrapped-gate path of the 3rd-generation multi-key TFHE scheme of
+ * Animesh005/Torus-FHE.
+ *
+ * The reference has no FFI layer: its seam is the set of plain Julia functions
+ * exported from module TFHE (3-gen-mk-tfhe/src/TFHE.jl:113-119, 177-196).  Each
+ * entry point below names the reference function (file:line, relative to
+ * 3-gen-mk-tfhe/src/) it replaces; INTEGRATION.md shows the Julia `ccall`
+ * binding and the Python `ctypes` binding.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative MKTFHE_E* code; the
+ *    message is available from mktfhe_last_error().  No exceptions or aborts
+ *    cross this boundary.
+ *  - one context = one GPU, used by one host thread at a time.  Multi-GPU = one
+ *    context per process/rank (torch.distributed / torchrun), gates sharded by
+ *    the host, keys broadcast once (mktfhe_key_buffers + NCCL).
+ *  - plain (non-_dev) entry points take HOST pointers; the caller owns them and
+ *    nothing is retained after return except uploaded keys (copied).
+ *  - *_dev entry points take DEVICE pointers valid on the context's GPU and a
+ *    cudaStream_t (as void*, NULL = the context's own stream); they are
+ *    asynchronous with respect to the host.
+ *  - ciphertext layout: MKLweSample (mk_internals.jl:23-37) `a::Array{Int32,2}`
+ *    of shape (n, k), column-major == int32 [k][n] per sample; batches are
+ *    int32 a[G][k][n], int32 b[G].
+ */
+#ifndef MKTFHE_B200_H
+#define MKTFHE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MKTFHE_OK 0
+#define MKTFHE_EINVAL (-1)   /* bad argument / unsupported parameter set */
+#define MKTFHE_ECUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define MKTFHE_ESTATE (-3)   /* keys not loaded / not finalized */
+#define MKTFHE_ENOMEM (-4)
+
+/* gate ids; the linear prologue constants are those of 3gen_mk_gates.jl */
+#define MKTFHE_GATE_NAND 0   /* mk_gate_nand_3gen  3gen_mk_gates.jl:8-14   +1/8 - x - y   */
+#define MKTFHE_GATE_OR 1     /* mk_gate_or_3gen    3gen_mk_gates.jl:24-30  +1/8 + x + y   */
+#define MKTFHE_GATE_AND 2    /* mk_gate_and_3gen   3gen_mk_gates.jl:40-46  -1/8 + x + y   */
+#define MKTFHE_GATE_XOR 3    /* mk_gate_xor_3gen   3gen_mk_gates.jl:68-74  +1/4 + 2x + 2y */
+#define MKTFHE_GATE_AND3 4   /* mk_gate_3and_3gen  3gen_mk_gates.jl:55-64  -1/4 + x+y+z   */
+
+/* Integer part of SchemeParameters_3gen (api.jl:50-67); rlwe_mask_size = 1 and
+ * rlwe_is32 = false as in every 3gen set (mk_api.jl:32-322).  Supported:
+ * N = 1024, 1 <= l <= 4, l*bgbit <= 32 and 2l*N*2^(bgbit-1) < 2^30 (so the
+ * two-limb Goldilocks product is exact), n*k <= 8192, t*basebit <= 31. */
+typedef struct {
+    int32_t n;        /* lwe_size */
+    int32_t N;        /* rlwe_polynomial_degree */
+    int32_t k;        /* parties */
+    int32_t l;        /* gsw_decomp_length */
+    int32_t bgbit;    /* gsw_log2_base */
+    int32_t t;        /* ks_decomp_length */
+    int32_t basebit;  /* ks_log2_base */
+    int32_t reserved;
+} mktfhe_params;
+
+typedef struct mktfhe_ctx mktfhe_ctx;
+
+/* -- lifetime ----------------------------------------------------------- */
+int mktfhe_create(const mktfhe_params *params, int device, mktfhe_ctx **out);
+void mktfhe_destroy(mktfhe_ctx *ctx);
+/* message of the last failing call on ctx (ctx == NULL: last mktfhe_create failure) */
+const char *mktfhe_last_error(const mktfhe_ctx *ctx);
+
+/* -- keys ---------------------------------------------------------------- */
+/* Replaces TransformedBootstrapKeyPart_3gen(bk::BootstrapKeyPart_3gen)
+ * (3gen_mk_internals.jl:45-55): takes party `party`'s INTEGER key
+ * bk.gsw_key[j].part_{1..4}[q].coeffs as int64 [n][4][l][N] (host), splits every
+ * polynomial in two 32-bit limbs, NTT-transforms them on the GPU and stores them
+ * in the streaming layout of the blind-rotate kernel. */
+int mktfhe_load_bsk(mktfhe_ctx *ctx, int party, const int64_t *polys);
+/* KeyswitchKey.key::Array{LweSample,3} of dims (base-1, t, N) (keyswitch.jl:7-42),
+ * flattened as int32 [N][t][base-1][n+1] (a[0..n-1] then b), host. */
+int mktfhe_load_ksk(mktfhe_ctx *ctx, int party, const int32_t *rows);
+/* all parties loaded (or received through mktfhe_key_buffers) -> ready */
+int mktfhe_finalize_keys(mktfhe_ctx *ctx);
+/* device-resident key buffers, for a one-time NCCL broadcast from rank 0:
+ * non-root ranks receive into these pointers, then call mktfhe_finalize_keys
+ * with no loads. */
+int mktfhe_key_buffers(mktfhe_ctx *ctx, void **bsk_dev, size_t *bsk_bytes, void **ksk_dev, size_t *ksk_bytes);
+int mktfhe_mark_keys_received(mktfhe_ctx *ctx);
+
+/* -- the hot path ---------------------------------------------------------- */
+/* mk_bootstrap_3gen(bk, ks, mu, x) (3gen_mk_internals.jl:112-116) on a batch:
+ * mod-switch, blind rotate over the k*n key elements, sample extraction
+ * (rlwe_extract_sample_64, rlwe.jl:70-74) and mk_keyswitch_3gen
+ * (mk_internals.jl:730-744).  mu is the Torus64 test-vector message. */
+int mktfhe_bootstrap_batch(mktfhe_ctx *ctx, int64_t mu, size_t G, const int32_t *a_in, const int32_t *b_in,
+                           int32_t *a_out, int32_t *b_out);
+/* mk_gate_{nand,or,and,xor,3and}_3gen(bk, ks, x, y[, z]) (3gen_mk_gates.jl:8-74)
+ * on a batch: linear prologue fused into the bootstrap; output message
+ * encode_message64(1, 8) = 2^61.  za/zb are only read for MKTFHE_GATE_AND3. */
+int mktfhe_gate_batch(mktfhe_ctx *ctx, int gate, size_t G, const int32_t *xa, const int32_t *xb,
+                      const int32_t *ya, const int32_t *yb, const int32_t *za, const int32_t *zb,
+                      int32_t *oa, int32_t *ob);
+/* device-pointer variants (inputs/outputs resident in HBM) */
+int mktfhe_bootstrap_batch_dev(mktfhe_ctx *ctx, int64_t mu, size_t G, const int32_t *a_in, const int32_t *b_in,
+                               int32_t *a_out, int32_t *b_out, void *stream);
+int mktfhe_gate_batch_dev(mktfhe_ctx *ctx, int gate, size_t G, const int32_t *xa, const int32_t *xb,
+                          const int32_t *ya, const int32_t *yb, const int32_t *za, const int32_t *zb,
+                          int32_t *oa, int32_t *ob, void *stream);
+
+/* -- parity hooks (host pointers; one call per stage of the path) ---------- */
+/* tgsw_extern_mul_3gen(accum, bk[party].gsw_key[j]) (tgsw_3gen.jl:102-113) for
+ * G accumulators: acc = int64 [G][2][N] with [0] = mask (accum.a[1]) and
+ * [1] = body (accum.a[2]); elem[g] = party*n + j. */
+int mktfhe_extprod_batch(mktfhe_ctx *ctx, size_t G, const int32_t *elem, const int64_t *acc_in, int64_t *acc_out);
+/* mk_bootstrap_wo_keyswitch_3gen (3gen_mk_internals.jl:99-109): returns the
+ * extracted sample ext = int32 [G][N+1] (a'[0..N-1], b') and, if acc_out is not
+ * NULL, the final accumulator int64 [G][2][N]. */
+int mktfhe_blind_rotate_batch(mktfhe_ctx *ctx, int64_t mu, size_t G, const int32_t *a_in, const int32_t *b_in,
+                              int32_t *ext_out, int64_t *acc_out);
+/* mk_keyswitch_3gen (mk_internals.jl:730-744) on ext = int32 [G][N+1] */
+int mktfhe_keyswitch_batch(mktfhe_ctx *ctx, size_t G, const int32_t *ext, int32_t *a_out, int32_t *b_out);
+/* exact negacyclic products c = a * b mod (X^N+1, 2^64) through the same NTT:
+ * a = int64 [G][N] with |a_i| < 2^15 ("digit" operand), b = int64 [G][N]. */
+int mktfhe_negacyclic_mul_batch(mktfhe_ctx *ctx, size_t G, const int64_t *a, const int64_t *b, int64_t *c);
+
+/* -- introspection ---------------------------------------------------------- */
+/* kernels launched by this context so far */
+uint64_t mktfhe_launch_count(const mktfhe_ctx *ctx);
+/* device time (ms, CUDA events on the launching stream) of the blind-rotate and
+ * key-switch kernels of the most recent batch call; blocks until they finished */
+int mktfhe_last_kernel_ms(mktfhe_ctx *ctx, float *blind_rotate_ms, float *keyswitch_ms);
+/* bytes of the streamed bootstrapping key read per gate (2 limbs) and of ksk rows per gate */
+int mktfhe_algorithmic_bytes(const mktfhe_ctx *ctx, double *bsk_bytes_per_gate, double *ksk_bytes_per_gate);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

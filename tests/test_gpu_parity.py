@@ -1,0 +1,226 @@
+"""GPU parity tests: every stage of the path, through the C ABI, against the CPU oracle on identical
+key and ciphertext bytes.  Bar: bit-exact (integer path).  Run with `pytest -m gpu` on a B200."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import DATA_SEED, GOLDEN, make_engine
+
+pytestmark = pytest.mark.gpu
+
+MU = 1 << 61   # encode_message64(1, 8)
+
+
+def test_library_is_native_and_loaded(engine2):
+    import torus_fhe_b200 as T
+    with open("/proc/self/maps") as f:
+        assert "libmktfhe_b200.so" in f.read()
+    assert engine2.ctx.launch_count() > 0   # the key transform already ran on the GPU
+
+
+def test_negacyclic_mul_vs_schoolbook(oracle, engine2, rng):
+    N, G = 1024, 6
+    a = rng.integers(-64, 64, size=(G, N), dtype=np.int64)
+    b = rng.integers(-2 ** 63, 2 ** 63 - 1, size=(G, N), dtype=np.int64)
+    a[1], b[1] = -64, -1                      # extreme magnitudes
+    a[2] = rng.integers(-2 ** 14, 2 ** 14, size=N)   # widest "digit" operand the hook promises
+    a[3], b[3] = 0, b[3]
+    got = engine2.ctx.negacyclic_mul_batch(a, b)
+    for g in range(G):
+        assert np.array_equal(got[g], oracle.negacyclic_mul(a[g], b[g], oracle.EXACT_SCHOOLBOOK)), g
+
+
+def test_extprod_bit_exact(oracle, keys2, engine2, rng):
+    """tgsw_extern_mul_3gen on random accumulators and real key rows: GPU == exact oracle, bit for bit."""
+    G = 24
+    acc = rng.integers(-2 ** 63, 2 ** 63 - 1, size=(G, 2, 1024), dtype=np.int64)
+    acc[0] = 0
+    acc[1] = -1
+    acc[2] = np.int64(2 ** 63 - 1)
+    acc[3] = np.int64(-2 ** 63)
+    elem = rng.integers(0, 2 * 520, size=G).astype(np.int32)
+    elem[:4] = [0, 519, 520, 1039]
+    got = engine2.ctx.extprod_batch(elem, acc)
+    for g in range(G):
+        party, j = divmod(int(elem[g]), 520)
+        backend = oracle.EXACT_SCHOOLBOOK if g < 6 else oracle.EXACT_NTT
+        assert np.array_equal(got[g], keys2.extprod(backend, party, j, acc[g])), g
+    # Float64 FFT restatement of the reference within 2^-38 of the torus on identical inputs (SURVEY H9 i)
+    with np.errstate(over="ignore"):
+        d = (keys2.extprod(oracle.FFT, 0, 0, acc[5]) - engine2.ctx.extprod_batch(np.array([0], np.int32), acc[5:6])[0]).astype(np.float64)
+    assert np.abs(d).max() <= 2.0 ** 26
+
+
+def test_blind_rotate_golden_and_oracle(oracle, keys2, engine2):
+    """mk_bootstrap_wo_keyswitch_3gen: accumulator and extracted sample bit-exact vs the committed fixture and the oracle."""
+    data = np.load(os.path.join(GOLDEN, "nand_2party.npz"))
+    with np.errstate(over="ignore"):
+        ta = (-data["xa"] - data["ya"]).astype(np.int32)
+        tb = (np.int32(1 << 29) - data["xb"] - data["yb"]).astype(np.int32)
+    ext, acc = engine2.ctx.blind_rotate_batch(MU, ta, tb, want_acc=True)
+    assert np.array_equal(ext, data["ext"])
+    for g in range(ext.shape[0]):
+        assert hashlib.sha256(acc[g].tobytes()).hexdigest() == str(data["acc_sha256"][g])
+    ea, eb, oacc, _ = keys2.bootstrap_wo_keyswitch(oracle.EXACT_NTT, MU, ta[0], tb[0], want_acc=True)
+    assert np.array_equal(acc[0], oacc) and np.array_equal(ext[0, :1024], ea) and ext[0, 1024] == eb
+
+
+def test_blind_rotate_edge_inputs(oracle, keys2, engine2, rng):
+    """bara == 0 everywhere (all steps skipped), extreme mask words, and b on the rounding boundary."""
+    G = 4
+    a = np.zeros((G, 2, 520), np.int32)
+    b = np.array([0, (1 << 20) - 1, 1 << 20, -(2 ** 31)], np.int32)
+    a[1] = (1 << 20) - 1            # rounds to 0 -> skipped
+    a[2, :, ::7] = 2 ** 31 - 1      # wraps to -1024
+    a[3] = rng.integers(-2 ** 31, 2 ** 31, size=(2, 520))
+    a[3, 0, :100] = 0
+    ext, acc = engine2.ctx.blind_rotate_batch(MU, a, b, want_acc=True)
+    for g in range(G):
+        ea, eb, oacc, _ = keys2.bootstrap_wo_keyswitch(oracle.EXACT_NTT, MU, a[g], b[g], want_acc=True)
+        assert np.array_equal(acc[g], oacc), g
+        assert np.array_equal(ext[g, :1024], ea) and ext[g, 1024] == eb, g
+    assert np.all(acc[0][0] == 0) and np.all(acc[0][1] == MU)   # untouched trivial accumulator
+
+
+def test_keyswitch_bit_exact(oracle, keys2, engine2, rng):
+    G = 8
+    ext = rng.integers(-2 ** 31, 2 ** 31, size=(G, 1025)).astype(np.int32)
+    ext[0] = 0
+    ext[1, :1024] = -(1 << 22)      # + prec_offset = 0: every digit zero, every row skipped
+    ext[2] = 2 ** 31 - 1
+    oa, ob = engine2.ctx.keyswitch_batch(ext)
+    for g in range(G):
+        ra, rb = keys2.keyswitch(ext[g, :1024], ext[g, 1024])
+        assert np.array_equal(oa[g], ra) and ob[g] == rb, g
+    assert np.all(oa[1] == 0) and ob[1] == ext[1, 1024]
+
+
+def test_nand_golden_fixture(engine2):
+    import torus_fhe_b200 as T
+    data = np.load(os.path.join(GOLDEN, "nand_2party.npz"))
+    oa, ob = engine2.ctx.gate_batch(T._cabi.GATE_NAND, (data["xa"], data["xb"]), (data["ya"], data["yb"]))
+    assert np.array_equal(oa, data["out_a"]) and np.array_equal(ob, data["out_b"])
+
+
+@pytest.mark.parametrize("gate", ["nand", "or", "and", "xor", "and3"])
+def test_gates_bit_exact_and_truth(oracle, keys2, engine2, gate):
+    """All five bootstrapped gates: outputs bit-exact vs the oracle's exact path; decryptions equal the plain gate and
+    the Float64-FFT restatement of the reference."""
+    import torus_fhe_b200 as T
+    gid = {"nand": T._cabi.GATE_NAND, "or": T._cabi.GATE_OR, "and": T._cabi.GATE_AND, "xor": T._cabi.GATE_XOR, "and3": T._cabi.GATE_AND3}[gate]
+    bits = np.array([[a, b, c] for a in (0, 1) for b in (0, 1) for c in (0, 1)], np.uint8)
+    x, y, z = keys2.encrypt(bits[:, 0], DATA_SEED + 1), keys2.encrypt(bits[:, 1], DATA_SEED + 2), keys2.encrypt(bits[:, 2], DATA_SEED + 3)
+    zz = z if gate == "and3" else None
+    oa, ob = engine2.ctx.gate_batch(gid, x, y, zz)
+    ra, rb = keys2.gate_batch(oracle.EXACT_NTT, gid, x, y, zz)
+    assert np.array_equal(oa, ra) and np.array_equal(ob, rb)
+    xb, yb, zb = (bits[:, i].astype(bool) for i in range(3))
+    exp = {"nand": ~(xb & yb), "or": xb | yb, "and": xb & yb, "xor": xb ^ yb,
+           "and3": (xb & yb & zb) | ~(xb | yb | zb)}[gate]   # 3AND(0,0,0) = true in the reference (phase wrap)
+    assert np.array_equal(keys2.decrypt(oa, ob), exp)
+    fa, fb = keys2.gate_batch(oracle.FFT, gid, x, y, zz)
+    assert np.array_equal(keys2.decrypt(fa, fb), exp)
+    # torus phase vs the FFT path: |delta| <= 2^-20 whenever the digit streams coincide (SURVEY H9 ii); otherwise the FFT path
+    # is an independent noise realisation and only the noise level can be bounded
+    d = (keys2.phase(oa, ob).astype(np.int64) - keys2.phase(fa, fb).astype(np.int64) + 2 ** 31) % 2 ** 32 - 2 ** 31
+    assert np.abs(d).max() < 2 ** 32 * 0.06
+
+
+def test_phase_vs_fft_conditional_bound(oracle, keys2, engine2):
+    """North-star tolerance: |phase_GPU - phase_FFT| <= 2^-20 of the torus, asserted on the bootstraps whose exact and FFT digit
+    streams coincide (the FFT path's ~2^27 float error can flip a gadget digit, after which the trajectories diverge: fact 11)."""
+    bits = np.array([0, 1, 1, 0, 1, 0], np.uint8)
+    x = keys2.encrypt(bits, DATA_SEED + 9)
+    ext, _ = engine2.ctx.blind_rotate_batch(MU, x[0], x[1])
+    same = 0
+    for g in range(bits.size):
+        ea, eb, _, dl_exact = keys2.bootstrap_wo_keyswitch(oracle.EXACT_NTT, MU, x[0][g], x[1][g], want_digits=True)
+        fa, fb, _, dl_fft = keys2.bootstrap_wo_keyswitch(oracle.FFT, MU, x[0][g], x[1][g], want_digits=True)
+        assert np.array_equal(ext[g, :1024], ea) and ext[g, 1024] == eb
+        if np.array_equal(dl_exact, dl_fft):
+            same += 1
+            # extracted samples are Torus32: 2^-20 of the torus = 2^12 units
+            d = (np.concatenate([ea, [eb]]).astype(np.int64) - np.concatenate([fa, [fb]]).astype(np.int64) + 2 ** 31) % 2 ** 32 - 2 ** 31
+            assert np.abs(d).max() <= 2 ** 12
+    assert same >= 1, "expected most bootstraps to share the digit stream (measured 84 % in the survey)"
+
+
+def test_full_batch_properties(keys2, engine2):
+    """BASELINE config 2 at full size: 16384 NAND gates on valid encryptions of random bits; size-independent checks:
+    decryptions equal the plain NAND, output phases sit at +-1/8 within noise, and the batch is order-independent."""
+    import torus_fhe_b200 as T
+    G = 16384
+    r = np.random.default_rng(DATA_SEED)
+    xs, ys = r.integers(0, 2, G).astype(np.uint8), r.integers(0, 2, G).astype(np.uint8)
+    x, y = keys2.encrypt(xs, DATA_SEED), keys2.encrypt(ys, DATA_SEED + 77)
+    oa, ob = engine2.ctx.gate_batch(T._cabi.GATE_NAND, x, y)
+    assert np.array_equal(keys2.decrypt(oa, ob), ~(xs.astype(bool) & ys.astype(bool)))
+    ph = keys2.phase(oa, ob).astype(np.float64) / 2 ** 32
+    assert np.abs(np.abs(ph) - 0.125).max() < 0.06
+    perm = r.permutation(G)[:512]
+    pa, pb = engine2.ctx.gate_batch(T._cabi.GATE_NAND, (x[0][perm], x[1][perm]), (y[0][perm], y[1][perm]))
+    assert np.array_equal(pa, oa[perm]) and np.array_equal(pb, ob[perm])
+
+
+def test_ragged_and_empty_batches(keys2, engine2):
+    import torus_fhe_b200 as T
+    e = np.empty((0, 2, 520), np.int32), np.empty(0, np.int32)
+    oa, ob = engine2.ctx.gate_batch(T._cabi.GATE_NAND, e, e)
+    assert oa.shape == (0, 2, 520) and ob.shape == (0,)
+    bits = np.array([1, 0, 1], np.uint8)
+    x = keys2.encrypt(bits, 5)
+    one = engine2.ctx.gate_batch(T._cabi.GATE_AND, (x[0][:1], x[1][:1]), (x[0][:1], x[1][:1]))
+    three = engine2.ctx.gate_batch(T._cabi.GATE_AND, x, x)
+    assert np.array_equal(one[0][0], three[0][0]) and one[1][0] == three[1][0]
+    assert np.array_equal(keys2.decrypt(*three), bits.astype(bool))
+
+
+def test_error_behaviour(keys2, engine2):
+    import torus_fhe_b200 as T
+    x = np.zeros((1, 2, 520), np.int32), np.zeros(1, np.int32)
+    with pytest.raises(T.MktfheError) as ei:
+        engine2.ctx.gate_batch(99, x, x)
+    assert ei.value.code == T._cabi.EINVAL
+    with pytest.raises(T.MktfheError) as ei:   # unsupported ring degree (16-party sets use N = 2048)
+        T._cabi.Context(590, 2048, 16, 1, 26, 4, 3)
+    assert ei.value.code == T._cabi.EINVAL
+    fresh = T._cabi.Context(520, 1024, 2, 2, 7, 3, 3)
+    with pytest.raises(T.MktfheError) as ei:   # keys never loaded
+        fresh.gate_batch(T._cabi.GATE_NAND, x, x)
+    assert ei.value.code == T._cabi.ESTATE
+    with pytest.raises(T.MktfheError) as ei:
+        fresh.finalize_keys()
+    assert ei.value.code == T._cabi.ESTATE
+    fresh.close()
+    with pytest.raises(ValueError):
+        engine2.ctx.gate_batch(T._cabi.GATE_NAND, (x[0][:, :1], x[1]), x)
+
+
+@pytest.mark.parametrize("pname", ["PARAMS_4PARTY", "PARAMS_8PARTY"])
+def test_more_parties(oracle, pname):
+    """BASELINE config 3: 4- and 8-party parameter sets (mk_api.jl:84-90, 140-146): l = 3 / 4, longer blind rotation."""
+    import torus_fhe_b200 as T
+    ks = oracle.KeySet(getattr(oracle, pname), seed=0xB20000A1 + 4, nthreads=os.cpu_count() or 8)
+    eng = make_engine(ks)
+    try:
+        bits = np.array([[0, 0], [0, 1], [1, 0], [1, 1]], np.uint8)
+        x, y = ks.encrypt(bits[:, 0], 31), ks.encrypt(bits[:, 1], 32)
+        acc = np.random.default_rng(3).integers(-2 ** 63, 2 ** 63 - 1, size=(3, 2, 1024), dtype=np.int64)
+        elem = np.array([0, ks.n, ks.k * ks.n - 1], np.int32)
+        got = eng.ctx.extprod_batch(elem, acc)
+        for g in range(3):
+            party, j = divmod(int(elem[g]), ks.n)
+            assert np.array_equal(got[g], keys_extprod(ks, oracle, party, j, acc[g])), g
+        oa, ob = eng.ctx.gate_batch(T._cabi.GATE_NAND, x, y)
+        ra, rb = ks.gate_batch(oracle.EXACT_NTT, oracle.GATE_NAND, x, y)
+        assert np.array_equal(oa, ra) and np.array_equal(ob, rb)
+        assert np.array_equal(ks.decrypt(oa, ob), ~(bits[:, 0].astype(bool) & bits[:, 1].astype(bool)))
+    finally:
+        eng.close()
+
+
+def keys_extprod(ks, oracle, party, j, acc):
+    return ks.extprod(oracle.EXACT_SCHOOLBOOK, party, j, acc)

@@ -1,0 +1,15 @@
+"""torus-fhe_b200: B200-native engine behind the 3gen multi-key TFHE gate API of
+Animesh005/Torus-FHE (3-gen-mk-tfhe/).  Import as `torus_fhe_b200` (the root shim
+`torus_fhe_b200.py` maps the importable name onto this directory).
+
+  _cabi.py     ctypes binding of the C ABI (include/mktfhe_b200.h) -> libmktfhe_b200.so
+  engine.py    GPU context + key loading/broadcast + batch sharding
+  tfhe3gen.py  the reference's exported names (gates, bootstrap, keys, encrypt/decrypt)
+  circuits.py  level-batched integer circuits (mk_add_3gen, mk_sub_3gen, ...)
+  csrc/        hand-written sm_100a kernels and the C ABI implementation
+"""
+from . import _cabi
+from ._cabi import MktfheError
+from .engine import Engine, shard_bounds, shard_batch
+from .tfhe3gen import *  # noqa: F401,F403
+from .tfhe3gen import engine_for, negacyclic_mul

@@ -1,0 +1,243 @@
+"""ctypes binding of libmktfhe_b200.so (C ABI declared in include/mktfhe_b200.h).
+
+This is the same boundary the Julia shim (julia/TFHE_B200.jl) binds with `ccall`.
+There is no fallback: if the shared library is missing or no sm_100a GPU is
+present, the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmktfhe_b200.so")
+
+OK, EINVAL, ECUDA, ESTATE, ENOMEM = 0, -1, -2, -3, -4
+GATE_NAND, GATE_OR, GATE_AND, GATE_XOR, GATE_AND3 = 0, 1, 2, 3, 4
+
+# every symbol include/mktfhe_b200.h declares
+EXPORTS = (
+    "mktfhe_create", "mktfhe_destroy", "mktfhe_last_error",
+    "mktfhe_load_bsk", "mktfhe_load_ksk", "mktfhe_finalize_keys", "mktfhe_key_buffers", "mktfhe_mark_keys_received",
+    "mktfhe_bootstrap_batch", "mktfhe_gate_batch", "mktfhe_bootstrap_batch_dev", "mktfhe_gate_batch_dev",
+    "mktfhe_extprod_batch", "mktfhe_blind_rotate_batch", "mktfhe_keyswitch_batch", "mktfhe_negacyclic_mul_batch",
+    "mktfhe_launch_count", "mktfhe_last_kernel_ms", "mktfhe_algorithmic_bytes",
+)
+
+
+class MktfheError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libmktfhe_b200 error {code}: {msg}")
+        self.code = code
+
+
+class CParams(C.Structure):
+    """mktfhe_params: integer part of SchemeParameters_3gen (3-gen-mk-tfhe/src/api.jl:50-67)."""
+    _fields_ = [("n", C.c_int32), ("N", C.c_int32), ("k", C.c_int32), ("l", C.c_int32),
+                ("bgbit", C.c_int32), ("t", C.c_int32), ("basebit", C.c_int32), ("reserved", C.c_int32)]
+
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile libmktfhe_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    import subprocess
+    out = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-s"], capture_output=True, text=True)
+    if verbose or out.returncode:
+        print(out.stdout[-4000:], out.stderr[-4000:])
+    if out.returncode:
+        raise RuntimeError("nvcc build of libmktfhe_b200.so failed")
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+    sigs = {
+        "mktfhe_create": (C.c_int, [C.POINTER(CParams), C.c_int, C.POINTER(vp)]),
+        "mktfhe_destroy": (None, [vp]),
+        "mktfhe_last_error": (C.c_char_p, [vp]),
+        "mktfhe_load_bsk": (C.c_int, [vp, C.c_int, vp]),
+        "mktfhe_load_ksk": (C.c_int, [vp, C.c_int, vp]),
+        "mktfhe_finalize_keys": (C.c_int, [vp]),
+        "mktfhe_key_buffers": (C.c_int, [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]),
+        "mktfhe_mark_keys_received": (C.c_int, [vp]),
+        "mktfhe_bootstrap_batch": (C.c_int, [vp, i64, sz, vp, vp, vp, vp]),
+        "mktfhe_gate_batch": (C.c_int, [vp, C.c_int, sz, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "mktfhe_bootstrap_batch_dev": (C.c_int, [vp, i64, sz, vp, vp, vp, vp, vp]),
+        "mktfhe_gate_batch_dev": (C.c_int, [vp, C.c_int, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "mktfhe_extprod_batch": (C.c_int, [vp, sz, vp, vp, vp]),
+        "mktfhe_blind_rotate_batch": (C.c_int, [vp, i64, sz, vp, vp, vp, vp]),
+        "mktfhe_keyswitch_batch": (C.c_int, [vp, sz, vp, vp, vp]),
+        "mktfhe_negacyclic_mul_batch": (C.c_int, [vp, sz, vp, vp, vp]),
+        "mktfhe_launch_count": (C.c_uint64, [vp]),
+        "mktfhe_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "mktfhe_algorithmic_bytes": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    }
+    assert set(sigs) == set(EXPORTS)
+    for name, (res, args) in sigs.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    _lib = L
+    return L
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+class Context:
+    """One mktfhe_ctx: one GPU, its keys, its stream."""
+
+    def __init__(self, n, N, k, l, bgbit, t, basebit, device=0):
+        L = lib()
+        self.prm = CParams(n, N, k, l, bgbit, t, basebit, 0)
+        self.n, self.N, self.k, self.l, self.bgbit, self.t, self.basebit = n, N, k, l, bgbit, t, basebit
+        self.device = device
+        h = C.c_void_p()
+        rc = L.mktfhe_create(C.byref(self.prm), device, C.byref(h))
+        if rc:
+            raise MktfheError(rc, L.mktfhe_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mktfhe_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _chk(self, rc):
+        if rc:
+            raise MktfheError(rc, lib().mktfhe_last_error(self.h).decode())
+
+    # -- keys
+    def load_bsk(self, party, polys):
+        """polys: int64 [n][4][l][N] = bk.gsw_key[j].part_{1..4}[q].coeffs (3gen_mk_internals.jl:10-43)."""
+        polys = _c(polys, np.int64)
+        if polys.size != self.n * 4 * self.l * self.N:
+            raise ValueError(f"bsk of party {party}: expected {(self.n, 4, self.l, self.N)}, got {polys.shape}")
+        self._chk(lib().mktfhe_load_bsk(self.h, party, _p(polys)))
+
+    def load_ksk(self, party, rows):
+        """rows: int32 [N][t][base-1][n+1] (keyswitch.jl:7-42)."""
+        rows = _c(rows, np.int32)
+        B1 = (1 << self.basebit) - 1
+        if rows.size != self.N * self.t * B1 * (self.n + 1):
+            raise ValueError(f"ksk of party {party}: expected {(self.N, self.t, B1, self.n + 1)}, got {rows.shape}")
+        self._chk(lib().mktfhe_load_ksk(self.h, party, _p(rows)))
+
+    def finalize_keys(self):
+        self._chk(lib().mktfhe_finalize_keys(self.h))
+
+    def key_buffers(self):
+        bp, bb, kp, kb = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
+        self._chk(lib().mktfhe_key_buffers(self.h, C.byref(bp), C.byref(bb), C.byref(kp), C.byref(kb)))
+        return (bp.value, bb.value), (kp.value, kb.value)
+
+    def mark_keys_received(self):
+        self._chk(lib().mktfhe_mark_keys_received(self.h))
+
+    # -- hot path, host buffers
+    def _ab(self, a, b):
+        b = _c(b, np.int32).reshape(-1)
+        a = _c(a, np.int32)
+        if a.size != b.size * self.k * self.n:
+            raise ValueError(f"ciphertext batch: a has {a.size} words, expected {b.size}*{self.k}*{self.n}")
+        return a, b
+
+    def bootstrap_batch(self, mu, a, b):
+        a, b = self._ab(a, b)
+        G = b.size
+        oa, ob = np.empty((G, self.k, self.n), np.int32), np.empty(G, np.int32)
+        self._chk(lib().mktfhe_bootstrap_batch(self.h, int(mu), G, _p(a), _p(b), _p(oa), _p(ob)))
+        return oa, ob
+
+    def gate_batch(self, gate, x, y, z=None, out=None):
+        xa, xb = self._ab(*x)
+        ya, yb = self._ab(*y)
+        G = xb.size
+        if yb.size != G:
+            raise ValueError("gate operands have different batch sizes")
+        za = zb = None
+        if z is not None:
+            za, zb = self._ab(*z)
+        if out is None:
+            oa, ob = np.empty((G, self.k, self.n), np.int32), np.empty(G, np.int32)
+        else:
+            oa, ob = out
+        self._chk(lib().mktfhe_gate_batch(self.h, gate, G, _p(xa), _p(xb), _p(ya), _p(yb), _p(za), _p(zb), _p(oa), _p(ob)))
+        return oa, ob
+
+    # -- hot path, device pointers (ints), asynchronous on `stream` (0 = context stream)
+    def bootstrap_batch_dev(self, mu, G, a_in, b_in, a_out, b_out, stream=0):
+        self._chk(lib().mktfhe_bootstrap_batch_dev(self.h, int(mu), G, a_in, b_in, a_out, b_out, stream or None))
+
+    def gate_batch_dev(self, gate, G, xa, xb, ya, yb, za, zb, oa, ob, stream=0):
+        self._chk(lib().mktfhe_gate_batch_dev(self.h, gate, G, xa, xb, ya, yb, za or None, zb or None, oa, ob, stream or None))
+
+    # -- parity hooks
+    def extprod_batch(self, elem, acc):
+        elem = _c(elem, np.int32).reshape(-1)
+        acc = _c(acc, np.int64)
+        G = elem.size
+        if acc.size != G * 2 * self.N:
+            raise ValueError("acc must be int64 [G][2][N]")
+        out = np.empty((G, 2, self.N), np.int64)
+        self._chk(lib().mktfhe_extprod_batch(self.h, G, _p(elem), _p(acc), _p(out)))
+        return out
+
+    def blind_rotate_batch(self, mu, a, b, want_acc=False):
+        a, b = self._ab(a, b)
+        G = b.size
+        ext = np.empty((G, self.N + 1), np.int32)
+        acc = np.empty((G, 2, self.N), np.int64) if want_acc else None
+        self._chk(lib().mktfhe_blind_rotate_batch(self.h, int(mu), G, _p(a), _p(b), _p(ext), _p(acc)))
+        return ext, acc
+
+    def keyswitch_batch(self, ext):
+        ext = _c(ext, np.int32)
+        G = ext.size // (self.N + 1)
+        if ext.size != G * (self.N + 1):
+            raise ValueError("ext must be int32 [G][N+1]")
+        oa, ob = np.empty((G, self.k, self.n), np.int32), np.empty(G, np.int32)
+        self._chk(lib().mktfhe_keyswitch_batch(self.h, G, _p(ext), _p(oa), _p(ob)))
+        return oa, ob
+
+    def negacyclic_mul_batch(self, a, b):
+        a, b = _c(a, np.int64), _c(b, np.int64)
+        G = a.size // self.N
+        if a.size != G * self.N or b.size != a.size:
+            raise ValueError("operands must be int64 [G][N]")
+        out = np.empty((G, self.N), np.int64)
+        self._chk(lib().mktfhe_negacyclic_mul_batch(self.h, G, _p(a), _p(b), _p(out)))
+        return out
+
+    # -- introspection
+    def launch_count(self):
+        return int(lib().mktfhe_launch_count(self.h))
+
+    def last_kernel_ms(self):
+        br, ks = C.c_float(), C.c_float()
+        self._chk(lib().mktfhe_last_kernel_ms(self.h, C.byref(br), C.byref(ks)))
+        return br.value, ks.value
+
+    def algorithmic_bytes(self):
+        b, k = C.c_double(), C.c_double()
+        self._chk(lib().mktfhe_algorithmic_bytes(self.h, C.byref(b), C.byref(k)))
+        return b.value, k.value

@@ -1,0 +1,485 @@
+// mktfhe_b200.cu -- C ABI (include/mktfhe_b200.h) over the sm_100a kernels in kernels.cuh.
+//
+// One context owns one GPU: the NTT-domain bootstrapping key (two 32-bit limbs per
+// reference polynomial), the key-switching key, the twiddle tables, one stream and
+// growable device staging buffers.  There is no CPU fallback: every entry point
+// either launches the CUDA kernels or returns an error code.
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mktfhe_b200.h"
+#include "kernels.cuh"
+#include "tables.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct mktfhe_ctx {
+    mktfhe_params prm{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // br start/stop, ks start/stop
+    bool ev_valid = false;
+    u64* d_bsk = nullptr;
+    size_t bsk_bytes = 0;
+    int32_t* d_ksk = nullptr;
+    size_t ksk_bytes = 0;
+    u64* d_tw_fwd = nullptr;
+    u64* d_tw_inv = nullptr;
+    std::vector<char> bsk_loaded, ksk_loaded;
+    bool ready = false;
+    DevBuf in[6], ext, oa, ob, accin, accout, elem, raw;
+    uint64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(mktfhe_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU_TRY(ctx, call)                                                                     \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? MKTFHE_ENOMEM : MKTFHE_ECUDA,  \
+                        "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int reserve(mktfhe_ctx* c, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return MKTFHE_OK;
+    if (b.p) CU_TRY(c, cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    CU_TRY(c, cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    return MKTFHE_OK;
+}
+
+int check_params(const mktfhe_params* p) {
+    if (!p) return fail(nullptr, MKTFHE_EINVAL, "params is NULL");
+    if (p->N != mk::N) return fail(nullptr, MKTFHE_EINVAL, "unsupported N=%d (only 1024)", p->N);
+    if (p->l < 1 || p->l > 4) return fail(nullptr, MKTFHE_EINVAL, "unsupported gsw_decomp_length l=%d (1..4)", p->l);
+    if (p->bgbit < 1 || p->l * p->bgbit > 32) return fail(nullptr, MKTFHE_EINVAL, "unsupported l*bgbit=%d (<=32)", p->l * p->bgbit);
+    // exactness of the two-limb Goldilocks product: 2l * N * 2^(bgbit-1) * 2^32 < p/2
+    if ((double)(2 * p->l) * p->N * (double)(1u << (p->bgbit - 1)) >= (double)(1u << 30))
+        return fail(nullptr, MKTFHE_EINVAL, "2l*N*Bg/2 too large for the two-limb exact product");
+    if (p->k < 1 || p->n < 1 || (long long)p->n * p->k > 8192) return fail(nullptr, MKTFHE_EINVAL, "need 1 <= n*k <= 8192");
+    if (p->n + 1 > mk::KS_THREADS * mk::KS_MAXCOLS) return fail(nullptr, MKTFHE_EINVAL, "n too large for the key-switch kernel");
+    if (p->t < 1 || p->basebit < 1 || p->t * p->basebit > 31) return fail(nullptr, MKTFHE_EINVAL, "need t*basebit <= 31");
+    return MKTFHE_OK;
+}
+
+size_t br_smem_bytes(const mktfhe_params& p) {
+    const int nt = 2 * p.l > mk::BR_WARPS ? 2 * p.l : mk::BR_WARPS;
+    size_t b = (size_t)2 * mk::N * 8 + (size_t)nt * ntt::TILE_ELEMS * 8 + (size_t)p.n * p.k * 2;
+    return (b + 15) & ~(size_t)15;
+}
+size_t ep_smem_bytes(const mktfhe_params& p) {
+    const int nt = 2 * p.l > mk::BR_WARPS ? 2 * p.l : mk::BR_WARPS;
+    return (size_t)2 * mk::N * 8 + (size_t)nt * ntt::TILE_ELEMS * 8;
+}
+
+template <int L>
+int set_attrs(mktfhe_ctx* c) {
+    CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(c->prm)));
+    CU_TRY(c, cudaFuncSetAttribute(mk::extprod_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ep_smem_bytes(c->prm)));
+    return MKTFHE_OK;
+}
+
+void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G) {
+    const size_t sm = br_smem_bytes(c->prm);
+    switch (c->prm.l) {
+    case 1: mk::blind_rotate_kernel<1><<<(unsigned)G, mk::BR_THREADS, sm, c->stream>>>(a); break;
+    case 2: mk::blind_rotate_kernel<2><<<(unsigned)G, mk::BR_THREADS, sm, c->stream>>>(a); break;
+    case 3: mk::blind_rotate_kernel<3><<<(unsigned)G, mk::BR_THREADS, sm, c->stream>>>(a); break;
+    default: mk::blind_rotate_kernel<4><<<(unsigned)G, mk::BR_THREADS, sm, c->stream>>>(a); break;
+    }
+    c->launches++;
+}
+
+mk::GateLinear gate_linear(int gate, bool* ok) {
+    *ok = true;
+    switch (gate) {   // 3gen_mk_gates.jl:8-74; encode_message(m, S) = m << (32 - log2 S)
+    case MKTFHE_GATE_NAND: return {(int32_t)(1u << 29), -1, -1, 0};
+    case MKTFHE_GATE_OR: return {(int32_t)(1u << 29), 1, 1, 0};
+    case MKTFHE_GATE_AND: return {(int32_t)(0u - (1u << 29)), 1, 1, 0};
+    case MKTFHE_GATE_XOR: return {(int32_t)(1u << 30), 2, 2, 0};
+    case MKTFHE_GATE_AND3: return {(int32_t)(0u - (1u << 30)), 1, 1, 1};
+    default: *ok = false; return {0, 0, 0, 0};
+    }
+}
+
+// device-pointer core shared by every bootstrap-like entry point
+int run_bootstrap_dev(mktfhe_ctx* c, mk::GateLinear lin, int64_t mu, size_t G, const int32_t* xa, const int32_t* xb,
+                      const int32_t* ya, const int32_t* yb, const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob,
+                      int32_t* ext_out, int64_t* acc_out, bool do_keyswitch, cudaStream_t st) {
+    if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
+    if (G == 0) return MKTFHE_OK;
+    if (G > 0x7fffffffu) return fail(c, MKTFHE_EINVAL, "batch too large");
+    cudaStream_t saved = c->stream;
+    if (st) c->stream = st;
+    int32_t* ext = ext_out;
+    if (!ext) {
+        int rc = reserve(c, c->ext, G * (mk::N + 1) * sizeof(int32_t));
+        if (rc) { c->stream = saved; return rc; }
+        ext = (int32_t*)c->ext.p;
+    }
+    mk::BlindRotateArgs a{};
+    a.n = c->prm.n; a.k = c->prm.k; a.bgbit = c->prm.bgbit;
+    a.bsk = c->d_bsk; a.tw_fwd = c->d_tw_fwd; a.tw_inv = c->d_tw_inv;
+    a.xa = xa; a.xb = xb; a.ya = ya; a.yb = yb; a.za = za; a.zb = zb;
+    a.lin = lin; a.mu = mu; a.ext_out = ext; a.acc_out = acc_out;
+    cudaEventRecord(c->ev[0], c->stream);
+    launch_blind_rotate(c, a, G);
+    cudaEventRecord(c->ev[1], c->stream);
+    cudaEventRecord(c->ev[2], c->stream);
+    if (do_keyswitch) {
+        mk::keyswitch_kernel<<<(unsigned)G, mk::KS_THREADS, 0, c->stream>>>(c->prm.n, c->prm.k, c->prm.t, c->prm.basebit, c->d_ksk, ext, oa, ob);
+        c->launches++;
+    }
+    cudaEventRecord(c->ev[3], c->stream);
+    c->ev_valid = true;
+    c->stream = saved;
+    CU_TRY(c, cudaGetLastError());
+    return MKTFHE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
+    if (!out) return fail(nullptr, MKTFHE_EINVAL, "out is NULL");
+    *out = nullptr;
+    int rc = check_params(params);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, MKTFHE_ECUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, MKTFHE_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10) return fail(nullptr, MKTFHE_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    mktfhe_ctx* c = new (std::nothrow) mktfhe_ctx();
+    if (!c) return fail(nullptr, MKTFHE_ENOMEM, "out of host memory");
+    c->prm = *params;
+    c->device = device;
+    c->bsk_loaded.assign(params->k, 0);
+    c->ksk_loaded.assign(params->k, 0);
+#define CREATE_TRY(call)                                                                                  \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            fail(nullptr, e_ == cudaErrorMemoryAllocation ? MKTFHE_ENOMEM : MKTFHE_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+            mktfhe_destroy(c);                                                                            \
+            return e_ == cudaErrorMemoryAllocation ? MKTFHE_ENOMEM : MKTFHE_ECUDA;                        \
+        }                                                                                                 \
+    } while (0)
+    CREATE_TRY(cudaSetDevice(device));
+    CREATE_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& ev : c->ev) CREATE_TRY(cudaEventCreate(&ev));
+    const int B1 = (1 << params->basebit) - 1;
+    c->bsk_bytes = (size_t)params->k * params->n * mk::bsk_elem_u64(params->l) * sizeof(u64);
+    c->ksk_bytes = (size_t)params->k * mk::N * params->t * B1 * (params->n + 1) * sizeof(int32_t);
+    CREATE_TRY(cudaMalloc(&c->d_bsk, c->bsk_bytes));
+    CREATE_TRY(cudaMalloc(&c->d_ksk, c->ksk_bytes));
+    CREATE_TRY(cudaMalloc(&c->d_tw_fwd, 1024 * sizeof(u64)));
+    CREATE_TRY(cudaMalloc(&c->d_tw_inv, 1024 * sizeof(u64)));
+    {
+        ntt::Tables T;
+        if (T.psi == 0) { fail(nullptr, MKTFHE_EINVAL, "internal: no 2048th root with psi^32 = 8"); mktfhe_destroy(c); return MKTFHE_EINVAL; }
+        CREATE_TRY(cudaMemcpy(c->d_tw_fwd, T.tw_fwd.data(), 1024 * sizeof(u64), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(c->d_tw_inv, T.tw_inv.data(), 1024 * sizeof(u64), cudaMemcpyHostToDevice));
+    }
+#undef CREATE_TRY
+    switch (params->l) {
+    case 1: rc = set_attrs<1>(c); break;
+    case 2: rc = set_attrs<2>(c); break;
+    case 3: rc = set_attrs<3>(c); break;
+    default: rc = set_attrs<4>(c); break;
+    }
+    if (rc) { g_create_error = c->err; mktfhe_destroy(c); return rc; }
+    *out = c;
+    return MKTFHE_OK;
+}
+
+void mktfhe_destroy(mktfhe_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->in[0], &c->in[1], &c->in[2], &c->in[3], &c->in[4], &c->in[5], &c->ext, &c->oa, &c->ob, &c->accin, &c->accout, &c->elem, &c->raw};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    if (c->d_bsk) cudaFree(c->d_bsk);
+    if (c->d_ksk) cudaFree(c->d_ksk);
+    if (c->d_tw_fwd) cudaFree(c->d_tw_fwd);
+    if (c->d_tw_inv) cudaFree(c->d_tw_inv);
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* mktfhe_last_error(const mktfhe_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int mktfhe_load_bsk(mktfhe_ctx* c, int party, const int64_t* polys) {
+    if (!c) return MKTFHE_EINVAL;
+    if (party < 0 || party >= c->prm.k || !polys) return fail(c, MKTFHE_EINVAL, "load_bsk: bad party %d or NULL key", party);
+    CU_TRY(c, cudaSetDevice(c->device));
+    const int n = c->prm.n, l = c->prm.l;
+    const size_t raw_bytes = (size_t)n * 4 * l * mk::N * sizeof(int64_t);
+    int rc = reserve(c, c->raw, raw_bytes);
+    if (rc) return rc;
+    CU_TRY(c, cudaMemcpyAsync(c->raw.p, polys, raw_bytes, cudaMemcpyHostToDevice, c->stream));
+    const int ntasks = n * 4 * l * 2;
+    mk::bsk_transform_kernel<<<(ntasks + mk::BR_WARPS - 1) / mk::BR_WARPS, mk::BR_THREADS, 0, c->stream>>>(
+        (const int64_t*)c->raw.p, c->d_bsk, n, l, party, c->d_tw_fwd, ntasks);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->bsk_loaded[party] = 1;
+    c->ready = false;
+    return MKTFHE_OK;
+}
+
+int mktfhe_load_ksk(mktfhe_ctx* c, int party, const int32_t* rows) {
+    if (!c) return MKTFHE_EINVAL;
+    if (party < 0 || party >= c->prm.k || !rows) return fail(c, MKTFHE_EINVAL, "load_ksk: bad party %d or NULL key", party);
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t per = c->ksk_bytes / c->prm.k;
+    CU_TRY(c, cudaMemcpyAsync((char*)c->d_ksk + per * party, rows, per, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->ksk_loaded[party] = 1;
+    c->ready = false;
+    return MKTFHE_OK;
+}
+
+int mktfhe_finalize_keys(mktfhe_ctx* c) {
+    if (!c) return MKTFHE_EINVAL;
+    for (int p = 0; p < c->prm.k; p++)
+        if (!c->bsk_loaded[p] || !c->ksk_loaded[p]) return fail(c, MKTFHE_ESTATE, "party %d: bootstrapping or key-switching key not loaded", p);
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->ready = true;
+    return MKTFHE_OK;
+}
+
+int mktfhe_key_buffers(mktfhe_ctx* c, void** bsk_dev, size_t* bsk_bytes, void** ksk_dev, size_t* ksk_bytes) {
+    if (!c) return MKTFHE_EINVAL;
+    if (bsk_dev) *bsk_dev = c->d_bsk;
+    if (bsk_bytes) *bsk_bytes = c->bsk_bytes;
+    if (ksk_dev) *ksk_dev = c->d_ksk;
+    if (ksk_bytes) *ksk_bytes = c->ksk_bytes;
+    return MKTFHE_OK;
+}
+
+int mktfhe_mark_keys_received(mktfhe_ctx* c) {
+    if (!c) return MKTFHE_EINVAL;
+    c->bsk_loaded.assign(c->prm.k, 1);
+    c->ksk_loaded.assign(c->prm.k, 1);
+    return MKTFHE_OK;
+}
+
+int mktfhe_bootstrap_batch_dev(mktfhe_ctx* c, int64_t mu, size_t G, const int32_t* a_in, const int32_t* b_in, int32_t* a_out,
+                               int32_t* b_out, void* stream) {
+    if (!c) return MKTFHE_EINVAL;
+    if (G && (!a_in || !b_in || !a_out || !b_out)) return fail(c, MKTFHE_EINVAL, "bootstrap_batch: NULL buffer");
+    CU_TRY(c, cudaSetDevice(c->device));
+    return run_bootstrap_dev(c, {0, 1, 0, 0}, mu, G, a_in, b_in, nullptr, nullptr, nullptr, nullptr, a_out, b_out, nullptr, nullptr, true,
+                             (cudaStream_t)stream);
+}
+
+int mktfhe_gate_batch_dev(mktfhe_ctx* c, int gate, size_t G, const int32_t* xa, const int32_t* xb, const int32_t* ya,
+                          const int32_t* yb, const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob, void* stream) {
+    if (!c) return MKTFHE_EINVAL;
+    bool ok;
+    mk::GateLinear lin = gate_linear(gate, &ok);
+    if (!ok) return fail(c, MKTFHE_EINVAL, "unknown gate id %d", gate);
+    if (G && (!xa || !xb || !ya || !yb || !oa || !ob || (lin.cz && (!za || !zb)))) return fail(c, MKTFHE_EINVAL, "gate_batch: NULL buffer");
+    CU_TRY(c, cudaSetDevice(c->device));
+    // output message encode_message64(1, 8) = 2^61 (rlwe_is32 == false, 3gen_mk_gates.jl:12)
+    return run_bootstrap_dev(c, lin, (int64_t)1 << 61, G, xa, xb, ya, yb, za, zb, oa, ob, nullptr, nullptr, true, (cudaStream_t)stream);
+}
+
+static int stage_in(mktfhe_ctx* c, DevBuf& b, const void* host, size_t bytes) {
+    int rc = reserve(c, b, bytes);
+    if (rc) return rc;
+    CU_TRY(c, cudaMemcpyAsync(b.p, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    return MKTFHE_OK;
+}
+
+int mktfhe_gate_batch(mktfhe_ctx* c, int gate, size_t G, const int32_t* xa, const int32_t* xb, const int32_t* ya, const int32_t* yb,
+                      const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob) {
+    if (!c) return MKTFHE_EINVAL;
+    bool ok;
+    mk::GateLinear lin = gate_linear(gate, &ok);
+    if (!ok) return fail(c, MKTFHE_EINVAL, "unknown gate id %d", gate);
+    if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
+    if (G == 0) return MKTFHE_OK;
+    if (!xa || !xb || !ya || !yb || !oa || !ob || (lin.cz && (!za || !zb))) return fail(c, MKTFHE_EINVAL, "gate_batch: NULL buffer");
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t kn = (size_t)c->prm.n * c->prm.k, abytes = G * kn * 4, bbytes = G * 4;
+    int rc;
+    if ((rc = stage_in(c, c->in[0], xa, abytes)) || (rc = stage_in(c, c->in[1], xb, bbytes)) ||
+        (rc = stage_in(c, c->in[2], ya, abytes)) || (rc = stage_in(c, c->in[3], yb, bbytes)))
+        return rc;
+    if (lin.cz && ((rc = stage_in(c, c->in[4], za, abytes)) || (rc = stage_in(c, c->in[5], zb, bbytes)))) return rc;
+    if ((rc = reserve(c, c->oa, abytes)) || (rc = reserve(c, c->ob, bbytes))) return rc;
+    rc = run_bootstrap_dev(c, lin, (int64_t)1 << 61, G, (int32_t*)c->in[0].p, (int32_t*)c->in[1].p, (int32_t*)c->in[2].p, (int32_t*)c->in[3].p,
+                           (int32_t*)c->in[4].p, (int32_t*)c->in[5].p, (int32_t*)c->oa.p, (int32_t*)c->ob.p, nullptr, nullptr, true, nullptr);
+    if (rc) return rc;
+    CU_TRY(c, cudaMemcpyAsync(oa, c->oa.p, abytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(ob, c->ob.p, bbytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return MKTFHE_OK;
+}
+
+int mktfhe_bootstrap_batch(mktfhe_ctx* c, int64_t mu, size_t G, const int32_t* a_in, const int32_t* b_in, int32_t* a_out, int32_t* b_out) {
+    if (!c) return MKTFHE_EINVAL;
+    if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
+    if (G == 0) return MKTFHE_OK;
+    if (!a_in || !b_in || !a_out || !b_out) return fail(c, MKTFHE_EINVAL, "bootstrap_batch: NULL buffer");
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t kn = (size_t)c->prm.n * c->prm.k, abytes = G * kn * 4, bbytes = G * 4;
+    int rc;
+    if ((rc = stage_in(c, c->in[0], a_in, abytes)) || (rc = stage_in(c, c->in[1], b_in, bbytes))) return rc;
+    if ((rc = reserve(c, c->oa, abytes)) || (rc = reserve(c, c->ob, bbytes))) return rc;
+    rc = run_bootstrap_dev(c, {0, 1, 0, 0}, mu, G, (int32_t*)c->in[0].p, (int32_t*)c->in[1].p, nullptr, nullptr, nullptr, nullptr,
+                           (int32_t*)c->oa.p, (int32_t*)c->ob.p, nullptr, nullptr, true, nullptr);
+    if (rc) return rc;
+    CU_TRY(c, cudaMemcpyAsync(a_out, c->oa.p, abytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(b_out, c->ob.p, bbytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return MKTFHE_OK;
+}
+
+int mktfhe_blind_rotate_batch(mktfhe_ctx* c, int64_t mu, size_t G, const int32_t* a_in, const int32_t* b_in, int32_t* ext_out, int64_t* acc_out) {
+    if (!c) return MKTFHE_EINVAL;
+    if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
+    if (G == 0) return MKTFHE_OK;
+    if (!a_in || !b_in || !ext_out) return fail(c, MKTFHE_EINVAL, "blind_rotate_batch: NULL buffer");
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t kn = (size_t)c->prm.n * c->prm.k, abytes = G * kn * 4, bbytes = G * 4;
+    const size_t ebytes = G * (mk::N + 1) * 4, accbytes = G * 2 * mk::N * 8;
+    int rc;
+    if ((rc = stage_in(c, c->in[0], a_in, abytes)) || (rc = stage_in(c, c->in[1], b_in, bbytes))) return rc;
+    if ((rc = reserve(c, c->ext, ebytes))) return rc;
+    if (acc_out && (rc = reserve(c, c->accout, accbytes))) return rc;
+    rc = run_bootstrap_dev(c, {0, 1, 0, 0}, mu, G, (int32_t*)c->in[0].p, (int32_t*)c->in[1].p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                           (int32_t*)c->ext.p, acc_out ? (int64_t*)c->accout.p : nullptr, false, nullptr);
+    if (rc) return rc;
+    CU_TRY(c, cudaMemcpyAsync(ext_out, c->ext.p, ebytes, cudaMemcpyDeviceToHost, c->stream));
+    if (acc_out) CU_TRY(c, cudaMemcpyAsync(acc_out, c->accout.p, accbytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return MKTFHE_OK;
+}
+
+int mktfhe_keyswitch_batch(mktfhe_ctx* c, size_t G, const int32_t* ext, int32_t* a_out, int32_t* b_out) {
+    if (!c) return MKTFHE_EINVAL;
+    if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
+    if (G == 0) return MKTFHE_OK;
+    if (!ext || !a_out || !b_out) return fail(c, MKTFHE_EINVAL, "keyswitch_batch: NULL buffer");
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t kn = (size_t)c->prm.n * c->prm.k, abytes = G * kn * 4, bbytes = G * 4, ebytes = G * (mk::N + 1) * 4;
+    int rc;
+    if ((rc = stage_in(c, c->ext, ext, ebytes)) || (rc = reserve(c, c->oa, abytes)) || (rc = reserve(c, c->ob, bbytes))) return rc;
+    mk::keyswitch_kernel<<<(unsigned)G, mk::KS_THREADS, 0, c->stream>>>(c->prm.n, c->prm.k, c->prm.t, c->prm.basebit, c->d_ksk,
+                                                                        (const int32_t*)c->ext.p, (int32_t*)c->oa.p, (int32_t*)c->ob.p);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(a_out, c->oa.p, abytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(b_out, c->ob.p, bbytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return MKTFHE_OK;
+}
+
+int mktfhe_extprod_batch(mktfhe_ctx* c, size_t G, const int32_t* elem, const int64_t* acc_in, int64_t* acc_out) {
+    if (!c) return MKTFHE_EINVAL;
+    if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
+    if (G == 0) return MKTFHE_OK;
+    if (!elem || !acc_in || !acc_out) return fail(c, MKTFHE_EINVAL, "extprod_batch: NULL buffer");
+    for (size_t g = 0; g < G; g++)
+        if (elem[g] < 0 || elem[g] >= c->prm.n * c->prm.k) return fail(c, MKTFHE_EINVAL, "extprod_batch: elem[%zu]=%d out of range", g, elem[g]);
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t accbytes = G * 2 * mk::N * 8;
+    int rc;
+    if ((rc = stage_in(c, c->elem, elem, G * 4)) || (rc = stage_in(c, c->accin, acc_in, accbytes)) || (rc = reserve(c, c->accout, accbytes))) return rc;
+    const size_t sm = ep_smem_bytes(c->prm);
+    const u64 *bsk = c->d_bsk, *tf = c->d_tw_fwd, *ti = c->d_tw_inv;
+    const int32_t* de = (const int32_t*)c->elem.p;
+    const int64_t* ai = (const int64_t*)c->accin.p;
+    int64_t* ao = (int64_t*)c->accout.p;
+    switch (c->prm.l) {
+    case 1: mk::extprod_kernel<1><<<(unsigned)G, mk::BR_THREADS, sm, c->stream>>>(bsk, tf, ti, c->prm.bgbit, de, ai, ao); break;
+    case 2: mk::extprod_kernel<2><<<(unsigned)G, mk::BR_THREADS, sm, c->stream>>>(bsk, tf, ti, c->prm.bgbit, de, ai, ao); break;
+    case 3: mk::extprod_kernel<3><<<(unsigned)G, mk::BR_THREADS, sm, c->stream>>>(bsk, tf, ti, c->prm.bgbit, de, ai, ao); break;
+    default: mk::extprod_kernel<4><<<(unsigned)G, mk::BR_THREADS, sm, c->stream>>>(bsk, tf, ti, c->prm.bgbit, de, ai, ao); break;
+    }
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(acc_out, c->accout.p, accbytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return MKTFHE_OK;
+}
+
+int mktfhe_negacyclic_mul_batch(mktfhe_ctx* c, size_t G, const int64_t* a, const int64_t* b, int64_t* out) {
+    if (!c) return MKTFHE_EINVAL;
+    if (G == 0) return MKTFHE_OK;
+    if (!a || !b || !out) return fail(c, MKTFHE_EINVAL, "negacyclic_mul_batch: NULL buffer");
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t bytes = G * mk::N * 8;
+    int rc;
+    if ((rc = stage_in(c, c->accin, a, bytes)) || (rc = stage_in(c, c->raw, b, bytes)) || (rc = reserve(c, c->accout, bytes))) return rc;
+    mk::negacyclic_mul_kernel<<<(unsigned)G, 96, 0, c->stream>>>((const int64_t*)c->accin.p, (const int64_t*)c->raw.p, (int64_t*)c->accout.p,
+                                                                  c->d_tw_fwd, c->d_tw_inv);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(out, c->accout.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return MKTFHE_OK;
+}
+
+uint64_t mktfhe_launch_count(const mktfhe_ctx* c) { return c ? c->launches : 0; }
+
+int mktfhe_last_kernel_ms(mktfhe_ctx* c, float* blind_rotate_ms, float* keyswitch_ms) {
+    if (!c) return MKTFHE_EINVAL;
+    if (!c->ev_valid) return fail(c, MKTFHE_ESTATE, "no batch has run yet");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaEventSynchronize(c->ev[3]));
+    float br = 0.f, ks = 0.f;
+    CU_TRY(c, cudaEventElapsedTime(&br, c->ev[0], c->ev[1]));
+    CU_TRY(c, cudaEventElapsedTime(&ks, c->ev[2], c->ev[3]));
+    if (blind_rotate_ms) *blind_rotate_ms = br;
+    if (keyswitch_ms) *keyswitch_ms = ks;
+    return MKTFHE_OK;
+}
+
+int mktfhe_algorithmic_bytes(const mktfhe_ctx* c, double* bsk_bytes_per_gate, double* ksk_bytes_per_gate) {
+    if (!c) return MKTFHE_EINVAL;
+    const mktfhe_params& p = c->prm;
+    const double B = (double)(1 << p.basebit);
+    if (bsk_bytes_per_gate) *bsk_bytes_per_gate = (double)c->bsk_bytes;
+    if (ksk_bytes_per_gate) *ksk_bytes_per_gate = (double)p.k * mk::N * p.t * (1.0 - 1.0 / B) * (p.n + 1) * 4.0;
+    return MKTFHE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,513 @@
+"""Host-side mirror of the reference's 3gen multi-key gate API (module TFHE,
+3-gen-mk-tfhe/src/TFHE.jl:56-196) over the C ABI of libmktfhe_b200.so.
+
+Same exported names, positional arguments and meaning as the Julia functions; the
+bootstrapped gates forward to the sm_100a kernels (no CPU path).  The Julia shim
+`julia/TFHE_B200.jl` is the `ccall` twin of this file; this Python twin exists
+because the image has no Julia, so it is what the tests and benchmarks drive.
+
+Batching: every `MKLweSample` may carry leading batch dimensions (`a` of shape
+batch + (k, n), `b` of shape batch); a plain sample is batch = ().  The
+reference's `a::Array{Int32,2}` of size (n, k), column-major, is the same memory
+as our C-order (k, n).
+
+Citations are relative to 3-gen-mk-tfhe/src/.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _cabi
+from .engine import Engine
+
+Torus32 = np.int32
+Torus64 = np.int64
+
+
+# ---------------------------------------------------------------------------------
+# numeric-functions.jl
+# ---------------------------------------------------------------------------------
+def _log2(x):
+    lg = int(x).bit_length() - 1
+    if (1 << lg) != x:
+        raise ValueError(f"{x} is not a power of two")
+    return lg
+
+
+def encode_message(mu, space):
+    """numeric-functions.jl:86-89: Torus32(mu) << (32 - log2(space)), wrapping."""
+    return np.int32(np.uint32((int(mu) << (32 - _log2(space))) & 0xFFFFFFFF).astype(np.int32))
+
+
+def encode_message64(mu, space):
+    """numeric-functions.jl:92-95."""
+    return np.int64(np.uint64((int(mu) << (64 - _log2(space))) & 0xFFFFFFFFFFFFFFFF).astype(np.int64))
+
+
+def decode_message(phase, space):
+    """numeric-functions.jl:70-73: (phase + 2^(32-log2(space)-1)) >> (32 - log2(space)), wrapping add, arithmetic shift."""
+    lg = _log2(space)
+    p = np.asarray(phase, dtype=np.int32)
+    s = (p.view(np.uint32) + np.uint32(1 << (32 - lg - 1))).view(np.int32) if p.ndim else \
+        np.uint32((int(p) + (1 << (32 - lg - 1))) & 0xFFFFFFFF).astype(np.int32)
+    return s >> (32 - lg)
+
+
+def dtot32(d):
+    """numeric-functions.jl:101-103: trunc(Int32, d * 2^32)."""
+    return np.trunc(np.asarray(d, dtype=np.float64) * 4294967296.0).astype(np.int64).astype(np.int32)
+
+
+def dtot64(d):
+    """numeric-functions.jl:105-107: trunc(Int64, d * 2^64) (|d| < 0.5)."""
+    return np.trunc(np.asarray(d, dtype=np.float64) * 18446744073709551616.0).astype(np.int64)
+
+
+_TERNARY_W = 0.113546097609674   # numeric-functions.jl:26-28
+
+
+def rand_negative_binary64(rng, n):
+    u = rng.random(n)
+    return np.where(u < _TERNARY_W, -1, np.where(u < 1.0 - _TERNARY_W, 0, 1)).astype(np.int64)
+
+
+def rand_uniform_torus32(rng, n):
+    return rng.integers(-2 ** 31, 2 ** 31, size=n, dtype=np.int64).astype(np.int32)
+
+
+def rand_uniform_torus64(rng, n):
+    return rng.integers(-2 ** 63, 2 ** 63 - 1, size=n, dtype=np.int64, endpoint=True)
+
+
+def rand_gaussian_torus32(rng, mean, sigma, n=None):
+    return (np.int32(mean) + dtot32(rng.standard_normal(n) * sigma)).astype(np.int32)
+
+
+def rand_gaussian_torus64(rng, mean, sigma, n=None):
+    return np.int64(mean) + dtot64(rng.standard_normal(n) * sigma)
+
+
+# ---------------------------------------------------------------------------------
+# parameters (api.jl:50-67, 156-166; mk_api.jl:32-146)
+# ---------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class SchemeParameters_3gen:
+    lwe_size: int
+    lwe_noise_stddev: float
+    rlwe_polynomial_degree: int
+    rlwe_mask_size: int
+    rlwe_is32: bool
+    gsw_decomp_length: int
+    gsw_log2_base: int
+    gsw_noise_stddev: float
+    ks_decomp_length: int
+    ks_log2_base: int
+    ks_noise_stddev: float
+    max_parties: int
+
+
+@dataclass(frozen=True)
+class LweParams:
+    size: int
+
+
+@dataclass(frozen=True)
+class RLweParams:
+    polynomial_degree: int
+    mask_size: int
+    is32: bool
+
+
+@dataclass(frozen=True)
+class TGswParams:
+    decomp_length: int
+    log2_base: int
+    is32: bool
+
+    @property
+    def gadget_values(self):   # tgsw.jl:26
+        bit = 32 if self.is32 else 64
+        return [1 << (bit - q * self.log2_base) for q in range(1, self.decomp_length + 1)]
+
+
+@dataclass(frozen=True)
+class KeyswitchParameters:
+    decomp_length: int
+    log2_base: int
+
+
+def lwe_parameters(p):
+    return LweParams(p.lwe_size)
+
+
+def rlwe_parameters(p):
+    return RLweParams(p.rlwe_polynomial_degree, p.rlwe_mask_size, p.rlwe_is32)
+
+
+def tgsw_parameters(p):
+    return TGswParams(p.gsw_decomp_length, p.gsw_log2_base, p.rlwe_is32)
+
+
+def keyswitch_parameters(p):
+    return KeyswitchParameters(p.ks_decomp_length, p.ks_log2_base)
+
+
+mktfhe_parameters_2party_3gen = SchemeParameters_3gen(520, 2 ** -13.52, 1024, 1, False, 2, 7, 2 ** -30.70, 3, 3, 2 ** -13.52, 2)
+mktfhe_parameters_3party_3gen = SchemeParameters_3gen(510, 2 ** -13.26, 1024, 1, False, 2, 7, 2 ** -30.70, 5, 2, 2 ** -13.26, 3)
+mktfhe_parameters_4party_3gen = SchemeParameters_3gen(510, 2 ** -13.26, 1024, 1, False, 3, 6, 2 ** -30.70, 5, 2, 2 ** -13.26, 4)
+mktfhe_parameters_5party_3gen = SchemeParameters_3gen(520, 2 ** -13.52, 1024, 1, False, 3, 6, 2 ** -30.70, 5, 2, 2 ** -13.52, 5)
+mktfhe_parameters_8party_3gen = SchemeParameters_3gen(540, 2 ** -14.04, 1024, 1, False, 4, 4, 2 ** -30.70, 5, 2, 2 ** -14.04, 8)
+# 16 parties and up use N = 2048 and a 26-bit gadget base (mk_api.jl:214-322): defined for
+# API completeness, rejected by mktfhe_create (MKTFHE_EINVAL) until the N = 2048 kernels exist.
+mktfhe_parameters_16party_3gen = SchemeParameters_3gen(590, 2 ** -15.34, 2048, 1, False, 1, 26, 2 ** -62.00, 4, 3, 2 ** -15.34, 16)
+
+
+# ---------------------------------------------------------------------------------
+# MKLweSample (mk_internals.jl:23-51, 94-96)
+# ---------------------------------------------------------------------------------
+def _w32(x):
+    return np.asarray(x).astype(np.int64).astype(np.int32) if not isinstance(x, np.ndarray) or x.dtype != np.int32 else x
+
+
+class MKLweSample:
+    __slots__ = ("params", "a", "b", "current_variance")
+
+    def __init__(self, params, a, b, current_variance=0.0):
+        self.params = params
+        self.a = np.asarray(a, dtype=np.int32)
+        self.b = np.asarray(b, dtype=np.int32)
+        self.current_variance = current_variance
+
+    @property
+    def batch_shape(self):
+        return self.b.shape
+
+    def __len__(self):
+        return self.b.shape[0]
+
+    def __getitem__(self, idx):
+        return MKLweSample(self.params, self.a[idx], self.b[idx], self.current_variance)
+
+    def __sub__(self, y):
+        with np.errstate(over="ignore"):
+            return MKLweSample(self.params, self.a - y.a, self.b - y.b, self.current_variance + y.current_variance)
+
+    def __add__(self, y):
+        with np.errstate(over="ignore"):
+            return MKLweSample(self.params, self.a + y.a, self.b + y.b, self.current_variance + y.current_variance)
+
+    def __neg__(self):
+        with np.errstate(over="ignore"):
+            return MKLweSample(self.params, -self.a, -self.b, self.current_variance)
+
+    def __rmul__(self, x):   # Torus32 * sample, mk_internals.jl:50-51
+        x = np.int32(x)
+        with np.errstate(over="ignore"):
+            return MKLweSample(self.params, x * self.a, x * self.b, float(x) * float(x) * self.current_variance)
+
+    @staticmethod
+    def stack(samples):
+        return MKLweSample(samples[0].params, np.stack([s.a for s in samples]), np.stack([s.b for s in samples]),
+                           max(s.current_variance for s in samples))
+
+
+def mk_lwe_noiseless_trivial(mu, params, parties, batch_shape=()):
+    return MKLweSample(params, np.zeros(tuple(batch_shape) + (parties, params.size), np.int32),
+                       np.full(batch_shape, np.int32(mu), np.int32), 0.0)
+
+
+# ---------------------------------------------------------------------------------
+# keys
+# ---------------------------------------------------------------------------------
+class LweKey:   # lwe.jl:7-14
+    def __init__(self, rng, params):
+        self.params = params
+        self.key = rng.integers(0, 2, size=params.size, dtype=np.int64).astype(np.int32) if rng is not None else None
+
+
+class SecretKey_3gen:   # api.jl:196-204
+    def __init__(self, rng, params, key=None):
+        self.params = params
+        self.key = LweKey(rng, lwe_parameters(params))
+        if key is not None:
+            self.key.key = np.asarray(key, dtype=np.int32)
+
+
+class RLweKey:   # rlwe.jl:13-31 (negative_random = true: sparse ternary)
+    def __init__(self, rng, params, negative_random=True, key=None):
+        self.params = params
+        if key is not None:
+            self.key = np.asarray(key, dtype=np.int64)
+        elif negative_random:
+            self.key = rand_negative_binary64(rng, params.polynomial_degree)
+        else:
+            self.key = rng.integers(0, 2, size=params.polynomial_degree, dtype=np.int64)
+
+
+_mul_ctx_cache = {}
+
+
+def _mul_context(N, device=0):
+    """A key-less context used only for exact negacyclic products during key generation."""
+    key = (N, device)
+    if key not in _mul_ctx_cache:
+        _mul_ctx_cache[key] = _cabi.Context(1, N, 1, 1, 1, 1, 1, device=device)
+    return _mul_ctx_cache[key]
+
+
+def negacyclic_mul(small, big):
+    """Exact product mod (X^N + 1, 2^64) on the GPU; `small` has |coeff| < 2^15."""
+    small, big = np.asarray(small, np.int64), np.asarray(big, np.int64)
+    N = small.shape[-1]
+    bshape = np.broadcast_shapes(small.shape, big.shape)
+    s = np.ascontiguousarray(np.broadcast_to(small, bshape)).reshape(-1, N)
+    b = np.ascontiguousarray(np.broadcast_to(big, bshape)).reshape(-1, N)
+    return _mul_context(N).negacyclic_mul_batch(s, b).reshape(bshape)
+
+
+class CRP_3gen:   # mk_internals.jl:177-196
+    def __init__(self, rng, tgsw_params, rlwe_params, a_same=False):
+        l, N = tgsw_params.decomp_length, rlwe_params.polynomial_degree
+        self.tgsw_params, self.rlwe_params = tgsw_params, rlwe_params
+        if a_same:
+            self.a = np.repeat(rand_uniform_torus64(rng, N)[None], l, axis=0)
+        else:
+            self.a = np.stack([rand_uniform_torus64(rng, N) for _ in range(l)])
+
+
+def GenCRP_3gen(rng, tgsw_params, rlwe_params, a_same=False):
+    return CRP_3gen(rng, tgsw_params, rlwe_params, a_same)
+
+
+class PublicKey:   # mk_internals.jl:266-298: b[q] = z * a[q] + e
+    def __init__(self, rng, rlwe_key, alpha, crp, tgsw_params, wo_FFT=0):
+        l, N = tgsw_params.decomp_length, rlwe_key.params.polynomial_degree
+        self.tgsw_params, self.rlwe_params = tgsw_params, rlwe_key.params
+        prod = negacyclic_mul(rlwe_key.key[None, :], crp.a)
+        with np.errstate(over="ignore"):
+            self.b = prod + np.stack([rand_gaussian_torus64(rng, 0, alpha, N) for _ in range(l)])
+
+
+class CommonPubKey_3gen:   # mk_internals.jl:325-345
+    def __init__(self, pubkeys, params, parties):
+        self.params, self.parties = params, parties
+        b = pubkeys[0].b.copy()
+        with np.errstate(over="ignore"):
+            for i in range(1, parties):
+                b = b + pubkeys[i].b
+        self.b = b
+
+
+class BootstrapKeyPart_3gen:
+    """3gen_mk_internals.jl:10-43: n TGSW encryptions (tgsw_encrypt_3gen, tgsw_3gen.jl:41-95) of the
+    LWE key bits under the common public key.  `gsw_key` is int64 [n][4][l][N] (part_1..part_4)."""
+
+    def __init__(self, rng, lwe_key, alpha, crp_a, common_pubkey, tgsw_params, rlwe_params, wo_FFT=0, gsw_key=None):
+        self.tgsw_params, self.rlwe_params = tgsw_params, rlwe_params
+        if gsw_key is not None:
+            self.gsw_key = np.asarray(gsw_key, dtype=np.int64)
+            self.key_size = self.gsw_key.shape[0]
+            return
+        n, l, N = lwe_key.params.size, tgsw_params.decomp_length, rlwe_params.polynomial_degree
+        self.key_size = n
+        r1 = rand_negative_binary64(rng, n * l * N).reshape(n, l, N)
+        r2 = rand_negative_binary64(rng, n * l * N).reshape(n, l, N)
+        err = rand_gaussian_torus64(rng, 0, alpha, n * 4 * l * N).reshape(n, 4, l, N)
+        B, A = common_pubkey.b[None], crp_a.a[None]
+        mg = lwe_key.key.astype(np.int64)[:, None] * np.array(tgsw_params.gadget_values, dtype=np.uint64).view(np.int64)[None, :]
+        with np.errstate(over="ignore"):
+            gsw = err
+            gsw[:, 0] += negacyclic_mul(r1, B)
+            gsw[:, 1] += negacyclic_mul(r2, B)
+            gsw[:, 2] += negacyclic_mul(r2, A)
+            gsw[:, 3] += negacyclic_mul(r1, A)
+            gsw[:, 0, :, 0] += mg   # Polynomial .+ scalar: constant coefficient
+            gsw[:, 2, :, 0] += mg
+        self.gsw_key = gsw
+
+    @classmethod
+    def from_array(cls, gsw_key, tgsw_params, rlwe_params):
+        return cls(None, None, 0.0, None, None, tgsw_params, rlwe_params, gsw_key=gsw_key)
+
+
+class TransformedBootstrapKeyPart_3gen:
+    """3gen_mk_internals.jl:45-55.  The reference keeps Complex{Float64} FFTs here; this build keeps
+    the integer polynomials and transforms them on the GPU (exact NTT) when the engine loads them."""
+
+    def __init__(self, bk):
+        self.tgsw_params, self.rlwe_params = bk.tgsw_params, bk.rlwe_params
+        self.gsw_key = bk.gsw_key
+        self.key_size = bk.key_size
+        self._engine = None
+
+
+class KeyswitchKey:
+    """keyswitch.jl:7-42.  `key` is int32 [N][t][base-1][n+1] (row = LweSample a[0..n-1], b), i.e. the
+    reference's Array{LweSample,3} of dims (base-1, t, N) in memory order."""
+
+    def __init__(self, rng, alpha, params, out_key, in_key, key=None):
+        self.params = params
+        if key is not None:
+            self.key = np.asarray(key, dtype=np.int32)
+            return
+        s = out_key.key.astype(np.int64)
+        z = in_key.key
+        n, N, t, bb = s.size, z.size, params.decomp_length, params.log2_base
+        B1 = (1 << bb) - 1
+        noise = rng.standard_normal((N, t, B1)) * alpha
+        noise -= noise.mean()                                              # :28-29
+        a = rand_uniform_torus32(rng, N * t * B1 * n).reshape(N, t, B1, n)
+        h = np.arange(1, B1 + 1, dtype=np.int64)[None, None, :]
+        sh = (32 - np.arange(1, t + 1) * bb)[None, :, None]
+        msg = (z[:, None, None] * h) << sh                                 # :35
+        dot = (a.astype(np.int64) * s).sum(-1)
+        b = (msg + dtot32(noise).astype(np.int64) + dot).astype(np.int32)  # lwe.jl:47-53
+        self.key = np.concatenate([a, b[..., None]], axis=-1)
+
+    @classmethod
+    def from_array(cls, key, params):
+        return cls(None, 0.0, params, None, None, key=key)
+
+
+# ---------------------------------------------------------------------------------
+# encrypt / decrypt (mk_api.jl:519-536, 576-633; mk_internals.jl:85-91)
+# ---------------------------------------------------------------------------------
+def mk_encrypt_3gen(rng, secret_keys, message):
+    """`message` may be a bool or an array of bools (batch)."""
+    params = secret_keys[0].params
+    msg = np.asarray(message, dtype=bool)
+    n, k = params.lwe_size, len(secret_keys)
+    a = rand_uniform_torus32(rng, msg.size * k * n).reshape(msg.shape + (k, n))
+    s = np.stack([sk.key.key for sk in secret_keys]).astype(np.int64)
+    mu = np.where(msg, int(encode_message(1, 8)), int(encode_message(-1, 8)))
+    e = dtot32(rng.standard_normal(msg.shape) * params.lwe_noise_stddev).astype(np.int64)
+    b = (mu + e + (a.astype(np.int64) * s).sum((-1, -2))).astype(np.int32)
+    return MKLweSample(lwe_parameters(params), a, b, params.lwe_noise_stddev ** 2)
+
+
+def mk_lwe_phase(sample, lwe_keys):
+    s = np.stack([k.key for k in lwe_keys]).astype(np.int64)
+    return (sample.b.astype(np.int64) - (sample.a.astype(np.int64) * s).sum((-1, -2))).astype(np.int32)
+
+
+def mk_decrypt_3gen(secret_keys, sample):
+    r = mk_lwe_phase(sample, [sk.key for sk in secret_keys]) > 0
+    return bool(r) if r.ndim == 0 else r
+
+
+def mk_int_encrypt_3gen(rng, secret_keys, message, WIDTH):
+    """LSB-first bit vector; `message` may be an int or an integer array (batch of instances)."""
+    m = np.asarray(message, dtype=np.int64)
+    return [mk_encrypt_3gen(rng, secret_keys, ((m >> i) & 1) == 1) for i in range(WIDTH)]
+
+
+def mk_int_decrypt_3gen(secret_keys, sample, WIDTH):
+    msb = np.asarray(mk_decrypt_3gen(secret_keys, sample[WIDTH - 1]))
+    result = np.zeros(msb.shape, np.int64)
+    for i in range(WIDTH - 1):
+        bit = np.asarray(mk_decrypt_3gen(secret_keys, sample[i]))
+        result += (bit ^ msb).astype(np.int64) << i
+    result = np.where(msb, -(result + 1), result)
+    return int(result) if result.ndim == 0 else result
+
+
+# ---------------------------------------------------------------------------------
+# engine lookup: the reference passes (bk, ks) to every gate; the GPU context that
+# holds their transformed copies is created on first use and cached on bk[0].
+# ---------------------------------------------------------------------------------
+def _scheme_params_of(bk, ks):
+    tg, ksp = bk[0].tgsw_params, ks[0].params
+    n = bk[0].key_size
+    return SchemeParameters_3gen(n, 0.0, bk[0].rlwe_params.polynomial_degree, bk[0].rlwe_params.mask_size, bk[0].rlwe_params.is32,
+                                 tg.decomp_length, tg.log2_base, 0.0, ksp.decomp_length, ksp.log2_base, 0.0, len(bk))
+
+
+def engine_for(bk, ks, device=None):
+    tag = (tuple(id(b) for b in bk), tuple(id(k) for k in ks))
+    cached = getattr(bk[0], "_engine", None)
+    if cached is not None and cached[0] == tag:
+        return cached[1]
+    if bk[0].rlwe_params.is32:
+        raise NotImplementedError("rlwe_is32 = true parameter sets are not part of the 3gen path (every 3gen set is Torus64)")
+    eng = Engine(_scheme_params_of(bk, ks), device=device)
+    eng.load_keys([b.gsw_key for b in bk], [k.key for k in ks])
+    bk[0]._engine = (tag, eng)
+    return eng
+
+
+def _flat(x, k, n):
+    return x.a.reshape(-1, k, n), x.b.reshape(-1)
+
+
+def _gate(bk, ks, gate, x, y, z=None):
+    eng = engine_for(bk, ks)
+    k, n = eng.params.max_parties, eng.params.lwe_size
+    shape = x.b.shape
+    oa, ob = eng.ctx.gate_batch(gate, _flat(x, k, n), _flat(y, k, n), _flat(z, k, n) if z is not None else None)
+    return MKLweSample(x.params, oa.reshape(shape + (k, n)), ob.reshape(shape), 0.0)   # variance 0.0: mk_internals.jl:738-743
+
+
+# ---------------------------------------------------------------------------------
+# the hot path (3gen_mk_internals.jl:99-116, mk_internals.jl:730-744)
+# ---------------------------------------------------------------------------------
+def mk_bootstrap_3gen(bk, ks, mu, x):
+    eng = engine_for(bk, ks)
+    k, n = eng.params.max_parties, eng.params.lwe_size
+    oa, ob = eng.ctx.bootstrap_batch(int(mu), *_flat(x, k, n))
+    return MKLweSample(x.params, oa.reshape(x.b.shape + (k, n)), ob.reshape(x.b.shape), 0.0)
+
+
+def mk_blind_rotate_and_extract_3gen(bk, ks, mu, x):
+    """mk_bootstrap_wo_keyswitch_3gen (3gen_mk_internals.jl:99-109): returns the extracted LWE sample
+    (a' int32 [.., N], b' int32 [..]) under the extracted RLWE keys."""
+    eng = engine_for(bk, ks)
+    k, n, N = eng.params.max_parties, eng.params.lwe_size, eng.params.rlwe_polynomial_degree
+    ext, _ = eng.ctx.blind_rotate_batch(int(mu), *_flat(x, k, n))
+    return ext[:, :N].reshape(x.b.shape + (N,)), ext[:, N].reshape(x.b.shape)
+
+
+def mk_keyswitch_3gen(bk, ks, ext_a, ext_b, lwe_params):
+    eng = engine_for(bk, ks)
+    k, n, N = eng.params.max_parties, eng.params.lwe_size, eng.params.rlwe_polynomial_degree
+    ext_a, ext_b = np.asarray(ext_a, np.int32), np.asarray(ext_b, np.int32)
+    ext = np.concatenate([ext_a.reshape(-1, N), ext_b.reshape(-1, 1)], axis=1)
+    oa, ob = eng.ctx.keyswitch_batch(ext)
+    return MKLweSample(lwe_params, oa.reshape(ext_b.shape + (k, n)), ob.reshape(ext_b.shape), 0.0)
+
+
+# gates, 3gen_mk_gates.jl:8-150
+def mk_gate_nand_3gen(bk, ks, x, y):
+    return _gate(bk, ks, _cabi.GATE_NAND, x, y)
+
+
+def mk_gate_or_3gen(bk, ks, x, y):
+    return _gate(bk, ks, _cabi.GATE_OR, x, y)
+
+
+def mk_gate_and_3gen(bk, ks, x, y):
+    return _gate(bk, ks, _cabi.GATE_AND, x, y)
+
+
+def mk_gate_3and_3gen(bk, ks, x, y, z):
+    return _gate(bk, ks, _cabi.GATE_AND3, x, y, z)
+
+
+def mk_gate_xor_3gen(bk, ks, x, y):
+    return _gate(bk, ks, _cabi.GATE_XOR, x, y)
+
+
+def mk_gate_not_3gen(x):
+    return -x
+
+
+def mk_gate_mux_3gen(bk, ks, x, y, z):
+    """3gen_mk_gates.jl:133-150: AND(x, y) and AND(-x, z) bootstrapped (one launch: the two ANDs are
+    independent), then 1/8 + t1 + t2 NOT bootstrapped, exactly as the reference."""
+    both = _gate(bk, ks, _cabi.GATE_AND, MKLweSample.stack([x, -x]), MKLweSample.stack([y, z]))
+    t1, t2 = both[0], both[1]
+    k = len(bk)
+    return mk_lwe_noiseless_trivial(encode_message(1, 8), t1.params, k, t1.b.shape) + t1 + t2
+
+
+def mk_copy_3gen(x):
+    return MKLweSample(x.params, x.a.copy(), x.b.copy(), x.current_variance)
