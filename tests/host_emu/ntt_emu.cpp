@@ -1,113 +1,138 @@
-// Host emulation of the warp-level 1024-point negacyclic NTT used by the CUDA
-// kernels: runs the very same per-thread passes (ntt1024.cuh) for 32 emulated
-// lanes and checks them against the O(N^2) definition and against an exact
-// schoolbook negacyclic product with the two-limb key split.
+// Host emulation of the warp-level 1024-point negacyclic RNS NTT used by the CUDA kernels: runs the very
+// same per-thread passes (torus-fhe_b200/csrc/ntt_rns.cuh) for 32 emulated lanes and checks them against
+// the O(N^2) definition, and the whole three-prime product (Montgomery pointwise products, folded key
+// scaling, Garner CRT) against an exact schoolbook negacyclic product mod 2^64.
 // Build: g++ -O2 -std=c++17 -I torus-fhe_b200/csrc tests/host_emu/ntt_emu.cpp -o ntt_emu
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-#include "ntt1024.cuh"
 #include "tables.h"
 
-using namespace ntt;
-static Tables T;
+using namespace rns;
+static HostTables T;
 
 static u64 rnd_state = 0x1234567ull;
 static u64 rnd() { rnd_state ^= rnd_state << 13; rnd_state ^= rnd_state >> 7; rnd_state ^= rnd_state << 17; return rnd_state; }
 
-// coefficient layout in -> NTT-domain layout out, reg[lane][r]
-static void warp_fwd(const u64* a, u64 out[32][32]) {
-    static u64 tile[TILE_ELEMS];
-    u64 x[32];
+// coefficient order in (values in [0, 4p)) -> transformed out[lane][c] (position 32 lane + c)
+static void warp_fwd(int pi, const u32* a, u32 out[32][32]) {
+    static u32 tile[TILE_WORDS];
+    const u32 p = T.c.p[pi];
+    u32 x[32];
     for (int lane = 0; lane < 32; lane++) {
-        for (int i1 = 0; i1 < 32; i1++) x[i1] = a[32 * i1 + lane];
-        fwd_pass1(x, T.tw_fwd.data(), lane);
+        for (int r = 0; r < 32; r++) x[r] = a[32 * r + lane];
+        fwd_passA(x, T.c.twA[pi][0], p);
         for (int r = 0; r < 32; r++) tile[r * TILE_STRIDE + lane] = x[r];
     }
     for (int lane = 0; lane < 32; lane++) {
-        for (int j = 0; j < 32; j++) x[j] = tile[lane * TILE_STRIDE + j];
-        fwd_pass2(x);
-        for (int r = 0; r < 32; r++) out[lane][r] = x[r];
+        for (int c = 0; c < 32; c++) x[c] = tile[lane * TILE_STRIDE + c];
+        fwd_passB(x, T.twB.data() + ((size_t)pi * 2 + 0) * 31 * 32 + lane, p);
+        for (int c = 0; c < 32; c++) out[lane][c] = x[c];
     }
 }
-static void warp_inv(u64 in[32][32], u64* a) {
-    static u64 tile[TILE_ELEMS];
-    u64 x[32];
+// transformed in[lane][c] (values in [0, 4p)) -> coefficient order, scaled by N
+static void warp_inv(int pi, u32 in[32][32], u32* a) {
+    static u32 tile[TILE_WORDS];
+    const u32 p = T.c.p[pi];
+    u32 x[32];
     for (int lane = 0; lane < 32; lane++) {
-        for (int r = 0; r < 32; r++) x[r] = in[lane][r];
-        inv_pass1(x, T.tw_inv.data(), lane);
-        for (int j = 0; j < 32; j++) tile[lane * TILE_STRIDE + j] = x[j];
+        for (int c = 0; c < 32; c++) x[c] = in[lane][c];
+        inv_passB(x, T.twB.data() + ((size_t)pi * 2 + 1) * 31 * 32 + lane, p);
+        for (int c = 0; c < 32; c++) tile[lane * TILE_STRIDE + c] = x[c];
     }
     for (int lane = 0; lane < 32; lane++) {
         for (int r = 0; r < 32; r++) x[r] = tile[r * TILE_STRIDE + lane];
-        inv_pass2(x);
-        for (int i1 = 0; i1 < 32; i1++) a[32 * i1 + lane] = x[i1];
+        inv_passA(x, T.c.twA[pi][1], p);
+        for (int r = 0; r < 32; r++) a[32 * r + lane] = x[r];
     }
 }
 
 int main() {
     int fails = 0;
-    if (T.psi == 0 || gl::pow(T.psi, 32) != 8 || gl::pow(T.psi, 1024) != gl::P - 1) { printf("FAIL psi\n"); return 1; }
-    // field ops vs __int128
-    for (int it = 0; it < 200000; it++) {
-        u64 a = rnd() % gl::P, b = rnd() % gl::P;
-        if (it < 64) { a = gl::P - 1 - (it & 7); b = gl::P - 1 - (it >> 3); }
-        unsigned __int128 m = (unsigned __int128)a * b;
-        if (gl::mul(a, b) != (u64)(m % gl::P)) { fails++; printf("FAIL mul\n"); break; }
-        if (gl::add(a, b) != (u64)(((unsigned __int128)a + b) % gl::P)) { fails++; printf("FAIL add\n"); break; }
-        if (gl::sub(a, b) != (u64)(((unsigned __int128)a + gl::P - b) % gl::P)) { fails++; printf("FAIL sub\n"); break; }
-        int s = it % 192;
-        if (gl::mul_pow2(a, s) != gl::mul(a, gl::pow(2, s))) { fails++; printf("FAIL mul_pow2 s=%d\n", s); break; }
-    }
-    // size-32 transforms vs definition
-    {
-        u64 x[32], y[32], ref[32];
-        for (int i = 0; i < 32; i++) x[i] = y[i] = rnd() % gl::P;
-        for (int k = 0; k < 32; k++) { u64 s = 0; for (int i = 0; i < 32; i++) s = gl::add(s, gl::mul(x[i], gl::pow(64, (u64)(i * k) % 32))); ref[k] = s; }
-        dif32(y);
-        for (int r = 0; r < 32; r++) if (y[r] != ref[brev5(r)]) { fails++; printf("FAIL dif32 r=%d\n", r); break; }
-        dit32_inv(y);
-        for (int i = 0; i < 32; i++) if (y[i] != gl::mul(x[i], 32)) { fails++; printf("FAIL dit32_inv i=%d\n", i); break; }
-        for (int i = 0; i < 32; i++) y[i] = x[i];
-        twist32(y); untwist32(y);
-        for (int i = 0; i < 32; i++) if (y[i] != x[i]) { fails++; printf("FAIL twist i=%d\n", i); break; }
-    }
-    // full 1024-point NTT vs definition A[k] = sum a_i psi^(i(2k+1)), layout check
-    {
-        std::vector<u64> a(N), back(N);
-        for (auto& v : a) v = rnd() % gl::P;
-        static u64 A[32][32];
-        warp_fwd(a.data(), A);
-        std::vector<u64> psipow(2048);
-        psipow[0] = 1; for (int i = 1; i < 2048; i++) psipow[i] = gl::mul(psipow[i - 1], T.psi);
-        for (int lane = 0; lane < 32 && !fails; lane += 5)
-            for (int r = 0; r < 32; r += 3) {
-                int k = brev5(lane) + 32 * brev5(r);
-                u64 s = 0;
-                for (int i = 0; i < N; i++) s = gl::add(s, gl::mul(a[i], psipow[(size_t)i * (2 * k + 1) % 2048]));
-                if (s != A[lane][r]) { fails++; printf("FAIL ntt1024 lane=%d r=%d\n", lane, r); break; }
-            }
-        warp_inv(A, back.data());
-        for (int i = 0; i < N; i++) if (back[i] != a[i]) { fails++; printf("FAIL roundtrip i=%d\n", i); break; }
-    }
-    // exact negacyclic product, signed 7-bit digits x 64-bit key, two 32-bit key limbs
-    for (int trial = 0; trial < 4; trial++) {
-        std::vector<int64_t> d(N); std::vector<u64> key(N), ref(N, 0), got(N);
-        for (int i = 0; i < N; i++) { d[i] = (int64_t)(rnd() % 128) - 64; key[i] = rnd(); }
-        if (trial == 1) for (int i = 0; i < N; i++) { d[i] = -64; key[i] = ~0ull; }
-        for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) {
-            u64 t = (u64)d[i] * key[j];
-            if (i + j < N) ref[i + j] += t; else ref[i + j - N] -= t;
+    for (int pi = 0; pi < NP; pi++) {
+        const u32 p = T.c.p[pi];
+        if (p >= (1u << 28) || (p - 1) % (2 * N) || powmod(T.psi[pi], N, p) != p - 1) { printf("FAIL prime %d\n", pi); return 1; }
+        if ((u32)(p * (0u - T.c.pinv_neg[pi])) != 1u) { printf("FAIL pinv %d\n", pi); return 1; }
+        // scalar primitives vs 64-bit arithmetic, including the lazy ranges
+        for (int it = 0; it < 200000; it++) {
+            const u32 w = rnd() % p, ws = shoup_of(w, p), y = (u32)rnd();
+            const u32 r = shoup_mul(y, w, ws, p);
+            if (r >= 2 * p || r % p != (u64)y * w % p) { fails++; printf("FAIL shoup\n"); break; }
+            const u32 d = (u32)rnd(), k = rnd() % p;
+            const u32 m = mont_mul(d, k, p, T.c.pinv_neg[pi]);
+            if (m >= 2 * p || (u64)m * (((u64)1 << 32) % p) % p != (u64)d * k % p) { fails++; printf("FAIL mont\n"); break; }
+            u32 X = rnd() % (4 * p), Y = rnd() % (4 * p), X0 = X, Y0 = Y;
+            ct_bfly(X, Y, w, ws, p, 2 * p);
+            const u64 wy = (u64)Y0 % p * w % p;
+            if (X >= 4 * p || Y >= 4 * p || X % p != (X0 % p + wy) % p || Y % p != (X0 % p + p - wy) % p) { fails++; printf("FAIL ct\n"); break; }
+            X = X0; Y = Y0;
+            gs_bfly(X, Y, w, ws, p, 4 * p);
+            if (X >= 4 * p || Y >= 2 * p || X % p != ((u64)X0 + Y0) % p || Y % p != ((u64)X0 % p + p - Y0 % p) % p * w % p) { fails++; printf("FAIL gs\n"); break; }
         }
-        std::vector<u64> df(N), lo(N), hi(N), rlo(N), rhi(N);
-        for (int i = 0; i < N; i++) { df[i] = gl::from_i64(d[i]); lo[i] = key[i] & gl::EPS; hi[i] = key[i] >> 32; }
-        static u64 D[32][32], L[32][32], H[32][32];
-        warp_fwd(df.data(), D); warp_fwd(lo.data(), L); warp_fwd(hi.data(), H);
-        for (int l = 0; l < 32; l++) for (int r = 0; r < 32; r++) { L[l][r] = gl::mul(L[l][r], D[l][r]); H[l][r] = gl::mul(H[l][r], D[l][r]); }
-        warp_inv(L, rlo.data()); warp_inv(H, rhi.data());
+        // forward transform vs the definition: out[pos] = A(psi^(2 brev(pos) + 1))
+        std::vector<u32> a(N), back(N);
+        for (auto& v : a) v = rnd() % (4 * p);
+        static u32 A[32][32];
+        warp_fwd(pi, a.data(), A);
+        std::vector<u32> psipow(2 * N);
+        psipow[0] = 1;
+        for (int i = 1; i < 2 * N; i++) psipow[i] = mulmod(psipow[i - 1], T.psi[pi], p);
+        for (int lane = 0; lane < 32 && !fails; lane += 3)
+            for (int c = 0; c < 32; c += 5) {
+                const u32 e = 2 * brev(ntt_pos(lane, c), LOGN) + 1;
+                u64 s = 0;
+                for (int i = 0; i < N; i++) s = (s + (u64)(a[i] % p) * psipow[(u64)i * e % (2 * N)]) % p;
+                if (A[lane][c] >= 4 * p || A[lane][c] % p != s) { fails++; printf("FAIL fwd prime=%d lane=%d c=%d\n", pi, lane, c); break; }
+            }
+        warp_inv(pi, A, back.data());
+        for (int i = 0; i < N; i++)
+            if (back[i] >= 4 * p || back[i] % p != (u64)(a[i] % p) * N % p) { fails++; printf("FAIL roundtrip prime=%d i=%d\n", pi, i); break; }
+    }
+    // exact negacyclic product of signed digits with a 64-bit key through the three primes
+    for (int trial = 0; trial < 5; trial++) {
+        const int L2 = 4;   // 2l polynomials accumulated before the inverse, as in the external product
+        std::vector<int64_t> d(L2 * N), key(L2 * N);
+        std::vector<u64> ref(N, 0);
+        for (int i = 0; i < L2 * N; i++) { d[i] = (int64_t)(rnd() % 128) - 64; key[i] = (int64_t)rnd(); }
+        if (trial == 1) for (int i = 0; i < L2 * N; i++) { d[i] = -64; key[i] = INT64_MIN; }          // largest magnitude: 2^81
+        if (trial == 2) for (int i = 0; i < L2 * N; i++) { d[i] = 63; key[i] = INT64_MAX; }
+        if (trial == 3) for (int i = 0; i < L2 * N; i++) { d[i] = (i & 1) ? 63 : -64; key[i] = (i & 2) ? INT64_MIN : INT64_MAX; }
+        for (int s = 0; s < L2; s++)
+            for (int i = 0; i < N; i++) {
+                if (!d[s * N + i]) continue;
+                for (int j = 0; j < N; j++) {
+                    const u64 t = (u64)d[s * N + i] * (u64)key[s * N + j];
+                    if (i + j < N) ref[i + j] += t; else ref[i + j - N] -= t;
+                }
+            }
+        static u32 res[NP][1024];
+        for (int pi = 0; pi < NP; pi++) {
+            const u32 p = T.c.p[pi];
+            static u32 D[32][32], K[32][32], ACC[32][32];
+            for (int l = 0; l < 32; l++) for (int c = 0; c < 32; c++) ACC[l][c] = 0;
+            std::vector<u32> tmp(N);
+            for (int s = 0; s < L2; s++) {
+                for (int i = 0; i < N; i++) tmp[i] = (u32)(d[s * N + i] + 64) + (p - 64);              // biased byte + (p - Bg/2)
+                warp_fwd(pi, tmp.data(), D);
+                for (int i = 0; i < N; i++) tmp[i] = residue_i64(key[s * N + i], p);
+                warp_fwd(pi, tmp.data(), K);
+                for (int l = 0; l < 32; l++)
+                    for (int c = 0; c < 32; c++) {
+                        const u32 kk = mulmod(K[l][c] % p, T.c.key_scale[pi], p);                      // stored key: NTT(K) N^-1 2^32
+                        ACC[l][c] += mont_mul(D[l][c], kk, p, T.c.pinv_neg[pi]);
+                    }
+            }
+            for (int l = 0; l < 32; l++)
+                for (int c = 0; c < 32; c++) {
+                    u32 v = ACC[l][c];
+                    if (v >= 8 * p) { fails++; printf("FAIL acc range\n"); }
+                    ACC[l][c] = umin32(v, v - 4 * p);
+                }
+            warp_inv(pi, ACC, res[pi]);
+        }
         for (int i = 0; i < N; i++) {
-            got[i] = gl::lift(rlo[i]) + (gl::lift(rhi[i]) << 32);
-            if (got[i] != ref[i]) { fails++; printf("FAIL product trial=%d i=%d\n", trial, i); break; }
+            const u64 got = crt_lift(res[0][i], res[1][i], res[2][i], T.c.crt);
+            if (got != ref[i]) { fails++; printf("FAIL product trial=%d i=%d got=%llx ref=%llx\n", trial, i, (unsigned long long)got, (unsigned long long)ref[i]); break; }
         }
     }
     printf(fails ? "ntt_emu: %d FAILURES\n" : "ntt_emu: OK\n", fails);

@@ -1,39 +1,50 @@
 // kernels.cuh -- sm_100a kernels of the 3gen MK-TFHE bootstrapped-gate path.
 //
-//   bsk_transform_kernel   one-time: int64 key polys -> two NTT-domain limbs, streaming layout
+//   bsk_transform_kernel   one-time: int64 key polynomials -> three NTT-domain residue polynomials, streaming layout
 //   blind_rotate_kernel    gate prologue + mod-switch + k*n mux-rotate steps + sample extraction
 //   keyswitch_kernel       multi-key LWE key switch (gather-accumulate over ksk rows)
 //   extprod_kernel / negacyclic_mul_kernel   parity hooks built from the same device code
 //
-// Reference semantics (3-gen-mk-tfhe/src/): 3gen_mk_internals.jl:59-116,
-// tgsw_3gen.jl:102-113, tgsw.jl:112-138, rlwe.jl:70-74, keyswitch.jl:45-80,
-// mk_internals.jl:730-744, numeric-functions.jl:70-73,109-111.
+// Reference semantics (3-gen-mk-tfhe/src/): 3gen_mk_internals.jl:59-116, tgsw_3gen.jl:102-113, tgsw.jl:112-138,
+// rlwe.jl:70-74, keyswitch.jl:45-80, mk_internals.jl:730-744, numeric-functions.jl:70-73,109-111.
+//
+// Work decomposition of the blind rotation: one gate = 3 warps (one per RNS prime, 96 threads); a CTA holds GPC
+// gates plus one shared-memory copy of the per-lane twiddle table.  Per gate, resident in shared memory for all
+// k*n steps: the Torus64 accumulator (2 x 1024 x 8 B), the current gadget digits (2l x 1024 bytes) and one padded
+// 32x33 word tile per warp (NTT transposes, then the inverse transforms' residues for the CRT).
 #pragma once
 #include <cuda_runtime.h>
-#include "ntt1024.cuh"
+#include "ntt_rns.cuh"
 
 namespace mk {
 
-constexpr int N = ntt::N;
-constexpr int BR_THREADS = 128;  // 4 warps: one polynomial transform each
-constexpr int BR_WARPS = BR_THREADS / 32;
 
-// BSK streaming layout (u64): [elem = party*n + j][outlimb = out*2 + limb][r 32][lane 32][s = src*l + q]
+
+using rns::uint2_;
+
+constexpr int N = rns::N;
+constexpr int TPG = 96;                              // threads per gate: one warp per prime
+constexpr int TWB_WORDS = rns::NP * 2 * 31 * 32 * 2; // per-lane twiddle table [prime][dir][31][32] of (w, w') = 47616 B
+constexpr int MAX_GPC = 5;                           // gates per CTA (named barriers 1..GPC)
+
+__constant__ rns::Consts c_rns;
+
+// BSK streaming layout (u32): [elem = party*n + j][prime][s = src*l + q][out][key slot]
 //   out : 0 = mask', 1 = body'   (accumulator polynomial written)
 //   src : 0 = body digits (c0), 1 = mask digits (c1)
 //   (out, src) -> reference part: body<-body part_1, body<-mask part_2, mask<-mask part_3, mask<-body part_4
-//   (r, lane) -> NTT index brev5(lane) + 32*brev5(r)  (ntt1024.cuh NTT-domain layout)
-__host__ __device__ inline size_t bsk_elem_u64(int l) { return (size_t)4 * N * 2 * l; }
+//   key slot: rns::key_slot(lane, c) of transformed position 32*lane + c; values NTT(K mod p) * N^-1 * 2^32 mod p
+__host__ __device__ inline size_t bsk_elem_words(int l) { return (size_t)rns::NP * 2 * l * 2 * N; }
+__host__ __device__ inline size_t gate_smem_bytes(int l) { return (size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)rns::NP * rns::TILE_WORDS * 4; }
 
 struct GateLinear {   // temp = mu0 + cx*x + cy*y + cz*z   (3gen_mk_gates.jl:8-74)
     int32_t mu0, cx, cy, cz;
 };
 
 struct BlindRotateArgs {
-    int n, k, bgbit;
-    const u64* bsk;
-    const u64* tw_fwd;
-    const u64* tw_inv;
+    int G, n, k, bgbit;
+    const u32* bsk;
+    const uint2_* twB;
     const int32_t *xa, *xb, *ya, *yb, *za, *zb;
     GateLinear lin;
     int64_t mu;
@@ -41,7 +52,7 @@ struct BlindRotateArgs {
     int64_t* acc_out;   // [G][2][N] or nullptr
 };
 
-__device__ __forceinline__ int tiles_needed(int l) { return 2 * l > BR_WARPS ? 2 * l : BR_WARPS; }
+__device__ __forceinline__ void gate_barrier(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(TPG) : "memory"); }
 
 // decode_message(x, 2N), numeric-functions.jl:70-73 (wrapping add, arithmetic shift)
 __device__ __forceinline__ int mod_switch_2N(int32_t x) {
@@ -53,262 +64,274 @@ __device__ __forceinline__ int32_t t64tot32(int64_t v) {
     return __double2int_rz(__ll2double_rn(v) * (1.0 / 4294967296.0));
 }
 
-// One external product (tgsw_extern_mul_3gen, tgsw_3gen.jl:102-113) on the
-// accumulator held in shared memory, by the 4 warps of the CTA.
-//   MUX = true : acc += ExtProd(X^a * acc - acc, key)   (mk_mux_rotate_3gen, 3gen_mk_internals.jl:59-62)
-//   MUX = false: acc  = ExtProd(acc, key)
-// acc: [2][N] u64, [0] = mask, [1] = body.  tiles: tiles_needed(L) padded 32x33 u64 tiles.
-template <int L, bool MUX>
-__device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u64* __restrict__ tiles, const u64* __restrict__ key,
-                                             int a, int bgbit, const u64* __restrict__ tw_fwd,
-                                             const u64* __restrict__ tw_inv) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // ---- phase A: rotate-subtract, gadget-decompose (tgsw.jl:112-138), forward NTT of the 2L digit polynomials
-    u64 off = 0;
-#pragma unroll
-    for (int q = 1; q <= L; q++) off += ((u64)1 << (64 - q * bgbit)) << (bgbit - 1);   // tgsw.jl:24-30
-    const int64_t dmask = ((int64_t)1 << bgbit) - 1, dhalf = (int64_t)1 << (bgbit - 1);
-    for (int s = warp; s < 2 * L; s += BR_WARPS) {
-        const int src = s / L, q = s - src * L;
-        const u64* poly = acc + (1 - src) * N;   // src 0 = body = acc[1]
-        const int sh = 64 - (q + 1) * bgbit;
-        u64 x[32];
-#pragma unroll
-        for (int i1 = 0; i1 < 32; i1++) {
-            const int i = 32 * i1 + lane;
-            u64 t;
-            if (MUX) {
-                const int idx = (i - a) & (2 * N - 1);        // (X^a * p)[i] = +-p[(i - a) mod 2N]
-                u64 v = poly[idx & (N - 1)];
-                if (idx & N) v = 0 - v;
-                t = v - poly[i];
-            } else {
-                t = poly[i];
-            }
-            const int64_t d = (((int64_t)(t + off) >> sh) & dmask) - dhalf;
-            x[i1] = gl::from_i64(d);
-        }
-        ntt::fwd_pass1(x, tw_fwd, lane);
-        u64* tile = tiles + s * ntt::TILE_ELEMS;
-#pragma unroll
-        for (int r = 0; r < 32; r++) tile[r * ntt::TILE_STRIDE + lane] = x[r];
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 32; j++) x[j] = tile[lane * ntt::TILE_STRIDE + j];
-        __syncwarp();
-        ntt::fwd_pass2(x);
-#pragma unroll
-        for (int r = 0; r < 32; r++) tile[r * ntt::TILE_STRIDE + lane] = x[r];
-    }
-    __syncthreads();
-    // ---- phase B: warp w accumulates output polynomial (out, limb) = (w >> 1, w & 1) in the NTT domain
-    u64 y[32];
-    {
-        const u64* kp = key + (size_t)warp * (N * 2 * L) + lane * (2 * L);
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            u64 kv[2 * L];
-            const ulonglong2* kp2 = reinterpret_cast<const ulonglong2*>(kp + (size_t)r * 32 * 2 * L);
-#pragma unroll
-            for (int s2 = 0; s2 < L; s2++) {
-                ulonglong2 v = __ldg(kp2 + s2);
-                kv[2 * s2] = v.x;
-                kv[2 * s2 + 1] = v.y;
-            }
-            u64 sum = 0;
-#pragma unroll
-            for (int s = 0; s < 2 * L; s++)
-                sum = gl::add(sum, gl::mul(tiles[s * ntt::TILE_ELEMS + r * ntt::TILE_STRIDE + lane], kv[s]));
-            y[r] = sum;
-        }
-    }
-    __syncthreads();   // all digit tiles consumed; tiles are scratch again
-    // ---- inverse NTT of the 4 output polynomials
-    ntt::inv_pass1(y, tw_inv, lane);
-    u64* tile = tiles + warp * ntt::TILE_ELEMS;
-#pragma unroll
-    for (int j = 0; j < 32; j++) tile[lane * ntt::TILE_STRIDE + j] = y[j];
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 32; r++) y[r] = tile[r * ntt::TILE_STRIDE + lane];
-    __syncwarp();
-    ntt::inv_pass2(y);
-    // ---- phase C: recombine limbs (exact mod 2^64) and update the accumulator
-    const int out = warp >> 1, limb = warp & 1;
-    if (limb == 1) {
-        u32* hb = reinterpret_cast<u32*>(tile);
-#pragma unroll
-        for (int i1 = 0; i1 < 32; i1++) hb[32 * i1 + lane] = (u32)gl::lift(y[i1]);
-    }
-    __syncthreads();
-    if (limb == 0) {
-        const u32* hb = reinterpret_cast<const u32*>(tiles + (warp + 1) * ntt::TILE_ELEMS);
-        u64* ap = acc + out * N;
-#pragma unroll
-        for (int i1 = 0; i1 < 32; i1++) {
-            const int i = 32 * i1 + lane;
-            const u64 v = gl::lift(y[i1]) + ((u64)hb[i] << 32);
-            ap[i] = MUX ? ap[i] + v : v;
-        }
-    }
-    __syncthreads();
+__device__ __forceinline__ void stage_twiddles(uint2_* twB_s, const uint2_* twB_g) {
+    const uint4* src = reinterpret_cast<const uint4*>(twB_g);
+    uint4* dst = reinterpret_cast<uint4*>(twB_s);
+    for (int i = threadIdx.x; i < TWB_WORDS / 4; i += blockDim.x) dst[i] = __ldg(src + i);
 }
 
-// One CTA per gate.  Accumulator resident in shared memory for all k*n steps.
-template <int L>
-__global__ void __launch_bounds__(BR_THREADS, 4) blind_rotate_kernel(BlindRotateArgs p) {
+// forward transform of the 32 elements of this thread (coefficients 32 r + lane -> positions 32 lane + c)
+__device__ __forceinline__ void warp_ntt_fwd(u32 (&x)[32], u32* tile, const uint2_* twA, const uint2_* twB_lane, u32 p, int lane) {
+    rns::fwd_passA(x, twA, p);
+#pragma unroll
+    for (int r = 0; r < 32; r++) tile[r * rns::TILE_STRIDE + lane] = x[r];
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 32; c++) x[c] = tile[lane * rns::TILE_STRIDE + c];
+    __syncwarp();
+    rns::fwd_passB(x, twB_lane, p);
+}
+// inverse transform (positions 32 lane + c -> coefficients 32 r + lane), scaled by N
+__device__ __forceinline__ void warp_ntt_inv(u32 (&x)[32], u32* tile, const uint2_* twA, const uint2_* twB_lane, u32 p, int lane) {
+    rns::inv_passB(x, twB_lane, p);
+#pragma unroll
+    for (int c = 0; c < 32; c++) tile[lane * rns::TILE_STRIDE + c] = x[c];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 32; r++) x[r] = tile[r * rns::TILE_STRIDE + lane];
+    __syncwarp();
+    rns::inv_passA(x, twA, p);
+}
+
+// One external product (tgsw_extern_mul_3gen, tgsw_3gen.jl:102-113) on the accumulator held in shared memory, by the
+// 96 threads of one gate (gtid = 0..95, warp = prime).
+//   MUX = true : acc += ExtProd(X^a * acc - acc, key)   (mk_mux_rotate_3gen, 3gen_mk_internals.jl:59-62)
+//   MUX = false: acc  = ExtProd(acc, key)
+// acc: [2][N] u64, [0] = mask, [1] = body.  dig: [2L][8][32] words of 4 biased digit bytes.  tiles: [3][TILE_WORDS].
+template <int L, bool MUX>
+__device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restrict__ dig, u32* __restrict__ tiles,
+                                             const uint2_* __restrict__ twB, const u32* __restrict__ key, int a, int bgbit,
+                                             int bar_id, int gtid) {
+    const int w = gtid >> 5, lane = gtid & 31;
+    // ---- phase 1: rotate-subtract and gadget-decompose (tgsw.jl:112-138); digits biased to [0, Bg) and packed 4 per word
+    {
+        u64 off = 0;
+#pragma unroll
+        for (int q = 1; q <= L; q++) off += ((u64)1 << (64 - q * bgbit)) << (bgbit - 1);   // tgsw.jl:24-30
+        const u32 dmask = (1u << bgbit) - 1;
+        for (int task = gtid; task < 512; task += TPG) {
+            const int c = task >> 8, rh = (task >> 5) & 7, ln = task & 31;
+            const u64* poly = acc + c * N;
+            u32 packed[L];
+#pragma unroll
+            for (int q = 0; q < L; q++) packed[q] = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int i = 32 * (4 * rh + b) + ln;
+                u64 t;
+                if (MUX) {
+                    const int idx = (i - a) & (2 * N - 1);        // (X^a * p)[i] = +-p[(i - a) mod 2N]
+                    u64 v = poly[idx & (N - 1)];
+                    if (idx & N) v = 0 - v;
+                    t = v - poly[i];
+                } else {
+                    t = poly[i];
+                }
+                t += off;
+#pragma unroll
+                for (int q = 0; q < L; q++) packed[q] |= ((u32)(t >> (64 - (q + 1) * bgbit)) & dmask) << (8 * b);
+            }
+            const int src = 1 - c;   // src 0 = body = acc[1]
+#pragma unroll
+            for (int q = 0; q < L; q++) dig[((src * L + q) * 8 + rh) * 32 + ln] = packed[q];
+        }
+    }
+    gate_barrier(bar_id);
+    // ---- phase 2: per prime, forward NTT of each digit polynomial and multiply-accumulate with the key (NTT domain)
+    const u32 p = c_rns.p[w], pinv = c_rns.pinv_neg[w];
+    u32* tile = tiles + w * rns::TILE_WORDS;
+    const uint2_* twBf = twB + ((size_t)(w * 2 + 0) * 31) * 32 + lane;
+    const uint2_* twBi = twB + ((size_t)(w * 2 + 1) * 31) * 32 + lane;
+    const uint4* kp = reinterpret_cast<const uint4*>(key + (size_t)w * (2 * L * 2 * N)) + lane;
+    u32 acc0[32], acc1[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++) acc0[c] = acc1[c] = 0;
+    const u32 bias = p - (1u << (bgbit - 1));
+#pragma unroll 1
+    for (int s = 0; s < 2 * L; s++) {
+        u32 x[32];
+#pragma unroll
+        for (int rh = 0; rh < 8; rh++) {
+            const u32 word = dig[(s * 8 + rh) * 32 + lane];
+#pragma unroll
+            for (int b = 0; b < 4; b++) x[4 * rh + b] = ((word >> (8 * b)) & 0xffu) + bias;
+        }
+        warp_ntt_fwd(x, tile, c_rns.twA[w][0], twBf, p, lane);
+        const uint4* k0 = kp + (size_t)(s * 2) * (N / 4);
+#pragma unroll
+        for (int q4 = 0; q4 < 8; q4++) {
+            const uint4 kv = __ldg(k0 + q4 * 32);
+            acc0[4 * q4 + 0] += rns::mont_mul(x[4 * q4 + 0], kv.x, p, pinv);
+            acc0[4 * q4 + 1] += rns::mont_mul(x[4 * q4 + 1], kv.y, p, pinv);
+            acc0[4 * q4 + 2] += rns::mont_mul(x[4 * q4 + 2], kv.z, p, pinv);
+            acc0[4 * q4 + 3] += rns::mont_mul(x[4 * q4 + 3], kv.w, p, pinv);
+        }
+        const uint4* k1 = k0 + N / 4;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; q4++) {
+            const uint4 kv = __ldg(k1 + q4 * 32);
+            acc1[4 * q4 + 0] += rns::mont_mul(x[4 * q4 + 0], kv.x, p, pinv);
+            acc1[4 * q4 + 1] += rns::mont_mul(x[4 * q4 + 1], kv.y, p, pinv);
+            acc1[4 * q4 + 2] += rns::mont_mul(x[4 * q4 + 2], kv.z, p, pinv);
+            acc1[4 * q4 + 3] += rns::mont_mul(x[4 * q4 + 3], kv.w, p, pinv);
+        }
+    }
+    // ---- phase 3: per output polynomial, inverse NTT of the three residue polynomials, Garner CRT, accumulator update
+#pragma unroll 1
+    for (int out = 0; out < 2; out++) {
+        u32 x[32];
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+            u32 v = out ? acc1[c] : acc0[c];                 // sum of 2L products, each in [0, 2p)
+            if (L > 2) v = rns::umin32(v, v - 8 * p);
+            x[c] = rns::umin32(v, v - 4 * p);                // [0, 4p)
+        }
+        warp_ntt_inv(x, tile, c_rns.twA[w][1], twBi, p, lane);
+#pragma unroll
+        for (int r = 0; r < 32; r++) tile[32 * r + lane] = x[r];   // residues in coefficient order
+        gate_barrier(bar_id);
+        u64* ap = acc + out * N;
+        for (int i = gtid; i < N; i += TPG) {
+            const u64 R = rns::crt_lift(tiles[i], tiles[rns::TILE_WORDS + i], tiles[2 * rns::TILE_WORDS + i], c_rns.crt);
+            ap[i] = MUX ? ap[i] + R : R;
+        }
+        gate_barrier(bar_id);
+    }
+}
+
+// GPC gates per CTA, 3 warps per gate.  Accumulators resident in shared memory for all k*n steps.
+template <int L, int GPC>
+__global__ void __launch_bounds__(GPC* TPG, 1) blind_rotate_kernel(BlindRotateArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64* acc = reinterpret_cast<u64*>(smem_raw);
-    u64* tiles = acc + 2 * N;
-    const int NT = 2 * L > BR_WARPS ? 2 * L : BR_WARPS;
-    int16_t* bara = reinterpret_cast<int16_t*>(tiles + NT * ntt::TILE_ELEMS);
-    __shared__ int s_barb;
-    const int g = blockIdx.x, tid = threadIdx.x, kn = p.k * p.n;
-    // gate prologue (3gen_mk_gates.jl) + mod switch (3gen_mk_internals.jl:102-103)
-    for (int i = tid; i < kn; i += BR_THREADS) {
-        uint32_t t = (uint32_t)p.lin.cx * (uint32_t)p.xa[(size_t)g * kn + i];
-        if (p.lin.cy) t += (uint32_t)p.lin.cy * (uint32_t)p.ya[(size_t)g * kn + i];
-        if (p.lin.cz) t += (uint32_t)p.lin.cz * (uint32_t)p.za[(size_t)g * kn + i];
-        bara[i] = (int16_t)mod_switch_2N((int32_t)t);
-    }
-    if (tid == 0) {
-        uint32_t t = (uint32_t)p.lin.mu0 + (uint32_t)p.lin.cx * (uint32_t)p.xb[g];
-        if (p.lin.cy) t += (uint32_t)p.lin.cy * (uint32_t)p.yb[g];
-        if (p.lin.cz) t += (uint32_t)p.lin.cz * (uint32_t)p.zb[g];
-        s_barb = mod_switch_2N((int32_t)t);
-    }
+    uint2_* twB = reinterpret_cast<uint2_*>(smem_raw);
+    stage_twiddles(twB, p.twB);
     __syncthreads();
+    const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot;
+    const int g = blockIdx.x * GPC + slot;
+    if (g >= p.G) return;   // no CTA-wide barrier below this line
+    unsigned char* base = smem_raw + TWB_WORDS * 4 + (size_t)slot * gate_smem_bytes(L);
+    u64* acc = reinterpret_cast<u64*>(base);
+    u32* dig = reinterpret_cast<u32*>(base + 2 * N * 8);
+    u32* tiles = dig + 2 * L * (N / 4);
+    const int kn = p.k * p.n;
+    // gate prologue (3gen_mk_gates.jl) + mod switch (3gen_mk_internals.jl:102-103); every thread of the gate computes
+    // the same rotation amounts from broadcast loads
+    auto rotation = [&](const int32_t* xs, const int32_t* ys, const int32_t* zs, size_t idx, uint32_t mu0) {
+        uint32_t t = mu0 + (uint32_t)p.lin.cx * (uint32_t)__ldg(xs + idx);
+        if (p.lin.cy) t += (uint32_t)p.lin.cy * (uint32_t)__ldg(ys + idx);
+        if (p.lin.cz) t += (uint32_t)p.lin.cz * (uint32_t)__ldg(zs + idx);
+        return mod_switch_2N((int32_t)t);
+    };
+    const int barb = rotation(p.xb, p.yb, p.zb, g, (uint32_t)p.lin.mu0);
     // acc = (0, X^{-barb} * testvect), testvect = mu * (1 + X + ... + X^{N-1})  (:88-92, rlwe.jl:113-119)
     {
-        const int s = (-s_barb) & (2 * N - 1);
-        for (int i = tid; i < N; i += BR_THREADS) {
+        const int s = (-barb) & (2 * N - 1);
+        for (int i = gtid; i < N; i += TPG) {
             const int idx = (i - s) & (2 * N - 1);
             acc[i] = 0;
             acc[N + i] = (idx & N) ? (u64)0 - (u64)p.mu : (u64)p.mu;
         }
     }
-    __syncthreads();
+    gate_barrier(bar_id);
     // mk_blind_rotate_3gen: parties outer, coefficients inner (:66-84); element index = party*n + j
-    const size_t estride = bsk_elem_u64(L);
+    const size_t estride = bsk_elem_words(L);
+    const size_t abase = (size_t)g * kn;
+    int a_next = rotation(p.xa, p.ya, p.za, abase, 0u);
     for (int it = 0; it < kn; it++) {
-        const int a = bara[it];
-        if (a == 0) continue;   // :69 (uniform across the CTA)
-        extprod_step<L, true>(acc, tiles, p.bsk + (size_t)it * estride, a, p.bgbit, p.tw_fwd, p.tw_inv);
+        const int a = a_next;
+        if (it + 1 < kn) a_next = rotation(p.xa, p.ya, p.za, abase + it + 1, 0u);
+        if (a == 0) continue;   // :69 (uniform across the gate)
+        extprod_step<L, true>(acc, dig, tiles, twB, p.bsk + (size_t)it * estride, a, p.bgbit, bar_id, gtid);
     }
     // rlwe_extract_sample_64 (rlwe.jl:70-74): a'_0 = mask_0, a'_i = -mask_{N-i}, b' = body_0
     int32_t* ext = p.ext_out + (size_t)g * (N + 1);
-    for (int i = tid; i < N; i += BR_THREADS) {
+    for (int i = gtid; i < N; i += TPG) {
         const u64 v = i == 0 ? acc[0] : (u64)0 - acc[N - i];
         ext[i] = t64tot32((int64_t)v);
     }
-    if (tid == 0) ext[N] = t64tot32((int64_t)acc[N]);
+    if (gtid == 0) ext[N] = t64tot32((int64_t)acc[N]);
     if (p.acc_out) {
         int64_t* ao = p.acc_out + (size_t)g * 2 * N;
-        for (int i = tid; i < 2 * N; i += BR_THREADS) ao[i] = (int64_t)acc[i];
+        for (int i = gtid; i < 2 * N; i += TPG) ao[i] = (int64_t)acc[i];
     }
 }
 
 // parity hook: acc_out[g] = ExtProd(acc_in[g], bsk[elem[g]])
-template <int L>
-__global__ void __launch_bounds__(BR_THREADS, 4) extprod_kernel(const u64* bsk, const u64* tw_fwd, const u64* tw_inv, int bgbit,
-                                                                 const int32_t* elem, const int64_t* acc_in, int64_t* acc_out) {
+template <int L, int GPC>
+__global__ void __launch_bounds__(GPC* TPG, 1) extprod_kernel(int G, const u32* bsk, const uint2_* twB_g, int bgbit, const int32_t* elem,
+                                                               const int64_t* acc_in, int64_t* acc_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64* acc = reinterpret_cast<u64*>(smem_raw);
-    u64* tiles = acc + 2 * N;
-    const int g = blockIdx.x, tid = threadIdx.x;
-    for (int i = tid; i < 2 * N; i += BR_THREADS) acc[i] = (u64)acc_in[(size_t)g * 2 * N + i];
+    uint2_* twB = reinterpret_cast<uint2_*>(smem_raw);
+    stage_twiddles(twB, twB_g);
     __syncthreads();
-    extprod_step<L, false>(acc, tiles, bsk + (size_t)elem[g] * bsk_elem_u64(L), 0, bgbit, tw_fwd, tw_inv);
-    for (int i = tid; i < 2 * N; i += BR_THREADS) acc_out[(size_t)g * 2 * N + i] = (int64_t)acc[i];
+    const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot;
+    const int g = blockIdx.x * GPC + slot;
+    if (g >= G) return;
+    unsigned char* base = smem_raw + TWB_WORDS * 4 + (size_t)slot * gate_smem_bytes(L);
+    u64* acc = reinterpret_cast<u64*>(base);
+    u32* dig = reinterpret_cast<u32*>(base + 2 * N * 8);
+    u32* tiles = dig + 2 * L * (N / 4);
+    for (int i = gtid; i < 2 * N; i += TPG) acc[i] = (u64)acc_in[(size_t)g * 2 * N + i];
+    gate_barrier(bar_id);
+    extprod_step<L, false>(acc, dig, tiles, twB, bsk + (size_t)elem[g] * bsk_elem_words(L), 0, bgbit, bar_id, gtid);
+    for (int i = gtid; i < 2 * N; i += TPG) acc_out[(size_t)g * 2 * N + i] = (int64_t)acc[i];
 }
 
-// One warp per (polynomial, limb): raw int64 key -> NTT-domain streaming layout.
-// raw: [n][4 parts][l][N] int64 of one party; task = ((j*4 + part)*l + q)*2 + limb.
-__global__ void __launch_bounds__(BR_THREADS) bsk_transform_kernel(const int64_t* __restrict__ raw, u64* __restrict__ bsk, int n, int l,
-                                                                     int party, const u64* __restrict__ tw_fwd, int ntasks) {
-    __shared__ u64 tiles[BR_WARPS * ntt::TILE_ELEMS];
+// One warp per (polynomial, prime): raw int64 key -> NTT-domain residues in the streaming layout.
+// raw: [n][4 parts][l][N] int64 of one party; task = ((j*4 + part)*l + q)*3 + prime.
+constexpr int XF_WARPS = 4;
+__global__ void __launch_bounds__(XF_WARPS * 32) bsk_transform_kernel(const int64_t* __restrict__ raw, u32* __restrict__ bsk, int n, int l, int party,
+                                                                        const uint2_* __restrict__ twB, int ntasks) {
+    __shared__ u32 tiles[XF_WARPS * rns::TILE_WORDS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int task = blockIdx.x * BR_WARPS + warp;
+    const int task = blockIdx.x * XF_WARPS + warp;
     if (task >= ntasks) return;
-    const int limb = task & 1, pq = task >> 1;
+    const int pi = task % 3, pq = task / 3;
     const int q = pq % l, part = (pq / l) & 3, j = pq / (4 * l);
     // part_1: body<-body, part_2: body<-mask, part_3: mask<-mask, part_4: mask<-body  (tgsw_3gen.jl:109-110)
     const int out = part < 2 ? 1 : 0;
     const int src = (part == 0 || part == 3) ? 0 : 1;
+    const u32 p = c_rns.p[pi];
     const int64_t* poly = raw + (size_t)pq * N;
-    u64 x[32];
+    u32 x[32];
 #pragma unroll
-    for (int i1 = 0; i1 < 32; i1++) {
-        const u64 v = (u64)poly[32 * i1 + lane];
-        x[i1] = limb ? (v >> 32) : (v & gl::EPS);
-    }
-    ntt::fwd_pass1(x, tw_fwd, lane);
-    u64* tile = tiles + warp * ntt::TILE_ELEMS;
-#pragma unroll
-    for (int r = 0; r < 32; r++) tile[r * ntt::TILE_STRIDE + lane] = x[r];
-    __syncwarp();
-#pragma unroll
-    for (int jj = 0; jj < 32; jj++) x[jj] = tile[lane * ntt::TILE_STRIDE + jj];
-    ntt::fwd_pass2(x);
+    for (int r = 0; r < 32; r++) x[r] = rns::residue_i64(poly[32 * r + lane], p);
+    warp_ntt_fwd(x, tiles + warp * rns::TILE_WORDS, c_rns.twA[pi][0], twB + ((size_t)(pi * 2 + 0) * 31) * 32 + lane, p, lane);
     const size_t e = (size_t)party * n + j;
-    u64* dst = bsk + e * bsk_elem_u64(l) + (size_t)(out * 2 + limb) * (N * 2 * l) + (size_t)lane * 2 * l + (src * l + q);
+    u32* dst = bsk + e * bsk_elem_words(l) + ((size_t)(pi * 2 * l + (src * l + q)) * 2 + out) * N;
 #pragma unroll
-    for (int r = 0; r < 32; r++) dst[(size_t)r * 32 * 2 * l] = x[r];
+    for (int c = 0; c < 32; c++) dst[rns::key_slot(lane, c)] = rns::mulmod(x[c] % p, c_rns.key_scale[pi], p);
 }
 
-// parity hook: exact c = a * b mod (X^N + 1, 2^64); 3 warps: a, b_lo, b_hi
-__global__ void __launch_bounds__(96) negacyclic_mul_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ b, int64_t* __restrict__ c,
-                                                             const u64* __restrict__ tw_fwd, const u64* __restrict__ tw_inv) {
-    __shared__ u64 tiles[3 * ntt::TILE_ELEMS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// parity hook and key-generation primitive: exact c = a * b mod (X^N + 1, 2^64) for |a_i| <= 2^8; 3 warps = 3 primes
+__global__ void __launch_bounds__(TPG) negacyclic_mul_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ b, int64_t* __restrict__ c,
+                                                              const uint2_* __restrict__ twB) {
+    __shared__ u32 tiles[rns::NP * rns::TILE_WORDS];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t g = blockIdx.x;
-    u64 x[32];
+    const u32 p = c_rns.p[w], pinv = c_rns.pinv_neg[w];
+    u32* tile = tiles + w * rns::TILE_WORDS;
+    const uint2_* twBf = twB + ((size_t)(w * 2 + 0) * 31) * 32 + lane;
+    const uint2_* twBi = twB + ((size_t)(w * 2 + 1) * 31) * 32 + lane;
+    u32 x[32], y[32];
 #pragma unroll
-    for (int i1 = 0; i1 < 32; i1++) {
-        const int i = 32 * i1 + lane;
-        if (warp == 0) x[i1] = gl::from_i64(a[g * N + i]);
-        else { const u64 v = (u64)b[g * N + i]; x[i1] = warp == 2 ? (v >> 32) : (v & gl::EPS); }
+    for (int r = 0; r < 32; r++) {
+        x[r] = rns::residue_i64(a[g * N + 32 * r + lane], p);
+        y[r] = rns::residue_i64(b[g * N + 32 * r + lane], p);
     }
-    ntt::fwd_pass1(x, tw_fwd, lane);
-    u64* tile = tiles + warp * ntt::TILE_ELEMS;
+    warp_ntt_fwd(x, tile, c_rns.twA[w][0], twBf, p, lane);
+    warp_ntt_fwd(y, tile, c_rns.twA[w][0], twBf, p, lane);
 #pragma unroll
-    for (int r = 0; r < 32; r++) tile[r * ntt::TILE_STRIDE + lane] = x[r];
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 32; j++) x[j] = tile[lane * ntt::TILE_STRIDE + j];
-    __syncwarp();
-    ntt::fwd_pass2(x);
-    if (warp == 0) {
-#pragma unroll
-        for (int r = 0; r < 32; r++) tile[r * ntt::TILE_STRIDE + lane] = x[r];
+    for (int cc = 0; cc < 32; cc++) {
+        const u32 ks = rns::mulmod(y[cc] % p, c_rns.key_scale[w], p);
+        x[cc] = rns::mont_mul(x[cc], ks, p, pinv);
     }
+    warp_ntt_inv(x, tile, c_rns.twA[w][1], twBi, p, lane);
+#pragma unroll
+    for (int r = 0; r < 32; r++) tile[32 * r + lane] = x[r];
     __syncthreads();
-    if (warp > 0) {
-#pragma unroll
-        for (int r = 0; r < 32; r++) x[r] = gl::mul(x[r], tiles[r * ntt::TILE_STRIDE + lane]);
-        ntt::inv_pass1(x, tw_inv, lane);
-#pragma unroll
-        for (int j = 0; j < 32; j++) tile[lane * ntt::TILE_STRIDE + j] = x[j];
-        __syncwarp();
-#pragma unroll
-        for (int r = 0; r < 32; r++) x[r] = tile[r * ntt::TILE_STRIDE + lane];
-        __syncwarp();
-        ntt::inv_pass2(x);
-        if (warp == 2) {
-            u32* hb = reinterpret_cast<u32*>(tile);
-#pragma unroll
-            for (int i1 = 0; i1 < 32; i1++) hb[32 * i1 + lane] = (u32)gl::lift(x[i1]);
-        }
-    }
-    __syncthreads();
-    if (warp == 1) {
-        const u32* hb = reinterpret_cast<const u32*>(tiles + 2 * ntt::TILE_ELEMS);
-#pragma unroll
-        for (int i1 = 0; i1 < 32; i1++) {
-            const int i = 32 * i1 + lane;
-            c[g * N + i] = (int64_t)(gl::lift(x[i1]) + ((u64)hb[i] << 32));
-        }
-    }
+    for (int i = threadIdx.x; i < N; i += TPG)
+        c[g * N + i] = (int64_t)rns::crt_lift(tiles[i], tiles[rns::TILE_WORDS + i], tiles[2 * rns::TILE_WORDS + i], c_rns.crt);
 }
 
 // Multi-key LWE key switch (mk_keyswitch_3gen mk_internals.jl:730-744, keyswitch keyswitch.jl:45-80).

@@ -1,10 +1,11 @@
 // mktfhe_b200.cu -- C ABI (include/mktfhe_b200.h) over the sm_100a kernels in kernels.cuh.
 //
-// One context owns one GPU: the NTT-domain bootstrapping key (two 32-bit limbs per
+// One context owns one GPU: the NTT-domain bootstrapping key (three 28-bit-prime residues per
 // reference polynomial), the key-switching key, the twiddle tables, one stream and
 // growable device staging buffers.  There is no CPU fallback: every entry point
 // either launches the CUDA kernels or returns an error code.
 #include <cuda_runtime.h>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -33,12 +34,12 @@ struct mktfhe_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // br start/stop, ks start/stop
     bool ev_valid = false;
-    u64* d_bsk = nullptr;
+    u32* d_bsk = nullptr;
     size_t bsk_bytes = 0;
     int32_t* d_ksk = nullptr;
     size_t ksk_bytes = 0;
-    u64* d_tw_fwd = nullptr;
-    u64* d_tw_inv = nullptr;
+    rns::uint2_* d_twB = nullptr;
+    int gpc = 1;                 // gates per CTA of the blind-rotate / external-product kernels
     std::vector<char> bsk_loaded, ksk_loaded;
     bool ready = false;
     DevBuf in[6], ext, oa, ob, accin, accout, elem, raw;
@@ -80,40 +81,48 @@ int check_params(const mktfhe_params* p) {
     if (p->N != mk::N) return fail(nullptr, MKTFHE_EINVAL, "unsupported N=%d (only 1024)", p->N);
     if (p->l < 1 || p->l > 4) return fail(nullptr, MKTFHE_EINVAL, "unsupported gsw_decomp_length l=%d (1..4)", p->l);
     if (p->bgbit < 1 || p->l * p->bgbit > 32) return fail(nullptr, MKTFHE_EINVAL, "unsupported l*bgbit=%d (<=32)", p->l * p->bgbit);
-    // exactness of the two-limb Goldilocks product: 2l * N * 2^(bgbit-1) * 2^32 < p/2
-    if ((double)(2 * p->l) * p->N * (double)(1u << (p->bgbit - 1)) >= (double)(1u << 30))
-        return fail(nullptr, MKTFHE_EINVAL, "2l*N*Bg/2 too large for the two-limb exact product");
+    if (p->bgbit > 8) return fail(nullptr, MKTFHE_EINVAL, "unsupported gsw_log2_base=%d (digits are packed in bytes: <= 8)", p->bgbit);
+    // exactness of the three-prime CRT: |sum| <= 2l * N * 2^(bgbit-1) * 2^63 must stay below M/4
+    if (std::log2((double)(2 * p->l) * p->N) + (p->bgbit - 1) + 63.0 >= rns::log2_crt_bound())
+        return fail(nullptr, MKTFHE_EINVAL, "2l*N*Bg/2*2^63 exceeds the CRT range of the three-prime exact product");
     if (p->k < 1 || p->n < 1 || (long long)p->n * p->k > 8192) return fail(nullptr, MKTFHE_EINVAL, "need 1 <= n*k <= 8192");
     if (p->n + 1 > mk::KS_THREADS * mk::KS_MAXCOLS) return fail(nullptr, MKTFHE_EINVAL, "n too large for the key-switch kernel");
     if (p->t < 1 || p->basebit < 1 || p->t * p->basebit > 31) return fail(nullptr, MKTFHE_EINVAL, "need t*basebit <= 31");
     return MKTFHE_OK;
 }
 
-size_t br_smem_bytes(const mktfhe_params& p) {
-    const int nt = 2 * p.l > mk::BR_WARPS ? 2 * p.l : mk::BR_WARPS;
-    size_t b = (size_t)2 * mk::N * 8 + (size_t)nt * ntt::TILE_ELEMS * 8 + (size_t)p.n * p.k * 2;
-    return (b + 15) & ~(size_t)15;
+int pick_gpc(int l) {
+    int g = mk::MAX_GPC;
+    while (g > 1 && (size_t)mk::TWB_WORDS * 4 + g * mk::gate_smem_bytes(l) > 227 * 1024) g--;
+    return g;
 }
-size_t ep_smem_bytes(const mktfhe_params& p) {
-    const int nt = 2 * p.l > mk::BR_WARPS ? 2 * p.l : mk::BR_WARPS;
-    return (size_t)2 * mk::N * 8 + (size_t)nt * ntt::TILE_ELEMS * 8;
-}
+size_t br_smem_bytes(const mktfhe_ctx* c) { return (size_t)mk::TWB_WORDS * 4 + c->gpc * mk::gate_smem_bytes(c->prm.l); }
 
-template <int L>
+// (L, GPC) instantiations: pick_gpc gives 5 gates per CTA for l <= 3 and 4 for l = 4
+#define MK_DISPATCH_L(c, KERNEL, ...)                                      \
+    switch ((c)->prm.l) {                                                  \
+    case 1: KERNEL(1, 5, __VA_ARGS__); break;                              \
+    case 2: KERNEL(2, 5, __VA_ARGS__); break;                              \
+    case 3: KERNEL(3, 5, __VA_ARGS__); break;                              \
+    default: KERNEL(4, 4, __VA_ARGS__); break;                             \
+    }
+
 int set_attrs(mktfhe_ctx* c) {
-    CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_smem_bytes(c->prm)));
-    CU_TRY(c, cudaFuncSetAttribute(mk::extprod_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ep_smem_bytes(c->prm)));
+    const int sm = (int)br_smem_bytes(c);
+#define SET_ATTR(L, GPC, dummy)                                                                                                    \
+    CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));             \
+    CU_TRY(c, cudaFuncSetAttribute(mk::extprod_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    MK_DISPATCH_L(c, SET_ATTR, 0)
+#undef SET_ATTR
     return MKTFHE_OK;
 }
 
 void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G) {
-    const size_t sm = br_smem_bytes(c->prm);
-    switch (c->prm.l) {
-    case 1: mk::blind_rotate_kernel<1><<<(unsigned)G, mk::BR_THREADS, sm, c->stream>>>(a); break;
-    case 2: mk::blind_rotate_kernel<2><<<(unsigned)G, mk::BR_THREADS, sm, c->stream>>>(a); break;
-    case 3: mk::blind_rotate_kernel<3><<<(unsigned)G, mk::BR_THREADS, sm, c->stream>>>(a); break;
-    default: mk::blind_rotate_kernel<4><<<(unsigned)G, mk::BR_THREADS, sm, c->stream>>>(a); break;
-    }
+    const size_t sm = br_smem_bytes(c);
+    const unsigned grid = (unsigned)((G + c->gpc - 1) / c->gpc);
+#define LAUNCH_BR(L, GPC, dummy) mk::blind_rotate_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, c->stream>>>(a)
+    MK_DISPATCH_L(c, LAUNCH_BR, 0)
+#undef LAUNCH_BR
     c->launches++;
 }
 
@@ -145,8 +154,8 @@ int run_bootstrap_dev(mktfhe_ctx* c, mk::GateLinear lin, int64_t mu, size_t G, c
         ext = (int32_t*)c->ext.p;
     }
     mk::BlindRotateArgs a{};
-    a.n = c->prm.n; a.k = c->prm.k; a.bgbit = c->prm.bgbit;
-    a.bsk = c->d_bsk; a.tw_fwd = c->d_tw_fwd; a.tw_inv = c->d_tw_inv;
+    a.G = (int)G; a.n = c->prm.n; a.k = c->prm.k; a.bgbit = c->prm.bgbit;
+    a.bsk = c->d_bsk; a.twB = c->d_twB;
     a.xa = xa; a.xb = xb; a.ya = ya; a.yb = yb; a.za = za; a.zb = zb;
     a.lin = lin; a.mu = mu; a.ext_out = ext; a.acc_out = acc_out;
     cudaEventRecord(c->ev[0], c->stream);
@@ -200,25 +209,19 @@ int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
     CREATE_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto& ev : c->ev) CREATE_TRY(cudaEventCreate(&ev));
     const int B1 = (1 << params->basebit) - 1;
-    c->bsk_bytes = (size_t)params->k * params->n * mk::bsk_elem_u64(params->l) * sizeof(u64);
+    c->bsk_bytes = (size_t)params->k * params->n * mk::bsk_elem_words(params->l) * sizeof(u32);
+    c->gpc = pick_gpc(params->l);
     c->ksk_bytes = (size_t)params->k * mk::N * params->t * B1 * (params->n + 1) * sizeof(int32_t);
     CREATE_TRY(cudaMalloc(&c->d_bsk, c->bsk_bytes));
     CREATE_TRY(cudaMalloc(&c->d_ksk, c->ksk_bytes));
-    CREATE_TRY(cudaMalloc(&c->d_tw_fwd, 1024 * sizeof(u64)));
-    CREATE_TRY(cudaMalloc(&c->d_tw_inv, 1024 * sizeof(u64)));
+    CREATE_TRY(cudaMalloc(&c->d_twB, (size_t)mk::TWB_WORDS * 4));
     {
-        ntt::Tables T;
-        if (T.psi == 0) { fail(nullptr, MKTFHE_EINVAL, "internal: no 2048th root with psi^32 = 8"); mktfhe_destroy(c); return MKTFHE_EINVAL; }
-        CREATE_TRY(cudaMemcpy(c->d_tw_fwd, T.tw_fwd.data(), 1024 * sizeof(u64), cudaMemcpyHostToDevice));
-        CREATE_TRY(cudaMemcpy(c->d_tw_inv, T.tw_inv.data(), 1024 * sizeof(u64), cudaMemcpyHostToDevice));
+        rns::HostTables T;
+        CREATE_TRY(cudaMemcpyToSymbol(mk::c_rns, &T.c, sizeof(rns::Consts)));
+        CREATE_TRY(cudaMemcpy(c->d_twB, T.twB.data(), (size_t)mk::TWB_WORDS * 4, cudaMemcpyHostToDevice));
     }
 #undef CREATE_TRY
-    switch (params->l) {
-    case 1: rc = set_attrs<1>(c); break;
-    case 2: rc = set_attrs<2>(c); break;
-    case 3: rc = set_attrs<3>(c); break;
-    default: rc = set_attrs<4>(c); break;
-    }
+    rc = set_attrs(c);
     if (rc) { g_create_error = c->err; mktfhe_destroy(c); return rc; }
     *out = c;
     return MKTFHE_OK;
@@ -232,8 +235,7 @@ void mktfhe_destroy(mktfhe_ctx* c) {
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->d_bsk) cudaFree(c->d_bsk);
     if (c->d_ksk) cudaFree(c->d_ksk);
-    if (c->d_tw_fwd) cudaFree(c->d_tw_fwd);
-    if (c->d_tw_inv) cudaFree(c->d_tw_inv);
+    if (c->d_twB) cudaFree(c->d_twB);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -250,9 +252,9 @@ int mktfhe_load_bsk(mktfhe_ctx* c, int party, const int64_t* polys) {
     int rc = reserve(c, c->raw, raw_bytes);
     if (rc) return rc;
     CU_TRY(c, cudaMemcpyAsync(c->raw.p, polys, raw_bytes, cudaMemcpyHostToDevice, c->stream));
-    const int ntasks = n * 4 * l * 2;
-    mk::bsk_transform_kernel<<<(ntasks + mk::BR_WARPS - 1) / mk::BR_WARPS, mk::BR_THREADS, 0, c->stream>>>(
-        (const int64_t*)c->raw.p, c->d_bsk, n, l, party, c->d_tw_fwd, ntasks);
+    const int ntasks = n * 4 * l * rns::NP;
+    mk::bsk_transform_kernel<<<(ntasks + mk::XF_WARPS - 1) / mk::XF_WARPS, mk::XF_WARPS * 32, 0, c->stream>>>(
+        (const int64_t*)c->raw.p, c->d_bsk, n, l, party, c->d_twB, ntasks);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     CU_TRY(c, cudaStreamSynchronize(c->stream));
@@ -423,17 +425,13 @@ int mktfhe_extprod_batch(mktfhe_ctx* c, size_t G, const int32_t* elem, const int
     const size_t accbytes = G * 2 * mk::N * 8;
     int rc;
     if ((rc = stage_in(c, c->elem, elem, G * 4)) || (rc = stage_in(c, c->accin, acc_in, accbytes)) || (rc = reserve(c, c->accout, accbytes))) return rc;
-    const size_t sm = ep_smem_bytes(c->prm);
-    const u64 *bsk = c->d_bsk, *tf = c->d_tw_fwd, *ti = c->d_tw_inv;
-    const int32_t* de = (const int32_t*)c->elem.p;
-    const int64_t* ai = (const int64_t*)c->accin.p;
-    int64_t* ao = (int64_t*)c->accout.p;
-    switch (c->prm.l) {
-    case 1: mk::extprod_kernel<1><<<(unsigned)G, mk::BR_THREADS, sm, c->stream>>>(bsk, tf, ti, c->prm.bgbit, de, ai, ao); break;
-    case 2: mk::extprod_kernel<2><<<(unsigned)G, mk::BR_THREADS, sm, c->stream>>>(bsk, tf, ti, c->prm.bgbit, de, ai, ao); break;
-    case 3: mk::extprod_kernel<3><<<(unsigned)G, mk::BR_THREADS, sm, c->stream>>>(bsk, tf, ti, c->prm.bgbit, de, ai, ao); break;
-    default: mk::extprod_kernel<4><<<(unsigned)G, mk::BR_THREADS, sm, c->stream>>>(bsk, tf, ti, c->prm.bgbit, de, ai, ao); break;
-    }
+    const size_t sm = br_smem_bytes(c);
+    const unsigned grid = (unsigned)((G + c->gpc - 1) / c->gpc);
+#define LAUNCH_EP(L, GPC, dummy)                                                                                          \
+    mk::extprod_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, c->stream>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, (const int32_t*)c->elem.p, \
+                                                                       (const int64_t*)c->accin.p, (int64_t*)c->accout.p)
+    MK_DISPATCH_L(c, LAUNCH_EP, 0)
+#undef LAUNCH_EP
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     CU_TRY(c, cudaMemcpyAsync(acc_out, c->accout.p, accbytes, cudaMemcpyDeviceToHost, c->stream));
@@ -449,8 +447,8 @@ int mktfhe_negacyclic_mul_batch(mktfhe_ctx* c, size_t G, const int64_t* a, const
     const size_t bytes = G * mk::N * 8;
     int rc;
     if ((rc = stage_in(c, c->accin, a, bytes)) || (rc = stage_in(c, c->raw, b, bytes)) || (rc = reserve(c, c->accout, bytes))) return rc;
-    mk::negacyclic_mul_kernel<<<(unsigned)G, 96, 0, c->stream>>>((const int64_t*)c->accin.p, (const int64_t*)c->raw.p, (int64_t*)c->accout.p,
-                                                                  c->d_tw_fwd, c->d_tw_inv);
+    mk::negacyclic_mul_kernel<<<(unsigned)G, mk::TPG, 0, c->stream>>>((const int64_t*)c->accin.p, (const int64_t*)c->raw.p, (int64_t*)c->accout.p,
+                                                                      c->d_twB);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     CU_TRY(c, cudaMemcpyAsync(out, c->accout.p, bytes, cudaMemcpyDeviceToHost, c->stream));

@@ -1,0 +1,137 @@
+// rns.cuh -- exact arithmetic of the external product: a residue number system of three 28-bit
+// NTT-friendly primes with lazy (Harvey) butterflies, one warp per (polynomial, prime).
+//
+// Why three 32-bit-word primes instead of one 64-bit prime (DESIGN.md §"Arithmetic"):
+// the first build of this repo used the Goldilocks prime 2^64-2^32+1 with two 32-bit key limbs.  It was
+// bit-exact but ncu showed it bound by the ALU pipe (64 % busy, fma pipe 10 %): every 64-bit modular
+// add/sub/shift is 6-12 IADD3/ISETP/SEL on a 32-bit datapath.  A 28-bit prime makes a whole butterfly
+// 1 IMAD.HI + 2 IMAD + 2 IADD3 + 1 VIADDMNMX (3 fma-pipe + 3 alu-pipe instructions), and the exact
+// integer result (|R| <= 2l*N*(Bg/2)*2^63 < 2^82) is recovered from the three residues by Garner's CRT
+// (M = p0*p1*p2 ~ 2^84), then reduced mod 2^64 -- exactly the Torus64 wrap the reference computes.
+//
+// All functions are __host__ __device__ so tests/host_emu runs the very same code on the CPU.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MK_HD __host__ __device__ __forceinline__
+#else
+#define MK_HD inline
+#endif
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+
+namespace rns {
+
+constexpr int NP = 3;                       // primes
+constexpr int LOGN = 10, N = 1 << LOGN;     // ring degree
+// the three largest primes p = 1 (mod 2N) below 2^28; 16p < 2^32 leaves room for lazy sums of 8 products
+constexpr u32 PRIME0 = 268369921u, PRIME1 = 268367873u, PRIME2 = 268361729u;
+
+struct alignas(8) uint2_ { u32 x, y; };                // (w, floor(w * 2^32 / p)) twiddle pair; same layout as CUDA's uint2
+
+MK_HD u32 mulhi32(u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (u32)(((u64)a * b) >> 32);
+#endif
+}
+MK_HD u32 umin32(u32 a, u32 b) { return a < b ? a : b; }
+
+// Shoup multiplication by a constant w (wp = floor(w 2^32 / p)): any y < 2^32 -> y*w mod p in [0, 2p)
+MK_HD u32 shoup_mul(u32 y, u32 w, u32 wp, u32 p) { return y * w - mulhi32(y, wp) * p; }
+
+// Harvey butterflies, values kept in [0, 4p).
+// forward (Cooley-Tukey): (X, Y) -> (X + wY, X - wY)
+MK_HD void ct_bfly(u32& X, u32& Y, u32 w, u32 wp, u32 p, u32 p2) {
+    const u32 x = umin32(X, X - p2);              // [0, 2p)     (VIADDMNMX.U32)
+    const u32 t = shoup_mul(Y, w, wp, p);         // [0, 2p)
+    X = x + t;
+    Y = x - t + p2;
+}
+// inverse (Gentleman-Sande): (X, Y) -> (X + Y, (X - Y) w); X out in [0, 4p), Y out in [0, 2p)
+MK_HD void gs_bfly(u32& X, u32& Y, u32 w, u32 wp, u32 p, u32 p4) {
+    const u32 s = X + Y, d = X - Y + p4;          // < 8p < 2^31
+    X = umin32(s, s - p4);
+    Y = shoup_mul(d, w, wp, p);
+}
+
+// Montgomery product d * k * 2^-32 mod p in [0, 2p): d < 2^32, k < p, pinv_neg = -p^-1 mod 2^32
+MK_HD u32 mont_mul(u32 d, u32 k, u32 p, u32 pinv_neg) {
+    const u64 prod = (u64)d * k;
+    const u32 m = (u32)prod * pinv_neg;
+    return (u32)((prod + (u64)m * p) >> 32);
+}
+
+// 32-point in-register networks.  x[j] are the 32 elements a thread owns; stage k (k = 0..4) pairs
+// elements at gap g = 16 >> k inside blocks of 2g; the twiddle of block b is entry e = 2^k - 1 + b of a
+// 31-entry table that `tw(e)` returns (uniform across the warp in the pass over the high index bits,
+// per-lane in the pass over the low index bits -- see ntt_rns.cuh).
+template <class TW>
+MK_HD void ct32(u32 (&x)[32], TW tw, u32 p) {
+    const u32 p2 = 2 * p;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const int g = 16 >> k;
+#pragma unroll
+        for (int b = 0; b < (1 << k); b++) {
+            const uint2_ w = tw((1 << k) - 1 + b);
+#pragma unroll
+            for (int j = 0; j < g; j++) ct_bfly(x[2 * g * b + j], x[2 * g * b + j + g], w.x, w.y, p, p2);
+        }
+    }
+}
+template <class TW>
+MK_HD void gs32(u32 (&x)[32], TW tw, u32 p) {
+    const u32 p4 = 4 * p;
+#pragma unroll
+    for (int k = 4; k >= 0; k--) {
+        const int g = 16 >> k;
+#pragma unroll
+        for (int b = 0; b < (1 << k); b++) {
+            const uint2_ w = tw((1 << k) - 1 + b);
+#pragma unroll
+            for (int j = 0; j < g; j++) gs_bfly(x[2 * g * b + j], x[2 * g * b + j + g], w.x, w.y, p, p4);
+        }
+    }
+}
+
+// ---- plain modular helpers (table generation, key transform; not on the hot path) ----
+MK_HD u32 mulmod(u32 a, u32 b, u32 p) { return (u32)(((u64)a * b) % p); }
+MK_HD u32 powmod(u32 a, u64 e, u32 p) {
+    u32 r = 1;
+    while (e) { if (e & 1) r = mulmod(r, a, p); a = mulmod(a, a, p); e >>= 1; }
+    return r;
+}
+MK_HD u32 shoup_of(u32 w, u32 p) { return (u32)(((u64)w << 32) / p); }
+// signed 64-bit integer -> residue in [0, p)
+MK_HD u32 residue_i64(int64_t v, u32 p) {
+    const int64_t r = v % (int64_t)p;
+    return (u32)(r < 0 ? r + (int64_t)p : r);
+}
+
+// Garner CRT constants
+struct Crt {
+    u32 p[3];
+    u32 c01, c01s, c02, c02s, c12, c12s;   // p0^-1 mod p1, p0^-1 mod p2, p1^-1 mod p2 with Shoup companions
+    u64 p01;                               // p0 * p1
+    u64 m_mod64;                           // p0 * p1 * p2 mod 2^64
+};
+// residues r_i in [0, 4 p_i) of an integer R with |R| < M/4 -> R mod 2^64 (two's complement)
+MK_HD u64 crt_lift(u32 r0, u32 r1, u32 r2, const Crt& c) {
+    const u32 p0 = c.p[0], p1 = c.p[1], p2 = c.p[2];
+    u32 v0 = umin32(r0, r0 - 2 * p0);
+    v0 = umin32(v0, v0 - p0);                                          // [0, p0)
+    u32 v1 = shoup_mul(r1 + 2 * p1 - v0, c.c01, c.c01s, p1);           // v0 < p0 < 2 p1
+    v1 = umin32(v1, v1 - p1);                                          // [0, p1)
+    const u32 u = shoup_mul(r2 + 2 * p2 - v0, c.c02, c.c02s, p2);      // [0, 2 p2)
+    u32 v2 = shoup_mul(u + 2 * p2 - v1, c.c12, c.c12s, p2);
+    v2 = umin32(v2, v2 - p2);                                          // [0, p2)
+    u64 R = (u64)v0 + (u64)p0 * v1 + c.p01 * v2;
+    if (v2 > p2 / 2) R -= c.m_mod64;                                   // negative representative
+    return R;
+}
+
+}  // namespace rns
