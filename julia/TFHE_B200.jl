@@ -1,0 +1,145 @@
+# TFHE_B200.jl -- `ccall` shim that puts libmktfhe_b200.so behind the reference's 3gen gate API.
+#
+# NOT EXECUTED IN THIS REPO'S CI: the build image has no Julia.  The executable twin of this file is
+# torus-fhe_b200/tfhe3gen.py (ctypes, same C ABI, same names), which the tests and benchmarks drive.
+#
+# Usage inside the reference tree (3-gen-mk-tfhe/): `include("src/TFHE.jl"); include("TFHE_B200.jl"); using .TFHE_B200`
+# after key generation replace
+#     bk_keys = [TransformedBootstrapKeyPart_3gen(bk_keys[i]) for i in 1:parties]      # multikey_3gen.jl:28
+# by
+#     bk_keys = [TFHE_B200.TransformedBootstrapKeyPart_3gen(bk_keys[i]) for i in 1:parties]
+# and call TFHE_B200.mk_gate_nand_3gen(bk_keys, ks_keys, x, y) etc.  Signatures are those of
+# 3-gen-mk-tfhe/src/3gen_mk_gates.jl:8-150 and src/3gen_mk_internals.jl:112-116; vector methods batch.
+module TFHE_B200
+
+using ..TFHE: TGswParams, RLweParams, BootstrapKeyPart_3gen, KeyswitchKey, MKLweSample, LweParams,
+              encode_message, encode_message64, mk_lwe_noiseless_trivial
+
+const LIB = get(ENV, "MKTFHE_B200_LIB", "libmktfhe_b200")
+
+struct CParams            # mktfhe_params (include/mktfhe_b200.h)
+    n::Int32; N::Int32; k::Int32; l::Int32; bgbit::Int32; t::Int32; basebit::Int32; reserved::Int32
+end
+
+const GATE_NAND, GATE_OR, GATE_AND, GATE_XOR, GATE_AND3 = Cint(0), Cint(1), Cint(2), Cint(3), Cint(4)
+
+check(ctx, rc) = rc == 0 ? nothing :
+    error("libmktfhe_b200 error $rc: " * unsafe_string(ccall((:mktfhe_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx)))
+
+"""Same name, constructor arity and fields as 3gen_mk_internals.jl:45-55, but it keeps the INTEGER polynomials
+(the reference keeps only Complex{Float64} FFTs, from which the exact key cannot be recovered)."""
+struct TransformedBootstrapKeyPart_3gen
+    tgsw_params :: TGswParams
+    rlwe_params :: RLweParams
+    gsw_key :: Array{Int64, 4}        # (N, l, 4, n) column-major == C int64 [n][4][l][N]
+    key_size :: Int
+    function TransformedBootstrapKeyPart_3gen(bk::BootstrapKeyPart_3gen)
+        n, l = bk.key_size, bk.tgsw_params.decomp_length
+        N = bk.rlwe_params.polynomial_degree
+        g = Array{Int64, 4}(undef, N, l, 4, n)
+        for j in 1:n, q in 1:l
+            s = bk.gsw_key[j]
+            g[:, q, 1, j] = s.part_1[q].coeffs
+            g[:, q, 2, j] = s.part_2[q].coeffs
+            g[:, q, 3, j] = s.part_3[q].coeffs
+            g[:, q, 4, j] = s.part_4[q].coeffs
+        end
+        new(bk.tgsw_params, bk.rlwe_params, g, n)
+    end
+end
+
+mutable struct Engine
+    ctx :: Ptr{Cvoid}
+    prm :: CParams
+end
+
+const ENGINES = IdDict{Any, Engine}()
+
+"""KeyswitchKey.key :: Array{LweSample,3} of dims (base-1, t, N) (keyswitch.jl:7-42) -> Int32 (n+1, base-1, t, N),
+i.e. C int32 [N][t][base-1][n+1]."""
+function flatten_ksk(ks::KeyswitchKey)
+    B1, t, N = size(ks.key)
+    n = ks.out_lwe_params.size
+    rows = Array{Int32, 4}(undef, n + 1, B1, t, N)
+    for i in 1:N, j in 1:t, h in 1:B1
+        rows[1:n, h, j, i] = ks.key[h, j, i].a
+        rows[n + 1, h, j, i] = ks.key[h, j, i].b
+    end
+    rows
+end
+
+function engine_for(bk::Array{TransformedBootstrapKeyPart_3gen, 1}, ks::Array{KeyswitchKey, 1}; device::Integer = 0)
+    haskey(ENGINES, bk) && return ENGINES[bk]
+    bk[1].rlwe_params.is32 && error("rlwe_is32 = true is not part of the 3gen path")
+    prm = CParams(bk[1].key_size, bk[1].rlwe_params.polynomial_degree, length(bk), bk[1].tgsw_params.decomp_length,
+                  bk[1].tgsw_params.log2_base, ks[1].params.decomp_length, ks[1].params.log2_base, 0)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:mktfhe_create, LIB), Cint, (Ref{CParams}, Cint, Ref{Ptr{Cvoid}}), prm, device, out)
+    rc == 0 || error("mktfhe_create: " * unsafe_string(ccall((:mktfhe_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    ctx = out[]
+    for p in 1:length(bk)
+        check(ctx, ccall((:mktfhe_load_bsk, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}), ctx, p - 1, bk[p].gsw_key))
+        check(ctx, ccall((:mktfhe_load_ksk, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int32}), ctx, p - 1, flatten_ksk(ks[p])))
+    end
+    check(ctx, ccall((:mktfhe_finalize_keys, LIB), Cint, (Ptr{Cvoid},), ctx))
+    e = Engine(ctx, prm)
+    finalizer(x -> ccall((:mktfhe_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.ctx), e)
+    ENGINES[bk] = e
+end
+
+# MKLweSample.a is (n, parties) column-major == C int32 [k][n]; a batch is the samples back to back
+pack_a(xs::Vector{MKLweSample}) = reduce(hcat, [vec(x.a) for x in xs])     # (k*n, G)
+pack_b(xs::Vector{MKLweSample}) = Int32[x.b for x in xs]
+
+function unpack(params::LweParams, n, k, oa::Matrix{Int32}, ob::Vector{Int32})
+    [MKLweSample(params, reshape(oa[:, g], n, k), ob[g], 0.0) for g in 1:length(ob)]   # variance 0.0: mk_internals.jl:738-743
+end
+
+"""mk_bootstrap_3gen(bk, ks, mu, x) (3gen_mk_internals.jl:112-116); `x` may be a vector (one launch for the batch)."""
+function mk_bootstrap_3gen(bk::Array{TransformedBootstrapKeyPart_3gen, 1}, ks::Array{KeyswitchKey, 1},
+                           mu::Union{Int32, Int64}, xs::Vector{MKLweSample})
+    e = engine_for(bk, ks); n, k, G = Int(e.prm.n), Int(e.prm.k), length(xs)
+    a, b = pack_a(xs), pack_b(xs)
+    oa, ob = Matrix{Int32}(undef, n * k, G), Vector{Int32}(undef, G)
+    check(e.ctx, ccall((:mktfhe_bootstrap_batch, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Csize_t, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}), e.ctx, Int64(mu), G, a, b, oa, ob))
+    unpack(xs[1].params, n, k, oa, ob)
+end
+mk_bootstrap_3gen(bk::Array{TransformedBootstrapKeyPart_3gen, 1}, ks, mu, x::MKLweSample) = mk_bootstrap_3gen(bk, ks, mu, [x])[1]
+
+function gate_batch(bk, ks, gate::Cint, xs::Vector{MKLweSample}, ys::Vector{MKLweSample}, zs::Union{Nothing, Vector{MKLweSample}} = nothing)
+    e = engine_for(bk, ks); n, k, G = Int(e.prm.n), Int(e.prm.k), length(xs)
+    length(ys) == G || error("gate operands have different batch sizes")
+    xa, xb, ya, yb = pack_a(xs), pack_b(xs), pack_a(ys), pack_b(ys)
+    za = zs === nothing ? Ptr{Int32}(C_NULL) : pack_a(zs)
+    zb = zs === nothing ? Ptr{Int32}(C_NULL) : pack_b(zs)
+    oa, ob = Matrix{Int32}(undef, n * k, G), Vector{Int32}(undef, G)
+    check(e.ctx, ccall((:mktfhe_gate_batch, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Csize_t, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
+        e.ctx, gate, G, xa, xb, ya, yb, za, zb, oa, ob))
+    unpack(xs[1].params, n, k, oa, ob)
+end
+
+const BK = Array{TransformedBootstrapKeyPart_3gen, 1}
+const KS = Array{KeyswitchKey, 1}
+const V = Vector{MKLweSample}
+
+# scalar and batched gates, 3gen_mk_gates.jl:8-150
+for (fname, gid) in ((:mk_gate_nand_3gen, GATE_NAND), (:mk_gate_or_3gen, GATE_OR), (:mk_gate_and_3gen, GATE_AND), (:mk_gate_xor_3gen, GATE_XOR))
+    @eval $fname(bk::BK, ks::KS, x::V, y::V) = gate_batch(bk, ks, $gid, x, y)
+    @eval $fname(bk::BK, ks::KS, x::MKLweSample, y::MKLweSample) = gate_batch(bk, ks, $gid, [x], [y])[1]
+end
+mk_gate_3and_3gen(bk::BK, ks::KS, x::V, y::V, z::V) = gate_batch(bk, ks, GATE_AND3, x, y, z)
+mk_gate_3and_3gen(bk::BK, ks::KS, x::MKLweSample, y::MKLweSample, z::MKLweSample) = gate_batch(bk, ks, GATE_AND3, [x], [y], [z])[1]
+mk_gate_not_3gen(x::MKLweSample) = -x
+
+"""3gen_mk_gates.jl:133-150: the two ANDs in one launch, then 1/8 + t1 + t2 NOT bootstrapped (as the reference)."""
+function mk_gate_mux_3gen(bk::BK, ks::KS, x::MKLweSample, y::MKLweSample, z::MKLweSample)
+    t = gate_batch(bk, ks, GATE_AND, [x, -x], [y, z])
+    mk_lwe_noiseless_trivial(encode_message(1, 8), t[1].params, length(bk)) + t[1] + t[2]
+end
+
+export TransformedBootstrapKeyPart_3gen, mk_bootstrap_3gen, mk_gate_nand_3gen, mk_gate_or_3gen, mk_gate_and_3gen,
+       mk_gate_xor_3gen, mk_gate_3and_3gen, mk_gate_not_3gen, mk_gate_mux_3gen
+
+end # module
