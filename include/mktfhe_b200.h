@@ -49,8 +49,9 @@ extern "C" {
 
 /* Integer part of SchemeParameters_3gen (api.jl:50-67); rlwe_mask_size = 1 and
  * rlwe_is32 = false as in every 3gen set (mk_api.jl:32-322).  Supported:
- * N = 1024, 1 <= l <= 4, l*bgbit <= 32 and 2l*N*2^(bgbit-1) < 2^30 (so the
- * two-limb Goldilocks product is exact), n*k <= 8192, t*basebit <= 31. */
+ * N = 1024, 1 <= l <= 4, bgbit <= 8, 2l*N*2^(bgbit-1)*2^63 < M/4 with M ~ 2^84 the
+ * product of the three NTT primes (so the CRT result is exact), n*k <= 8192,
+ * t*basebit <= 31. */
 typedef struct {
     int32_t n;        /* lwe_size */
     int32_t N;        /* rlwe_polynomial_degree */
@@ -74,8 +75,8 @@ const char *mktfhe_last_error(const mktfhe_ctx *ctx);
 /* Replaces TransformedBootstrapKeyPart_3gen(bk::BootstrapKeyPart_3gen)
  * (3gen_mk_internals.jl:45-55): takes party `party`'s INTEGER key
  * bk.gsw_key[j].part_{1..4}[q].coeffs as int64 [n][4][l][N] (host), splits every
- * polynomial in two 32-bit limbs, NTT-transforms them on the GPU and stores them
- * in the streaming layout of the blind-rotate kernel. */
+ * polynomial modulo the three 28-bit NTT primes, transforms the residues on the
+ * GPU and stores them in the streaming layout of the blind-rotate kernel. */
 int mktfhe_load_bsk(mktfhe_ctx *ctx, int party, const int64_t *polys);
 /* KeyswitchKey.key::Array{LweSample,3} of dims (base-1, t, N) (keyswitch.jl:7-42),
  * flattened as int32 [N][t][base-1][n+1] (a[0..n-1] then b), host. */
@@ -108,6 +109,17 @@ int mktfhe_gate_batch_dev(mktfhe_ctx *ctx, int gate, size_t G, const int32_t *xa
                           const int32_t *ya, const int32_t *yb, const int32_t *za, const int32_t *zb,
                           int32_t *oa, int32_t *ob, void *stream);
 
+/* One launch for a batch whose gates differ: gate_ids[g] in MKTFHE_GATE_* selects the prologue of gate g (a dependency
+ * level of a circuit such as mk_add_3gen, 3gen_mk_gates.jl:183-220, mixes XOR/AND/OR gates).  za/zb may be NULL when
+ * no gate is MKTFHE_GATE_AND3.  The _dev variant takes device pointers (gate_ids included) and does not validate ids:
+ * an id outside 0..4 bootstraps the zero sample. */
+int mktfhe_gate_batch_mixed(mktfhe_ctx *ctx, size_t G, const int32_t *gate_ids, const int32_t *xa, const int32_t *xb,
+                            const int32_t *ya, const int32_t *yb, const int32_t *za, const int32_t *zb,
+                            int32_t *oa, int32_t *ob);
+int mktfhe_gate_batch_mixed_dev(mktfhe_ctx *ctx, size_t G, const int32_t *gate_ids, const int32_t *xa, const int32_t *xb,
+                                const int32_t *ya, const int32_t *yb, const int32_t *za, const int32_t *zb,
+                                int32_t *oa, int32_t *ob, void *stream);
+
 /* -- parity hooks (host pointers; one call per stage of the path) ---------- */
 /* tgsw_extern_mul_3gen(accum, bk[party].gsw_key[j]) (tgsw_3gen.jl:102-113) for
  * G accumulators: acc = int64 [G][2][N] with [0] = mask (accum.a[1]) and
@@ -120,8 +132,9 @@ int mktfhe_blind_rotate_batch(mktfhe_ctx *ctx, int64_t mu, size_t G, const int32
                               int32_t *ext_out, int64_t *acc_out);
 /* mk_keyswitch_3gen (mk_internals.jl:730-744) on ext = int32 [G][N+1] */
 int mktfhe_keyswitch_batch(mktfhe_ctx *ctx, size_t G, const int32_t *ext, int32_t *a_out, int32_t *b_out);
-/* exact negacyclic products c = a * b mod (X^N+1, 2^64) through the same NTT:
- * a = int64 [G][N] with |a_i| < 2^15 ("digit" operand), b = int64 [G][N]. */
+/* exact negacyclic products c = a * b mod (X^N+1, 2^64) through the same three-prime NTT + CRT:
+ * a = int64 [G][N] with |a_i| <= 2^8 ("digit" / ternary operand: N * 2^8 * 2^63 stays inside the CRT range),
+ * b = int64 [G][N].  Also the primitive of key generation (tgsw_3gen.jl:85-88 uses DarkIntegers' exact `*`). */
 int mktfhe_negacyclic_mul_batch(mktfhe_ctx *ctx, size_t G, const int64_t *a, const int64_t *b, int64_t *c);
 
 /* -- introspection ---------------------------------------------------------- */
@@ -130,7 +143,7 @@ uint64_t mktfhe_launch_count(const mktfhe_ctx *ctx);
 /* device time (ms, CUDA events on the launching stream) of the blind-rotate and
  * key-switch kernels of the most recent batch call; blocks until they finished */
 int mktfhe_last_kernel_ms(mktfhe_ctx *ctx, float *blind_rotate_ms, float *keyswitch_ms);
-/* bytes of the streamed bootstrapping key read per gate (2 limbs) and of ksk rows per gate */
+/* bytes of the streamed bootstrapping key read per gate (three u32 residues per coefficient) and of ksk rows gathered per gate */
 int mktfhe_algorithmic_bytes(const mktfhe_ctx *ctx, double *bsk_bytes_per_gate, double *ksk_bytes_per_gate);
 
 #ifdef __cplusplus

@@ -1,0 +1,151 @@
+"""CPU tests of the host-side mirror of the reference API (torus-fhe_b200/tfhe3gen.py, circuits.py, engine.py):
+everything that does not launch a kernel."""
+import numpy as np
+import pytest
+
+import torus_fhe_b200 as T
+from torus_fhe_b200 import circuits
+
+
+def test_parameter_sets_match_reference():
+    # 3-gen-mk-tfhe/src/mk_api.jl:32-38, 84-90, 140-146
+    p = T.mktfhe_parameters_2party_3gen
+    assert (p.lwe_size, p.rlwe_polynomial_degree, p.gsw_decomp_length, p.gsw_log2_base, p.ks_decomp_length, p.ks_log2_base, p.max_parties) == (520, 1024, 2, 7, 3, 3, 2)
+    assert not p.rlwe_is32 and p.rlwe_mask_size == 1 and abs(p.lwe_noise_stddev - 2 ** -13.52) < 1e-15
+    p = T.mktfhe_parameters_4party_3gen
+    assert (p.lwe_size, p.gsw_decomp_length, p.gsw_log2_base, p.ks_decomp_length, p.ks_log2_base, p.max_parties) == (510, 3, 6, 5, 2, 4)
+    p = T.mktfhe_parameters_8party_3gen
+    assert (p.lwe_size, p.gsw_decomp_length, p.gsw_log2_base, p.ks_decomp_length, p.ks_log2_base, p.max_parties) == (540, 4, 4, 5, 2, 8)
+    assert T.tgsw_parameters(T.mktfhe_parameters_2party_3gen).gadget_values == [1 << 57, 1 << 50]   # tgsw.jl:26
+
+
+def test_encode_decode_agree_with_oracle(oracle):
+    L = oracle.lib()
+    for mu, space in [(1, 8), (-1, 8), (1, 4), (-1, 4), (3, 8)]:
+        assert int(T.encode_message(mu, space)) == L.mko_encode_message32(mu, space)
+        assert int(T.encode_message64(mu, space)) == L.mko_encode_message64(mu, space)
+    xs = np.array([0, 1, -1, 2 ** 31 - 1, -2 ** 31, (1 << 20) - 1, 1 << 20, -(1 << 20) - 1, 123456789], np.int32)
+    got = T.decode_message(xs, 2048)
+    assert [int(v) for v in got] == [L.mko_decode_message32(int(v), 2048) for v in xs]
+    assert int(T.decode_message(np.int32(-5), 2048)) == L.mko_decode_message32(-5, 2048)
+
+
+def test_mklwesample_linear_ops_wrap(rng):
+    p = T.LweParams(8)
+    x = T.MKLweSample(p, rng.integers(-2 ** 31, 2 ** 31, (2, 8)), np.int32(2 ** 31 - 5), 1.0)
+    y = T.MKLweSample(p, rng.integers(-2 ** 31, 2 ** 31, (2, 8)), np.int32(100), 2.0)
+    s = x + y
+    assert int(s.b) == ((2 ** 31 - 5 + 100 + 2 ** 31) % 2 ** 32) - 2 ** 31 and s.current_variance == 3.0
+    d = x - y
+    assert np.array_equal(d.a, (x.a.astype(np.int64) - y.a).astype(np.int32))
+    n = -x
+    assert np.array_equal((n + x).a, np.zeros((2, 8), np.int32)) and int((n + x).b) == 0
+    t = np.int32(2) * x                                   # Torus32 * sample, mk_internals.jl:50-51
+    assert np.array_equal(t.a, (2 * x.a.astype(np.int64)).astype(np.int32)) and t.current_variance == 4.0
+    tr = T.mk_lwe_noiseless_trivial(T.encode_message(1, 8), p, 2)
+    assert tr.a.shape == (2, 8) and not tr.a.any() and int(tr.b) == 1 << 29
+    st = T.MKLweSample.stack([x, y])
+    assert st.b.shape == (2,) and np.array_equal(st[1].a, y.a)
+
+
+def test_encrypt_decrypt_roundtrip_and_ints(rng):
+    params = T.mktfhe_parameters_2party_3gen
+    sk = [T.SecretKey_3gen(rng, params) for _ in range(2)]
+    assert sk[0].key.key.shape == (520,) and set(np.unique(sk[0].key.key)) <= {0, 1}
+    bits = rng.integers(0, 2, 200).astype(bool)
+    ct = T.mk_encrypt_3gen(rng, sk, bits)
+    assert ct.a.shape == (200, 2, 520) and ct.b.shape == (200,)
+    assert np.array_equal(T.mk_decrypt_3gen(sk, ct), bits)
+    ph = T.mk_lwe_phase(ct, [s.key for s in sk]).astype(np.float64) / 2 ** 32
+    assert np.abs(np.abs(ph) - 0.125).max() < 0.001      # sigma_lwe = 2^-13.52
+    one = T.mk_encrypt_3gen(rng, sk, True)
+    assert one.b.shape == () and T.mk_decrypt_3gen(sk, one) is True
+    # LSB-first two's complement, mk_api.jl:576-589, 612-633
+    for v in (0, 1, 5, 127, -1, -128, -77):
+        assert T.mk_int_decrypt_3gen(sk, T.mk_int_encrypt_3gen(rng, sk, v, 8), 8) == v
+    vals = np.array([3, -4, 100, -100])
+    assert np.array_equal(T.mk_int_decrypt_3gen(sk, T.mk_int_encrypt_3gen(rng, sk, vals, 8), 8), vals)
+
+
+def test_keyswitch_key_generation_is_consistent(rng):
+    """KeyswitchKey (keyswitch.jl:14-41) from the host mirror: every row decrypts under the output key to
+    (z_i * h) << (32 - j * log2_base) up to the key-switch noise."""
+    params = T.mktfhe_parameters_2party_3gen
+    sk = T.SecretKey_3gen(rng, params)
+    rk = T.RLweKey(rng, T.RLweParams(64, 1, False), True)
+    assert set(np.unique(rk.key)) <= {-1, 0, 1}
+    ks = T.KeyswitchKey(rng, params.ks_noise_stddev, T.keyswitch_parameters(params), sk.key, rk)
+    assert ks.key.shape == (64, 3, 7, 521)
+    a, b = ks.key[..., :520].astype(np.int64), ks.key[..., 520].astype(np.int64)
+    phase = (b - (a * sk.key.key.astype(np.int64)).sum(-1)).astype(np.int32)
+    h = np.arange(1, 8)[None, None, :]
+    sh = (32 - np.arange(1, 4) * 3)[None, :, None]
+    msg = ((rk.key[:, None, None] * h) << sh).astype(np.int32)
+    err = (phase.astype(np.int64) - msg + 2 ** 31) % 2 ** 32 - 2 ** 31
+    assert np.abs(err).max() < 2 ** 32 * params.ks_noise_stddev * 6
+    assert abs(err.mean()) < 2 ** 32 * params.ks_noise_stddev * 0.2      # recentred noise, keyswitch.jl:28-29
+
+
+def test_shard_bounds_cover_batch_exactly():
+    for G in (0, 1, 7, 16384, 16385):
+        for ws in (1, 2, 3, 8):
+            spans = [T.shard_bounds(G, ws, r) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == G
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(ws - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+class _Bit:
+    """Plaintext stand-in for MKLweSample (batch of booleans in .b) to check circuit wiring without a GPU."""
+    params = None
+    current_variance = 0.0
+
+    def __init__(self, b):
+        self.b = np.asarray(b, dtype=bool)
+        self.a = np.zeros(self.b.shape + (1, 1), np.int32)
+
+
+def _plain_level(bk, ks, jobs):
+    f = {"nand": lambda x, y: ~(x & y), "or": lambda x, y: x | y, "and": lambda x, y: x & y, "xor": lambda x, y: x ^ y}
+    return [_Bit(f[k](*np.broadcast_arrays(x.b, y.b))) for k, x, y in jobs]
+
+
+def _bits(v, W):
+    return [_Bit(((np.asarray(v) >> i) & 1).astype(bool)) for i in range(W)]
+
+
+def _val(bits, W, signed=True):
+    v = sum(b.b.astype(np.int64) << i for i, b in enumerate(bits[:W]))
+    return np.where(v >= 1 << (W - 1), v - (1 << W), v) if signed else v
+
+
+def test_circuit_wiring_against_plain_integers(monkeypatch):
+    monkeypatch.setattr(circuits, "gate_level", _plain_level)
+    monkeypatch.setattr(circuits, "mk_copy_3gen", lambda x: _Bit(x.b.copy()))
+    W = 8
+    r = np.random.default_rng(5)
+    x, y = r.integers(-60, 60, 64), r.integers(-60, 60, 64)
+    one, zero = _Bit(np.ones(64, bool)), _Bit(np.zeros(64, bool))
+    assert np.array_equal(_val(circuits.mk_add_3gen(None, None, _bits(x, W), _bits(y, W), zero, W), W), x + y)
+    assert np.array_equal(_val(circuits.mk_sub_3gen(None, None, _bits(x, W), _bits(y, W), one, W), W), x - y)
+    assert np.array_equal(circuits.mk_less_3gen(None, None, _bits(x, W), _bits(y, W), one, W).b, x < y)
+    assert np.array_equal(circuits.mk_grt_3gen(None, None, _bits(x, W), _bits(y, W), one, W).b, x > y)
+    assert np.array_equal(circuits.mk_leq_3gen(None, None, _bits(x, W), _bits(y, W), one, W).b, x <= y)
+    assert np.array_equal(circuits.mk_geq_3gen(None, None, _bits(x, W), _bits(y, W), one, W).b, x >= y)
+    assert np.array_equal(_val(circuits.mk_inv_3gen(None, None, _bits(x, W), one, W), W), ~x)
+    c = circuits.mk_int_add_with_carry_3gen(None, None, _bits(x & 255, W), _bits(y & 255, W), zero, W)
+    assert len(c) == W + 1 and np.array_equal(_val(c, W + 1, signed=False), (x & 255) + (y & 255))
+    # mk_int_mul_3gen: literal transcription of the reference loop (1-based, 3gen_mk_gates.jl:312-362) on plain bits
+    a, b = r.integers(0, 16, 64), r.integers(0, 16, 64)
+    Wm = 4
+    got = _val(circuits.mk_int_mul_3gen(None, None, _bits(a, Wm), _bits(b, Wm), zero, Wm), Wm, signed=False)
+    row = lambda i: ((b >> (i - 1)) & 1) * a                      # BArr[i, :] as an integer, 1-based i
+    tmp, ctr, low = row(1) >> 1, 1, row(1) & 1                    # result[1]; tmpIn = row 1 shifted, top bit ZERO
+    for i in range(2, Wm):
+        s = tmp + row(i)
+        low |= (s & 1) << (i - 1)
+        tmp, ctr = s >> 1, i
+    s = tmp + row(ctr)                                            # the reference adds row `ctr` again, not row WIDTH
+    expect = (low | (s << ctr)) & ((1 << Wm) - 1)
+    assert np.array_equal(got, expect)

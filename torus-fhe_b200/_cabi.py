@@ -20,6 +20,7 @@ EXPORTS = (
     "mktfhe_create", "mktfhe_destroy", "mktfhe_last_error",
     "mktfhe_load_bsk", "mktfhe_load_ksk", "mktfhe_finalize_keys", "mktfhe_key_buffers", "mktfhe_mark_keys_received",
     "mktfhe_bootstrap_batch", "mktfhe_gate_batch", "mktfhe_bootstrap_batch_dev", "mktfhe_gate_batch_dev",
+    "mktfhe_gate_batch_mixed", "mktfhe_gate_batch_mixed_dev",
     "mktfhe_extprod_batch", "mktfhe_blind_rotate_batch", "mktfhe_keyswitch_batch", "mktfhe_negacyclic_mul_batch",
     "mktfhe_launch_count", "mktfhe_last_kernel_ms", "mktfhe_algorithmic_bytes",
 )
@@ -73,6 +74,8 @@ def lib():
         "mktfhe_gate_batch": (C.c_int, [vp, C.c_int, sz, vp, vp, vp, vp, vp, vp, vp, vp]),
         "mktfhe_bootstrap_batch_dev": (C.c_int, [vp, i64, sz, vp, vp, vp, vp, vp]),
         "mktfhe_gate_batch_dev": (C.c_int, [vp, C.c_int, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "mktfhe_gate_batch_mixed": (C.c_int, [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "mktfhe_gate_batch_mixed_dev": (C.c_int, [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "mktfhe_extprod_batch": (C.c_int, [vp, sz, vp, vp, vp]),
         "mktfhe_blind_rotate_batch": (C.c_int, [vp, i64, sz, vp, vp, vp, vp]),
         "mktfhe_keyswitch_batch": (C.c_int, [vp, sz, vp, vp, vp]),
@@ -182,6 +185,21 @@ class Context:
         else:
             oa, ob = out
         self._chk(lib().mktfhe_gate_batch(self.h, gate, G, _p(xa), _p(xb), _p(ya), _p(yb), _p(za), _p(zb), _p(oa), _p(ob)))
+        return oa, ob
+
+    def gate_batch_mixed(self, gate_ids, x, y, z=None):
+        """One launch for gates of different kinds: gate_ids[g] selects the prologue of gate g."""
+        gate_ids = _c(gate_ids, np.int32).reshape(-1)
+        xa, xb = self._ab(*x)
+        ya, yb = self._ab(*y)
+        G = xb.size
+        if yb.size != G or gate_ids.size != G:
+            raise ValueError("gate operands / ids have different batch sizes")
+        za = zb = None
+        if z is not None:
+            za, zb = self._ab(*z)
+        oa, ob = np.empty((G, self.k, self.n), np.int32), np.empty(G, np.int32)
+        self._chk(lib().mktfhe_gate_batch_mixed(self.h, G, _p(gate_ids), _p(xa), _p(xb), _p(ya), _p(yb), _p(za), _p(zb), _p(oa), _p(ob)))
         return oa, ob
 
     # -- hot path, device pointers (ints), asynchronous on `stream` (0 = context stream)

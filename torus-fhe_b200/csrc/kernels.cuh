@@ -47,10 +47,23 @@ struct BlindRotateArgs {
     const uint2_* twB;
     const int32_t *xa, *xb, *ya, *yb, *za, *zb;
     GateLinear lin;
+    const int32_t* gate_ids;   // [G] per-gate ids (mixed batches) or nullptr: every gate uses `lin`
     int64_t mu;
     int32_t* ext_out;   // [G][N+1]
     int64_t* acc_out;   // [G][2][N] or nullptr
 };
+
+// linear prologue constants of the five bootstrapped gates, 3gen_mk_gates.jl:8-74 (encode_message(m, S) = m << (32 - log2 S))
+__host__ __device__ inline GateLinear gate_linear(int gate) {
+    switch (gate) {
+    case 0: return {(int32_t)(1u << 29), -1, -1, 0};            // NAND   +1/8 - x - y
+    case 1: return {(int32_t)(1u << 29), 1, 1, 0};              // OR     +1/8 + x + y
+    case 2: return {(int32_t)(0u - (1u << 29)), 1, 1, 0};       // AND    -1/8 + x + y
+    case 3: return {(int32_t)(1u << 30), 2, 2, 0};              // XOR    +1/4 + 2x + 2y
+    case 4: return {(int32_t)(0u - (1u << 30)), 1, 1, 1};       // 3AND   -1/4 + x + y + z
+    default: return {0, 0, 0, 0};
+    }
+}
 
 __device__ __forceinline__ void gate_barrier(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(TPG) : "memory"); }
 
@@ -216,13 +229,14 @@ __global__ void __launch_bounds__(GPC* TPG, 1) blind_rotate_kernel(BlindRotateAr
     const int kn = p.k * p.n;
     // gate prologue (3gen_mk_gates.jl) + mod switch (3gen_mk_internals.jl:102-103); every thread of the gate computes
     // the same rotation amounts from broadcast loads
+    const GateLinear lin = p.gate_ids ? gate_linear(__ldg(p.gate_ids + g)) : p.lin;
     auto rotation = [&](const int32_t* xs, const int32_t* ys, const int32_t* zs, size_t idx, uint32_t mu0) {
-        uint32_t t = mu0 + (uint32_t)p.lin.cx * (uint32_t)__ldg(xs + idx);
-        if (p.lin.cy) t += (uint32_t)p.lin.cy * (uint32_t)__ldg(ys + idx);
-        if (p.lin.cz) t += (uint32_t)p.lin.cz * (uint32_t)__ldg(zs + idx);
+        uint32_t t = mu0 + (uint32_t)lin.cx * (uint32_t)__ldg(xs + idx);
+        if (lin.cy) t += (uint32_t)lin.cy * (uint32_t)__ldg(ys + idx);
+        if (lin.cz) t += (uint32_t)lin.cz * (uint32_t)__ldg(zs + idx);
         return mod_switch_2N((int32_t)t);
     };
-    const int barb = rotation(p.xb, p.yb, p.zb, g, (uint32_t)p.lin.mu0);
+    const int barb = rotation(p.xb, p.yb, p.zb, g, (uint32_t)lin.mu0);
     // acc = (0, X^{-barb} * testvect), testvect = mu * (1 + X + ... + X^{N-1})  (:88-92, rlwe.jl:113-119)
     {
         const int s = (-barb) & (2 * N - 1);

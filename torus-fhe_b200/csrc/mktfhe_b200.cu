@@ -42,7 +42,7 @@ struct mktfhe_ctx {
     int gpc = 1;                 // gates per CTA of the blind-rotate / external-product kernels
     std::vector<char> bsk_loaded, ksk_loaded;
     bool ready = false;
-    DevBuf in[6], ext, oa, ob, accin, accout, elem, raw;
+    DevBuf in[6], ext, oa, ob, accin, accout, elem, raw, gids;
     uint64_t launches = 0;
     std::string err;
 };
@@ -127,21 +127,14 @@ void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G) 
 }
 
 mk::GateLinear gate_linear(int gate, bool* ok) {
-    *ok = true;
-    switch (gate) {   // 3gen_mk_gates.jl:8-74; encode_message(m, S) = m << (32 - log2 S)
-    case MKTFHE_GATE_NAND: return {(int32_t)(1u << 29), -1, -1, 0};
-    case MKTFHE_GATE_OR: return {(int32_t)(1u << 29), 1, 1, 0};
-    case MKTFHE_GATE_AND: return {(int32_t)(0u - (1u << 29)), 1, 1, 0};
-    case MKTFHE_GATE_XOR: return {(int32_t)(1u << 30), 2, 2, 0};
-    case MKTFHE_GATE_AND3: return {(int32_t)(0u - (1u << 30)), 1, 1, 1};
-    default: *ok = false; return {0, 0, 0, 0};
-    }
+    *ok = gate >= MKTFHE_GATE_NAND && gate <= MKTFHE_GATE_AND3;
+    return mk::gate_linear(gate);
 }
 
 // device-pointer core shared by every bootstrap-like entry point
 int run_bootstrap_dev(mktfhe_ctx* c, mk::GateLinear lin, int64_t mu, size_t G, const int32_t* xa, const int32_t* xb,
                       const int32_t* ya, const int32_t* yb, const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob,
-                      int32_t* ext_out, int64_t* acc_out, bool do_keyswitch, cudaStream_t st) {
+                      int32_t* ext_out, int64_t* acc_out, bool do_keyswitch, cudaStream_t st, const int32_t* gate_ids = nullptr) {
     if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
     if (G == 0) return MKTFHE_OK;
     if (G > 0x7fffffffu) return fail(c, MKTFHE_EINVAL, "batch too large");
@@ -157,7 +150,7 @@ int run_bootstrap_dev(mktfhe_ctx* c, mk::GateLinear lin, int64_t mu, size_t G, c
     a.G = (int)G; a.n = c->prm.n; a.k = c->prm.k; a.bgbit = c->prm.bgbit;
     a.bsk = c->d_bsk; a.twB = c->d_twB;
     a.xa = xa; a.xb = xb; a.ya = ya; a.yb = yb; a.za = za; a.zb = zb;
-    a.lin = lin; a.mu = mu; a.ext_out = ext; a.acc_out = acc_out;
+    a.lin = lin; a.gate_ids = gate_ids; a.mu = mu; a.ext_out = ext; a.acc_out = acc_out;
     cudaEventRecord(c->ev[0], c->stream);
     launch_blind_rotate(c, a, G);
     cudaEventRecord(c->ev[1], c->stream);
@@ -231,7 +224,7 @@ void mktfhe_destroy(mktfhe_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = {&c->in[0], &c->in[1], &c->in[2], &c->in[3], &c->in[4], &c->in[5], &c->ext, &c->oa, &c->ob, &c->accin, &c->accout, &c->elem, &c->raw};
+    DevBuf* bufs[] = {&c->in[0], &c->in[1], &c->in[2], &c->in[3], &c->in[4], &c->in[5], &c->ext, &c->oa, &c->ob, &c->accin, &c->accout, &c->elem, &c->raw, &c->gids};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->d_bsk) cudaFree(c->d_bsk);
     if (c->d_ksk) cudaFree(c->d_ksk);
@@ -348,6 +341,46 @@ int mktfhe_gate_batch(mktfhe_ctx* c, int gate, size_t G, const int32_t* xa, cons
     if ((rc = reserve(c, c->oa, abytes)) || (rc = reserve(c, c->ob, bbytes))) return rc;
     rc = run_bootstrap_dev(c, lin, (int64_t)1 << 61, G, (int32_t*)c->in[0].p, (int32_t*)c->in[1].p, (int32_t*)c->in[2].p, (int32_t*)c->in[3].p,
                            (int32_t*)c->in[4].p, (int32_t*)c->in[5].p, (int32_t*)c->oa.p, (int32_t*)c->ob.p, nullptr, nullptr, true, nullptr);
+    if (rc) return rc;
+    CU_TRY(c, cudaMemcpyAsync(oa, c->oa.p, abytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(ob, c->ob.p, bbytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return MKTFHE_OK;
+}
+
+int mktfhe_gate_batch_mixed_dev(mktfhe_ctx* c, size_t G, const int32_t* gate_ids, const int32_t* xa, const int32_t* xb, const int32_t* ya,
+                                const int32_t* yb, const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob, void* stream) {
+    if (!c) return MKTFHE_EINVAL;
+    if (G && (!gate_ids || !xa || !xb || !ya || !yb || !oa || !ob)) return fail(c, MKTFHE_EINVAL, "gate_batch_mixed: NULL buffer");
+    CU_TRY(c, cudaSetDevice(c->device));
+    // za/zb are read only by MKTFHE_GATE_AND3 gates; point them at x when absent so no gate dereferences NULL
+    return run_bootstrap_dev(c, {0, 0, 0, 0}, (int64_t)1 << 61, G, xa, xb, ya, yb, za ? za : xa, zb ? zb : xb, oa, ob, nullptr, nullptr, true,
+                             (cudaStream_t)stream, gate_ids);
+}
+
+int mktfhe_gate_batch_mixed(mktfhe_ctx* c, size_t G, const int32_t* gate_ids, const int32_t* xa, const int32_t* xb, const int32_t* ya,
+                            const int32_t* yb, const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob) {
+    if (!c) return MKTFHE_EINVAL;
+    if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
+    if (G == 0) return MKTFHE_OK;
+    if (!gate_ids || !xa || !xb || !ya || !yb || !oa || !ob) return fail(c, MKTFHE_EINVAL, "gate_batch_mixed: NULL buffer");
+    bool need_z = false;
+    for (size_t g = 0; g < G; g++) {
+        if (gate_ids[g] < MKTFHE_GATE_NAND || gate_ids[g] > MKTFHE_GATE_AND3) return fail(c, MKTFHE_EINVAL, "gate_ids[%zu] = %d is not a gate id", g, gate_ids[g]);
+        need_z |= gate_ids[g] == MKTFHE_GATE_AND3;
+    }
+    if (need_z && (!za || !zb)) return fail(c, MKTFHE_EINVAL, "gate_batch_mixed: a 3AND gate needs z");
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t kn = (size_t)c->prm.n * c->prm.k, abytes = G * kn * 4, bbytes = G * 4;
+    int rc;
+    if ((rc = stage_in(c, c->gids, gate_ids, bbytes)) || (rc = stage_in(c, c->in[0], xa, abytes)) || (rc = stage_in(c, c->in[1], xb, bbytes)) ||
+        (rc = stage_in(c, c->in[2], ya, abytes)) || (rc = stage_in(c, c->in[3], yb, bbytes)))
+        return rc;
+    if (need_z && ((rc = stage_in(c, c->in[4], za, abytes)) || (rc = stage_in(c, c->in[5], zb, bbytes)))) return rc;
+    if ((rc = reserve(c, c->oa, abytes)) || (rc = reserve(c, c->ob, bbytes))) return rc;
+    rc = mktfhe_gate_batch_mixed_dev(c, G, (int32_t*)c->gids.p, (int32_t*)c->in[0].p, (int32_t*)c->in[1].p, (int32_t*)c->in[2].p, (int32_t*)c->in[3].p,
+                                     need_z ? (int32_t*)c->in[4].p : nullptr, need_z ? (int32_t*)c->in[5].p : nullptr, (int32_t*)c->oa.p,
+                                     (int32_t*)c->ob.p, nullptr);
     if (rc) return rc;
     CU_TRY(c, cudaMemcpyAsync(oa, c->oa.p, abytes, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaMemcpyAsync(ob, c->ob.p, bbytes, cudaMemcpyDeviceToHost, c->stream));
