@@ -14,7 +14,7 @@ static HostTables T;
 static u64 rnd_state = 0x1234567ull;
 static u64 rnd() { rnd_state ^= rnd_state << 13; rnd_state ^= rnd_state >> 7; rnd_state ^= rnd_state << 17; return rnd_state; }
 
-// coefficient order in (values in [0, 4p)) -> transformed out[lane][c] (position 32 lane + c)
+// coefficient order in (values in [0, 2p)) -> transformed out[lane][c] (position 32 lane + c, values in [0, 14p))
 static void warp_fwd(int pi, const u32* a, u32 out[32][32]) {
     static u32 tile[TILE_WORDS];
     const u32 p = T.c.p[pi];
@@ -25,7 +25,10 @@ static void warp_fwd(int pi, const u32* a, u32 out[32][32]) {
         for (int r = 0; r < 32; r++) tile[r * TILE_STRIDE + lane] = x[r];
     }
     for (int lane = 0; lane < 32; lane++) {
-        for (int c = 0; c < 32; c++) x[c] = tile[lane * TILE_STRIDE + c];
+        for (int c = 0; c < 32; c++) {
+            if (tile[lane * TILE_STRIDE + c] >= 12 * p) { printf("FAIL passA range\n"); exit(1); }
+            x[c] = reduce_to_4p(tile[lane * TILE_STRIDE + c], 4 * p);
+        }
         fwd_passB(x, T.twB.data() + ((size_t)pi * 2 + 0) * 31 * 32 + lane, p);
         for (int c = 0; c < 32; c++) out[lane][c] = x[c];
     }
@@ -62,16 +65,21 @@ int main() {
             const u32 m = mont_mul(d, k, p, T.c.pinv_neg[pi]);
             if (m >= 2 * p || (u64)m * (((u64)1 << 32) % p) % p != (u64)d * k % p) { fails++; printf("FAIL mont\n"); break; }
             u32 X = rnd() % (4 * p), Y = rnd() % (4 * p), X0 = X, Y0 = Y;
-            ct_bfly(X, Y, w, ws, p, 2 * p);
+            ct_bfly<true>(X, Y, w, ws, p, 2 * p);
             const u64 wy = (u64)Y0 % p * w % p;
             if (X >= 4 * p || Y >= 4 * p || X % p != (X0 % p + wy) % p || Y % p != (X0 % p + p - wy) % p) { fails++; printf("FAIL ct\n"); break; }
+            X = X0 + 8 * p; Y = (u32)rnd();                      // lazy form: X < 12p, any 32-bit Y
+            const u32 Xl = X, Yl = Y;
+            ct_bfly<false>(X, Y, w, ws, p, 2 * p);
+            const u64 wyl = (u64)Yl % p * w % p;
+            if (X >= 14 * p || Y >= 14 * p || X % p != (Xl % p + wyl) % p || Y % p != (Xl % p + p - wyl) % p) { fails++; printf("FAIL ct lazy\n"); break; }
             X = X0; Y = Y0;
-            gs_bfly(X, Y, w, ws, p, 4 * p);
+            gs_bfly<true>(X, Y, w, ws, p, 4 * p, 4 * p);
             if (X >= 4 * p || Y >= 2 * p || X % p != ((u64)X0 + Y0) % p || Y % p != ((u64)X0 % p + p - Y0 % p) % p * w % p) { fails++; printf("FAIL gs\n"); break; }
         }
         // forward transform vs the definition: out[pos] = A(psi^(2 brev(pos) + 1))
         std::vector<u32> a(N), back(N);
-        for (auto& v : a) v = rnd() % (4 * p);
+        for (auto& v : a) v = rnd() % (2 * p);
         static u32 A[32][32];
         warp_fwd(pi, a.data(), A);
         std::vector<u32> psipow(2 * N);
@@ -82,8 +90,9 @@ int main() {
                 const u32 e = 2 * brev(ntt_pos(lane, c), LOGN) + 1;
                 u64 s = 0;
                 for (int i = 0; i < N; i++) s = (s + (u64)(a[i] % p) * psipow[(u64)i * e % (2 * N)]) % p;
-                if (A[lane][c] >= 4 * p || A[lane][c] % p != s) { fails++; printf("FAIL fwd prime=%d lane=%d c=%d\n", pi, lane, c); break; }
+                if (A[lane][c] >= 14 * p || A[lane][c] % p != s) { fails++; printf("FAIL fwd prime=%d lane=%d c=%d\n", pi, lane, c); break; }
             }
+        for (int l = 0; l < 32; l++) for (int c = 0; c < 32; c++) A[l][c] = reduce_to_4p(A[l][c], 4 * p);
         warp_inv(pi, A, back.data());
         for (int i = 0; i < N; i++)
             if (back[i] >= 4 * p || back[i] % p != (u64)(a[i] % p) * N % p) { fails++; printf("FAIL roundtrip prime=%d i=%d\n", pi, i); break; }

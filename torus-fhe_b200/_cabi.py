@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmktfhe_b200.so")
+LIB_PATH = os.environ.get("MKTFHE_B200_LIB") or os.path.join(_HERE, "libmktfhe_b200.so")   # env override: kernel experiments
 
 OK, EINVAL, ECUDA, ESTATE, ENOMEM = 0, -1, -2, -3, -4
 GATE_NAND, GATE_OR, GATE_AND, GATE_XOR, GATE_AND3 = 0, 1, 2, 3, 4

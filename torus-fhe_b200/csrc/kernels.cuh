@@ -25,7 +25,10 @@ using rns::uint2_;
 constexpr int N = rns::N;
 constexpr int TPG = 96;                              // threads per gate: one warp per prime
 constexpr int TWB_WORDS = rns::NP * 2 * 31 * 32 * 2; // per-lane twiddle table [prime][dir][31][32] of (w, w') = 47616 B
-constexpr int MAX_GPC = 5;                           // gates per CTA (named barriers 1..GPC)
+#ifndef MK_MAX_GPC
+#define MK_MAX_GPC 4      // measured: 4 gates x 3 warps at 168 registers beat 5 gates at 128 registers (profiles/ab_r1.txt)
+#endif
+constexpr int MAX_GPC = MK_MAX_GPC;                  // gates per CTA (named barriers 1..GPC)
 
 __constant__ rns::Consts c_rns;
 
@@ -35,7 +38,22 @@ __constant__ rns::Consts c_rns;
 //   (out, src) -> reference part: body<-body part_1, body<-mask part_2, mask<-mask part_3, mask<-body part_4
 //   key slot: rns::key_slot(lane, c) of transformed position 32*lane + c; values NTT(K mod p) * N^-1 * 2^32 mod p
 __host__ __device__ inline size_t bsk_elem_words(int l) { return (size_t)rns::NP * 2 * l * 2 * N; }
-__host__ __device__ inline size_t gate_smem_bytes(int l) { return (size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)rns::NP * rns::TILE_WORDS * 4; }
+#ifndef MK_TILE_SETS
+#define MK_TILE_SETS 1      // 2: separate residue tiles per output polynomial -> 3 gate barriers per step instead of 5
+#endif
+constexpr int TILE_SETS = MK_TILE_SETS;
+constexpr int TWA_WORDS = rns::NP * 2 * 32 * 2;      // pass-A twiddles [prime][dir][32 (31 used)] of (w, w') staged in shared memory = 1536 B
+constexpr int TW_SMEM_BYTES = (TWB_WORDS + TWA_WORDS) * 4;
+__host__ __device__ inline size_t gate_smem_bytes(int l) {
+    return (size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)TILE_SETS * rns::NP * rns::TILE_WORDS * 4;
+}
+
+// gates per CTA: as many as fit in the 227 KB of shared memory beside the twiddle tables (at most MAX_GPC)
+constexpr int gpc_for(int l) {
+    int g = MAX_GPC;
+    while (g > 1 && (size_t)TW_SMEM_BYTES + (size_t)g * ((size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)TILE_SETS * rns::NP * rns::TILE_WORDS * 4) > 227 * 1024) g--;
+    return g;
+}
 
 struct GateLinear {   // temp = mu0 + cx*x + cy*y + cz*z   (3gen_mk_gates.jl:8-74)
     int32_t mu0, cx, cy, cz;
@@ -77,22 +95,27 @@ __device__ __forceinline__ int32_t t64tot32(int64_t v) {
     return __double2int_rz(__ll2double_rn(v) * (1.0 / 4294967296.0));
 }
 
+// per-lane pass-B table from global memory, uniform pass-A table from __constant__ memory (a broadcast LDS is cheaper than an
+// LDC whose address the compiler cannot prove warp-uniform)
 __device__ __forceinline__ void stage_twiddles(uint2_* twB_s, const uint2_* twB_g) {
     const uint4* src = reinterpret_cast<const uint4*>(twB_g);
     uint4* dst = reinterpret_cast<uint4*>(twB_s);
     for (int i = threadIdx.x; i < TWB_WORDS / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    uint2_* twA_s = twB_s + TWB_WORDS / 2;
+    for (int i = threadIdx.x; i < rns::NP * 2 * 31; i += blockDim.x) twA_s[(i / 31) * 32 + i % 31] = c_rns.twA[i / 62][(i / 31) & 1][i % 31];
 }
 
-// forward transform of the 32 elements of this thread (coefficients 32 r + lane -> positions 32 lane + c)
+// forward transform of the 32 elements of this thread (coefficients 32 r + lane, in [0, 2p) -> positions 32 lane + c, in [0, 14p))
 __device__ __forceinline__ void warp_ntt_fwd(u32 (&x)[32], u32* tile, const uint2_* twA, const uint2_* twB_lane, u32 p, int lane) {
+    const u32 p4 = rns::keep_in_register(4 * p);
     rns::fwd_passA(x, twA, p);
 #pragma unroll
     for (int r = 0; r < 32; r++) tile[r * rns::TILE_STRIDE + lane] = x[r];
     __syncwarp();
 #pragma unroll
-    for (int c = 0; c < 32; c++) x[c] = tile[lane * rns::TILE_STRIDE + c];
+    for (int c = 0; c < 32; c++) x[c] = rns::reduce_to_4p(tile[lane * rns::TILE_STRIDE + c], p4);  // pass A leaves [0, 12p)
     __syncwarp();
-    rns::fwd_passB(x, twB_lane, p);
+    rns::fwd_passB(x, twB_lane, p);                                                               // -> [0, 14p)
 }
 // inverse transform (positions 32 lane + c -> coefficients 32 r + lane), scaled by N
 __device__ __forceinline__ void warp_ntt_inv(u32 (&x)[32], u32* tile, const uint2_* twA, const uint2_* twB_lane, u32 p, int lane) {
@@ -155,6 +178,8 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
     u32* tile = tiles + w * rns::TILE_WORDS;
     const uint2_* twBf = twB + ((size_t)(w * 2 + 0) * 31) * 32 + lane;
     const uint2_* twBi = twB + ((size_t)(w * 2 + 1) * 31) * 32 + lane;
+    const uint2_* twAf = twB + TWB_WORDS / 2 + (w * 2 + 0) * 32;
+    const uint2_* twAi = twAf + 32;
     const uint4* kp = reinterpret_cast<const uint4*>(key + (size_t)w * (2 * L * 2 * N)) + lane;
     u32 acc0[32], acc1[32];
 #pragma unroll
@@ -167,46 +192,52 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
         for (int rh = 0; rh < 8; rh++) {
             const u32 word = dig[(s * 8 + rh) * 32 + lane];
 #pragma unroll
-            for (int b = 0; b < 4; b++) x[4 * rh + b] = ((word >> (8 * b)) & 0xffu) + bias;
+            for (int b = 0; b < 4; b++) x[4 * rh + b] = rns::alu_add((word >> (8 * b)) & 0xffu, bias);
         }
-        warp_ntt_fwd(x, tile, c_rns.twA[w][0], twBf, p, lane);
+        warp_ntt_fwd(x, tile, twAf, twBf, p, lane);
         const uint4* k0 = kp + (size_t)(s * 2) * (N / 4);
 #pragma unroll
         for (int q4 = 0; q4 < 8; q4++) {
             const uint4 kv = __ldg(k0 + q4 * 32);
-            acc0[4 * q4 + 0] += rns::mont_mul(x[4 * q4 + 0], kv.x, p, pinv);
-            acc0[4 * q4 + 1] += rns::mont_mul(x[4 * q4 + 1], kv.y, p, pinv);
-            acc0[4 * q4 + 2] += rns::mont_mul(x[4 * q4 + 2], kv.z, p, pinv);
-            acc0[4 * q4 + 3] += rns::mont_mul(x[4 * q4 + 3], kv.w, p, pinv);
+            acc0[4 * q4 + 0] = rns::alu_add(acc0[4 * q4 + 0], rns::mont_mul(x[4 * q4 + 0], kv.x, p, pinv));
+            acc0[4 * q4 + 1] = rns::alu_add(acc0[4 * q4 + 1], rns::mont_mul(x[4 * q4 + 1], kv.y, p, pinv));
+            acc0[4 * q4 + 2] = rns::alu_add(acc0[4 * q4 + 2], rns::mont_mul(x[4 * q4 + 2], kv.z, p, pinv));
+            acc0[4 * q4 + 3] = rns::alu_add(acc0[4 * q4 + 3], rns::mont_mul(x[4 * q4 + 3], kv.w, p, pinv));
         }
         const uint4* k1 = k0 + N / 4;
 #pragma unroll
         for (int q4 = 0; q4 < 8; q4++) {
             const uint4 kv = __ldg(k1 + q4 * 32);
-            acc1[4 * q4 + 0] += rns::mont_mul(x[4 * q4 + 0], kv.x, p, pinv);
-            acc1[4 * q4 + 1] += rns::mont_mul(x[4 * q4 + 1], kv.y, p, pinv);
-            acc1[4 * q4 + 2] += rns::mont_mul(x[4 * q4 + 2], kv.z, p, pinv);
-            acc1[4 * q4 + 3] += rns::mont_mul(x[4 * q4 + 3], kv.w, p, pinv);
+            acc1[4 * q4 + 0] = rns::alu_add(acc1[4 * q4 + 0], rns::mont_mul(x[4 * q4 + 0], kv.x, p, pinv));
+            acc1[4 * q4 + 1] = rns::alu_add(acc1[4 * q4 + 1], rns::mont_mul(x[4 * q4 + 1], kv.y, p, pinv));
+            acc1[4 * q4 + 2] = rns::alu_add(acc1[4 * q4 + 2], rns::mont_mul(x[4 * q4 + 2], kv.z, p, pinv));
+            acc1[4 * q4 + 3] = rns::alu_add(acc1[4 * q4 + 3], rns::mont_mul(x[4 * q4 + 3], kv.w, p, pinv));
         }
     }
     // ---- phase 3: per output polynomial, inverse NTT of the three residue polynomials, Garner CRT, accumulator update
+    const u32 p4 = rns::keep_in_register(4 * p);
 #pragma unroll 1
     for (int out = 0; out < 2; out++) {
         u32 x[32];
 #pragma unroll
         for (int c = 0; c < 32; c++) {
             u32 v = out ? acc1[c] : acc0[c];                 // sum of 2L products, each in [0, 2p)
-            if (L > 2) v = rns::umin32(v, v - 8 * p);
-            x[c] = rns::umin32(v, v - 4 * p);                // [0, 4p)
+            if (L > 2) v = rns::umin32(v, v - 2 * p4);
+            x[c] = rns::umin32(v, v - p4);                   // [0, 4p)
         }
-        warp_ntt_inv(x, tile, c_rns.twA[w][1], twBi, p, lane);
+        u32* otile = TILE_SETS == 2 ? tile + out * (rns::NP * rns::TILE_WORDS) : tile;
+        warp_ntt_inv(x, otile, twAi, twBi, p, lane);
 #pragma unroll
-        for (int r = 0; r < 32; r++) tile[32 * r + lane] = x[r];   // residues in coefficient order
+        for (int r = 0; r < 32; r++) otile[32 * r + lane] = x[r];   // residues in coefficient order
+        if (TILE_SETS == 2 && out == 0) continue;
         gate_barrier(bar_id);
-        u64* ap = acc + out * N;
-        for (int i = gtid; i < N; i += TPG) {
-            const u64 R = rns::crt_lift(tiles[i], tiles[rns::TILE_WORDS + i], tiles[2 * rns::TILE_WORDS + i], c_rns.crt);
-            ap[i] = MUX ? ap[i] + R : R;
+        for (int o = (TILE_SETS == 2 ? 0 : out); o <= out; o++) {
+            const u32* rt = TILE_SETS == 2 ? tiles + o * (rns::NP * rns::TILE_WORDS) : tiles;
+            u64* ap = acc + o * N;
+            for (int i = gtid; i < N; i += TPG) {
+                const u64 R = rns::crt_lift(rt[i], rt[rns::TILE_WORDS + i], rt[2 * rns::TILE_WORDS + i], c_rns.crt);
+                ap[i] = MUX ? ap[i] + R : R;
+            }
         }
         gate_barrier(bar_id);
     }
@@ -222,7 +253,7 @@ __global__ void __launch_bounds__(GPC* TPG, 1) blind_rotate_kernel(BlindRotateAr
     const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot;
     const int g = blockIdx.x * GPC + slot;
     if (g >= p.G) return;   // no CTA-wide barrier below this line
-    unsigned char* base = smem_raw + TWB_WORDS * 4 + (size_t)slot * gate_smem_bytes(L);
+    unsigned char* base = smem_raw + TW_SMEM_BYTES + (size_t)slot * gate_smem_bytes(L);
     u64* acc = reinterpret_cast<u64*>(base);
     u32* dig = reinterpret_cast<u32*>(base + 2 * N * 8);
     u32* tiles = dig + 2 * L * (N / 4);
@@ -281,7 +312,7 @@ __global__ void __launch_bounds__(GPC* TPG, 1) extprod_kernel(int G, const u32* 
     const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot;
     const int g = blockIdx.x * GPC + slot;
     if (g >= G) return;
-    unsigned char* base = smem_raw + TWB_WORDS * 4 + (size_t)slot * gate_smem_bytes(L);
+    unsigned char* base = smem_raw + TW_SMEM_BYTES + (size_t)slot * gate_smem_bytes(L);
     u64* acc = reinterpret_cast<u64*>(base);
     u32* dig = reinterpret_cast<u32*>(base + 2 * N * 8);
     u32* tiles = dig + 2 * L * (N / 4);

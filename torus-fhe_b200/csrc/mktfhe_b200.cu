@@ -91,20 +91,15 @@ int check_params(const mktfhe_params* p) {
     return MKTFHE_OK;
 }
 
-int pick_gpc(int l) {
-    int g = mk::MAX_GPC;
-    while (g > 1 && (size_t)mk::TWB_WORDS * 4 + g * mk::gate_smem_bytes(l) > 227 * 1024) g--;
-    return g;
-}
-size_t br_smem_bytes(const mktfhe_ctx* c) { return (size_t)mk::TWB_WORDS * 4 + c->gpc * mk::gate_smem_bytes(c->prm.l); }
+size_t br_smem_bytes(const mktfhe_ctx* c) { return (size_t)mk::TW_SMEM_BYTES + c->gpc * mk::gate_smem_bytes(c->prm.l); }
 
-// (L, GPC) instantiations: pick_gpc gives 5 gates per CTA for l <= 3 and 4 for l = 4
+// (L, GPC) instantiations: mk::gpc_for(l) gates per CTA
 #define MK_DISPATCH_L(c, KERNEL, ...)                                      \
     switch ((c)->prm.l) {                                                  \
-    case 1: KERNEL(1, 5, __VA_ARGS__); break;                              \
-    case 2: KERNEL(2, 5, __VA_ARGS__); break;                              \
-    case 3: KERNEL(3, 5, __VA_ARGS__); break;                              \
-    default: KERNEL(4, 4, __VA_ARGS__); break;                             \
+    case 1: KERNEL(1, mk::gpc_for(1), __VA_ARGS__); break;                 \
+    case 2: KERNEL(2, mk::gpc_for(2), __VA_ARGS__); break;                 \
+    case 3: KERNEL(3, mk::gpc_for(3), __VA_ARGS__); break;                 \
+    default: KERNEL(4, mk::gpc_for(4), __VA_ARGS__); break;                \
     }
 
 int set_attrs(mktfhe_ctx* c) {
@@ -203,7 +198,7 @@ int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
     for (auto& ev : c->ev) CREATE_TRY(cudaEventCreate(&ev));
     const int B1 = (1 << params->basebit) - 1;
     c->bsk_bytes = (size_t)params->k * params->n * mk::bsk_elem_words(params->l) * sizeof(u32);
-    c->gpc = pick_gpc(params->l);
+    c->gpc = mk::gpc_for(params->l);
     c->ksk_bytes = (size_t)params->k * mk::N * params->t * B1 * (params->n + 1) * sizeof(int32_t);
     CREATE_TRY(cudaMalloc(&c->d_bsk, c->bsk_bytes));
     CREATE_TRY(cudaMalloc(&c->d_ksk, c->ksk_bytes));

@@ -9,6 +9,7 @@
 //   pass A (t = 512..32): thread `lane` holds a[32 r + lane] in x[r]; the twiddle depends on r only
 //                         -> the 31-entry table is uniform across the warp (__constant__ memory)
 //   transpose through a padded 32x33 tile:  store x[r] -> tile[33 r + lane];  load x[c] = tile[33 lane + c]
+//   (forward: values are lazily reduced -- inputs < 2p, < 12p after pass A, brought below 4p on the tile load, < 14p after pass B)
 //   pass B (t = 16..1)  : thread `lane` holds a[32 lane + c] in x[c]; the twiddle depends on (lane, c)
 //                         -> 31 entries per lane (table [31][32] staged in shared memory)
 // The inverse (Gentleman-Sande, inverse twiddles) runs pass B, the transposed move, then pass A; its 1/N

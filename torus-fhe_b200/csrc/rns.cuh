@@ -39,22 +39,44 @@ MK_HD u32 mulhi32(u32 a, u32 b) {
 #endif
 }
 MK_HD u32 umin32(u32 a, u32 b) { return a < b ? a : b; }
+// a + b on the alu pipe: ptxas likes to turn two-input adds into IMAD.IADD "to balance the pipes", but here the fma pipe
+// is the binding one (IMAD.HI is half rate).  max(a + b, 0) is a single VIADDMNMX.U32 and cannot be moved.
+MK_HD u32 alu_add(u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+    return __viaddmax_u32(a, b, 0u);
+#else
+    return a + b;
+#endif
+}
+// Keeps a loop-invariant multiple of p in its own register: without this ptxas rematerialises `x - 4p` as
+// IMAD(p, -4, x), spending a slot of the binding fma pipe on what should be an IADD3 / VIADDMNMX of the alu pipe.
+MK_HD u32 keep_in_register(u32 v) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+r"(v));
+#endif
+    return v;
+}
 
 // Shoup multiplication by a constant w (wp = floor(w 2^32 / p)): any y < 2^32 -> y*w mod p in [0, 2p)
 MK_HD u32 shoup_mul(u32 y, u32 w, u32 wp, u32 p) { return y * w - mulhi32(y, wp) * p; }
 
-// Harvey butterflies, values kept in [0, 4p).
-// forward (Cooley-Tukey): (X, Y) -> (X + wY, X - wY)
+// Harvey butterflies with lazy reduction.  16p < 2^32 (p < 2^28), Shoup products accept any 32-bit input and return
+// [0, 2p), so sums may grow for several stages before a conditional subtraction is needed.
+// forward (Cooley-Tukey): (X, Y) -> (X + wY, X - wY).  X < B on input  =>  both outputs < B + 2p.
+//   REDUCE: first bring X from [0, 4p) to [0, 2p)   (VIADDMNMX.U32)
+template <bool REDUCE>
 MK_HD void ct_bfly(u32& X, u32& Y, u32 w, u32 wp, u32 p, u32 p2) {
-    const u32 x = umin32(X, X - p2);              // [0, 2p)     (VIADDMNMX.U32)
+    const u32 x = REDUCE ? umin32(X, X - p2) : X;
     const u32 t = shoup_mul(Y, w, wp, p);         // [0, 2p)
-    X = x + t;
+    X = alu_add(x, t);
     Y = x - t + p2;
 }
-// inverse (Gentleman-Sande): (X, Y) -> (X + Y, (X - Y) w); X out in [0, 4p), Y out in [0, 2p)
-MK_HD void gs_bfly(u32& X, u32& Y, u32 w, u32 wp, u32 p, u32 p4) {
-    const u32 s = X + Y, d = X - Y + p4;          // < 8p < 2^31
-    X = umin32(s, s - p4);
+// inverse (Gentleman-Sande): (X, Y) -> (X + Y, (X - Y) w).  X, Y < B on input (B <= 4p)  =>  X out < 2B (REDUCE: brought
+// back below 4p when 2B = 8p), Y out in [0, 2p).  `off` is a multiple of p that is >= B.
+template <bool REDUCE>
+MK_HD void gs_bfly(u32& X, u32& Y, u32 w, u32 wp, u32 p, u32 off, u32 p4) {
+    const u32 s = alu_add(X, Y), d = X - Y + off;
+    X = REDUCE ? umin32(s, s - p4) : s;           // VIADDMNMX.U32 when p4 lives in a register
     Y = shoup_mul(d, w, wp, p);
 }
 
@@ -69,9 +91,11 @@ MK_HD u32 mont_mul(u32 d, u32 k, u32 p, u32 pinv_neg) {
 // elements at gap g = 16 >> k inside blocks of 2g; the twiddle of block b is entry e = 2^k - 1 + b of a
 // 31-entry table that `tw(e)` returns (uniform across the warp in the pass over the high index bits,
 // per-lane in the pass over the low index bits -- see ntt_rns.cuh).
+//
+// ct32: inputs < B with B <= 4p; no reduction inside (the bound grows by 2p per stage); outputs < B + 10p <= 14p < 2^32.
 template <class TW>
 MK_HD void ct32(u32 (&x)[32], TW tw, u32 p) {
-    const u32 p2 = 2 * p;
+    const u32 p2 = keep_in_register(2 * p);
 #pragma unroll
     for (int k = 0; k < 5; k++) {
         const int g = 16 >> k;
@@ -79,13 +103,19 @@ MK_HD void ct32(u32 (&x)[32], TW tw, u32 p) {
         for (int b = 0; b < (1 << k); b++) {
             const uint2_ w = tw((1 << k) - 1 + b);
 #pragma unroll
-            for (int j = 0; j < g; j++) ct_bfly(x[2 * g * b + j], x[2 * g * b + j + g], w.x, w.y, p, p2);
+            for (int j = 0; j < g; j++) ct_bfly<false>(x[2 * g * b + j], x[2 * g * b + j + g], w.x, w.y, p, p2);
         }
     }
 }
+// [0, 16p) -> [0, 4p): between the two passes of a forward transform
+MK_HD u32 reduce_to_4p(u32 v, u32 p4) {           // p4 = 4p (held in a register by the caller)
+    v = umin32(v, v - 2 * p4);
+    return umin32(v, v - p4);
+}
+// gs32: inputs in [0, 4p); the sum output is reduced every stage (it doubles otherwise); outputs in [0, 4p).
 template <class TW>
 MK_HD void gs32(u32 (&x)[32], TW tw, u32 p) {
-    const u32 p4 = 4 * p;
+    const u32 p4 = keep_in_register(4 * p);
 #pragma unroll
     for (int k = 4; k >= 0; k--) {
         const int g = 16 >> k;
@@ -93,7 +123,7 @@ MK_HD void gs32(u32 (&x)[32], TW tw, u32 p) {
         for (int b = 0; b < (1 << k); b++) {
             const uint2_ w = tw((1 << k) - 1 + b);
 #pragma unroll
-            for (int j = 0; j < g; j++) gs_bfly(x[2 * g * b + j], x[2 * g * b + j + g], w.x, w.y, p, p4);
+            for (int j = 0; j < g; j++) gs_bfly<true>(x[2 * g * b + j], x[2 * g * b + j + g], w.x, w.y, p, p4, p4);
         }
     }
 }
