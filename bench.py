@@ -259,7 +259,13 @@ def run_ours(args):
         ct_io = 2 * (k * n + 1) * 4 + (N + 1) * 4
         alg_bytes = G * (bsk_1limb + ct_io)
         achieved = alg_bytes / (br_ms * 1e-3) / 1e9
-        modmul = k * n * ((2 * l + 4) * (N // 2) * 10 + 8 * l * N)   # 2-limb count of SURVEY §8(d)
+        # algorithmic IMAD-pipe slots per gate of the three-prime RNS formulation: per blind-rotate step
+        # (6l + 6) NTTs x 5120 butterflies x 4 slots (IMAD.HI is half rate), 12l x 1024 Montgomery products x 5 slots,
+        # 2048 CRT lifts x 17 slots
+        imad_slots = k * n * ((6 * l + 6) * 5120 * 4 + 12 * l * 1024 * 5 + 2 * 1024 * 17)
+        imad_peak = 18.26e12       # measured: tools/pipe_ubench.cu -> profiles/pipe_ubench_r1.txt (62.8 IMAD lanes/clk/SM)
+        ncu_traffic = {"bytes": 451.5e6, "gates_in_captured_launch": 2368,
+                       "source": "profiles/ncu_r1_c_blind_rotate.txt (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)"}
         value = world * G * args.steps / (ms * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "ms_per_bootstrap_amortized": ms / args.steps / G, "higher_is_better": True, "scaling": "weak",
@@ -273,11 +279,14 @@ def run_ours(args):
                         "d2h_bytes_per_step": int((G * k * n + G) * 4)},
                 "gpu_launches": int(launches),
                 "roofline": {"kernel": "blind_rotate_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / hbm_peak, "traffic": ncu_traffic["bytes"], "traffic_note": ncu_traffic, "peak_source": peak_src,
+                             "note": "contract roofline (HBM); the kernel is IMAD-pipe bound and streams the key from L2 (hit rate 97.8 %): see integer_bound",
                              "algorithmic_bytes_per_gate": bsk_1limb + ct_io, "streamed_bytes_per_gate_this_build": bsk_stream,
                              "kernel_ms": br_ms, "keyswitch_ms": ks_ms, "keyswitch_gather_GBps": G * ksk_gather / (ks_ms * 1e-3) / 1e9,
                              "kernel_share_of_step": br_ms / (ms / args.steps),
-                             "integer_bound": {"modmuls_per_gate": modmul, "gmodmul_per_s": G * modmul / (br_ms * 1e-3) / 1e9}},
+                             "integer_bound": {"bound": "imad_pipe", "algorithmic_slots_per_gate": imad_slots,
+                                               "achieved": G * imad_slots / (br_ms * 1e-3) / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-slots/s",
+                                               "frac": G * imad_slots / (br_ms * 1e-3) / imad_peak}},
                 "clocks": clocks, "decryptions_correct": ok}
         if world == 1 and not args.no_cpu_baseline:
             O, oks = oracle_keyset()

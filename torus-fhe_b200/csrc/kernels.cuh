@@ -52,11 +52,31 @@ __host__ __device__ inline size_t gate_smem_bytes(int l) {
     return (size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)TILE_SETS * rns::NP * rns::TILE_WORDS * 4;
 }
 
+// Optional key staging by TMA (cp.async.bulk + mbarrier): each prime warp owns a 4 KB shared-memory slot into which the first
+// key polynomial (output 0) of the next digit polynomial is streamed while the warp is busy with the NTT; the second key
+// polynomial still arrives by LDG.128 (the compiler hoists those loads into pass B).  MEASURED AND REJECTED for now
+// (profiles/ab_r1.txt: 19.8 k vs 21.2 k gates/s): the key is L2-resident, ptxas already overlaps the LDGs with pass B, and the
+// 48 KB of slots push the register allocator into spills and shrink the L1.  Kept compilable (-DMK_TMA_KEY=1) because the
+// trade-off changes once more gates share one key fetch.
+#ifndef MK_TMA_KEY
+#define MK_TMA_KEY 0
+#endif
+constexpr int KSTAGE_BYTES = N * 4;                 // one key polynomial of one prime
+__host__ __device__ constexpr size_t gate_bytes_c(int l) {
+    return (size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)TILE_SETS * rns::NP * rns::TILE_WORDS * 4;
+}
 // gates per CTA: as many as fit in the 227 KB of shared memory beside the twiddle tables (at most MAX_GPC)
-constexpr int gpc_for(int l) {
+__host__ __device__ constexpr int gpc_for(int l) {
     int g = MAX_GPC;
     while (g > 1 && (size_t)TW_SMEM_BYTES + (size_t)g * ((size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)TILE_SETS * rns::NP * rns::TILE_WORDS * 4) > 227 * 1024) g--;
     return g;
+}
+
+__host__ __device__ constexpr bool tma_key_for(int l) {
+    return MK_TMA_KEY && (size_t)TW_SMEM_BYTES + (size_t)gpc_for(l) * (gate_bytes_c(l) + rns::NP * (KSTAGE_BYTES + 8)) <= 227 * 1024;
+}
+__host__ __device__ constexpr size_t cta_smem_bytes(int l) {
+    return (size_t)TW_SMEM_BYTES + (size_t)gpc_for(l) * (gate_bytes_c(l) + (tma_key_for(l) ? rns::NP * (KSTAGE_BYTES + 8) : 0));
 }
 
 struct GateLinear {   // temp = mu0 + cx*x + cy*y + cz*z   (3gen_mk_gates.jl:8-74)
@@ -88,6 +108,32 @@ __host__ __device__ inline GateLinear gate_linear(int gate) {
 }
 
 __device__ __forceinline__ void gate_barrier(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(TPG) : "memory"); }
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// one elected lane: announce `bytes` on the barrier and start the bulk copy global -> shared that completes it
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // earlier generic reads of the slot before the async write
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 
 // decode_message(x, 2N), numeric-functions.jl:70-73 (wrapping add, arithmetic shift)
 __device__ __forceinline__ int mod_switch_2N(int32_t x) {
@@ -138,11 +184,14 @@ __device__ __forceinline__ void warp_ntt_inv(u32 (&x)[32], u32* tile, const uint
 //   MUX = true : acc += ExtProd(X^a * acc - acc, key)   (mk_mux_rotate_3gen, 3gen_mk_internals.jl:59-62)
 //   MUX = false: acc  = ExtProd(acc, key)
 // acc: [2][N] u64, [0] = mask, [1] = body.  dig: [2L][8][32] words of 4 biased digit bytes.  tiles: [3][TILE_WORDS].
+// kstage/kbar: this warp's TMA key slot and its mbarrier (nullptr when the staging is disabled); kphase: its parity bit.
 template <int L, bool MUX>
 __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restrict__ dig, u32* __restrict__ tiles,
                                              const uint2_* __restrict__ twB, const u32* __restrict__ key, int a, int bgbit,
-                                             int bar_id, int gtid) {
+                                             int bar_id, int gtid, u32* kstage, u64* kbar, u32& kphase) {
+    constexpr bool TMA = tma_key_for(L);
     const int w = gtid >> 5, lane = gtid & 31;
+    if (TMA && lane == 0) tma_load_1d(kstage, key + (size_t)w * (2 * L * 2 * N), KSTAGE_BYTES, kbar);   // K[s = 0][out = 0]
     // ---- phase 1: rotate-subtract and gadget-decompose (tgsw.jl:112-138); digits biased to [0, Bg) and packed 4 per word
     {
         u64 off = 0;
@@ -200,15 +249,23 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
         }
         warp_ntt_fwd(x, tile, twAf, twBf, p, lane);
         const uint4* k0 = kp + (size_t)(s * 2) * (N / 4);
+        if (TMA) {
+            mbar_wait(kbar, kphase);
+            kphase ^= 1;
+        }
 #pragma unroll
         for (int q4 = 0; q4 < 8; q4++) {
-            const uint4 kv = __ldg(k0 + q4 * 32);
+            const uint4 kv = TMA ? reinterpret_cast<const uint4*>(kstage)[q4 * 32 + lane] : __ldg(k0 + q4 * 32);
             acc0[4 * q4 + 0] = rns::alu_add(acc0[4 * q4 + 0], rns::mont_mul(x[4 * q4 + 0], kv.x, p, pinv));
             acc0[4 * q4 + 1] = rns::alu_add(acc0[4 * q4 + 1], rns::mont_mul(x[4 * q4 + 1], kv.y, p, pinv));
             acc0[4 * q4 + 2] = rns::alu_add(acc0[4 * q4 + 2], rns::mont_mul(x[4 * q4 + 2], kv.z, p, pinv));
             acc0[4 * q4 + 3] = rns::alu_add(acc0[4 * q4 + 3], rns::mont_mul(x[4 * q4 + 3], kv.w, p, pinv));
         }
         const uint4* k1 = k0 + N / 4;
+        if (TMA && s + 1 < 2 * L) {      // the slot has been consumed by every lane: stream K[s + 1][out = 0] into it
+            __syncwarp();
+            if (lane == 0) tma_load_1d(kstage, key + (size_t)w * (2 * L * 2 * N) + (size_t)(s + 1) * 2 * N, KSTAGE_BYTES, kbar);
+        }
 #pragma unroll
         for (int q4 = 0; q4 < 8; q4++) {
             const uint4 kv = __ldg(k1 + q4 * 32);
@@ -261,6 +318,19 @@ __global__ void __launch_bounds__(GPC* TPG, 1) blind_rotate_kernel(BlindRotateAr
     u64* acc = reinterpret_cast<u64*>(base);
     u32* dig = reinterpret_cast<u32*>(base + 2 * N * 8);
     u32* tiles = dig + 2 * L * (N / 4);
+    // TMA key slots and their mbarriers live after the GPC gate regions
+    unsigned char* kbase = smem_raw + TW_SMEM_BYTES + (size_t)GPC * gate_smem_bytes(L);
+    const int gw = (slot * TPG + gtid) >> 5;    // warp index inside the CTA
+    u32* kstage = reinterpret_cast<u32*>(kbase + (size_t)gw * KSTAGE_BYTES);
+    u64* kbar = reinterpret_cast<u64*>(kbase + (size_t)GPC * rns::NP * KSTAGE_BYTES) + gw;
+    u32 kphase = 0;
+    if (tma_key_for(L)) {
+        if ((gtid & 31) == 0) {
+            mbar_init(kbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     const int kn = p.k * p.n;
     // gate prologue (3gen_mk_gates.jl) + mod switch (3gen_mk_internals.jl:102-103); every thread of the gate computes
     // the same rotation amounts from broadcast loads
@@ -290,7 +360,7 @@ __global__ void __launch_bounds__(GPC* TPG, 1) blind_rotate_kernel(BlindRotateAr
         const int a = a_next;
         if (it + 1 < kn) a_next = rotation(p.xa, p.ya, p.za, abase + it + 1, 0u);
         if (a == 0) continue;   // :69 (uniform across the gate)
-        extprod_step<L, true>(acc, dig, tiles, twB, p.bsk + (size_t)it * estride, a, p.bgbit, bar_id, gtid);
+        extprod_step<L, true>(acc, dig, tiles, twB, p.bsk + (size_t)it * estride, a, p.bgbit, bar_id, gtid, kstage, kbar, kphase);
     }
     // rlwe_extract_sample_64 (rlwe.jl:70-74): a'_0 = mask_0, a'_i = -mask_{N-i}, b' = body_0
     int32_t* ext = p.ext_out + (size_t)g * (N + 1);
@@ -320,9 +390,21 @@ __global__ void __launch_bounds__(GPC* TPG, 1) extprod_kernel(int G, const u32* 
     u64* acc = reinterpret_cast<u64*>(base);
     u32* dig = reinterpret_cast<u32*>(base + 2 * N * 8);
     u32* tiles = dig + 2 * L * (N / 4);
+    unsigned char* kbase = smem_raw + TW_SMEM_BYTES + (size_t)GPC * gate_smem_bytes(L);
+    const int gw = (slot * TPG + gtid) >> 5;
+    u32* kstage = reinterpret_cast<u32*>(kbase + (size_t)gw * KSTAGE_BYTES);
+    u64* kbar = reinterpret_cast<u64*>(kbase + (size_t)GPC * rns::NP * KSTAGE_BYTES) + gw;
+    u32 kphase = 0;
+    if (tma_key_for(L)) {
+        if ((gtid & 31) == 0) {
+            mbar_init(kbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     for (int i = gtid; i < 2 * N; i += TPG) acc[i] = (u64)acc_in[(size_t)g * 2 * N + i];
     gate_barrier(bar_id);
-    extprod_step<L, false>(acc, dig, tiles, twB, bsk + (size_t)elem[g] * bsk_elem_words(L), 0, bgbit, bar_id, gtid);
+    extprod_step<L, false>(acc, dig, tiles, twB, bsk + (size_t)elem[g] * bsk_elem_words(L), 0, bgbit, bar_id, gtid, kstage, kbar, kphase);
     for (int i = gtid; i < 2 * N; i += TPG) acc_out[(size_t)g * 2 * N + i] = (int64_t)acc[i];
 }
 

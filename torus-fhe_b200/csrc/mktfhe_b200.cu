@@ -91,7 +91,7 @@ int check_params(const mktfhe_params* p) {
     return MKTFHE_OK;
 }
 
-size_t br_smem_bytes(const mktfhe_ctx* c) { return (size_t)mk::TW_SMEM_BYTES + c->gpc * mk::gate_smem_bytes(c->prm.l); }
+size_t br_smem_bytes(const mktfhe_ctx* c) { return mk::cta_smem_bytes(c->prm.l); }
 
 // (L, GPC) instantiations: mk::gpc_for(l) gates per CTA
 #define MK_DISPATCH_L(c, KERNEL, ...)                                      \
