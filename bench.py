@@ -162,7 +162,8 @@ def run_ours(args):
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    params = T.mktfhe_parameters_2party_3gen
+    params = {2: T.mktfhe_parameters_2party_3gen, 3: T.mktfhe_parameters_3party_3gen, 4: T.mktfhe_parameters_4party_3gen,
+              5: T.mktfhe_parameters_5party_3gen, 8: T.mktfhe_parameters_8party_3gen}[args.parties]
     G, k, n = args.gates, params.max_parties, params.lwe_size
     eng = T.Engine(params, device=local)
     rng = np.random.default_rng(KEY_SEED)
@@ -255,7 +256,7 @@ def run_ours(args):
         hbm_peak, peak_src = measured_peaks()
         N, l = params.rlwe_polynomial_degree, params.gsw_decomp_length
         bsk_1limb = k * n * 4 * l * N * 8                         # 68.2 MB per 2-party bootstrap (reference FFT key size)
-        bsk_stream, ksk_gather = ctx.algorithmic_bytes()          # what this build streams (two 32-bit limbs) / gathers per gate
+        bsk_stream, ksk_gather = ctx.algorithmic_bytes()          # what this build streams (three u32 residues per coefficient) / gathers per gate
         ct_io = 2 * (k * n + 1) * 4 + (N + 1) * 4
         alg_bytes = G * (bsk_1limb + ct_io)
         achieved = alg_bytes / (br_ms * 1e-3) / 1e9
@@ -267,12 +268,13 @@ def run_ours(args):
         ncu_traffic = {"bytes": 451.5e6, "gates_in_captured_launch": 2368,
                        "source": "profiles/ncu_r1_c_blind_rotate.txt (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)"}
         value = world * G * args.steps / (ms * 1e-3)
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        line = {"metric": METRIC.replace("2-party", f"{k}-party"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "ms_per_bootstrap_amortized": ms / args.steps / G, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32 RNS (three 28-bit-prime NTTs + CRT, exact mod 2^64) / int32 LWE", "data": "synthetic",
-                "config": {"workload": f"2-party NAND x{G} per GPU (mktfhe_parameters_2party_3gen: n=520 N=1024 l=2 Bg=2^7 t=3 Bks=2^3)",
+                "config": {"workload": f"{k}-party NAND x{G} per GPU (mktfhe_parameters_{k}party_3gen: n={n} N={N} l={l} Bg=2^{params.gsw_log2_base} "
+                                       f"t={params.ks_decomp_length} Bks=2^{params.ks_log2_base})",
                            "gates_per_step_per_gpu": G, "parallelism": f"gate-sharded replicas x{world}",
-                           "l2_policy": "inputs (136 MB/step) + keys (226 MB) exceed the 126 MB L2; no flush needed",
+                           "l2_policy": f"inputs ({2 * G * (k * n + 1) * 4 / 1e6:.0f} MB/step) + keys ({(bsk_stream + ctx.key_buffers()[1][1]) / 1e6:.0f} MB) exceed the 126 MB L2; no flush needed",
                            "keys": "generated by the product host mirror (GPU exact products), broadcast over NCCL" if world > 1 else
                                    "generated by the product host mirror (GPU exact products)", "key_setup_s": round(t_keys, 2)},
                 "e2e": {"value": world * G * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(2 * (G * k * n + G) * 4),
@@ -288,7 +290,7 @@ def run_ours(args):
                                                "achieved": G * imad_slots / (br_ms * 1e-3) / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-slots/s",
                                                "frac": G * imad_slots / (br_ms * 1e-3) / imad_peak}},
                 "clocks": clocks, "decryptions_correct": ok}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.parties == 2:
             O, oks = oracle_keyset()
             cores = host_cores()
             cnt = max(cores, 8) * 4
@@ -313,6 +315,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--gates", type=int, default=16384, help="gates per step per GPU")
+    ap.add_argument("--parties", type=int, default=2, choices=[2, 3, 4, 5, 8], help="parameter set (BASELINE configs[2]: 4 and 8)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
