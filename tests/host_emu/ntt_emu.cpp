@@ -64,6 +64,9 @@ int main() {
             const u32 d = (u32)rnd(), k = rnd() % p;
             const u32 m = mont_mul(d, k, p, T.c.pinv_neg[pi]);
             if (m >= 2 * p || (u64)m * (((u64)1 << 32) % p) % p != (u64)d * k % p) { fails++; printf("FAIL mont\n"); break; }
+            const u32 d2 = (u32)(rnd() % (14ull * p)), k2 = rnd() % p, d1 = d % (14 * p);
+            const u32 m2 = mont_mul2(d1, k, d2, k2, p, T.c.pinv_neg[pi]);
+            if (m2 >= 3 * p || (u64)m2 * (((u64)1 << 32) % p) % p != ((u64)d1 * k % p + (u64)d2 * k2 % p) % p) { fails++; printf("FAIL mont2\n"); break; }
             u32 X = rnd() % (4 * p), Y = rnd() % (4 * p), X0 = X, Y0 = Y;
             ct_bfly<true>(X, Y, w, ws, p, 2 * p);
             const u64 wy = (u64)Y0 % p * w % p;

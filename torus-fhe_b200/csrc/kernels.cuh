@@ -23,12 +23,34 @@ namespace mk {
 using rns::uint2_;
 
 constexpr int N = rns::N;
-constexpr int TPG = 96;                              // threads per gate: one warp per prime
-constexpr int TWB_WORDS = rns::NP * 2 * 31 * 32 * 2; // per-lane twiddle table [prime][dir][31][32] of (w, w') = 47616 B
-#ifndef MK_MAX_GPC
-#define MK_MAX_GPC 4      // measured: 4 gates x 3 warps at 168 registers beat 5 gates at 128 registers (profiles/ab_r1.txt)
+constexpr int TWB_WORDS = rns::NP * 2 * 31 * 32 * 2; // per-lane pass-B twiddle table [prime][dir][31][32] of (w, w') = 47616 B
+constexpr int TWA_WORDS = rns::NP * 2 * 32 * 2;      // pass-A twiddles [prime][dir][32 (31 used)] of (w, w') staged in shared memory = 1536 B
+constexpr int TW_SMEM_BYTES = (TWB_WORDS + TWA_WORDS) * 4;
+
+// Warps per gate.  3: one warp per prime (32 coefficients per thread + both outputs' accumulators = 96 live registers,
+// 4 gates x 3 warps per SM at 168 registers).  6: one warp per (prime, output polynomial): the two warps of a prime split
+// the forward transforms by parity of the digit polynomial, exchange the transformed digits through their tiles, and each
+// accumulates and inverse-transforms ONE output with one Montgomery reduction per pair of products (64 live registers,
+// 2 gates x 6 warps per SM at 168 registers).  Measured (profiles/ab_r1.txt): 6 warps / 2 gates 22.3 k gates/s,
+// 3 warps / 4 gates 20.6 k, 6 warps / 3 gates (96 registers, spills) 20.7 k.
+#ifndef MK_WPG
+#define MK_WPG 6
 #endif
-constexpr int MAX_GPC = MK_MAX_GPC;                  // gates per CTA (named barriers 1..GPC)
+constexpr int WPG = MK_WPG;
+constexpr int TPG = 32 * WPG;                        // threads per gate
+#ifndef MK_MAX_GPC
+#define MK_MAX_GPC (MK_WPG == 6 ? 2 : 4)            // gates per CTA: 12 warps per SM so that each thread gets 168 registers
+#endif
+constexpr int MAX_GPC = MK_MAX_GPC;
+#ifndef MK_S_UNROLL
+#define MK_S_UNROLL (MK_WPG == 6 ? 1 : 2)           // unroll factor of the loop over digit polynomials
+#endif
+constexpr int S_UNROLL = MK_S_UNROLL;
+// register cap: the largest multiple of 8 with ceil(warps / 4) * 4 * 32 * regs <= 65536 (the register file is allocated in
+// units of 4 warps); 12 warps -> 168.  More registers measurably help even without spills (128: -7 %).
+#ifndef MK_MAXNREG
+#define MK_MAXNREG 168
+#endif
 
 __constant__ rns::Consts c_rns;
 
@@ -38,46 +60,15 @@ __constant__ rns::Consts c_rns;
 //   (out, src) -> reference part: body<-body part_1, body<-mask part_2, mask<-mask part_3, mask<-body part_4
 //   key slot: rns::key_slot(lane, c) of transformed position 32*lane + c; values NTT(K mod p) * N^-1 * 2^32 mod p
 __host__ __device__ inline size_t bsk_elem_words(int l) { return (size_t)rns::NP * 2 * l * 2 * N; }
-#ifndef MK_TILE_SETS
-#define MK_TILE_SETS 1      // 2: separate residue tiles per output polynomial -> 3 gate barriers per step instead of 5
-#endif
-constexpr int TILE_SETS = MK_TILE_SETS;
-#ifndef MK_S_UNROLL
-#define MK_S_UNROLL 2       // unroll factor of the loop over the 2l digit polynomials: 2 measured best (1: -2.7 %, 4: spills, -7 %)
-#endif
-constexpr int S_UNROLL = MK_S_UNROLL;
-constexpr int TWA_WORDS = rns::NP * 2 * 32 * 2;      // pass-A twiddles [prime][dir][32 (31 used)] of (w, w') staged in shared memory = 1536 B
-constexpr int TW_SMEM_BYTES = (TWB_WORDS + TWA_WORDS) * 4;
-__host__ __device__ inline size_t gate_smem_bytes(int l) {
-    return (size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)TILE_SETS * rns::NP * rns::TILE_WORDS * 4;
-}
-
-// Optional key staging by TMA (cp.async.bulk + mbarrier): each prime warp owns a 4 KB shared-memory slot into which the first
-// key polynomial (output 0) of the next digit polynomial is streamed while the warp is busy with the NTT; the second key
-// polynomial still arrives by LDG.128 (the compiler hoists those loads into pass B).  MEASURED AND REJECTED for now
-// (profiles/ab_r1.txt: 19.8 k vs 21.2 k gates/s): the key is L2-resident, ptxas already overlaps the LDGs with pass B, and the
-// 48 KB of slots push the register allocator into spills and shrink the L1.  Kept compilable (-DMK_TMA_KEY=1) because the
-// trade-off changes once more gates share one key fetch.
-#ifndef MK_TMA_KEY
-#define MK_TMA_KEY 0
-#endif
-constexpr int KSTAGE_BYTES = N * 4;                 // one key polynomial of one prime
-__host__ __device__ constexpr size_t gate_bytes_c(int l) {
-    return (size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)TILE_SETS * rns::NP * rns::TILE_WORDS * 4;
-}
+// per gate: Torus64 accumulator, packed digits, one padded tile per warp
+__host__ __device__ constexpr size_t gate_smem_bytes(int l) { return (size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)WPG * rns::TILE_WORDS * 4; }
 // gates per CTA: as many as fit in the 227 KB of shared memory beside the twiddle tables (at most MAX_GPC)
 __host__ __device__ constexpr int gpc_for(int l) {
     int g = MAX_GPC;
-    while (g > 1 && (size_t)TW_SMEM_BYTES + (size_t)g * ((size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)TILE_SETS * rns::NP * rns::TILE_WORDS * 4) > 227 * 1024) g--;
+    while (g > 1 && (size_t)TW_SMEM_BYTES + (size_t)g * gate_smem_bytes(l) > 227 * 1024) g--;
     return g;
 }
-
-__host__ __device__ constexpr bool tma_key_for(int l) {
-    return MK_TMA_KEY && (size_t)TW_SMEM_BYTES + (size_t)gpc_for(l) * (gate_bytes_c(l) + rns::NP * (KSTAGE_BYTES + 8)) <= 227 * 1024;
-}
-__host__ __device__ constexpr size_t cta_smem_bytes(int l) {
-    return (size_t)TW_SMEM_BYTES + (size_t)gpc_for(l) * (gate_bytes_c(l) + (tma_key_for(l) ? rns::NP * (KSTAGE_BYTES + 8) : 0));
-}
+__host__ __device__ constexpr size_t cta_smem_bytes(int l) { return (size_t)TW_SMEM_BYTES + (size_t)gpc_for(l) * gate_smem_bytes(l); }
 
 struct GateLinear {   // temp = mu0 + cx*x + cy*y + cz*z   (3gen_mk_gates.jl:8-74)
     int32_t mu0, cx, cy, cz;
@@ -108,32 +99,7 @@ __host__ __device__ inline GateLinear gate_linear(int gate) {
 }
 
 __device__ __forceinline__ void gate_barrier(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(TPG) : "memory"); }
-
-__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-// one elected lane: announce `bytes` on the barrier and start the bulk copy global -> shared that completes it
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // earlier generic reads of the slot before the async write
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra LAB_WAIT;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 // decode_message(x, 2N), numeric-functions.jl:70-73 (wrapping add, arithmetic shift)
 __device__ __forceinline__ int mod_switch_2N(int32_t x) {
@@ -179,158 +145,190 @@ __device__ __forceinline__ void warp_ntt_inv(u32 (&x)[32], u32* tile, const uint
     rns::inv_passA(x, twA, p);
 }
 
-// One external product (tgsw_extern_mul_3gen, tgsw_3gen.jl:102-113) on the accumulator held in shared memory, by the
-// 96 threads of one gate (gtid = 0..95, warp = prime).
+// Phase 1 of a step: rotate-subtract and gadget-decompose (tgsw.jl:112-138); digits biased to [0, Bg) and packed 4 per word
+// in the order the NTT warps read them (dig: [2L][8][32] words).
+template <int L, bool MUX>
+__device__ __forceinline__ void decompose_phase(const u64* __restrict__ acc, u32* __restrict__ dig, int a, int bgbit, int gtid) {
+    u64 off = 0;
+#pragma unroll
+    for (int q = 1; q <= L; q++) off += ((u64)1 << (64 - q * bgbit)) << (bgbit - 1);   // tgsw.jl:24-30
+    const u32 dmask = (1u << bgbit) - 1;
+    for (int task = gtid; task < 512; task += TPG) {
+        const int c = task >> 8, rh = (task >> 5) & 7, ln = task & 31;
+        const u64* poly = acc + c * N;
+        u32 packed[L];
+#pragma unroll
+        for (int q = 0; q < L; q++) packed[q] = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int i = 32 * (4 * rh + b) + ln;
+            u64 t;
+            if (MUX) {
+                const int idx = (i - a) & (2 * N - 1);        // (X^a * p)[i] = +-p[(i - a) mod 2N]
+                u64 v = poly[idx & (N - 1)];
+                if (idx & N) v = 0 - v;
+                t = v - poly[i];
+            } else {
+                t = poly[i];
+            }
+            t += off;
+#pragma unroll
+            for (int q = 0; q < L; q++) packed[q] |= ((u32)(t >> (64 - (q + 1) * bgbit)) & dmask) << (8 * b);
+        }
+        const int src = 1 - c;   // src 0 = body = acc[1]
+#pragma unroll
+        for (int q = 0; q < L; q++) dig[((src * L + q) * 8 + rh) * 32 + ln] = packed[q];
+    }
+}
+
+// digit polynomial s of this gate -> the 32 coefficients 32 r + lane of this thread, as residues in [0, 2p)
+__device__ __forceinline__ void load_digits(u32 (&x)[32], const u32* __restrict__ dig, int s, int lane, u32 bias) {
+#pragma unroll
+    for (int rh = 0; rh < 8; rh++) {
+        const u32 word = dig[(s * 8 + rh) * 32 + lane];
+#pragma unroll
+        for (int b = 0; b < 4; b++) x[4 * rh + b] = rns::alu_add((word >> (8 * b)) & 0xffu, bias);
+    }
+}
+
+// One external product (tgsw_extern_mul_3gen, tgsw_3gen.jl:102-113) on the accumulator held in shared memory, by the TPG
+// threads of one gate.
 //   MUX = true : acc += ExtProd(X^a * acc - acc, key)   (mk_mux_rotate_3gen, 3gen_mk_internals.jl:59-62)
 //   MUX = false: acc  = ExtProd(acc, key)
-// acc: [2][N] u64, [0] = mask, [1] = body.  dig: [2L][8][32] words of 4 biased digit bytes.  tiles: [3][TILE_WORDS].
-// kstage/kbar: this warp's TMA key slot and its mbarrier (nullptr when the staging is disabled); kphase: its parity bit.
+// acc: [2][N] u64, [0] = mask, [1] = body.  tiles: [WPG][TILE_WORDS].  bar_id: gate barrier; pbar_id: first pair barrier.
 template <int L, bool MUX>
 __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restrict__ dig, u32* __restrict__ tiles,
                                              const uint2_* __restrict__ twB, const u32* __restrict__ key, int a, int bgbit,
-                                             int bar_id, int gtid, u32* kstage, u64* kbar, u32& kphase) {
-    constexpr bool TMA = tma_key_for(L);
-    const int w = gtid >> 5, lane = gtid & 31;
-    if (TMA && lane == 0) tma_load_1d(kstage, key + (size_t)w * (2 * L * 2 * N), KSTAGE_BYTES, kbar);   // K[s = 0][out = 0]
-    // ---- phase 1: rotate-subtract and gadget-decompose (tgsw.jl:112-138); digits biased to [0, Bg) and packed 4 per word
-    {
-        u64 off = 0;
-#pragma unroll
-        for (int q = 1; q <= L; q++) off += ((u64)1 << (64 - q * bgbit)) << (bgbit - 1);   // tgsw.jl:24-30
-        const u32 dmask = (1u << bgbit) - 1;
-        for (int task = gtid; task < 512; task += TPG) {
-            const int c = task >> 8, rh = (task >> 5) & 7, ln = task & 31;
-            const u64* poly = acc + c * N;
-            u32 packed[L];
-#pragma unroll
-            for (int q = 0; q < L; q++) packed[q] = 0;
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const int i = 32 * (4 * rh + b) + ln;
-                u64 t;
-                if (MUX) {
-                    const int idx = (i - a) & (2 * N - 1);        // (X^a * p)[i] = +-p[(i - a) mod 2N]
-                    u64 v = poly[idx & (N - 1)];
-                    if (idx & N) v = 0 - v;
-                    t = v - poly[i];
-                } else {
-                    t = poly[i];
-                }
-                t += off;
-#pragma unroll
-                for (int q = 0; q < L; q++) packed[q] |= ((u32)(t >> (64 - (q + 1) * bgbit)) & dmask) << (8 * b);
-            }
-            const int src = 1 - c;   // src 0 = body = acc[1]
-#pragma unroll
-            for (int q = 0; q < L; q++) dig[((src * L + q) * 8 + rh) * 32 + ln] = packed[q];
-        }
-    }
+                                             int bar_id, int pbar_id, int gtid) {
+    const int gw = gtid >> 5, lane = gtid & 31;
+    const int w = WPG == 6 ? gw >> 1 : gw;            // prime of this warp
+    decompose_phase<L, MUX>(acc, dig, a, bgbit, gtid);
     gate_barrier(bar_id);
-    // ---- phase 2: per prime, forward NTT of each digit polynomial and multiply-accumulate with the key (NTT domain)
     const u32 p = c_rns.p[w], pinv = c_rns.pinv_neg[w];
-    u32* tile = tiles + w * rns::TILE_WORDS;
+    const u32 p4 = rns::keep_in_register(4 * p);
+    u32* tile = tiles + gw * rns::TILE_WORDS;
     const uint2_* twBf = twB + ((size_t)(w * 2 + 0) * 31) * 32 + lane;
     const uint2_* twBi = twB + ((size_t)(w * 2 + 1) * 31) * 32 + lane;
     const uint2_* twAf = twB + TWB_WORDS / 2 + (w * 2 + 0) * 32;
     const uint2_* twAi = twAf + 32;
-    const uint4* kp = reinterpret_cast<const uint4*>(key + (size_t)w * (2 * L * 2 * N)) + lane;
-    u32 acc0[32], acc1[32];
-#pragma unroll
-    for (int c = 0; c < 32; c++) acc0[c] = acc1[c] = 0;
+    const uint4* kp = reinterpret_cast<const uint4*>(key + (size_t)w * (2 * L * 2 * N)) + lane;   // K[prime][s][out][slot]
     const u32 bias = p - (1u << (bgbit - 1));
+    if (WPG == 6) {
+        // ---- phase 2 (6 warps): this warp transforms the digit polynomials of its parity, reads the partner's from the
+        // partner's tile, and accumulates output polynomial `o` for both, two products per Montgomery reduction
+        const int o = gw & 1;
+        const u32* ptile = tiles + (gw ^ 1) * rns::TILE_WORDS;
+        const int pb = pbar_id + w;
+        u32 accv[32];
+#pragma unroll
+        for (int c = 0; c < 32; c++) accv[c] = 0;
 #pragma unroll S_UNROLL
-    for (int s = 0; s < 2 * L; s++) {
-        u32 x[32];
+        for (int i = 0; i < L; i++) {
+            const int s_own = 2 * i + o, s_for = 2 * i + 1 - o;
+            u32 x[32];
+            load_digits(x, dig, s_own, lane, bias);
+            warp_ntt_fwd(x, tile, twAf, twBf, p, lane);
 #pragma unroll
-        for (int rh = 0; rh < 8; rh++) {
-            const u32 word = dig[(s * 8 + rh) * 32 + lane];
+            for (int c = 0; c < 32; c++) tile[c * 32 + lane] = x[c];
+            pair_barrier(pb);
+            const uint4* k_own = kp + (size_t)(s_own * 2 + o) * (N / 4);
+            const uint4* k_for = kp + (size_t)(s_for * 2 + o) * (N / 4);
 #pragma unroll
-            for (int b = 0; b < 4; b++) x[4 * rh + b] = rns::alu_add((word >> (8 * b)) & 0xffu, bias);
+            for (int q4 = 0; q4 < 8; q4++) {
+                const uint4 ka = __ldg(k_own + q4 * 32), kb = __ldg(k_for + q4 * 32);
+                accv[4 * q4 + 0] = rns::alu_add(accv[4 * q4 + 0], rns::mont_mul2(x[4 * q4 + 0], ka.x, ptile[(4 * q4 + 0) * 32 + lane], kb.x, p, pinv));
+                accv[4 * q4 + 1] = rns::alu_add(accv[4 * q4 + 1], rns::mont_mul2(x[4 * q4 + 1], ka.y, ptile[(4 * q4 + 1) * 32 + lane], kb.y, p, pinv));
+                accv[4 * q4 + 2] = rns::alu_add(accv[4 * q4 + 2], rns::mont_mul2(x[4 * q4 + 2], ka.z, ptile[(4 * q4 + 2) * 32 + lane], kb.z, p, pinv));
+                accv[4 * q4 + 3] = rns::alu_add(accv[4 * q4 + 3], rns::mont_mul2(x[4 * q4 + 3], ka.w, ptile[(4 * q4 + 3) * 32 + lane], kb.w, p, pinv));
+            }
+            pair_barrier(pb);                                  // both warps are done with each other's tile
         }
-        warp_ntt_fwd(x, tile, twAf, twBf, p, lane);
-        const uint4* k0 = kp + (size_t)(s * 2) * (N / 4);
-        if (TMA) {
-            mbar_wait(kbar, kphase);
-            kphase ^= 1;
-        }
-#pragma unroll
-        for (int q4 = 0; q4 < 8; q4++) {
-            const uint4 kv = TMA ? reinterpret_cast<const uint4*>(kstage)[q4 * 32 + lane] : __ldg(k0 + q4 * 32);
-            acc0[4 * q4 + 0] = rns::alu_add(acc0[4 * q4 + 0], rns::mont_mul(x[4 * q4 + 0], kv.x, p, pinv));
-            acc0[4 * q4 + 1] = rns::alu_add(acc0[4 * q4 + 1], rns::mont_mul(x[4 * q4 + 1], kv.y, p, pinv));
-            acc0[4 * q4 + 2] = rns::alu_add(acc0[4 * q4 + 2], rns::mont_mul(x[4 * q4 + 2], kv.z, p, pinv));
-            acc0[4 * q4 + 3] = rns::alu_add(acc0[4 * q4 + 3], rns::mont_mul(x[4 * q4 + 3], kv.w, p, pinv));
-        }
-        const uint4* k1 = k0 + N / 4;
-        if (TMA && s + 1 < 2 * L) {      // the slot has been consumed by every lane: stream K[s + 1][out = 0] into it
-            __syncwarp();
-            if (lane == 0) tma_load_1d(kstage, key + (size_t)w * (2 * L * 2 * N) + (size_t)(s + 1) * 2 * N, KSTAGE_BYTES, kbar);
-        }
-#pragma unroll
-        for (int q4 = 0; q4 < 8; q4++) {
-            const uint4 kv = __ldg(k1 + q4 * 32);
-            acc1[4 * q4 + 0] = rns::alu_add(acc1[4 * q4 + 0], rns::mont_mul(x[4 * q4 + 0], kv.x, p, pinv));
-            acc1[4 * q4 + 1] = rns::alu_add(acc1[4 * q4 + 1], rns::mont_mul(x[4 * q4 + 1], kv.y, p, pinv));
-            acc1[4 * q4 + 2] = rns::alu_add(acc1[4 * q4 + 2], rns::mont_mul(x[4 * q4 + 2], kv.z, p, pinv));
-            acc1[4 * q4 + 3] = rns::alu_add(acc1[4 * q4 + 3], rns::mont_mul(x[4 * q4 + 3], kv.w, p, pinv));
-        }
-    }
-    // ---- phase 3: per output polynomial, inverse NTT of the three residue polynomials, Garner CRT, accumulator update
-    const u32 p4 = rns::keep_in_register(4 * p);
-#pragma unroll 1
-    for (int out = 0; out < 2; out++) {
+        // ---- phase 3 (6 warps): inverse transform of this warp's residue polynomial; then CRT of both outputs by the whole gate
         u32 x[32];
 #pragma unroll
         for (int c = 0; c < 32; c++) {
-            u32 v = out ? acc1[c] : acc0[c];                 // sum of 2L products, each in [0, 2p)
+            u32 v = accv[c];                                   // sum of L double products, each < 2.75p
             if (L > 2) v = rns::umin32(v, v - 2 * p4);
-            x[c] = rns::umin32(v, v - p4);                   // [0, 4p)
+            x[c] = rns::umin32(v, v - p4);                     // [0, 4p)
         }
-        u32* otile = TILE_SETS == 2 ? tile + out * (rns::NP * rns::TILE_WORDS) : tile;
-        warp_ntt_inv(x, otile, twAi, twBi, p, lane);
+        warp_ntt_inv(x, tile, twAi, twBi, p, lane);
 #pragma unroll
-        for (int r = 0; r < 32; r++) otile[32 * r + lane] = x[r];   // residues in coefficient order
-        if (TILE_SETS == 2 && out == 0) continue;
+        for (int r = 0; r < 32; r++) tile[32 * r + lane] = x[r];   // residues in coefficient order
         gate_barrier(bar_id);
-        for (int o = (TILE_SETS == 2 ? 0 : out); o <= out; o++) {
-            const u32* rt = TILE_SETS == 2 ? tiles + o * (rns::NP * rns::TILE_WORDS) : tiles;
-            u64* ap = acc + o * N;
-            for (int i = gtid; i < N; i += TPG) {
-                const u64 R = rns::crt_lift(rt[i], rt[rns::TILE_WORDS + i], rt[2 * rns::TILE_WORDS + i], c_rns.crt);
-                ap[i] = MUX ? ap[i] + R : R;
+        for (int idx = gtid; idx < 2 * N; idx += TPG) {
+            const int oo = idx >> 10, i = idx & (N - 1);
+            const u32* rt = tiles + oo * rns::TILE_WORDS;      // tile of warp (prime w', output oo) = tiles[(2 w' + oo)]
+            const u64 R = rns::crt_lift(rt[i], rt[2 * rns::TILE_WORDS + i], rt[4 * rns::TILE_WORDS + i], c_rns.crt);
+            acc[idx] = MUX ? acc[idx] + R : R;
+        }
+        gate_barrier(bar_id);
+    } else {
+        // ---- phase 2 (3 warps): per prime, forward NTT of each digit polynomial and multiply-accumulate with the key
+        u32 acc0[32], acc1[32];
+#pragma unroll
+        for (int c = 0; c < 32; c++) acc0[c] = acc1[c] = 0;
+#pragma unroll S_UNROLL
+        for (int s = 0; s < 2 * L; s++) {
+            u32 x[32];
+            load_digits(x, dig, s, lane, bias);
+            warp_ntt_fwd(x, tile, twAf, twBf, p, lane);
+            const uint4* k0 = kp + (size_t)(s * 2) * (N / 4);
+#pragma unroll
+            for (int q4 = 0; q4 < 8; q4++) {
+                const uint4 kv = __ldg(k0 + q4 * 32);
+                acc0[4 * q4 + 0] = rns::alu_add(acc0[4 * q4 + 0], rns::mont_mul(x[4 * q4 + 0], kv.x, p, pinv));
+                acc0[4 * q4 + 1] = rns::alu_add(acc0[4 * q4 + 1], rns::mont_mul(x[4 * q4 + 1], kv.y, p, pinv));
+                acc0[4 * q4 + 2] = rns::alu_add(acc0[4 * q4 + 2], rns::mont_mul(x[4 * q4 + 2], kv.z, p, pinv));
+                acc0[4 * q4 + 3] = rns::alu_add(acc0[4 * q4 + 3], rns::mont_mul(x[4 * q4 + 3], kv.w, p, pinv));
+            }
+            const uint4* k1 = k0 + N / 4;
+#pragma unroll
+            for (int q4 = 0; q4 < 8; q4++) {
+                const uint4 kv = __ldg(k1 + q4 * 32);
+                acc1[4 * q4 + 0] = rns::alu_add(acc1[4 * q4 + 0], rns::mont_mul(x[4 * q4 + 0], kv.x, p, pinv));
+                acc1[4 * q4 + 1] = rns::alu_add(acc1[4 * q4 + 1], rns::mont_mul(x[4 * q4 + 1], kv.y, p, pinv));
+                acc1[4 * q4 + 2] = rns::alu_add(acc1[4 * q4 + 2], rns::mont_mul(x[4 * q4 + 2], kv.z, p, pinv));
+                acc1[4 * q4 + 3] = rns::alu_add(acc1[4 * q4 + 3], rns::mont_mul(x[4 * q4 + 3], kv.w, p, pinv));
             }
         }
-        gate_barrier(bar_id);
+        // ---- phase 3 (3 warps): per output polynomial, inverse NTT of the three residue polynomials, Garner CRT, update
+#pragma unroll 1
+        for (int out = 0; out < 2; out++) {
+            u32 x[32];
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                u32 v = out ? acc1[c] : acc0[c];                 // sum of 2L products, each in [0, 2p)
+                if (L > 2) v = rns::umin32(v, v - 2 * p4);
+                x[c] = rns::umin32(v, v - p4);                   // [0, 4p)
+            }
+            warp_ntt_inv(x, tile, twAi, twBi, p, lane);
+#pragma unroll
+            for (int r = 0; r < 32; r++) tile[32 * r + lane] = x[r];   // residues in coefficient order
+            gate_barrier(bar_id);
+            u64* ap = acc + out * N;
+            for (int i = gtid; i < N; i += TPG) {
+                const u64 R = rns::crt_lift(tiles[i], tiles[rns::TILE_WORDS + i], tiles[2 * rns::TILE_WORDS + i], c_rns.crt);
+                ap[i] = MUX ? ap[i] + R : R;
+            }
+            gate_barrier(bar_id);
+        }
     }
 }
 
-// GPC gates per CTA, 3 warps per gate.  Accumulators resident in shared memory for all k*n steps.
+// GPC gates per CTA, WPG warps per gate.  Accumulators resident in shared memory for all k*n steps.
 template <int L, int GPC>
-__global__ void __launch_bounds__(GPC* TPG, 1) blind_rotate_kernel(BlindRotateArgs p) {
+__global__ void __maxnreg__(MK_MAXNREG) blind_rotate_kernel(BlindRotateArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2_* twB = reinterpret_cast<uint2_*>(smem_raw);
     stage_twiddles(twB, p.twB);
     __syncthreads();
-    const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot;
+    const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot, pbar_id = 1 + GPC + slot * rns::NP;
     const int g = blockIdx.x * GPC + slot;
     if (g >= p.G) return;   // no CTA-wide barrier below this line
     unsigned char* base = smem_raw + TW_SMEM_BYTES + (size_t)slot * gate_smem_bytes(L);
     u64* acc = reinterpret_cast<u64*>(base);
     u32* dig = reinterpret_cast<u32*>(base + 2 * N * 8);
     u32* tiles = dig + 2 * L * (N / 4);
-    // TMA key slots and their mbarriers live after the GPC gate regions
-    unsigned char* kbase = smem_raw + TW_SMEM_BYTES + (size_t)GPC * gate_smem_bytes(L);
-    const int gw = (slot * TPG + gtid) >> 5;    // warp index inside the CTA
-    u32* kstage = reinterpret_cast<u32*>(kbase + (size_t)gw * KSTAGE_BYTES);
-    u64* kbar = reinterpret_cast<u64*>(kbase + (size_t)GPC * rns::NP * KSTAGE_BYTES) + gw;
-    u32 kphase = 0;
-    if (tma_key_for(L)) {
-        if ((gtid & 31) == 0) {
-            mbar_init(kbar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
-    }
     const int kn = p.k * p.n;
     // gate prologue (3gen_mk_gates.jl) + mod switch (3gen_mk_internals.jl:102-103); every thread of the gate computes
     // the same rotation amounts from broadcast loads
@@ -360,7 +358,7 @@ __global__ void __launch_bounds__(GPC* TPG, 1) blind_rotate_kernel(BlindRotateAr
         const int a = a_next;
         if (it + 1 < kn) a_next = rotation(p.xa, p.ya, p.za, abase + it + 1, 0u);
         if (a == 0) continue;   // :69 (uniform across the gate)
-        extprod_step<L, true>(acc, dig, tiles, twB, p.bsk + (size_t)it * estride, a, p.bgbit, bar_id, gtid, kstage, kbar, kphase);
+        extprod_step<L, true>(acc, dig, tiles, twB, p.bsk + (size_t)it * estride, a, p.bgbit, bar_id, pbar_id, gtid);
     }
     // rlwe_extract_sample_64 (rlwe.jl:70-74): a'_0 = mask_0, a'_i = -mask_{N-i}, b' = body_0
     int32_t* ext = p.ext_out + (size_t)g * (N + 1);
@@ -377,34 +375,22 @@ __global__ void __launch_bounds__(GPC* TPG, 1) blind_rotate_kernel(BlindRotateAr
 
 // parity hook: acc_out[g] = ExtProd(acc_in[g], bsk[elem[g]])
 template <int L, int GPC>
-__global__ void __launch_bounds__(GPC* TPG, 1) extprod_kernel(int G, const u32* bsk, const uint2_* twB_g, int bgbit, const int32_t* elem,
+__global__ void __maxnreg__(MK_MAXNREG) extprod_kernel(int G, const u32* bsk, const uint2_* twB_g, int bgbit, const int32_t* elem,
                                                                const int64_t* acc_in, int64_t* acc_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2_* twB = reinterpret_cast<uint2_*>(smem_raw);
     stage_twiddles(twB, twB_g);
     __syncthreads();
-    const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot;
+    const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot, pbar_id = 1 + GPC + slot * rns::NP;
     const int g = blockIdx.x * GPC + slot;
     if (g >= G) return;
     unsigned char* base = smem_raw + TW_SMEM_BYTES + (size_t)slot * gate_smem_bytes(L);
     u64* acc = reinterpret_cast<u64*>(base);
     u32* dig = reinterpret_cast<u32*>(base + 2 * N * 8);
     u32* tiles = dig + 2 * L * (N / 4);
-    unsigned char* kbase = smem_raw + TW_SMEM_BYTES + (size_t)GPC * gate_smem_bytes(L);
-    const int gw = (slot * TPG + gtid) >> 5;
-    u32* kstage = reinterpret_cast<u32*>(kbase + (size_t)gw * KSTAGE_BYTES);
-    u64* kbar = reinterpret_cast<u64*>(kbase + (size_t)GPC * rns::NP * KSTAGE_BYTES) + gw;
-    u32 kphase = 0;
-    if (tma_key_for(L)) {
-        if ((gtid & 31) == 0) {
-            mbar_init(kbar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
-    }
     for (int i = gtid; i < 2 * N; i += TPG) acc[i] = (u64)acc_in[(size_t)g * 2 * N + i];
     gate_barrier(bar_id);
-    extprod_step<L, false>(acc, dig, tiles, twB, bsk + (size_t)elem[g] * bsk_elem_words(L), 0, bgbit, bar_id, gtid, kstage, kbar, kphase);
+    extprod_step<L, false>(acc, dig, tiles, twB, bsk + (size_t)elem[g] * bsk_elem_words(L), 0, bgbit, bar_id, pbar_id, gtid);
     for (int i = gtid; i < 2 * N; i += TPG) acc_out[(size_t)g * 2 * N + i] = (int64_t)acc[i];
 }
 
@@ -435,7 +421,8 @@ __global__ void __launch_bounds__(XF_WARPS * 32) bsk_transform_kernel(const int6
 }
 
 // parity hook and key-generation primitive: exact c = a * b mod (X^N + 1, 2^64) for |a_i| <= 2^8; 3 warps = 3 primes
-__global__ void __launch_bounds__(TPG) negacyclic_mul_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ b, int64_t* __restrict__ c,
+constexpr int NM_THREADS = 32 * rns::NP;
+__global__ void __launch_bounds__(NM_THREADS) negacyclic_mul_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ b, int64_t* __restrict__ c,
                                                               const uint2_* __restrict__ twB) {
     __shared__ u32 tiles[rns::NP * rns::TILE_WORDS];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -461,7 +448,7 @@ __global__ void __launch_bounds__(TPG) negacyclic_mul_kernel(const int64_t* __re
 #pragma unroll
     for (int r = 0; r < 32; r++) tile[32 * r + lane] = x[r];
     __syncthreads();
-    for (int i = threadIdx.x; i < N; i += TPG)
+    for (int i = threadIdx.x; i < N; i += NM_THREADS)
         c[g * N + i] = (int64_t)rns::crt_lift(tiles[i], tiles[rns::TILE_WORDS + i], tiles[2 * rns::TILE_WORDS + i], c_rns.crt);
 }
 

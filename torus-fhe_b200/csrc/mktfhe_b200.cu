@@ -475,7 +475,7 @@ int mktfhe_negacyclic_mul_batch(mktfhe_ctx* c, size_t G, const int64_t* a, const
     const size_t bytes = G * mk::N * 8;
     int rc;
     if ((rc = stage_in(c, c->accin, a, bytes)) || (rc = stage_in(c, c->raw, b, bytes)) || (rc = reserve(c, c->accout, bytes))) return rc;
-    mk::negacyclic_mul_kernel<<<(unsigned)G, mk::TPG, 0, c->stream>>>((const int64_t*)c->accin.p, (const int64_t*)c->raw.p, (int64_t*)c->accout.p,
+    mk::negacyclic_mul_kernel<<<(unsigned)G, mk::NM_THREADS, 0, c->stream>>>((const int64_t*)c->accin.p, (const int64_t*)c->raw.p, (int64_t*)c->accout.p,
                                                                       c->d_twB);
     c->launches++;
     CU_TRY(c, cudaGetLastError());

@@ -87,6 +87,14 @@ MK_HD u32 mont_mul(u32 d, u32 k, u32 p, u32 pinv_neg) {
     return (u32)((prod + (u64)m * p) >> 32);
 }
 
+// (d1 * k1 + d2 * k2) * 2^-32 mod p with ONE reduction: d < 2^32, k < p < 2^28, so the sum is < 2^61; result < 2.75p when
+// d1, d2 < 14p (the forward transform's output range)
+MK_HD u32 mont_mul2(u32 d1, u32 k1, u32 d2, u32 k2, u32 p, u32 pinv_neg) {
+    const u64 prod = (u64)d1 * k1 + (u64)d2 * k2;
+    const u32 m = (u32)prod * pinv_neg;
+    return (u32)((prod + (u64)m * p) >> 32);
+}
+
 // 32-point in-register networks.  x[j] are the 32 elements a thread owns; stage k (k = 0..4) pairs
 // elements at gap g = 16 >> k inside blocks of 2g; the twiddle of block b is entry e = 2^k - 1 + b of a
 // 31-entry table that `tw(e)` returns (uniform across the warp in the pass over the high index bits,
