@@ -284,7 +284,8 @@ def run_ours(args):
                              "frac": achieved / hbm_peak, "traffic": ncu_traffic["bytes"], "traffic_note": ncu_traffic, "peak_source": peak_src,
                              "note": "contract roofline (HBM); the kernel is IMAD-pipe bound and streams the key from L2 (hit rate 97.8 %): see integer_bound",
                              "algorithmic_bytes_per_gate": bsk_1limb + ct_io, "streamed_bytes_per_gate_this_build": bsk_stream,
-                             "kernel_ms": br_ms, "keyswitch_ms": ks_ms, "keyswitch_gather_GBps": G * ksk_gather / (ks_ms * 1e-3) / 1e9,
+                             "kernel_ms": br_ms, "keyswitch_ms": ks_ms, "keyswitch_gather_GBps": (G * ksk_gather / (ks_ms * 1e-3) / 1e9) if ks_ms > 0.05 else None,
+                             "keyswitch_fused_into_blind_rotate": ks_ms <= 0.05,
                              "kernel_share_of_step": br_ms / (ms / args.steps),
                              "integer_bound": {"bound": "imad_pipe", "algorithmic_slots_per_gate": imad_slots,
                                                "achieved": G * imad_slots / (br_ms * 1e-3) / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-slots/s",

@@ -82,8 +82,12 @@ struct BlindRotateArgs {
     GateLinear lin;
     const int32_t* gate_ids;   // [G] per-gate ids (mixed batches) or nullptr: every gate uses `lin`
     int64_t mu;
-    int32_t* ext_out;   // [G][N+1]
+    int32_t* ext_out;   // [G][N+1] extracted samples, or nullptr
     int64_t* acc_out;   // [G][2][N] or nullptr
+    // fused key switch (epilogue of the same kernel): ksk [k][N][t][B-1][n+1] followed by one all-zero row
+    const int32_t* ksk; // nullptr: no key switch in this launch
+    int ks_t, ks_basebit;
+    int32_t *oa, *ob;   // [G][k][n], [G]
 };
 
 // linear prologue constants of the five bootstrapped gates, 3gen_mk_gates.jl:8-74 (encode_message(m, S) = m << (32 - log2 S))
@@ -315,6 +319,63 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
     }
 }
 
+// Sample extraction + multi-key LWE key switch of ONE gate by its TPG threads, as the epilogue of the blind rotation
+// (rlwe_extract_sample_64 rlwe.jl:70-74, mk_keyswitch_3gen mk_internals.jl:730-744, keyswitch keyswitch.jl:45-80).
+// The gather of k*N*t rows (11.2 MB from L2 at the 2-party parameters) is latency/LSU work; fused here it overlaps with the
+// IMAD-bound steps of the other gate on the SM instead of running as a separate 4 %-of-step kernel.
+// Thread `gtid` owns output columns gtid, gtid + TPG, ... (NCOL of them); zero digits read the all-zero row instead of
+// branching, so the T * 4 row reads of four consecutive coefficients are all in flight together.
+constexpr int KSF_NCOL = 3;
+__host__ __device__ constexpr bool ks_fusable(int n, int t) { return n + 1 <= KSF_NCOL * TPG && (t == 3 || t == 5); }
+template <int T>
+__device__ __forceinline__ void fused_keyswitch(const u64* __restrict__ acc, u32* __restrict__ s_a, const BlindRotateArgs& p, int g, int gtid,
+                                                int bar_id) {
+    const int n = p.n, row = n + 1, bb = p.ks_basebit, B1 = (1 << bb) - 1;
+    const uint32_t prec_offset = 1u << (32 - (1 + bb * T));   // keyswitch.jl:58
+    for (int i = gtid; i < N; i += TPG) {
+        const u64 v = i == 0 ? acc[0] : (u64)0 - acc[N - i];
+        const int32_t ai = t64tot32((int64_t)v);
+        if (p.ext_out) p.ext_out[(size_t)g * (N + 1) + i] = ai;
+        s_a[i] = (uint32_t)ai + prec_offset;                  // :59
+    }
+    const int32_t eb = t64tot32((int64_t)acc[N]);
+    if (p.ext_out && gtid == 0) p.ext_out[(size_t)g * (N + 1) + N] = eb;
+    gate_barrier(bar_id);
+    const size_t party_words = (size_t)N * T * B1 * row;
+    const int32_t* zero_row = p.ksk + (size_t)p.k * party_words;
+    uint32_t bsum = 0;
+    for (int party = 0; party < p.k; party++) {
+        uint32_t out[KSF_NCOL];
+#pragma unroll
+        for (int c = 0; c < KSF_NCOL; c++) out[c] = 0;
+        const int32_t* rows = p.ksk + (size_t)party * party_words;
+#pragma unroll 1
+        for (int i = 0; i < N; i += 4) {
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++) {
+                const uint32_t ai = s_a[i + ii];
+#pragma unroll
+                for (int j = 1; j <= T; j++) {
+                    const uint32_t d = (ai >> (32 - j * bb)) & (uint32_t)B1;   // :65-67
+                    const int32_t* r = d ? rows + (((size_t)(i + ii) * T + (j - 1)) * B1 + (d - 1)) * row : zero_row;   // :74-76
+#pragma unroll
+                    for (int c = 0; c < KSF_NCOL; c++) {
+                        const int col = gtid + c * TPG;
+                        if (col < row) out[c] -= (uint32_t)__ldg(r + col);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < KSF_NCOL; c++) {
+            const int col = gtid + c * TPG;
+            if (col < n) p.oa[((size_t)g * p.k + party) * n + col] = (int32_t)out[c];
+            if (col == n) bsum += out[c];
+        }
+    }
+    if (gtid == n % TPG) p.ob[g] = (int32_t)((uint32_t)eb + bsum);   // thread owning column n
+}
+
 // GPC gates per CTA, WPG warps per gate.  Accumulators resident in shared memory for all k*n steps.
 template <int L, int GPC>
 __global__ void __maxnreg__(MK_MAXNREG) blind_rotate_kernel(BlindRotateArgs p) {
@@ -360,6 +421,15 @@ __global__ void __maxnreg__(MK_MAXNREG) blind_rotate_kernel(BlindRotateArgs p) {
         if (a == 0) continue;   // :69 (uniform across the gate)
         extprod_step<L, true>(acc, dig, tiles, twB, p.bsk + (size_t)it * estride, a, p.bgbit, bar_id, pbar_id, gtid);
     }
+    if (p.acc_out) {
+        int64_t* ao = p.acc_out + (size_t)g * 2 * N;
+        for (int i = gtid; i < 2 * N; i += TPG) ao[i] = (int64_t)acc[i];
+    }
+    if (p.ksk) {   // fused extraction + key switch (the host only sets ksk when ks_fusable(n, t))
+        if (p.ks_t == 3) fused_keyswitch<3>(acc, tiles, p, g, gtid, bar_id);
+        else fused_keyswitch<5>(acc, tiles, p, g, gtid, bar_id);
+        return;
+    }
     // rlwe_extract_sample_64 (rlwe.jl:70-74): a'_0 = mask_0, a'_i = -mask_{N-i}, b' = body_0
     int32_t* ext = p.ext_out + (size_t)g * (N + 1);
     for (int i = gtid; i < N; i += TPG) {
@@ -367,10 +437,6 @@ __global__ void __maxnreg__(MK_MAXNREG) blind_rotate_kernel(BlindRotateArgs p) {
         ext[i] = t64tot32((int64_t)v);
     }
     if (gtid == 0) ext[N] = t64tot32((int64_t)acc[N]);
-    if (p.acc_out) {
-        int64_t* ao = p.acc_out + (size_t)g * 2 * N;
-        for (int i = gtid; i < 2 * N; i += TPG) ao[i] = (int64_t)acc[i];
-    }
 }
 
 // parity hook: acc_out[g] = ExtProd(acc_in[g], bsk[elem[g]])

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -40,6 +41,7 @@ struct mktfhe_ctx {
     size_t ksk_bytes = 0;
     rns::uint2_* d_twB = nullptr;
     int gpc = 1;                 // gates per CTA of the blind-rotate / external-product kernels
+    bool fuse_ks = true;         // key switch as the epilogue of the blind-rotate kernel (MKTFHE_B200_FUSE_KS=0 disables: A/B runs)
     std::vector<char> bsk_loaded, ksk_loaded;
     bool ready = false;
     DevBuf in[6], ext, oa, ob, accin, accout, elem, raw, gids;
@@ -136,7 +138,7 @@ int run_bootstrap_dev(mktfhe_ctx* c, mk::GateLinear lin, int64_t mu, size_t G, c
     cudaStream_t saved = c->stream;
     if (st) c->stream = st;
     int32_t* ext = ext_out;
-    if (!ext) {
+    if (!ext && !(do_keyswitch && c->fuse_ks && mk::ks_fusable(c->prm.n, c->prm.t))) {
         int rc = reserve(c, c->ext, G * (mk::N + 1) * sizeof(int32_t));
         if (rc) { c->stream = saved; return rc; }
         ext = (int32_t*)c->ext.p;
@@ -146,11 +148,16 @@ int run_bootstrap_dev(mktfhe_ctx* c, mk::GateLinear lin, int64_t mu, size_t G, c
     a.bsk = c->d_bsk; a.twB = c->d_twB;
     a.xa = xa; a.xb = xb; a.ya = ya; a.yb = yb; a.za = za; a.zb = zb;
     a.lin = lin; a.gate_ids = gate_ids; a.mu = mu; a.ext_out = ext; a.acc_out = acc_out;
+    const bool fuse = do_keyswitch && c->fuse_ks && mk::ks_fusable(c->prm.n, c->prm.t);
+    if (fuse) {
+        a.ksk = c->d_ksk; a.ks_t = c->prm.t; a.ks_basebit = c->prm.basebit; a.oa = oa; a.ob = ob;
+        if (!ext_out) a.ext_out = nullptr;   // nobody asked for the extracted samples
+    }
     cudaEventRecord(c->ev[0], c->stream);
     launch_blind_rotate(c, a, G);
     cudaEventRecord(c->ev[1], c->stream);
     cudaEventRecord(c->ev[2], c->stream);
-    if (do_keyswitch) {
+    if (do_keyswitch && !fuse) {
         mk::keyswitch_kernel<<<(unsigned)G, mk::KS_THREADS, 0, c->stream>>>(c->prm.n, c->prm.k, c->prm.t, c->prm.basebit, c->d_ksk, ext, oa, ob);
         c->launches++;
     }
@@ -199,9 +206,12 @@ int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
     const int B1 = (1 << params->basebit) - 1;
     c->bsk_bytes = (size_t)params->k * params->n * mk::bsk_elem_words(params->l) * sizeof(u32);
     c->gpc = mk::gpc_for(params->l);
+    if (const char* e = getenv("MKTFHE_B200_FUSE_KS")) c->fuse_ks = atoi(e) != 0;
     c->ksk_bytes = (size_t)params->k * mk::N * params->t * B1 * (params->n + 1) * sizeof(int32_t);
     CREATE_TRY(cudaMalloc(&c->d_bsk, c->bsk_bytes));
-    CREATE_TRY(cudaMalloc(&c->d_ksk, c->ksk_bytes));
+    // the key-switching key is followed by one all-zero row (read by the fused key switch for zero digits)
+    CREATE_TRY(cudaMalloc(&c->d_ksk, c->ksk_bytes + (size_t)(params->n + 1) * sizeof(int32_t)));
+    CREATE_TRY(cudaMemset((char*)c->d_ksk + c->ksk_bytes, 0, (size_t)(params->n + 1) * sizeof(int32_t)));
     CREATE_TRY(cudaMalloc(&c->d_twB, (size_t)mk::TWB_WORDS * 4));
     {
         rns::HostTables T;
