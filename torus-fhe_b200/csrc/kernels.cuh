@@ -60,6 +60,9 @@ __constant__ rns::Consts c_rns;
 //   (out, src) -> reference part: body<-body part_1, body<-mask part_2, mask<-mask part_3, mask<-body part_4
 //   key slot: rns::key_slot(lane, c) of transformed position 32*lane + c; values NTT(K mod p) * N^-1 * 2^32 mod p
 __host__ __device__ inline size_t bsk_elem_words(int l) { return (size_t)rns::NP * 2 * l * 2 * N; }
+// KSK device layout: int32 [party][N][t][B-1][ks_row_stride(n)] -- rows (a[0..n-1], b) padded to a multiple of 4 words so that a
+// row is read with 16-byte loads -- followed by one all-zero row
+__host__ __device__ constexpr int ks_row_stride(int n) { return (n + 1 + 3) & ~3; }
 // per gate: Torus64 accumulator, packed digits, one padded tile per warp
 __host__ __device__ constexpr size_t gate_smem_bytes(int l) { return (size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)WPG * rns::TILE_WORDS * 4; }
 // gates per CTA: as many as fit in the 227 KB of shared memory beside the twiddle tables (at most MAX_GPC)
@@ -84,7 +87,7 @@ struct BlindRotateArgs {
     int64_t mu;
     int32_t* ext_out;   // [G][N+1] extracted samples, or nullptr
     int64_t* acc_out;   // [G][2][N] or nullptr
-    // fused key switch (epilogue of the same kernel): ksk [k][N][t][B-1][n+1] followed by one all-zero row
+    // fused key switch (epilogue of the same kernel): ksk [k][N][t][B-1][ks_row_stride(n)] followed by one all-zero row
     const int32_t* ksk; // nullptr: no key switch in this launch
     int ks_t, ks_basebit;
     int32_t *oa, *ob;   // [G][k][n], [G]
@@ -323,14 +326,13 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
 // (rlwe_extract_sample_64 rlwe.jl:70-74, mk_keyswitch_3gen mk_internals.jl:730-744, keyswitch keyswitch.jl:45-80).
 // The gather of k*N*t rows (11.2 MB from L2 at the 2-party parameters) is latency/LSU work; fused here it overlaps with the
 // IMAD-bound steps of the other gate on the SM instead of running as a separate 4 %-of-step kernel.
-// Thread `gtid` owns output columns gtid, gtid + TPG, ... (NCOL of them); zero digits read the all-zero row instead of
-// branching, so the T * 4 row reads of four consecutive coefficients are all in flight together.
-constexpr int KSF_NCOL = 3;
-__host__ __device__ constexpr bool ks_fusable(int n, int t) { return n + 1 <= KSF_NCOL * TPG && (t == 3 || t == 5); }
+// Thread `gtid` owns the four output columns 4*gtid .. 4*gtid+3 (one LDG.128 per row); zero digits read the all-zero row
+// instead of branching, so the 4 * T row reads of four consecutive coefficients are all in flight together.
+__host__ __device__ constexpr bool ks_fusable(int n, int t) { return ks_row_stride(n) <= 4 * TPG && (t == 3 || t == 5); }
 template <int T>
 __device__ __forceinline__ void fused_keyswitch(const u64* __restrict__ acc, u32* __restrict__ s_a, const BlindRotateArgs& p, int g, int gtid,
                                                 int bar_id) {
-    const int n = p.n, row = n + 1, bb = p.ks_basebit, B1 = (1 << bb) - 1;
+    const int n = p.n, stride = ks_row_stride(n), bb = p.ks_basebit, B1 = (1 << bb) - 1;
     const uint32_t prec_offset = 1u << (32 - (1 + bb * T));   // keyswitch.jl:58
     for (int i = gtid; i < N; i += TPG) {
         const u64 v = i == 0 ? acc[0] : (u64)0 - acc[N - i];
@@ -341,13 +343,13 @@ __device__ __forceinline__ void fused_keyswitch(const u64* __restrict__ acc, u32
     const int32_t eb = t64tot32((int64_t)acc[N]);
     if (p.ext_out && gtid == 0) p.ext_out[(size_t)g * (N + 1) + N] = eb;
     gate_barrier(bar_id);
-    const size_t party_words = (size_t)N * T * B1 * row;
-    const int32_t* zero_row = p.ksk + (size_t)p.k * party_words;
+    const int col0 = 4 * gtid;
+    if (col0 >= stride) return;                               // no barrier below: idle threads may leave
+    const size_t party_words = (size_t)N * T * B1 * stride;
+    const uint4* zero_row = reinterpret_cast<const uint4*>(p.ksk + (size_t)p.k * party_words) + gtid;
     uint32_t bsum = 0;
     for (int party = 0; party < p.k; party++) {
-        uint32_t out[KSF_NCOL];
-#pragma unroll
-        for (int c = 0; c < KSF_NCOL; c++) out[c] = 0;
+        uint4 out = make_uint4(0, 0, 0, 0);
         const int32_t* rows = p.ksk + (size_t)party * party_words;
 #pragma unroll 1
         for (int i = 0; i < N; i += 4) {
@@ -357,23 +359,22 @@ __device__ __forceinline__ void fused_keyswitch(const u64* __restrict__ acc, u32
 #pragma unroll
                 for (int j = 1; j <= T; j++) {
                     const uint32_t d = (ai >> (32 - j * bb)) & (uint32_t)B1;   // :65-67
-                    const int32_t* r = d ? rows + (((size_t)(i + ii) * T + (j - 1)) * B1 + (d - 1)) * row : zero_row;   // :74-76
-#pragma unroll
-                    for (int c = 0; c < KSF_NCOL; c++) {
-                        const int col = gtid + c * TPG;
-                        if (col < row) out[c] -= (uint32_t)__ldg(r + col);
-                    }
+                    const uint4* r = d ? reinterpret_cast<const uint4*>(rows + (((size_t)(i + ii) * T + (j - 1)) * B1 + (d - 1)) * stride) + gtid
+                                       : zero_row;                              // :74-76
+                    const uint4 v = __ldg(r);
+                    out.x -= v.x; out.y -= v.y; out.z -= v.z; out.w -= v.w;
                 }
             }
         }
+        const uint32_t o4[4] = {out.x, out.y, out.z, out.w};
 #pragma unroll
-        for (int c = 0; c < KSF_NCOL; c++) {
-            const int col = gtid + c * TPG;
-            if (col < n) p.oa[((size_t)g * p.k + party) * n + col] = (int32_t)out[c];
-            if (col == n) bsum += out[c];
+        for (int c = 0; c < 4; c++) {
+            const int col = col0 + c;
+            if (col < n) p.oa[((size_t)g * p.k + party) * n + col] = (int32_t)o4[c];
+            if (col == n) bsum += o4[c];
         }
     }
-    if (gtid == n % TPG) p.ob[g] = (int32_t)((uint32_t)eb + bsum);   // thread owning column n
+    if (col0 <= n && n < col0 + 4) p.ob[g] = (int32_t)((uint32_t)eb + bsum);   // thread owning column n
 }
 
 // GPC gates per CTA, WPG warps per gate.  Accumulators resident in shared memory for all k*n steps.
@@ -520,14 +521,14 @@ __global__ void __launch_bounds__(NM_THREADS) negacyclic_mul_kernel(const int64_
 
 // Multi-key LWE key switch (mk_keyswitch_3gen mk_internals.jl:730-744, keyswitch keyswitch.jl:45-80).
 // One CTA per sample; thread c owns output columns c, c+KS_THREADS, ... of the (n+1)-wide rows.
-// ksk: int32 [k][N][t][B-1][n+1].
+// ksk: int32 [k][N][t][B-1][ks_row_stride(n)] (rows padded to 16 bytes).
 constexpr int KS_THREADS = 256;
 constexpr int KS_MAXCOLS = 4;   // n + 1 <= 1024
 __global__ void __launch_bounds__(KS_THREADS) keyswitch_kernel(int n, int k, int t, int basebit, const int32_t* __restrict__ ksk,
                                                                 const int32_t* __restrict__ ext, int32_t* __restrict__ oa, int32_t* __restrict__ ob) {
     __shared__ uint32_t s_a[N];
     const int g = blockIdx.x, tid = threadIdx.x;
-    const int B1 = (1 << basebit) - 1, row = n + 1;
+    const int B1 = (1 << basebit) - 1, row = n + 1, stride = ks_row_stride(n);
     const uint32_t prec_offset = 1u << (32 - (1 + basebit * t));   // keyswitch.jl:58
     const int32_t* e = ext + (size_t)g * (N + 1);
     for (int i = tid; i < N; i += KS_THREADS) s_a[i] = (uint32_t)e[i] + prec_offset;   // :59
@@ -538,13 +539,13 @@ __global__ void __launch_bounds__(KS_THREADS) keyswitch_kernel(int n, int k, int
         uint32_t acc[KS_MAXCOLS];
 #pragma unroll
         for (int c = 0; c < KS_MAXCOLS; c++) acc[c] = 0;
-        const int32_t* rows = ksk + (size_t)p * N * t * B1 * row;
+        const int32_t* rows = ksk + (size_t)p * N * t * B1 * stride;
         for (int i = 0; i < N; i++) {
             const uint32_t ai = s_a[i];
             for (int j = 1; j <= t; j++) {
                 const uint32_t d = (ai >> (32 - j * basebit)) & (uint32_t)B1;   // :65-67
                 if (d != 0) {                                                 // :74-76
-                    const int32_t* r = rows + (((size_t)i * t + (j - 1)) * B1 + (d - 1)) * row;
+                    const int32_t* r = rows + (((size_t)i * t + (j - 1)) * B1 + (d - 1)) * stride;
 #pragma unroll
                     for (int c = 0; c < KS_MAXCOLS; c++) {
                         const int col = tid + c * KS_THREADS;

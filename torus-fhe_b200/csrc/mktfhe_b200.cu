@@ -207,11 +207,12 @@ int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
     c->bsk_bytes = (size_t)params->k * params->n * mk::bsk_elem_words(params->l) * sizeof(u32);
     c->gpc = mk::gpc_for(params->l);
     if (const char* e = getenv("MKTFHE_B200_FUSE_KS")) c->fuse_ks = atoi(e) != 0;
-    c->ksk_bytes = (size_t)params->k * mk::N * params->t * B1 * (params->n + 1) * sizeof(int32_t);
+    const size_t ks_stride = mk::ks_row_stride(params->n);   // rows padded to 16 bytes on the device
+    c->ksk_bytes = (size_t)params->k * mk::N * params->t * B1 * ks_stride * sizeof(int32_t);
     CREATE_TRY(cudaMalloc(&c->d_bsk, c->bsk_bytes));
     // the key-switching key is followed by one all-zero row (read by the fused key switch for zero digits)
-    CREATE_TRY(cudaMalloc(&c->d_ksk, c->ksk_bytes + (size_t)(params->n + 1) * sizeof(int32_t)));
-    CREATE_TRY(cudaMemset((char*)c->d_ksk + c->ksk_bytes, 0, (size_t)(params->n + 1) * sizeof(int32_t)));
+    CREATE_TRY(cudaMalloc(&c->d_ksk, c->ksk_bytes + ks_stride * sizeof(int32_t)));
+    CREATE_TRY(cudaMemset(c->d_ksk, 0, c->ksk_bytes + ks_stride * sizeof(int32_t)));
     CREATE_TRY(cudaMalloc(&c->d_twB, (size_t)mk::TWB_WORDS * 4));
     {
         rns::HostTables T;
@@ -265,8 +266,9 @@ int mktfhe_load_ksk(mktfhe_ctx* c, int party, const int32_t* rows) {
     if (!c) return MKTFHE_EINVAL;
     if (party < 0 || party >= c->prm.k || !rows) return fail(c, MKTFHE_EINVAL, "load_ksk: bad party %d or NULL key", party);
     CU_TRY(c, cudaSetDevice(c->device));
-    const size_t per = c->ksk_bytes / c->prm.k;
-    CU_TRY(c, cudaMemcpyAsync((char*)c->d_ksk + per * party, rows, per, cudaMemcpyHostToDevice, c->stream));
+    const size_t per = c->ksk_bytes / c->prm.k, nrows = per / (mk::ks_row_stride(c->prm.n) * sizeof(int32_t));
+    const size_t src_pitch = (size_t)(c->prm.n + 1) * sizeof(int32_t), dst_pitch = (size_t)mk::ks_row_stride(c->prm.n) * sizeof(int32_t);
+    CU_TRY(c, cudaMemcpy2DAsync((char*)c->d_ksk + per * party, dst_pitch, rows, src_pitch, src_pitch, nrows, cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     c->ksk_loaded[party] = 1;
     c->ready = false;
