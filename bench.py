@@ -159,8 +159,8 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the single JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "NONE"        # NCCL prints its version banner on stdout at VERSION/WARN: keep stdout to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     params = {2: T.mktfhe_parameters_2party_3gen, 3: T.mktfhe_parameters_3party_3gen, 4: T.mktfhe_parameters_4party_3gen,
               5: T.mktfhe_parameters_5party_3gen, 8: T.mktfhe_parameters_8party_3gen}[args.parties]
