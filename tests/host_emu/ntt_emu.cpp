@@ -80,6 +80,20 @@ int main() {
             gs_bfly<true>(X, Y, w, ws, p, 4 * p, 4 * p);
             if (X >= 4 * p || Y >= 2 * p || X % p != ((u64)X0 + Y0) % p || Y % p != ((u64)X0 % p + p - Y0 % p) % p * w % p) { fails++; printf("FAIL gs\n"); break; }
         }
+        // pass A with the first stage's products taken from a table (gadget digits) == plain pass A, modulo p
+        {
+            u32 xa[32], xb[32];
+            const u32 w0 = T.c.twA[pi][0][0].x;
+            for (int r = 0; r < 32; r++) {
+                const int d = (int)(rnd() % 128) - 64;
+                xa[r] = (u32)(d + 64) + (p - 64);
+                xb[r] = r < 16 ? xa[r] : mulmod(d >= 0 ? (u32)d : p - (u32)(-d), w0, p);
+            }
+            fwd_passA(xa, T.c.twA[pi][0], p);
+            fwd_passA_pre(xb, T.c.twA[pi][0], p);
+            for (int r = 0; r < 32; r++)
+                if (xb[r] >= 12 * p || xa[r] % p != xb[r] % p) { fails++; printf("FAIL passA_pre prime=%d r=%d\n", pi, r); break; }
+        }
         // forward transform vs the definition: out[pos] = A(psi^(2 brev(pos) + 1))
         std::vector<u32> a(N), back(N);
         for (auto& v : a) v = rnd() % (2 * p);

@@ -25,7 +25,8 @@ using rns::uint2_;
 constexpr int N = rns::N;
 constexpr int TWB_WORDS = rns::NP * 2 * 31 * 32 * 2; // per-lane pass-B twiddle table [prime][dir][31][32] of (w, w') = 47616 B
 constexpr int TWA_WORDS = rns::NP * 2 * 32 * 2;      // pass-A twiddles [prime][dir][32 (31 used)] of (w, w') staged in shared memory = 1536 B
-constexpr int TW_SMEM_BYTES = (TWB_WORDS + TWA_WORDS) * 4;
+constexpr int LUT_WORDS = rns::NP * 256;               // stage-0 products w0 * (digit - Bg/2) mod p for every biased digit byte
+constexpr int TW_SMEM_BYTES = (TWB_WORDS + TWA_WORDS + LUT_WORDS) * 4;
 
 // Warps per gate.  3: one warp per prime (32 coefficients per thread + both outputs' accumulators = 96 live registers,
 // 4 gates x 3 warps per SM at 168 registers).  6: one warp per (prime, output polynomial): the two warps of a prime split
@@ -127,6 +128,18 @@ __device__ __forceinline__ void stage_twiddles(uint2_* twB_s, const uint2_* twB_
     uint2_* twA_s = twB_s + TWB_WORDS / 2;
     for (int i = threadIdx.x; i < rns::NP * 2 * 31; i += blockDim.x) twA_s[(i / 31) * 32 + i % 31] = c_rns.twA[i / 62][(i / 31) & 1][i % 31];
 }
+// the first forward stage multiplies coefficients 512..1023 by one twiddle w0; for gadget digits (Bg <= 256 values) that product
+// comes from this table: lut[prime][byte] = w0 * (byte - Bg/2) mod p
+__device__ __forceinline__ void stage_digit_lut(u32* lut, int bgbit) {
+    const int half = 1 << (bgbit - 1);
+    for (int i = threadIdx.x; i < rns::NP * 256; i += blockDim.x) {
+        const int pi = i >> 8, byte = i & 255;
+        const u32 p = c_rns.p[pi];
+        const int d = byte - half;
+        const u32 r = d >= 0 ? (u32)d : p - (u32)(-d);
+        lut[i] = byte < 2 * half ? rns::mulmod(r, c_rns.twA[pi][0][0].x, p) : 0u;
+    }
+}
 
 // forward transform of the 32 elements of this thread (coefficients 32 r + lane, in [0, 2p) -> positions 32 lane + c, in [0, 14p))
 __device__ __forceinline__ void warp_ntt_fwd(u32 (&x)[32], u32* tile, const uint2_* twA, const uint2_* twB_lane, u32 p, int lane) {
@@ -139,6 +152,18 @@ __device__ __forceinline__ void warp_ntt_fwd(u32 (&x)[32], u32* tile, const uint
     for (int c = 0; c < 32; c++) x[c] = rns::reduce_to_4p(tile[lane * rns::TILE_STRIDE + c], p4);  // pass A leaves [0, 12p)
     __syncwarp();
     rns::fwd_passB(x, twB_lane, p);                                                               // -> [0, 14p)
+}
+// same for gadget digits: x[0..15] = digit + (p - Bg/2), x[16..31] = lut[digit byte] (first-stage products)
+__device__ __forceinline__ void warp_ntt_fwd_digits(u32 (&x)[32], u32* tile, const uint2_* twA, const uint2_* twB_lane, u32 p, int lane) {
+    const u32 p4 = rns::keep_in_register(4 * p);
+    rns::fwd_passA_pre(x, twA, p);
+#pragma unroll
+    for (int r = 0; r < 32; r++) tile[r * rns::TILE_STRIDE + lane] = x[r];
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 32; c++) x[c] = rns::reduce_to_4p(tile[lane * rns::TILE_STRIDE + c], p4);
+    __syncwarp();
+    rns::fwd_passB(x, twB_lane, p);
 }
 // inverse transform (positions 32 lane + c -> coefficients 32 r + lane), scaled by N
 __device__ __forceinline__ void warp_ntt_inv(u32 (&x)[32], u32* tile, const uint2_* twA, const uint2_* twB_lane, u32 p, int lane) {
@@ -188,13 +213,17 @@ __device__ __forceinline__ void decompose_phase(const u64* __restrict__ acc, u32
     }
 }
 
-// digit polynomial s of this gate -> the 32 coefficients 32 r + lane of this thread, as residues in [0, 2p)
-__device__ __forceinline__ void load_digits(u32 (&x)[32], const u32* __restrict__ dig, int s, int lane, u32 bias) {
+// digit polynomial s of this gate -> the 32 coefficients 32 r + lane of this thread: r < 16 as residues digit + (p - Bg/2) in
+// [0, 2p); r >= 16 (the half the first NTT stage multiplies by w0) directly as the products w0 * digit from the table
+__device__ __forceinline__ void load_digits(u32 (&x)[32], const u32* __restrict__ dig, const u32* __restrict__ lut, int s, int lane, u32 bias) {
 #pragma unroll
     for (int rh = 0; rh < 8; rh++) {
         const u32 word = dig[(s * 8 + rh) * 32 + lane];
 #pragma unroll
-        for (int b = 0; b < 4; b++) x[4 * rh + b] = rns::alu_add((word >> (8 * b)) & 0xffu, bias);
+        for (int b = 0; b < 4; b++) {
+            const u32 byte = __byte_perm(word, 0, 0x4440 + b);
+            x[4 * rh + b] = rh < 4 ? rns::alu_add(byte, bias) : lut[byte];
+        }
     }
 }
 
@@ -218,6 +247,7 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
     const uint2_* twBi = twB + ((size_t)(w * 2 + 1) * 31) * 32 + lane;
     const uint2_* twAf = twB + TWB_WORDS / 2 + (w * 2 + 0) * 32;
     const uint2_* twAi = twAf + 32;
+    const u32* lut = reinterpret_cast<const u32*>(twB) + TWB_WORDS + TWA_WORDS + w * 256;
     const uint4* kp = reinterpret_cast<const uint4*>(key + (size_t)w * (2 * L * 2 * N)) + lane;   // K[prime][s][out][slot]
     const u32 bias = p - (1u << (bgbit - 1));
     if (WPG == 6) {
@@ -233,8 +263,8 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
         for (int i = 0; i < L; i++) {
             const int s_own = 2 * i + o, s_for = 2 * i + 1 - o;
             u32 x[32];
-            load_digits(x, dig, s_own, lane, bias);
-            warp_ntt_fwd(x, tile, twAf, twBf, p, lane);
+            load_digits(x, dig, lut, s_own, lane, bias);
+            warp_ntt_fwd_digits(x, tile, twAf, twBf, p, lane);
 #pragma unroll
             for (int c = 0; c < 32; c++) tile[c * 32 + lane] = x[c];
             pair_barrier(pb);
@@ -277,8 +307,8 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
 #pragma unroll S_UNROLL
         for (int s = 0; s < 2 * L; s++) {
             u32 x[32];
-            load_digits(x, dig, s, lane, bias);
-            warp_ntt_fwd(x, tile, twAf, twBf, p, lane);
+            load_digits(x, dig, lut, s, lane, bias);
+            warp_ntt_fwd_digits(x, tile, twAf, twBf, p, lane);
             const uint4* k0 = kp + (size_t)(s * 2) * (N / 4);
 #pragma unroll
             for (int q4 = 0; q4 < 8; q4++) {
@@ -383,6 +413,7 @@ __global__ void __maxnreg__(MK_MAXNREG) blind_rotate_kernel(BlindRotateArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2_* twB = reinterpret_cast<uint2_*>(smem_raw);
     stage_twiddles(twB, p.twB);
+    stage_digit_lut(reinterpret_cast<u32*>(twB) + TWB_WORDS + TWA_WORDS, p.bgbit);
     __syncthreads();
     const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot, pbar_id = 1 + GPC + slot * rns::NP;
     const int g = blockIdx.x * GPC + slot;
@@ -447,6 +478,7 @@ __global__ void __maxnreg__(MK_MAXNREG) extprod_kernel(int G, const u32* bsk, co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2_* twB = reinterpret_cast<uint2_*>(smem_raw);
     stage_twiddles(twB, twB_g);
+    stage_digit_lut(reinterpret_cast<u32*>(twB) + TWB_WORDS + TWA_WORDS, bgbit);
     __syncthreads();
     const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot, pbar_id = 1 + GPC + slot * rns::NP;
     const int g = blockIdx.x * GPC + slot;

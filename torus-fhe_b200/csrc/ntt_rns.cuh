@@ -40,6 +40,7 @@ struct TwLane {           // pass B: t already points at column `lane` of a [31]
 };
 
 MK_HD void fwd_passA(u32 (&x)[32], const uint2_* twA_fwd, u32 p) { ct32(x, TwUniform{twA_fwd}, p); }
+MK_HD void fwd_passA_pre(u32 (&x)[32], const uint2_* twA_fwd, u32 p) { ct32_pre(x, TwUniform{twA_fwd}, p); }
 MK_HD void fwd_passB(u32 (&x)[32], const uint2_* twB_fwd_lane, u32 p) { ct32(x, TwLane{twB_fwd_lane}, p); }
 MK_HD void inv_passB(u32 (&x)[32], const uint2_* twB_inv_lane, u32 p) { gs32(x, TwLane{twB_inv_lane}, p); }
 MK_HD void inv_passA(u32 (&x)[32], const uint2_* twA_inv, u32 p) { gs32(x, TwUniform{twA_inv}, p); }

@@ -115,6 +115,28 @@ MK_HD void ct32(u32 (&x)[32], TW tw, u32 p) {
         }
     }
 }
+// ct32 whose first stage is already half done: x[16..31] hold w0 * y (the stage-0 twiddle products, in [0, p)) instead of y.
+// Used for the gadget digits, whose 7-bit values make w0 * y a table lookup instead of a multiplication.
+template <class TW>
+MK_HD void ct32_pre(u32 (&x)[32], TW tw, u32 p) {
+    const u32 p2 = keep_in_register(2 * p);
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const u32 X = x[j], t = x[j + 16];
+        x[j] = alu_add(X, t);
+        x[j + 16] = X - t + p2;
+    }
+#pragma unroll
+    for (int k = 1; k < 5; k++) {
+        const int g = 16 >> k;
+#pragma unroll
+        for (int b = 0; b < (1 << k); b++) {
+            const uint2_ w = tw((1 << k) - 1 + b);
+#pragma unroll
+            for (int j = 0; j < g; j++) ct_bfly<false>(x[2 * g * b + j], x[2 * g * b + j + g], w.x, w.y, p, p2);
+        }
+    }
+}
 // [0, 16p) -> [0, 4p): between the two passes of a forward transform
 MK_HD u32 reduce_to_4p(u32 v, u32 p4) {           // p4 = 4p (held in a register by the caller)
     v = umin32(v, v - 2 * p4);
