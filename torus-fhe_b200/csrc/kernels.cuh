@@ -25,7 +25,14 @@ using rns::uint2_;
 constexpr int N = rns::N;
 constexpr int TWB_WORDS = rns::NP * 2 * 31 * 32 * 2; // per-lane pass-B twiddle table [prime][dir][31][32] of (w, w') = 47616 B
 constexpr int TWA_WORDS = rns::NP * 2 * 32 * 2;      // pass-A twiddles [prime][dir][32 (31 used)] of (w, w') staged in shared memory = 1536 B
-constexpr int LUT_WORDS = rns::NP * 256;               // stage-0 products w0 * (digit - Bg/2) mod p for every biased digit byte
+// stage-0 products w0 * (digit - Bg/2) mod p for every biased digit byte, one column per lane (lut[prime][byte][lane]) so that
+// the data-dependent lookups never conflict on a shared-memory bank (Bg <= 128 keeps that at 48 KB), or compact
+#ifndef MK_LUT_REPL
+#define MK_LUT_REPL 1        // measured: the 48 KB per-lane replica is slower (smaller L1 for the key stream) than 3-way bank conflicts
+#endif
+constexpr int LUT_REPL = MK_LUT_REPL;                 // 32: replicated per lane; 1: compact
+constexpr int LUT_BYTES_MAX = LUT_REPL == 32 ? 128 : 256;
+constexpr int LUT_WORDS = rns::NP * LUT_BYTES_MAX * LUT_REPL;
 constexpr int TW_SMEM_BYTES = (TWB_WORDS + TWA_WORDS + LUT_WORDS) * 4;
 
 // Warps per gate.  3: one warp per prime (32 coefficients per thread + both outputs' accumulators = 96 live registers,
@@ -132,12 +139,14 @@ __device__ __forceinline__ void stage_twiddles(uint2_* twB_s, const uint2_* twB_
 // comes from this table: lut[prime][byte] = w0 * (byte - Bg/2) mod p
 __device__ __forceinline__ void stage_digit_lut(u32* lut, int bgbit) {
     const int half = 1 << (bgbit - 1);
-    for (int i = threadIdx.x; i < rns::NP * 256; i += blockDim.x) {
-        const int pi = i >> 8, byte = i & 255;
+    for (int i = threadIdx.x; i < rns::NP * LUT_BYTES_MAX; i += blockDim.x) {
+        const int pi = i / LUT_BYTES_MAX, byte = i % LUT_BYTES_MAX;
         const u32 p = c_rns.p[pi];
         const int d = byte - half;
         const u32 r = d >= 0 ? (u32)d : p - (u32)(-d);
-        lut[i] = byte < 2 * half ? rns::mulmod(r, c_rns.twA[pi][0][0].x, p) : 0u;
+        const u32 v = byte < 2 * half ? rns::mulmod(r, c_rns.twA[pi][0][0].x, p) : 0u;
+#pragma unroll
+        for (int l = 0; l < LUT_REPL; l++) lut[i * LUT_REPL + l] = v;
     }
 }
 
@@ -222,7 +231,7 @@ __device__ __forceinline__ void load_digits(u32 (&x)[32], const u32* __restrict_
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const u32 byte = __byte_perm(word, 0, 0x4440 + b);
-            x[4 * rh + b] = rh < 4 ? rns::alu_add(byte, bias) : lut[byte];
+            x[4 * rh + b] = rh < 4 ? rns::alu_add(byte, bias) : lut[byte * LUT_REPL];
         }
     }
 }
@@ -247,7 +256,7 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
     const uint2_* twBi = twB + ((size_t)(w * 2 + 1) * 31) * 32 + lane;
     const uint2_* twAf = twB + TWB_WORDS / 2 + (w * 2 + 0) * 32;
     const uint2_* twAi = twAf + 32;
-    const u32* lut = reinterpret_cast<const u32*>(twB) + TWB_WORDS + TWA_WORDS + w * 256;
+    const u32* lut = reinterpret_cast<const u32*>(twB) + TWB_WORDS + TWA_WORDS + w * (LUT_BYTES_MAX * LUT_REPL) + (LUT_REPL == 32 ? lane : 0);
     const uint4* kp = reinterpret_cast<const uint4*>(key + (size_t)w * (2 * L * 2 * N)) + lane;   // K[prime][s][out][slot]
     const u32 bias = p - (1u << (bgbit - 1));
     if (WPG == 6) {

@@ -83,7 +83,8 @@ int check_params(const mktfhe_params* p) {
     if (p->N != mk::N) return fail(nullptr, MKTFHE_EINVAL, "unsupported N=%d (only 1024)", p->N);
     if (p->l < 1 || p->l > 4) return fail(nullptr, MKTFHE_EINVAL, "unsupported gsw_decomp_length l=%d (1..4)", p->l);
     if (p->bgbit < 1 || p->l * p->bgbit > 32) return fail(nullptr, MKTFHE_EINVAL, "unsupported l*bgbit=%d (<=32)", p->l * p->bgbit);
-    if (p->bgbit > 8) return fail(nullptr, MKTFHE_EINVAL, "unsupported gsw_log2_base=%d (digits are packed in bytes: <= 8)", p->bgbit);
+    if ((1 << p->bgbit) > mk::LUT_BYTES_MAX)
+        return fail(nullptr, MKTFHE_EINVAL, "unsupported gsw_log2_base=%d (digit lookup table holds %d values)", p->bgbit, mk::LUT_BYTES_MAX);
     // exactness of the three-prime CRT: |sum| <= 2l * N * 2^(bgbit-1) * 2^63 must stay below M/4
     if (std::log2((double)(2 * p->l) * p->N) + (p->bgbit - 1) + 63.0 >= rns::log2_crt_bound())
         return fail(nullptr, MKTFHE_EINVAL, "2l*N*Bg/2*2^63 exceeds the CRT range of the three-prime exact product");
