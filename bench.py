@@ -265,8 +265,9 @@ def run_ours(args):
         # 2048 CRT lifts x 17 slots
         imad_slots = k * n * ((6 * l + 6) * 5120 * 4 + 12 * l * 1024 * 5 + 2 * 1024 * 17)
         imad_peak = 18.26e12       # measured: tools/pipe_ubench.cu -> profiles/pipe_ubench_r1.txt (62.8 IMAD lanes/clk/SM)
-        ncu_traffic = {"bytes": 451.5e6, "gates_in_captured_launch": 2368,
-                       "source": "profiles/ncu_r1_c_blind_rotate.txt (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)"}
+        ncu_traffic = {"bytes": 1.594e9, "gates_in_captured_launch": 2368, "waves_in_captured_launch": 8,
+                       "source": "profiles/ncu_r1_f_blind_rotate.txt (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture): "
+                                 "one pass over bsk (102 MB) + ksk (90 MB) per wave of 296 gates, i.e. 0.67 MB per gate against 68 MB algorithmic"}
         value = world * G * args.steps / (ms * 1e-3)
         line = {"metric": METRIC.replace("2-party", f"{k}-party"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "ms_per_bootstrap_amortized": ms / args.steps / G, "higher_is_better": True, "scaling": "weak",
@@ -282,7 +283,7 @@ def run_ours(args):
                 "gpu_launches": int(launches),
                 "roofline": {"kernel": "blind_rotate_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved / hbm_peak, "traffic": ncu_traffic["bytes"], "traffic_note": ncu_traffic, "peak_source": peak_src,
-                             "note": "contract roofline (HBM); the kernel is IMAD-pipe bound and streams the key from L2 (hit rate 97.8 %): see integer_bound",
+                             "note": "contract roofline (HBM); the kernel is IMAD-pipe bound and streams the key from L2 (hit rate 97.6 %): see integer_bound",
                              "algorithmic_bytes_per_gate": bsk_1limb + ct_io, "streamed_bytes_per_gate_this_build": bsk_stream,
                              "kernel_ms": br_ms, "keyswitch_ms": ks_ms, "keyswitch_gather_GBps": (G * ksk_gather / (ks_ms * 1e-3) / 1e9) if ks_ms > 0.05 else None,
                              "keyswitch_fused_into_blind_rotate": ks_ms <= 0.05,
