@@ -41,6 +41,13 @@ constexpr int TW_SMEM_BYTES = (TWB_WORDS + TWA_WORDS + LUT_WORDS) * 4;
 // accumulates and inverse-transforms ONE output with one Montgomery reduction per pair of products (64 live registers,
 // 2 gates x 6 warps per SM at 168 registers).  Measured (profiles/ab_r1.txt): 6 warps / 2 gates 22.3 k gates/s,
 // 3 warps / 4 gates 20.6 k, 6 warps / 3 gates (96 registers, spills) 20.7 k.
+// cache policy of the two key streams (A/B knobs): __ldg = read-only path, allocating in L1; __ldcs = streaming (evict first)
+#ifndef MK_KS_LD
+#define MK_KS_LD __ldg
+#endif
+#ifndef MK_KEY_LD
+#define MK_KEY_LD __ldg
+#endif
 #ifndef MK_WPG
 #define MK_WPG 6
 #endif
@@ -281,7 +288,7 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
             const uint4* k_for = kp + (size_t)(s_for * 2 + o) * (N / 4);
 #pragma unroll
             for (int q4 = 0; q4 < 8; q4++) {
-                const uint4 ka = __ldg(k_own + q4 * 32), kb = __ldg(k_for + q4 * 32);
+                const uint4 ka = MK_KEY_LD(k_own + q4 * 32), kb = MK_KEY_LD(k_for + q4 * 32);
                 accv[4 * q4 + 0] = rns::alu_add(accv[4 * q4 + 0], rns::mont_mul2(x[4 * q4 + 0], ka.x, ptile[(4 * q4 + 0) * 32 + lane], kb.x, p, pinv));
                 accv[4 * q4 + 1] = rns::alu_add(accv[4 * q4 + 1], rns::mont_mul2(x[4 * q4 + 1], ka.y, ptile[(4 * q4 + 1) * 32 + lane], kb.y, p, pinv));
                 accv[4 * q4 + 2] = rns::alu_add(accv[4 * q4 + 2], rns::mont_mul2(x[4 * q4 + 2], ka.z, ptile[(4 * q4 + 2) * 32 + lane], kb.z, p, pinv));
@@ -400,7 +407,7 @@ __device__ __forceinline__ void fused_keyswitch(const u64* __restrict__ acc, u32
                     const uint32_t d = (ai >> (32 - j * bb)) & (uint32_t)B1;   // :65-67
                     const uint4* r = d ? reinterpret_cast<const uint4*>(rows + (((size_t)(i + ii) * T + (j - 1)) * B1 + (d - 1)) * stride) + gtid
                                        : zero_row;                              // :74-76
-                    const uint4 v = __ldg(r);
+                    const uint4 v = MK_KS_LD(r);
                     out.x -= v.x; out.y -= v.y; out.z -= v.z; out.w -= v.w;
                 }
             }

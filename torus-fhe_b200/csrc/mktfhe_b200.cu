@@ -94,7 +94,10 @@ int check_params(const mktfhe_params* p) {
     return MKTFHE_OK;
 }
 
-size_t br_smem_bytes(const mktfhe_ctx* c) { return mk::cta_smem_bytes(c->prm.l); }
+#ifndef MK_EXTRA_SMEM
+#define MK_EXTRA_SMEM 0     // diagnostic: unused shared memory to move the L1 carve-out
+#endif
+size_t br_smem_bytes(const mktfhe_ctx* c) { return mk::cta_smem_bytes(c->prm.l) + MK_EXTRA_SMEM; }
 
 // (L, GPC) instantiations: mk::gpc_for(l) gates per CTA
 #define MK_DISPATCH_L(c, KERNEL, ...)                                      \
