@@ -22,7 +22,8 @@ def test_header_and_binding_agree():
 
 def test_library_exports_every_declared_symbol():
     import torus_fhe_b200 as T
-    assert os.path.exists(T._cabi.LIB_PATH), "build with __graft_entry__.build()"
+    if not os.path.exists(T._cabi.LIB_PATH):
+        T._cabi.build()          # nvcc cross-compiles sm_100a without a GPU (about a minute)
     L = ctypes.CDLL(T._cabi.LIB_PATH)
     for s in declared_symbols():
         assert hasattr(L, s), s

@@ -13,5 +13,5 @@ from ._cabi import MktfheError
 from .engine import Engine, shard_bounds, shard_batch
 from .tfhe3gen import *  # noqa: F401,F403
 from .tfhe3gen import engine_for, negacyclic_mul
-from .circuits import (gate_level, mk_add_3gen, mk_add_3gen_v2, mk_inv_3gen, mk_sub_3gen, mk_less_3gen, mk_grt_3gen, mk_leq_3gen,
+from .circuits import (gate_level, mk_int_add_3gen_gpu, mk_add_3gen, mk_add_3gen_v2, mk_inv_3gen, mk_sub_3gen, mk_less_3gen, mk_grt_3gen, mk_leq_3gen,
                        mk_geq_3gen, mk_int_add_with_carry_3gen, mk_int_mul_3gen)

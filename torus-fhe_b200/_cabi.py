@@ -209,6 +209,9 @@ class Context:
     def gate_batch_dev(self, gate, G, xa, xb, ya, yb, za, zb, oa, ob, stream=0):
         self._chk(lib().mktfhe_gate_batch_dev(self.h, gate, G, xa, xb, ya, yb, za or None, zb or None, oa, ob, stream or None))
 
+    def gate_batch_mixed_dev(self, G, gate_ids, xa, xb, ya, yb, za, zb, oa, ob, stream=0):
+        self._chk(lib().mktfhe_gate_batch_mixed_dev(self.h, G, gate_ids, xa, xb, ya, yb, za or None, zb or None, oa, ob, stream or None))
+
     # -- parity hooks
     def extprod_batch(self, elem, acc):
         elem = _c(elem, np.int32).reshape(-1)

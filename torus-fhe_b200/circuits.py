@@ -9,7 +9,7 @@ including its quirks (`mk_int_mul_3gen` reuses row WIDTH-1 in its last adder, 3g
 import numpy as np
 
 from . import _cabi
-from .tfhe3gen import MKLweSample, engine_for, mk_copy_3gen
+from .tfhe3gen import MKLweSample, MKLweSampleGPU, engine_for, mk_copy_3gen
 
 _G = {"nand": _cabi.GATE_NAND, "or": _cabi.GATE_OR, "and": _cabi.GATE_AND, "xor": _cabi.GATE_XOR}
 
@@ -19,6 +19,8 @@ def gate_level(bk, ks, jobs):
     in ONE launch; returns the list of outputs in order."""
     eng = engine_for(bk, ks)
     k, n = eng.params.max_parties, eng.params.lwe_size
+    if isinstance(jobs[0][1], MKLweSampleGPU):
+        return _gate_level_gpu(eng, jobs, k, n)
     xa, xb, ya, yb, ids, shapes = [], [], [], [], [], []
     for kind, x, y in jobs:
         if x.b.shape != y.b.shape:
@@ -36,6 +38,39 @@ def gate_level(bk, ks, jobs):
         outs.append(MKLweSample(params, oa[pos:pos + cnt].reshape(shp + (k, n)), ob[pos:pos + cnt].reshape(shp), 0.0))
         pos += cnt
     return outs
+
+
+def _gate_level_gpu(eng, jobs, k, n):
+    """Device-resident level: operands are gathered with torch.cat in HBM and the level is one mktfhe_gate_batch_mixed_dev call."""
+    import torch
+    xa, xb, ya, yb, ids, shapes = [], [], [], [], [], []
+    dev = jobs[0][1].a.device
+    for kind, x, y in jobs:
+        shp = torch.broadcast_shapes(tuple(x.b.shape), tuple(y.b.shape))
+        shapes.append(tuple(shp))
+        xa.append(x.a.expand(shp + (k, n)).reshape(-1, k, n)); xb.append(x.b.expand(shp).reshape(-1))
+        ya.append(y.a.expand(shp + (k, n)).reshape(-1, k, n)); yb.append(y.b.expand(shp).reshape(-1))
+        ids.append(torch.full((xb[-1].numel(),), _G[kind], dtype=torch.int32, device=dev))
+    xa, xb, ya, yb, ids = (torch.cat(t).contiguous() for t in (xa, xb, ya, yb, ids))
+    G = xb.numel()
+    oa = torch.empty((G, k, n), dtype=torch.int32, device=dev)
+    ob = torch.empty(G, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    eng.ctx.gate_batch_mixed_dev(G, ids.data_ptr(), xa.data_ptr(), xb.data_ptr(), ya.data_ptr(), yb.data_ptr(), 0, 0, oa.data_ptr(), ob.data_ptr(),
+                                 stream=stream)
+    if not stream:
+        torch.cuda.synchronize(dev)
+    outs, pos = [], 0
+    for shp in shapes:
+        cnt = int(np.prod(shp, dtype=np.int64))
+        outs.append(MKLweSampleGPU(jobs[0][1].params, oa[pos:pos + cnt].reshape(shp + (k, n)), ob[pos:pos + cnt].reshape(shp), 0.0))
+        pos += cnt
+    return outs
+
+
+def mk_int_add_3gen_gpu(bk, ks, a, b, Cin, WIDTH):
+    """3gen_mk_gates.jl:447-463: the adder on device-resident samples (the reference's version allocates a CuArray of host structs)."""
+    return mk_add_3gen(bk, ks, a, b, Cin, WIDTH)
 
 
 def _broadcast(x, y):

@@ -171,6 +171,7 @@ def _w32(x):
 
 class MKLweSample:
     __slots__ = ("params", "a", "b", "current_variance")
+    __array_ufunc__ = None      # numpy scalars (Torus32(2) * sample) defer to __rmul__
 
     def __init__(self, params, a, b, current_variance=0.0):
         self.params = params
@@ -209,6 +210,56 @@ class MKLweSample:
     def stack(samples):
         return MKLweSample(samples[0].params, np.stack([s.a for s in samples]), np.stack([s.b for s in samples]),
                            max(s.current_variance for s in samples))
+
+
+class MKLweSampleGPU:
+    """mk_internals.jl:56-82: the reference's CuArray twin of MKLweSample (it only ever carries the linear ops there; the
+    bootstrap call in gpu_circuits.jl:27-36 is commented out).  Here `a` / `b` are torch int32 tensors resident on the GPU of the
+    engine; every gate below accepts it and runs through the device-pointer C-ABI entries, so ciphertexts stay in HBM between
+    gates and dependency levels."""
+    __slots__ = ("params", "a", "b", "current_variance")
+    __array_ufunc__ = None
+
+    def __init__(self, params, a, b, current_variance=0.0):
+        self.params, self.a, self.b, self.current_variance = params, a, b, current_variance
+
+    @staticmethod
+    def from_host(x, device=None):
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        return MKLweSampleGPU(x.params, torch.from_numpy(np.ascontiguousarray(x.a)).to(dev), torch.from_numpy(np.ascontiguousarray(x.b)).to(dev),
+                              x.current_variance)
+
+    def cpu(self):
+        return MKLweSample(self.params, self.a.cpu().numpy(), self.b.cpu().numpy(), self.current_variance)
+
+    @property
+    def batch_shape(self):
+        return tuple(self.b.shape)
+
+    def __getitem__(self, idx):
+        return MKLweSampleGPU(self.params, self.a[idx], self.b[idx], self.current_variance)
+
+    def __sub__(self, y):
+        return MKLweSampleGPU(self.params, self.a - y.a, self.b - y.b, self.current_variance + y.current_variance)
+
+    def __add__(self, y):
+        return MKLweSampleGPU(self.params, self.a + y.a, self.b + y.b, self.current_variance + y.current_variance)
+
+    def __neg__(self):
+        return MKLweSampleGPU(self.params, -self.a, -self.b, self.current_variance)
+
+    def __rmul__(self, x):
+        x = int(x)
+        return MKLweSampleGPU(self.params, self.a * x, self.b * x, float(x) * float(x) * self.current_variance)
+
+
+def mk_lwe_noiseless_trivial_gpu(mu, params, parties, batch_shape=(), device=None):
+    """gpu_circuits.jl:23-25."""
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    return MKLweSampleGPU(params, torch.zeros(tuple(batch_shape) + (parties, params.size), dtype=torch.int32, device=dev),
+                          torch.full(tuple(batch_shape), int(mu), dtype=torch.int32, device=dev), 0.0)
 
 
 def mk_lwe_noiseless_trivial(mu, params, parties, batch_shape=()):
@@ -439,8 +490,28 @@ def _flat(x, k, n):
     return x.a.reshape(-1, k, n), x.b.reshape(-1)
 
 
+def _gate_gpu(eng, gate, x, y, z):
+    """Device-resident operands: mktfhe_gate_batch_dev on torch's current stream; nothing crosses PCIe."""
+    import torch
+    k, n = eng.params.max_parties, eng.params.lwe_size
+    ops = [(t.a.reshape(-1, k, n).contiguous(), t.b.reshape(-1).contiguous()) for t in (x, y) + ((z,) if z is not None else ())]
+    G = ops[0][1].numel()
+    oa = torch.empty((G, k, n), dtype=torch.int32, device=ops[0][0].device)
+    ob = torch.empty(G, dtype=torch.int32, device=ops[0][0].device)
+    za, zb = (ops[2][0].data_ptr(), ops[2][1].data_ptr()) if z is not None else (0, 0)
+    stream = torch.cuda.current_stream(ops[0][0].device).cuda_stream
+    eng.ctx.gate_batch_dev(gate, G, ops[0][0].data_ptr(), ops[0][1].data_ptr(), ops[1][0].data_ptr(), ops[1][1].data_ptr(), za, zb,
+                           oa.data_ptr(), ob.data_ptr(), stream=stream)
+    if not stream:                      # legacy default stream: the context's own stream did the work
+        torch.cuda.synchronize(ops[0][0].device)
+    shape = tuple(x.b.shape)
+    return MKLweSampleGPU(x.params, oa.reshape(shape + (k, n)), ob.reshape(shape), 0.0)
+
+
 def _gate(bk, ks, gate, x, y, z=None):
     eng = engine_for(bk, ks)
+    if isinstance(x, MKLweSampleGPU):
+        return _gate_gpu(eng, gate, x, y, z)
     k, n = eng.params.max_parties, eng.params.lwe_size
     shape = x.b.shape
     oa, ob = eng.ctx.gate_batch(gate, _flat(x, k, n), _flat(y, k, n), _flat(z, k, n) if z is not None else None)
@@ -496,6 +567,11 @@ def mk_gate_xor_3gen(bk, ks, x, y):
     return _gate(bk, ks, _cabi.GATE_XOR, x, y)
 
 
+def mk_gate_xor_3gen_gpu(bk, ks, x, y):
+    """3gen_mk_gates.jl:437-445 / gpu_circuits.jl:27-36, finished: the reference stops after the linear part."""
+    return mk_gate_xor_3gen(bk, ks, x, y)
+
+
 def mk_gate_not_3gen(x):
     return -x
 
@@ -503,11 +579,18 @@ def mk_gate_not_3gen(x):
 def mk_gate_mux_3gen(bk, ks, x, y, z):
     """3gen_mk_gates.jl:133-150: AND(x, y) and AND(-x, z) bootstrapped (one launch: the two ANDs are
     independent), then 1/8 + t1 + t2 NOT bootstrapped, exactly as the reference."""
+    k = len(bk)
+    if isinstance(x, MKLweSampleGPU):
+        import torch
+        both = _gate(bk, ks, _cabi.GATE_AND, MKLweSampleGPU(x.params, torch.stack([x.a, -x.a]), torch.stack([x.b, -x.b])),
+                     MKLweSampleGPU(y.params, torch.stack([y.a, z.a]), torch.stack([y.b, z.b])))
+        return mk_lwe_noiseless_trivial_gpu(encode_message(1, 8), x.params, k, tuple(x.b.shape), x.a.device.index) + both[0] + both[1]
     both = _gate(bk, ks, _cabi.GATE_AND, MKLweSample.stack([x, -x]), MKLweSample.stack([y, z]))
     t1, t2 = both[0], both[1]
-    k = len(bk)
     return mk_lwe_noiseless_trivial(encode_message(1, 8), t1.params, k, t1.b.shape) + t1 + t2
 
 
 def mk_copy_3gen(x):
+    if isinstance(x, MKLweSampleGPU):
+        return MKLweSampleGPU(x.params, x.a.clone(), x.b.clone(), x.current_variance)
     return MKLweSample(x.params, x.a.copy(), x.b.copy(), x.current_variance)
