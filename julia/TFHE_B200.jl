@@ -139,7 +139,34 @@ function mk_gate_mux_3gen(bk::BK, ks::KS, x::MKLweSample, y::MKLweSample, z::MKL
     mk_lwe_noiseless_trivial(encode_message(1, 8), t[1].params, length(bk)) + t[1] + t[2]
 end
 
+# ---- interchange files (torus-fhe_b200/interchange.py documents the layout): dump the reference's own keys / ciphertexts so that
+# the B200 engine and its CPU oracle can be checked on the very bytes the Julia code produced
+function write_keys(path::String, params, bk::Array{TransformedBootstrapKeyPart_3gen, 1}, ks::Array{KeyswitchKey, 1}, secret_keys = nothing)
+    open(path, "w") do f
+        write(f, "MKTFHE3K"); write(f, UInt32(1))
+        for v in (bk[1].key_size, bk[1].rlwe_params.polynomial_degree, length(bk), bk[1].tgsw_params.decomp_length, bk[1].tgsw_params.log2_base,
+                  ks[1].params.decomp_length, ks[1].params.log2_base, secret_keys === nothing ? 0 : 1)
+            write(f, Int32(v))
+        end
+        write(f, Float64(params.lwe_noise_stddev)); write(f, Float64(params.gsw_noise_stddev)); write(f, Float64(params.ks_noise_stddev))
+        for p in 1:length(bk); write(f, bk[p].gsw_key); end            # (N, l, 4, n) column-major == int64 [n][4][l][N]
+        for p in 1:length(ks); write(f, flatten_ksk(ks[p])); end       # (n+1, B-1, t, N) column-major == int32 [N][t][B-1][n+1]
+        if secret_keys !== nothing
+            for sk in secret_keys; write(f, Int32.(sk.key.key)); end
+        end
+    end
+end
+
+function write_ciphertexts(path::String, xs::Vector{MKLweSample})
+    open(path, "w") do f
+        write(f, "MKTFHE3C"); write(f, UInt32(1))
+        write(f, Int32(size(xs[1].a, 2))); write(f, Int32(size(xs[1].a, 1))); write(f, UInt64(length(xs)))
+        for x in xs; write(f, x.a); end
+        for x in xs; write(f, Int32(x.b)); end
+    end
+end
+
 export TransformedBootstrapKeyPart_3gen, mk_bootstrap_3gen, mk_gate_nand_3gen, mk_gate_or_3gen, mk_gate_and_3gen,
-       mk_gate_xor_3gen, mk_gate_3and_3gen, mk_gate_not_3gen, mk_gate_mux_3gen
+       mk_gate_xor_3gen, mk_gate_3and_3gen, mk_gate_not_3gen, mk_gate_mux_3gen, write_keys, write_ciphertexts
 
 end # module

@@ -225,3 +225,22 @@ def test_more_parties(oracle, pname):
 
 def keys_extprod(ks, oracle, party, j, acc):
     return ks.extprod(oracle.EXACT_SCHOOLBOOK, party, j, acc)
+
+
+def test_fused_and_separate_keyswitch_agree(keys2, engine2, monkeypatch):
+    """The key switch runs as the epilogue of the blind-rotate kernel; MKTFHE_B200_FUSE_KS=0 selects the stand-alone kernel.
+    Both must give the same bytes (and the keys must survive a trip through the interchange file format)."""
+    import torus_fhe_b200 as T
+    bits = np.array([[0, 0], [0, 1], [1, 0], [1, 1], [1, 1]], np.uint8)
+    x, y = keys2.encrypt(bits[:, 0], 71), keys2.encrypt(bits[:, 1], 72)
+    fused = engine2.ctx.gate_batch(T._cabi.GATE_XOR, x, y)
+    monkeypatch.setenv("MKTFHE_B200_FUSE_KS", "0")
+    eng = make_engine(keys2)
+    try:
+        l0 = eng.ctx.launch_count()
+        sep = eng.ctx.gate_batch(T._cabi.GATE_XOR, x, y)
+        assert eng.ctx.launch_count() - l0 == 2
+    finally:
+        eng.close()
+    assert np.array_equal(fused[0], sep[0]) and np.array_equal(fused[1], sep[1])
+    assert np.array_equal(keys2.decrypt(*fused), bits[:, 0].astype(bool) ^ bits[:, 1].astype(bool))

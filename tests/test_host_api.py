@@ -149,3 +149,26 @@ def test_circuit_wiring_against_plain_integers(monkeypatch):
     s = tmp + row(ctr)                                            # the reference adds row `ctr` again, not row WIDTH
     expect = (low | (s << ctr)) & ((1 << Wm) - 1)
     assert np.array_equal(got, expect)
+
+
+def test_interchange_roundtrip(tmp_path, toy_keys, oracle):
+    """Key / ciphertext files (the format a Julia host writes): byte-exact round trip, and the oracle rebuilt from the file decrypts."""
+    ks = toy_keys
+    p = ks.prm
+    sp = T.SchemeParameters_3gen(p.n, p.sigma_lwe, p.N, 1, False, p.l, p.bgbit, p.sigma_gsw, p.t, p.basebit, p.sigma_ks, p.k)
+    kf, cf = str(tmp_path / "keys.bin"), str(tmp_path / "ct.bin")
+    T.interchange.write_keys(kf, sp, [ks.bsk[i] for i in range(p.k)], [ks.ksk[i] for i in range(p.k)], ks.lwe_keys)
+    sp2, bsk, ksk, lwe = T.interchange.read_keys(kf)
+    assert sp2 == sp and np.array_equal(np.stack(bsk), ks.bsk) and np.array_equal(np.stack(ksk), ks.ksk) and np.array_equal(lwe, ks.lwe_keys)
+    bits = np.array([1, 0, 1, 1, 0], np.uint8)
+    a, b = ks.encrypt(bits, 9)
+    T.interchange.write_ciphertexts(cf, a, b)
+    a2, b2 = T.interchange.read_ciphertexts(cf)
+    assert np.array_equal(a2, a) and np.array_equal(b2, b)
+    clone = oracle.KeySet(oracle.params(p.n, p.N, p.k, p.l, p.bgbit, p.t, p.basebit, p.sigma_lwe, p.sigma_gsw, p.sigma_ks),
+                          raw_bsk=np.stack(bsk), raw_ksk=np.stack(ksk))
+    oa, ob = clone.gate_batch(oracle.EXACT_NTT, oracle.GATE_NAND, (a2, b2), (a2, b2), nthreads=2)
+    ph = (ob.astype(np.int64) - (oa.astype(np.int64) * lwe[None]).sum((-1, -2))).astype(np.int32)
+    assert np.array_equal(ph > 0, ~bits.astype(bool))          # NAND(x, x) = NOT x
+    with pytest.raises(ValueError):
+        T.interchange.read_keys(cf)

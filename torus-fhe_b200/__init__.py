@@ -6,6 +6,7 @@ Animesh005/Torus-FHE (3-gen-mk-tfhe/).  Import as `torus_fhe_b200` (the root shi
   engine.py    GPU context + key loading/broadcast + batch sharding
   tfhe3gen.py  the reference's exported names (gates, bootstrap, keys, encrypt/decrypt)
   circuits.py  level-batched integer circuits (mk_add_3gen, mk_sub_3gen, ...)
+  interchange.py binary key / ciphertext files a Julia host can write (fixtures from the real reference)
   workloads.py the reference's VolumeMatching workload on batched circuit instances
   csrc/        hand-written sm_100a kernels and the C ABI implementation
 """
@@ -17,3 +18,4 @@ from .tfhe3gen import engine_for, negacyclic_mul
 from .circuits import (gate_level, mk_int_add_3gen_gpu, mk_add_3gen, mk_add_3gen_v2, mk_inv_3gen, mk_sub_3gen, mk_less_3gen, mk_grt_3gen, mk_leq_3gen,
                        mk_geq_3gen, mk_int_add_with_carry_3gen, mk_int_mul_3gen)
 from .workloads import VolumeMatch, volume_match_plain
+from . import interchange
