@@ -67,6 +67,17 @@ int main() {
             const u32 d2 = (u32)(rnd() % (14ull * p)), k2 = rnd() % p, d1 = d % (14 * p);
             const u32 m2 = mont_mul2(d1, k, d2, k2, p, T.c.pinv_neg[pi]);
             if (m2 >= 3 * p || (u64)m2 * (((u64)1 << 32) % p) % p != ((u64)d1 * k % p + (u64)d2 * k2 % p) % p) { fails++; printf("FAIL mont2\n"); break; }
+            {   // eight products of the kernel's ranges accumulate in 64 bits without overflow and reduce to < 8p
+                u64 acc = 0, ref = 0;
+                for (int e = 0; e < 8; e++) {
+                    const u32 dd = it == 0 ? 14 * p - 1 : (u32)(rnd() % (14ull * p)), kk = it == 0 ? p - 1 : rnd() % p;
+                    acc += (u64)dd * kk;
+                    ref = (ref + (u64)dd * kk % p) % p;
+                }
+                const u32 mm = (u32)acc * T.c.pinv_neg[pi];
+                const u32 v = (u32)((acc + (u64)mm * p) >> 32);
+                if (acc + (u64)mm * p < acc || v >= 8 * p || (u64)v * (((u64)1 << 32) % p) % p != ref) { fails++; printf("FAIL acc64\n"); break; }
+            }
             u32 X = rnd() % (4 * p), Y = rnd() % (4 * p), X0 = X, Y0 = Y;
             ct_bfly<true>(X, Y, w, ws, p, 2 * p);
             const u64 wy = (u64)Y0 % p * w % p;
