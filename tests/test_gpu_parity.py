@@ -262,3 +262,35 @@ def test_repeated_launches_are_bitwise_deterministic(keys2, engine2):
     pick = [0, 1, 1183, 2367]
     ra, rb = keys2.gate_batch(1, 0, (x[0][pick], x[1][pick]), (y[0][pick], y[1][pick]))      # backend EXACT_NTT, gate NAND
     assert np.array_equal(first[0][pick], ra) and np.array_equal(first[1][pick], rb)
+
+
+@pytest.mark.parametrize("prm", [
+    dict(n=40, N=1024, k=1, l=1, bgbit=7, t=3, basebit=3),     # single party, one gadget level
+    dict(n=33, N=1024, k=3, l=2, bgbit=5, t=5, basebit=2),     # odd party count and LWE dimension
+    dict(n=24, N=1024, k=2, l=4, bgbit=3, t=2, basebit=4),     # t = 2: the stand-alone key-switch kernel (fused loop covers t = 3, 5)
+    dict(n=600, N=1024, k=2, l=3, bgbit=6, t=3, basebit=2),    # n + 1 > 576 columns: not fusable either
+], ids=["k1_l1", "k3_l2", "l4_t2", "n600"])
+def test_synthetic_parameter_sets_bit_exact(oracle, prm):
+    """Every template instantiation (l = 1..4), party counts 1..3, both key-switch paths: bootstrap bit-exact vs the exact oracle.
+    (Noise levels of these synthetic sets are irrelevant: parity is on identical key and ciphertext bytes.)"""
+    import torus_fhe_b200 as T
+    full = dict(prm, sigma_lwe=2.0 ** -20, sigma_gsw=2.0 ** -45, sigma_ks=2.0 ** -20)
+    ks = oracle.KeySet(full, seed=1234 + prm["n"], nthreads=os.cpu_count() or 8)
+    eng = make_engine(ks)
+    try:
+        r = np.random.default_rng(prm["n"])
+        G = 5
+        a = r.integers(-2 ** 31, 2 ** 31, (G, ks.k, ks.n)).astype(np.int32)
+        b = r.integers(-2 ** 31, 2 ** 31, G).astype(np.int32)
+        a[0] = 0                                                  # all rotations skipped
+        oa, ob = eng.ctx.bootstrap_batch(MU, a, b)
+        ra, rb = ks.bootstrap_batch(oracle.EXACT_NTT, MU, a, b)
+        assert np.array_equal(oa, ra) and np.array_equal(ob, rb)
+        acc = r.integers(-2 ** 63, 2 ** 63 - 1, size=(2, 2, 1024), dtype=np.int64)
+        elem = np.array([0, ks.k * ks.n - 1], np.int32)
+        got = eng.ctx.extprod_batch(elem, acc)
+        for g in range(2):
+            party, j = divmod(int(elem[g]), ks.n)
+            assert np.array_equal(got[g], ks.extprod(oracle.EXACT_SCHOOLBOOK, party, j, acc[g])), g
+    finally:
+        eng.close()
