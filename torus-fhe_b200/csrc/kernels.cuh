@@ -48,6 +48,12 @@ constexpr int TW_SMEM_BYTES = (TWB_WORDS + TWA_WORDS + LUT_WORDS) * 4;
 #ifndef MK_KEY_LD
 #define MK_KEY_LD __ldg
 #endif
+#ifndef MK_LOCKSTEP
+#define MK_LOCKSTEP 0
+#endif
+#ifndef MK_STAGGER_NS
+#define MK_STAGGER_NS 0
+#endif
 #ifndef MK_ACC64
 #define MK_ACC64 1      // 1: the 2L products of a point accumulate in 64 bits, one Montgomery reduction (0: one per pair; +0.4 % measured)
 #endif
@@ -481,13 +487,24 @@ __global__ void __maxnreg__(MK_MAXNREG) blind_rotate_kernel(BlindRotateArgs p) {
         }
     }
     gate_barrier(bar_id);
+#if MK_STAGGER_NS
+    // The gates of a CTA execute identical instruction streams and would run in phase (both in the IMAD-free decompose / CRT
+    // phases at the same time).  Start every other gate a fraction of a step later so that those phases interleave.
+    if (slot & 1) __nanosleep(MK_STAGGER_NS);
+#endif
     // mk_blind_rotate_3gen: parties outer, coefficients inner (:66-84); element index = party*n + j
     const size_t estride = bsk_elem_words(L);
     const size_t abase = (size_t)g * kn;
     int a_next = rotation(p.xa, p.ya, p.za, abase, 0u);
+    const bool cta_full = (blockIdx.x + 1) * GPC <= p.G;      // every gate slot of this CTA is active
     for (int it = 0; it < kn; it++) {
         const int a = a_next;
         if (it + 1 < kn) a_next = rotation(p.xa, p.ya, p.za, abase + it + 1, 0u);
+#if MK_LOCKSTEP
+        // keep the gates of a CTA on the same key element: their key loads then hit the same L1 lines (measured: running them
+        // out of phase costs 3 %)
+        if (cta_full && (it % MK_LOCKSTEP) == 0) asm volatile("bar.sync 15, %0;" ::"r"(GPC * TPG) : "memory");
+#endif
         if (a == 0) continue;   // :69 (uniform across the gate)
         extprod_step<L, true>(acc, dig, tiles, twB, p.bsk + (size_t)it * estride, a, p.bgbit, bar_id, pbar_id, gtid);
     }
