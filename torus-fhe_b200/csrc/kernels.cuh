@@ -1,80 +1,80 @@
 // kernels.cuh -- sm_100a kernels of the 3gen MK-TFHE bootstrapped-gate path.
 //
+//   blind_rotate_kernel    gate prologue + mod-switch + k*n mux-rotate steps + sample extraction + (fused) multi-key key switch
+//   keyswitch_kernel       stand-alone key switch (parity hook; parameter sets the fused epilogue does not cover)
 //   bsk_transform_kernel   one-time: int64 key polynomials -> three NTT-domain residue polynomials, streaming layout
-//   blind_rotate_kernel    gate prologue + mod-switch + k*n mux-rotate steps + sample extraction
-//   keyswitch_kernel       multi-key LWE key switch (gather-accumulate over ksk rows)
-//   extprod_kernel / negacyclic_mul_kernel   parity hooks built from the same device code
+//   extprod_kernel / negacyclic_mul_kernel   parity hooks / key-generation primitive built from the same device code
 //
 // Reference semantics (3-gen-mk-tfhe/src/): 3gen_mk_internals.jl:59-116, tgsw_3gen.jl:102-113, tgsw.jl:112-138,
 // rlwe.jl:70-74, keyswitch.jl:45-80, mk_internals.jl:730-744, numeric-functions.jl:70-73,109-111.
 //
-// Work decomposition of the blind rotation: one gate = 3 warps (one per RNS prime, 96 threads); a CTA holds GPC
-// gates plus one shared-memory copy of the per-lane twiddle table.  Per gate, resident in shared memory for all
-// k*n steps: the Torus64 accumulator (2 x 1024 x 8 B), the current gadget digits (2l x 1024 bytes) and one padded
-// 32x33 word tile per warp (NTT transposes, then the inverse transforms' residues for the CRT).
+// Work decomposition of the blind rotation: one gate = 6 warps, one per (RNS prime, output polynomial);
+// a CTA holds 2 gates (12 warps at 168 registers, one CTA per SM) plus one shared-memory copy of the twiddle tables.  Per gate,
+// resident in shared memory for all k*n steps: the Torus64 accumulator (2 x 1024 x 8 B), the current gadget digits
+// (2l x 1024 bytes) and one padded 32x33 word tile per warp (NTT transposes, the exchange of transformed digits between the
+// two warps of a prime, then the inverse transforms' residues for the CRT).
 #pragma once
 #include <cuda_runtime.h>
 #include "ntt_rns.cuh"
 
 namespace mk {
 
-
-
 using rns::uint2_;
 
 constexpr int N = rns::N;
-constexpr int TWB_WORDS = rns::NP * 2 * 31 * 32 * 2; // per-lane pass-B twiddle table [prime][dir][31][32] of (w, w') = 47616 B
-constexpr int TWA_WORDS = rns::NP * 2 * 32 * 2;      // pass-A twiddles [prime][dir][32 (31 used)] of (w, w') staged in shared memory = 1536 B
-// stage-0 products w0 * (digit - Bg/2) mod p for every biased digit byte, one column per lane (lut[prime][byte][lane]) so that
-// the data-dependent lookups never conflict on a shared-memory bank (Bg <= 128 keeps that at 48 KB), or compact
-#ifndef MK_LUT_REPL
-#define MK_LUT_REPL 1        // measured: the 48 KB per-lane replica is slower (smaller L1 for the key stream) than 3-way bank conflicts
-#endif
-constexpr int LUT_REPL = MK_LUT_REPL;                 // 32: replicated per lane; 1: compact
-constexpr int LUT_BYTES_MAX = LUT_REPL == 32 ? 128 : 256;
-constexpr int LUT_WORDS = rns::NP * LUT_BYTES_MAX * LUT_REPL;
-constexpr int TW_SMEM_BYTES = (TWB_WORDS + TWA_WORDS + LUT_WORDS) * 4;
 
-// Warps per gate.  3: one warp per prime (32 coefficients per thread + both outputs' accumulators = 96 live registers,
-// 4 gates x 3 warps per SM at 168 registers).  6: one warp per (prime, output polynomial): the two warps of a prime split
-// the forward transforms by parity of the digit polynomial, exchange the transformed digits through their tiles, and each
-// accumulates and inverse-transforms ONE output with one Montgomery reduction per pair of products (64 live registers,
-// 2 gates x 6 warps per SM at 168 registers).  Measured (profiles/ab_r1.txt): 6 warps / 2 gates 22.3 k gates/s,
-// 3 warps / 4 gates 20.6 k, 6 warps / 3 gates (96 registers, spills) 20.7 k.
-// cache policy of the two key streams (A/B knobs): __ldg = read-only path, allocating in L1; __ldcs = streaming (evict first)
-#ifndef MK_KS_LD
-#define MK_KS_LD __ldg
-#endif
-#ifndef MK_KEY_LD
-#define MK_KEY_LD __ldg
-#endif
-#ifndef MK_LOCKSTEP
-#define MK_LOCKSTEP 0
-#endif
-#ifndef MK_STAGGER_NS
-#define MK_STAGGER_NS 0
-#endif
-#ifndef MK_ACC64
-#define MK_ACC64 1      // 1: the 2L products of a point accumulate in 64 bits, one Montgomery reduction (0: one per pair; +0.4 % measured)
-#endif
+// ---- tuning knobs; every default below was chosen by an A/B run recorded in profiles/ab_r1.txt ---------------------------
+// Warps per gate.  6: one warp per (prime, output polynomial): the two warps of a prime split the forward transforms by parity
+// of the digit polynomial, exchange the transformed digits through their tiles, and each accumulates and inverse-transforms ONE
+// output (64 live registers).  3: one warp per prime doing both outputs (96 live registers; 4 gates per CTA).
 #ifndef MK_WPG
 #define MK_WPG 6
 #endif
-constexpr int WPG = MK_WPG;
-constexpr int TPG = 32 * WPG;                        // threads per gate
 #ifndef MK_MAX_GPC
 #define MK_MAX_GPC (MK_WPG == 6 ? 2 : 4)            // gates per CTA: 12 warps per SM so that each thread gets 168 registers
 #endif
-constexpr int MAX_GPC = MK_MAX_GPC;
-#ifndef MK_S_UNROLL
-#define MK_S_UNROLL (MK_WPG == 6 ? 1 : 2)           // unroll factor of the loop over digit polynomials
-#endif
-constexpr int S_UNROLL = MK_S_UNROLL;
 // register cap: the largest multiple of 8 with ceil(warps / 4) * 4 * 32 * regs <= 65536 (the register file is allocated in
 // units of 4 warps); 12 warps -> 168.  More registers measurably help even without spills (128: -7 %).
 #ifndef MK_MAXNREG
 #define MK_MAXNREG 168
 #endif
+#ifndef MK_S_UNROLL
+#define MK_S_UNROLL (MK_WPG == 6 ? 1 : 2)           // unroll factor of the loop over digit polynomials
+#endif
+#ifndef MK_ACC64
+#define MK_ACC64 1          // 1: the 2L products of a point accumulate in 64 bits, one Montgomery reduction; 0: one per pair
+#endif
+#ifndef MK_LUT_REPL
+#define MK_LUT_REPL 1       // 32: per-lane replica of the digit table (conflict-free, 48 KB) -- slower: it shrinks the L1
+#endif
+// cache policy of the two key streams: __ldg = read-only path, allocating in L1 (the gates of a CTA share key lines there);
+// __ldcs = streaming
+#ifndef MK_KEY_LD
+#define MK_KEY_LD __ldg
+#endif
+#ifndef MK_KS_LD
+#define MK_KS_LD __ldg
+#endif
+#ifndef MK_LOCKSTEP
+#define MK_LOCKSTEP 0       // n > 0: CTA-wide barrier every n steps to keep the gates on the same key element (measured: loses)
+#endif
+#ifndef MK_STAGGER_NS
+#define MK_STAGGER_NS 0     // start odd gate slots this many ns late to interleave the IMAD-free phases (measured: loses)
+#endif
+// ----------------------------------------------------------------------------------------------------------------------------
+constexpr int WPG = MK_WPG;
+constexpr int TPG = 32 * WPG;                        // threads per gate
+constexpr int MAX_GPC = MK_MAX_GPC;
+constexpr int S_UNROLL = MK_S_UNROLL;
+
+// shared-memory tables, staged once per CTA
+constexpr int TWB_WORDS = rns::NP * 2 * 31 * 32 * 2; // per-lane pass-B twiddles [prime][dir][31][32] of (w, w') = 47616 B
+constexpr int TWA_WORDS = rns::NP * 2 * 32 * 2;      // warp-uniform pass-A twiddles [prime][dir][32 (31 used)] of (w, w') = 1536 B
+// stage-0 products w0 * (digit - Bg/2) mod p for every biased digit byte: lut[prime][byte] (or [prime][byte][lane] when replicated)
+constexpr int LUT_REPL = MK_LUT_REPL;
+constexpr int LUT_BYTES_MAX = LUT_REPL == 32 ? 128 : 256;
+constexpr int LUT_WORDS = rns::NP * LUT_BYTES_MAX * LUT_REPL;
+constexpr int TW_SMEM_BYTES = (TWB_WORDS + TWA_WORDS + LUT_WORDS) * 4;
 
 __constant__ rns::Consts c_rns;
 
