@@ -269,10 +269,11 @@ def run_ours(args):
         ct_io = 2 * (k * n + 1) * 4 + (N + 1) * 4
         alg_bytes = G * (bsk_1limb + ct_io)
         achieved = alg_bytes / (br_ms * 1e-3) / 1e9
-        # algorithmic IMAD-pipe slots per gate of the three-prime RNS formulation: per blind-rotate step
-        # (6l + 6) NTTs x 5120 butterflies x 4 slots (IMAD.HI is half rate), 12l x 1024 Montgomery products x 5 slots,
-        # 2048 CRT lifts x 17 slots
-        imad_slots = k * n * ((6 * l + 6) * 5120 * 4 + 12 * l * 1024 * 5 + 2 * 1024 * 17)
+        # algorithmic IMAD-pipe slots per gate of the three-prime RNS formulation, counting only work the
+        # formulation cannot avoid: per blind-rotate step 6l forward NTTs of 4608 multiplying butterflies (the first stage of a digit
+        # transform is a table lookup) and 6 inverse NTTs of 5120, 4 slots each (IMAD.HI is half rate); 12l x 1024 pointwise products
+        # accumulated in 64 bits (IMAD.WIDE = 2 slots) + 6 x 1024 Montgomery reductions (3 slots); 2048 CRT lifts (17 slots)
+        imad_slots = k * n * ((6 * l * 4608 + 6 * 5120) * 4 + 12 * l * 1024 * 2 + 6 * 1024 * 3 + 2 * 1024 * 17)
         imad_peak = 18.26e12       # measured: tools/pipe_ubench.cu -> profiles/pipe_ubench_r1.txt (62.8 IMAD lanes/clk/SM)
         ncu_traffic = {"bytes": 1.594e9, "gates_in_captured_launch": 2368, "waves_in_captured_launch": 8,
                        "source": "profiles/ncu_r1_f_blind_rotate.txt (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture): "
@@ -300,7 +301,9 @@ def run_ours(args):
                              "kernel_share_of_step": br_ms / (ms / args.steps),
                              "integer_bound": {"bound": "imad_pipe", "algorithmic_slots_per_gate": imad_slots,
                                                "achieved": G * imad_slots / (br_ms * 1e-3) / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-slots/s",
-                                               "frac": G * imad_slots / (br_ms * 1e-3) / imad_peak}},
+                                               "frac": G * imad_slots / (br_ms * 1e-3) / imad_peak,
+                                               "ncu_fma_pipe_busy": 0.68, "ncu_source": "profiles/ncu_r1_f_opmix.txt (executed fma-pipe slots incl. "
+                                               "address/move overhead: 15.6 k warp-slots per gate-step)"}},
                 "clocks": clocks, "decryptions_correct": ok}
         if world == 1 and not args.no_cpu_baseline and args.parties == 2:
             O, oks = oracle_keyset()

@@ -112,6 +112,9 @@ int set_attrs(mktfhe_ctx* c) {
     const int sm = (int)br_smem_bytes(c);
 #define SET_ATTR(L, GPC, dummy)                                                                                                    \
     CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));             \
+    if (getenv("MKTFHE_B200_CARVEOUT"))                                                                                            \
+        CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_kernel<L, GPC>, cudaFuncAttributePreferredSharedMemoryCarveout,            \
+                                       atoi(getenv("MKTFHE_B200_CARVEOUT"))));                                                     \
     CU_TRY(c, cudaFuncSetAttribute(mk::extprod_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     MK_DISPATCH_L(c, SET_ATTR, 0)
 #undef SET_ATTR
