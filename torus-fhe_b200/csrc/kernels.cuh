@@ -44,6 +44,9 @@ constexpr int N = rns::N;
 #ifndef MK_ACC64
 #define MK_ACC64 1          // 1: the 2L products of a point accumulate in 64 bits, one Montgomery reduction; 0: one per pair
 #endif
+#ifndef MK_CRT_ILP
+#define MK_CRT_ILP (MK_WPG == 6 ? 11 : 6)   // Garner chains interleaved per thread in the CRT phase; 11 = all of a thread's coefficients at once
+#endif
 #ifndef MK_LUT_REPL
 #define MK_LUT_REPL 1       // 32: per-lane replica of the digit table (conflict-free, 48 KB) -- slower: it shrinks the L1
 #endif
@@ -336,11 +339,27 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
 #pragma unroll
         for (int r = 0; r < 32; r++) tile[32 * r + lane] = x[r];   // residues in coefficient order
         gate_barrier(bar_id);
-        for (int idx = gtid; idx < 2 * N; idx += TPG) {
-            const int oo = idx >> 10, i = idx & (N - 1);
-            const u32* rt = tiles + oo * rns::TILE_WORDS;      // tile of warp (prime w', output oo) = tiles[(2 w' + oo)]
-            const u64 R = rns::crt_lift(rt[i], rt[2 * rns::TILE_WORDS + i], rt[4 * rns::TILE_WORDS + i], c_rns.crt);
-            acc[idx] = MUX ? acc[idx] + R : R;
+        // Garner's lift is one long dependent chain per coefficient: CRT_ILP coefficients are interleaved per thread
+        constexpr int CRT_ILP = MK_CRT_ILP, CRT_ROUNDS = (2 * N + TPG * CRT_ILP - 1) / (TPG * CRT_ILP);
+#pragma unroll 1
+        for (int round = 0; round < CRT_ROUNDS; round++) {
+            u32 r0[CRT_ILP], r1[CRT_ILP], r2[CRT_ILP];
+            u64 old[CRT_ILP];
+#pragma unroll
+            for (int j = 0; j < CRT_ILP; j++) {
+                const int idx = gtid + (round * CRT_ILP + j) * TPG;
+                const int cl = idx < 2 * N ? idx : 0;           // clamp: out-of-range slots compute on coefficient 0 and are dropped
+                const int oo = cl >> 10, i = cl & (N - 1);
+                const u32* rt = tiles + oo * rns::TILE_WORDS;  // tile of warp (prime w', output oo) = tiles[(2 w' + oo)]
+                r0[j] = rt[i]; r1[j] = rt[2 * rns::TILE_WORDS + i]; r2[j] = rt[4 * rns::TILE_WORDS + i];
+                old[j] = MUX ? acc[cl] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < CRT_ILP; j++) {
+                const int idx = gtid + (round * CRT_ILP + j) * TPG;
+                const u64 R = rns::crt_lift(r0[j], r1[j], r2[j], c_rns.crt);
+                if (idx < 2 * N) acc[idx] = old[j] + R;
+            }
         }
         gate_barrier(bar_id);
     } else {
