@@ -514,11 +514,19 @@ __global__ void __maxnreg__(MK_MAXNREG) blind_rotate_kernel(BlindRotateArgs p) {
     // mk_blind_rotate_3gen: parties outer, coefficients inner (:66-84); element index = party*n + j
     const size_t estride = bsk_elem_words(L);
     const size_t abase = (size_t)g * kn;
-    int a_next = rotation(p.xa, p.ya, p.za, abase, 0u);
+    // the mask words of step it + 1 are loaded (raw) while step it runs and only combined / mod-switched when needed, so the
+    // load latency never sits on the critical path
+    int32_t rx = __ldg(p.xa + abase), ry = lin.cy ? __ldg(p.ya + abase) : 0, rz = lin.cz ? __ldg(p.za + abase) : 0;
+#if MK_LOCKSTEP
     const bool cta_full = (blockIdx.x + 1) * GPC <= p.G;      // every gate slot of this CTA is active
+#endif
     for (int it = 0; it < kn; it++) {
-        const int a = a_next;
-        if (it + 1 < kn) a_next = rotation(p.xa, p.ya, p.za, abase + it + 1, 0u);
+        const int a = mod_switch_2N((int32_t)((uint32_t)lin.cx * (uint32_t)rx + (uint32_t)lin.cy * (uint32_t)ry + (uint32_t)lin.cz * (uint32_t)rz));
+        if (it + 1 < kn) {
+            rx = __ldg(p.xa + abase + it + 1);
+            if (lin.cy) ry = __ldg(p.ya + abase + it + 1);
+            if (lin.cz) rz = __ldg(p.za + abase + it + 1);
+        }
 #if MK_LOCKSTEP
         // keep the gates of a CTA on the same key element: their key loads then hit the same L1 lines (measured: running them
         // out of phase costs 3 %)
