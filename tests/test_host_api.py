@@ -172,3 +172,66 @@ def test_interchange_roundtrip(tmp_path, toy_keys, oracle):
     assert np.array_equal(ph > 0, ~bits.astype(bool))          # NAND(x, x) = NOT x
     with pytest.raises(ValueError):
         T.interchange.read_keys(cf)
+
+
+class _PBit:
+    """Plaintext stand-in with MKLweSample's constructor / indexing surface (batch of booleans in .b, dummy .a)."""
+
+    def __init__(self, params, a, b, current_variance=0.0):
+        self.params, self.b, self.current_variance = params, np.asarray(b, dtype=bool), 0.0
+        self.a = np.zeros(self.b.shape + (1, 1), np.int32)
+
+    @property
+    def batch_shape(self):
+        return self.b.shape
+
+    def __getitem__(self, idx):
+        return _PBit(None, None, self.b[idx])
+
+
+def _pbits(v, W):
+    return [_PBit(None, None, ((np.asarray(v) >> i) & 1).astype(bool)) for i in range(W)]
+
+
+def _plain_level_p(bk, ks, jobs):
+    return [_PBit(None, None, o.b) for o in _plain_level(bk, ks, jobs)]
+
+
+def test_truncated_multiplier_and_conv_layer_wiring(monkeypatch):
+    """mk_int_mul_lo_3gen / add_mod_3gen / enc_conv2d on plain bits == integer arithmetic mod 2^WIDTH, for every shard split."""
+    from torus_fhe_b200 import workloads
+    calls = []
+
+    def counting_level(bk, ks, jobs):
+        calls.append(sum(int(np.prod(np.broadcast_shapes(x.b.shape, y.b.shape), dtype=np.int64)) for _, x, y in jobs))
+        return _plain_level_p(bk, ks, jobs)
+    monkeypatch.setattr(circuits, "gate_level", counting_level)
+    monkeypatch.setattr(workloads, "_cat", lambda xs, axis: _PBit(None, None, np.concatenate([x.b for x in xs], axis)))
+    r = np.random.default_rng(9)
+    for W in (1, 2, 3, 5, 8):
+        a, b = r.integers(-(1 << (W - 1)), 1 << (W - 1), 200) if W > 1 else r.integers(-1, 1, 200), r.integers(-(1 << (W - 1)), max(1 << (W - 1), 1), 200)
+        wrap = lambda v: ((v + (1 << (W - 1))) % (1 << W)) - (1 << (W - 1))
+        assert np.array_equal(_val(circuits.add_mod_3gen(None, None, _pbits(a, W), _pbits(b, W), W), W), wrap(a + b))
+        calls.clear()
+        assert np.array_equal(_val(circuits.mk_int_mul_lo_3gen(None, None, _pbits(a, W), _pbits(b, W), W), W), wrap(a * b))
+        add = lambda w: 1 if w == 1 else 5 * w - 6
+        assert sum(calls) == 200 * (W * (W + 1) // 2 + sum(add(W - i) for i in range(1, W)))
+    W, H, C, K = 4, 7, 2, 3
+    inp, ker = r.integers(-8, 8, (H, H)), r.integers(-8, 8, (C, K, K))
+    zero = _PBit(None, None, False)
+    for stride, padding in ((1, 0), (2, 0), (1, 1), (2, 1)):
+        exp = workloads.conv2d_plain(inp, ker, stride, padding, W)
+        monkeypatch.setattr(workloads, "_pad", lambda x, z, p: _PBit(None, None, np.pad(x.b, p)))
+        calls.clear()
+        out = workloads.enc_conv2d(None, None, _pbits(inp, W), zero, _pbits(ker, W), stride, padding, W)
+        assert out[0].b.shape == exp.shape == workloads.conv2d_output_shape((H, H), (C, K, K), stride, padding)
+        assert np.array_equal(_val(out, W), exp)
+        assert sum(calls) == workloads.conv2d_gate_count((H, H), (C, K, K), stride, padding, W)
+        # sharded over 3 ranks: the slices tile the flattened outputs and equal the unsharded result
+        got = np.zeros(exp.size, np.int64)
+        for rank in range(3):
+            lo, hi, bits = workloads.enc_conv2d(None, None, _pbits(inp, W), zero, _pbits(ker, W), stride, padding, W, shard=(3, rank))
+            got[lo:hi] = _val(bits, W)
+        assert np.array_equal(got.reshape(exp.shape), exp)
+    # plaintext model sanity: one known window
+    assert workloads.conv2d_plain(np.arange(9).reshape(3, 3), np.ones((1, 3, 3), int), 1, 0, 8)[0, 0, 0] == 36

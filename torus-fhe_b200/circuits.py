@@ -151,3 +151,39 @@ def mk_int_mul_3gen(bk, ks, a, b, ZERO, WIDTH):
     for i in range(WIDTH + 1):
         result[i + ctr] = mk_copy_3gen(tmpArr[i])
     return [mk_copy_3gen(result[i]) for i in range(WIDTH)]
+
+
+def mk_int_add_3gen(bk, ks, a, b, Cin, WIDTH):
+    """The adder `enc_conv2d` calls (3gen_mk_gates.jl:389; its definition at :158-180 is commented out in the reference): same
+    ripple-carry circuit as mk_add_3gen."""
+    return mk_add_3gen(bk, ks, a, b, Cin, WIDTH)
+
+
+def add_mod_3gen(bk, ks, a, b, w):
+    """a + b mod 2^w on w-bit operands: the ripple adder of 3gen_mk_gates.jl:291-310 without the carry-in (bit 0 is a half adder)
+    and without the gates that only feed the dropped carry-out: 5w - 6 gates (1 for w = 1) on 2w - 2 levels."""
+    if w == 1:
+        return gate_level(bk, ks, [("xor", a[0], b[0])])
+    lvl0 = gate_level(bk, ks, [("xor", a[i], b[i]) for i in range(w)] + [("and", a[i], b[i]) for i in range(w - 1)])
+    t1, t2 = lvl0[:w], lvl0[w:]
+    result, cin = [t1[0]], t2[0]
+    for i in range(1, w - 1):
+        s, t3 = gate_level(bk, ks, [("xor", t1[i], cin), ("and", t1[i], cin)])
+        (cin,) = gate_level(bk, ks, [("or", t2[i], t3)])
+        result.append(s)
+    result += gate_level(bk, ks, [("xor", t1[w - 1], cin)])
+    return result
+
+
+def mk_int_mul_lo_3gen(bk, ks, a, b, WIDTH):
+    """Low WIDTH bits of a * b (two's-complement wrap, i.e. the product of WIDTH-bit ints mod 2^WIDTH): the shift-and-add array the
+    reference's mk_int_mul_3gen (3gen_mk_gates.jl:312-362) aims at, with its last-row slip corrected and the partial products
+    that cannot reach the kept bits left out.  WIDTH (WIDTH + 1) / 2 ANDs in one launch, then WIDTH - 1 shrinking adders."""
+    prods = gate_level(bk, ks, [("and", a[j], b[i]) for i in range(WIDTH) for j in range(WIDTH - i)])
+    rows, pos = [], 0
+    for i in range(WIDTH):
+        rows.append(prods[pos:pos + WIDTH - i]); pos += WIDTH - i
+    acc = list(rows[0])
+    for i in range(1, WIDTH):
+        acc[i:] = add_mod_3gen(bk, ks, acc[i:], rows[i], WIDTH - i)
+    return acc

@@ -486,6 +486,28 @@ def engine_for(bk, ks, device=None):
     return eng
 
 
+class RemoteKeys:
+    """Stand-in for (bk, ks) on a rank whose engine received the keys by broadcast (Engine.broadcast_keys) instead of from host
+    arrays: the gate API finds the engine through it."""
+
+    def __init__(self, eng):
+        self._engine = ((id(self),), eng)
+        self.tgsw_params, self.rlwe_params = tgsw_parameters(eng.params), rlwe_parameters(eng.params)
+
+    @staticmethod
+    def pair(eng):
+        r = RemoteKeys(eng)
+        bk, ks = [r] * eng.params.max_parties, [r] * eng.params.max_parties
+        r._engine = ((tuple(id(b) for b in bk), tuple(id(k) for k in ks)), eng)
+        return bk, ks
+
+
+def attach_engine(bk, ks, eng):
+    """Make `eng` (already holding these keys) the engine the gate API uses for (bk, ks)."""
+    bk[0]._engine = ((tuple(id(b) for b in bk), tuple(id(k) for k in ks)), eng)
+    return eng
+
+
 def _flat(x, k, n):
     return x.a.reshape(-1, k, n), x.b.reshape(-1)
 
