@@ -164,6 +164,10 @@ def test_full_batch_properties(keys2, engine2):
     perm = r.permutation(G)[:512]
     pa, pb = engine2.ctx.gate_batch(T._cabi.GATE_NAND, (x[0][perm], x[1][perm]), (y[0][perm], y[1][perm]))
     assert np.array_equal(pa, oa[perm]) and np.array_equal(pb, ob[perm])
+    # batches that fit on the SMs one gate each take the one-gate-per-CTA launch: same bits
+    q = perm[:100]
+    qa, qb = engine2.ctx.gate_batch(T._cabi.GATE_NAND, (x[0][q], x[1][q]), (y[0][q], y[1][q]))
+    assert np.array_equal(qa, oa[q]) and np.array_equal(qb, ob[q])
 
 
 def test_ragged_and_empty_batches(keys2, engine2):

@@ -41,6 +41,7 @@ struct mktfhe_ctx {
     size_t ksk_bytes = 0;
     rns::uint2_* d_twB = nullptr;
     int gpc = 1;                 // gates per CTA of the blind-rotate / external-product kernels
+    int num_sms = 0;
     bool fuse_ks = true;         // key switch as the epilogue of the blind-rotate kernel (MKTFHE_B200_FUSE_KS=0 disables: A/B runs)
     std::vector<char> bsk_loaded, ksk_loaded;
     bool ready = false;
@@ -118,10 +119,25 @@ int set_attrs(mktfhe_ctx* c) {
     CU_TRY(c, cudaFuncSetAttribute(mk::extprod_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     MK_DISPATCH_L(c, SET_ATTR, 0)
 #undef SET_ATTR
+    // small batches: one gate per CTA (see launch_blind_rotate)
+    const int sm1 = (int)(mk::TW_SMEM_BYTES + mk::gate_smem_bytes(c->prm.l));
+#define SET_ATTR1(L, GPC, dummy) CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_kernel<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm1));
+    MK_DISPATCH_L(c, SET_ATTR1, 0)
+#undef SET_ATTR1
     return MKTFHE_OK;
 }
 
 void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G) {
+    if (c->gpc > 1 && G <= (size_t)c->num_sms) {
+        // a batch that fits on the SMs one gate each: a gate alone on an SM finishes ~25 % sooner than two sharing one, so narrow
+        // circuit levels (and single bootstraps) run one gate per CTA; bit-identical results
+        const size_t sm1 = mk::TW_SMEM_BYTES + mk::gate_smem_bytes(c->prm.l);
+#define LAUNCH_BR1(L, GPC, dummy) mk::blind_rotate_kernel<L, 1><<<(unsigned)G, mk::TPG, sm1, c->stream>>>(a)
+        MK_DISPATCH_L(c, LAUNCH_BR1, 0)
+#undef LAUNCH_BR1
+        c->launches++;
+        return;
+    }
     const size_t sm = br_smem_bytes(c);
     const unsigned grid = (unsigned)((G + c->gpc - 1) / c->gpc);
 #define LAUNCH_BR(L, GPC, dummy) mk::blind_rotate_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, c->stream>>>(a)
@@ -213,6 +229,7 @@ int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
     const int B1 = (1 << params->basebit) - 1;
     c->bsk_bytes = (size_t)params->k * params->n * mk::bsk_elem_words(params->l) * sizeof(u32);
     c->gpc = mk::gpc_for(params->l);
+    cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
     if (const char* e = getenv("MKTFHE_B200_FUSE_KS")) c->fuse_ks = atoi(e) != 0;
     const size_t ks_stride = mk::ks_row_stride(params->n);   // rows padded to 16 bytes on the device
     c->ksk_bytes = (size_t)params->k * mk::N * params->t * B1 * ks_stride * sizeof(int32_t);

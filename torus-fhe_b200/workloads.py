@@ -89,7 +89,7 @@ def _take(x, idx):
     """x[idx] for a tuple of integer index arrays over the leading (batch) dimensions, host or device sample."""
     if _is_gpu(x):
         import torch
-        idx = tuple(torch.as_tensor(np.asarray(i), device=x.a.device) for i in idx)
+        idx = tuple(torch.as_tensor(np.array(i), device=x.a.device) for i in idx)
     return x[idx]
 
 
