@@ -67,6 +67,10 @@ constexpr int N = rns::N;
 // ----------------------------------------------------------------------------------------------------------------------------
 constexpr int WPG = MK_WPG;
 constexpr int TPG = 32 * WPG;                        // threads per gate
+// Latency launch (batches that fit on the SMs one gate each, l = 2): 12 warps per gate, one per (prime, output polynomial, digit
+// pair), so the two forward transforms a throughput warp runs back to back run side by side; the partial sums of the two digit
+// pairs are combined through a tile before the inverse transform.  Same arithmetic, bit-identical results.
+constexpr int LAT_WPG = 12;
 constexpr int MAX_GPC = MK_MAX_GPC;
 constexpr int S_UNROLL = MK_S_UNROLL;
 
@@ -91,7 +95,9 @@ __host__ __device__ inline size_t bsk_elem_words(int l) { return (size_t)rns::NP
 // row is read with 16-byte loads -- followed by one all-zero row
 __host__ __device__ constexpr int ks_row_stride(int n) { return (n + 1 + 3) & ~3; }
 // per gate: Torus64 accumulator, packed digits, one padded tile per warp
-__host__ __device__ constexpr size_t gate_smem_bytes(int l) { return (size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)WPG * rns::TILE_WORDS * 4; }
+__host__ __device__ constexpr size_t gate_smem_bytes(int l, int wpg = WPG) {
+    return (size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)wpg * rns::TILE_WORDS * 4;
+}
 // gates per CTA: as many as fit in the 227 KB of shared memory beside the twiddle tables (at most MAX_GPC)
 __host__ __device__ constexpr int gpc_for(int l) {
     int g = MAX_GPC;
@@ -132,7 +138,8 @@ __host__ __device__ inline GateLinear gate_linear(int gate) {
     }
 }
 
-__device__ __forceinline__ void gate_barrier(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(TPG) : "memory"); }
+template <int W = WPG>
+__device__ __forceinline__ void gate_barrier(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(32 * W) : "memory"); }
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 // decode_message(x, 2N), numeric-functions.jl:70-73 (wrapping add, arithmetic shift)
@@ -207,13 +214,13 @@ __device__ __forceinline__ void warp_ntt_inv(u32 (&x)[32], u32* tile, const uint
 
 // Phase 1 of a step: rotate-subtract and gadget-decompose (tgsw.jl:112-138); digits biased to [0, Bg) and packed 4 per word
 // in the order the NTT warps read them (dig: [2L][8][32] words).
-template <int L, bool MUX>
+template <int L, bool MUX, int W = WPG>
 __device__ __forceinline__ void decompose_phase(const u64* __restrict__ acc, u32* __restrict__ dig, int a, int bgbit, int gtid) {
     u64 off = 0;
 #pragma unroll
     for (int q = 1; q <= L; q++) off += ((u64)1 << (64 - q * bgbit)) << (bgbit - 1);   // tgsw.jl:24-30
     const u32 dmask = (1u << bgbit) - 1;
-    for (int task = gtid; task < 512; task += TPG) {
+    for (int task = gtid; task < 512; task += 32 * W) {
         const int c = task >> 8, rh = (task >> 5) & 7, ln = task & 31;
         const u64* poly = acc + c * N;
         u32 packed[L];
@@ -260,14 +267,43 @@ __device__ __forceinline__ void load_digits(u32 (&x)[32], const u32* __restrict_
 //   MUX = true : acc += ExtProd(X^a * acc - acc, key)   (mk_mux_rotate_3gen, 3gen_mk_internals.jl:59-62)
 //   MUX = false: acc  = ExtProd(acc, key)
 // acc: [2][N] u64, [0] = mask, [1] = body.  tiles: [WPG][TILE_WORDS].  bar_id: gate barrier; pbar_id: first pair barrier.
-template <int L, bool MUX>
+// Garner's lift of both output polynomials by all threads of the gate, added to (MUX) or stored in the accumulator.  The residues
+// of output oo sit in coefficient order at tiles + oo * out_stride (+ off1 / off2 words for primes 1 / 2).  The lift is one long dependent
+// chain per coefficient: CRT_ILP coefficients are interleaved per thread.
+template <bool MUX, int W, int CRT_ILP>
+__device__ __forceinline__ void crt_phase(u64* __restrict__ acc, const u32* __restrict__ tiles, int out_stride, int off1, int off2, int gtid) {
+    constexpr int T = 32 * W, CRT_ROUNDS = (2 * N + T * CRT_ILP - 1) / (T * CRT_ILP);
+#pragma unroll 1
+    for (int round = 0; round < CRT_ROUNDS; round++) {
+        u32 r0[CRT_ILP], r1[CRT_ILP], r2[CRT_ILP];
+        u64 old[CRT_ILP];
+#pragma unroll
+        for (int j = 0; j < CRT_ILP; j++) {
+            const int idx = gtid + (round * CRT_ILP + j) * T;
+            const int cl = idx < 2 * N ? idx : 0;           // clamp: out-of-range slots compute on coefficient 0 and are dropped
+            const int oo = cl >> 10, i = cl & (N - 1);
+            const u32* rt = tiles + oo * out_stride;
+            r0[j] = rt[i]; r1[j] = rt[off1 + i]; r2[j] = rt[off2 + i];
+            old[j] = MUX ? acc[cl] : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < CRT_ILP; j++) {
+            const int idx = gtid + (round * CRT_ILP + j) * T;
+            const u64 R = rns::crt_lift(r0[j], r1[j], r2[j], c_rns.crt);
+            if (idx < 2 * N) acc[idx] = old[j] + R;
+        }
+    }
+}
+
+template <int L, bool MUX, int W = WPG>
 __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restrict__ dig, u32* __restrict__ tiles,
                                              const uint2_* __restrict__ twB, const u32* __restrict__ key, int a, int bgbit,
                                              int bar_id, int pbar_id, int gtid) {
+    static_assert(W == 3 || W == 6 || (W == LAT_WPG && L == 2), "warps per gate: 3, 6, or 12 (l = 2 only)");
     const int gw = gtid >> 5, lane = gtid & 31;
-    const int w = WPG == 6 ? gw >> 1 : gw;            // prime of this warp
-    decompose_phase<L, MUX>(acc, dig, a, bgbit, gtid);
-    gate_barrier(bar_id);
+    const int w = W == 12 ? gw >> 2 : W == 6 ? gw >> 1 : gw;            // prime of this warp
+    decompose_phase<L, MUX, W>(acc, dig, a, bgbit, gtid);
+    gate_barrier<W>(bar_id);
     const u32 p = c_rns.p[w], pinv = c_rns.pinv_neg[w];
     const u32 p4 = rns::keep_in_register(4 * p);
     u32* tile = tiles + gw * rns::TILE_WORDS;
@@ -278,7 +314,53 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
     const u32* lut = reinterpret_cast<const u32*>(twB) + TWB_WORDS + TWA_WORDS + w * (LUT_BYTES_MAX * LUT_REPL) + (LUT_REPL == 32 ? lane : 0);
     const uint4* kp = reinterpret_cast<const uint4*>(key + (size_t)w * (2 * L * 2 * N)) + lane;   // K[prime][s][out][slot]
     const u32 bias = p - (1u << (bgbit - 1));
-    if (WPG == 6) {
+    if constexpr (W == LAT_WPG) {
+        // ---- phase 2 (12 warps): warp (prime w, output o, digit pair i) = 4 w + 2 o + (i ^ (w & 1)) transforms digit polynomial
+        // 2i + o, reads 2i + 1 - o from its partner (w, 1 - o, i), and forms the partial sum of output o over this pair.  The
+        // (w & 1) twist spreads the six i = 0 warps, which alone run the inverse transforms, over all four schedulers.
+        const int o = (gw >> 1) & 1, i = (gw ^ w) & 1;
+        const u32* ptile = tiles + (gw ^ 2) * rns::TILE_WORDS;
+        const int pb = pbar_id + 2 * w + i, cb = pbar_id + 6 + 2 * w + o;
+        const int s_own = 2 * i + o, s_for = 2 * i + 1 - o;
+        u32 x[32];
+        load_digits(x, dig, lut, s_own, lane, bias);
+        warp_ntt_fwd_digits(x, tile, twAf, twBf, p, lane);
+#pragma unroll
+        for (int c = 0; c < 32; c++) tile[c * 32 + lane] = x[c];
+        pair_barrier(pb);
+        const uint4* k_own = kp + (size_t)(s_own * 2 + o) * (N / 4);
+        const uint4* k_for = kp + (size_t)(s_for * 2 + o) * (N / 4);
+#pragma unroll
+        for (int q4 = 0; q4 < 8; q4++) {
+            const uint4 ka = MK_KEY_LD(k_own + q4 * 32), kb = MK_KEY_LD(k_for + q4 * 32);
+            x[4 * q4 + 0] = rns::mont_mul2(x[4 * q4 + 0], ka.x, ptile[(4 * q4 + 0) * 32 + lane], kb.x, p, pinv);   // < 2.75p
+            x[4 * q4 + 1] = rns::mont_mul2(x[4 * q4 + 1], ka.y, ptile[(4 * q4 + 1) * 32 + lane], kb.y, p, pinv);
+            x[4 * q4 + 2] = rns::mont_mul2(x[4 * q4 + 2], ka.z, ptile[(4 * q4 + 2) * 32 + lane], kb.z, p, pinv);
+            x[4 * q4 + 3] = rns::mont_mul2(x[4 * q4 + 3], ka.w, ptile[(4 * q4 + 3) * 32 + lane], kb.w, p, pinv);
+        }
+        pair_barrier(pb);                                      // the partner is done with this warp's tile
+        // ---- phase 3: the i = 1 warp hands its partial sum to the i = 0 warp of the same (prime, output), which adds it,
+        // inverse-transforms and leaves the residues in its tile; then the CRT of both outputs by the whole gate
+        if (i == 1) {
+#pragma unroll
+            for (int c = 0; c < 32; c++) tile[c * 32 + lane] = x[c];
+            pair_barrier(cb);
+        } else {
+            pair_barrier(cb);
+            const u32* otile = tiles + (gw ^ 1) * rns::TILE_WORDS;
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                const u32 v = x[c] + otile[c * 32 + lane];      // < 5.5p
+                x[c] = rns::umin32(v, v - p4);                  // [0, 4p)
+            }
+            warp_ntt_inv(x, tile, twAi, twBi, p, lane);
+#pragma unroll
+            for (int r = 0; r < 32; r++) tile[32 * r + lane] = x[r];   // residues in coefficient order
+        }
+        gate_barrier<W>(bar_id);
+        crt_phase<MUX, W, 6>(acc, tiles, 2 * rns::TILE_WORDS, 5 * rns::TILE_WORDS, 8 * rns::TILE_WORDS, gtid);   // warp (w, o, i = 0) = 4 w + 2 o + (w & 1)
+        gate_barrier<W>(bar_id);
+    } else if constexpr (W == 6) {
         // ---- phase 2 (6 warps): this warp transforms the digit polynomials of its parity, reads the partner's from the
         // partner's tile, and accumulates output polynomial `o` for both, two products per Montgomery reduction
         const int o = gw & 1;
@@ -338,30 +420,9 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
         warp_ntt_inv(x, tile, twAi, twBi, p, lane);
 #pragma unroll
         for (int r = 0; r < 32; r++) tile[32 * r + lane] = x[r];   // residues in coefficient order
-        gate_barrier(bar_id);
-        // Garner's lift is one long dependent chain per coefficient: CRT_ILP coefficients are interleaved per thread
-        constexpr int CRT_ILP = MK_CRT_ILP, CRT_ROUNDS = (2 * N + TPG * CRT_ILP - 1) / (TPG * CRT_ILP);
-#pragma unroll 1
-        for (int round = 0; round < CRT_ROUNDS; round++) {
-            u32 r0[CRT_ILP], r1[CRT_ILP], r2[CRT_ILP];
-            u64 old[CRT_ILP];
-#pragma unroll
-            for (int j = 0; j < CRT_ILP; j++) {
-                const int idx = gtid + (round * CRT_ILP + j) * TPG;
-                const int cl = idx < 2 * N ? idx : 0;           // clamp: out-of-range slots compute on coefficient 0 and are dropped
-                const int oo = cl >> 10, i = cl & (N - 1);
-                const u32* rt = tiles + oo * rns::TILE_WORDS;  // tile of warp (prime w', output oo) = tiles[(2 w' + oo)]
-                r0[j] = rt[i]; r1[j] = rt[2 * rns::TILE_WORDS + i]; r2[j] = rt[4 * rns::TILE_WORDS + i];
-                old[j] = MUX ? acc[cl] : 0;
-            }
-#pragma unroll
-            for (int j = 0; j < CRT_ILP; j++) {
-                const int idx = gtid + (round * CRT_ILP + j) * TPG;
-                const u64 R = rns::crt_lift(r0[j], r1[j], r2[j], c_rns.crt);
-                if (idx < 2 * N) acc[idx] = old[j] + R;
-            }
-        }
-        gate_barrier(bar_id);
+        gate_barrier<W>(bar_id);
+        crt_phase<MUX, W, MK_CRT_ILP>(acc, tiles, rns::TILE_WORDS, 2 * rns::TILE_WORDS, 4 * rns::TILE_WORDS, gtid);   // warp (w, o) = 2 w + o
+        gate_barrier<W>(bar_id);
     } else {
         // ---- phase 2 (3 warps): per prime, forward NTT of each digit polynomial and multiply-accumulate with the key
         u32 acc0[32], acc1[32];
@@ -404,13 +465,13 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
             warp_ntt_inv(x, tile, twAi, twBi, p, lane);
 #pragma unroll
             for (int r = 0; r < 32; r++) tile[32 * r + lane] = x[r];   // residues in coefficient order
-            gate_barrier(bar_id);
+            gate_barrier<W>(bar_id);
             u64* ap = acc + out * N;
-            for (int i = gtid; i < N; i += TPG) {
+            for (int i = gtid; i < N; i += 32 * W) {
                 const u64 R = rns::crt_lift(tiles[i], tiles[rns::TILE_WORDS + i], tiles[2 * rns::TILE_WORDS + i], c_rns.crt);
                 ap[i] = MUX ? ap[i] + R : R;
             }
-            gate_barrier(bar_id);
+            gate_barrier<W>(bar_id);
         }
     }
 }
@@ -422,12 +483,12 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
 // Thread `gtid` owns the four output columns 4*gtid .. 4*gtid+3 (one LDG.128 per row); zero digits read the all-zero row
 // instead of branching, so the 4 * T row reads of four consecutive coefficients are all in flight together.
 __host__ __device__ constexpr bool ks_fusable(int n, int t) { return ks_row_stride(n) <= 4 * TPG && (t == 3 || t == 5); }
-template <int T>
+template <int T, int W = WPG>
 __device__ __forceinline__ void fused_keyswitch(const u64* __restrict__ acc, u32* __restrict__ s_a, const BlindRotateArgs& p, int g, int gtid,
                                                 int bar_id) {
     const int n = p.n, stride = ks_row_stride(n), bb = p.ks_basebit, B1 = (1 << bb) - 1;
     const uint32_t prec_offset = 1u << (32 - (1 + bb * T));   // keyswitch.jl:58
-    for (int i = gtid; i < N; i += TPG) {
+    for (int i = gtid; i < N; i += 32 * W) {
         const u64 v = i == 0 ? acc[0] : (u64)0 - acc[N - i];
         const int32_t ai = t64tot32((int64_t)v);
         if (p.ext_out) p.ext_out[(size_t)g * (N + 1) + i] = ai;
@@ -435,7 +496,7 @@ __device__ __forceinline__ void fused_keyswitch(const u64* __restrict__ acc, u32
     }
     const int32_t eb = t64tot32((int64_t)acc[N]);
     if (p.ext_out && gtid == 0) p.ext_out[(size_t)g * (N + 1) + N] = eb;
-    gate_barrier(bar_id);
+    gate_barrier<W>(bar_id);
     const int col0 = 4 * gtid;
     if (col0 >= stride) return;                               // no barrier below: idle threads may leave
     const size_t party_words = (size_t)N * T * B1 * stride;
@@ -471,17 +532,19 @@ __device__ __forceinline__ void fused_keyswitch(const u64* __restrict__ acc, u32
 }
 
 // GPC gates per CTA, WPG warps per gate.  Accumulators resident in shared memory for all k*n steps.
-template <int L, int GPC>
+template <int L, int GPC, int W = WPG>
 __global__ void __maxnreg__(MK_MAXNREG) blind_rotate_kernel(BlindRotateArgs p) {
+    constexpr int TPG = 32 * W;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2_* twB = reinterpret_cast<uint2_*>(smem_raw);
     stage_twiddles(twB, p.twB);
     stage_digit_lut(reinterpret_cast<u32*>(twB) + TWB_WORDS + TWA_WORDS, p.bgbit);
     __syncthreads();
+    static_assert(W != LAT_WPG || GPC == 1, "the latency launch holds one gate per CTA (barrier ids 1..13)");
     const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot, pbar_id = 1 + GPC + slot * rns::NP;
     const int g = blockIdx.x * GPC + slot;
     if (g >= p.G) return;   // no CTA-wide barrier below this line
-    unsigned char* base = smem_raw + TW_SMEM_BYTES + (size_t)slot * gate_smem_bytes(L);
+    unsigned char* base = smem_raw + TW_SMEM_BYTES + (size_t)slot * gate_smem_bytes(L, W);
     u64* acc = reinterpret_cast<u64*>(base);
     u32* dig = reinterpret_cast<u32*>(base + 2 * N * 8);
     u32* tiles = dig + 2 * L * (N / 4);
@@ -505,7 +568,7 @@ __global__ void __maxnreg__(MK_MAXNREG) blind_rotate_kernel(BlindRotateArgs p) {
             acc[N + i] = (idx & N) ? (u64)0 - (u64)p.mu : (u64)p.mu;
         }
     }
-    gate_barrier(bar_id);
+    gate_barrier<W>(bar_id);
 #if MK_STAGGER_NS
     // The gates of a CTA execute identical instruction streams and would run in phase (both in the IMAD-free decompose / CRT
     // phases at the same time).  Start every other gate a fraction of a step later so that those phases interleave.
@@ -533,15 +596,15 @@ __global__ void __maxnreg__(MK_MAXNREG) blind_rotate_kernel(BlindRotateArgs p) {
         if (cta_full && (it % MK_LOCKSTEP) == 0) asm volatile("bar.sync 15, %0;" ::"r"(GPC * TPG) : "memory");
 #endif
         if (a == 0) continue;   // :69 (uniform across the gate)
-        extprod_step<L, true>(acc, dig, tiles, twB, p.bsk + (size_t)it * estride, a, p.bgbit, bar_id, pbar_id, gtid);
+        extprod_step<L, true, W>(acc, dig, tiles, twB, p.bsk + (size_t)it * estride, a, p.bgbit, bar_id, pbar_id, gtid);
     }
     if (p.acc_out) {
         int64_t* ao = p.acc_out + (size_t)g * 2 * N;
         for (int i = gtid; i < 2 * N; i += TPG) ao[i] = (int64_t)acc[i];
     }
     if (p.ksk) {   // fused extraction + key switch (the host only sets ksk when ks_fusable(n, t))
-        if (p.ks_t == 3) fused_keyswitch<3>(acc, tiles, p, g, gtid, bar_id);
-        else fused_keyswitch<5>(acc, tiles, p, g, gtid, bar_id);
+        if (p.ks_t == 3) fused_keyswitch<3, W>(acc, tiles, p, g, gtid, bar_id);
+        else fused_keyswitch<5, W>(acc, tiles, p, g, gtid, bar_id);
         return;
     }
     // rlwe_extract_sample_64 (rlwe.jl:70-74): a'_0 = mask_0, a'_i = -mask_{N-i}, b' = body_0

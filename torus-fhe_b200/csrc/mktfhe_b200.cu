@@ -42,6 +42,7 @@ struct mktfhe_ctx {
     rns::uint2_* d_twB = nullptr;
     int gpc = 1;                 // gates per CTA of the blind-rotate / external-product kernels
     int num_sms = 0;
+    bool latency_kernel = true;  // MKTFHE_B200_LATENCY=0 turns the 12-warp small-batch launch off (A/B)
     bool fuse_ks = true;         // key switch as the epilogue of the blind-rotate kernel (MKTFHE_B200_FUSE_KS=0 disables: A/B runs)
     std::vector<char> bsk_loaded, ksk_loaded;
     bool ready = false;
@@ -124,6 +125,9 @@ int set_attrs(mktfhe_ctx* c) {
 #define SET_ATTR1(L, GPC, dummy) CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_kernel<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm1));
     MK_DISPATCH_L(c, SET_ATTR1, 0)
 #undef SET_ATTR1
+    if (c->prm.l == 2)
+        CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_kernel<2, 1, mk::LAT_WPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(mk::TW_SMEM_BYTES + mk::gate_smem_bytes(2, mk::LAT_WPG))));
     return MKTFHE_OK;
 }
 
@@ -131,6 +135,12 @@ void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G) 
     if (c->gpc > 1 && G <= (size_t)c->num_sms) {
         // a batch that fits on the SMs one gate each: a gate alone on an SM finishes ~25 % sooner than two sharing one, so narrow
         // circuit levels (and single bootstraps) run one gate per CTA; bit-identical results
+        if (c->prm.l == 2 && c->latency_kernel) {
+            // l = 2: 12 warps per gate (mk::LAT_WPG), the two forward transforms of a warp side by side
+            mk::blind_rotate_kernel<2, 1, mk::LAT_WPG><<<(unsigned)G, 32 * mk::LAT_WPG, mk::TW_SMEM_BYTES + mk::gate_smem_bytes(2, mk::LAT_WPG), c->stream>>>(a);
+            c->launches++;
+            return;
+        }
         const size_t sm1 = mk::TW_SMEM_BYTES + mk::gate_smem_bytes(c->prm.l);
 #define LAUNCH_BR1(L, GPC, dummy) mk::blind_rotate_kernel<L, 1><<<(unsigned)G, mk::TPG, sm1, c->stream>>>(a)
         MK_DISPATCH_L(c, LAUNCH_BR1, 0)
@@ -230,6 +240,7 @@ int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
     c->bsk_bytes = (size_t)params->k * params->n * mk::bsk_elem_words(params->l) * sizeof(u32);
     c->gpc = mk::gpc_for(params->l);
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
+    if (const char* e = getenv("MKTFHE_B200_LATENCY")) c->latency_kernel = atoi(e) != 0;
     if (const char* e = getenv("MKTFHE_B200_FUSE_KS")) c->fuse_ks = atoi(e) != 0;
     const size_t ks_stride = mk::ks_row_stride(params->n);   // rows padded to 16 bytes on the device
     c->ksk_bytes = (size_t)params->k * mk::N * params->t * B1 * ks_stride * sizeof(int32_t);
