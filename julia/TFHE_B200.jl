@@ -139,6 +139,44 @@ function mk_gate_mux_3gen(bk::BK, ks::KS, x::MKLweSample, y::MKLweSample, z::MKL
     mk_lwe_noiseless_trivial(encode_message(1, 8), t[1].params, length(bk)) + t[1] + t[2]
 end
 
+# ---- level-batched circuits, 3gen_mk_gates.jl:183-310 (torus-fhe_b200/circuits.py is the tested twin): every dependency level of a
+# circuit is ONE mixed-gate launch (mktfhe_gate_batch_mixed) instead of one launch per gate.  `jobs` = [(gate_id, x, y), ...]
+function gate_level(bk::BK, ks::KS, jobs::Vector{Tuple{Cint, MKLweSample, MKLweSample}})
+    e = engine_for(bk, ks); n, k, G = Int(e.prm.n), Int(e.prm.k), length(jobs)
+    ids = Int32[j[1] for j in jobs]
+    xs, ys = MKLweSample[j[2] for j in jobs], MKLweSample[j[3] for j in jobs]
+    oa, ob = Matrix{Int32}(undef, n * k, G), Vector{Int32}(undef, G)
+    check(e.ctx, ccall((:mktfhe_gate_batch_mixed, LIB), Cint,
+        (Ptr{Cvoid}, Csize_t, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
+        e.ctx, G, ids, pack_a(xs), pack_b(xs), pack_a(ys), pack_b(ys), Ptr{Int32}(C_NULL), Ptr{Int32}(C_NULL), oa, ob))
+    unpack(xs[1].params, n, k, oa, ob)
+end
+
+mk_copy_3gen(x::MKLweSample) = MKLweSample(x.params, copy(x.a), x.b, x.current_variance)
+
+"""3gen_mk_gates.jl:291-310: WIDTH sum bits plus the final carry; 1 + 2 WIDTH launches instead of 5 WIDTH."""
+function mk_int_add_with_carry_3gen(bk::BK, ks::KS, a::Vector{MKLweSample}, b::Vector{MKLweSample}, Cin::MKLweSample, WIDTH)
+    lvl0 = gate_level(bk, ks, vcat([(GATE_XOR, a[i], b[i]) for i in 1:WIDTH], [(GATE_AND, a[i], b[i]) for i in 1:WIDTH]))
+    tmp1, tmp2 = lvl0[1:WIDTH], lvl0[WIDTH+1:2*WIDTH]
+    result = Vector{MKLweSample}(undef, WIDTH + 1)
+    cin = Cin
+    for i in 1:WIDTH
+        st = gate_level(bk, ks, [(GATE_XOR, tmp1[i], cin), (GATE_AND, tmp1[i], cin)])
+        result[i] = st[1]
+        cin = gate_level(bk, ks, [(GATE_OR, tmp2[i], st[2])])[1]
+    end
+    result[WIDTH + 1] = cin
+    result
+end
+mk_add_3gen(bk::BK, ks::KS, a, b, Cin::MKLweSample, WIDTH) = mk_int_add_with_carry_3gen(bk, ks, a, b, Cin, WIDTH)[1:WIDTH]      # :183-200
+mk_add_3gen_v2(bk::BK, ks::KS, a, b, Cin::MKLweSample, WIDTH) = mk_add_3gen(bk, ks, a, b, Cin, WIDTH)                            # :203-220
+mk_inv_3gen(bk::BK, ks::KS, a, one::MKLweSample, WIDTH) = gate_level(bk, ks, [(GATE_XOR, a[i], one) for i in 1:WIDTH])           # :223-233
+mk_sub_3gen(bk::BK, ks::KS, a, b, one::MKLweSample, WIDTH) = mk_add_3gen(bk, ks, a, mk_inv_3gen(bk, ks, b, one, WIDTH), one, WIDTH)   # :236-244
+mk_less_3gen(bk::BK, ks::KS, a, b, one::MKLweSample, WIDTH) = mk_copy_3gen(mk_sub_3gen(bk, ks, a, b, one, WIDTH)[WIDTH])          # :247-255
+mk_grt_3gen(bk::BK, ks::KS, a, b, one::MKLweSample, WIDTH) = mk_copy_3gen(mk_sub_3gen(bk, ks, b, a, one, WIDTH)[WIDTH])           # :258-266
+mk_leq_3gen(bk::BK, ks::KS, a, b, one::MKLweSample, WIDTH) = mk_gate_xor_3gen(bk, ks, mk_grt_3gen(bk, ks, a, b, one, WIDTH), one)   # :269-277
+mk_geq_3gen(bk::BK, ks::KS, a, b, one::MKLweSample, WIDTH) = mk_gate_xor_3gen(bk, ks, mk_less_3gen(bk, ks, a, b, one, WIDTH), one)  # :280-288
+
 # ---- interchange files (torus-fhe_b200/interchange.py documents the layout): dump the reference's own keys / ciphertexts so that
 # the B200 engine and its CPU oracle can be checked on the very bytes the Julia code produced
 function write_keys(path::String, params, bk::Array{TransformedBootstrapKeyPart_3gen, 1}, ks::Array{KeyswitchKey, 1}, secret_keys = nothing)
@@ -167,6 +205,7 @@ function write_ciphertexts(path::String, xs::Vector{MKLweSample})
 end
 
 export TransformedBootstrapKeyPart_3gen, mk_bootstrap_3gen, mk_gate_nand_3gen, mk_gate_or_3gen, mk_gate_and_3gen,
-       mk_gate_xor_3gen, mk_gate_3and_3gen, mk_gate_not_3gen, mk_gate_mux_3gen, write_keys, write_ciphertexts
+       mk_gate_xor_3gen, mk_gate_3and_3gen, mk_gate_not_3gen, mk_gate_mux_3gen, gate_level, mk_copy_3gen, mk_int_add_with_carry_3gen,
+       mk_add_3gen, mk_add_3gen_v2, mk_inv_3gen, mk_sub_3gen, mk_less_3gen, mk_grt_3gen, mk_leq_3gen, mk_geq_3gen, write_keys, write_ciphertexts
 
 end # module

@@ -17,6 +17,24 @@ def test_parameter_sets_match_reference():
     p = T.mktfhe_parameters_8party_3gen
     assert (p.lwe_size, p.gsw_decomp_length, p.gsw_log2_base, p.ks_decomp_length, p.ks_log2_base, p.max_parties) == (540, 4, 4, 5, 2, 8)
     assert T.tgsw_parameters(T.mktfhe_parameters_2party_3gen).gadget_values == [1 << 57, 1 << 50]   # tgsw.jl:26
+    # the N >= 2048 sets exist by name (mk_api.jl:214-322); the engine rejects them at mktfhe_create
+    for k, n, N, l, bg in ((16, 590, 2048, 1, 26), (32, 620, 2048, 1, 26), (64, 650, 2048, 1, 25), (128, 670, 2048, 1, 24), (256, 740, 2048, 2, 18),
+                           (512, 730, 4096, 1, 27)):
+        p = getattr(T, f"mktfhe_parameters_{k}party_3gen")
+        assert (p.max_parties, p.lwe_size, p.rlwe_polynomial_degree, p.gsw_decomp_length, p.gsw_log2_base) == (k, n, N, l, bg) and not p.rlwe_is32
+
+
+def test_decode64_and_noise_calc():
+    # numeric-functions.jl:75-78, 117-131
+    assert int(T.decode_message64(T.encode_message64(3, 8), 8)) == 3 and int(T.decode_message64(np.int64(-5), 2048)) == 0
+    assert int(T.decode_message64(np.int64(2 ** 63 - 1), 4)) == -2                        # wrapping add, arithmetic shift
+    e = lambda f: np.int32(int(f * 2 ** 32))
+    assert abs(T.noise_calc(e(0.125), e(0.13)) - 0.005) < 1e-9
+    assert abs(T.noise_calc(e(0.125), e(-0.49)) - (1.0 - 0.49 - 0.125)) < 1e-9           # d < m - 0.5: wraps upwards
+    assert abs(T.noise_calc(e(-0.125), e(-0.12)) - 0.005) < 1e-9
+    assert abs(T.noise_calc(e(-0.125), e(0.45)) - (1.0 - 0.45 - 0.125)) < 1e-9           # d > m + 0.5
+    assert T.noise_calc(np.int32(0), e(0.25)) == 0.25
+    assert T.noise_calc(np.array([e(0.125)] * 2), np.array([e(0.13), e(0.12)])).shape == (2,)
 
 
 def test_encode_decode_agree_with_oracle(oracle):

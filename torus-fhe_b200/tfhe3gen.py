@@ -53,6 +53,24 @@ def decode_message(phase, space):
     return s >> (32 - lg)
 
 
+def decode_message64(phase, space):
+    """numeric-functions.jl:75-78: the same on Torus64."""
+    lg = _log2(space)
+    p = np.asarray(phase, dtype=np.int64)
+    return (p.view(np.uint64) + np.uint64(1 << (64 - lg - 1))).view(np.int64) >> (64 - lg)
+
+
+def noise_calc(m_torus, d_torus):
+    """numeric-functions.jl:117-131: distance on the torus (as a fraction of it) between a decrypted phase `d_torus` and the message
+    `m_torus` it should carry, with the reference's wrap rules (note its asymmetric sign for negative messages, kept)."""
+    m = np.asarray(m_torus, dtype=np.int32).astype(np.float64) / 2.0 ** 32
+    d = np.asarray(d_torus, dtype=np.int32).astype(np.float64) / 2.0 ** 32
+    pos = np.where((d < 0) & (d < m - 0.5), 1.0 + d - m, d - m)
+    neg = np.where(d > m + 0.5, 1.0 - d + m, d - m)
+    out = np.where(m > 0, pos, np.where(m < 0, neg, d))
+    return float(out) if out.ndim == 0 else out
+
+
 def dtot32(d):
     """numeric-functions.jl:101-103: trunc(Int32, d * 2^32)."""
     return np.trunc(np.asarray(d, dtype=np.float64) * 4294967296.0).astype(np.int64).astype(np.int32)
@@ -160,6 +178,11 @@ mktfhe_parameters_8party_3gen = SchemeParameters_3gen(540, 2 ** -14.04, 1024, 1,
 # 16 parties and up use N = 2048 and a 26-bit gadget base (mk_api.jl:214-322): defined for
 # API completeness, rejected by mktfhe_create (MKTFHE_EINVAL) until the N = 2048 kernels exist.
 mktfhe_parameters_16party_3gen = SchemeParameters_3gen(590, 2 ** -15.34, 2048, 1, False, 1, 26, 2 ** -62.00, 4, 3, 2 ** -15.34, 16)
+mktfhe_parameters_32party_3gen = SchemeParameters_3gen(620, 2 ** -16.12, 2048, 1, False, 1, 26, 2 ** -62.00, 4, 3, 2 ** -16.12, 32)      # :246-252
+mktfhe_parameters_64party_3gen = SchemeParameters_3gen(650, 2 ** -16.90, 2048, 1, False, 1, 25, 2 ** -62.00, 4, 3, 2 ** -16.90, 64)      # :268-274
+mktfhe_parameters_128party_3gen = SchemeParameters_3gen(670, 2 ** -17.42, 2048, 1, False, 1, 24, 2 ** -62.00, 5, 3, 2 ** -17.42, 128)   # :292-298
+mktfhe_parameters_256party_3gen = SchemeParameters_3gen(740, 2 ** -19.24, 2048, 1, False, 2, 18, 2 ** -62.00, 8, 2, 2 ** -19.24, 256)   # :304-310
+mktfhe_parameters_512party_3gen = SchemeParameters_3gen(730, 2 ** -18.98, 4096, 1, False, 1, 27, 2 ** -62.00, 5, 3, 2 ** -18.98, 512)   # :316-322
 
 
 # ---------------------------------------------------------------------------------
