@@ -141,6 +141,7 @@ __host__ __device__ inline GateLinear gate_linear(int gate) {
 template <int W = WPG>
 __device__ __forceinline__ void gate_barrier(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(32 * W) : "memory"); }
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void quad_barrier(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // decode_message(x, 2N), numeric-functions.jl:70-73 (wrapping add, arithmetic shift)
 __device__ __forceinline__ int mod_switch_2N(int32_t x) {
@@ -320,14 +321,14 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
         // (w & 1) twist spreads the six i = 0 warps, which alone run the inverse transforms, over all four schedulers.
         const int o = (gw >> 1) & 1, i = (gw ^ w) & 1;
         const u32* ptile = tiles + (gw ^ 2) * rns::TILE_WORDS;
-        const int pb = pbar_id + 2 * w + i, cb = pbar_id + 6 + 2 * w + o;
+        const int qb = pbar_id + w;      // one named barrier per prime: its four warps exchange tiles among themselves only
         const int s_own = 2 * i + o, s_for = 2 * i + 1 - o;
         u32 x[32];
         load_digits(x, dig, lut, s_own, lane, bias);
         warp_ntt_fwd_digits(x, tile, twAf, twBf, p, lane);
 #pragma unroll
         for (int c = 0; c < 32; c++) tile[c * 32 + lane] = x[c];
-        pair_barrier(pb);
+        quad_barrier(qb);
         const uint4* k_own = kp + (size_t)(s_own * 2 + o) * (N / 4);
         const uint4* k_for = kp + (size_t)(s_for * 2 + o) * (N / 4);
 #pragma unroll
@@ -338,15 +339,15 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
             x[4 * q4 + 2] = rns::mont_mul2(x[4 * q4 + 2], ka.z, ptile[(4 * q4 + 2) * 32 + lane], kb.z, p, pinv);
             x[4 * q4 + 3] = rns::mont_mul2(x[4 * q4 + 3], ka.w, ptile[(4 * q4 + 3) * 32 + lane], kb.w, p, pinv);
         }
-        pair_barrier(pb);                                      // the partner is done with this warp's tile
+        quad_barrier(qb);                                      // the partner is done with this warp's tile
         // ---- phase 3: the i = 1 warp hands its partial sum to the i = 0 warp of the same (prime, output), which adds it,
         // inverse-transforms and leaves the residues in its tile; then the CRT of both outputs by the whole gate
         if (i == 1) {
 #pragma unroll
             for (int c = 0; c < 32; c++) tile[c * 32 + lane] = x[c];
-            pair_barrier(cb);
+            quad_barrier(qb);
         } else {
-            pair_barrier(cb);
+            quad_barrier(qb);
             const u32* otile = tiles + (gw ^ 1) * rns::TILE_WORDS;
 #pragma unroll
             for (int c = 0; c < 32; c++) {
@@ -532,15 +533,15 @@ __device__ __forceinline__ void fused_keyswitch(const u64* __restrict__ acc, u32
 }
 
 // GPC gates per CTA, WPG warps per gate.  Accumulators resident in shared memory for all k*n steps.
-template <int L, int GPC, int W = WPG>
-__global__ void __maxnreg__(MK_MAXNREG) blind_rotate_kernel(BlindRotateArgs p) {
+template <int L, int GPC, int W>
+__device__ __forceinline__ void blind_rotate_body(const BlindRotateArgs& p) {
     constexpr int TPG = 32 * W;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2_* twB = reinterpret_cast<uint2_*>(smem_raw);
     stage_twiddles(twB, p.twB);
     stage_digit_lut(reinterpret_cast<u32*>(twB) + TWB_WORDS + TWA_WORDS, p.bgbit);
     __syncthreads();
-    static_assert(W != LAT_WPG || GPC == 1, "the latency launch holds one gate per CTA (barrier ids 1..13)");
+    static_assert(W == 3 || (1 + rns::NP) * GPC < 16, "named barriers: one per gate plus one per (gate, prime)");
     const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot, pbar_id = 1 + GPC + slot * rns::NP;
     const int g = blockIdx.x * GPC + slot;
     if (g >= p.G) return;   // no CTA-wide barrier below this line
@@ -615,6 +616,10 @@ __global__ void __maxnreg__(MK_MAXNREG) blind_rotate_kernel(BlindRotateArgs p) {
     }
     if (gtid == 0) ext[N] = t64tot32((int64_t)acc[N]);
 }
+
+// GPC gates per CTA, W warps per gate, 12 warps per SM at 168 registers (throughput: <L, 2, 6>; small batches: <L, 1, 6>, <2, 1, 12>)
+template <int L, int GPC, int W = WPG>
+__global__ void __maxnreg__(MK_MAXNREG) blind_rotate_kernel(BlindRotateArgs p) { blind_rotate_body<L, GPC, W>(p); }
 
 // parity hook: acc_out[g] = ExtProd(acc_in[g], bsk[elem[g]])
 template <int L, int GPC>
