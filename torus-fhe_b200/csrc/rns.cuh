@@ -172,13 +172,36 @@ MK_HD u32 residue_i64(int64_t v, u32 p) {
     return (u32)(r < 0 ? r + (int64_t)p : r);
 }
 
-// Garner CRT constants
+// CRT constants.  Two interchangeable lifts: Garner's mixed radix (MK_CRT_FLOAT = 0, the default) and the floating-point-corrected
+// sum (MK_CRT_FLOAT = 1, see crt_lift): exact and 5 IMAD slots shorter per coefficient, but its four int<->float conversions run on
+// the 16-lane XU pipe and the kernel measured 6.5 % slower (profiles/ab_r1.txt).
+#ifndef MK_CRT_FLOAT
+#define MK_CRT_FLOAT 0
+#endif
 struct Crt {
     u32 p[3];
     u32 c01, c01s, c02, c02s, c12, c12s;   // p0^-1 mod p1, p0^-1 mod p2, p1^-1 mod p2 with Shoup companions
     u64 p01;                               // p0 * p1
     u64 m_mod64;                           // p0 * p1 * p2 mod 2^64
+    u64 C[3];                              // M / p_i (< 2^56, exact)
+    float inv_p[3];                        // 1 / p_i
+    u32 yscale[3];                         // (M / p_i)^-1 mod p_i, folded into the stored key when MK_CRT_FLOAT
 };
+#if MK_CRT_FLOAT
+// Residues y_i = R * (M / p_i)^-1 mod p_i, lazily reduced (any representative below 2^32 / 3), of an integer R with |R| < M/4
+// -> R mod 2^64 (two's complement).  R = sum_i y_i (M / p_i) - kappa M with kappa = round(sum_i y_i / p_i): since |R| / M < 1/4 the
+// sum is within 1/4 of the integer kappa, so a float32 estimate (error < 2^-18 here) always rounds to it.  Three independent
+// 32 x 64-bit products instead of Garner's three dependent modular ones; the factor (M / p_i)^-1 rides in the key scaling.
+MK_HD u64 crt_lift(u32 y0, u32 y1, u32 y2, const Crt& c) {
+    const float x = (float)y0 * c.inv_p[0] + (float)y1 * c.inv_p[1] + (float)y2 * c.inv_p[2];
+#if defined(__CUDA_ARCH__)
+    const u32 kappa = __float2uint_rn(x);
+#else
+    const u32 kappa = (u32)(x + 0.5f);
+#endif
+    return (u64)y0 * c.C[0] + (u64)y1 * c.C[1] + (u64)y2 * c.C[2] - (u64)kappa * c.m_mod64;
+}
+#else
 // residues r_i in [0, 4 p_i) of an integer R with |R| < M/4 -> R mod 2^64 (two's complement)
 MK_HD u64 crt_lift(u32 r0, u32 r1, u32 r2, const Crt& c) {
     const u32 p0 = c.p[0], p1 = c.p[1], p2 = c.p[2];
@@ -193,5 +216,6 @@ MK_HD u64 crt_lift(u32 r0, u32 r1, u32 r2, const Crt& c) {
     if (v2 > p2 / 2) R -= c.m_mod64;                                   // negative representative
     return R;
 }
+#endif
 
 }  // namespace rns

@@ -63,6 +63,15 @@ struct HostTables {
         t.c12 = invmod(primes[1] % primes[2], primes[2]); t.c12s = shoup_of(t.c12, primes[2]);
         t.p01 = (u64)primes[0] * primes[1];
         t.m_mod64 = t.p01 * (u64)primes[2];          // wraps mod 2^64
+        for (int i = 0; i < NP; i++) {
+            const u32 pa = primes[(i + 1) % NP], pb = primes[(i + 2) % NP], pi = primes[i];
+            t.C[i] = (u64)pa * pb;
+            t.inv_p[i] = 1.0f / (float)pi;
+            t.yscale[i] = invmod((u32)(t.C[i] % pi), pi);
+#if MK_CRT_FLOAT
+            c.key_scale[i] = mulmod(c.key_scale[i], t.yscale[i], pi);     // the lift's (M / p_i)^-1 rides in the stored key
+#endif
+        }
     }
 };
 
