@@ -223,6 +223,10 @@ def test_more_parties(oracle, pname):
         ra, rb = ks.gate_batch(oracle.EXACT_NTT, oracle.GATE_NAND, x, y)
         assert np.array_equal(oa, ra) and np.array_equal(ob, rb)
         assert np.array_equal(ks.decrypt(oa, ob), ~(bits[:, 0].astype(bool) & bits[:, 1].astype(bool)))
+        # the same gates 40 times over: more than one gate per SM, i.e. the throughput launch (two gates per CTA) of this l
+        tile = lambda c: (np.tile(c[0], (40, 1, 1)), np.tile(c[1], 40))
+        ba, bb = eng.ctx.gate_batch(T._cabi.GATE_NAND, tile(x), tile(y))
+        assert np.array_equal(ba, np.tile(oa, (40, 1, 1))) and np.array_equal(bb, np.tile(ob, 40))
     finally:
         eng.close()
 
@@ -290,6 +294,8 @@ def test_synthetic_parameter_sets_bit_exact(oracle, prm):
         oa, ob = eng.ctx.bootstrap_batch(MU, a, b)
         ra, rb = ks.bootstrap_batch(oracle.EXACT_NTT, MU, a, b)
         assert np.array_equal(oa, ra) and np.array_equal(ob, rb)
+        ba, bb = eng.ctx.bootstrap_batch(MU, np.tile(a, (30, 1, 1)), np.tile(b, 30))      # 150 samples: the throughput launch shape
+        assert np.array_equal(ba, np.tile(oa, (30, 1, 1))) and np.array_equal(bb, np.tile(ob, 30))
         acc = r.integers(-2 ** 63, 2 ** 63 - 1, size=(2, 2, 1024), dtype=np.int64)
         elem = np.array([0, ks.k * ks.n - 1], np.int32)
         got = eng.ctx.extprod_batch(elem, acc)
