@@ -164,6 +164,11 @@ def test_full_batch_properties(keys2, engine2):
     perm = r.permutation(G)[:512]
     pa, pb = engine2.ctx.gate_batch(T._cabi.GATE_NAND, (x[0][perm], x[1][perm]), (y[0][perm], y[1][perm]))
     assert np.array_equal(pa, oa[perm]) and np.array_equal(pb, ob[perm])
+    # a batch that leaves a small tail after its full waves is split into a throughput launch and a one-gate-per-CTA launch
+    l0 = engine2.ctx.launch_count()
+    t = perm[:296 + 40]
+    ta, tb = engine2.ctx.gate_batch(T._cabi.GATE_NAND, (x[0][t], x[1][t]), (y[0][t], y[1][t]))
+    assert np.array_equal(ta, oa[t]) and np.array_equal(tb, ob[t]) and engine2.ctx.launch_count() - l0 == 2
     # batches that fit on the SMs one gate each take the one-gate-per-CTA launch: same bits
     q = perm[:100]
     qa, qb = engine2.ctx.gate_batch(T._cabi.GATE_NAND, (x[0][q], x[1][q]), (y[0][q], y[1][q]))

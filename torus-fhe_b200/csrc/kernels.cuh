@@ -112,6 +112,7 @@ struct GateLinear {   // temp = mu0 + cx*x + cy*y + cz*z   (3gen_mk_gates.jl:8-7
 
 struct BlindRotateArgs {
     int G, n, k, bgbit;
+    int g0;             // first gate of this launch (a batch may be split into a throughput launch and a tail launch); gates g0 .. G-1
     const u32* bsk;
     const uint2_* twB;
     const int32_t *xa, *xb, *ya, *yb, *za, *zb;
@@ -543,7 +544,7 @@ __device__ __forceinline__ void blind_rotate_body(const BlindRotateArgs& p) {
     __syncthreads();
     static_assert(W == 3 || (1 + rns::NP) * GPC < 16, "named barriers: one per gate plus one per (gate, prime)");
     const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot, pbar_id = 1 + GPC + slot * rns::NP;
-    const int g = blockIdx.x * GPC + slot;
+    const int g = p.g0 + blockIdx.x * GPC + slot;
     if (g >= p.G) return;   // no CTA-wide barrier below this line
     unsigned char* base = smem_raw + TW_SMEM_BYTES + (size_t)slot * gate_smem_bytes(L, W);
     u64* acc = reinterpret_cast<u64*>(base);

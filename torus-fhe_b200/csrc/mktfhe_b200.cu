@@ -42,6 +42,7 @@ struct mktfhe_ctx {
     rns::uint2_* d_twB = nullptr;
     int gpc = 1;                 // gates per CTA of the blind-rotate / external-product kernels
     int num_sms = 0;
+    bool split_tail = true;      // MKTFHE_B200_SPLIT_TAIL=0: no separate one-gate-per-CTA launch for the tail of a large batch (A/B)
     bool latency_kernel = true;  // MKTFHE_B200_LATENCY=0 turns the 12-warp small-batch launch off (A/B)
     bool fuse_ks = true;         // key switch as the epilogue of the blind-rotate kernel (MKTFHE_B200_FUSE_KS=0 disables: A/B runs)
     std::vector<char> bsk_loaded, ksk_loaded;
@@ -131,29 +132,40 @@ int set_attrs(mktfhe_ctx* c) {
     return MKTFHE_OK;
 }
 
-void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G) {
-    if (c->gpc > 1 && G <= (size_t)c->num_sms) {
-        // a batch that fits on the SMs one gate each: a gate alone on an SM finishes ~25 % sooner than two sharing one, so narrow
-        // circuit levels (and single bootstraps) run one gate per CTA; bit-identical results
-        if (c->prm.l == 2 && c->latency_kernel) {
-            // l = 2: 12 warps per gate (mk::LAT_WPG), the two forward transforms of a warp side by side
-            mk::blind_rotate_kernel<2, 1, mk::LAT_WPG><<<(unsigned)G, 32 * mk::LAT_WPG, mk::TW_SMEM_BYTES + mk::gate_smem_bytes(2, mk::LAT_WPG), c->stream>>>(a);
-            c->launches++;
-            return;
-        }
+// one gate per CTA for gates [g0, g1): the 12-warp latency kernel when l = 2, else the six-warp kernel alone on its SM
+void launch_one_gate_per_cta(mktfhe_ctx* c, mk::BlindRotateArgs a, size_t g0, size_t g1) {
+    a.g0 = (int)g0; a.G = (int)g1;
+    const unsigned grid = (unsigned)(g1 - g0);
+    if (c->prm.l == 2 && c->latency_kernel) {
+        mk::blind_rotate_kernel<2, 1, mk::LAT_WPG><<<grid, 32 * mk::LAT_WPG, mk::TW_SMEM_BYTES + mk::gate_smem_bytes(2, mk::LAT_WPG), c->stream>>>(a);
+    } else {
         const size_t sm1 = mk::TW_SMEM_BYTES + mk::gate_smem_bytes(c->prm.l);
-#define LAUNCH_BR1(L, GPC, dummy) mk::blind_rotate_kernel<L, 1><<<(unsigned)G, mk::TPG, sm1, c->stream>>>(a)
+#define LAUNCH_BR1(L, GPC, dummy) mk::blind_rotate_kernel<L, 1><<<grid, mk::TPG, sm1, c->stream>>>(a)
         MK_DISPATCH_L(c, LAUNCH_BR1, 0)
 #undef LAUNCH_BR1
-        c->launches++;
-        return;
     }
-    const size_t sm = br_smem_bytes(c);
-    const unsigned grid = (unsigned)((G + c->gpc - 1) / c->gpc);
-#define LAUNCH_BR(L, GPC, dummy) mk::blind_rotate_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, c->stream>>>(a)
-    MK_DISPATCH_L(c, LAUNCH_BR, 0)
-#undef LAUNCH_BR
     c->launches++;
+}
+
+// Launch shapes.  Throughput: gpc gates per CTA, one CTA per SM, i.e. waves of gpc * num_sms gates.  A batch -- or the tail a batch
+// leaves after its full waves -- of at most one gate per SM runs one gate per CTA instead: a gate alone on an SM finishes in 7.3 ms
+// (12-warp latency kernel, l = 2) or 9.5 ms (six warps) against 12.3 ms for two gates sharing it.  Bit-identical results.
+void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G) {
+    const size_t wave = (size_t)c->gpc * (size_t)c->num_sms;
+    size_t tail = c->gpc > 1 ? G % wave : 0;
+    if (tail > (size_t)c->num_sms || (!c->split_tail && tail != G)) tail = 0;
+    const size_t head = G - tail;
+    if (head) {
+        mk::BlindRotateArgs h = a;
+        h.g0 = 0; h.G = (int)head;
+        const size_t sm = br_smem_bytes(c);
+        const unsigned grid = (unsigned)((head + c->gpc - 1) / c->gpc);
+#define LAUNCH_BR(L, GPC, dummy) mk::blind_rotate_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, c->stream>>>(h)
+        MK_DISPATCH_L(c, LAUNCH_BR, 0)
+#undef LAUNCH_BR
+        c->launches++;
+    }
+    if (tail) launch_one_gate_per_cta(c, a, head, G);
 }
 
 mk::GateLinear gate_linear(int gate, bool* ok) {
@@ -241,6 +253,7 @@ int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
     c->gpc = mk::gpc_for(params->l);
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
     if (const char* e = getenv("MKTFHE_B200_LATENCY")) c->latency_kernel = atoi(e) != 0;
+    if (const char* e = getenv("MKTFHE_B200_SPLIT_TAIL")) c->split_tail = atoi(e) != 0;
     if (const char* e = getenv("MKTFHE_B200_FUSE_KS")) c->fuse_ks = atoi(e) != 0;
     const size_t ks_stride = mk::ks_row_stride(params->n);   // rows padded to 16 bytes on the device
     c->ksk_bytes = (size_t)params->k * mk::N * params->t * B1 * ks_stride * sizeof(int32_t);
