@@ -298,6 +298,8 @@ def run_ours(args):
                              "frac": achieved / hbm_peak, "traffic": traffic, "traffic_note": ncu_traffic, "peak_source": peak_src,
                              "note": "contract roofline (HBM); the kernel is IMAD-pipe bound and streams the key from L2 (hit rate 97.3 %): see integer_bound",
                              "algorithmic_bytes_per_gate": bsk_1limb + ct_io, "streamed_bytes_per_gate_this_build": bsk_stream,
+                             "key_stream_from_hbm_GBps": {"value": 5793, "frac_of_peak": 5793 / hbm_peak, "source": "profiles/key_stream_ubench_r1.txt: the kernel's key access "
+                                                           "pattern over a 4 GiB buffer at the kernel's occupancy (in the product L2 serves the stream)"},
                              "kernel_ms": br_ms, "keyswitch_ms": ks_ms, "keyswitch_gather_GBps": (G * ksk_gather / (ks_ms * 1e-3) / 1e9) if ks_ms > 0.05 else None,
                              "keyswitch_fused_into_blind_rotate": ks_ms <= 0.05,
                              "kernel_share_of_step": br_ms / (ms / args.steps),
