@@ -67,10 +67,17 @@ constexpr int N = rns::N;
 // ----------------------------------------------------------------------------------------------------------------------------
 constexpr int WPG = MK_WPG;
 constexpr int TPG = 32 * WPG;                        // threads per gate
-// Latency launch (batches that fit on the SMs one gate each, l = 2): 12 warps per gate, one per (prime, output polynomial, digit
-// pair), so the two forward transforms a throughput warp runs back to back run side by side; the partial sums of the two digit
-// pairs are combined through a tile before the inverse transform.  Same arithmetic, bit-identical results.
-constexpr int LAT_WPG = 12;
+// Latency launch (batches that fit on the SMs one gate each, l >= 2): 6 l warps per gate, one per (prime, output polynomial, digit
+// pair), so the l forward transforms a throughput warp runs back to back run side by side; the partial sums of the digit pairs are
+// combined through the tiles before the inverse transform.  Same arithmetic, bit-identical results.
+__host__ __device__ constexpr int lat_wpg(int l) { return 6 * l; }
+// Warp numbering of the latency launch: gw = 2 l w + l o + slot, slot in [0, l).  The six warps with digit pair i = 0 alone run the
+// inverse transforms; lat_inv_slot picks their slot so that they spread over the four schedulers of the SM (gw mod 4) instead of
+// piling onto two of them (measured on l = 2: 8.3 ms -> 7.3 ms per launch).  Digit pair of a warp: i = (slot - inv_slot + l) mod l.
+__host__ __device__ constexpr int lat_inv_slot(int l, int w, int o) {
+    return l == 2 ? (w & 1) : l == 3 ? (w == 2 ? 2 - o : 0) : l == 4 ? ((2 * w + o) & 3) : 0;
+}
+__host__ __device__ constexpr int lat_warp(int l, int w, int o, int i) { return 2 * l * w + l * o + (i + lat_inv_slot(l, w, o)) % l; }
 constexpr int MAX_GPC = MK_MAX_GPC;
 constexpr int S_UNROLL = MK_S_UNROLL;
 
@@ -142,7 +149,6 @@ __host__ __device__ inline GateLinear gate_linear(int gate) {
 template <int W = WPG>
 __device__ __forceinline__ void gate_barrier(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(32 * W) : "memory"); }
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void quad_barrier(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // decode_message(x, 2N), numeric-functions.jl:70-73 (wrapping add, arithmetic shift)
 __device__ __forceinline__ int mod_switch_2N(int32_t x) {
@@ -297,13 +303,39 @@ __device__ __forceinline__ void crt_phase(u64* __restrict__ acc, const u32* __re
     }
 }
 
+// the same with an arbitrary tile per (prime, output) (latency launch); 2048 / (32 W) coefficients per thread, all chains at once
+template <bool MUX, int W>
+__device__ __forceinline__ void crt_phase_lat(u64* __restrict__ acc, const u32* __restrict__ tiles, int t00, int t01, int t10, int t11, int t20,
+                                              int t21, int gtid) {
+    constexpr int T = 32 * W, ILP = (2 * N + T - 1) / T;
+    u32 r0[ILP], r1[ILP], r2[ILP];
+    u64 old[ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; j++) {
+        const int idx = gtid + j * T;
+        const int cl = idx < 2 * N ? idx : 0;
+        const int oo = cl >> 10, i = cl & (N - 1);
+        r0[j] = tiles[(oo ? t01 : t00) * rns::TILE_WORDS + i];
+        r1[j] = tiles[(oo ? t11 : t10) * rns::TILE_WORDS + i];
+        r2[j] = tiles[(oo ? t21 : t20) * rns::TILE_WORDS + i];
+        old[j] = MUX ? acc[cl] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < ILP; j++) {
+        const int idx = gtid + j * T;
+        const u64 R = rns::crt_lift(r0[j], r1[j], r2[j], c_rns.crt);
+        if (idx < 2 * N) acc[idx] = old[j] + R;
+    }
+}
+
 template <int L, bool MUX, int W = WPG>
 __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restrict__ dig, u32* __restrict__ tiles,
                                              const uint2_* __restrict__ twB, const u32* __restrict__ key, int a, int bgbit,
                                              int bar_id, int pbar_id, int gtid) {
-    static_assert(W == 3 || W == 6 || (W == LAT_WPG && L == 2), "warps per gate: 3, 6, or 12 (l = 2 only)");
+    static_assert(W == 3 || W == 6 || (L >= 2 && W == lat_wpg(L)), "warps per gate: 3, 6, or 6 l (latency launch)");
+    constexpr bool LAT = L >= 2 && W == lat_wpg(L);
     const int gw = gtid >> 5, lane = gtid & 31;
-    const int w = W == 12 ? gw >> 2 : W == 6 ? gw >> 1 : gw;            // prime of this warp
+    const int w = LAT ? gw / (2 * L) : W == 6 ? gw >> 1 : gw;          // prime of this warp
     decompose_phase<L, MUX, W>(acc, dig, a, bgbit, gtid);
     gate_barrier<W>(bar_id);
     const u32 p = c_rns.p[w], pinv = c_rns.pinv_neg[w];
@@ -316,20 +348,21 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
     const u32* lut = reinterpret_cast<const u32*>(twB) + TWB_WORDS + TWA_WORDS + w * (LUT_BYTES_MAX * LUT_REPL) + (LUT_REPL == 32 ? lane : 0);
     const uint4* kp = reinterpret_cast<const uint4*>(key + (size_t)w * (2 * L * 2 * N)) + lane;   // K[prime][s][out][slot]
     const u32 bias = p - (1u << (bgbit - 1));
-    if constexpr (W == LAT_WPG) {
-        // ---- phase 2 (12 warps): warp (prime w, output o, digit pair i) = 4 w + 2 o + (i ^ (w & 1)) transforms digit polynomial
-        // 2i + o, reads 2i + 1 - o from its partner (w, 1 - o, i), and forms the partial sum of output o over this pair.  The
-        // (w & 1) twist spreads the six i = 0 warps, which alone run the inverse transforms, over all four schedulers.
-        const int o = (gw >> 1) & 1, i = (gw ^ w) & 1;
-        const u32* ptile = tiles + (gw ^ 2) * rns::TILE_WORDS;
-        const int qb = pbar_id + w;      // one named barrier per prime: its four warps exchange tiles among themselves only
+    if constexpr (LAT) {
+        // ---- phase 2 (6 l warps): warp (prime w, output o, digit pair i) transforms digit polynomial 2i + o, reads 2i + 1 - o from
+        // its partner (w, 1 - o, i), and forms the partial sum of output o over this pair
+        const int o = (gw / L) & 1, slot = gw % L;
+        const int i = (slot - lat_inv_slot(L, w, o) + L) % L;
+        const u32* ptile = tiles + lat_warp(L, w, 1 - o, i) * rns::TILE_WORDS;
+        const int qb = pbar_id + w;      // one named barrier per prime: its 2 l warps exchange tiles among themselves only
+        auto prime_barrier = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(qb), "r"(64 * L) : "memory"); };
         const int s_own = 2 * i + o, s_for = 2 * i + 1 - o;
         u32 x[32];
         load_digits(x, dig, lut, s_own, lane, bias);
         warp_ntt_fwd_digits(x, tile, twAf, twBf, p, lane);
 #pragma unroll
         for (int c = 0; c < 32; c++) tile[c * 32 + lane] = x[c];
-        quad_barrier(qb);
+        prime_barrier();
         const uint4* k_own = kp + (size_t)(s_own * 2 + o) * (N / 4);
         const uint4* k_for = kp + (size_t)(s_for * 2 + o) * (N / 4);
 #pragma unroll
@@ -340,19 +373,21 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
             x[4 * q4 + 2] = rns::mont_mul2(x[4 * q4 + 2], ka.z, ptile[(4 * q4 + 2) * 32 + lane], kb.z, p, pinv);
             x[4 * q4 + 3] = rns::mont_mul2(x[4 * q4 + 3], ka.w, ptile[(4 * q4 + 3) * 32 + lane], kb.w, p, pinv);
         }
-        quad_barrier(qb);                                      // the partner is done with this warp's tile
-        // ---- phase 3: the i = 1 warp hands its partial sum to the i = 0 warp of the same (prime, output), which adds it,
+        prime_barrier();                                       // the partner is done with this warp's tile
+        // ---- phase 3: the i > 0 warps hand their partial sums to the i = 0 warp of the same (prime, output), which adds them,
         // inverse-transforms and leaves the residues in its tile; then the CRT of both outputs by the whole gate
-        if (i == 1) {
+        if (i != 0) {
 #pragma unroll
             for (int c = 0; c < 32; c++) tile[c * 32 + lane] = x[c];
-            quad_barrier(qb);
+            prime_barrier();
         } else {
-            quad_barrier(qb);
-            const u32* otile = tiles + (gw ^ 1) * rns::TILE_WORDS;
+            prime_barrier();
 #pragma unroll
             for (int c = 0; c < 32; c++) {
-                const u32 v = x[c] + otile[c * 32 + lane];      // < 5.5p
+                u32 v = x[c];
+#pragma unroll
+                for (int ii = 1; ii < L; ii++) v += tiles[lat_warp(L, w, o, ii) * rns::TILE_WORDS + c * 32 + lane];   // < 2.75 l p <= 11p
+                if (L > 2) v = rns::umin32(v, v - 2 * p4);
                 x[c] = rns::umin32(v, v - p4);                  // [0, 4p)
             }
             warp_ntt_inv(x, tile, twAi, twBi, p, lane);
@@ -360,7 +395,10 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
             for (int r = 0; r < 32; r++) tile[32 * r + lane] = x[r];   // residues in coefficient order
         }
         gate_barrier<W>(bar_id);
-        crt_phase<MUX, W, 6>(acc, tiles, 2 * rns::TILE_WORDS, 5 * rns::TILE_WORDS, 8 * rns::TILE_WORDS, gtid);   // warp (w, o, i = 0) = 4 w + 2 o + (w & 1)
+        // residues of (prime w', output oo) are in the tile of warp lat_warp(L, w', oo, 0)
+        constexpr int t00 = lat_warp(L, 0, 0, 0), t01 = lat_warp(L, 0, 1, 0), t10 = lat_warp(L, 1, 0, 0), t11 = lat_warp(L, 1, 1, 0),
+                      t20 = lat_warp(L, 2, 0, 0), t21 = lat_warp(L, 2, 1, 0);
+        crt_phase_lat<MUX, W>(acc, tiles, t00, t01, t10, t11, t20, t21, gtid);
         gate_barrier<W>(bar_id);
     } else if constexpr (W == 6) {
         // ---- phase 2 (6 warps): this warp transforms the digit polynomials of its parity, reads the partner's from the
@@ -618,9 +656,13 @@ __device__ __forceinline__ void blind_rotate_body(const BlindRotateArgs& p) {
     if (gtid == 0) ext[N] = t64tot32((int64_t)acc[N]);
 }
 
-// GPC gates per CTA, W warps per gate, 12 warps per SM at 168 registers (throughput: <L, 2, 6>; small batches: <L, 1, 6>, <2, 1, 12>)
+// GPC gates per CTA, W warps per gate, 12 warps per SM at 168 registers (throughput: <L, 2, 6>; small batches of l = 1: <1, 1, 6>)
 template <int L, int GPC, int W = WPG>
 __global__ void __maxnreg__(MK_MAXNREG) blind_rotate_kernel(BlindRotateArgs p) { blind_rotate_body<L, GPC, W>(p); }
+
+// latency launch: one gate per CTA, 6 l warps (168 registers at l = 2, 112 at l = 3, 80 at l = 4: a latency warp keeps no wide accumulators)
+template <int L>
+__global__ void __launch_bounds__(32 * lat_wpg(L), 1) blind_rotate_lat_kernel(BlindRotateArgs p) { blind_rotate_body<L, 1, lat_wpg(L)>(p); }
 
 // parity hook: acc_out[g] = ExtProd(acc_in[g], bsk[elem[g]])
 template <int L, int GPC>

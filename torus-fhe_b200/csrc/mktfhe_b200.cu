@@ -121,25 +121,30 @@ int set_attrs(mktfhe_ctx* c) {
     CU_TRY(c, cudaFuncSetAttribute(mk::extprod_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     MK_DISPATCH_L(c, SET_ATTR, 0)
 #undef SET_ATTR
-    // small batches: one gate per CTA (see launch_blind_rotate)
-    const int sm1 = (int)(mk::TW_SMEM_BYTES + mk::gate_smem_bytes(c->prm.l));
+    // small batches and tails: one gate per CTA (see launch_blind_rotate)
+    const int l = c->prm.l;
+    const int sm1 = (int)(mk::TW_SMEM_BYTES + mk::gate_smem_bytes(l));        // six warps, one gate per CTA (l = 1, or MKTFHE_B200_LATENCY=0)
 #define SET_ATTR1(L, GPC, dummy) CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_kernel<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm1));
     MK_DISPATCH_L(c, SET_ATTR1, 0)
 #undef SET_ATTR1
-    if (c->prm.l == 2)
-        CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_kernel<2, 1, mk::LAT_WPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(mk::TW_SMEM_BYTES + mk::gate_smem_bytes(2, mk::LAT_WPG))));
+    const int sml = (int)(mk::TW_SMEM_BYTES + mk::gate_smem_bytes(l, mk::lat_wpg(l)));
+    if (l == 2) CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_lat_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sml));
+    if (l == 3) CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_lat_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sml));
+    if (l == 4) CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_lat_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sml));
     return MKTFHE_OK;
 }
 
-// one gate per CTA for gates [g0, g1): the 12-warp latency kernel when l = 2, else the six-warp kernel alone on its SM
+// one gate per CTA for gates [g0, g1): the latency kernel of 6 l warps per gate (l >= 2), else the six-warp kernel alone on its SM
 void launch_one_gate_per_cta(mktfhe_ctx* c, mk::BlindRotateArgs a, size_t g0, size_t g1) {
     a.g0 = (int)g0; a.G = (int)g1;
     const unsigned grid = (unsigned)(g1 - g0);
-    if (c->prm.l == 2 && c->latency_kernel) {
-        mk::blind_rotate_kernel<2, 1, mk::LAT_WPG><<<grid, 32 * mk::LAT_WPG, mk::TW_SMEM_BYTES + mk::gate_smem_bytes(2, mk::LAT_WPG), c->stream>>>(a);
-    } else {
-        const size_t sm1 = mk::TW_SMEM_BYTES + mk::gate_smem_bytes(c->prm.l);
+    const int l = c->prm.l;
+    const size_t sml = mk::TW_SMEM_BYTES + mk::gate_smem_bytes(l, mk::lat_wpg(l));
+    if (l == 2 && c->latency_kernel) mk::blind_rotate_lat_kernel<2><<<grid, 32 * mk::lat_wpg(2), sml, c->stream>>>(a);
+    else if (l == 3 && c->latency_kernel) mk::blind_rotate_lat_kernel<3><<<grid, 32 * mk::lat_wpg(3), sml, c->stream>>>(a);
+    else if (l == 4 && c->latency_kernel) mk::blind_rotate_lat_kernel<4><<<grid, 32 * mk::lat_wpg(4), sml, c->stream>>>(a);
+    else {
+        const size_t sm1 = mk::TW_SMEM_BYTES + mk::gate_smem_bytes(l);
 #define LAUNCH_BR1(L, GPC, dummy) mk::blind_rotate_kernel<L, 1><<<grid, mk::TPG, sm1, c->stream>>>(a)
         MK_DISPATCH_L(c, LAUNCH_BR1, 0)
 #undef LAUNCH_BR1
@@ -148,8 +153,8 @@ void launch_one_gate_per_cta(mktfhe_ctx* c, mk::BlindRotateArgs a, size_t g0, si
 }
 
 // Launch shapes.  Throughput: gpc gates per CTA, one CTA per SM, i.e. waves of gpc * num_sms gates.  A batch -- or the tail a batch
-// leaves after its full waves -- of at most one gate per SM runs one gate per CTA instead: a gate alone on an SM finishes in 7.3 ms
-// (12-warp latency kernel, l = 2) or 9.5 ms (six warps) against 12.3 ms for two gates sharing it.  Bit-identical results.
+// leaves after its full waves -- of at most one gate per SM runs one gate per CTA instead, on the latency kernel (6 l warps per gate): at
+// l = 2 a gate alone on an SM finishes in 7.3 ms against 12.3 ms for two gates sharing it.  Bit-identical results.
 void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G) {
     const size_t wave = (size_t)c->gpc * (size_t)c->num_sms;
     size_t tail = c->gpc > 1 ? G % wave : 0;
