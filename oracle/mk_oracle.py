@@ -30,8 +30,12 @@ def params(n, N, k, l, bgbit, t, basebit, sigma_lwe, sigma_gsw, sigma_ks):
     return Params(n, N, k, l, bgbit, t, basebit, 0, sigma_lwe, sigma_gsw, sigma_ks)
 
 
-# 3-gen-mk-tfhe/src/mk_api.jl:32-38, 84-90, 140-146
+# 3-gen-mk-tfhe/src/mk_api.jl:32-38, 44-50, 84-90, 98-104, 140-146
 PARAMS_2PARTY = dict(n=520, N=1024, k=2, l=2, bgbit=7, t=3, basebit=3,
+                     sigma_lwe=2.0 ** -13.52, sigma_gsw=2.0 ** -30.70, sigma_ks=2.0 ** -13.52)
+PARAMS_3PARTY = dict(n=510, N=1024, k=3, l=2, bgbit=7, t=5, basebit=2,
+                     sigma_lwe=2.0 ** -13.26, sigma_gsw=2.0 ** -30.70, sigma_ks=2.0 ** -13.26)
+PARAMS_5PARTY = dict(n=520, N=1024, k=5, l=3, bgbit=6, t=5, basebit=2,
                      sigma_lwe=2.0 ** -13.52, sigma_gsw=2.0 ** -30.70, sigma_ks=2.0 ** -13.52)
 PARAMS_4PARTY = dict(n=510, N=1024, k=4, l=3, bgbit=6, t=5, basebit=2,
                      sigma_lwe=2.0 ** -13.26, sigma_gsw=2.0 ** -30.70, sigma_ks=2.0 ** -13.26)

@@ -209,9 +209,10 @@ def test_error_behaviour(keys2, engine2):
         engine2.ctx.gate_batch(T._cabi.GATE_NAND, (x[0][:, :1], x[1]), x)
 
 
-@pytest.mark.parametrize("pname", ["PARAMS_4PARTY", "PARAMS_8PARTY"])
+@pytest.mark.parametrize("pname", ["PARAMS_3PARTY", "PARAMS_4PARTY", "PARAMS_5PARTY", "PARAMS_8PARTY"])
 def test_more_parties(oracle, pname):
-    """BASELINE config 3: 4- and 8-party parameter sets (mk_api.jl:84-90, 140-146): l = 3 / 4, longer blind rotation."""
+    """BASELINE config 3: the 3-, 4-, 5- and 8-party parameter sets (mk_api.jl:44-50, 84-90, 98-104, 140-146): l = 2 / 3 / 3 / 4, longer
+    blind rotation, t = 5 key switch."""
     import torus_fhe_b200 as T
     ks = oracle.KeySet(getattr(oracle, pname), seed=0xB20000A1 + 4, nthreads=os.cpu_count() or 8)
     eng = make_engine(ks)
