@@ -1,6 +1,8 @@
 // kernels.cuh -- sm_100a kernels of the 3gen MK-TFHE bootstrapped-gate path.
 //
-//   blind_rotate_kernel    gate prologue + mod-switch + k*n mux-rotate steps + sample extraction + (fused) multi-key key switch
+//   blind_rotate_kernel    gate prologue + mod-switch + k*n mux-rotate steps + sample extraction + (fused) multi-key key switch:
+//                          throughput shape, two six-warp gates per CTA
+//   blind_rotate_lat_kernel  the same body with one gate per CTA on 6 l warps: batches (and tails of batches) of at most one gate per SM
 //   keyswitch_kernel       stand-alone key switch (parity hook; parameter sets the fused epilogue does not cover)
 //   bsk_transform_kernel   one-time: int64 key polynomials -> three NTT-domain residue polynomials, streaming layout
 //   extprod_kernel / negacyclic_mul_kernel   parity hooks / key-generation primitive built from the same device code
@@ -12,7 +14,8 @@
 // a CTA holds 2 gates (12 warps at 168 registers, one CTA per SM) plus one shared-memory copy of the twiddle tables.  Per gate,
 // resident in shared memory for all k*n steps: the Torus64 accumulator (2 x 1024 x 8 B), the current gadget digits
 // (2l x 1024 bytes) and one padded 32x33 word tile per warp (NTT transposes, the exchange of transformed digits between the
-// two warps of a prime, then the inverse transforms' residues for the CRT).
+// two warps of a prime, then the inverse transforms' residues for the CRT).  The latency shape (lat_wpg below) spends 6 l warps on one
+// gate: one warp per (prime, output polynomial, digit pair).
 #pragma once
 #include <cuda_runtime.h>
 #include "ntt_rns.cuh"
