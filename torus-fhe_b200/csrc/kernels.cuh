@@ -540,38 +540,95 @@ __device__ __forceinline__ void fused_keyswitch(const u64* __restrict__ acc, u32
     const int32_t eb = t64tot32((int64_t)acc[N]);
     if (p.ext_out && gtid == 0) p.ext_out[(size_t)g * (N + 1) + N] = eb;
     gate_barrier<W>(bar_id);
-    const int col0 = 4 * gtid;
-    if (col0 >= stride) return;                               // no barrier below: idle threads may leave
+    if constexpr (W < 12) {
+        // six-warp gates (throughput launch): one group of stride / 4 threads does the whole gather
+        const int col0 = 4 * gtid;
+        if (col0 >= stride) return;                               // no barrier below: idle threads may leave
+        const size_t party_words = (size_t)N * T * B1 * stride;
+        const uint4* zero_row = reinterpret_cast<const uint4*>(p.ksk + (size_t)p.k * party_words) + gtid;
+        uint32_t bsum = 0;
+        for (int party = 0; party < p.k; party++) {
+            uint4 out = make_uint4(0, 0, 0, 0);
+            const int32_t* rows = p.ksk + (size_t)party * party_words;
+#pragma unroll 1
+            for (int i = 0; i < N; i += 4) {
+#pragma unroll
+                for (int ii = 0; ii < 4; ii++) {
+                    const uint32_t ai = s_a[i + ii];
+#pragma unroll
+                    for (int j = 1; j <= T; j++) {
+                        const uint32_t d = (ai >> (32 - j * bb)) & (uint32_t)B1;   // :65-67
+                        const uint4* r = d ? reinterpret_cast<const uint4*>(rows + (((size_t)(i + ii) * T + (j - 1)) * B1 + (d - 1)) * stride) + gtid
+                                           : zero_row;                              // :74-76
+                        const uint4 v = MK_KS_LD(r);
+                        out.x -= v.x; out.y -= v.y; out.z -= v.z; out.w -= v.w;
+                    }
+                }
+            }
+            const uint32_t o4[4] = {out.x, out.y, out.z, out.w};
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int col = col0 + c;
+                if (col < n) p.oa[((size_t)g * p.k + party) * n + col] = (int32_t)o4[c];
+                if (col == n) bsum += o4[c];
+            }
+        }
+        if (col0 <= n && n < col0 + 4) p.ob[g] = (int32_t)((uint32_t)eb + bsum);   // thread owning column n
+        return;
+    }
+    // A row needs stride / 4 threads (131 at n = 520).  With the 6 l warps of the latency launch several such groups fit: group q takes
+    // the coefficients i = 4q, 4q + 1, .. (mod 4 * groups) and the partial sums meet in shared memory behind s_a.
+    const int tpr = stride / 4;                               // threads per row (stride is a multiple of 4)
+    constexpr int MAXG = 4;
+    const int groups = min(MAXG, 32 * W / tpr);
+    const int grp = gtid / tpr, t = gtid - grp * tpr;
+    const bool active = grp < groups;
+    const int col0 = 4 * t;
     const size_t party_words = (size_t)N * T * B1 * stride;
-    const uint4* zero_row = reinterpret_cast<const uint4*>(p.ksk + (size_t)p.k * party_words) + gtid;
+    const uint4* zero_row = reinterpret_cast<const uint4*>(p.ksk + (size_t)p.k * party_words) + t;
+    uint4* part = reinterpret_cast<uint4*>(s_a + N);          // [2 (party parity)][groups - 1][tpr] partial sums
     uint32_t bsum = 0;
     for (int party = 0; party < p.k; party++) {
         uint4 out = make_uint4(0, 0, 0, 0);
         const int32_t* rows = p.ksk + (size_t)party * party_words;
+        if (active) {
 #pragma unroll 1
-        for (int i = 0; i < N; i += 4) {
+            for (int i = 4 * grp; i < N; i += 4 * groups) {
 #pragma unroll
-            for (int ii = 0; ii < 4; ii++) {
-                const uint32_t ai = s_a[i + ii];
+                for (int ii = 0; ii < 4; ii++) {
+                    const uint32_t ai = s_a[i + ii];
 #pragma unroll
-                for (int j = 1; j <= T; j++) {
-                    const uint32_t d = (ai >> (32 - j * bb)) & (uint32_t)B1;   // :65-67
-                    const uint4* r = d ? reinterpret_cast<const uint4*>(rows + (((size_t)(i + ii) * T + (j - 1)) * B1 + (d - 1)) * stride) + gtid
-                                       : zero_row;                              // :74-76
-                    const uint4 v = MK_KS_LD(r);
-                    out.x -= v.x; out.y -= v.y; out.z -= v.z; out.w -= v.w;
+                    for (int j = 1; j <= T; j++) {
+                        const uint32_t d = (ai >> (32 - j * bb)) & (uint32_t)B1;   // :65-67
+                        const uint4* r = d ? reinterpret_cast<const uint4*>(rows + (((size_t)(i + ii) * T + (j - 1)) * B1 + (d - 1)) * stride) + t
+                                           : zero_row;                              // :74-76
+                        const uint4 v = MK_KS_LD(r);
+                        out.x -= v.x; out.y -= v.y; out.z -= v.z; out.w -= v.w;
+                    }
                 }
             }
         }
-        const uint32_t o4[4] = {out.x, out.y, out.z, out.w};
+        if (groups > 1) {
+            uint4* pp = part + (size_t)(party & 1) * (MAXG - 1) * tpr;
+            if (active && grp > 0) pp[(grp - 1) * tpr + t] = out;
+            gate_barrier<W>(bar_id);
+            if (grp == 0)
+                for (int q = 1; q < groups; q++) {
+                    const uint4 v = pp[(q - 1) * tpr + t];
+                    out.x += v.x; out.y += v.y; out.z += v.z; out.w += v.w;
+                }
+        }
+        if (grp == 0) {
+            const uint32_t o4[4] = {out.x, out.y, out.z, out.w};
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const int col = col0 + c;
-            if (col < n) p.oa[((size_t)g * p.k + party) * n + col] = (int32_t)o4[c];
-            if (col == n) bsum += o4[c];
+            for (int c = 0; c < 4; c++) {
+                const int col = col0 + c;
+                if (col < n) p.oa[((size_t)g * p.k + party) * n + col] = (int32_t)o4[c];
+                if (col == n) bsum += o4[c];
+            }
         }
     }
-    if (col0 <= n && n < col0 + 4) p.ob[g] = (int32_t)((uint32_t)eb + bsum);   // thread owning column n
+    if (grp == 0 && col0 <= n && n < col0 + 4) p.ob[g] = (int32_t)((uint32_t)eb + bsum);   // thread owning column n
 }
 
 // GPC gates per CTA, WPG warps per gate.  Accumulators resident in shared memory for all k*n steps.
