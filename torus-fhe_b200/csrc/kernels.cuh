@@ -61,6 +61,9 @@ constexpr int N = rns::N;
 #ifndef MK_KS_LD
 #define MK_KS_LD __ldg
 #endif
+#ifndef MK_KS_UNROLL
+#define MK_KS_UNROLL 4      // coefficients per iteration of the fused key-switch gather (x t row loads in flight per thread)
+#endif
 #ifndef MK_LOCKSTEP
 #define MK_LOCKSTEP 0       // n > 0: CTA-wide barrier every n steps to keep the gates on the same key element (measured: loses)
 #endif
@@ -551,9 +554,9 @@ __device__ __forceinline__ void fused_keyswitch(const u64* __restrict__ acc, u32
             uint4 out = make_uint4(0, 0, 0, 0);
             const int32_t* rows = p.ksk + (size_t)party * party_words;
 #pragma unroll 1
-            for (int i = 0; i < N; i += 4) {
+            for (int i = 0; i < N; i += MK_KS_UNROLL) {
 #pragma unroll
-                for (int ii = 0; ii < 4; ii++) {
+                for (int ii = 0; ii < MK_KS_UNROLL; ii++) {
                     const uint32_t ai = s_a[i + ii];
 #pragma unroll
                     for (int j = 1; j <= T; j++) {
