@@ -277,8 +277,8 @@ def run_ours(args):
         # accumulated in 64 bits (IMAD.WIDE = 2 slots) + 6 x 1024 Montgomery reductions (3 slots); 2048 CRT lifts (17 slots)
         imad_slots = k * n * ((6 * l * 4608 + 6 * 5120) * 4 + 12 * l * 1024 * 2 + 6 * 1024 * 3 + 2 * 1024 * 17)
         imad_peak = 18.26e12       # measured: tools/pipe_ubench.cu -> profiles/pipe_ubench_r1.txt (62.8 IMAD lanes/clk/SM)
-        ncu_traffic = {"bytes_in_captured_launch": 1.588e9, "gates_in_captured_launch": 2368, "waves_in_captured_launch": 8,
-                       "source": "profiles/ncu_r1_g_blind_rotate.txt (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture of a "
+        ncu_traffic = {"bytes_in_captured_launch": 1.589e9, "gates_in_captured_launch": 2368, "waves_in_captured_launch": 8,
+                       "source": "profiles/ncu_r1_m_blind_rotate.txt (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture of a "
                                  "2368-gate launch): one pass over bsk (102 MB) + ksk (90 MB) per wave of 296 gates, i.e. 0.67 MB per gate against "
                                  "68 MB algorithmic; scaled here to this launch's gate count"}
         traffic = ncu_traffic["bytes_in_captured_launch"] * G / ncu_traffic["gates_in_captured_launch"]
@@ -298,7 +298,7 @@ def run_ours(args):
                 "gpu_launches": int(launches),
                 "roofline": {"kernel": "blind_rotate_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved / hbm_peak, "traffic": traffic, "traffic_note": ncu_traffic, "peak_source": peak_src,
-                             "note": "contract roofline (HBM); the kernel is IMAD-pipe bound and streams the key from L2 (hit rate 97.3 %): see integer_bound",
+                             "note": "contract roofline (HBM); the kernel is IMAD-pipe bound and streams the key from L2 (hit rate 98 %): see integer_bound",
                              "algorithmic_bytes_per_gate": per_gate, "algorithmic_bytes_breakdown": {"bsk": bsk_1limb, "ksk_rows_gathered": ksk_gather if fused_ks else 0,
                                                                                                        "ciphertext_io": ct_io},
                              "streamed_bytes_per_gate_this_build": bsk_stream,
@@ -311,7 +311,7 @@ def run_ours(args):
                                                "achieved": G * imad_slots / (br_ms * 1e-3) / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-slots/s",
                                                "frac": G * imad_slots / (br_ms * 1e-3) / imad_peak,
                                                "ncu_fmaheavy_pipe_busy": 0.66, "ncu_issue_active": 0.57,
-                                               "ncu_source": "profiles/ncu_r1_g_blind_rotate.txt, ncu_r1_g_opmix.txt (executed fma-pipe slots incl. "
+                                               "ncu_source": "profiles/ncu_r1_m_blind_rotate.txt, ncu_r1_m_opmix.txt (executed fma-pipe slots incl. "
                                                "address/move overhead: 15.1 k warp-slots per gate-step)"}},
                 "clocks": clocks, "decryptions_correct": ok}
         if world == 1 and not args.no_cpu_baseline and args.parties == 2:
