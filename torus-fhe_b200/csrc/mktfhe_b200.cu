@@ -158,7 +158,9 @@ void launch_one_gate_per_cta(mktfhe_ctx* c, mk::BlindRotateArgs a, size_t g0, si
 void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G) {
     const size_t wave = (size_t)c->gpc * (size_t)c->num_sms;
     size_t tail = c->gpc > 1 ? G % wave : 0;
-    if (tail > (size_t)c->num_sms || (!c->split_tail && tail != G)) tail = 0;
+    // the tail of a larger batch is split off only at l = 2, where it was measured to pay on two workloads; at l = 3 the split lost 1.2 %
+    // (the partial last wave of the throughput grid cost 3 ms there, not a full wave), profiles/ab_r1.txt
+    if (tail > (size_t)c->num_sms || ((!c->split_tail || c->prm.l != 2) && tail != G)) tail = 0;
     const size_t head = G - tail;
     if (head) {
         mk::BlindRotateArgs h = a;
