@@ -17,3 +17,23 @@ def test_ntt_host_emulation(tmp_path, crt_float):
                            os.path.join(ROOT, "tests", "host_emu", "ntt_emu.cpp"), "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ntt_emu: OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_ntt2048_host_emulation(tmp_path):
+    """Arithmetic core for the N = 2048 parameter sets (ntt2048.cuh, groundwork): transform vs definition, four-prime Garner lift,
+    exact products of 26-bit digits with 64-bit keys vs schoolbook."""
+    exe = str(tmp_path / "ntt2048_emu")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "torus-fhe_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "host_emu", "ntt2048_emu.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ntt2048_emu: OK" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_ntt2048_on_gpu(tmp_path):
+    """The same core as a warp-level CUDA kernel: exact negacyclic products of degree 2048 on the B200 vs schoolbook."""
+    exe = str(tmp_path / "ntt2048_gpu")
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I", os.path.join(ROOT, "torus-fhe_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "host_emu", "ntt2048_gpu.cu"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ntt2048_gpu: OK" in out.stdout, out.stdout + out.stderr
