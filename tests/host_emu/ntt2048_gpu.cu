@@ -1,7 +1,8 @@
 // ntt2048_gpu.cu -- the N = 2048 arithmetic core (torus-fhe_b200/csrc/ntt2048.cuh) on the GPU: one warp per (product, prime) computes
 // c = a * b mod (X^2048 + 1, p) with the warp-level transform (64 coefficients per thread, padded 64 x 33 tile), the host lifts the
 // four residue polynomials with crt4_lift and compares with an exact schoolbook product mod 2^64.  a: 26-bit signed gadget digits,
-// b: 64-bit keys -- the operand shapes of an external product at the 16-party parameters.  Groundwork: not part of the library yet.
+// b: 64-bit keys -- the operand shapes of an external product at the 16-party parameters.  Stand-alone check of the core under
+// kernels2k.cuh.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I torus-fhe_b200/csrc tests/host_emu/ntt2048_gpu.cu -o ntt2048_gpu
 #include <cstdio>
 #include <cstdlib>

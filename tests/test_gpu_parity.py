@@ -310,3 +310,49 @@ def test_synthetic_parameter_sets_bit_exact(oracle, prm):
             assert np.array_equal(got[g], ks.extprod(oracle.EXACT_SCHOOLBOOK, party, j, acc[g])), g
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("prm", [
+    dict(n=6, N=2048, k=2, l=1, bgbit=26, t=4, basebit=3),     # shape of mktfhe_parameters_16party_3gen / 32party (mk_api.jl:214-252)
+    dict(n=5, N=2048, k=3, l=1, bgbit=24, t=5, basebit=3),     # shape of mktfhe_parameters_128party_3gen (:292-298), odd party count
+], ids=["bg26_t4", "bg24_t5"])
+def test_n2048_parameter_sets_bit_exact(oracle, prm):
+    """The N = 2048, l = 1 path (kernels2k.cuh: four primes, 26-bit gadget digits): accumulator, extracted sample and key-switched
+    bootstrap bit-exact against the oracle's exact schoolbook back-end, gates decrypt to the truth table, and the exact product hook
+    at degree 2048.  Reduced LWE dimension so that the O(N^2) oracle finishes in seconds."""
+    import torus_fhe_b200 as T
+    full = dict(prm, sigma_lwe=2.0 ** -15.34, sigma_gsw=2.0 ** -62, sigma_ks=2.0 ** -15.34)
+    ks = oracle.KeySet(full, seed=2048 + prm["bgbit"], nthreads=os.cpu_count() or 8)
+    eng = make_engine(ks)
+    try:
+        r = np.random.default_rng(prm["bgbit"])
+        G = 5
+        a = r.integers(-2 ** 31, 2 ** 31, (G, ks.k, ks.n)).astype(np.int32)
+        b = r.integers(-2 ** 31, 2 ** 31, G).astype(np.int32)
+        a[0] = 0                                                  # all rotations skipped
+        ext, acc = eng.ctx.blind_rotate_batch(MU, a, b, want_acc=True)
+        for g in range(G):
+            ea, eb, oacc, _ = ks.bootstrap_wo_keyswitch(oracle.EXACT_SCHOOLBOOK, MU, a[g], b[g], want_acc=True)
+            assert np.array_equal(acc[g], oacc), g
+            assert np.array_equal(ext[g, :2048], ea) and ext[g, 2048] == eb, g
+        oa, ob = eng.ctx.bootstrap_batch(MU, a, b)
+        ra, rb = ks.bootstrap_batch(oracle.EXACT_SCHOOLBOOK, MU, a, b)
+        assert np.array_equal(oa, ra) and np.array_equal(ob, rb)
+        bits = np.array([[0, 0], [0, 1], [1, 0], [1, 1]], np.uint8)
+        x, y = ks.encrypt(bits[:, 0], 31), ks.encrypt(bits[:, 1], 32)
+        for gate, plain in ((T._cabi.GATE_NAND, ~(bits[:, 0].astype(bool) & bits[:, 1].astype(bool))), (T._cabi.GATE_XOR, bits[:, 0].astype(bool) ^ bits[:, 1].astype(bool))):
+            ga, gb = eng.ctx.gate_batch(gate, x, y)
+            qa, qb = ks.gate_batch(oracle.EXACT_SCHOOLBOOK, gate, x, y)
+            assert np.array_equal(ga, qa) and np.array_equal(gb, qb)
+            assert np.array_equal(ks.decrypt(ga, gb), plain)
+        small = r.integers(-2 ** 25, 2 ** 25, (3, 2048), dtype=np.int64)
+        small[1] = -2 ** 25
+        big = r.integers(-2 ** 63, 2 ** 63 - 1, (3, 2048), dtype=np.int64)
+        big[1] = -2 ** 63
+        got = eng.ctx.negacyclic_mul_batch(small, big)
+        for i in range(3):
+            assert np.array_equal(got[i], oracle.negacyclic_mul(small[i], big[i], oracle.EXACT_SCHOOLBOOK)), i
+        with pytest.raises(T.MktfheError):
+            eng.ctx.extprod_batch(np.array([0], np.int32), acc[:1])     # the single-product hook is N = 1024 only
+    finally:
+        eng.close()

@@ -20,7 +20,7 @@ def test_ntt_host_emulation(tmp_path, crt_float):
 
 
 def test_ntt2048_host_emulation(tmp_path):
-    """Arithmetic core for the N = 2048 parameter sets (ntt2048.cuh, groundwork): transform vs definition, four-prime Garner lift,
+    """Arithmetic core of the N = 2048 parameter sets (ntt2048.cuh): transform vs definition, four-prime Garner lift,
     exact products of 26-bit digits with 64-bit keys vs schoolbook."""
     exe = str(tmp_path / "ntt2048_emu")
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "torus-fhe_b200", "csrc"),

@@ -1,0 +1,271 @@
+// kernels2k.cuh -- the bootstrapped-gate path for the N = 2048, l = 1 parameter sets (mktfhe_parameters_{16,32,64,128}party_3gen,
+// mk_api.jl:214-298): gadget digits of up to 27 bits, four 28-bit primes (ntt2048.cuh), one gate per CTA.
+//
+// First, functional version of this path: same step structure as kernels.cuh (decompose -> forward transforms -> multiply-accumulate
+// -> inverse transforms -> CRT), eight warps per gate = (prime, polynomial), the accumulator resident in shared memory for all k*n
+// steps.  Not tuned yet: per-lane twiddles come from global memory (their 127 KB do not fit beside the tiles), the key switch is the
+// stand-alone kernel.  Reference semantics as in kernels.cuh (3gen_mk_internals.jl:59-116, tgsw_3gen.jl:102-113, tgsw.jl:112-138,
+// rlwe.jl:70-74, keyswitch.jl:45-80).
+#pragma once
+#include <cuda_runtime.h>
+#include "kernels.cuh"
+#include "ntt2048.cuh"
+
+namespace mk2k {
+
+using rns::uint2_;
+constexpr int N = rns2k::N, NP = rns2k::NP;
+constexpr int WARPS = 2 * NP, THREADS = 32 * WARPS;          // warp = (prime, polynomial)
+constexpr int TILE_WORDS = rns2k::TILE_WORDS, TILE_STRIDE = rns2k::TILE_STRIDE;
+
+__constant__ rns2k::Consts c_k2;
+
+// BSK layout (u32): [elem = party*n + j][prime][src][out][2048 key slots]; (out, src) <-> reference parts as in kernels.cuh.
+// key slot of transformed position 32 (lane + 32 h) + c: a warp-wide 128-bit load is one contiguous 512-byte segment
+__host__ __device__ inline size_t bsk_elem_words() { return (size_t)NP * 2 * 2 * N; }
+__host__ __device__ inline int key_slot(int lane, int h, int c) { return ((h * 8 + (c >> 2)) * 32 + lane) * 4 + (c & 3); }
+__host__ __device__ constexpr size_t smem_bytes() { return (size_t)2 * N * 8 + (size_t)2 * N * 4 + (size_t)WARPS * TILE_WORDS * 4; }
+
+struct Args {
+    int G, n, k, bgbit;
+    const u32* bsk;
+    const uint2_* twB;
+    const int32_t *xa, *xb, *ya, *yb, *za, *zb;
+    mk::GateLinear lin;
+    const int32_t* gate_ids;
+    int64_t mu;
+    int32_t* ext_out;   // [G][N+1]
+    int64_t* acc_out;   // [G][2][N] or nullptr
+};
+
+// decode_message(x, 2N) for N = 2048: (x + 2^19) >> 20
+__device__ __forceinline__ int mod_switch_2N(int32_t x) { return (int32_t)((uint32_t)x + (1u << 19)) >> 20; }
+
+// forward transform of this warp's polynomial: x[r] = a[32 r + lane] in [0, 2p) -> y[h][c] = position 32 (lane + 32 h) + c, < 14p
+__device__ __forceinline__ void warp_fwd(u32 (&x)[64], u32 (&y)[2][32], u32* tile, const uint2_* twB, int pi, u32 p, int lane) {
+    rns2k::fwd_passA64(x, c_k2.twA[pi][0], p);
+#pragma unroll
+    for (int r = 0; r < 64; r++) tile[r * TILE_STRIDE + lane] = x[r];
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+#pragma unroll
+        for (int c = 0; c < 32; c++) y[h][c] = rns2k::reduce_to_4p(tile[(lane + 32 * h) * TILE_STRIDE + c], 4 * p);
+        rns2k::fwd_passB32(y[h], twB + rns2k::twB_index(pi, 0, h, 0, lane), p);
+    }
+    __syncwarp();
+}
+// inverse: y[h][c] in [0, 4p) -> x[r] = N * a[32 r + lane] in [0, 4p)
+__device__ __forceinline__ void warp_inv(u32 (&y)[2][32], u32 (&x)[64], u32* tile, const uint2_* twB, int pi, u32 p, int lane) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        rns2k::inv_passB32(y[h], twB + rns2k::twB_index(pi, 1, h, 0, lane), p);
+#pragma unroll
+        for (int c = 0; c < 32; c++) tile[(lane + 32 * h) * TILE_STRIDE + c] = y[h][c];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 64; r++) x[r] = tile[r * TILE_STRIDE + lane];
+    __syncwarp();
+    rns2k::inv_passA64(x, c_k2.twA[pi][1], p);
+}
+
+// one gate per CTA; acc[0] = mask, acc[1] = body
+__global__ void __launch_bounds__(THREADS, 1) blind_rotate2k_kernel(Args p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* acc = reinterpret_cast<u64*>(smem_raw);
+    int32_t* dig = reinterpret_cast<int32_t*>(smem_raw + (size_t)2 * N * 8);           // [src][N] signed digits; src 0 = body, 1 = mask
+    u32* tiles = reinterpret_cast<u32*>(smem_raw + (size_t)2 * N * 8 + (size_t)2 * N * 4);
+    const int tid = threadIdx.x, gw = tid >> 5, lane = tid & 31;
+    const int w = gw >> 1, s = gw & 1;                     // prime; digit polynomial transformed = output polynomial accumulated
+    const int g = blockIdx.x;
+    const u32 pr = c_k2.p[w], pinv = c_k2.pinv_neg[w];
+    u32* tile = tiles + gw * TILE_WORDS;
+    const u32* ptile = tiles + (gw ^ 1) * TILE_WORDS;
+    const int kn = p.k * p.n;
+    const mk::GateLinear lin = p.gate_ids ? mk::gate_linear(__ldg(p.gate_ids + g)) : p.lin;
+    auto rotation = [&](const int32_t* xs, const int32_t* ys, const int32_t* zs, size_t idx, uint32_t mu0) {
+        uint32_t t = mu0 + (uint32_t)lin.cx * (uint32_t)__ldg(xs + idx);
+        if (lin.cy) t += (uint32_t)lin.cy * (uint32_t)__ldg(ys + idx);
+        if (lin.cz) t += (uint32_t)lin.cz * (uint32_t)__ldg(zs + idx);
+        return mod_switch_2N((int32_t)t);
+    };
+    {   // acc = (0, X^{-barb} * testvect)  (3gen_mk_internals.jl:88-92)
+        const int barb = rotation(p.xb, p.yb, p.zb, g, (uint32_t)lin.mu0);
+        const int sh = (-barb) & (2 * N - 1);
+        for (int i = tid; i < N; i += THREADS) {
+            const int idx = (i - sh) & (2 * N - 1);
+            acc[i] = 0;
+            acc[N + i] = (idx & N) ? (u64)0 - (u64)p.mu : (u64)p.mu;
+        }
+    }
+    __syncthreads();
+    const u64 off = ((u64)1 << (64 - p.bgbit)) << (p.bgbit - 1);          // tgsw.jl:24-30 with l = 1
+    const u64 dmask = ((u64)1 << p.bgbit) - 1;
+    const int64_t half = (int64_t)1 << (p.bgbit - 1);
+    const size_t abase = (size_t)g * kn;
+    for (int it = 0; it < kn; it++) {
+        const int a = rotation(p.xa, p.ya, p.za, abase + it, 0u);
+        if (a == 0) continue;                                              // 3gen_mk_internals.jl:69
+        // ---- decompose X^a * acc - acc (tgsw.jl:112-138, l = 1)
+        for (int i = tid; i < 2 * N; i += THREADS) {
+            const int c = i >> 11, ii = i & (N - 1);
+            const u64* poly = acc + c * N;
+            const int idx = (ii - a) & (2 * N - 1);
+            u64 v = poly[idx & (N - 1)];
+            if (idx & N) v = 0 - v;
+            const u64 t = v - poly[ii] + off;
+            dig[(1 - c) * N + ii] = (int32_t)((int64_t)((t >> (64 - p.bgbit)) & dmask) - half);
+        }
+        __syncthreads();
+        // ---- forward transform of digit polynomial s under prime w; exchange with the partner (w, 1 - s)
+        u32 x[64], y[2][32];
+#pragma unroll
+        for (int r = 0; r < 64; r++) x[r] = (u32)(dig[s * N + 32 * r + lane] + (int32_t)pr);      // signed digit + p in [0, 2p)
+        warp_fwd(x, y, tile, p.twB, w, pr, lane);
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int c = 0; c < 32; c++) tile[(h * 32 + c) * 32 + lane] = y[h][c];
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + w) : "memory");
+        // ---- output polynomial o = s: both digit polynomials times their key rows, one Montgomery reduction per point
+        const u32* kw = p.bsk + (size_t)it * bsk_elem_words() + (size_t)w * (2 * 2 * N);
+        const uint4* k_own = reinterpret_cast<const uint4*>(kw + (size_t)(s * 2 + s) * N) + lane;
+        const uint4* k_for = reinterpret_cast<const uint4*>(kw + (size_t)((1 - s) * 2 + s) * N) + lane;
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int q4 = 0; q4 < 8; q4++) {
+                const uint4 ka = __ldg(k_own + (h * 8 + q4) * 32), kb = __ldg(k_for + (h * 8 + q4) * 32);
+                const u32* pt = ptile + (h * 32 + 4 * q4) * 32 + lane;
+                y[h][4 * q4 + 0] = rns::mont_mul2(y[h][4 * q4 + 0], ka.x, pt[0], kb.x, pr, pinv);       // < 2.75p
+                y[h][4 * q4 + 1] = rns::mont_mul2(y[h][4 * q4 + 1], ka.y, pt[32], kb.y, pr, pinv);
+                y[h][4 * q4 + 2] = rns::mont_mul2(y[h][4 * q4 + 2], ka.z, pt[64], kb.z, pr, pinv);
+                y[h][4 * q4 + 3] = rns::mont_mul2(y[h][4 * q4 + 3], ka.w, pt[96], kb.w, pr, pinv);
+            }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + w) : "memory");              // the partner is done with this warp's tile
+        // ---- inverse transform, residues to the tile in coefficient order, CRT by the whole gate
+        warp_inv(y, x, tile, p.twB, w, pr, lane);
+#pragma unroll
+        for (int r = 0; r < 64; r++) tile[32 * r + lane] = x[r];
+        __syncthreads();
+        for (int i = tid; i < 2 * N; i += THREADS) {
+            const int o = i >> 11, ii = i & (N - 1);
+            const u32 r[NP] = {tiles[(0 * 2 + o) * TILE_WORDS + ii], tiles[(1 * 2 + o) * TILE_WORDS + ii], tiles[(2 * 2 + o) * TILE_WORDS + ii],
+                               tiles[(3 * 2 + o) * TILE_WORDS + ii]};
+            acc[i] += rns2k::crt4_lift(r, c_k2);
+        }
+        __syncthreads();
+    }
+    if (p.acc_out) {
+        int64_t* ao = p.acc_out + (size_t)g * 2 * N;
+        for (int i = tid; i < 2 * N; i += THREADS) ao[i] = (int64_t)acc[i];
+    }
+    // rlwe_extract_sample_64 (rlwe.jl:70-74): a'_0 = mask_0, a'_i = -mask_{N-i}, b' = body_0
+    int32_t* ext = p.ext_out + (size_t)g * (N + 1);
+    for (int i = tid; i < N; i += THREADS) {
+        const u64 v = i == 0 ? acc[0] : (u64)0 - acc[N - i];
+        ext[i] = mk::t64tot32((int64_t)v);
+    }
+    if (tid == 0) ext[N] = mk::t64tot32((int64_t)acc[N]);
+}
+
+// One warp per (polynomial, prime): raw int64 key of one party, [n][4 parts][N] (l = 1) -> transformed residues in the streaming layout
+constexpr int XF_WARPS = 2;
+__global__ void __launch_bounds__(XF_WARPS * 32) bsk_transform2k_kernel(const int64_t* __restrict__ raw, u32* __restrict__ bsk, int n, int party,
+                                                                         const uint2_* __restrict__ twB, int ntasks) {
+    __shared__ u32 tiles[XF_WARPS * TILE_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int task = blockIdx.x * XF_WARPS + warp;
+    if (task >= ntasks) return;
+    const int pi = task % NP, pq = task / NP;
+    const int part = pq & 3, j = pq >> 2;
+    const int out = part < 2 ? 1 : 0;                       // part_1: body<-body, part_2: body<-mask, part_3: mask<-mask, part_4: mask<-body
+    const int src = (part == 0 || part == 3) ? 0 : 1;
+    const u32 p = c_k2.p[pi];
+    const int64_t* poly = raw + (size_t)pq * N;
+    u32 x[64], y[2][32];
+#pragma unroll
+    for (int r = 0; r < 64; r++) x[r] = rns::residue_i64(poly[32 * r + lane], p);
+    warp_fwd(x, y, tiles + warp * TILE_WORDS, twB, pi, p, lane);
+    u32* dst = bsk + ((size_t)party * n + j) * bsk_elem_words() + ((size_t)(pi * 2 + src) * 2 + out) * N;
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int c = 0; c < 32; c++) dst[key_slot(lane, h, c)] = rns::mulmod(y[h][c] % p, c_k2.key_scale[pi], p);
+}
+
+// exact c = a * b mod (X^2048 + 1, 2^64) for |a_i| <= 2^25 (key generation primitive / parity hook); NP warps = NP primes
+__global__ void __launch_bounds__(32 * NP) negacyclic_mul2k_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ b, int64_t* __restrict__ c,
+                                                                   const uint2_* __restrict__ twB) {
+    __shared__ u32 tiles[NP * TILE_WORDS];
+    const int pi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t g = blockIdx.x;
+    const u32 p = c_k2.p[pi], pinv = c_k2.pinv_neg[pi];
+    u32* tile = tiles + pi * TILE_WORDS;
+    u32 x[64], ya[2][32], yb[2][32];
+#pragma unroll
+    for (int r = 0; r < 64; r++) x[r] = rns::residue_i64(a[g * N + 32 * r + lane], p);
+    warp_fwd(x, ya, tile, twB, pi, p, lane);
+#pragma unroll
+    for (int r = 0; r < 64; r++) x[r] = rns::residue_i64(b[g * N + 32 * r + lane], p);
+    warp_fwd(x, yb, tile, twB, pi, p, lane);
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int cc = 0; cc < 32; cc++) {
+            const u32 ks = rns::mulmod(yb[h][cc] % p, c_k2.key_scale[pi], p);
+            ya[h][cc] = rns::mont_mul(ya[h][cc], ks, p, pinv);
+        }
+    warp_inv(ya, x, tile, twB, pi, p, lane);
+#pragma unroll
+    for (int r = 0; r < 64; r++) tile[32 * r + lane] = x[r];
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += 32 * NP) {
+        const u32 r[NP] = {tiles[i], tiles[TILE_WORDS + i], tiles[2 * TILE_WORDS + i], tiles[3 * TILE_WORDS + i]};
+        c[g * N + i] = (int64_t)rns2k::crt4_lift(r, c_k2);
+    }
+}
+
+// stand-alone multi-key key switch for N = 2048 (same algorithm as mk::keyswitch_kernel)
+__global__ void __launch_bounds__(mk::KS_THREADS) keyswitch2k_kernel(int n, int k, int t, int basebit, const int32_t* __restrict__ ksk,
+                                                                      const int32_t* __restrict__ ext, int32_t* __restrict__ oa, int32_t* __restrict__ ob) {
+    __shared__ uint32_t s_a[N];
+    const int g = blockIdx.x, tid = threadIdx.x;
+    const int B1 = (1 << basebit) - 1, row = n + 1, stride = mk::ks_row_stride(n);
+    const uint32_t prec_offset = 1u << (32 - (1 + basebit * t));   // keyswitch.jl:58
+    const int32_t* e = ext + (size_t)g * (N + 1);
+    for (int i = tid; i < N; i += mk::KS_THREADS) s_a[i] = (uint32_t)e[i] + prec_offset;
+    __syncthreads();
+    const int ncols = (row + mk::KS_THREADS - 1) / mk::KS_THREADS;
+    uint32_t bsum = 0;
+    for (int p = 0; p < k; p++) {
+        uint32_t acc[mk::KS_MAXCOLS];
+#pragma unroll
+        for (int c = 0; c < mk::KS_MAXCOLS; c++) acc[c] = 0;
+        const int32_t* rows = ksk + (size_t)p * N * t * B1 * stride;
+        for (int i = 0; i < N; i++) {
+            const uint32_t ai = s_a[i];
+            for (int j = 1; j <= t; j++) {
+                const uint32_t d = (ai >> (32 - j * basebit)) & (uint32_t)B1;
+                if (d != 0) {
+                    const int32_t* r = rows + (((size_t)i * t + (j - 1)) * B1 + (d - 1)) * stride;
+#pragma unroll
+                    for (int c = 0; c < mk::KS_MAXCOLS; c++) {
+                        const int col = tid + c * mk::KS_THREADS;
+                        if (c < ncols && col < row) acc[c] -= (uint32_t)__ldg(r + col);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < mk::KS_MAXCOLS; c++) {
+            const int col = tid + c * mk::KS_THREADS;
+            if (c < ncols && col < n) oa[((size_t)g * k + p) * n + col] = (int32_t)acc[c];
+            if (c < ncols && col == n) bsum += acc[c];
+        }
+    }
+    if (tid == n % mk::KS_THREADS) ob[g] = (int32_t)((uint32_t)e[N] + bsum);
+}
+
+}  // namespace mk2k

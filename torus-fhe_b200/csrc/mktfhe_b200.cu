@@ -16,6 +16,8 @@
 
 #include "../../include/mktfhe_b200.h"
 #include "kernels.cuh"
+#include "kernels2k.cuh"
+#include "tables2048.h"
 #include "tables.h"
 
 namespace {
@@ -83,7 +85,18 @@ int reserve(mktfhe_ctx* c, DevBuf& b, size_t bytes) {
 
 int check_params(const mktfhe_params* p) {
     if (!p) return fail(nullptr, MKTFHE_EINVAL, "params is NULL");
-    if (p->N != mk::N) return fail(nullptr, MKTFHE_EINVAL, "unsupported N=%d (only 1024)", p->N);
+    if (p->N == mk2k::N) {
+        // N = 2048 sets (mk_api.jl:214-298): l = 1 with a wide gadget base, four-prime exact product (kernels2k.cuh)
+        if (p->l != 1) return fail(nullptr, MKTFHE_EINVAL, "N=2048 is supported with gsw_decomp_length l=1 only (got %d)", p->l);
+        if (p->bgbit < 1 || p->bgbit > 27) return fail(nullptr, MKTFHE_EINVAL, "N=2048: unsupported gsw_log2_base=%d (1..27)", p->bgbit);
+        if (std::log2((double)(2 * p->l) * p->N) + (p->bgbit - 1) + 63.0 >= rns2k::log2_crt_bound())
+            return fail(nullptr, MKTFHE_EINVAL, "2l*N*Bg/2*2^63 exceeds the CRT range of the four-prime exact product");
+        if (p->k < 1 || p->n < 1 || (long long)p->n * p->k > (1 << 18)) return fail(nullptr, MKTFHE_EINVAL, "need 1 <= n*k <= 2^18");
+        if (p->n + 1 > mk::KS_THREADS * mk::KS_MAXCOLS) return fail(nullptr, MKTFHE_EINVAL, "n too large for the key-switch kernel");
+        if (p->t < 1 || p->basebit < 1 || p->t * p->basebit > 31) return fail(nullptr, MKTFHE_EINVAL, "need t*basebit <= 31");
+        return MKTFHE_OK;
+    }
+    if (p->N != mk::N) return fail(nullptr, MKTFHE_EINVAL, "unsupported N=%d (1024 or 2048)", p->N);
     if (p->l < 1 || p->l > 4) return fail(nullptr, MKTFHE_EINVAL, "unsupported gsw_decomp_length l=%d (1..4)", p->l);
     if (p->bgbit < 1 || p->l * p->bgbit > 32) return fail(nullptr, MKTFHE_EINVAL, "unsupported l*bgbit=%d (<=32)", p->l * p->bgbit);
     if ((1 << p->bgbit) > mk::LUT_BYTES_MAX)
@@ -112,6 +125,10 @@ size_t br_smem_bytes(const mktfhe_ctx* c) { return mk::cta_smem_bytes(c->prm.l) 
     }
 
 int set_attrs(mktfhe_ctx* c) {
+    if (c->prm.N == mk2k::N) {
+        CU_TRY(c, cudaFuncSetAttribute(mk2k::blind_rotate2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk2k::smem_bytes()));
+        return MKTFHE_OK;
+    }
     const int sm = (int)br_smem_bytes(c);
 #define SET_ATTR(L, GPC, dummy)                                                                                                    \
     CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));             \
@@ -189,6 +206,34 @@ int run_bootstrap_dev(mktfhe_ctx* c, mk::GateLinear lin, int64_t mu, size_t G, c
     if (G > 0x7fffffffu) return fail(c, MKTFHE_EINVAL, "batch too large");
     cudaStream_t saved = c->stream;
     if (st) c->stream = st;
+    if (c->prm.N == mk2k::N) {
+        // N = 2048: one gate per CTA, stand-alone key switch (kernels2k.cuh)
+        int32_t* ext2 = ext_out;
+        if (!ext2) {
+            int rc = reserve(c, c->ext, G * (mk2k::N + 1) * sizeof(int32_t));
+            if (rc) { c->stream = saved; return rc; }
+            ext2 = (int32_t*)c->ext.p;
+        }
+        mk2k::Args a{};
+        a.G = (int)G; a.n = c->prm.n; a.k = c->prm.k; a.bgbit = c->prm.bgbit;
+        a.bsk = c->d_bsk; a.twB = c->d_twB;
+        a.xa = xa; a.xb = xb; a.ya = ya; a.yb = yb; a.za = za; a.zb = zb;
+        a.lin = lin; a.gate_ids = gate_ids; a.mu = mu; a.ext_out = ext2; a.acc_out = acc_out;
+        cudaEventRecord(c->ev[0], c->stream);
+        mk2k::blind_rotate2k_kernel<<<(unsigned)G, mk2k::THREADS, mk2k::smem_bytes(), c->stream>>>(a);
+        c->launches++;
+        cudaEventRecord(c->ev[1], c->stream);
+        cudaEventRecord(c->ev[2], c->stream);
+        if (do_keyswitch) {
+            mk2k::keyswitch2k_kernel<<<(unsigned)G, mk::KS_THREADS, 0, c->stream>>>(c->prm.n, c->prm.k, c->prm.t, c->prm.basebit, c->d_ksk, ext2, oa, ob);
+            c->launches++;
+        }
+        cudaEventRecord(c->ev[3], c->stream);
+        c->ev_valid = true;
+        c->stream = saved;
+        CU_TRY(c, cudaGetLastError());
+        return MKTFHE_OK;
+    }
     int32_t* ext = ext_out;
     if (!ext && !(do_keyswitch && c->fuse_ks && mk::ks_fusable(c->prm.n, c->prm.t))) {
         int rc = reserve(c, c->ext, G * (mk::N + 1) * sizeof(int32_t));
@@ -256,20 +301,26 @@ int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
     CREATE_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto& ev : c->ev) CREATE_TRY(cudaEventCreate(&ev));
     const int B1 = (1 << params->basebit) - 1;
-    c->bsk_bytes = (size_t)params->k * params->n * mk::bsk_elem_words(params->l) * sizeof(u32);
-    c->gpc = mk::gpc_for(params->l);
+    const bool big = params->N == mk2k::N;
+    c->bsk_bytes = (size_t)params->k * params->n * (big ? mk2k::bsk_elem_words() : mk::bsk_elem_words(params->l)) * sizeof(u32);
+    c->gpc = big ? 1 : mk::gpc_for(params->l);
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
     if (const char* e = getenv("MKTFHE_B200_LATENCY")) c->latency_kernel = atoi(e) != 0;
     if (const char* e = getenv("MKTFHE_B200_SPLIT_TAIL")) c->split_tail = atoi(e) != 0;
     if (const char* e = getenv("MKTFHE_B200_FUSE_KS")) c->fuse_ks = atoi(e) != 0;
     const size_t ks_stride = mk::ks_row_stride(params->n);   // rows padded to 16 bytes on the device
-    c->ksk_bytes = (size_t)params->k * mk::N * params->t * B1 * ks_stride * sizeof(int32_t);
+    c->ksk_bytes = (size_t)params->k * params->N * params->t * B1 * ks_stride * sizeof(int32_t);
     CREATE_TRY(cudaMalloc(&c->d_bsk, c->bsk_bytes));
     // the key-switching key is followed by one all-zero row (read by the fused key switch for zero digits)
     CREATE_TRY(cudaMalloc(&c->d_ksk, c->ksk_bytes + ks_stride * sizeof(int32_t)));
     CREATE_TRY(cudaMemset(c->d_ksk, 0, c->ksk_bytes + ks_stride * sizeof(int32_t)));
-    CREATE_TRY(cudaMalloc(&c->d_twB, (size_t)mk::TWB_WORDS * 4));
-    {
+    if (big) {
+        rns2k::HostTables T2;
+        CREATE_TRY(cudaMalloc(&c->d_twB, T2.twB.size() * sizeof(rns::uint2_)));
+        CREATE_TRY(cudaMemcpyToSymbol(mk2k::c_k2, &T2.c, sizeof(rns2k::Consts)));
+        CREATE_TRY(cudaMemcpy(c->d_twB, T2.twB.data(), T2.twB.size() * sizeof(rns::uint2_), cudaMemcpyHostToDevice));
+    } else {
+        CREATE_TRY(cudaMalloc(&c->d_twB, (size_t)mk::TWB_WORDS * 4));
         rns::HostTables T;
         CREATE_TRY(cudaMemcpyToSymbol(mk::c_rns, &T.c, sizeof(rns::Consts)));
         CREATE_TRY(cudaMemcpy(c->d_twB, T.twB.data(), (size_t)mk::TWB_WORDS * 4, cudaMemcpyHostToDevice));
@@ -302,13 +353,19 @@ int mktfhe_load_bsk(mktfhe_ctx* c, int party, const int64_t* polys) {
     if (party < 0 || party >= c->prm.k || !polys) return fail(c, MKTFHE_EINVAL, "load_bsk: bad party %d or NULL key", party);
     CU_TRY(c, cudaSetDevice(c->device));
     const int n = c->prm.n, l = c->prm.l;
-    const size_t raw_bytes = (size_t)n * 4 * l * mk::N * sizeof(int64_t);
+    const size_t raw_bytes = (size_t)n * 4 * l * c->prm.N * sizeof(int64_t);
     int rc = reserve(c, c->raw, raw_bytes);
     if (rc) return rc;
     CU_TRY(c, cudaMemcpyAsync(c->raw.p, polys, raw_bytes, cudaMemcpyHostToDevice, c->stream));
-    const int ntasks = n * 4 * l * rns::NP;
-    mk::bsk_transform_kernel<<<(ntasks + mk::XF_WARPS - 1) / mk::XF_WARPS, mk::XF_WARPS * 32, 0, c->stream>>>(
-        (const int64_t*)c->raw.p, c->d_bsk, n, l, party, c->d_twB, ntasks);
+    if (c->prm.N == mk2k::N) {
+        const int ntasks = n * 4 * rns2k::NP;
+        mk2k::bsk_transform2k_kernel<<<(ntasks + mk2k::XF_WARPS - 1) / mk2k::XF_WARPS, mk2k::XF_WARPS * 32, 0, c->stream>>>(
+            (const int64_t*)c->raw.p, c->d_bsk, n, party, c->d_twB, ntasks);
+    } else {
+        const int ntasks = n * 4 * l * rns::NP;
+        mk::bsk_transform_kernel<<<(ntasks + mk::XF_WARPS - 1) / mk::XF_WARPS, mk::XF_WARPS * 32, 0, c->stream>>>(
+            (const int64_t*)c->raw.p, c->d_bsk, n, l, party, c->d_twB, ntasks);
+    }
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     CU_TRY(c, cudaStreamSynchronize(c->stream));
@@ -476,7 +533,7 @@ int mktfhe_blind_rotate_batch(mktfhe_ctx* c, int64_t mu, size_t G, const int32_t
     if (!a_in || !b_in || !ext_out) return fail(c, MKTFHE_EINVAL, "blind_rotate_batch: NULL buffer");
     CU_TRY(c, cudaSetDevice(c->device));
     const size_t kn = (size_t)c->prm.n * c->prm.k, abytes = G * kn * 4, bbytes = G * 4;
-    const size_t ebytes = G * (mk::N + 1) * 4, accbytes = G * 2 * mk::N * 8;
+    const size_t ebytes = G * ((size_t)c->prm.N + 1) * 4, accbytes = G * 2 * (size_t)c->prm.N * 8;
     int rc;
     if ((rc = stage_in(c, c->in[0], a_in, abytes)) || (rc = stage_in(c, c->in[1], b_in, bbytes))) return rc;
     if ((rc = reserve(c, c->ext, ebytes))) return rc;
@@ -496,11 +553,15 @@ int mktfhe_keyswitch_batch(mktfhe_ctx* c, size_t G, const int32_t* ext, int32_t*
     if (G == 0) return MKTFHE_OK;
     if (!ext || !a_out || !b_out) return fail(c, MKTFHE_EINVAL, "keyswitch_batch: NULL buffer");
     CU_TRY(c, cudaSetDevice(c->device));
-    const size_t kn = (size_t)c->prm.n * c->prm.k, abytes = G * kn * 4, bbytes = G * 4, ebytes = G * (mk::N + 1) * 4;
+    const size_t kn = (size_t)c->prm.n * c->prm.k, abytes = G * kn * 4, bbytes = G * 4, ebytes = G * ((size_t)c->prm.N + 1) * 4;
     int rc;
     if ((rc = stage_in(c, c->ext, ext, ebytes)) || (rc = reserve(c, c->oa, abytes)) || (rc = reserve(c, c->ob, bbytes))) return rc;
-    mk::keyswitch_kernel<<<(unsigned)G, mk::KS_THREADS, 0, c->stream>>>(c->prm.n, c->prm.k, c->prm.t, c->prm.basebit, c->d_ksk,
-                                                                        (const int32_t*)c->ext.p, (int32_t*)c->oa.p, (int32_t*)c->ob.p);
+    if (c->prm.N == mk2k::N)
+        mk2k::keyswitch2k_kernel<<<(unsigned)G, mk::KS_THREADS, 0, c->stream>>>(c->prm.n, c->prm.k, c->prm.t, c->prm.basebit, c->d_ksk,
+                                                                              (const int32_t*)c->ext.p, (int32_t*)c->oa.p, (int32_t*)c->ob.p);
+    else
+        mk::keyswitch_kernel<<<(unsigned)G, mk::KS_THREADS, 0, c->stream>>>(c->prm.n, c->prm.k, c->prm.t, c->prm.basebit, c->d_ksk,
+                                                                            (const int32_t*)c->ext.p, (int32_t*)c->oa.p, (int32_t*)c->ob.p);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     CU_TRY(c, cudaMemcpyAsync(a_out, c->oa.p, abytes, cudaMemcpyDeviceToHost, c->stream));
@@ -514,6 +575,7 @@ int mktfhe_extprod_batch(mktfhe_ctx* c, size_t G, const int32_t* elem, const int
     if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
     if (G == 0) return MKTFHE_OK;
     if (!elem || !acc_in || !acc_out) return fail(c, MKTFHE_EINVAL, "extprod_batch: NULL buffer");
+    if (c->prm.N == mk2k::N) return fail(c, MKTFHE_EINVAL, "extprod_batch: the single-external-product hook exists for N=1024 only");
     for (size_t g = 0; g < G; g++)
         if (elem[g] < 0 || elem[g] >= c->prm.n * c->prm.k) return fail(c, MKTFHE_EINVAL, "extprod_batch: elem[%zu]=%d out of range", g, elem[g]);
     CU_TRY(c, cudaSetDevice(c->device));
@@ -539,11 +601,15 @@ int mktfhe_negacyclic_mul_batch(mktfhe_ctx* c, size_t G, const int64_t* a, const
     if (G == 0) return MKTFHE_OK;
     if (!a || !b || !out) return fail(c, MKTFHE_EINVAL, "negacyclic_mul_batch: NULL buffer");
     CU_TRY(c, cudaSetDevice(c->device));
-    const size_t bytes = G * mk::N * 8;
+    const size_t bytes = G * (size_t)c->prm.N * 8;
     int rc;
     if ((rc = stage_in(c, c->accin, a, bytes)) || (rc = stage_in(c, c->raw, b, bytes)) || (rc = reserve(c, c->accout, bytes))) return rc;
-    mk::negacyclic_mul_kernel<<<(unsigned)G, mk::NM_THREADS, 0, c->stream>>>((const int64_t*)c->accin.p, (const int64_t*)c->raw.p, (int64_t*)c->accout.p,
-                                                                      c->d_twB);
+    if (c->prm.N == mk2k::N)
+        mk2k::negacyclic_mul2k_kernel<<<(unsigned)G, 32 * mk2k::NP, 0, c->stream>>>((const int64_t*)c->accin.p, (const int64_t*)c->raw.p,
+                                                                                 (int64_t*)c->accout.p, c->d_twB);
+    else
+        mk::negacyclic_mul_kernel<<<(unsigned)G, mk::NM_THREADS, 0, c->stream>>>((const int64_t*)c->accin.p, (const int64_t*)c->raw.p,
+                                                                          (int64_t*)c->accout.p, c->d_twB);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     CU_TRY(c, cudaMemcpyAsync(out, c->accout.p, bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -571,7 +637,7 @@ int mktfhe_algorithmic_bytes(const mktfhe_ctx* c, double* bsk_bytes_per_gate, do
     const mktfhe_params& p = c->prm;
     const double B = (double)(1 << p.basebit);
     if (bsk_bytes_per_gate) *bsk_bytes_per_gate = (double)c->bsk_bytes;
-    if (ksk_bytes_per_gate) *ksk_bytes_per_gate = (double)p.k * mk::N * p.t * (1.0 - 1.0 / B) * (p.n + 1) * 4.0;
+    if (ksk_bytes_per_gate) *ksk_bytes_per_gate = (double)p.k * p.N * p.t * (1.0 - 1.0 / B) * (p.n + 1) * 4.0;
     return MKTFHE_OK;
 }
 

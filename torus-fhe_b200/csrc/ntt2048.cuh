@@ -1,6 +1,6 @@
-// ntt2048.cuh -- arithmetic core for the N = 2048 parameter sets (mktfhe_parameters_{16..256}party_3gen, mk_api.jl:214-310):
-// GROUNDWORK, not yet wired into a kernel.  Verified on the CPU by tests/host_emu/ntt2048_emu.cpp, which runs
-// these very functions for 32 emulated lanes against the O(N^2) definition and an exact schoolbook product.
+// ntt2048.cuh -- arithmetic core of the N = 2048 parameter sets (mktfhe_parameters_{16..128}party_3gen, mk_api.jl:214-298), used by
+// kernels2k.cuh.  Verified on the CPU by tests/host_emu/ntt2048_emu.cpp, which runs these very functions for 32 emulated lanes
+// against the O(N^2) definition and an exact schoolbook product.
 //
 // What changes against the N = 1024 path (rns.cuh / ntt_rns.cuh):
 //   * gadget digits are up to 26 bits (l = 1, Bg = 2^26 at 16 / 32 parties), so the exact integer result of an external product
