@@ -163,7 +163,7 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "NONE"        # NCCL prints its version banner on stdout at VERSION/WARN: keep stdout to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     params = {2: T.mktfhe_parameters_2party_3gen, 3: T.mktfhe_parameters_3party_3gen, 4: T.mktfhe_parameters_4party_3gen,
-              5: T.mktfhe_parameters_5party_3gen, 8: T.mktfhe_parameters_8party_3gen}[args.parties]
+              5: T.mktfhe_parameters_5party_3gen, 8: T.mktfhe_parameters_8party_3gen, 16: T.mktfhe_parameters_16party_3gen}[args.parties]
     G, k, n = args.gates, params.max_parties, params.lwe_size
     eng = T.Engine(params, device=local)
     rng = np.random.default_rng(KEY_SEED)
@@ -283,10 +283,11 @@ def run_ours(args):
                                  "68 MB algorithmic; scaled here to this launch's gate count"}
         traffic = ncu_traffic["bytes_in_captured_launch"] * G / ncu_traffic["gates_in_captured_launch"]
         value = world * G * args.steps / (ms * 1e-3)
+        big = N != 1024            # N = 2048 sets: first functional kernels, no slot model / ncu capture yet
         line = {"metric": METRIC.replace("2-party", f"{k}-party"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "ms_per_bootstrap_amortized": ms / args.steps / G,
                 "ms_single_bootstrap_latency": lat_ms, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u32 RNS (three 28-bit-prime NTTs + CRT, exact mod 2^64) / int32 LWE", "data": "synthetic",
+                "vs_baseline": None, "dtype": ("u32 RNS (four 28-bit-prime NTTs + CRT, exact mod 2^64) / int32 LWE" if N != 1024 else "u32 RNS (three 28-bit-prime NTTs + CRT, exact mod 2^64) / int32 LWE"), "data": "synthetic",
                 "config": {"workload": f"{k}-party NAND x{G} per GPU (mktfhe_parameters_{k}party_3gen: n={n} N={N} l={l} Bg=2^{params.gsw_log2_base} "
                                        f"t={params.ks_decomp_length} Bks=2^{params.ks_log2_base})",
                            "gates_per_step_per_gpu": G, "parallelism": f"gate-sharded replicas x{world}",
@@ -297,7 +298,7 @@ def run_ours(args):
                         "d2h_bytes_per_step": int((G * k * n + G) * 4)},
                 "gpu_launches": int(launches),
                 "roofline": {"kernel": "blind_rotate_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": achieved / hbm_peak, "traffic": traffic, "traffic_note": ncu_traffic, "peak_source": peak_src,
+                             "frac": achieved / hbm_peak, "traffic": None if big else traffic, "traffic_note": None if big else ncu_traffic, "peak_source": peak_src,
                              "note": "contract roofline (HBM); the kernel is IMAD-pipe bound and streams the key from L2 (hit rate 98 %): see integer_bound",
                              "algorithmic_bytes_per_gate": per_gate, "algorithmic_bytes_breakdown": {"bsk": bsk_1limb, "ksk_rows_gathered": ksk_gather if fused_ks else 0,
                                                                                                        "ciphertext_io": ct_io},
@@ -307,7 +308,7 @@ def run_ours(args):
                              "kernel_ms": br_ms, "keyswitch_ms": ks_ms, "keyswitch_gather_GBps": (G * ksk_gather / (ks_ms * 1e-3) / 1e9) if ks_ms > 0.05 else None,
                              "keyswitch_fused_into_blind_rotate": ks_ms <= 0.05,
                              "kernel_share_of_step": br_ms / (ms / args.steps),
-                             "integer_bound": {"bound": "imad_pipe", "algorithmic_slots_per_gate": imad_slots,
+                             "integer_bound": None if big else {"bound": "imad_pipe", "algorithmic_slots_per_gate": imad_slots,
                                                "achieved": G * imad_slots / (br_ms * 1e-3) / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-slots/s",
                                                "frac": G * imad_slots / (br_ms * 1e-3) / imad_peak,
                                                "ncu_fmaheavy_pipe_busy": 0.66, "ncu_issue_active": 0.57,
@@ -455,7 +456,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--gates", type=int, default=16384, help="gates per step per GPU")
-    ap.add_argument("--parties", type=int, default=2, choices=[2, 3, 4, 5, 8], help="parameter set (BASELINE configs[2]: 4 and 8)")
+    ap.add_argument("--parties", type=int, default=2, choices=[2, 3, 4, 5, 8, 16],
+                    help="parameter set (BASELINE configs[2]: 4 and 8; 16 = the first N = 2048 set, one gate per SM: use --gates 148 or a multiple)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="nand", choices=["nand", "adder", "conv"],
