@@ -315,9 +315,10 @@ def test_synthetic_parameter_sets_bit_exact(oracle, prm):
 @pytest.mark.parametrize("prm", [
     dict(n=6, N=2048, k=2, l=1, bgbit=26, t=4, basebit=3),     # shape of mktfhe_parameters_16party_3gen / 32party (mk_api.jl:214-252)
     dict(n=5, N=2048, k=3, l=1, bgbit=24, t=5, basebit=3),     # shape of mktfhe_parameters_128party_3gen (:292-298), odd party count
-], ids=["bg26_t4", "bg24_t5"])
+    dict(n=4, N=2048, k=2, l=2, bgbit=18, t=8, basebit=2),     # shape of mktfhe_parameters_256party_3gen (:304-310): two gadget levels
+], ids=["bg26_t4", "bg24_t5", "l2_bg18_t8"])
 def test_n2048_parameter_sets_bit_exact(oracle, prm):
-    """The N = 2048, l = 1 path (kernels2k.cuh: four primes, 26-bit gadget digits): accumulator, extracted sample and key-switched
+    """The N = 2048 path (kernels2k.cuh: four primes, up to 26-bit gadget digits, l = 1 or 2): accumulator, extracted sample and key-switched
     bootstrap bit-exact against the oracle's exact schoolbook back-end, gates decrypt to the truth table, and the exact product hook
     at degree 2048.  Reduced LWE dimension so that the O(N^2) oracle finishes in seconds."""
     import torus_fhe_b200 as T

@@ -1,5 +1,6 @@
-// kernels2k.cuh -- the bootstrapped-gate path for the N = 2048, l = 1 parameter sets (mktfhe_parameters_{16,32,64,128}party_3gen,
-// mk_api.jl:214-298): gadget digits of up to 27 bits, four 28-bit primes (ntt2048.cuh), one gate per CTA.
+// kernels2k.cuh -- the bootstrapped-gate path for the N = 2048 parameter sets (mktfhe_parameters_{16,32,64,128}party_3gen with l = 1,
+// mktfhe_parameters_256party_3gen with l = 2; mk_api.jl:214-310): gadget digits of up to 27 bits, four 28-bit primes (ntt2048.cuh),
+// one gate per CTA.
 //
 // First, functional version of this path: same step structure as kernels.cuh (decompose -> forward transforms -> multiply-accumulate
 // -> inverse transforms -> CRT), eight warps per gate = (prime, polynomial), the accumulator resident in shared memory for all k*n
@@ -20,11 +21,12 @@ constexpr int TILE_WORDS = rns2k::TILE_WORDS, TILE_STRIDE = rns2k::TILE_STRIDE;
 
 __constant__ rns2k::Consts c_k2;
 
-// BSK layout (u32): [elem = party*n + j][prime][src][out][2048 key slots]; (out, src) <-> reference parts as in kernels.cuh.
+// BSK layout (u32): [elem = party*n + j][prime][s = src*l + q][out][2048 key slots]; (out, src) <-> reference parts as in kernels.cuh.
 // key slot of transformed position 32 (lane + 32 h) + c: a warp-wide 128-bit load is one contiguous 512-byte segment
-__host__ __device__ inline size_t bsk_elem_words() { return (size_t)NP * 2 * 2 * N; }
+// BSK rows per (element, prime): s = src * l + q (digit polynomial) x out
+__host__ __device__ inline size_t bsk_elem_words(int l) { return (size_t)NP * 2 * l * 2 * N; }
 __host__ __device__ inline int key_slot(int lane, int h, int c) { return ((h * 8 + (c >> 2)) * 32 + lane) * 4 + (c & 3); }
-__host__ __device__ constexpr size_t smem_bytes() { return (size_t)2 * N * 8 + (size_t)2 * N * 4 + (size_t)WARPS * TILE_WORDS * 4; }
+__host__ __device__ constexpr size_t smem_bytes(int l) { return (size_t)2 * N * 8 + (size_t)2 * l * N * 4 + (size_t)WARPS * TILE_WORDS * 4; }
 
 struct Args {
     int G, n, k, bgbit;
@@ -70,14 +72,16 @@ __device__ __forceinline__ void warp_inv(u32 (&y)[2][32], u32 (&x)[64], u32* til
     rns2k::inv_passA64(x, c_k2.twA[pi][1], p);
 }
 
-// one gate per CTA; acc[0] = mask, acc[1] = body
+// one gate per CTA; acc[0] = mask, acc[1] = body.  Warp (prime w, o): transforms the digit polynomials 2i + o, i < L, one after the
+// other, and accumulates output polynomial o over all 2L of them (its own from registers, the partner's from the partner's tile)
+template <int L>
 __global__ void __launch_bounds__(THREADS, 1) blind_rotate2k_kernel(Args p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* acc = reinterpret_cast<u64*>(smem_raw);
-    int32_t* dig = reinterpret_cast<int32_t*>(smem_raw + (size_t)2 * N * 8);           // [src][N] signed digits; src 0 = body, 1 = mask
-    u32* tiles = reinterpret_cast<u32*>(smem_raw + (size_t)2 * N * 8 + (size_t)2 * N * 4);
+    int32_t* dig = reinterpret_cast<int32_t*>(smem_raw + (size_t)2 * N * 8);           // [s = src*L + q][N] signed digits; src 0 = body, 1 = mask
+    u32* tiles = reinterpret_cast<u32*>(smem_raw + (size_t)2 * N * 8 + (size_t)2 * L * N * 4);
     const int tid = threadIdx.x, gw = tid >> 5, lane = tid & 31;
-    const int w = gw >> 1, s = gw & 1;                     // prime; digit polynomial transformed = output polynomial accumulated
+    const int w = gw >> 1, o = gw & 1;                     // prime; output polynomial accumulated = parity of the digit polynomials transformed
     const int g = blockIdx.x;
     const u32 pr = c_k2.p[w], pinv = c_k2.pinv_neg[w];
     u32* tile = tiles + gw * TILE_WORDS;
@@ -100,7 +104,9 @@ __global__ void __launch_bounds__(THREADS, 1) blind_rotate2k_kernel(Args p) {
         }
     }
     __syncthreads();
-    const u64 off = ((u64)1 << (64 - p.bgbit)) << (p.bgbit - 1);          // tgsw.jl:24-30 with l = 1
+    u64 off = 0;
+#pragma unroll
+    for (int q = 1; q <= L; q++) off += ((u64)1 << (64 - q * p.bgbit)) << (p.bgbit - 1);   // tgsw.jl:24-30
     const u64 dmask = ((u64)1 << p.bgbit) - 1;
     const int64_t half = (int64_t)1 << (p.bgbit - 1);
     const size_t abase = (size_t)g * kn;
@@ -115,35 +121,51 @@ __global__ void __launch_bounds__(THREADS, 1) blind_rotate2k_kernel(Args p) {
             u64 v = poly[idx & (N - 1)];
             if (idx & N) v = 0 - v;
             const u64 t = v - poly[ii] + off;
-            dig[(1 - c) * N + ii] = (int32_t)((int64_t)((t >> (64 - p.bgbit)) & dmask) - half);
+#pragma unroll
+            for (int q = 0; q < L; q++) dig[((1 - c) * L + q) * N + ii] = (int32_t)((int64_t)((t >> (64 - (q + 1) * p.bgbit)) & dmask) - half);
         }
         __syncthreads();
-        // ---- forward transform of digit polynomial s under prime w; exchange with the partner (w, 1 - s)
-        u32 x[64], y[2][32];
+        // ---- forward transforms of the digit polynomials 2i + o under prime w; exchange with the partner (w, 1 - o); multiply-accumulate
+        u32 x[64], y[2][32], accv[2][32];
+        const u32* kw = p.bsk + (size_t)it * bsk_elem_words(L) + (size_t)w * (2 * L * 2 * N);
+#pragma unroll 1
+        for (int i = 0; i < L; i++) {
+            const int s_own = 2 * i + o, s_for = 2 * i + 1 - o;
 #pragma unroll
-        for (int r = 0; r < 64; r++) x[r] = (u32)(dig[s * N + 32 * r + lane] + (int32_t)pr);      // signed digit + p in [0, 2p)
-        warp_fwd(x, y, tile, p.twB, w, pr, lane);
+            for (int r = 0; r < 64; r++) x[r] = (u32)(dig[s_own * N + 32 * r + lane] + (int32_t)pr);      // signed digit + p in [0, 2p)
+            warp_fwd(x, y, tile, p.twB, w, pr, lane);
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+                for (int c = 0; c < 32; c++) tile[(h * 32 + c) * 32 + lane] = y[h][c];
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + w) : "memory");
+            // both digit polynomials of the pair times their key rows of output o, one Montgomery reduction per point
+            const uint4* k_own = reinterpret_cast<const uint4*>(kw + (size_t)(s_own * 2 + o) * N) + lane;
+            const uint4* k_for = reinterpret_cast<const uint4*>(kw + (size_t)(s_for * 2 + o) * N) + lane;
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+                for (int q4 = 0; q4 < 8; q4++) {
+                    const uint4 ka = __ldg(k_own + (h * 8 + q4) * 32), kb = __ldg(k_for + (h * 8 + q4) * 32);
+                    const u32* pt = ptile + (h * 32 + 4 * q4) * 32 + lane;
+                    const u32 v0 = rns::mont_mul2(y[h][4 * q4 + 0], ka.x, pt[0], kb.x, pr, pinv);       // < 2.75p
+                    const u32 v1 = rns::mont_mul2(y[h][4 * q4 + 1], ka.y, pt[32], kb.y, pr, pinv);
+                    const u32 v2 = rns::mont_mul2(y[h][4 * q4 + 2], ka.z, pt[64], kb.z, pr, pinv);
+                    const u32 v3 = rns::mont_mul2(y[h][4 * q4 + 3], ka.w, pt[96], kb.w, pr, pinv);
+                    accv[h][4 * q4 + 0] = i == 0 ? v0 : accv[h][4 * q4 + 0] + v0;
+                    accv[h][4 * q4 + 1] = i == 0 ? v1 : accv[h][4 * q4 + 1] + v1;
+                    accv[h][4 * q4 + 2] = i == 0 ? v2 : accv[h][4 * q4 + 2] + v2;
+                    accv[h][4 * q4 + 3] = i == 0 ? v3 : accv[h][4 * q4 + 3] + v3;
+                }
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + w) : "memory");          // the partner is done with this warp's tile
+        }
 #pragma unroll
         for (int h = 0; h < 2; h++)
 #pragma unroll
-            for (int c = 0; c < 32; c++) tile[(h * 32 + c) * 32 + lane] = y[h][c];
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + w) : "memory");
-        // ---- output polynomial o = s: both digit polynomials times their key rows, one Montgomery reduction per point
-        const u32* kw = p.bsk + (size_t)it * bsk_elem_words() + (size_t)w * (2 * 2 * N);
-        const uint4* k_own = reinterpret_cast<const uint4*>(kw + (size_t)(s * 2 + s) * N) + lane;
-        const uint4* k_for = reinterpret_cast<const uint4*>(kw + (size_t)((1 - s) * 2 + s) * N) + lane;
-#pragma unroll
-        for (int h = 0; h < 2; h++)
-#pragma unroll
-            for (int q4 = 0; q4 < 8; q4++) {
-                const uint4 ka = __ldg(k_own + (h * 8 + q4) * 32), kb = __ldg(k_for + (h * 8 + q4) * 32);
-                const u32* pt = ptile + (h * 32 + 4 * q4) * 32 + lane;
-                y[h][4 * q4 + 0] = rns::mont_mul2(y[h][4 * q4 + 0], ka.x, pt[0], kb.x, pr, pinv);       // < 2.75p
-                y[h][4 * q4 + 1] = rns::mont_mul2(y[h][4 * q4 + 1], ka.y, pt[32], kb.y, pr, pinv);
-                y[h][4 * q4 + 2] = rns::mont_mul2(y[h][4 * q4 + 2], ka.z, pt[64], kb.z, pr, pinv);
-                y[h][4 * q4 + 3] = rns::mont_mul2(y[h][4 * q4 + 3], ka.w, pt[96], kb.w, pr, pinv);
+            for (int c = 0; c < 32; c++) {
+                const u32 v = accv[h][c];                                      // < 2.75 L p
+                y[h][c] = L > 1 ? rns::umin32(v, v - 4 * pr) : v;              // [0, 4p)
             }
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + w) : "memory");              // the partner is done with this warp's tile
         // ---- inverse transform, residues to the tile in coefficient order, CRT by the whole gate
         warp_inv(y, x, tile, p.twB, w, pr, lane);
 #pragma unroll
@@ -170,16 +192,16 @@ __global__ void __launch_bounds__(THREADS, 1) blind_rotate2k_kernel(Args p) {
     if (tid == 0) ext[N] = mk::t64tot32((int64_t)acc[N]);
 }
 
-// One warp per (polynomial, prime): raw int64 key of one party, [n][4 parts][N] (l = 1) -> transformed residues in the streaming layout
+// One warp per (polynomial, prime): raw int64 key of one party, [n][4 parts][l][N] -> transformed residues in the streaming layout
 constexpr int XF_WARPS = 2;
-__global__ void __launch_bounds__(XF_WARPS * 32) bsk_transform2k_kernel(const int64_t* __restrict__ raw, u32* __restrict__ bsk, int n, int party,
+__global__ void __launch_bounds__(XF_WARPS * 32) bsk_transform2k_kernel(const int64_t* __restrict__ raw, u32* __restrict__ bsk, int n, int l, int party,
                                                                          const uint2_* __restrict__ twB, int ntasks) {
     __shared__ u32 tiles[XF_WARPS * TILE_WORDS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int task = blockIdx.x * XF_WARPS + warp;
     if (task >= ntasks) return;
     const int pi = task % NP, pq = task / NP;
-    const int part = pq & 3, j = pq >> 2;
+    const int q = pq % l, part = (pq / l) & 3, j = pq / (4 * l);
     const int out = part < 2 ? 1 : 0;                       // part_1: body<-body, part_2: body<-mask, part_3: mask<-mask, part_4: mask<-body
     const int src = (part == 0 || part == 3) ? 0 : 1;
     const u32 p = c_k2.p[pi];
@@ -188,7 +210,7 @@ __global__ void __launch_bounds__(XF_WARPS * 32) bsk_transform2k_kernel(const in
 #pragma unroll
     for (int r = 0; r < 64; r++) x[r] = rns::residue_i64(poly[32 * r + lane], p);
     warp_fwd(x, y, tiles + warp * TILE_WORDS, twB, pi, p, lane);
-    u32* dst = bsk + ((size_t)party * n + j) * bsk_elem_words() + ((size_t)(pi * 2 + src) * 2 + out) * N;
+    u32* dst = bsk + ((size_t)party * n + j) * bsk_elem_words(l) + ((size_t)(pi * 2 * l + (src * l + q)) * 2 + out) * N;
 #pragma unroll
     for (int h = 0; h < 2; h++)
 #pragma unroll

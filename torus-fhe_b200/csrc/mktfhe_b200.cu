@@ -86,8 +86,8 @@ int reserve(mktfhe_ctx* c, DevBuf& b, size_t bytes) {
 int check_params(const mktfhe_params* p) {
     if (!p) return fail(nullptr, MKTFHE_EINVAL, "params is NULL");
     if (p->N == mk2k::N) {
-        // N = 2048 sets (mk_api.jl:214-298): l = 1 with a wide gadget base, four-prime exact product (kernels2k.cuh)
-        if (p->l != 1) return fail(nullptr, MKTFHE_EINVAL, "N=2048 is supported with gsw_decomp_length l=1 only (got %d)", p->l);
+        // N = 2048 sets (mk_api.jl:214-310): l = 1 or 2 with a wide gadget base, four-prime exact product (kernels2k.cuh)
+        if (p->l < 1 || p->l > 2) return fail(nullptr, MKTFHE_EINVAL, "N=2048 is supported with gsw_decomp_length l=1 or 2 (got %d)", p->l);
         if (p->bgbit < 1 || p->bgbit > 27) return fail(nullptr, MKTFHE_EINVAL, "N=2048: unsupported gsw_log2_base=%d (1..27)", p->bgbit);
         if (std::log2((double)(2 * p->l) * p->N) + (p->bgbit - 1) + 63.0 >= rns2k::log2_crt_bound())
             return fail(nullptr, MKTFHE_EINVAL, "2l*N*Bg/2*2^63 exceeds the CRT range of the four-prime exact product");
@@ -126,7 +126,8 @@ size_t br_smem_bytes(const mktfhe_ctx* c) { return mk::cta_smem_bytes(c->prm.l) 
 
 int set_attrs(mktfhe_ctx* c) {
     if (c->prm.N == mk2k::N) {
-        CU_TRY(c, cudaFuncSetAttribute(mk2k::blind_rotate2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk2k::smem_bytes()));
+        if (c->prm.l == 1) CU_TRY(c, cudaFuncSetAttribute(mk2k::blind_rotate2k_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk2k::smem_bytes(1)));
+        else CU_TRY(c, cudaFuncSetAttribute(mk2k::blind_rotate2k_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk2k::smem_bytes(2)));
         return MKTFHE_OK;
     }
     const int sm = (int)br_smem_bytes(c);
@@ -220,7 +221,8 @@ int run_bootstrap_dev(mktfhe_ctx* c, mk::GateLinear lin, int64_t mu, size_t G, c
         a.xa = xa; a.xb = xb; a.ya = ya; a.yb = yb; a.za = za; a.zb = zb;
         a.lin = lin; a.gate_ids = gate_ids; a.mu = mu; a.ext_out = ext2; a.acc_out = acc_out;
         cudaEventRecord(c->ev[0], c->stream);
-        mk2k::blind_rotate2k_kernel<<<(unsigned)G, mk2k::THREADS, mk2k::smem_bytes(), c->stream>>>(a);
+        if (c->prm.l == 1) mk2k::blind_rotate2k_kernel<1><<<(unsigned)G, mk2k::THREADS, mk2k::smem_bytes(1), c->stream>>>(a);
+        else mk2k::blind_rotate2k_kernel<2><<<(unsigned)G, mk2k::THREADS, mk2k::smem_bytes(2), c->stream>>>(a);
         c->launches++;
         cudaEventRecord(c->ev[1], c->stream);
         cudaEventRecord(c->ev[2], c->stream);
@@ -302,7 +304,7 @@ int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
     for (auto& ev : c->ev) CREATE_TRY(cudaEventCreate(&ev));
     const int B1 = (1 << params->basebit) - 1;
     const bool big = params->N == mk2k::N;
-    c->bsk_bytes = (size_t)params->k * params->n * (big ? mk2k::bsk_elem_words() : mk::bsk_elem_words(params->l)) * sizeof(u32);
+    c->bsk_bytes = (size_t)params->k * params->n * (big ? mk2k::bsk_elem_words(params->l) : mk::bsk_elem_words(params->l)) * sizeof(u32);
     c->gpc = big ? 1 : mk::gpc_for(params->l);
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
     if (const char* e = getenv("MKTFHE_B200_LATENCY")) c->latency_kernel = atoi(e) != 0;
@@ -358,9 +360,9 @@ int mktfhe_load_bsk(mktfhe_ctx* c, int party, const int64_t* polys) {
     if (rc) return rc;
     CU_TRY(c, cudaMemcpyAsync(c->raw.p, polys, raw_bytes, cudaMemcpyHostToDevice, c->stream));
     if (c->prm.N == mk2k::N) {
-        const int ntasks = n * 4 * rns2k::NP;
+        const int ntasks = n * 4 * l * rns2k::NP;
         mk2k::bsk_transform2k_kernel<<<(ntasks + mk2k::XF_WARPS - 1) / mk2k::XF_WARPS, mk2k::XF_WARPS * 32, 0, c->stream>>>(
-            (const int64_t*)c->raw.p, c->d_bsk, n, party, c->d_twB, ntasks);
+            (const int64_t*)c->raw.p, c->d_bsk, n, l, party, c->d_twB, ntasks);
     } else {
         const int ntasks = n * 4 * l * rns::NP;
         mk::bsk_transform_kernel<<<(ntasks + mk::XF_WARPS - 1) / mk::XF_WARPS, mk::XF_WARPS * 32, 0, c->stream>>>(

@@ -175,9 +175,9 @@ mktfhe_parameters_3party_3gen = SchemeParameters_3gen(510, 2 ** -13.26, 1024, 1,
 mktfhe_parameters_4party_3gen = SchemeParameters_3gen(510, 2 ** -13.26, 1024, 1, False, 3, 6, 2 ** -30.70, 5, 2, 2 ** -13.26, 4)
 mktfhe_parameters_5party_3gen = SchemeParameters_3gen(520, 2 ** -13.52, 1024, 1, False, 3, 6, 2 ** -30.70, 5, 2, 2 ** -13.52, 5)
 mktfhe_parameters_8party_3gen = SchemeParameters_3gen(540, 2 ** -14.04, 1024, 1, False, 4, 4, 2 ** -30.70, 5, 2, 2 ** -14.04, 8)
-# 16 parties and up use N = 2048 and a 24..26-bit gadget base with l = 1 (mk_api.jl:214-298): served by the four-prime N = 2048
-# kernels (csrc/kernels2k.cuh).  The 256-party (l = 2) and 512-party (N = 4096) sets are defined for API completeness and rejected
-# by mktfhe_create (MKTFHE_EINVAL).
+# 16 parties and up use N = 2048 and an 18..26-bit gadget base with l = 1 or 2 (mk_api.jl:214-310): served by the four-prime N = 2048
+# kernels (csrc/kernels2k.cuh).  The 512-party set (N = 4096) is defined for API completeness and rejected by mktfhe_create
+# (MKTFHE_EINVAL).
 mktfhe_parameters_16party_3gen = SchemeParameters_3gen(590, 2 ** -15.34, 2048, 1, False, 1, 26, 2 ** -62.00, 4, 3, 2 ** -15.34, 16)
 mktfhe_parameters_32party_3gen = SchemeParameters_3gen(620, 2 ** -16.12, 2048, 1, False, 1, 26, 2 ** -62.00, 4, 3, 2 ** -16.12, 32)      # :246-252
 mktfhe_parameters_64party_3gen = SchemeParameters_3gen(650, 2 ** -16.90, 2048, 1, False, 1, 25, 2 ** -62.00, 4, 3, 2 ** -16.90, 64)      # :268-274
