@@ -36,9 +36,16 @@ struct Args {
     mk::GateLinear lin;
     const int32_t* gate_ids;
     int64_t mu;
-    int32_t* ext_out;   // [G][N+1]
+    int32_t* ext_out;   // [G][N+1], or nullptr when the key switch is fused and nobody asked for the extracted samples
     int64_t* acc_out;   // [G][2][N] or nullptr
+    // fused key switch (epilogue of the same kernel): ksk [k][N][t][B-1][ks_row_stride(n)] followed by one all-zero row
+    const int32_t* ksk; // nullptr: no key switch in this launch
+    int ks_t, ks_basebit;
+    int32_t *oa, *ob;   // [G][k][n], [G]
 };
+
+// the fused epilogue covers the key-switch shapes of the N = 2048 sets (t = 4, 5, 8) when a row fits the CTA four columns per thread
+__host__ __device__ constexpr bool ks_fusable(int n, int t) { return mk::ks_row_stride(n) <= 4 * THREADS && (t == 4 || t == 5 || t == 8); }
 
 // decode_message(x, 2N) for N = 2048: (x + 2^19) >> 20
 __device__ __forceinline__ int mod_switch_2N(int32_t x) { return (int32_t)((uint32_t)x + (1u << 19)) >> 20; }
@@ -70,6 +77,55 @@ __device__ __forceinline__ void warp_inv(u32 (&y)[2][32], u32 (&x)[64], u32* til
     for (int r = 0; r < 64; r++) x[r] = tile[r * TILE_STRIDE + lane];
     __syncwarp();
     rns2k::inv_passA64(x, c_k2.twA[pi][1], p);
+}
+
+// Sample extraction + multi-key key switch of the gate by its CTA (rlwe.jl:70-74, mk_internals.jl:730-744, keyswitch.jl:45-80), same
+// scheme as mk::fused_keyswitch: thread c owns the four output columns 4c .. 4c+3 (one LDG.128 per row), zero digits read the all-zero
+// row so that the row reads of four consecutive coefficients are in flight together.
+template <int T>
+__device__ __forceinline__ void fused_keyswitch2k(const u64* __restrict__ acc, u32* __restrict__ s_a, const Args& p, int g, int tid) {
+    const int n = p.n, stride = mk::ks_row_stride(n), bb = p.ks_basebit, B1 = (1 << bb) - 1;
+    const uint32_t prec_offset = 1u << (32 - (1 + bb * T));   // keyswitch.jl:58
+    for (int i = tid; i < N; i += THREADS) {
+        const u64 v = i == 0 ? acc[0] : (u64)0 - acc[N - i];
+        const int32_t ai = mk::t64tot32((int64_t)v);
+        if (p.ext_out) p.ext_out[(size_t)g * (N + 1) + i] = ai;
+        s_a[i] = (uint32_t)ai + prec_offset;
+    }
+    const int32_t eb = mk::t64tot32((int64_t)acc[N]);
+    if (p.ext_out && tid == 0) p.ext_out[(size_t)g * (N + 1) + N] = eb;
+    __syncthreads();
+    const int col0 = 4 * tid;
+    if (col0 >= stride) return;                               // no barrier below
+    const size_t party_words = (size_t)N * T * B1 * stride;
+    const uint4* zero_row = reinterpret_cast<const uint4*>(p.ksk + (size_t)p.k * party_words) + tid;
+    uint32_t bsum = 0;
+    for (int party = 0; party < p.k; party++) {
+        uint4 out = make_uint4(0, 0, 0, 0);
+        const int32_t* rows = p.ksk + (size_t)party * party_words;
+#pragma unroll 1
+        for (int i = 0; i < N; i += 4) {
+#pragma unroll
+            for (int ii = 0; ii < 4; ii++) {
+                const uint32_t ai = s_a[i + ii];
+#pragma unroll
+                for (int j = 1; j <= T; j++) {
+                    const uint32_t d = (ai >> (32 - j * bb)) & (uint32_t)B1;
+                    const uint4* r = d ? reinterpret_cast<const uint4*>(rows + (((size_t)(i + ii) * T + (j - 1)) * B1 + (d - 1)) * stride) + tid : zero_row;
+                    const uint4 v = __ldg(r);
+                    out.x -= v.x; out.y -= v.y; out.z -= v.z; out.w -= v.w;
+                }
+            }
+        }
+        const uint32_t o4[4] = {out.x, out.y, out.z, out.w};
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int col = col0 + c;
+            if (col < n) p.oa[((size_t)g * p.k + party) * n + col] = (int32_t)o4[c];
+            if (col == n) bsum += o4[c];
+        }
+    }
+    if (col0 <= n && n < col0 + 4) p.ob[g] = (int32_t)((uint32_t)eb + bsum);
 }
 
 // one gate per CTA; acc[0] = mask, acc[1] = body.  Warp (prime w, o): transforms the digit polynomials 2i + o, i < L, one after the
@@ -182,6 +238,12 @@ __global__ void __launch_bounds__(THREADS, 1) blind_rotate2k_kernel(Args p) {
     if (p.acc_out) {
         int64_t* ao = p.acc_out + (size_t)g * 2 * N;
         for (int i = tid; i < 2 * N; i += THREADS) ao[i] = (int64_t)acc[i];
+    }
+    if (p.ksk) {   // fused extraction + key switch (the host only sets ksk when ks_fusable(n, t)); the tiles are free now
+        if (p.ks_t == 4) fused_keyswitch2k<4>(acc, tiles, p, g, tid);
+        else if (p.ks_t == 5) fused_keyswitch2k<5>(acc, tiles, p, g, tid);
+        else fused_keyswitch2k<8>(acc, tiles, p, g, tid);
+        return;
     }
     // rlwe_extract_sample_64 (rlwe.jl:70-74): a'_0 = mask_0, a'_i = -mask_{N-i}, b' = body_0
     int32_t* ext = p.ext_out + (size_t)g * (N + 1);

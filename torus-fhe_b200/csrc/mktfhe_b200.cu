@@ -208,9 +208,10 @@ int run_bootstrap_dev(mktfhe_ctx* c, mk::GateLinear lin, int64_t mu, size_t G, c
     cudaStream_t saved = c->stream;
     if (st) c->stream = st;
     if (c->prm.N == mk2k::N) {
-        // N = 2048: one gate per CTA, stand-alone key switch (kernels2k.cuh)
+        // N = 2048: one gate per CTA (kernels2k.cuh); the key switch is the kernel's epilogue when its shape is covered
+        const bool fuse2 = do_keyswitch && c->fuse_ks && mk2k::ks_fusable(c->prm.n, c->prm.t);
         int32_t* ext2 = ext_out;
-        if (!ext2) {
+        if (!ext2 && !fuse2) {
             int rc = reserve(c, c->ext, G * (mk2k::N + 1) * sizeof(int32_t));
             if (rc) { c->stream = saved; return rc; }
             ext2 = (int32_t*)c->ext.p;
@@ -220,13 +221,14 @@ int run_bootstrap_dev(mktfhe_ctx* c, mk::GateLinear lin, int64_t mu, size_t G, c
         a.bsk = c->d_bsk; a.twB = c->d_twB;
         a.xa = xa; a.xb = xb; a.ya = ya; a.yb = yb; a.za = za; a.zb = zb;
         a.lin = lin; a.gate_ids = gate_ids; a.mu = mu; a.ext_out = ext2; a.acc_out = acc_out;
+        if (fuse2) { a.ksk = c->d_ksk; a.ks_t = c->prm.t; a.ks_basebit = c->prm.basebit; a.oa = oa; a.ob = ob; }
         cudaEventRecord(c->ev[0], c->stream);
         if (c->prm.l == 1) mk2k::blind_rotate2k_kernel<1><<<(unsigned)G, mk2k::THREADS, mk2k::smem_bytes(1), c->stream>>>(a);
         else mk2k::blind_rotate2k_kernel<2><<<(unsigned)G, mk2k::THREADS, mk2k::smem_bytes(2), c->stream>>>(a);
         c->launches++;
         cudaEventRecord(c->ev[1], c->stream);
         cudaEventRecord(c->ev[2], c->stream);
-        if (do_keyswitch) {
+        if (do_keyswitch && !fuse2) {
             mk2k::keyswitch2k_kernel<<<(unsigned)G, mk::KS_THREADS, 0, c->stream>>>(c->prm.n, c->prm.k, c->prm.t, c->prm.basebit, c->d_ksk, ext2, oa, ob);
             c->launches++;
         }
