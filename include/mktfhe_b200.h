@@ -20,7 +20,9 @@
  *    nothing is retained after return except uploaded keys (copied).
  *  - *_dev entry points take DEVICE pointers valid on the context's GPU and a
  *    cudaStream_t (as void*, NULL = the context's own stream); they are
- *    asynchronous with respect to the host.
+ *    asynchronous with respect to the host.  The context's own stream is
+ *    non-blocking: with NULL the caller must make sure the operands are
+ *    complete (they are not ordered after work on the legacy default stream).
  *  - ciphertext layout: MKLweSample (mk_internals.jl:23-37) `a::Array{Int32,2}`
  *    of shape (n, k), column-major == int32 [k][n] per sample; batches are
  *    int32 a[G][k][n], int32 b[G].

@@ -56,6 +56,8 @@ def _gate_level_gpu(eng, jobs, k, n):
     oa = torch.empty((G, k, n), dtype=torch.int32, device=dev)
     ob = torch.empty(G, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
+    if not stream:                      # legacy default stream: the context's own stream does not wait for it -- operands must be complete
+        torch.cuda.synchronize(dev)
     eng.ctx.gate_batch_mixed_dev(G, ids.data_ptr(), xa.data_ptr(), xb.data_ptr(), ya.data_ptr(), yb.data_ptr(), 0, 0, oa.data_ptr(), ob.data_ptr(),
                                  stream=stream)
     if not stream:

@@ -546,6 +546,8 @@ def _gate_gpu(eng, gate, x, y, z):
     ob = torch.empty(G, dtype=torch.int32, device=ops[0][0].device)
     za, zb = (ops[2][0].data_ptr(), ops[2][1].data_ptr()) if z is not None else (0, 0)
     stream = torch.cuda.current_stream(ops[0][0].device).cuda_stream
+    if not stream:                      # legacy default stream: the library then works on the context's own (non-blocking) stream, which
+        torch.cuda.synchronize(ops[0][0].device)     # does not wait for the default stream -- the operands must be complete first
     eng.ctx.gate_batch_dev(gate, G, ops[0][0].data_ptr(), ops[0][1].data_ptr(), ops[1][0].data_ptr(), ops[1][1].data_ptr(), za, zb,
                            oa.data_ptr(), ob.data_ptr(), stream=stream)
     if not stream:                      # legacy default stream: the context's own stream did the work
