@@ -194,8 +194,11 @@ def test_error_behaviour(keys2, engine2):
     with pytest.raises(T.MktfheError) as ei:
         engine2.ctx.gate_batch(99, x, x)
     assert ei.value.code == T._cabi.EINVAL
-    with pytest.raises(T.MktfheError) as ei:   # unsupported ring degree (16-party sets use N = 2048)
-        T._cabi.Context(590, 2048, 16, 1, 26, 4, 3)
+    with pytest.raises(T.MktfheError) as ei:   # unsupported ring degree (the 512-party set uses N = 4096)
+        T._cabi.Context(730, 4096, 512, 1, 27, 5, 3)
+    assert ei.value.code == T._cabi.EINVAL
+    with pytest.raises(T.MktfheError) as ei:   # N = 2048 is served with l = 1 or 2 only
+        T._cabi.Context(16, 2048, 2, 3, 7, 3, 3)
     assert ei.value.code == T._cabi.EINVAL
     fresh = T._cabi.Context(520, 1024, 2, 2, 7, 3, 3)
     with pytest.raises(T.MktfheError) as ei:   # keys never loaded

@@ -17,7 +17,7 @@ def test_parameter_sets_match_reference():
     p = T.mktfhe_parameters_8party_3gen
     assert (p.lwe_size, p.gsw_decomp_length, p.gsw_log2_base, p.ks_decomp_length, p.ks_log2_base, p.max_parties) == (540, 4, 4, 5, 2, 8)
     assert T.tgsw_parameters(T.mktfhe_parameters_2party_3gen).gadget_values == [1 << 57, 1 << 50]   # tgsw.jl:26
-    # the N >= 2048 sets exist by name (mk_api.jl:214-322); the engine rejects them at mktfhe_create
+    # the N >= 2048 sets by name (mk_api.jl:214-322): N = 2048 is served by csrc/kernels2k.cuh, N = 4096 (512 parties) is rejected at mktfhe_create
     for k, n, N, l, bg in ((16, 590, 2048, 1, 26), (32, 620, 2048, 1, 26), (64, 650, 2048, 1, 25), (128, 670, 2048, 1, 24), (256, 740, 2048, 2, 18),
                            (512, 730, 4096, 1, 27)):
         p = getattr(T, f"mktfhe_parameters_{k}party_3gen")
