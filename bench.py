@@ -278,7 +278,7 @@ def run_ours(args):
         imad_slots = k * n * ((6 * l * 4608 + 6 * 5120) * 4 + 12 * l * 1024 * 2 + 6 * 1024 * 3 + 2 * 1024 * 17)
         imad_peak = 18.26e12       # measured: tools/pipe_ubench.cu -> profiles/pipe_ubench_r1.txt (62.8 IMAD lanes/clk/SM)
         ncu_traffic = {"bytes_in_captured_launch": 1.589e9, "gates_in_captured_launch": 2368, "waves_in_captured_launch": 8,
-                       "source": "profiles/ncu_r1_m_blind_rotate.txt (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture of a "
+                       "source": "profiles/ncu_r1_n_blind_rotate.txt (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture of a "
                                  "2368-gate launch): one pass over bsk (102 MB) + ksk (90 MB) per wave of 296 gates, i.e. 0.67 MB per gate against "
                                  "68 MB algorithmic; scaled here to this launch's gate count"}
         traffic = ncu_traffic["bytes_in_captured_launch"] * G / ncu_traffic["gates_in_captured_launch"]
@@ -312,7 +312,7 @@ def run_ours(args):
                                                "achieved": G * imad_slots / (br_ms * 1e-3) / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-slots/s",
                                                "frac": G * imad_slots / (br_ms * 1e-3) / imad_peak,
                                                "ncu_fmaheavy_pipe_busy": 0.66, "ncu_issue_active": 0.57,
-                                               "ncu_source": "profiles/ncu_r1_m_blind_rotate.txt, ncu_r1_m_opmix.txt (executed fma-pipe slots incl. "
+                                               "ncu_source": "profiles/ncu_r1_n_blind_rotate.txt, ncu_r1_n_opmix.txt (executed fma-pipe slots incl. "
                                                "address/move overhead: 15.1 k warp-slots per gate-step)"}},
                 "clocks": clocks, "decryptions_correct": ok}
         if world == 1 and not args.no_cpu_baseline and args.parties == 2:
