@@ -8,8 +8,10 @@
  *
  * Three multiplication back-ends for the external product:
  *   MKO_EXACT_SCHOOLBOOK  exact negacyclic product mod 2^64 (ground truth)
- *   MKO_EXACT_NTT         exact, Goldilocks radix-2 NTT, 2 key limbs (bulk tests;
- *                         cross-validated against schoolbook in tests/)
+ *   MKO_EXACT_NTT         exact, Goldilocks radix-2 NTT, the key in 2 limbs of 32 bits
+ *                         (N = 1024 sets) or 3 of 22 bits (N = 2048 sets, 26-bit digits),
+ *                         see ntt_limb_plan (bulk tests; cross-validated against
+ *                         schoolbook in tests/)
  *   MKO_FFT               Float64 folded negacyclic FFT exactly as
  *                         polynomials.jl:208-242 (the reference's arithmetic;
  *                         also the timed CPU baseline)
@@ -323,7 +325,8 @@ struct mko_keyset {
     int64_t *bsk;        /* [k][n][4][l][N]   BootstrapKeyPart_3gen, 3gen_mk_internals.jl:10-43 */
     int32_t *ksk;        /* [k][N][t][B-1][n+1] KeyswitchKey, keyswitch.jl:7-42 */
     double *bsk_fft;     /* [k][n][4][l][N/2][2] TransformedBootstrapKeyPart_3gen :45-55 */
-    u64 *bsk_ntt;        /* [k][n][4][l][2][N] */
+    u64 *bsk_ntt;        /* [k][n][4][l][ntt_limbs][N]: the key in limbs of ntt_limb_bits bits, each transformed */
+    int ntt_limbs, ntt_limb_bits;
     mko_tables *tab;
     pthread_mutex_t lock;
 };
@@ -486,25 +489,38 @@ void mko_prepare_fft_key(mko_keyset *ks) {
     }
     pthread_mutex_unlock(&ks->lock);
 }
+/* Limb split of the exact Goldilocks back-end: the sum over the 2l digit polynomials of digit * limb products must stay below
+ * 2^62 (half the field, so that the signed lift is unambiguous): 2l * N * 2^(bgbit-1) * 2^limb_bits < 2^62.  Two 32-bit limbs cover
+ * the N = 1024 sets (7-bit digits); the 24..26-bit digits of the N = 2048 sets need three limbs of 22 bits. */
+static void ntt_limb_plan(const mko_params *p, int *limbs, int *bits) {
+    int room = 62 - (ilog2(2 * p->l * p->N) + (p->bgbit - 1));   /* ilog2 of a non power of two rounds down: add one below */
+    if ((2 * p->l * p->N) & (2 * p->l * p->N - 1)) room -= 1;
+    if (room >= 32) { *limbs = 2; *bits = 32; }
+    else if (room >= 22) { *limbs = 3; *bits = 22; }
+    else { *limbs = 4; *bits = 16; }
+}
 static void prep_ntt_elem(void *v, int e, int tid) {
     (void)tid;
     mko_keyset *ks = (mko_keyset *)v;
-    int N = ks->p.N, l = ks->p.l;
+    int N = ks->p.N, l = ks->p.l, NL = ks->ntt_limbs, LB = ks->ntt_limb_bits;
+    const u64 lmask = LB == 64 ? ~0ull : (((u64)1 << LB) - 1);
     u64 *tmp = malloc(sizeof(u64) * N);
     for (int q = 0; q < 4 * l; q++) {
         const int64_t *src = ks->bsk + ((size_t)e * 4 * l + q) * N;
-        u64 *dst = ks->bsk_ntt + ((size_t)e * 4 * l + q) * 2 * N;
-        for (int i = 0; i < N; i++) tmp[i] = (u64)src[i] & GL_EPS;
-        gl_negacyclic_fwd(ks->tab, tmp, dst);
-        for (int i = 0; i < N; i++) tmp[i] = (u64)src[i] >> 32;
-        gl_negacyclic_fwd(ks->tab, tmp, dst + N);
+        u64 *dst = ks->bsk_ntt + ((size_t)e * 4 * l + q) * NL * N;
+        for (int limb = 0; limb < NL; limb++) {
+            /* the top limb keeps every remaining bit (it is the only one that may exceed limb_bits when NL * LB < 64: never here) */
+            for (int i = 0; i < N; i++) tmp[i] = limb == NL - 1 ? (u64)src[i] >> (limb * LB) : ((u64)src[i] >> (limb * LB)) & lmask;
+            gl_negacyclic_fwd(ks->tab, tmp, dst + (size_t)limb * N);
+        }
     }
     free(tmp);
 }
 void mko_prepare_ntt_key(mko_keyset *ks) {
     pthread_mutex_lock(&ks->lock);
     if (!ks->bsk_ntt) {
-        ks->bsk_ntt = malloc(bsk_len(&ks->p) * 2 * sizeof(u64));
+        ntt_limb_plan(&ks->p, &ks->ntt_limbs, &ks->ntt_limb_bits);
+        ks->bsk_ntt = malloc(bsk_len(&ks->p) * ks->ntt_limbs * sizeof(u64));
         parallel_for(ks->p.k * ks->p.n, 8, prep_ntt_elem, ks);
     }
     pthread_mutex_unlock(&ks->lock);
@@ -570,26 +586,30 @@ static void extprod_impl(mko_keyset *ks, int backend, int party, int j, const in
         free(res);
     } else if (backend == MKO_EXACT_NTT) {
         mko_prepare_ntt_key(ks);
-        const u64 *key = ks->bsk_ntt + e * 4 * l * 2 * N;
-        u64 *dh = malloc(sizeof(u64) * 2 * l * N), *tmp = malloc(sizeof(u64) * N), *r = malloc(sizeof(u64) * 2 * N);
+        const int NL = ks->ntt_limbs, LB = ks->ntt_limb_bits;
+        const u64 *key = ks->bsk_ntt + e * 4 * l * NL * N;
+        u64 *dh = malloc(sizeof(u64) * 2 * l * N), *tmp = malloc(sizeof(u64) * N), *r = malloc(sizeof(u64) * NL * N);
         for (int s = 0; s < 2 * l; s++) {
             for (int i = 0; i < N; i++) tmp[i] = gl_from_i64(dig[(size_t)s * N + i]);
             gl_negacyclic_fwd(ks->tab, tmp, dh + (size_t)s * N);
         }
         for (int out = 0; out < 2; out++) {
-            for (int limb = 0; limb < 2; limb++) {
+            for (int limb = 0; limb < NL; limb++) {
                 u64 *rr = r + (size_t)limb * N;
                 memset(rr, 0, sizeof(u64) * N);
                 for (int src = 0; src < 2; src++)
                     for (int q = 0; q < l; q++) {
-                        const u64 *kp = key + (((size_t)part_of[out][src] * l + q) * 2 + limb) * N;
+                        const u64 *kp = key + (((size_t)part_of[out][src] * l + q) * NL + limb) * N;
                         const u64 *dp = dh + ((size_t)src * l + q) * N;
                         for (int i = 0; i < N; i++) rr[i] = gl_add(rr[i], gl_mul(dp[i], kp[i]));
                     }
                 gl_negacyclic_inv(ks->tab, rr);
             }
-            for (int i = 0; i < N; i++)
-                acc_out[(size_t)out * N + i] = (int64_t)((u64)gl_lift(r[i]) + ((u64)gl_lift(r[N + i]) << 32));
+            for (int i = 0; i < N; i++) {
+                u64 v = 0;
+                for (int limb = 0; limb < NL; limb++) v += (u64)gl_lift(r[(size_t)limb * N + i]) << (limb * LB);
+                acc_out[(size_t)out * N + i] = (int64_t)v;
+            }
         }
         free(dh); free(tmp); free(r);
     } else { /* MKO_FFT */

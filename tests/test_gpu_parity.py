@@ -360,3 +360,21 @@ def test_n2048_parameter_sets_bit_exact(oracle, prm):
             eng.ctx.extprod_batch(np.array([0], np.int32), acc[:1])     # the single-product hook is N = 1024 only
     finally:
         eng.close()
+
+
+def test_n2048_full_lwe_dimension_bit_exact(oracle):
+    """The 16-party parameter shape at its full LWE dimension (n = 590: 1180 blind-rotate steps with two parties), against the oracle's
+    exact NTT back-end (three 22-bit key limbs; proven equal to schoolbook in tests/test_oracle.py)."""
+    import torus_fhe_b200 as T
+    full = dict(n=590, N=2048, k=2, l=1, bgbit=26, t=4, basebit=3, sigma_lwe=2.0 ** -15.34, sigma_gsw=2.0 ** -62, sigma_ks=2.0 ** -15.34)
+    ks = oracle.KeySet(full, seed=0xB200_2048, nthreads=os.cpu_count() or 8)
+    eng = make_engine(ks)
+    try:
+        bits = np.array([[0, 0], [0, 1], [1, 0], [1, 1]], np.uint8)
+        x, y = ks.encrypt(bits[:, 0], 31), ks.encrypt(bits[:, 1], 32)
+        oa, ob = eng.ctx.gate_batch(T._cabi.GATE_NAND, x, y)
+        ra, rb = ks.gate_batch(oracle.EXACT_NTT, oracle.GATE_NAND, x, y)
+        assert np.array_equal(oa, ra) and np.array_equal(ob, rb)
+        assert np.array_equal(ks.decrypt(oa, ob), ~(bits[:, 0].astype(bool) & bits[:, 1].astype(bool)))
+    finally:
+        eng.close()

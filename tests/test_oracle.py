@@ -155,3 +155,18 @@ def test_fullsize_nand_and_golden(oracle, keys2):
     assert np.array_equal(keys2.decrypt(fa, fb), exp)
     ph = keys2.phase(oa, ob).astype(np.float64) / 2 ** 32
     assert np.all(np.abs(np.abs(ph) - 0.125) < 0.05)
+
+
+def test_exact_ntt_backend_stays_exact_for_wide_gadget_digits(oracle):
+    """The N = 2048 sets have 18..26-bit gadget digits: the Goldilocks back-end then splits the key into three 22-bit limbs
+    (ntt_limb_plan) and must still equal the schoolbook back-end bit for bit, bootstraps included."""
+    import numpy as np
+    for prm in (dict(n=6, N=2048, k=2, l=1, bgbit=26, t=4, basebit=3), dict(n=4, N=2048, k=2, l=2, bgbit=18, t=8, basebit=2)):
+        ks = oracle.KeySet(dict(prm, sigma_lwe=2.0 ** -15.34, sigma_gsw=2.0 ** -62, sigma_ks=2.0 ** -15.34), seed=5, nthreads=4)
+        r = np.random.default_rng(prm["bgbit"])
+        acc = r.integers(-2 ** 63, 2 ** 63 - 1, size=(2, 2048), dtype=np.int64)
+        assert np.array_equal(ks.extprod(oracle.EXACT_NTT, 1, 2, acc), ks.extprod(oracle.EXACT_SCHOOLBOOK, 1, 2, acc))
+        a = r.integers(-2 ** 31, 2 ** 31, (2, ks.k, ks.n)).astype(np.int32)
+        b = r.integers(-2 ** 31, 2 ** 31, 2).astype(np.int32)
+        o1, o2 = ks.bootstrap_batch(oracle.EXACT_SCHOOLBOOK, 1 << 61, a, b), ks.bootstrap_batch(oracle.EXACT_NTT, 1 << 61, a, b)
+        assert np.array_equal(o1[0], o2[0]) and np.array_equal(o1[1], o2[1])
