@@ -12,8 +12,8 @@
 # 3-gen-mk-tfhe/src/3gen_mk_gates.jl:8-150 and src/3gen_mk_internals.jl:112-116; vector methods batch.
 module TFHE_B200
 
-using ..TFHE: TGswParams, RLweParams, BootstrapKeyPart_3gen, KeyswitchKey, MKLweSample, LweParams,
-              encode_message, encode_message64, mk_lwe_noiseless_trivial
+using ..TFHE: TGswParams, RLweParams, BootstrapKeyPart_3gen, KeyswitchKey, MKLweSample, LweSample, LweParams,
+              encode_message, encode_message64, decode_message, mk_lwe_noiseless_trivial
 
 const LIB = get(ENV, "MKTFHE_B200_LIB", "libmktfhe_b200")
 
@@ -53,7 +53,8 @@ mutable struct Engine
     prm :: CParams
 end
 
-const ENGINES = IdDict{Any, Engine}()
+const ENGINES = IdDict{Any, Engine}()          # keyed by the bk array
+const ENGINES_BY_KS = IdDict{Any, Engine}()    # the same engines keyed by the ks array (mk_keyswitch_3gen receives ks only)
 
 """KeyswitchKey.key :: Array{LweSample,3} of dims (base-1, t, N) (keyswitch.jl:7-42) -> Int32 (n+1, base-1, t, N),
 i.e. C int32 [N][t][base-1][n+1]."""
@@ -84,8 +85,13 @@ function engine_for(bk::Array{TransformedBootstrapKeyPart_3gen, 1}, ks::Array{Ke
     check(ctx, ccall((:mktfhe_finalize_keys, LIB), Cint, (Ptr{Cvoid},), ctx))
     e = Engine(ctx, prm)
     finalizer(x -> ccall((:mktfhe_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.ctx), e)
+    ENGINES_BY_KS[ks] = e
     ENGINES[bk] = e
 end
+
+# entry points of the reference that receive only one of (bk, ks): the GPU context holds both, so the pair must have been seen before
+cached_engine(d::IdDict, keys, what) = haskey(d, keys) ? d[keys] :
+    error("no GPU engine holds these $what yet: call TFHE_B200.engine_for(bk, ks) (or any gate) with the key pair first")
 
 # MKLweSample.a is (n, parties) column-major == C int32 [k][n]; a batch is the samples back to back
 pack_a(xs::Vector{MKLweSample}) = reduce(hcat, [vec(x.a) for x in xs])     # (k*n, G)
@@ -106,6 +112,48 @@ function mk_bootstrap_3gen(bk::Array{TransformedBootstrapKeyPart_3gen, 1}, ks::A
     unpack(xs[1].params, n, k, oa, ob)
 end
 mk_bootstrap_3gen(bk::Array{TransformedBootstrapKeyPart_3gen, 1}, ks, mu, x::MKLweSample) = mk_bootstrap_3gen(bk, ks, mu, [x])[1]
+
+function blind_rotate_batch(e::Engine, mu::Int64, a::Matrix{Int32}, b::Vector{Int32})
+    N, G = Int(e.prm.N), length(b)
+    ext = Matrix{Int32}(undef, N + 1, G)                      # C int32 [G][N+1]: a'[0..N-1], b'
+    check(e.ctx, ccall((:mktfhe_blind_rotate_batch, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Csize_t, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}), e.ctx, mu, G, a, b, ext, Ptr{Int64}(C_NULL)))
+    [LweSample(LweParams(N), ext[1:N, g], ext[N + 1, g], 0.0) for g in 1:G]
+end
+
+"""mk_bootstrap_wo_keyswitch_3gen(bk, mu, x) (3gen_mk_internals.jl:99-109): the extracted LweSample of dimension N."""
+function mk_bootstrap_wo_keyswitch_3gen(bk::Array{TransformedBootstrapKeyPart_3gen, 1}, mu::Union{Int32, Int64}, xs::Vector{MKLweSample})
+    blind_rotate_batch(cached_engine(ENGINES, bk, "bootstrapping keys"), Int64(mu), pack_a(xs), pack_b(xs))
+end
+mk_bootstrap_wo_keyswitch_3gen(bk::Array{TransformedBootstrapKeyPart_3gen, 1}, mu::Union{Int32, Int64}, x::MKLweSample) =
+    mk_bootstrap_wo_keyswitch_3gen(bk, mu, [x])[1]
+
+"""mk_blind_rotate_and_extract_3gen(v, bk, barb, bara) (3gen_mk_internals.jl:88-95).  `v` must be the constant test vector
+repeat([mu], N), the only one the reference builds (:105-108).  The kernel mod-switches its input itself, so it is handed the
+torus elements bar * 2^32 / 2N, which decode_message(., 2N) maps back to bar."""
+function mk_blind_rotate_and_extract_3gen(v, bk::Array{TransformedBootstrapKeyPart_3gen, 1}, barb::Int32, bara::Array{Int32, 2})
+    e = cached_engine(ENGINES, bk, "bootstrapping keys")
+    N = Int(e.prm.N)
+    c = v.coeffs
+    (length(c) == N && all(==(c[1]), c)) || error("the engine rotates the constant test vector repeat([mu], N) only")
+    size(bara) == (Int(e.prm.n), Int(e.prm.k)) || error("bara must be (n, parties)")
+    sh = 32 - (trailing_zeros(N) + 1)
+    blind_rotate_batch(e, Int64(c[1]), reshape(bara .<< sh, :, 1), Int32[barb << sh])[1]
+end
+
+"""mk_keyswitch_3gen(ks, sample) (mk_internals.jl:730-744); `sample` may be a vector of extracted LweSamples."""
+function mk_keyswitch_3gen(ks::Array{KeyswitchKey, 1}, us::Vector{LweSample})
+    e = cached_engine(ENGINES_BY_KS, ks, "key-switching keys"); n, k, N, G = Int(e.prm.n), Int(e.prm.k), Int(e.prm.N), length(us)
+    ext = Matrix{Int32}(undef, N + 1, G)
+    for g in 1:G
+        length(us[g].a) == N || error("mk_keyswitch_3gen expects LweSamples of dimension N = $N")
+        ext[1:N, g] = us[g].a; ext[N + 1, g] = us[g].b
+    end
+    oa, ob = Matrix{Int32}(undef, n * k, G), Vector{Int32}(undef, G)
+    check(e.ctx, ccall((:mktfhe_keyswitch_batch, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}), e.ctx, G, ext, oa, ob))
+    unpack(ks[1].out_lwe_params, n, k, oa, ob)
+end
+mk_keyswitch_3gen(ks::Array{KeyswitchKey, 1}, u::LweSample) = mk_keyswitch_3gen(ks, [u])[1]
 
 function gate_batch(bk, ks, gate::Cint, xs::Vector{MKLweSample}, ys::Vector{MKLweSample}, zs::Union{Nothing, Vector{MKLweSample}} = nothing)
     e = engine_for(bk, ks); n, k, G = Int(e.prm.n), Int(e.prm.k), length(xs)
@@ -177,6 +225,28 @@ mk_grt_3gen(bk::BK, ks::KS, a, b, one::MKLweSample, WIDTH) = mk_copy_3gen(mk_sub
 mk_leq_3gen(bk::BK, ks::KS, a, b, one::MKLweSample, WIDTH) = mk_gate_xor_3gen(bk, ks, mk_grt_3gen(bk, ks, a, b, one, WIDTH), one)   # :269-277
 mk_geq_3gen(bk::BK, ks::KS, a, b, one::MKLweSample, WIDTH) = mk_gate_xor_3gen(bk, ks, mk_less_3gen(bk, ks, a, b, one, WIDTH), one)  # :280-288
 
+"""3gen_mk_gates.jl:312-362, statement for statement on top of the batched levels: all WIDTH^2 partial products are one launch.
+As in the reference the final adder re-uses row `ctr` (the last row already added) instead of row WIDTH -- replicated, not fixed."""
+function mk_int_mul_3gen(bk::BK, ks::KS, a::Vector{MKLweSample}, b::Vector{MKLweSample}, ZERO::MKLweSample, WIDTH)
+    prods = gate_level(bk, ks, [(GATE_AND, a[j], b[i]) for i in 1:WIDTH for j in 1:WIDTH])
+    BArr = [prods[(i - 1) * WIDTH + j] for i in 1:WIDTH, j in 1:WIDTH]
+    result = Vector{MKLweSample}(undef, 2 * WIDTH + 1)
+    result[1] = mk_copy_3gen(BArr[1, 1])
+    tmpIn = MKLweSample[[mk_copy_3gen(BArr[1, i + 1]) for i in 1:WIDTH-1]; mk_copy_3gen(ZERO)]
+    ctr = 1
+    for i in 2:WIDTH-1
+        tmpArr = mk_int_add_with_carry_3gen(bk, ks, tmpIn, BArr[i, :], ZERO, WIDTH)
+        result[i] = mk_copy_3gen(tmpArr[1])
+        tmpIn = MKLweSample[mk_copy_3gen(tmpArr[j + 1]) for j in 1:WIDTH]
+        ctr = i
+    end
+    tmpArr = mk_int_add_with_carry_3gen(bk, ks, tmpIn, BArr[ctr, :], ZERO, WIDTH)
+    for i in 1:WIDTH+1
+        result[i + ctr] = mk_copy_3gen(tmpArr[i])
+    end
+    MKLweSample[mk_copy_3gen(result[i]) for i in 1:WIDTH]
+end
+
 # ---- interchange files (torus-fhe_b200/interchange.py documents the layout): dump the reference's own keys / ciphertexts so that
 # the B200 engine and its CPU oracle can be checked on the very bytes the Julia code produced
 function write_keys(path::String, params, bk::Array{TransformedBootstrapKeyPart_3gen, 1}, ks::Array{KeyswitchKey, 1}, secret_keys = nothing)
@@ -204,7 +274,8 @@ function write_ciphertexts(path::String, xs::Vector{MKLweSample})
     end
 end
 
-export TransformedBootstrapKeyPart_3gen, mk_bootstrap_3gen, mk_gate_nand_3gen, mk_gate_or_3gen, mk_gate_and_3gen,
+export TransformedBootstrapKeyPart_3gen, mk_bootstrap_3gen, mk_bootstrap_wo_keyswitch_3gen, mk_blind_rotate_and_extract_3gen,
+       mk_keyswitch_3gen, mk_int_mul_3gen, engine_for, mk_gate_nand_3gen, mk_gate_or_3gen, mk_gate_and_3gen,
        mk_gate_xor_3gen, mk_gate_3and_3gen, mk_gate_not_3gen, mk_gate_mux_3gen, gate_level, mk_copy_3gen, mk_int_add_with_carry_3gen,
        mk_add_3gen, mk_add_3gen_v2, mk_inv_3gen, mk_sub_3gen, mk_less_3gen, mk_grt_3gen, mk_leq_3gen, mk_geq_3gen, write_keys, write_ciphertexts
 

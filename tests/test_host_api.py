@@ -253,3 +253,60 @@ def test_truncated_multiplier_and_conv_layer_wiring(monkeypatch):
         assert np.array_equal(got.reshape(exp.shape), exp)
     # plaintext model sanity: one known window
     assert workloads.conv2d_plain(np.arange(9).reshape(3, 3), np.ones((1, 3, 3), int), 1, 0, 8)[0, 0, 0] == 36
+
+
+def test_blind_rotate_and_keyswitch_entry_points_follow_the_reference_signatures():
+    """mk_bootstrap_wo_keyswitch_3gen(bk, mu, x), mk_blind_rotate_and_extract_3gen(v, bk, barb, bara) and mk_keyswitch_3gen(ks, u)
+    (3gen_mk_internals.jl:88-109, mk_internals.jl:730-744) with a recording stand-in for the GPU context: argument packing, the
+    mod-switch round trip of the rotations, shapes, and the loud errors (no engine, other test vectors, bad shapes)."""
+    import types
+    import torus_fhe_b200 as T
+    prm = T.SchemeParameters_3gen(6, 0.0, 1024, 1, False, 2, 7, 0.0, 3, 3, 0.0, 2)
+    k, n, N = 2, 6, 1024
+    calls = {}
+
+    class Ctx:
+        def blind_rotate_batch(self, mu, a, b):
+            calls["br"] = (mu, a.copy(), b.copy())
+            G = b.size
+            return np.arange(G * (N + 1), dtype=np.int32).reshape(G, N + 1), None
+
+        def keyswitch_batch(self, ext):
+            calls["ks"] = ext.copy()
+            G = ext.shape[0]
+            return np.ones((G, k, n), np.int32), np.full(G, 7, np.int32)
+
+    eng = types.SimpleNamespace(params=prm, ctx=Ctx())
+    bk = [types.SimpleNamespace(_engine=None) for _ in range(k)]
+    ks = [types.SimpleNamespace() for _ in range(k)]
+    mu = T.encode_message64(1, 8)
+    x = T.MKLweSample(T.LweParams(n), np.zeros((3, k, n), np.int32), np.zeros(3, np.int32))
+    with pytest.raises(RuntimeError, match="engine_for"):
+        T.mk_bootstrap_wo_keyswitch_3gen(bk, mu, x)
+    with pytest.raises(RuntimeError, match="engine_for"):
+        T.mk_keyswitch_3gen(ks, T.LweSample(T.LweParams(N), np.zeros((3, N), np.int32), np.zeros(3, np.int32)))
+    T.attach_engine(bk, ks, eng)
+    u = T.mk_bootstrap_wo_keyswitch_3gen(bk, mu, x)
+    assert isinstance(u, T.LweSample) and u.params.size == N and u.a.shape == (3, N) and u.b.shape == (3,)
+    assert calls["br"][0] == int(mu) and u.b[1] == 2 * (N + 1) - 1 and u.a[1, 0] == N + 1
+    # reference form: rotations already mod-switched; the kernel's own mod-switch must give them back
+    r = np.random.default_rng(3)
+    barb, bara = r.integers(-N, N, 3), r.integers(-N, N, (3, k, n))
+    barb[0], bara[0, 0, 0], bara[0, 0, 1] = -N, N - 1, 0
+    u = T.mk_blind_rotate_and_extract_3gen(np.full(N, mu, np.int64), bk, barb, bara)
+    _, a_in, b_in = calls["br"]
+    assert a_in.dtype == np.int32 and a_in.shape == (3, k, n)
+    assert np.array_equal(T.decode_message(a_in, 2 * N), bara) and np.array_equal(T.decode_message(b_in, 2 * N), barb)
+    assert u.a.shape == (3, N)
+    tv = np.full(N, mu, np.int64); tv[5] += 1
+    with pytest.raises(ValueError, match="constant test vector"):
+        T.mk_blind_rotate_and_extract_3gen(tv, bk, barb, bara)
+    with pytest.raises(ValueError, match="rotations"):
+        T.mk_blind_rotate_and_extract_3gen(np.full(N, mu, np.int64), bk, barb, bara + N)
+    with pytest.raises(ValueError, match="rotations"):
+        T.mk_blind_rotate_and_extract_3gen(np.full(N, mu, np.int64), bk, barb, bara[:, :1])
+    out = T.mk_keyswitch_3gen(ks, u)
+    assert isinstance(out, T.MKLweSample) and out.a.shape == (3, k, n) and out.params.size == n and out.current_variance == 0.0
+    assert np.array_equal(calls["ks"][:, :N], u.a) and np.array_equal(calls["ks"][:, N], u.b) and np.all(out.b == 7)
+    with pytest.raises(ValueError, match="dimension N"):
+        T.mk_keyswitch_3gen(ks, T.LweSample(T.LweParams(n), np.zeros((3, n), np.int32), np.zeros(3, np.int32)))

@@ -506,7 +506,7 @@ def engine_for(bk, ks, device=None):
         raise NotImplementedError("rlwe_is32 = true parameter sets are not part of the 3gen path (every 3gen set is Torus64)")
     eng = Engine(_scheme_params_of(bk, ks), device=device)
     eng.load_keys([b.gsw_key for b in bk], [k.key for k in ks])
-    bk[0]._engine = (tag, eng)
+    bk[0]._engine = ks[0]._engine = (tag, eng)
     return eng
 
 
@@ -528,7 +528,7 @@ class RemoteKeys:
 
 def attach_engine(bk, ks, eng):
     """Make `eng` (already holding these keys) the engine the gate API uses for (bk, ks)."""
-    bk[0]._engine = ((tuple(id(b) for b in bk), tuple(id(k) for k in ks)), eng)
+    bk[0]._engine = ks[0]._engine = ((tuple(id(b) for b in bk), tuple(id(k) for k in ks)), eng)
     return eng
 
 
@@ -576,22 +576,62 @@ def mk_bootstrap_3gen(bk, ks, mu, x):
     return MKLweSample(x.params, oa.reshape(x.b.shape + (k, n)), ob.reshape(x.b.shape), 0.0)
 
 
-def mk_blind_rotate_and_extract_3gen(bk, ks, mu, x):
-    """mk_bootstrap_wo_keyswitch_3gen (3gen_mk_internals.jl:99-109): returns the extracted LWE sample
-    (a' int32 [.., N], b' int32 [..]) under the extracted RLWE keys."""
-    eng = engine_for(bk, ks)
+class LweSample:
+    """lwe.jl:23-33: a single-key LWE sample; here the sample extracted from the accumulator, of dimension N under the sum of the
+    parties' extracted RLWE keys (rlwe.jl:70-74).  `a` is int32 [.., size], `b` int32 [..] (leading dimensions = batch)."""
+    __slots__ = ("params", "a", "b", "current_variance")
+
+    def __init__(self, params, a, b, current_variance=0.0):
+        self.params = params
+        self.a = np.asarray(a, dtype=np.int32)
+        self.b = np.asarray(b, dtype=np.int32)
+        self.current_variance = current_variance
+
+
+def _cached_engine(keys, what):
+    """Engine of a call that receives only one of (bk, ks), as mk_bootstrap_wo_keyswitch_3gen and mk_keyswitch_3gen do in the
+    reference: the GPU context always holds both keys, so it must have been created from the pair before."""
+    cached = getattr(keys[0], "_engine", None)
+    if cached is None:
+        raise RuntimeError(f"no GPU engine holds these {what} yet: call engine_for(bk, ks) (or any gate) with the key pair first")
+    return cached[1]
+
+
+def mk_blind_rotate_and_extract_3gen(v, bk, barb, bara):
+    """3gen_mk_internals.jl:88-95: acc = X^{-barb} v, blind rotation by `bara` over every party's key, sample extraction.
+    `v` must be the constant test vector [mu] * N (the only one the reference's callers build, :105-108); `barb` int32 [..] and
+    `bara` int32 [.., k, n] are rotations in [-N, N) as decode_message(x, 2N) returns them.  Returns the extracted LweSample."""
+    eng = _cached_engine(bk, "bootstrapping keys")
+    k, n, N = eng.params.max_parties, eng.params.lwe_size, eng.params.rlwe_polynomial_degree
+    v = np.asarray(v, dtype=np.int64).reshape(-1)
+    if v.size != N or np.any(v != v[0]):
+        raise ValueError("the engine rotates the constant test vector repeat([mu], N) only (3gen_mk_internals.jl:105-108)")
+    barb, bara = np.asarray(barb, np.int64), np.asarray(bara, np.int64)
+    if bara.shape != barb.shape + (k, n) or any(np.any((r < -N) | (r >= N)) for r in (barb, bara)):
+        raise ValueError(f"need rotations in [-N, N) of shapes [..] and [.., {k}, {n}]")
+    # the kernel mod-switches its input itself: hand it the torus elements bar * 2^32 / 2N, which decode_message maps back to bar
+    sh = 32 - _log2(2 * N)
+    ext, _ = eng.ctx.blind_rotate_batch(int(v[0]), (bara << sh).astype(np.int32).reshape(-1, k, n), (barb << sh).astype(np.int32).reshape(-1))
+    return LweSample(LweParams(N), ext[:, :N].reshape(barb.shape + (N,)), ext[:, N].reshape(barb.shape), 0.0)
+
+
+def mk_bootstrap_wo_keyswitch_3gen(bk, mu, x):
+    """3gen_mk_internals.jl:99-109: mod-switch, blind rotation of the test vector [mu] * N, extraction; no key switch."""
+    eng = _cached_engine(bk, "bootstrapping keys")
     k, n, N = eng.params.max_parties, eng.params.lwe_size, eng.params.rlwe_polynomial_degree
     ext, _ = eng.ctx.blind_rotate_batch(int(mu), *_flat(x, k, n))
-    return ext[:, :N].reshape(x.b.shape + (N,)), ext[:, N].reshape(x.b.shape)
+    return LweSample(LweParams(N), ext[:, :N].reshape(x.b.shape + (N,)), ext[:, N].reshape(x.b.shape), 0.0)
 
 
-def mk_keyswitch_3gen(bk, ks, ext_a, ext_b, lwe_params):
-    eng = engine_for(bk, ks)
+def mk_keyswitch_3gen(ks, sample):
+    """mk_internals.jl:730-744: the extracted LweSample (dimension N) to an MKLweSample under the parties' LWE keys."""
+    eng = _cached_engine(ks, "key-switching keys")
     k, n, N = eng.params.max_parties, eng.params.lwe_size, eng.params.rlwe_polynomial_degree
-    ext_a, ext_b = np.asarray(ext_a, np.int32), np.asarray(ext_b, np.int32)
-    ext = np.concatenate([ext_a.reshape(-1, N), ext_b.reshape(-1, 1)], axis=1)
+    if sample.a.shape != sample.b.shape + (N,):
+        raise ValueError(f"mk_keyswitch_3gen expects an LweSample of dimension N = {N}")
+    ext = np.concatenate([sample.a.reshape(-1, N), sample.b.reshape(-1, 1)], axis=1)
     oa, ob = eng.ctx.keyswitch_batch(ext)
-    return MKLweSample(lwe_params, oa.reshape(ext_b.shape + (k, n)), ob.reshape(ext_b.shape), 0.0)
+    return MKLweSample(LweParams(n), oa.reshape(sample.b.shape + (k, n)), ob.reshape(sample.b.shape), 0.0)
 
 
 # gates, 3gen_mk_gates.jl:8-150
