@@ -33,7 +33,7 @@ static void warp_fwd(int pi, const u32* a, u32 out[32][2][32]) {
     for (int lane = 0; lane < 32; lane++)
         for (int h = 0; h < 2; h++) {
             u32 y[32];
-            for (int c = 0; c < 32; c++) y[c] = rns2k::reduce_to_4p(tile[(lane + 32 * h) * TILE_STRIDE + c], 4 * p);
+            for (int c = 0; c < 32; c++) y[c] = rns2k::reduce_to_4p(tile[(lane + 32 * h) * TILE_STRIDE + c], 8 * p, 4 * p);
             fwd_passB32(y, T.twB.data() + twB_index(pi, 0, h, 0, lane), p);
             for (int c = 0; c < 32; c++) out[lane][h][c] = y[c];
         }
@@ -46,13 +46,13 @@ static void warp_inv(int pi, u32 in[32][2][32], u32* a) {
         for (int h = 0; h < 2; h++) {
             u32 y[32];
             for (int c = 0; c < 32; c++) y[c] = in[lane][h][c];
-            inv_passB32(y, T.twB.data() + twB_index(pi, 1, h, 0, lane), p);
+            inv_passB32(y, T.twB.data() + twB_index(pi, 1, h, 0, lane), p, opaque_multiple(4 * p));
             for (int c = 0; c < 32; c++) tile[(lane + 32 * h) * TILE_STRIDE + c] = y[c];
         }
     for (int lane = 0; lane < 32; lane++) {
         u32 x[64];
         for (int r = 0; r < 64; r++) x[r] = tile[r * TILE_STRIDE + lane];
-        inv_passA64(x, T.c.twA[pi][1], p);
+        inv_passA64(x, T.c.twA[pi][1], p, opaque_multiple(4 * p));
         for (int r = 0; r < 64; r++) a[32 * r + lane] = x[r];
     }
 }

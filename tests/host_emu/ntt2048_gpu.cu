@@ -23,7 +23,7 @@ __device__ __forceinline__ void warp_fwd(u32 (&x)[64], u32 (&y)[2][32], u32* til
 #pragma unroll
     for (int h = 0; h < 2; h++) {
 #pragma unroll
-        for (int c = 0; c < 32; c++) y[h][c] = rns2k::reduce_to_4p(tile[(lane + 32 * h) * TILE_STRIDE + c], 4 * p);
+        for (int c = 0; c < 32; c++) y[h][c] = rns2k::reduce_to_4p(tile[(lane + 32 * h) * TILE_STRIDE + c], rns2k::opaque_multiple(8 * p), rns2k::opaque_multiple(4 * p));
         fwd_passB32(y[h], twB + twB_index(pi, 0, h, 0, lane), p);
     }
     __syncwarp();
@@ -31,7 +31,7 @@ __device__ __forceinline__ void warp_fwd(u32 (&x)[64], u32 (&y)[2][32], u32* til
 __device__ __forceinline__ void warp_inv(u32 (&y)[2][32], u32 (&x)[64], u32* tile, const uint2_* twB, int pi, u32 p, int lane) {
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        inv_passB32(y[h], twB + twB_index(pi, 1, h, 0, lane), p);
+        inv_passB32(y[h], twB + twB_index(pi, 1, h, 0, lane), p, rns2k::opaque_multiple(4 * p));
 #pragma unroll
         for (int c = 0; c < 32; c++) tile[(lane + 32 * h) * TILE_STRIDE + c] = y[h][c];
     }
@@ -39,7 +39,7 @@ __device__ __forceinline__ void warp_inv(u32 (&y)[2][32], u32 (&x)[64], u32* til
 #pragma unroll
     for (int r = 0; r < 64; r++) x[r] = tile[r * TILE_STRIDE + lane];
     __syncwarp();
-    inv_passA64(x, c_k.twA[pi][1], p);
+    inv_passA64(x, c_k.twA[pi][1], p, rns2k::opaque_multiple(4 * p));
 }
 
 // grid = products, block = NP warps; res[g][prime][N] residues in [0, 4p) in coefficient order

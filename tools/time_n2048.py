@@ -9,7 +9,7 @@ for p in range(k):
     ctx.load_bsk(p, r.integers(-2**63, 2**63-1, (n, 4, 1, N), dtype=np.int64))
     ctx.load_ksk(p, r.integers(-2**31, 2**31, (N, 4, 7, n + 1)).astype(np.int32))
 ctx.finalize_keys()
-for G in (1, 148, 296):
+for G in ([int(v) for v in sys.argv[1:]] or (1, 148, 296)):
     a = r.integers(-2**31, 2**31, (G, k, n)).astype(np.int32); b = r.integers(-2**31, 2**31, G).astype(np.int32)
     ctx.bootstrap_batch(1 << 61, a, b)
     ctx.bootstrap_batch(1 << 61, a, b)

@@ -12,12 +12,17 @@
 #include "kernels.cuh"
 #include "ntt2048.cuh"
 
+#ifndef MK2K_CRT_UNROLL
+#define MK2K_CRT_UNROLL 4   // Garner chains of the CRT phase interleaved per thread (16 coefficients per thread and step); A/B 1 / 4 / 16 in profiles/ab_r1.txt
+#endif
+
 namespace mk2k {
 
 using rns::uint2_;
 constexpr int N = rns2k::N, NP = rns2k::NP;
 constexpr int WARPS = 2 * NP, THREADS = 32 * WARPS;          // warp = (prime, polynomial)
 constexpr int TILE_WORDS = rns2k::TILE_WORDS, TILE_STRIDE = rns2k::TILE_STRIDE;
+constexpr int CRT_UNROLL = MK2K_CRT_UNROLL;
 
 __constant__ rns2k::Consts c_k2;
 
@@ -56,19 +61,21 @@ __device__ __forceinline__ void warp_fwd(u32 (&x)[64], u32 (&y)[2][32], u32* til
 #pragma unroll
     for (int r = 0; r < 64; r++) tile[r * TILE_STRIDE + lane] = x[r];
     __syncwarp();
+    const u32 p8 = rns2k::opaque_multiple(8 * p), p4 = rns2k::opaque_multiple(4 * p);
 #pragma unroll
     for (int h = 0; h < 2; h++) {
 #pragma unroll
-        for (int c = 0; c < 32; c++) y[h][c] = rns2k::reduce_to_4p(tile[(lane + 32 * h) * TILE_STRIDE + c], 4 * p);
+        for (int c = 0; c < 32; c++) y[h][c] = rns2k::reduce_to_4p(tile[(lane + 32 * h) * TILE_STRIDE + c], p8, p4);
         rns2k::fwd_passB32(y[h], twB + rns2k::twB_index(pi, 0, h, 0, lane), p);
     }
     __syncwarp();
 }
 // inverse: y[h][c] in [0, 4p) -> x[r] = N * a[32 r + lane] in [0, 4p)
 __device__ __forceinline__ void warp_inv(u32 (&y)[2][32], u32 (&x)[64], u32* tile, const uint2_* twB, int pi, u32 p, int lane) {
+    const u32 p4 = rns2k::opaque_multiple(4 * p);
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        rns2k::inv_passB32(y[h], twB + rns2k::twB_index(pi, 1, h, 0, lane), p);
+        rns2k::inv_passB32(y[h], twB + rns2k::twB_index(pi, 1, h, 0, lane), p, p4);
 #pragma unroll
         for (int c = 0; c < 32; c++) tile[(lane + 32 * h) * TILE_STRIDE + c] = y[h][c];
     }
@@ -76,7 +83,7 @@ __device__ __forceinline__ void warp_inv(u32 (&y)[2][32], u32 (&x)[64], u32* til
 #pragma unroll
     for (int r = 0; r < 64; r++) x[r] = tile[r * TILE_STRIDE + lane];
     __syncwarp();
-    rns2k::inv_passA64(x, c_k2.twA[pi][1], p);
+    rns2k::inv_passA64(x, c_k2.twA[pi][1], p, p4);
 }
 
 // Sample extraction + multi-key key switch of the gate by its CTA (rlwe.jl:70-74, mk_internals.jl:730-744, keyswitch.jl:45-80), same
@@ -227,6 +234,7 @@ __global__ void __launch_bounds__(THREADS, 1) blind_rotate2k_kernel(Args p) {
 #pragma unroll
         for (int r = 0; r < 64; r++) tile[32 * r + lane] = x[r];
         __syncthreads();
+#pragma unroll CRT_UNROLL
         for (int i = tid; i < 2 * N; i += THREADS) {
             const int o = i >> 11, ii = i & (N - 1);
             const u32 r[NP] = {tiles[(0 * 2 + o) * TILE_WORDS + ii], tiles[(1 * 2 + o) * TILE_WORDS + ii], tiles[(2 * 2 + o) * TILE_WORDS + ii],

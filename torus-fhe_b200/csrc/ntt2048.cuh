@@ -38,10 +38,24 @@ MK_HD void ct_net(u32 (&x)[1 << LOGM], TW tw, u32 p) {
         }
     }
 }
-// Gentleman-Sande inverse of the same network: inputs and outputs in [0, 4p) (the sum output is reduced every stage)
+// A warp-uniform multiple of p that ptxas cannot derive from p again.  rns::keep_in_register is opaque to the front end only: under
+// this kernel's register pressure (64 coefficients per thread) ptxas rematerialised `s - 4p` as IMAD(p, -4, s) + VIMNMX -- one slot of the
+// binding fma pipe and one extra issue slot per inverse butterfly (profiles/ncu_r1_o_2k_opmix.txt: 2.7 IMAD per IMAD.HI instead of 2).
+// A value that went through a SHFL has to stay in its register, and `min(s, s - p4)` becomes one VIADDMNMX.U32 with a negated operand.
+// Call with all 32 lanes converged; the value must be the same in every lane (it is read back from lane 0).
+#ifndef MK2K_OPAQUE
+#define MK2K_OPAQUE 1
+#endif
+MK_HD u32 opaque_multiple(u32 v) {
+#if defined(__CUDA_ARCH__) && MK2K_OPAQUE
+    return __shfl_sync(0xffffffffu, v, 0);
+#else
+    return rns::keep_in_register(v);
+#endif
+}
+// Gentleman-Sande inverse of the same network: inputs and outputs in [0, 4p) (the sum output is reduced every stage); p4 = 4p
 template <int LOGM, class TW>
-MK_HD void gs_net(u32 (&x)[1 << LOGM], TW tw, u32 p) {
-    const u32 p4 = rns::keep_in_register(4 * p);
+MK_HD void gs_net(u32 (&x)[1 << LOGM], TW tw, u32 p, u32 p4) {
 #pragma unroll
     for (int k = LOGM - 1; k >= 0; k--) {
         const int g = (1 << (LOGM - 1)) >> k;
@@ -85,11 +99,15 @@ MK_HD size_t twB_index(int prime, int dir, int half, int entry, int lane) { retu
 MK_HD void fwd_passA64(u32 (&x)[64], const uint2_* twA_fwd, u32 p) { ct_net<6>(x, TwUniform{twA_fwd}, p); }
 // y[c] = the run of 32 consecutive coefficients of block q, in [0, 4p)  ->  positions 32 q + c of the transformed polynomial, < 14p
 MK_HD void fwd_passB32(u32 (&y)[32], const uint2_* twB_fwd_lane, u32 p) { rns::ct32(y, TwLane{twB_fwd_lane}, p); }
-MK_HD void inv_passB32(u32 (&y)[32], const uint2_* twB_inv_lane, u32 p) { rns::gs32(y, TwLane{twB_inv_lane}, p); }
-MK_HD void inv_passA64(u32 (&x)[64], const uint2_* twA_inv, u32 p) { gs_net<6>(x, TwUniform{twA_inv}, p); }
+// the inverse passes take p4 = opaque_multiple(4p), made once per transform (gs_net<5> is rns::gs32 with that parameter)
+MK_HD void inv_passB32(u32 (&y)[32], const uint2_* twB_inv_lane, u32 p, u32 p4) { gs_net<5>(y, TwLane{twB_inv_lane}, p, p4); }
+MK_HD void inv_passA64(u32 (&x)[64], const uint2_* twA_inv, u32 p, u32 p4) { gs_net<6>(x, TwUniform{twA_inv}, p, p4); }
 
-// [0, 16p) -> [0, 4p) between the passes of the forward transform
-MK_HD u32 reduce_to_4p(u32 v, u32 p4) { return rns::reduce_to_4p(v, p4); }
+// [0, 16p) -> [0, 4p) between the passes of the forward transform; p8 = 8p, p4 = 4p, both opaque_multiple()s
+MK_HD u32 reduce_to_4p(u32 v, u32 p8, u32 p4) {
+    v = rns::umin32(v, v - p8);
+    return rns::umin32(v, v - p4);
+}
 
 // residues r_i in [0, 4 p_i) of an integer R with |R| < M/4 -> R mod 2^64 (two's complement); Garner's mixed radix over four primes
 MK_HD u64 crt4_lift(const u32 (&r)[NP], const Consts& c) {
