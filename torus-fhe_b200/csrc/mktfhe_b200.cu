@@ -85,6 +85,9 @@ int reserve(mktfhe_ctx* c, DevBuf& b, size_t bytes) {
 
 int check_params(const mktfhe_params* p) {
     if (!p) return fail(nullptr, MKTFHE_EINVAL, "params is NULL");
+    // shifts by these fields follow: bound them before anything computes 1 << bgbit or 1 << basebit
+    if (p->bgbit < 1 || p->bgbit > 30) return fail(nullptr, MKTFHE_EINVAL, "unsupported gsw_log2_base=%d", p->bgbit);
+    if (p->basebit < 1 || p->basebit > 16) return fail(nullptr, MKTFHE_EINVAL, "unsupported ks_log2_base=%d (1..16)", p->basebit);
     if (p->N == mk2k::N) {
         // N = 2048 sets (mk_api.jl:214-310): l = 1 or 2 with a wide gadget base, four-prime exact product (kernels2k.cuh)
         if (p->l < 1 || p->l > 2) return fail(nullptr, MKTFHE_EINVAL, "N=2048 is supported with gsw_decomp_length l=1 or 2 (got %d)", p->l);
