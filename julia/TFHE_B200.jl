@@ -180,6 +180,12 @@ end
 mk_gate_3and_3gen(bk::BK, ks::KS, x::V, y::V, z::V) = gate_batch(bk, ks, GATE_AND3, x, y, z)
 mk_gate_3and_3gen(bk::BK, ks::KS, x::MKLweSample, y::MKLweSample, z::MKLweSample) = gate_batch(bk, ks, GATE_AND3, [x], [y], [z])[1]
 mk_gate_not_3gen(x::MKLweSample) = -x
+# the `_wb` variants (3gen_mk_gates.jl:16-21, 32-37, 48-53, 76-81): the linear prologue alone, not bootstrapped -- plain Julia
+mk_gate_nand_3gen_wb(bk::BK, ks::KS, x::MKLweSample, y::MKLweSample) = mk_lwe_noiseless_trivial(encode_message(1, 8), x.params, length(bk)) - x - y
+mk_gate_or_3gen_wb(bk::BK, ks::KS, x::MKLweSample, y::MKLweSample) = mk_lwe_noiseless_trivial(encode_message(1, 8), x.params, length(bk)) + x + y
+mk_gate_and_3gen_wb(bk::BK, ks::KS, x::MKLweSample, y::MKLweSample) = mk_lwe_noiseless_trivial(encode_message(-1, 8), x.params, length(bk)) + x + y
+mk_gate_xor_3gen_wb(bk::BK, ks::KS, x::MKLweSample, y::MKLweSample) =
+    mk_lwe_noiseless_trivial(encode_message(1, 4), x.params, length(bk)) + Int32(2) * x + Int32(2) * y
 
 """3gen_mk_gates.jl:133-150: the two ANDs in one launch, then 1/8 + t1 + t2 NOT bootstrapped (as the reference)."""
 function mk_gate_mux_3gen(bk::BK, ks::KS, x::MKLweSample, y::MKLweSample, z::MKLweSample)
@@ -276,7 +282,8 @@ end
 
 export TransformedBootstrapKeyPart_3gen, mk_bootstrap_3gen, mk_bootstrap_wo_keyswitch_3gen, mk_blind_rotate_and_extract_3gen,
        mk_keyswitch_3gen, mk_int_mul_3gen, engine_for, mk_gate_nand_3gen, mk_gate_or_3gen, mk_gate_and_3gen,
-       mk_gate_xor_3gen, mk_gate_3and_3gen, mk_gate_not_3gen, mk_gate_mux_3gen, gate_level, mk_copy_3gen, mk_int_add_with_carry_3gen,
+       mk_gate_xor_3gen, mk_gate_3and_3gen, mk_gate_not_3gen, mk_gate_mux_3gen, mk_gate_nand_3gen_wb, mk_gate_or_3gen_wb, mk_gate_and_3gen_wb,
+       mk_gate_xor_3gen_wb, gate_level, mk_copy_3gen, mk_int_add_with_carry_3gen,
        mk_add_3gen, mk_add_3gen_v2, mk_inv_3gen, mk_sub_3gen, mk_less_3gen, mk_grt_3gen, mk_leq_3gen, mk_geq_3gen, write_keys, write_ciphertexts
 
 end # module

@@ -310,3 +310,56 @@ def test_blind_rotate_and_keyswitch_entry_points_follow_the_reference_signatures
     assert np.array_equal(calls["ks"][:, :N], u.a) and np.array_equal(calls["ks"][:, N], u.b) and np.all(out.b == 7)
     with pytest.raises(ValueError, match="dimension N"):
         T.mk_keyswitch_3gen(ks, T.LweSample(T.LweParams(n), np.zeros((3, n), np.int32), np.zeros(3, np.int32)))
+
+
+def test_exported_name_surface_is_the_reference_3gen_surface():
+    """every 3gen name 3-gen-mk-tfhe/src/TFHE.jl exports (lines 11-15, 32-96, 113-119, 135-165, 177-196) resolves in
+    the host mirror, plus the un-exported mk_bootstrap_wo_keyswitch_3gen the parity tests use; gates keep the reference's positional
+    arguments (bk, ks, x, y[, z]) and circuits (bk, ks, a, b, carry-or-one, WIDTH)."""
+    import inspect
+    import torus_fhe_b200 as T
+    names = """SecretKey_3gen RLweKey KeyswitchKey MKLweSample CRP_3gen PublicKey CommonPubKey_3gen BootstrapKeyPart_3gen
+        TransformedBootstrapKeyPart_3gen lwe_parameters rlwe_parameters tgsw_parameters keyswitch_parameters encode_message encode_message64
+        decode_message decode_message64 noise_calc mk_lwe_noiseless_trivial mk_keyswitch_3gen mk_lwe_phase mk_blind_rotate_and_extract_3gen
+        mk_bootstrap_3gen GenCRP_3gen mk_encrypt_3gen mk_int_encrypt_3gen mk_decrypt_3gen mk_int_decrypt_3gen mk_gate_nand_3gen mk_gate_or_3gen
+        mk_gate_xor_3gen mk_gate_and_3gen mk_gate_3and_3gen mk_gate_not_3gen mk_gate_mux_3gen mk_copy_3gen mk_add_3gen mk_add_3gen_v2 mk_inv_3gen
+        mk_sub_3gen mk_less_3gen mk_grt_3gen mk_leq_3gen mk_geq_3gen mk_int_add_with_carry_3gen mk_int_mul_3gen
+        mk_bootstrap_wo_keyswitch_3gen""".split()
+    names += [f"mktfhe_parameters_{k}party_3gen" for k in (2, 3, 4, 5, 8, 16, 32, 64, 128, 256, 512)]
+    assert [n for n in names if not hasattr(T, n)] == []
+    arity = {"mk_gate_nand_3gen": 4, "mk_gate_or_3gen": 4, "mk_gate_and_3gen": 4, "mk_gate_xor_3gen": 4, "mk_gate_3and_3gen": 5, "mk_gate_mux_3gen": 5,
+             "mk_gate_not_3gen": 1, "mk_bootstrap_3gen": 4, "mk_bootstrap_wo_keyswitch_3gen": 3, "mk_blind_rotate_and_extract_3gen": 4,
+             "mk_keyswitch_3gen": 2, "mk_add_3gen": 6, "mk_add_3gen_v2": 6, "mk_sub_3gen": 6, "mk_inv_3gen": 5, "mk_less_3gen": 6, "mk_grt_3gen": 6,
+             "mk_leq_3gen": 6, "mk_geq_3gen": 6, "mk_int_add_with_carry_3gen": 6, "mk_int_mul_3gen": 6}
+    for name, n in arity.items():
+        params = [p for p in inspect.signature(getattr(T, name)).parameters.values() if p.default is inspect.Parameter.empty]
+        assert len(params) == n, (name, [p.name for p in params])
+
+
+def test_unbootstrapped_gate_variants_are_the_gate_prologues(oracle, rng):
+    """mk_gate_{nand,or,and,xor}_3gen_wb (3gen_mk_gates.jl:16-21, 32-37, 48-53, 76-81) return the gate's linear prologue: the same
+    sample the oracle (and the kernel's fused prologue) feeds to the bootstrap."""
+    import ctypes as C
+    import torus_fhe_b200 as T
+    L = oracle.lib()
+    L.mko_gate_prologue.restype = None
+    L.mko_gate_prologue.argtypes = [C.POINTER(oracle.Params), C.c_int] + [C.c_void_p, C.c_int32] * 3 + [C.c_void_p, C.c_void_p]
+    k, n = 3, 17
+    prm = oracle.params(n, 64, k, 2, 7, 3, 3, 0.0, 0.0, 0.0)
+    lp = T.LweParams(n)
+    mk = lambda: T.MKLweSample(lp, rng.integers(-2 ** 31, 2 ** 31, size=(k, n), dtype=np.int64).astype(np.int32),
+                               np.int32(rng.integers(-2 ** 31, 2 ** 31)), 0.25)
+    x, y = mk(), mk()
+    bk = [None] * k        # only its length is read, as in the reference
+    for fn, gate in ((T.mk_gate_nand_3gen_wb, oracle.GATE_NAND), (T.mk_gate_or_3gen_wb, oracle.GATE_OR),
+                     (T.mk_gate_and_3gen_wb, oracle.GATE_AND), (T.mk_gate_xor_3gen_wb, oracle.GATE_XOR)):
+        out = fn(bk, None, x, y)
+        ta, tb = np.empty((k, n), np.int32), C.c_int32(0)
+        L.mko_gate_prologue(C.byref(prm), gate, x.a.ctypes.data, int(x.b), y.a.ctypes.data, int(y.b), None, 0, ta.ctypes.data, C.byref(tb))
+        assert np.array_equal(out.a, ta) and int(out.b) == tb.value, fn.__name__
+        assert out.current_variance == (0.5 if gate != oracle.GATE_XOR else 2.0)      # mk_internals.jl:40-51
+    # batched samples too
+    xb = T.MKLweSample.stack([x, y, x])
+    yb = T.MKLweSample.stack([y, y, x])
+    out = T.mk_gate_nand_3gen_wb(bk, None, xb, yb)
+    assert out.a.shape == (3, k, n) and np.array_equal(out[0].a, T.mk_gate_nand_3gen_wb(bk, None, x, y).a)

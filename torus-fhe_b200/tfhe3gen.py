@@ -664,6 +664,36 @@ def mk_gate_not_3gen(x):
     return -x
 
 
+def _gate_wb(bk, mu0, cx, x, y):
+    """The `_wb` ("without bootstrap") variants, 3gen_mk_gates.jl:16-21, 32-37, 48-53, 76-81: the linear prologue of the gate alone,
+    returned un-bootstrapped.  Host (or torch) arithmetic on the sample; bk only supplies the party count, ks is unused, as there."""
+    if isinstance(x, MKLweSampleGPU):
+        t = mk_lwe_noiseless_trivial_gpu(mu0, x.params, len(bk), tuple(x.b.shape), x.a.device.index)
+    else:
+        t = mk_lwe_noiseless_trivial(mu0, x.params, len(bk), x.b.shape)
+    if cx == -1:
+        return t - x - y
+    if cx == 1:
+        return t + x + y
+    return t + cx * x + cx * y
+
+
+def mk_gate_nand_3gen_wb(bk, ks, x, y):
+    return _gate_wb(bk, encode_message(1, 8), -1, x, y)
+
+
+def mk_gate_or_3gen_wb(bk, ks, x, y):
+    return _gate_wb(bk, encode_message(1, 8), 1, x, y)
+
+
+def mk_gate_and_3gen_wb(bk, ks, x, y):
+    return _gate_wb(bk, encode_message(-1, 8), 1, x, y)
+
+
+def mk_gate_xor_3gen_wb(bk, ks, x, y):
+    return _gate_wb(bk, encode_message(1, 4), 2, x, y)
+
+
 def mk_gate_mux_3gen(bk, ks, x, y, z):
     """3gen_mk_gates.jl:133-150: AND(x, y) and AND(-x, z) bootstrapped (one launch: the two ANDs are
     independent), then 1/8 + t1 + t2 NOT bootstrapped, exactly as the reference."""
