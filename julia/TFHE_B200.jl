@@ -12,8 +12,8 @@
 # 3-gen-mk-tfhe/src/3gen_mk_gates.jl:8-150 and src/3gen_mk_internals.jl:112-116; vector methods batch.
 module TFHE_B200
 
-using ..TFHE: TGswParams, RLweParams, BootstrapKeyPart_3gen, KeyswitchKey, MKLweSample, LweSample, LweParams,
-              encode_message, encode_message64, decode_message, mk_lwe_noiseless_trivial
+using ..TFHE: TGswParams, RLweParams, BootstrapKeyPart_3gen, KeyswitchKey, MKLweSample, LweSample, LweParams, RLweSample,
+              encode_message, encode_message64, decode_message, mk_lwe_noiseless_trivial, torus_polynomial, mul_by_monomial
 
 const LIB = get(ENV, "MKTFHE_B200_LIB", "libmktfhe_b200")
 
@@ -54,6 +54,7 @@ mutable struct Engine
 end
 
 const ENGINES = IdDict{Any, Engine}()          # keyed by the bk array
+const PART_OWNER = IdDict{Any, Tuple{Engine, Int}}()   # key part -> (engine holding it, 0-based party): the per-element entry points
 const ENGINES_BY_KS = IdDict{Any, Engine}()    # the same engines keyed by the ks array (mk_keyswitch_3gen receives ks only)
 
 """KeyswitchKey.key :: Array{LweSample,3} of dims (base-1, t, N) (keyswitch.jl:7-42) -> Int32 (n+1, base-1, t, N),
@@ -85,6 +86,7 @@ function engine_for(bk::Array{TransformedBootstrapKeyPart_3gen, 1}, ks::Array{Ke
     check(ctx, ccall((:mktfhe_finalize_keys, LIB), Cint, (Ptr{Cvoid},), ctx))
     e = Engine(ctx, prm)
     finalizer(x -> ccall((:mktfhe_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.ctx), e)
+    for p in 1:length(bk); PART_OWNER[bk[p].gsw_key] = (e, p - 1); end
     ENGINES_BY_KS[ks] = e
     ENGINES[bk] = e
 end
@@ -154,6 +156,46 @@ function mk_keyswitch_3gen(ks::Array{KeyswitchKey, 1}, us::Vector{LweSample})
     unpack(ks[1].out_lwe_params, n, k, oa, ob)
 end
 mk_keyswitch_3gen(ks::Array{KeyswitchKey, 1}, u::LweSample) = mk_keyswitch_3gen(ks, [u])[1]
+
+# ---- the path's internal entry points, stage by stage (3gen_mk_internals.jl:59-84, tgsw_3gen.jl:102-113); the tested twin is
+# torus-fhe_b200/tfhe3gen.py.  Gates and bootstraps never take this route: they run the whole loop inside one kernel.
+"""Element j (1-based) of a party's bootstrapping key, resident on the GPU (the reference's type holds its FFTs, tgsw_3gen.jl:23-39)."""
+struct TransformedTGswSample_3gen
+    part :: TransformedBootstrapKeyPart_3gen
+    j :: Int
+end
+tgsw_samples(bk::TransformedBootstrapKeyPart_3gen) = [TransformedTGswSample_3gen(bk, j) for j in 1:bk.key_size]
+
+"""tgsw_extern_mul_3gen(accum, sample) (tgsw_3gen.jl:102-113) through mktfhe_extprod_batch: accum.a = [mask, body]."""
+function tgsw_extern_mul_3gen(accum::RLweSample, sample::TransformedTGswSample_3gen)
+    haskey(PART_OWNER, sample.part.gsw_key) || error("no GPU engine holds this key part yet: call TFHE_B200.engine_for(bk, ks) first")
+    e, party = PART_OWNER[sample.part.gsw_key]
+    N = Int(e.prm.N)
+    acc = hcat(Vector{Int64}(accum.a[1].coeffs), Vector{Int64}(accum.a[2].coeffs))      # (N, 2) column-major == C int64 [2][N]
+    out = Matrix{Int64}(undef, N, 2)
+    elem = Int32[party * Int(e.prm.n) + sample.j - 1]
+    check(e.ctx, ccall((:mktfhe_extprod_batch, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}), e.ctx, 1, elem, acc, out))
+    RLweSample(accum.params, [torus_polynomial(out[:, 1]), torus_polynomial(out[:, 2])], 0.0)
+end
+
+mk_mux_rotate_3gen(accum::RLweSample, bki::TransformedTGswSample_3gen, barai::Int32) =                  # :59-62
+    accum + tgsw_extern_mul_3gen(mul_by_monomial(accum, barai) - accum, bki)
+
+function mk_ith_blind_rotate_3gen(acc::RLweSample, gsw_key::Array{TransformedTGswSample_3gen, 1}, bara::Array{Int32, 1})   # :66-75
+    for i in eachindex(bara)
+        if bara[i] != 0
+            acc = mk_mux_rotate_3gen(acc, gsw_key[i], bara[i])
+        end
+    end
+    acc
+end
+
+function mk_blind_rotate_3gen(accum::RLweSample, bk::Array{TransformedBootstrapKeyPart_3gen, 1}, bara::Array{Int32, 2})     # :78-84
+    for i in 1:length(bk)
+        accum = mk_ith_blind_rotate_3gen(accum, tgsw_samples(bk[i]), bara[:, i])
+    end
+    accum
+end
 
 function gate_batch(bk, ks, gate::Cint, xs::Vector{MKLweSample}, ys::Vector{MKLweSample}, zs::Union{Nothing, Vector{MKLweSample}} = nothing)
     e = engine_for(bk, ks); n, k, G = Int(e.prm.n), Int(e.prm.k), length(xs)
@@ -284,6 +326,7 @@ export TransformedBootstrapKeyPart_3gen, mk_bootstrap_3gen, mk_bootstrap_wo_keys
        mk_keyswitch_3gen, mk_int_mul_3gen, engine_for, mk_gate_nand_3gen, mk_gate_or_3gen, mk_gate_and_3gen,
        mk_gate_xor_3gen, mk_gate_3and_3gen, mk_gate_not_3gen, mk_gate_mux_3gen, mk_gate_nand_3gen_wb, mk_gate_or_3gen_wb, mk_gate_and_3gen_wb,
        mk_gate_xor_3gen_wb, gate_level, mk_copy_3gen, mk_int_add_with_carry_3gen,
-       mk_add_3gen, mk_add_3gen_v2, mk_inv_3gen, mk_sub_3gen, mk_less_3gen, mk_grt_3gen, mk_leq_3gen, mk_geq_3gen, write_keys, write_ciphertexts
+       mk_add_3gen, mk_add_3gen_v2, mk_inv_3gen, mk_sub_3gen, mk_less_3gen, mk_grt_3gen, mk_leq_3gen, mk_geq_3gen, write_keys, write_ciphertexts,
+       TransformedTGswSample_3gen, tgsw_samples, tgsw_extern_mul_3gen, mk_mux_rotate_3gen, mk_ith_blind_rotate_3gen, mk_blind_rotate_3gen
 
 end # module

@@ -324,12 +324,17 @@ def test_exported_name_surface_is_the_reference_3gen_surface():
         mk_bootstrap_3gen GenCRP_3gen mk_encrypt_3gen mk_int_encrypt_3gen mk_decrypt_3gen mk_int_decrypt_3gen mk_gate_nand_3gen mk_gate_or_3gen
         mk_gate_xor_3gen mk_gate_and_3gen mk_gate_3and_3gen mk_gate_not_3gen mk_gate_mux_3gen mk_copy_3gen mk_add_3gen mk_add_3gen_v2 mk_inv_3gen
         mk_sub_3gen mk_less_3gen mk_grt_3gen mk_leq_3gen mk_geq_3gen mk_int_add_with_carry_3gen mk_int_mul_3gen
-        mk_bootstrap_wo_keyswitch_3gen""".split()
+        mk_bootstrap_wo_keyswitch_3gen mk_gate_nand_3gen_wb mk_gate_or_3gen_wb mk_gate_and_3gen_wb mk_gate_xor_3gen_wb mk_gate_xor_3gen_gpu
+        mk_int_add_3gen_gpu xor_3gen_gpu mk_lwe_noiseless_trivial_gpu enc_conv2d
+        TGswSample_3gen TransformedTGswSample_3gen tgsw_encrypt_3gen tgsw_extern_mul_3gen mk_mux_rotate_3gen mk_ith_blind_rotate_3gen
+        mk_blind_rotate_3gen RLweSample rlwe_noiseless_trivial rlwe_extract_sample_64 mul_by_monomial t64tot32""".split()
+    # = every function and type of 3gen_mk_gates.jl, 3gen_mk_internals.jl, tgsw_3gen.jl and gpu_circuits.jl, plus what they call in rlwe.jl
     names += [f"mktfhe_parameters_{k}party_3gen" for k in (2, 3, 4, 5, 8, 16, 32, 64, 128, 256, 512)]
     assert [n for n in names if not hasattr(T, n)] == []
     arity = {"mk_gate_nand_3gen": 4, "mk_gate_or_3gen": 4, "mk_gate_and_3gen": 4, "mk_gate_xor_3gen": 4, "mk_gate_3and_3gen": 5, "mk_gate_mux_3gen": 5,
              "mk_gate_not_3gen": 1, "mk_bootstrap_3gen": 4, "mk_bootstrap_wo_keyswitch_3gen": 3, "mk_blind_rotate_and_extract_3gen": 4,
-             "mk_keyswitch_3gen": 2, "mk_add_3gen": 6, "mk_add_3gen_v2": 6, "mk_sub_3gen": 6, "mk_inv_3gen": 5, "mk_less_3gen": 6, "mk_grt_3gen": 6,
+             "mk_keyswitch_3gen": 2, "tgsw_extern_mul_3gen": 2, "mk_mux_rotate_3gen": 3, "mk_ith_blind_rotate_3gen": 3, "mk_blind_rotate_3gen": 3,
+             "tgsw_encrypt_3gen": 5, "mk_add_3gen": 6, "mk_add_3gen_v2": 6, "mk_sub_3gen": 6, "mk_inv_3gen": 5, "mk_less_3gen": 6, "mk_grt_3gen": 6,
              "mk_leq_3gen": 6, "mk_geq_3gen": 6, "mk_int_add_with_carry_3gen": 6, "mk_int_mul_3gen": 6}
     for name, n in arity.items():
         params = [p for p in inspect.signature(getattr(T, name)).parameters.values() if p.default is inspect.Parameter.empty]
@@ -363,3 +368,114 @@ def test_unbootstrapped_gate_variants_are_the_gate_prologues(oracle, rng):
     yb = T.MKLweSample.stack([y, y, x])
     out = T.mk_gate_nand_3gen_wb(bk, None, xb, yb)
     assert out.a.shape == (3, k, n) and np.array_equal(out[0].a, T.mk_gate_nand_3gen_wb(bk, None, x, y).a)
+
+
+def test_path_internals_follow_the_reference_step_by_step(oracle, toy_keys):
+    """tgsw_extern_mul_3gen / mk_mux_rotate_3gen / mk_ith_blind_rotate_3gen / mk_blind_rotate_3gen / rlwe_extract_sample_64
+    (3gen_mk_internals.jl:59-95, tgsw_3gen.jl:102-113, rlwe.jl:70-74) in the host mirror: the host-side steps (monomial product,
+    sample arithmetic, loop order, zero skip, extraction) against the oracle, with the GPU external product replaced by the
+    oracle's -- on the B200 the same functions are checked against the fused kernel (tests/test_zz_gpu_path_internals.py)."""
+    import torus_fhe_b200 as T
+    ks = toy_keys
+    N, n, k = ks.N, ks.n, ks.k
+
+    class FakeCtx:
+        calls = 0
+
+        def extprod_batch(self, elem, acc):
+            out = np.empty_like(acc)
+            for g, e in enumerate(np.asarray(elem).reshape(-1)):
+                out[g] = ks.extprod(oracle.EXACT_SCHOOLBOOK, int(e) // n, int(e) % n, acc[g])
+                FakeCtx.calls += 1
+            return out
+
+    class FakeEngine:
+        params = T.SchemeParameters_3gen(n, 0.0, N, 1, False, ks.l, ks.prm.bgbit, 0.0, ks.t, ks.prm.basebit, 0.0, k)
+        ctx = FakeCtx()
+
+    tg, rl = T.TGswParams(ks.l, ks.prm.bgbit, False), T.RLweParams(N, 1, False)
+    bk = [T.TransformedBootstrapKeyPart_3gen(T.BootstrapKeyPart_3gen.from_array(ks.bsk[p], tg, rl)) for p in range(k)]
+    sample = bk[1].tgsw_samples[3]
+    with pytest.raises(RuntimeError, match="engine_for"):
+        T.tgsw_extern_mul_3gen(T.RLweSample(rl, np.zeros((2, N), np.int64)), sample)
+    kk = [T.KeyswitchKey.from_array(ks.ksk[p], T.KeyswitchParameters(ks.t, ks.prm.basebit)) for p in range(k)]
+    T.attach_engine(bk, kk, FakeEngine())
+    assert np.array_equal(sample.part_3, ks.bsk[1, 3, 2]) and sample._locate()[1] == 1 * n + 3
+
+    r = np.random.default_rng(5)
+    poly = r.integers(-2 ** 63, 2 ** 63 - 1, size=N, dtype=np.int64)
+    for s in (0, 1, -1, 7, N, N + 5, -N - 5, 2 * N, 5 * N + 3):
+        assert np.array_equal(T.mul_by_monomial(poly, s), oracle.mul_by_monomial(poly, s)), s
+    acc = T.RLweSample(rl, r.integers(-2 ** 63, 2 ** 63 - 1, size=(2, N), dtype=np.int64))
+    assert np.array_equal(T.tgsw_extern_mul_3gen(acc, sample).a, ks.extprod(oracle.EXACT_SCHOOLBOOK, 1, 3, acc.a))
+    assert np.array_equal(T.mk_mux_rotate_3gen(acc, sample, np.int32(-9)).a, ks.mux_rotate(oracle.EXACT_SCHOOLBOOK, 1, 3, -9, acc.a))
+    batch = T.RLweSample(rl, np.stack([acc.a, -acc.a]))        # a leading batch dimension goes through one call
+    out = T.mk_mux_rotate_3gen(batch, sample, 17)
+    assert np.array_equal(out.a[0], ks.mux_rotate(oracle.EXACT_SCHOOLBOOK, 1, 3, 17, acc.a))
+
+    # the whole blind rotation, stage by stage, equals the oracle's bootstrap without key switch (accumulator and extracted sample)
+    mu = T.encode_message64(1, 8)
+    a, b = ks.encrypt(np.array([1], np.uint8), 5)
+    x = T.MKLweSample(T.LweParams(n), a[0], b[0])
+    barb, bara = T.decode_message(x.b, 2 * N), T.decode_message(x.a, 2 * N)
+    bara = bara.copy()
+    bara[0, 2] = 0                                             # a zero rotation is skipped (3gen_mk_internals.jl:69)
+    FakeCtx.calls = 0
+    accum = T.rlwe_noiseless_trivial(T.mul_by_monomial(np.full(N, mu, np.int64), -int(barb)), rl)
+    accum = T.mk_blind_rotate_3gen(accum, bk, bara)
+    assert FakeCtx.calls == int(np.count_nonzero(bara))
+    # the oracle mod-switches itself: hand it torus elements that decode to the same rotations
+    sh = 32 - int(np.log2(2 * N))
+    ext_a, ext_b, acc_ref, _ = ks.bootstrap_wo_keyswitch(oracle.EXACT_SCHOOLBOOK, int(mu), (bara.astype(np.int64) << sh).astype(np.int32),
+                                                         np.int32(int(barb) << sh), want_acc=True)
+    assert np.array_equal(accum.a, acc_ref)
+    u = T.rlwe_extract_sample_64(accum)
+    assert u.params.size == N and np.array_equal(u.a, ext_a) and int(u.b) == int(ext_b)
+    L = oracle.lib()
+    for v in (-1, -(1 << 32), (1 << 32) - 1, -(1 << 32) - 1, 1 << 61, -2 ** 63, (1 << 62) + (1 << 32) - 1):
+        assert int(T.t64tot32(np.int64(v))) == L.mko_t64tot32(v)
+
+
+def test_key_generation_formulas_with_the_exact_product_swapped_for_the_oracle(oracle, monkeypatch):
+    """tgsw_encrypt_3gen / BootstrapKeyPart_3gen / PublicKey / CommonPubKey_3gen of the host mirror (tgsw_3gen.jl:41-95,
+    mk_internals.jl:266-345) produce TGSW encryptions of the LWE key bits under the joint RLWE key -- checked with the secret keys
+    in hand, the GPU's exact product replaced here by the oracle's schoolbook (on the B200: tests/test_gpu_api.py)."""
+    import torus_fhe_b200 as T
+    from torus_fhe_b200 import tfhe3gen
+    from test_oracle_semantics import rlwe_phase, torus
+
+    def cpu_mul(small, big):
+        small, big = np.asarray(small, np.int64), np.asarray(big, np.int64)
+        shape = np.broadcast_shapes(small.shape, big.shape)
+        s = np.broadcast_to(small, shape).reshape(-1, shape[-1])
+        b = np.broadcast_to(big, shape).reshape(-1, shape[-1])
+        return np.stack([oracle.negacyclic_mul(s[i], b[i], oracle.EXACT_SCHOOLBOOK) for i in range(s.shape[0])]).reshape(shape)
+
+    monkeypatch.setattr(tfhe3gen, "negacyclic_mul", cpu_mul)
+    rng = np.random.default_rng(9)
+    params = T.SchemeParameters_3gen(6, 2.0 ** -18, 64, 1, False, 2, 7, 2.0 ** -40, 3, 3, 2.0 ** -18, 2)
+    tg, rl = T.tgsw_parameters(params), T.rlwe_parameters(params)
+    sk = [T.SecretKey_3gen(rng, params) for _ in range(2)]
+    rk = [T.RLweKey(rng, rl, True) for _ in range(2)]
+    crp = T.CRP_3gen(rng, tg, rl, True)
+    pk = [T.PublicKey(rng, rk[i], params.gsw_noise_stddev, crp, tg, 1) for i in range(2)]
+    cpk = T.CommonPubKey_3gen(pk, params, 2)
+    Z = (rk[0].key + rk[1].key).astype(np.int64)
+    assert set(np.unique(rk[0].key)) <= {-1, 0, 1}
+
+    def check(parts, m):
+        for q in range(tg.decomp_length):
+            g = np.int64(tg.gadget_values[q])
+            exp = np.zeros(64, np.int64)
+            exp[0] = m * g
+            assert np.abs(torus(rlwe_phase(np.stack([parts[3][q], parts[0][q]]), Z) - exp)).max() < 2.0 ** -30      # body-digit row
+            assert np.abs(torus(rlwe_phase(np.stack([parts[2][q], parts[1][q]]), Z) + (m * g) * Z)).max() < 2.0 ** -30   # mask-digit row
+
+    for m in (0, 1):
+        s = T.tgsw_encrypt_3gen(rng, m, params.gsw_noise_stddev, cpk, crp)
+        assert isinstance(s, T.TGswSample_3gen) and s.part_1.shape == (2, 64)
+        check([s.part_1, s.part_2, s.part_3, s.part_4], m)
+    bkp = T.BootstrapKeyPart_3gen(rng, sk[0].key, params.gsw_noise_stddev, crp, cpk, tg, rl, 1)
+    assert bkp.gsw_key.shape == (6, 4, 2, 64)
+    for j in range(6):
+        check(bkp.gsw_key[j], int(sk[0].key.key[j]))

@@ -414,6 +414,13 @@ class TransformedBootstrapKeyPart_3gen:
         self.gsw_key = bk.gsw_key
         self.key_size = bk.key_size
         self._engine = None
+        self._owner = None
+
+    @property
+    def tgsw_samples(self):
+        """The reference's view of this key, Array{TransformedTGswSample_3gen,1} (3gen_mk_internals.jl:47): element j is the TGSW
+        encryption of LWE key bit j.  (`gsw_key` itself stays the flat int64 [n][4][l][N] array the engine loads.)"""
+        return [TransformedTGswSample_3gen(self, j) for j in range(self.key_size)]
 
 
 class KeyswitchKey:
@@ -507,7 +514,18 @@ def engine_for(bk, ks, device=None):
     eng = Engine(_scheme_params_of(bk, ks), device=device)
     eng.load_keys([b.gsw_key for b in bk], [k.key for k in ks])
     bk[0]._engine = ks[0]._engine = (tag, eng)
+    _tag_parts(bk, eng)
     return eng
+
+
+def _tag_parts(bk, eng):
+    """Each key part remembers the engine that holds it and its party index: the per-element entry points of the reference
+    (tgsw_extern_mul_3gen, mk_mux_rotate_3gen, mk_ith_blind_rotate_3gen) receive one part or one of its TGSW samples, not the array."""
+    for i, b in enumerate(bk):
+        try:
+            b._owner = (eng, i)
+        except AttributeError:      # RemoteKeys and other stand-ins without the slot
+            pass
 
 
 class RemoteKeys:
@@ -529,6 +547,7 @@ class RemoteKeys:
 def attach_engine(bk, ks, eng):
     """Make `eng` (already holding these keys) the engine the gate API uses for (bk, ks)."""
     bk[0]._engine = ks[0]._engine = ((tuple(id(b) for b in bk), tuple(id(k) for k in ks)), eng)
+    _tag_parts(bk, eng)
     return eng
 
 
@@ -632,6 +651,169 @@ def mk_keyswitch_3gen(ks, sample):
     ext = np.concatenate([sample.a.reshape(-1, N), sample.b.reshape(-1, 1)], axis=1)
     oa, ob = eng.ctx.keyswitch_batch(ext)
     return MKLweSample(LweParams(n), oa.reshape(sample.b.shape + (k, n)), ob.reshape(sample.b.shape), 0.0)
+
+
+# ---------------------------------------------------------------------------------
+# the path's internal entry points, same names and arguments as the reference; each forwards to
+# the parity hook of the C ABI that runs that stage on the GPU
+# ---------------------------------------------------------------------------------
+class RLweSample:
+    """rlwe.jl:43-50 with mask_size = 1: `a` is int64 [.., 2, N]; a[.., 0, :] is the mask (the reference's accum.a[1]) and
+    a[.., 1, :] the body (accum.a[2]).  Leading dimensions are a batch."""
+    __slots__ = ("params", "a", "current_variance")
+
+    def __init__(self, params, a, current_variance=0.0):
+        self.params = params
+        self.a = np.asarray(a, dtype=np.int64)
+        self.current_variance = current_variance
+
+    def __add__(self, y):      # rlwe.jl:121-122
+        with np.errstate(over="ignore"):
+            return RLweSample(self.params, self.a + y.a, self.current_variance + y.current_variance)
+
+    def __sub__(self, y):      # rlwe.jl:125-126
+        with np.errstate(over="ignore"):
+            return RLweSample(self.params, self.a - y.a, self.current_variance + y.current_variance)
+
+
+def mul_by_monomial(x, s):
+    """X^s * x mod X^N + 1 for any integer s (DarkIntegers.mul_by_monomial on a polynomial, rlwe.jl:130-131 on a sample):
+    coefficient i moves to i + s, changing sign every time it wraps past N."""
+    if isinstance(x, RLweSample):
+        return RLweSample(x.params, mul_by_monomial(x.a, s), x.current_variance)
+    x = np.asarray(x, dtype=np.int64)
+    N = x.shape[-1]
+    s = int(s) % (2 * N)
+    with np.errstate(over="ignore"):
+        if s >= N:
+            x, s = -x, s - N
+        return np.concatenate([-x[..., N - s:], x[..., :N - s]], axis=-1) if s else x.copy()
+
+
+def rlwe_noiseless_trivial(mu, params):
+    """rlwe.jl:113-119: mask 0, body = the polynomial mu."""
+    mu = np.asarray(mu, dtype=np.int64)
+    return RLweSample(params, np.stack([np.zeros_like(mu), mu], axis=-2), 0.0)
+
+
+def t64tot32(d):
+    """numeric-functions.jl:109-111: trunc(Int32, Float64(d) / 2^32) -- toward zero, through Float64."""
+    q = np.trunc(np.asarray(d, dtype=np.int64).astype(np.float64) / 2.0 ** 32)
+    if np.any(q >= 2.0 ** 31):
+        raise OverflowError("InexactError: trunc(Int32, 2.147483648e9)")      # what the reference throws (probability ~2^-54)
+    return q.astype(np.int32)
+
+
+def rlwe_extract_sample_64(x):
+    """rlwe.jl:70-74 with polynomials.jl:69-72: a'_0 = mask_0, a'_j = -mask_{N-j}, b' = body_0, each through t64tot32."""
+    mask, body = x.a[..., 0, :], x.a[..., 1, :]
+    N = mask.shape[-1]
+    with np.errstate(over="ignore"):
+        rev = np.concatenate([mask[..., :1], -mask[..., :0:-1]], axis=-1)
+    return LweSample(LweParams(N), t64tot32(rev), t64tot32(body[..., 0]), 0.0)
+
+
+class TGswSample_3gen:
+    """tgsw_3gen.jl:3-20: part_1..part_4, each l integer polynomials (int64 [l][N])."""
+
+    def __init__(self, tgsw_params, rlwe_params, parts):
+        self.tgsw_params, self.rlwe_params = tgsw_params, rlwe_params
+        self.parts = np.asarray(parts, dtype=np.int64)       # [4][l][N]
+
+    part_1 = property(lambda self: self.parts[0])
+    part_2 = property(lambda self: self.parts[1])
+    part_3 = property(lambda self: self.parts[2])
+    part_4 = property(lambda self: self.parts[3])
+
+
+def tgsw_encrypt_3gen(rng, message, alpha, common_pubkey, crp_a, negative_random=True, wo_FFT=0):
+    """tgsw_3gen.jl:41-95, same positional arguments: part_1 = r1 B + m g + e, part_4 = r1 a + e (the row pair of a body digit),
+    part_2 = r2 B + e, part_3 = r2 a + m g + e (of a mask digit); r1, r2 sparse ternary (uniform bits when negative_random is
+    false), `+ m g` on the constant coefficient.  As in the reference the noise is params.gsw_noise_stddev of the common public key's
+    parameter set (`alpha` is accepted and not read, :64-67), and both values of wo_FFT mean the same here: the products are exact,
+    on the GPU (mktfhe_negacyclic_mul_batch)."""
+    params = common_pubkey.params
+    tgsw_params, rlwe_params = tgsw_parameters(params), rlwe_parameters(params)
+    l, N = tgsw_params.decomp_length, rlwe_params.polynomial_degree
+    draw = rand_negative_binary64 if negative_random else (lambda r, n: r.integers(0, 2, size=n, dtype=np.int64))
+    r1 = draw(rng, l * N).reshape(l, N)
+    r2 = draw(rng, l * N).reshape(l, N)
+    parts = rand_gaussian_torus64(rng, 0, params.gsw_noise_stddev, 4 * l * N).reshape(4, l, N)
+    mg = np.int64(message) * np.array(tgsw_params.gadget_values, dtype=np.uint64).view(np.int64)
+    with np.errstate(over="ignore"):
+        parts[0] += negacyclic_mul(r1, common_pubkey.b)
+        parts[1] += negacyclic_mul(r2, common_pubkey.b)
+        parts[2] += negacyclic_mul(r2, crp_a.a)
+        parts[3] += negacyclic_mul(r1, crp_a.a)
+        parts[0, :, 0] += mg
+        parts[2, :, 0] += mg
+    return TGswSample_3gen(tgsw_params, rlwe_params, parts)
+
+
+class TransformedTGswSample_3gen:
+    """tgsw_3gen.jl:23-39: element j of a party's bootstrapping key.  The reference holds its FFTs; here it is a handle on the
+    element already transformed (exact NTT) and resident on the GPU of the engine that loaded the key part."""
+
+    def __init__(self, part, j):
+        if not 0 <= j < part.key_size:
+            raise IndexError(f"key element {j} outside 0..{part.key_size - 1}")
+        self.part, self.j = part, int(j)
+        self.tgsw_params, self.rlwe_params = part.tgsw_params, part.rlwe_params
+
+    part_1 = property(lambda self: self.part.gsw_key[self.j, 0])
+    part_2 = property(lambda self: self.part.gsw_key[self.j, 1])
+    part_3 = property(lambda self: self.part.gsw_key[self.j, 2])
+    part_4 = property(lambda self: self.part.gsw_key[self.j, 3])
+
+    def _locate(self):
+        owner = getattr(self.part, "_owner", None)
+        if owner is None:
+            raise RuntimeError("no GPU engine holds this bootstrapping key part yet: call engine_for(bk, ks) (or any gate) with the key pair first")
+        eng, party = owner
+        return eng, party * eng.params.lwe_size + self.j
+
+
+def tgsw_extern_mul_3gen(accum, sample):
+    """tgsw_3gen.jl:102-113 on the GPU (mktfhe_extprod_batch): body' = sum_q dec(body)_q part_1[q] + dec(mask)_q part_2[q],
+    mask' = sum_q dec(body)_q part_4[q] + dec(mask)_q part_3[q], exact mod 2^64.  `accum` may carry a batch."""
+    eng, elem = sample._locate()
+    N = eng.params.rlwe_polynomial_degree
+    if accum.a.shape[-2:] != (2, N):
+        raise ValueError(f"accumulator must be [.., 2, {N}]")
+    acc = accum.a.reshape(-1, 2, N)
+    out = eng.ctx.extprod_batch(np.full(acc.shape[0], elem, np.int32), acc)
+    return RLweSample(accum.params, out.reshape(accum.a.shape), 0.0)
+
+
+def mk_mux_rotate_3gen(accum, bki, barai):
+    """3gen_mk_internals.jl:59-62: accum + ExtProd(X^barai accum - accum, bki)."""
+    return accum + tgsw_extern_mul_3gen(mul_by_monomial(accum, int(barai)) - accum, bki)
+
+
+def mk_ith_blind_rotate_3gen(acc, gsw_key, bara):
+    """3gen_mk_internals.jl:66-75: one party's n steps; zero rotations are skipped.  `gsw_key` is the party's
+    `tgsw_samples` (or the key part itself); `bara` int32 [n]."""
+    if isinstance(gsw_key, TransformedBootstrapKeyPart_3gen):
+        gsw_key = gsw_key.tgsw_samples
+    for i, barai in enumerate(np.asarray(bara).reshape(-1)):
+        if barai != 0:
+            acc = mk_mux_rotate_3gen(acc, gsw_key[i], barai)
+    return acc
+
+
+def mk_blind_rotate_3gen(accum, bk, bara):
+    """3gen_mk_internals.jl:78-84: parties outer, coefficients inner.  `bara` is int32 [k][n] (the reference's (n, parties)
+    column-major array).  One external-product launch per step: the stage-by-stage form of the path, for parity work -- gates and
+    bootstraps run the whole loop inside one kernel (mk_bootstrap_3gen)."""
+    bara = np.asarray(bara)
+    for i in range(len(bk)):
+        accum = mk_ith_blind_rotate_3gen(accum, bk[i], bara[i])
+    return accum
+
+
+def xor_3gen_gpu(bk, ks, x, y):
+    """gpu_circuits.jl:27-36 (the reference's function builds the linear part and stops); finished here."""
+    return mk_gate_xor_3gen(bk, ks, x, y)
 
 
 # gates, 3gen_mk_gates.jl:8-150
