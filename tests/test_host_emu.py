@@ -37,3 +37,14 @@ def test_ntt2048_on_gpu(tmp_path):
                            os.path.join(ROOT, "tests", "host_emu", "ntt2048_gpu.cu"), "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ntt2048_gpu: OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_f64_channel_prototype(tmp_path):
+    """Round-2 candidate: one RNS channel carried in doubles so its butterflies leave the binding IMAD pipe.
+    Host emulation of tools/f64_channel/ntt_f64.cuh: same residues as the u32 channel position by position, exact three-prime
+    product with the unchanged Garner lift, all intermediates exact integers far below 2^53.  Not linked into the library."""
+    exe = str(tmp_path / "f64_emu")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "torus-fhe_b200", "csrc"),
+                           "-I", os.path.join(ROOT, "tools", "f64_channel"), os.path.join(ROOT, "tools", "f64_channel", "emu.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "f64_emu: OK" in out.stdout, out.stdout + out.stderr
