@@ -8,9 +8,9 @@
 //   2. both in every warp, interleaved;
 //   3. warp-specialised: IMAD warps and DFMA warps resident on the same SM (the shape the kernel would use: warp = (prime, output));
 //   4. a Harvey butterfly in u32 next to the same butterfly in doubles, alone and side by side.
-// Ceiling known before measuring: the scheduler issues one instruction per clock; a u32 butterfly is 6 instructions for 8 fmaheavy cycles,
-// the double butterfly 8 instructions for 16 FP64 cycles, so 2 integer warps + 1 FP64 warp per scheduler are issue-bound at 20 cycles where
-// 3 integer warps are pipe-bound at 24: at most 1.2x in the butterfly phases (mode 6 below measures exactly this mix).
+// Ceiling known before measuring: the scheduler issues one instruction per clock; a u32 butterfly is 5 (forward) or 6 (inverse) instructions for 8 fmaheavy
+// cycles, the double butterfly 8 instructions for 16 FP64 cycles, so 2 integer warps + 1 FP64 warp per scheduler are issue-bound at 18-20 cycles
+// where 3 integer warps are pipe-bound at 24: at most 1.2-1.33x in the butterfly phases (mode 6 below measures exactly this mix).
 // Decision rule (written before measuring): go if (3) sustains >= 1.6x the thread-ops of IMAD alone AND the double butterfly costs
 // <= 2.2x the u32 butterfly in isolation (then a 4 + 2 warp split per gate balances the two pipes).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o fp64_pipe_ubench fp64_pipe_ubench.cu ; run on the B200.
