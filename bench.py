@@ -349,6 +349,8 @@ def run_circuit(args):
     ca, cb = T.mk_int_encrypt_3gen(rng, secret_keys, a, W), T.mk_int_encrypt_3gen(rng, secret_keys, b, W)
     zero = T.mk_encrypt_3gen(rng, secret_keys, np.zeros(I, bool))
     eng = T.engine_for(bk, ks)
+    if args.workload == "less":
+        return run_comparator(args, T, rng, secret_keys, bk, ks, eng, a, b, ca, cb)
     T.mk_add_3gen_v2(bk, ks, [c[:8] for c in ca], [c[:8] for c in cb], zero[:8], W)      # warm-up (small)
     l0 = eng.ctx.launch_count()
     t0 = time.perf_counter()
@@ -364,6 +366,26 @@ def run_circuit(args):
                               "Float64-FFT restatement), i.e. ~3e-4 failures per gate fed by bootstrapped inputs: a few % of 16-bit sums differ; the "
                               "GPU path is bit-exact with the exact oracle gate by gate (tests/test_gpu_parity.py)",
                       "config": {"workload": f"mk_add_3gen_v2 WIDTH={W} x {I} instances, host-resident ciphertexts between levels"}}))
+    return 0
+
+
+def run_comparator(args, T, rng, secret_keys, bk, ks, eng, a, b, ca, cb):
+    """BASELINE configs[3], the comparator half: mk_less_3gen (3gen_mk_gates.jl:247-255) = sign bit of a - b through mk_sub_3gen:
+    WIDTH XOR gates (the inversion of b) in one launch, then the ripple-carry adder's 1 + 2*WIDTH levels; 6*WIDTH gates per instance."""
+    W, I = args.width, args.instances
+    one = T.mk_encrypt_3gen(rng, secret_keys, np.ones(I, bool))
+    T.mk_less_3gen(bk, ks, [c[:8] for c in ca], [c[:8] for c in cb], one[:8], W)          # warm-up (small)
+    l0 = eng.ctx.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = T.mk_less_3gen(bk, ks, ca, cb, one, W)
+    dt = (time.perf_counter() - t0) / args.steps
+    got = np.asarray(T.mk_decrypt_3gen(secret_keys, res))
+    print(json.dumps({"metric": f"{W}-bit MK less-than circuits/sec (2-party, {I} instances batched per level)", "value": I / dt, "unit": "circuits/s",
+                      "gates_per_s": 6 * W * I / dt, "levels": 2 + 2 * W, "launches_per_circuit_batch": (eng.ctx.launch_count() - l0) // args.steps,
+                      "instances_correct_frac": float(np.mean(got == (a < b))), "n_gpus": 1,
+                      "note": "same per-gate failure rate of the scheme's default parameters as the adder line",
+                      "config": {"workload": f"mk_less_3gen WIDTH={W} x {I} instances, host-resident ciphertexts between levels"}}))
     return 0
 
 
@@ -460,15 +482,15 @@ def main():
                     help="parameter set (BASELINE configs[2]: 4 and 8; 16 = the first N = 2048 set, one gate per SM: use --gates 148 or a multiple)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="nand", choices=["nand", "adder", "conv"],
-                    help="nand = the headline metric; adder = BASELINE configs[3]; conv = BASELINE configs[4]")
+    ap.add_argument("--workload", default="nand", choices=["nand", "adder", "less", "conv"],
+                    help="nand = the headline metric; adder / less = BASELINE configs[3] (adder, comparator); conv = BASELINE configs[4]")
     ap.add_argument("--width", type=int, default=None, help="bits per encrypted integer (adder: 16, conv: 4)")
     ap.add_argument("--image", type=int, default=28, help="conv: input height = width")
     ap.add_argument("--instances", type=int, default=1024)
     args = ap.parse_args()
     if args.width is None:
         args.width = 4 if args.workload == "conv" else 16
-    if args.workload == "adder":
+    if args.workload in ("adder", "less"):
         sys.exit(run_circuit(args))
     if args.workload == "conv":
         sys.exit(run_conv(args))
