@@ -165,10 +165,7 @@ def test_integration_doc_names_only_existing_symbols():
     assert used and used <= set(decls), used - set(decls)
 
 
-def test_julia_shim_blocks_and_brackets_balance():
-    """No Julia here to parse the shim: at least every block opener outside brackets has its `end`, brackets nest, strings close,
-    and every exported name is defined."""
-    text = open(os.path.join(ROOT, "julia", "TFHE_B200.jl")).read()
+def _julia_balance(text):
     # strip docstrings / strings / comments
     text = re.sub(r'"""(.*?)"""', '""', text, flags=re.S)
     text = re.sub(r'"(?:\\.|[^"\\\n])*"', '""', text)
@@ -188,6 +185,16 @@ def test_julia_shim_blocks_and_brackets_balance():
                 blocks -= 1
                 assert blocks >= 0, "`end` without an opener"
     assert not stack and blocks == 0, (stack, blocks)
+    return text
+
+
+def test_julia_files_blocks_and_brackets_balance():
+    """No Julia here to parse the files: at least every block opener outside brackets has its `end`, brackets nest, strings close,
+    every exported name of the shim is defined, and the fixture script only calls writer functions the shim defines."""
+    text = _julia_balance(open(os.path.join(ROOT, "julia", "TFHE_B200.jl")).read())
+    dump = _julia_balance(open(os.path.join(ROOT, "julia", "dump_fixture.jl")).read())
+    for name in set(re.findall(r"TFHE_B200\.([A-Za-z_0-9]+)", dump)):
+        assert re.search(rf"(function |struct ){name}\b", text), f"dump_fixture.jl uses TFHE_B200.{name}, which the shim does not define"
     exported = re.search(r"\nexport (.*?)\n\n", text + "\n\n", flags=re.S).group(1)
     for name in re.findall(r"[A-Za-z_][A-Za-z_0-9]*", exported):
         assert re.search(rf"(function |struct |^|\(:){name}\b", text, flags=re.M), f"exported {name} is not defined"
