@@ -218,6 +218,40 @@ int main() {
             if (got != ref[i]) { fails++; printf("FAIL product trial=%d i=%d got=%llx ref=%llx\n", trial, i, (unsigned long long)got, (unsigned long long)ref[i]); break; }
         }
     }
+    // 5. feasibility of a 47-bit prime in the same arithmetic (the N = 2048 sets: one such channel would replace two u32 channels):
+    //    operands larger than an 11-stage forward pass lets them grow (|y| < 12 p; growth is < 0.54 p per stage), product checked against 128-bit
+    //    integers.  The hard limit is the quotient: |y w / p| must stay below 2^51 for the 1.5 * 2^52 rounding trick, i.e. |y| < 16 p at 47 bits.
+    {
+        auto mulmod128 = [](u64 a, u64 b, u64 m) { return (u64)((unsigned __int128)a * b % m); };
+        auto powmod128 = [&](u64 a, u64 e, u64 m) { u64 r = 1; while (e) { if (e & 1) r = mulmod128(r, a, m); a = mulmod128(a, a, m); e >>= 1; } return r; };
+        auto is_prime = [&](u64 n) {
+            for (u64 a : {2ull, 3ull, 5ull, 7ull, 11ull, 13ull, 17ull, 19ull, 23ull, 29ull, 31ull, 37ull}) {
+                if (n % a == 0) return n == a;
+                u64 d = n - 1; int r = 0;
+                while (!(d & 1)) { d >>= 1; r++; }
+                u64 x = powmod128(a, d, n);
+                if (x == 1 || x == n - 1) continue;
+                bool comp = true;
+                for (int i = 1; i < r && comp; i++) { x = mulmod128(x, x, n); if (x == n - 1) comp = false; }
+                if (comp) return false;
+            }
+            return true;
+        };
+        u64 p47 = 0;
+        for (u64 c = ((u64)1 << 47) / 4096; c > 0 && !p47; c--) if (is_prime(c * 4096 + 1)) p47 = c * 4096 + 1;   // largest p = 1 (mod 4096) below 2^47
+        rnsf::Mod M47{(double)p47, 1.0 / (double)p47};
+        double worst = 0;
+        for (int it = 0; it < 400000 && !fails; it++) {
+            const int64_t y = (int64_t)(rnd() % (24 * p47)) - (int64_t)(12 * p47);
+            const u64 w = rnd() % p47;
+            const double t = rnsf::mulmod((double)y, (double)w, M47);
+            const __int128 diff = (__int128)y * (__int128)w - (__int128)(int64_t)t;
+            if (t != std::nearbyint(t) || diff % (__int128)p47 != 0) { fails++; printf("FAIL 47-bit mulmod y=%lld w=%llu\n", (long long)y, (unsigned long long)w); }
+            if (std::fabs(t) / (double)p47 > worst) worst = std::fabs(t) / (double)p47;
+        }
+        printf("47-bit prime %llu: mulmod exact for |y| < 12 p, |result| <= %.3f p\n", (unsigned long long)p47, worst);
+        if (worst > 1.6) { fails++; printf("FAIL 47-bit range\n"); }
+    }
     printf("largest intermediate: 2^%.1f (exact integers need < 2^53)\n", std::log2(max_abs));
     if (max_abs >= 9007199254740992.0 / 256) { fails++; printf("FAIL headroom\n"); }
     printf(fails ? "f64_emu: %d FAILURES\n" : "f64_emu: OK\n", fails);

@@ -36,7 +36,8 @@ MK_HD double fma_(double a, double b, double c) {
 #endif
 }
 
-// y * w mod p as an exact integer in about (-p/2, p/2); y, w exact integers with |y * w| < 2^100
+// y * w mod p as an exact integer in about (-p/2, p/2); y, w exact integers with |y * w / p| < 2^51 (the quotient goes through the
+// 1.5 * 2^52 rounding trick): any |y| < 2^51 for a residue w < p
 MK_HD double mulmod(double y, double w, const Mod& m) {
     const double h = y * w;
     const double l = fma_(y, w, -h);
