@@ -15,3 +15,4 @@ for w in adder less; do
   done
 done
 python bench.py > $O/bench_r2_a.json 2> $O/bench_r2_a.err; echo "bench rc=$?"; cut -c1-300 $O/bench_r2_a.json
+for p in 4 8; do python bench.py --parties $p --steps 3 --warmup 3 > $O/bench_r2_a_${p}party.json 2> $O/bench_r2_a_${p}party.err; cut -c1-200 $O/bench_r2_a_${p}party.json; done
