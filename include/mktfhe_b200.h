@@ -13,9 +13,13 @@
  *  - every function returns 0 on success or a negative MKTFHE_E* code; the
  *    message is available from mktfhe_last_error().  No exceptions or aborts
  *    cross this boundary.
- *  - one context = one GPU, used by one host thread at a time.  Multi-GPU = one
- *    context per process/rank (torch.distributed / torchrun), gates sharded by
- *    the host, keys broadcast once (mktfhe_key_buffers + NCCL).
+ *  - a context is used by one host thread at a time.  mktfhe_create binds it to
+ *    one GPU; mktfhe_create_multi spans several GPUs of the box behind the same
+ *    handle: keys are loaded once and broadcast GPU to GPU inside
+ *    mktfhe_finalize_keys, and every host-pointer batch call shards [G]
+ *    contiguously over the GPUs (one internal host thread and stream per GPU, no
+ *    exchange on the data path).  The one-context-per-rank form (torchrun,
+ *    mktfhe_key_buffers + NCCL) remains available.
  *  - plain (non-_dev) entry points take HOST pointers; the caller owns them and
  *    nothing is retained after return except uploaded keys (copied).
  *  - *_dev entry points take DEVICE pointers valid on the context's GPU and a
@@ -23,6 +27,9 @@
  *    asynchronous with respect to the host.  The context's own stream is
  *    non-blocking: with NULL the caller must make sure the operands are
  *    complete (they are not ordered after work on the legacy default stream).
+ *    All calls on one context share its scratch buffers and timing events, so
+ *    they must be stream-ordered with each other (same stream, or ordered by
+ *    events): two *_dev calls in flight on unordered streams race.
  *  - ciphertext layout: MKLweSample (mk_internals.jl:23-37) `a::Array{Int32,2}`
  *    of shape (n, k), column-major == int32 [k][n] per sample; batches are
  *    int32 a[G][k][n], int32 b[G].
@@ -71,7 +78,25 @@ typedef struct mktfhe_ctx mktfhe_ctx;
 
 /* -- lifetime ----------------------------------------------------------- */
 int mktfhe_create(const mktfhe_params *params, int device, mktfhe_ctx **out);
+/* One context spanning n_devices GPUs of this box (the gate API of 3gen_mk_gates.jl has no notion of
+ * devices, so this is what lets `mk_gate_nand_3gen(bk, ks, xs, ys)` on a vector use the whole box).  devices = NULL means
+ * GPUs 0 .. n_devices-1, n_devices = 0 means every visible GPU; a device may be listed more than once (replicas sharing a
+ * GPU: a test aid).  Keys are loaded into the first device and broadcast in mktfhe_finalize_keys -- a binomial tree of
+ * cudaMemcpyPeerAsync over NVLink, or one grouped ncclBroadcast per key buffer when MKTFHE_B200_BCAST=nccl (libnccl.so.2
+ * is bound with dlopen at that point; no link-time dependency).  With n_devices = 1 the result is a plain context. */
+int mktfhe_create_multi(const mktfhe_params *params, int n_devices, const int *devices, mktfhe_ctx **out);
 void mktfhe_destroy(mktfhe_ctx *ctx);
+/* GPUs a context spans (1 for mktfhe_create) */
+int mktfhe_device_count(const mktfhe_ctx *ctx);
+/* replica i of a multi-device context as a single-device context (i = 0: ctx itself) and its CUDA device ordinal, for the
+ * *_dev entry points, which take pointers into one GPU; the replica is owned by ctx (do not destroy it). */
+int mktfhe_device_ctx(mktfhe_ctx *ctx, int i, mktfhe_ctx **replica, int *device);
+/* the contiguous slice [lo, hi) of a batch of G that replica i processes in the host-pointer calls */
+int mktfhe_shard_bounds(const mktfhe_ctx *ctx, size_t G, int i, size_t *lo, size_t *hi);
+/* page-lock / release a caller buffer (cudaHostRegister, portable): with pinned ciphertext buffers the per-GPU copies of a
+ * multi-device batch call are true DMA and overlap; pageable memory works but is staged by the driver. */
+int mktfhe_pin_host(void *p, size_t bytes);
+int mktfhe_unpin_host(void *p);
 /* message of the last failing call on ctx (ctx == NULL: last mktfhe_create failure) */
 const char *mktfhe_last_error(const mktfhe_ctx *ctx);
 
@@ -137,15 +162,21 @@ int mktfhe_blind_rotate_batch(mktfhe_ctx *ctx, int64_t mu, size_t G, const int32
 /* mk_keyswitch_3gen (mk_internals.jl:730-744) on ext = int32 [G][N+1] */
 int mktfhe_keyswitch_batch(mktfhe_ctx *ctx, size_t G, const int32_t *ext, int32_t *a_out, int32_t *b_out);
 /* exact negacyclic products c = a * b mod (X^N+1, 2^64) through the same three-prime NTT + CRT:
- * a = int64 [G][N] with |a_i| <= 2^8 ("digit" / ternary operand: N * 2^8 * 2^63 stays inside the CRT range),
+ * a = int64 [G][N] with |a_i| <= 2^8 at N = 1024, <= 2^25 at N = 2048 ("digit" / ternary operand: N * |a| * 2^63 stays inside
+ * the CRT range; larger entries are rejected with MKTFHE_EINVAL),
  * b = int64 [G][N].  Also the primitive of key generation (tgsw_3gen.jl:85-88 uses DarkIntegers' exact `*`). */
 int mktfhe_negacyclic_mul_batch(mktfhe_ctx *ctx, size_t G, const int64_t *a, const int64_t *b, int64_t *c);
 
 /* -- introspection ---------------------------------------------------------- */
-/* kernels launched by this context so far */
+/* hash of the kernel sources this library was built from (the ncu captures under profiles/ record the id they apply to) */
+const char *mktfhe_build_id(void);
+/* one-line JSON description of the context: build id, devices, how the keys were broadcast, whether the most recent
+ * bootstrap ran the key switch as the blind-rotate kernel's epilogue, gates per CTA, key bytes */
+int mktfhe_describe(const mktfhe_ctx *ctx, char *buf, size_t cap);
+/* kernels launched by this context so far (all devices) */
 uint64_t mktfhe_launch_count(const mktfhe_ctx *ctx);
 /* device time (ms, CUDA events on the launching stream) of the blind-rotate and
- * key-switch kernels of the most recent batch call; blocks until they finished */
+ * key-switch kernels of the most recent batch call (multi-device: the slowest GPU); blocks until they finished */
 int mktfhe_last_kernel_ms(mktfhe_ctx *ctx, float *blind_rotate_ms, float *keyswitch_ms);
 /* bytes of the streamed bootstrapping key read per gate (three u32 residues per coefficient) and of ksk rows gathered per gate */
 int mktfhe_algorithmic_bytes(const mktfhe_ctx *ctx, double *bsk_bytes_per_gate, double *ksk_bytes_per_gate);

@@ -70,25 +70,52 @@ function flatten_ksk(ks::KeyswitchKey)
     rows
 end
 
-function engine_for(bk::Array{TransformedBootstrapKeyPart_3gen, 1}, ks::Array{KeyswitchKey, 1}; device::Integer = 0)
+"""GPUs an engine spans when the caller does not say: ENV["MKTFHE_B200_DEVICES"] = "all" | "0,1,2,3" | unset (GPU 0 only)."""
+function default_devices()
+    v = get(ENV, "MKTFHE_B200_DEVICES", "")
+    v == "" && return Cint[0]
+    v == "all" && return Cint[]                  # empty = every visible GPU (n_devices = 0)
+    Cint[parse(Cint, x) for x in split(v, ",")]
+end
+
+"""The engine holding (bk, ks): created on first use.  `devices` lists the GPUs it spans (one context behind the whole gate
+API: keys are loaded once and broadcast GPU to GPU inside mktfhe_finalize_keys, every batched gate call is sharded over
+them by the library); an empty list means every visible GPU."""
+function engine_for(bk::Array{TransformedBootstrapKeyPart_3gen, 1}, ks::Array{KeyswitchKey, 1}; devices::Vector{Cint} = default_devices())
     haskey(ENGINES, bk) && return ENGINES[bk]
     bk[1].rlwe_params.is32 && error("rlwe_is32 = true is not part of the 3gen path")
     prm = CParams(bk[1].key_size, bk[1].rlwe_params.polynomial_degree, length(bk), bk[1].tgsw_params.decomp_length,
                   bk[1].tgsw_params.log2_base, ks[1].params.decomp_length, ks[1].params.log2_base, 0)
     out = Ref{Ptr{Cvoid}}(C_NULL)
-    rc = ccall((:mktfhe_create, LIB), Cint, (Ref{CParams}, Cint, Ref{Ptr{Cvoid}}), prm, device, out)
-    rc == 0 || error("mktfhe_create: " * unsafe_string(ccall((:mktfhe_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    rc = ccall((:mktfhe_create_multi, LIB), Cint, (Ref{CParams}, Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), prm, length(devices),
+               isempty(devices) ? Ptr{Cint}(C_NULL) : pointer(devices), out)
+    rc == 0 || error("mktfhe_create_multi: " * unsafe_string(ccall((:mktfhe_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
     ctx = out[]
     for p in 1:length(bk)
         check(ctx, ccall((:mktfhe_load_bsk, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}), ctx, p - 1, bk[p].gsw_key))
         check(ctx, ccall((:mktfhe_load_ksk, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int32}), ctx, p - 1, flatten_ksk(ks[p])))
     end
-    check(ctx, ccall((:mktfhe_finalize_keys, LIB), Cint, (Ptr{Cvoid},), ctx))
+    check(ctx, ccall((:mktfhe_finalize_keys, LIB), Cint, (Ptr{Cvoid},), ctx))      # includes the key broadcast to the other GPUs
     e = Engine(ctx, prm)
-    finalizer(x -> ccall((:mktfhe_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.ctx), e)
     for p in 1:length(bk); PART_OWNER[bk[p].gsw_key] = (e, p - 1); end
     ENGINES_BY_KS[ks] = e
     ENGINES[bk] = e
+end
+
+"""GPUs the engine of (bk, ks) spans."""
+device_count(bk, ks) = Int(ccall((:mktfhe_device_count, LIB), Cint, (Ptr{Cvoid},), engine_for(bk, ks).ctx))
+
+"""Frees the device key replicas of (bk, ks) (about 200 MB per GPU at 2 parties, gigabytes for the N = 2048 sets).  The lookup
+tables above hold every engine strongly -- the gate API must find it from `bk` alone, at any time -- so engines live until
+released here."""
+function release!(bk::Array{TransformedBootstrapKeyPart_3gen, 1}, ks::Array{KeyswitchKey, 1})
+    haskey(ENGINES, bk) || return nothing
+    e = ENGINES[bk]
+    delete!(ENGINES, bk); delete!(ENGINES_BY_KS, ks)
+    for p in 1:length(bk); delete!(PART_OWNER, bk[p].gsw_key); end
+    e.ctx == C_NULL || ccall((:mktfhe_destroy, LIB), Cvoid, (Ptr{Cvoid},), e.ctx)
+    e.ctx = C_NULL
+    nothing
 end
 
 # entry points of the reference that receive only one of (bk, ks): the GPU context holds both, so the pair must have been seen before
@@ -327,6 +354,7 @@ export TransformedBootstrapKeyPart_3gen, mk_bootstrap_3gen, mk_bootstrap_wo_keys
        mk_gate_xor_3gen, mk_gate_3and_3gen, mk_gate_not_3gen, mk_gate_mux_3gen, mk_gate_nand_3gen_wb, mk_gate_or_3gen_wb, mk_gate_and_3gen_wb,
        mk_gate_xor_3gen_wb, gate_level, mk_copy_3gen, mk_int_add_with_carry_3gen,
        mk_add_3gen, mk_add_3gen_v2, mk_inv_3gen, mk_sub_3gen, mk_less_3gen, mk_grt_3gen, mk_leq_3gen, mk_geq_3gen, write_keys, write_ciphertexts,
-       TransformedTGswSample_3gen, tgsw_samples, tgsw_extern_mul_3gen, mk_mux_rotate_3gen, mk_ith_blind_rotate_3gen, mk_blind_rotate_3gen
+       TransformedTGswSample_3gen, tgsw_samples, tgsw_extern_mul_3gen, mk_mux_rotate_3gen, mk_ith_blind_rotate_3gen, mk_blind_rotate_3gen,
+       release!, device_count, default_devices
 
 end # module

@@ -12,7 +12,7 @@
 
 #define CHECK(cond, ...) do { if (!(cond)) { fprintf(stderr, "FAIL %s:%d: ", __FILE__, __LINE__); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); return 1; } } while (0)
 
-int main(void) {
+int main(int argc, char **argv) {
     /* reduced LWE dimension so that CPU key generation takes a second; ring and gadget as the 2-party default (mk_api.jl:32-38) */
     mko_params op = {64, 1024, 2, 2, 7, 3, 3, 0, 1.0 / 11000.0, 5.7e-10, 1.0 / 11000.0};
     mko_keyset *ks = mko_keygen(&op, 7, 8);
@@ -73,6 +73,74 @@ int main(void) {
     float br_ms = 0, ks_ms = 0;
     CHECK(mktfhe_last_kernel_ms(ctx, &br_ms, &ks_ms) == MKTFHE_OK && br_ms > 0, "kernel timing");
     printf("cabi_direct: OK (5 gates x %d samples bit-exact vs the oracle; last blind rotate %.3f ms)\n", G, br_ms);
+
+    /* ---- one context spanning several GPUs (mktfhe_create_multi): same keys loaded once, broadcast inside finalize, batches
+     * sharded by the library.  Every visible GPU is used; on a one-GPU box the device is listed twice (two replicas sharing
+     * it), which runs the same broadcast and sharding code.  Results must equal the single-GPU context's byte for byte. */
+    {
+        int devs[64], nd = argc > 1 ? atoi(argv[1]) : 0;
+        mktfhe_ctx *probe = NULL;
+        CHECK(mktfhe_create_multi(&gp, 0, NULL, &probe) == MKTFHE_OK, "create_multi(all): %s", mktfhe_last_error(NULL));
+        const int visible = mktfhe_device_count(probe);
+        mktfhe_destroy(probe);
+        if (nd <= 0) nd = visible > 1 ? visible : 2;
+        for (int i = 0; i < nd; i++) devs[i] = i % visible;
+        mktfhe_ctx *mc = NULL;
+        CHECK(mktfhe_create_multi(&gp, nd, devs, &mc) == MKTFHE_OK && mktfhe_device_count(mc) == nd, "create_multi: %s", mktfhe_last_error(NULL));
+        for (int p = 0; p < op.k; p++) {
+            CHECK(mktfhe_load_bsk(mc, p, mko_bsk(ks) + p * bsk_party) == MKTFHE_OK, "multi load_bsk: %s", mktfhe_last_error(mc));
+            CHECK(mktfhe_load_ksk(mc, p, mko_ksk(ks) + p * ksk_party) == MKTFHE_OK, "multi load_ksk: %s", mktfhe_last_error(mc));
+        }
+        CHECK(mktfhe_gate_batch(mc, MKTFHE_GATE_NAND, G, xa, xb, ya, yb, NULL, NULL, oa, ob) == MKTFHE_ESTATE, "multi: gates before finalize");
+        CHECK(mktfhe_finalize_keys(mc) == MKTFHE_OK, "multi finalize (key broadcast): %s", mktfhe_last_error(mc));
+        /* a batch that does not divide evenly, so that slices differ in size; built by repeating the G samples */
+        enum { GM = 37 };
+        const size_t kn = (size_t)op.k * op.n;
+        int32_t *mxa = malloc(GM * kn * 4), *mya = malloc(GM * kn * 4), *mza = malloc(GM * kn * 4), *moa = malloc(GM * kn * 4), *mra = malloc(GM * kn * 4);
+        int32_t mxb[GM], myb[GM], mzb[GM], mob[GM], mrb[GM], ids[GM];
+        for (int g = 0; g < GM; g++) {
+            const int s = (g * 5 + 3) % G;
+            memcpy(mxa + g * kn, xa + s * kn, kn * 4); memcpy(mya + g * kn, ya + ((s + 1) % G) * kn, kn * 4); memcpy(mza + g * kn, za + s * kn, kn * 4);
+            mxb[g] = xb[s]; myb[g] = yb[(s + 1) % G]; mzb[g] = zb[s]; ids[g] = g % 5;
+        }
+        size_t covered = 0;
+        for (int i = 0; i < nd; i++) {
+            size_t lo, hi;
+            CHECK(mktfhe_shard_bounds(mc, GM, i, &lo, &hi) == MKTFHE_OK && lo == covered && hi >= lo, "shard_bounds");
+            covered = hi;
+        }
+        CHECK(covered == GM, "shards must cover the batch");
+        for (int gate = MKTFHE_GATE_NAND; gate <= MKTFHE_GATE_AND3; gate++) {
+            const int three = gate == MKTFHE_GATE_AND3;
+            CHECK(mktfhe_gate_batch(mc, gate, GM, mxa, mxb, mya, myb, three ? mza : NULL, three ? mzb : NULL, moa, mob) == MKTFHE_OK, "multi gate %d: %s", gate, mktfhe_last_error(mc));
+            CHECK(mktfhe_gate_batch(ctx, gate, GM, mxa, mxb, mya, myb, three ? mza : NULL, three ? mzb : NULL, mra, mrb) == MKTFHE_OK, "single gate %d: %s", gate, mktfhe_last_error(ctx));
+            CHECK(memcmp(moa, mra, GM * kn * 4) == 0 && memcmp(mob, mrb, sizeof mob) == 0, "gate %d: %d-device result differs from the 1-device result", gate, nd);
+        }
+        CHECK(mktfhe_gate_batch_mixed(mc, GM, ids, mxa, mxb, mya, myb, mza, mzb, moa, mob) == MKTFHE_OK, "multi mixed: %s", mktfhe_last_error(mc));
+        CHECK(mktfhe_gate_batch_mixed(ctx, GM, ids, mxa, mxb, mya, myb, mza, mzb, mra, mrb) == MKTFHE_OK, "single mixed: %s", mktfhe_last_error(ctx));
+        CHECK(memcmp(moa, mra, GM * kn * 4) == 0 && memcmp(mob, mrb, sizeof mob) == 0, "mixed batch: multi != single");
+        CHECK(mktfhe_bootstrap_batch(mc, mu, GM, mxa, mxb, moa, mob) == MKTFHE_OK, "multi bootstrap: %s", mktfhe_last_error(mc));
+        CHECK(mktfhe_bootstrap_batch(ctx, mu, GM, mxa, mxb, mra, mrb) == MKTFHE_OK, "single bootstrap");
+        CHECK(memcmp(moa, mra, GM * kn * 4) == 0 && memcmp(mob, mrb, sizeof mob) == 0, "bootstrap: multi != single");
+        /* fewer gates than devices, pinned caller buffers, and the error path of a slice */
+        CHECK(mktfhe_pin_host(mxa, GM * kn * 4) == MKTFHE_OK, "pin_host: %s", mktfhe_last_error(NULL));
+        CHECK(mktfhe_gate_batch(mc, MKTFHE_GATE_XOR, 1, mxa, mxb, mya, myb, NULL, NULL, moa, mob) == MKTFHE_OK, "multi batch of one");
+        CHECK(mktfhe_gate_batch(ctx, MKTFHE_GATE_XOR, 1, mxa, mxb, mya, myb, NULL, NULL, mra, mrb) == MKTFHE_OK, "single batch of one");
+        CHECK(memcmp(moa, mra, kn * 4) == 0 && mob[0] == mrb[0], "batch of one: multi != single");
+        CHECK(mktfhe_unpin_host(mxa) == MKTFHE_OK, "unpin_host");
+        ids[GM - 1] = 77;
+        CHECK(mktfhe_gate_batch_mixed(mc, GM, ids, mxa, mxb, mya, myb, mza, mzb, moa, mob) == MKTFHE_EINVAL && strstr(mktfhe_last_error(mc), "device"),
+              "a bad gate id in the last slice must surface with the device named: %s", mktfhe_last_error(mc));
+        CHECK(mktfhe_gate_batch_dev(mc, MKTFHE_GATE_NAND, 1, mxa, mxb, mya, myb, NULL, NULL, moa, mob, NULL) == MKTFHE_EINVAL, "_dev on a multi-device context");
+        mktfhe_ctx *r1 = NULL; int d1 = -1;
+        CHECK(mktfhe_device_ctx(mc, nd - 1, &r1, &d1) == MKTFHE_OK && r1 && d1 == devs[nd - 1], "device_ctx");
+        char desc[512];
+        CHECK(mktfhe_describe(mc, desc, sizeof desc) == MKTFHE_OK, "describe");
+        CHECK(mktfhe_last_kernel_ms(mc, &br_ms, &ks_ms) == MKTFHE_OK && br_ms > 0, "multi kernel timing");
+        printf("cabi_direct multi: OK (%d devices, %d visible; %d-gate batches equal the 1-device result byte for byte) %s\n", nd, visible, GM, desc);
+        mktfhe_destroy(mc);
+        free(mxa); free(mya); free(mza); free(moa); free(mra);
+    }
     mktfhe_destroy(ctx);
     mko_keyset_free(ks);
     free(xa); free(ya); free(za); free(oa); free(ra); free(ext);

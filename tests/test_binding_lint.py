@@ -19,7 +19,7 @@ def c_declarations():
     decls = {}
     for ret, name, args in re.findall(r"^\s*((?:const\s+)?[a-z_0-9]+\s*\**)\s*(mktfhe_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text, flags=re.M):
         params = []
-        for a in args.split(","):
+        for a in ([] if args.strip() == "void" else args.split(",")):
             a = a.replace("const", " ").strip()
             m = re.match(r"([a-z_0-9]+)\s*(\**)\s*[A-Za-z_0-9]*$", a)
             assert m, (name, a)
@@ -34,6 +34,7 @@ JULIA_TO_C = {
     "Ref{Ptr{Cvoid}}": {"mktfhe_ctx**", "void**"},
     "Ref{CParams}": {"mktfhe_params*"},
     "Cint": {"int"},
+    "Ptr{Cint}": {"int*"},
     "Cvoid": {"void"},
     "Csize_t": {"size_t"},
     "Int64": {"int64_t"},
@@ -98,7 +99,7 @@ def test_julia_ccalls_match_the_header():
             assert ct in JULIA_TO_C[jt], f"{name}: Julia {jt} bound to C {ct}"
     # every entry point of the hot path and of key loading is bound by the shim
     bound = {c[0] for c in calls}
-    for must in ("mktfhe_create", "mktfhe_destroy", "mktfhe_last_error", "mktfhe_load_bsk", "mktfhe_load_ksk", "mktfhe_finalize_keys",
+    for must in ("mktfhe_create_multi", "mktfhe_device_count", "mktfhe_destroy", "mktfhe_last_error", "mktfhe_load_bsk", "mktfhe_load_ksk", "mktfhe_finalize_keys",
                  "mktfhe_bootstrap_batch", "mktfhe_gate_batch", "mktfhe_gate_batch_mixed", "mktfhe_blind_rotate_batch", "mktfhe_keyswitch_batch"):
         assert must in bound, must
 
@@ -152,7 +153,7 @@ def test_ctypes_table_matches_the_header():
                 inner = at._type_
                 base = ct[:-1]
                 ok = {T._cabi.CParams: {"mktfhe_params"}, C.c_void_p: {"mktfhe_ctx*", "void*"}, C.c_size_t: {"size_t"}, C.c_float: {"float"},
-                      C.c_double: {"double"}}[inner]
+                      C.c_double: {"double"}, C.c_int: {"int"}}[inner]
                 assert base in ok, (name, at, ct)
 
 

@@ -40,4 +40,4 @@ def test_plain_c_host_links_and_fails_loudly_without_gpu(tmp_path, oracle):
 def test_plain_c_host_all_gates_bit_exact(tmp_path, oracle):
     exe = _build(tmp_path, oracle)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0 and "cabi_direct: OK" in out.stdout, out.stdout + out.stderr
+    assert out.returncode == 0 and "cabi_direct: OK" in out.stdout and "cabi_direct multi: OK" in out.stdout, out.stdout + out.stderr

@@ -17,12 +17,13 @@ GATE_NAND, GATE_OR, GATE_AND, GATE_XOR, GATE_AND3 = 0, 1, 2, 3, 4
 
 # every symbol include/mktfhe_b200.h declares
 EXPORTS = (
-    "mktfhe_create", "mktfhe_destroy", "mktfhe_last_error",
+    "mktfhe_create", "mktfhe_create_multi", "mktfhe_destroy", "mktfhe_last_error",
+    "mktfhe_device_count", "mktfhe_device_ctx", "mktfhe_shard_bounds", "mktfhe_pin_host", "mktfhe_unpin_host",
     "mktfhe_load_bsk", "mktfhe_load_ksk", "mktfhe_finalize_keys", "mktfhe_key_buffers", "mktfhe_mark_keys_received",
     "mktfhe_bootstrap_batch", "mktfhe_gate_batch", "mktfhe_bootstrap_batch_dev", "mktfhe_gate_batch_dev",
     "mktfhe_gate_batch_mixed", "mktfhe_gate_batch_mixed_dev",
     "mktfhe_extprod_batch", "mktfhe_blind_rotate_batch", "mktfhe_keyswitch_batch", "mktfhe_negacyclic_mul_batch",
-    "mktfhe_launch_count", "mktfhe_last_kernel_ms", "mktfhe_algorithmic_bytes",
+    "mktfhe_launch_count", "mktfhe_last_kernel_ms", "mktfhe_algorithmic_bytes", "mktfhe_build_id", "mktfhe_describe",
 )
 
 
@@ -63,7 +64,15 @@ def lib():
     vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
     sigs = {
         "mktfhe_create": (C.c_int, [C.POINTER(CParams), C.c_int, C.POINTER(vp)]),
+        "mktfhe_create_multi": (C.c_int, [C.POINTER(CParams), C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]),
         "mktfhe_destroy": (None, [vp]),
+        "mktfhe_device_count": (C.c_int, [vp]),
+        "mktfhe_device_ctx": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]),
+        "mktfhe_shard_bounds": (C.c_int, [vp, sz, C.c_int, C.POINTER(sz), C.POINTER(sz)]),
+        "mktfhe_pin_host": (C.c_int, [vp, sz]),
+        "mktfhe_unpin_host": (C.c_int, [vp]),
+        "mktfhe_build_id": (C.c_char_p, []),
+        "mktfhe_describe": (C.c_int, [vp, C.c_char_p, sz]),
         "mktfhe_last_error": (C.c_char_p, [vp]),
         "mktfhe_load_bsk": (C.c_int, [vp, C.c_int, vp]),
         "mktfhe_load_ksk": (C.c_int, [vp, C.c_int, vp]),
@@ -105,23 +114,64 @@ def _c(a, dt):
 
 
 class Context:
-    """One mktfhe_ctx: one GPU, its keys, its stream."""
+    """One mktfhe_ctx: its keys and, per GPU it spans, one stream.  `device` = one GPU (mktfhe_create); `devices` = a list of
+    GPUs, or "all", behind one handle (mktfhe_create_multi): keys are broadcast inside finalize_keys and the host-pointer
+    batch calls shard their batch over the GPUs."""
 
-    def __init__(self, n, N, k, l, bgbit, t, basebit, device=0):
+    def __init__(self, n, N, k, l, bgbit, t, basebit, device=0, devices=None, _borrowed=None):
         L = lib()
         self.prm = CParams(n, N, k, l, bgbit, t, basebit, 0)
         self.n, self.N, self.k, self.l, self.bgbit, self.t, self.basebit = n, N, k, l, bgbit, t, basebit
-        self.device = device
+        self._owned = _borrowed is None
+        if _borrowed is not None:                       # a replica of a multi-device context (owned by its parent)
+            self.h, self.device, self.devices = C.c_void_p(_borrowed), device, [device]
+            return
         h = C.c_void_p()
-        rc = L.mktfhe_create(C.byref(self.prm), device, C.byref(h))
+        if devices is None:
+            rc = L.mktfhe_create(C.byref(self.prm), device, C.byref(h))
+        elif isinstance(devices, str):
+            if devices != "all":
+                raise ValueError('devices must be a list of GPU ordinals or "all"')
+            rc = L.mktfhe_create_multi(C.byref(self.prm), 0, None, C.byref(h))
+        else:
+            devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = L.mktfhe_create_multi(C.byref(self.prm), len(devices), devs, C.byref(h))
         if rc:
             raise MktfheError(rc, L.mktfhe_last_error(None).decode())
         self.h = h
+        self.devices = [self.replica_device(i) for i in range(self.device_count())]
+        self.device = self.devices[0]
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and getattr(self, "_owned", False):
             lib().mktfhe_destroy(self.h)
-            self.h = None
+        self.h = None
+
+    # -- multi-device
+    def device_count(self):
+        return int(lib().mktfhe_device_count(self.h))
+
+    def replica_device(self, i):
+        d = C.c_int()
+        self._chk(lib().mktfhe_device_ctx(self.h, i, None, C.byref(d)))
+        return d.value
+
+    def replica(self, i):
+        """Replica i as a single-device Context (borrowed: valid while this context lives) for the *_dev calls."""
+        r, d = C.c_void_p(), C.c_int()
+        self._chk(lib().mktfhe_device_ctx(self.h, i, C.byref(r), C.byref(d)))
+        return Context(self.n, self.N, self.k, self.l, self.bgbit, self.t, self.basebit, device=d.value, _borrowed=r.value)
+
+    def shard_bounds(self, G, i):
+        lo, hi = C.c_size_t(), C.c_size_t()
+        self._chk(lib().mktfhe_shard_bounds(self.h, G, i, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def describe(self):
+        import json
+        buf = C.create_string_buffer(1024)
+        self._chk(lib().mktfhe_describe(self.h, buf, len(buf)))
+        return json.loads(buf.value.decode())
 
     __del__ = close
 
@@ -258,7 +308,25 @@ class Context:
         self._chk(lib().mktfhe_last_kernel_ms(self.h, C.byref(br), C.byref(ks)))
         return br.value, ks.value
 
+    @staticmethod
+    def build_id():
+        return lib().mktfhe_build_id().decode()
+
     def algorithmic_bytes(self):
         b, k = C.c_double(), C.c_double()
         self._chk(lib().mktfhe_algorithmic_bytes(self.h, C.byref(b), C.byref(k)))
         return b.value, k.value
+
+
+def pin_host(arr):
+    """Page-lock a numpy array in place (mktfhe_pin_host); returns the array.  Unpin with unpin_host before freeing it."""
+    rc = lib().mktfhe_pin_host(_p(arr), arr.nbytes)
+    if rc:
+        raise MktfheError(rc, lib().mktfhe_last_error(None).decode())
+    return arr
+
+
+def unpin_host(arr):
+    rc = lib().mktfhe_unpin_host(_p(arr))
+    if rc:
+        raise MktfheError(rc, lib().mktfhe_last_error(None).decode())

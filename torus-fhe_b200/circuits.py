@@ -45,6 +45,9 @@ def _gate_level_gpu(eng, jobs, k, n):
     import torch
     xa, xb, ya, yb, ids, shapes = [], [], [], [], [], []
     dev = jobs[0][1].a.device
+    if any(t.a.device != dev or t.b.device != dev for _, x, y in jobs for t in (x, y)):
+        raise ValueError("the operands of a gate level live on different devices")
+    ctx = eng.ctx_on(dev.index)                 # raises when the engine holds no key replica on that GPU
     for kind, x, y in jobs:
         shp = torch.broadcast_shapes(tuple(x.b.shape), tuple(y.b.shape))
         shapes.append(tuple(shp))
@@ -58,8 +61,8 @@ def _gate_level_gpu(eng, jobs, k, n):
     stream = torch.cuda.current_stream(dev).cuda_stream
     if not stream:                      # legacy default stream: the context's own stream does not wait for it -- operands must be complete
         torch.cuda.synchronize(dev)
-    eng.ctx.gate_batch_mixed_dev(G, ids.data_ptr(), xa.data_ptr(), xb.data_ptr(), ya.data_ptr(), yb.data_ptr(), 0, 0, oa.data_ptr(), ob.data_ptr(),
-                                 stream=stream)
+    ctx.gate_batch_mixed_dev(G, ids.data_ptr(), xa.data_ptr(), xb.data_ptr(), ya.data_ptr(), yb.data_ptr(), 0, 0, oa.data_ptr(), ob.data_ptr(),
+                             stream=stream)
     if not stream:
         torch.cuda.synchronize(dev)
     outs, pos = [], 0

@@ -11,7 +11,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <dlfcn.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mktfhe_b200.h"
@@ -37,6 +39,7 @@ struct mktfhe_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // br start/stop, ks start/stop
     bool ev_valid = false;
+    bool last_fused = false;     // the most recent bootstrap-like call ran the key switch as the blind-rotate kernel's epilogue
     u32* d_bsk = nullptr;
     size_t bsk_bytes = 0;
     int32_t* d_ksk = nullptr;
@@ -52,6 +55,11 @@ struct mktfhe_ctx {
     DevBuf in[6], ext, oa, ob, accin, accout, elem, raw, gids;
     uint64_t launches = 0;
     std::string err;
+    // multi-device context (mktfhe_create_multi): this context is replica 0 and owns one further single-device context per
+    // additional GPU; host-pointer batch calls shard [G] contiguously over all replicas, one host thread per replica
+    std::vector<mktfhe_ctx*> kids;
+    bool is_kid = false;
+    std::string bcast_how;       // how the keys reached the replicas ("p2p" / "nccl"), for mktfhe_describe
 };
 
 namespace {
@@ -156,17 +164,17 @@ int set_attrs(mktfhe_ctx* c) {
 }
 
 // one gate per CTA for gates [g0, g1): the latency kernel of 6 l warps per gate (l >= 2), else the six-warp kernel alone on its SM
-void launch_one_gate_per_cta(mktfhe_ctx* c, mk::BlindRotateArgs a, size_t g0, size_t g1) {
+void launch_one_gate_per_cta(mktfhe_ctx* c, mk::BlindRotateArgs a, size_t g0, size_t g1, cudaStream_t st) {
     a.g0 = (int)g0; a.G = (int)g1;
     const unsigned grid = (unsigned)(g1 - g0);
     const int l = c->prm.l;
     const size_t sml = mk::TW_SMEM_BYTES + mk::gate_smem_bytes(l, mk::lat_wpg(l));
-    if (l == 2 && c->latency_kernel) mk::blind_rotate_lat_kernel<2><<<grid, 32 * mk::lat_wpg(2), sml, c->stream>>>(a);
-    else if (l == 3 && c->latency_kernel) mk::blind_rotate_lat_kernel<3><<<grid, 32 * mk::lat_wpg(3), sml, c->stream>>>(a);
-    else if (l == 4 && c->latency_kernel) mk::blind_rotate_lat_kernel<4><<<grid, 32 * mk::lat_wpg(4), sml, c->stream>>>(a);
+    if (l == 2 && c->latency_kernel) mk::blind_rotate_lat_kernel<2><<<grid, 32 * mk::lat_wpg(2), sml, st>>>(a);
+    else if (l == 3 && c->latency_kernel) mk::blind_rotate_lat_kernel<3><<<grid, 32 * mk::lat_wpg(3), sml, st>>>(a);
+    else if (l == 4 && c->latency_kernel) mk::blind_rotate_lat_kernel<4><<<grid, 32 * mk::lat_wpg(4), sml, st>>>(a);
     else {
         const size_t sm1 = mk::TW_SMEM_BYTES + mk::gate_smem_bytes(l);
-#define LAUNCH_BR1(L, GPC, dummy) mk::blind_rotate_kernel<L, 1><<<grid, mk::TPG, sm1, c->stream>>>(a)
+#define LAUNCH_BR1(L, GPC, dummy) mk::blind_rotate_kernel<L, 1><<<grid, mk::TPG, sm1, st>>>(a)
         MK_DISPATCH_L(c, LAUNCH_BR1, 0)
 #undef LAUNCH_BR1
     }
@@ -176,24 +184,35 @@ void launch_one_gate_per_cta(mktfhe_ctx* c, mk::BlindRotateArgs a, size_t g0, si
 // Launch shapes.  Throughput: gpc gates per CTA, one CTA per SM, i.e. waves of gpc * num_sms gates.  A batch -- or the tail a batch
 // leaves after its full waves -- of at most one gate per SM runs one gate per CTA instead, on the latency kernel (6 l warps per gate): at
 // l = 2 a gate alone on an SM finishes in 7.3 ms against 12.3 ms for two gates sharing it.  Bit-identical results.
-void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G) {
+void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G, cudaStream_t st) {
     const size_t wave = (size_t)c->gpc * (size_t)c->num_sms;
     size_t tail = c->gpc > 1 ? G % wave : 0;
     // the tail of a larger batch is split off only at l = 2, where it was measured to pay on two workloads; at l = 3 the split lost 1.2 %
     // (the partial last wave of the throughput grid cost 3 ms there, not a full wave), profiles/ab_r1.txt
     if (tail > (size_t)c->num_sms || ((!c->split_tail || c->prm.l != 2) && tail != G)) tail = 0;
     const size_t head = G - tail;
+#if MK_LAT2
+    if (head && c->prm.l == 2) {
+        mk::BlindRotateArgs h = a;
+        h.g0 = 0; h.G = (int)head;
+        const size_t sm2 = mk::TW_SMEM_BYTES + 2 * mk::gate_smem_bytes(2, mk::lat_wpg(2));
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(mk::blind_rotate_lat2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2); attr_set = true; }
+        mk::blind_rotate_lat2_kernel<2><<<(unsigned)((head + 1) / 2), 2 * 32 * mk::lat_wpg(2), sm2, st>>>(h);
+        c->launches++;
+    } else
+#endif
     if (head) {
         mk::BlindRotateArgs h = a;
         h.g0 = 0; h.G = (int)head;
         const size_t sm = br_smem_bytes(c);
         const unsigned grid = (unsigned)((head + c->gpc - 1) / c->gpc);
-#define LAUNCH_BR(L, GPC, dummy) mk::blind_rotate_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, c->stream>>>(h)
+#define LAUNCH_BR(L, GPC, dummy) mk::blind_rotate_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, st>>>(h)
         MK_DISPATCH_L(c, LAUNCH_BR, 0)
 #undef LAUNCH_BR
         c->launches++;
     }
-    if (tail) launch_one_gate_per_cta(c, a, head, G);
+    if (tail) launch_one_gate_per_cta(c, a, head, G, st);
 }
 
 mk::GateLinear gate_linear(int gate, bool* ok) {
@@ -201,74 +220,196 @@ mk::GateLinear gate_linear(int gate, bool* ok) {
     return mk::gate_linear(gate);
 }
 
-// device-pointer core shared by every bootstrap-like entry point
+// device-pointer core shared by every bootstrap-like entry point.  `st` = the caller's stream or nullptr for the context's own.
+// Per-context scratch (c->ext when the key switch is a separate launch, the timing events) is shared by all calls: calls on one
+// context must be stream-ordered with each other (include/mktfhe_b200.h, conventions).
 int run_bootstrap_dev(mktfhe_ctx* c, mk::GateLinear lin, int64_t mu, size_t G, const int32_t* xa, const int32_t* xb,
                       const int32_t* ya, const int32_t* yb, const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob,
                       int32_t* ext_out, int64_t* acc_out, bool do_keyswitch, cudaStream_t st, const int32_t* gate_ids = nullptr) {
     if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
     if (G == 0) return MKTFHE_OK;
     if (G > 0x7fffffffu) return fail(c, MKTFHE_EINVAL, "batch too large");
-    cudaStream_t saved = c->stream;
-    if (st) c->stream = st;
-    if (c->prm.N == mk2k::N) {
+    if (!st) st = c->stream;
+    const bool big = c->prm.N == mk2k::N;
+    const bool fuse = do_keyswitch && c->fuse_ks && (big ? mk2k::ks_fusable(c->prm.n, c->prm.t) : mk::ks_fusable(c->prm.n, c->prm.t));
+    c->last_fused = fuse;
+    int32_t* ext = ext_out;
+    if (!ext && !fuse) {
+        int rc = reserve(c, c->ext, G * ((size_t)c->prm.N + 1) * sizeof(int32_t));
+        if (rc) return rc;
+        ext = (int32_t*)c->ext.p;
+    }
+    c->ev_valid = false;
+    CU_TRY(c, cudaEventRecord(c->ev[0], st));
+    if (big) {
         // N = 2048: one gate per CTA (kernels2k.cuh); the key switch is the kernel's epilogue when its shape is covered
-        const bool fuse2 = do_keyswitch && c->fuse_ks && mk2k::ks_fusable(c->prm.n, c->prm.t);
-        int32_t* ext2 = ext_out;
-        if (!ext2 && !fuse2) {
-            int rc = reserve(c, c->ext, G * (mk2k::N + 1) * sizeof(int32_t));
-            if (rc) { c->stream = saved; return rc; }
-            ext2 = (int32_t*)c->ext.p;
-        }
         mk2k::Args a{};
         a.G = (int)G; a.n = c->prm.n; a.k = c->prm.k; a.bgbit = c->prm.bgbit;
         a.bsk = c->d_bsk; a.twB = c->d_twB;
         a.xa = xa; a.xb = xb; a.ya = ya; a.yb = yb; a.za = za; a.zb = zb;
-        a.lin = lin; a.gate_ids = gate_ids; a.mu = mu; a.ext_out = ext2; a.acc_out = acc_out;
-        if (fuse2) { a.ksk = c->d_ksk; a.ks_t = c->prm.t; a.ks_basebit = c->prm.basebit; a.oa = oa; a.ob = ob; }
-        cudaEventRecord(c->ev[0], c->stream);
-        if (c->prm.l == 1) mk2k::blind_rotate2k_kernel<1><<<(unsigned)G, mk2k::THREADS, mk2k::smem_bytes(1), c->stream>>>(a);
-        else mk2k::blind_rotate2k_kernel<2><<<(unsigned)G, mk2k::THREADS, mk2k::smem_bytes(2), c->stream>>>(a);
+        a.lin = lin; a.gate_ids = gate_ids; a.mu = mu; a.ext_out = ext; a.acc_out = acc_out;
+        if (fuse) { a.ksk = c->d_ksk; a.ks_t = c->prm.t; a.ks_basebit = c->prm.basebit; a.oa = oa; a.ob = ob; }
+        if (c->prm.l == 1) mk2k::blind_rotate2k_kernel<1><<<(unsigned)G, mk2k::THREADS, mk2k::smem_bytes(1), st>>>(a);
+        else mk2k::blind_rotate2k_kernel<2><<<(unsigned)G, mk2k::THREADS, mk2k::smem_bytes(2), st>>>(a);
         c->launches++;
-        cudaEventRecord(c->ev[1], c->stream);
-        cudaEventRecord(c->ev[2], c->stream);
-        if (do_keyswitch && !fuse2) {
-            mk2k::keyswitch2k_kernel<<<(unsigned)G, mk::KS_THREADS, 0, c->stream>>>(c->prm.n, c->prm.k, c->prm.t, c->prm.basebit, c->d_ksk, ext2, oa, ob);
-            c->launches++;
+    } else {
+        mk::BlindRotateArgs a{};
+        a.G = (int)G; a.n = c->prm.n; a.k = c->prm.k; a.bgbit = c->prm.bgbit;
+        a.bsk = c->d_bsk; a.twB = c->d_twB;
+        a.xa = xa; a.xb = xb; a.ya = ya; a.yb = yb; a.za = za; a.zb = zb;
+        a.lin = lin; a.gate_ids = gate_ids; a.mu = mu; a.ext_out = ext; a.acc_out = acc_out;
+        if (fuse) {
+            a.ksk = c->d_ksk; a.ks_t = c->prm.t; a.ks_basebit = c->prm.basebit; a.oa = oa; a.ob = ob;
+            if (!ext_out) a.ext_out = nullptr;   // nobody asked for the extracted samples
         }
-        cudaEventRecord(c->ev[3], c->stream);
-        c->ev_valid = true;
-        c->stream = saved;
-        CU_TRY(c, cudaGetLastError());
-        return MKTFHE_OK;
+        launch_blind_rotate(c, a, G, st);
     }
-    int32_t* ext = ext_out;
-    if (!ext && !(do_keyswitch && c->fuse_ks && mk::ks_fusable(c->prm.n, c->prm.t))) {
-        int rc = reserve(c, c->ext, G * (mk::N + 1) * sizeof(int32_t));
-        if (rc) { c->stream = saved; return rc; }
-        ext = (int32_t*)c->ext.p;
-    }
-    mk::BlindRotateArgs a{};
-    a.G = (int)G; a.n = c->prm.n; a.k = c->prm.k; a.bgbit = c->prm.bgbit;
-    a.bsk = c->d_bsk; a.twB = c->d_twB;
-    a.xa = xa; a.xb = xb; a.ya = ya; a.yb = yb; a.za = za; a.zb = zb;
-    a.lin = lin; a.gate_ids = gate_ids; a.mu = mu; a.ext_out = ext; a.acc_out = acc_out;
-    const bool fuse = do_keyswitch && c->fuse_ks && mk::ks_fusable(c->prm.n, c->prm.t);
-    if (fuse) {
-        a.ksk = c->d_ksk; a.ks_t = c->prm.t; a.ks_basebit = c->prm.basebit; a.oa = oa; a.ob = ob;
-        if (!ext_out) a.ext_out = nullptr;   // nobody asked for the extracted samples
-    }
-    cudaEventRecord(c->ev[0], c->stream);
-    launch_blind_rotate(c, a, G);
-    cudaEventRecord(c->ev[1], c->stream);
-    cudaEventRecord(c->ev[2], c->stream);
-    if (do_keyswitch && !fuse) {
-        mk::keyswitch_kernel<<<(unsigned)G, mk::KS_THREADS, 0, c->stream>>>(c->prm.n, c->prm.k, c->prm.t, c->prm.basebit, c->d_ksk, ext, oa, ob);
-        c->launches++;
-    }
-    cudaEventRecord(c->ev[3], c->stream);
-    c->ev_valid = true;
-    c->stream = saved;
     CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaEventRecord(c->ev[1], st));
+    CU_TRY(c, cudaEventRecord(c->ev[2], st));
+    if (do_keyswitch && !fuse) {
+        if (big) mk2k::keyswitch2k_kernel<<<(unsigned)G, mk::KS_THREADS, 0, st>>>(c->prm.n, c->prm.k, c->prm.t, c->prm.basebit, c->d_ksk, ext, oa, ob);
+        else mk::keyswitch_kernel<<<(unsigned)G, mk::KS_THREADS, 0, st>>>(c->prm.n, c->prm.k, c->prm.t, c->prm.basebit, c->d_ksk, ext, oa, ob);
+        c->launches++;
+        CU_TRY(c, cudaGetLastError());
+    }
+    CU_TRY(c, cudaEventRecord(c->ev[3], st));
+    c->ev_valid = true;
+    return MKTFHE_OK;
+}
+
+// ---- multi-device contexts (mktfhe_create_multi) ---------------------------------------------------------------------------
+// gates shard across GPUs, every GPU holds a full key replica, the one-time key broadcast is the only
+// exchange.  The context the caller holds is replica 0; c->kids are single-device contexts on the further GPUs.
+inline size_t n_replicas(const mktfhe_ctx* c) { return 1 + c->kids.size(); }
+inline mktfhe_ctx* replica(mktfhe_ctx* c, size_t i) { return i == 0 ? c : c->kids[i - 1]; }
+// contiguous slice [lo, hi) of G units owned by replica r of R; sizes differ by at most one
+inline void shard_bounds(size_t G, size_t R, size_t r, size_t* lo, size_t* hi) {
+    const size_t base = G / R, rem = G % R;
+    *lo = r * base + (r < rem ? r : rem);
+    *hi = *lo + base + (r < rem ? 1 : 0);
+}
+// f(replica, lo, hi) for every replica with a non-empty slice, one host thread per replica so that their host<->device copies
+// (pinned or pageable caller memory alike), launches and waits overlap.  First failing replica's code and message win.
+template <class F>
+int for_each_shard(mktfhe_ctx* c, size_t G, F f) {
+    const size_t R = n_replicas(c);
+    std::vector<int> rc(R, MKTFHE_OK);
+    std::vector<std::thread> th;
+    th.reserve(R);
+    for (size_t r = 1; r < R; r++) {
+        size_t lo, hi;
+        shard_bounds(G, R, r, &lo, &hi);
+        if (hi == lo) continue;
+        try {
+            th.emplace_back([&rc, &f, c, r, lo, hi]() { rc[r] = f(replica(c, r), lo, hi); });
+        } catch (...) {
+            rc[r] = f(replica(c, r), lo, hi);   // no thread to be had: run the slice here
+        }
+    }
+    size_t lo, hi;
+    shard_bounds(G, R, 0, &lo, &hi);
+    if (hi > lo) rc[0] = f(c, lo, hi);
+    for (auto& t : th) t.join();
+    for (size_t r = 0; r < R; r++)
+        if (rc[r]) {
+            if (r) c->err = "device " + std::to_string(replica(c, r)->device) + ": " + replica(c, r)->err;
+            return rc[r];
+        }
+    return MKTFHE_OK;
+}
+
+// NCCL, bound at run time (no link-time dependency; torch ships its own libnccl.so.2 and a process must not hold two)
+struct NcclApi {
+    void* h = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (h) return true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (h) break;
+        }
+        if (!h) return false;
+#define NCCL_SYM(field, sym) *(void**)(&field) = dlsym(h, sym)
+        NCCL_SYM(CommInitAll, "ncclCommInitAll"); NCCL_SYM(CommDestroy, "ncclCommDestroy"); NCCL_SYM(GroupStart, "ncclGroupStart");
+        NCCL_SYM(GroupEnd, "ncclGroupEnd"); NCCL_SYM(Broadcast, "ncclBroadcast"); NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef NCCL_SYM
+        return CommInitAll && CommDestroy && GroupStart && GroupEnd && Broadcast && GetErrorString;
+    }
+};
+
+// one grouped ncclBroadcast per key buffer from replica 0 (single process, one communicator per device)
+int broadcast_keys_nccl(mktfhe_ctx* c) {
+    static NcclApi api;
+    if (!api.load()) return fail(c, MKTFHE_ECUDA, "MKTFHE_B200_BCAST=nccl: libnccl.so.2 not loadable (%s)", dlerror());
+    const size_t R = n_replicas(c);
+    std::vector<int> devs(R);
+    for (size_t r = 0; r < R; r++) devs[r] = replica(c, r)->device;
+    std::vector<void*> comms(R, nullptr);
+    int e = api.CommInitAll(comms.data(), (int)R, devs.data());
+    if (e) return fail(c, MKTFHE_ECUDA, "ncclCommInitAll: %s", api.GetErrorString(e));
+    const size_t kbytes = c->ksk_bytes;
+    int bad = 0;
+    for (int which = 0; which < 2 && !bad; which++) {
+        api.GroupStart();
+        for (size_t r = 0; r < R; r++) {
+            mktfhe_ctx* d = replica(c, r);
+            void* buf = which == 0 ? (void*)d->d_bsk : (void*)d->d_ksk;
+            e = api.Broadcast(buf, buf, which == 0 ? c->bsk_bytes : kbytes, /* ncclInt8 */ 0, 0, comms[r], d->stream);
+            if (e) bad = e;
+        }
+        e = api.GroupEnd();
+        if (e) bad = e;
+    }
+    for (size_t r = 0; r < R; r++) {
+        cudaSetDevice(replica(c, r)->device);
+        cudaStreamSynchronize(replica(c, r)->stream);
+    }
+    for (void* cm : comms) if (cm) api.CommDestroy(cm);
+    if (bad) return fail(c, MKTFHE_ECUDA, "ncclBroadcast: %s", api.GetErrorString(bad));
+    c->bcast_how = "nccl";
+    return MKTFHE_OK;
+}
+
+// binomial tree of peer copies: in the round of span s the replicas [0, s) each send both key buffers to replica + s
+// (cudaMemcpyPeerAsync: NVLink when peer access is on, staged through the host otherwise)
+int broadcast_keys_p2p(mktfhe_ctx* c) {
+    const size_t R = n_replicas(c);
+    for (size_t span = 1; span < R; span <<= 1) {
+        for (size_t src = 0; src < span && src + span < R; src++) {
+            mktfhe_ctx *s = replica(c, src), *d = replica(c, src + span);
+            CU_TRY(c, cudaSetDevice(d->device));
+            CU_TRY(c, cudaMemcpyPeerAsync(d->d_bsk, d->device, s->d_bsk, s->device, c->bsk_bytes, d->stream));
+            CU_TRY(c, cudaMemcpyPeerAsync(d->d_ksk, d->device, s->d_ksk, s->device, c->ksk_bytes, d->stream));
+        }
+        for (size_t src = 0; src < span && src + span < R; src++) {
+            mktfhe_ctx* d = replica(c, src + span);
+            CU_TRY(c, cudaSetDevice(d->device));
+            CU_TRY(c, cudaStreamSynchronize(d->stream));
+        }
+    }
+    c->bcast_how = "p2p";
+    return MKTFHE_OK;
+}
+
+int broadcast_keys(mktfhe_ctx* c) {
+    const char* how = getenv("MKTFHE_B200_BCAST");
+    bool distinct = true;
+    for (size_t i = 0; i < n_replicas(c); i++)
+        for (size_t j = 0; j < i; j++) distinct &= replica(c, i)->device != replica(c, j)->device;
+    int rc = (how && !strcmp(how, "nccl") && distinct) ? broadcast_keys_nccl(c) : broadcast_keys_p2p(c);
+    if (rc) return rc;
+    for (mktfhe_ctx* k : c->kids) {
+        k->bsk_loaded.assign(k->prm.k, 1);
+        k->ksk_loaded.assign(k->prm.k, 1);
+        k->ready = true;
+    }
+    CU_TRY(c, cudaSetDevice(c->device));
     return MKTFHE_OK;
 }
 
@@ -341,6 +482,8 @@ int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
 
 void mktfhe_destroy(mktfhe_ctx* c) {
     if (!c) return;
+    for (mktfhe_ctx* k : c->kids) mktfhe_destroy(k);
+    c->kids.clear();
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->in[0], &c->in[1], &c->in[2], &c->in[3], &c->in[4], &c->in[5], &c->ext, &c->oa, &c->ob, &c->accin, &c->accout, &c->elem, &c->raw, &c->gids};
@@ -400,6 +543,10 @@ int mktfhe_finalize_keys(mktfhe_ctx* c) {
         if (!c->bsk_loaded[p] || !c->ksk_loaded[p]) return fail(c, MKTFHE_ESTATE, "party %d: bootstrapping or key-switching key not loaded", p);
     CU_TRY(c, cudaSetDevice(c->device));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (!c->kids.empty()) {   // multi-device context: the one-time key broadcast from replica 0
+        int rc = broadcast_keys(c);
+        if (rc) return rc;
+    }
     c->ready = true;
     return MKTFHE_OK;
 }
@@ -423,6 +570,7 @@ int mktfhe_mark_keys_received(mktfhe_ctx* c) {
 int mktfhe_bootstrap_batch_dev(mktfhe_ctx* c, int64_t mu, size_t G, const int32_t* a_in, const int32_t* b_in, int32_t* a_out,
                                int32_t* b_out, void* stream) {
     if (!c) return MKTFHE_EINVAL;
+    if (!c->kids.empty()) return fail(c, MKTFHE_EINVAL, "device pointers belong to one GPU: use the per-device context (mktfhe_device_ctx)");
     if (G && (!a_in || !b_in || !a_out || !b_out)) return fail(c, MKTFHE_EINVAL, "bootstrap_batch: NULL buffer");
     CU_TRY(c, cudaSetDevice(c->device));
     return run_bootstrap_dev(c, {0, 1, 0, 0}, mu, G, a_in, b_in, nullptr, nullptr, nullptr, nullptr, a_out, b_out, nullptr, nullptr, true,
@@ -432,6 +580,7 @@ int mktfhe_bootstrap_batch_dev(mktfhe_ctx* c, int64_t mu, size_t G, const int32_
 int mktfhe_gate_batch_dev(mktfhe_ctx* c, int gate, size_t G, const int32_t* xa, const int32_t* xb, const int32_t* ya,
                           const int32_t* yb, const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob, void* stream) {
     if (!c) return MKTFHE_EINVAL;
+    if (!c->kids.empty()) return fail(c, MKTFHE_EINVAL, "device pointers belong to one GPU: use the per-device context (mktfhe_device_ctx)");
     bool ok;
     mk::GateLinear lin = gate_linear(gate, &ok);
     if (!ok) return fail(c, MKTFHE_EINVAL, "unknown gate id %d", gate);
@@ -448,7 +597,7 @@ static int stage_in(mktfhe_ctx* c, DevBuf& b, const void* host, size_t bytes) {
     return MKTFHE_OK;
 }
 
-int mktfhe_gate_batch(mktfhe_ctx* c, int gate, size_t G, const int32_t* xa, const int32_t* xb, const int32_t* ya, const int32_t* yb,
+static int mktfhe_gate_batch_1(mktfhe_ctx* c, int gate, size_t G, const int32_t* xa, const int32_t* xb, const int32_t* ya, const int32_t* yb,
                       const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob) {
     if (!c) return MKTFHE_EINVAL;
     bool ok;
@@ -477,6 +626,7 @@ int mktfhe_gate_batch(mktfhe_ctx* c, int gate, size_t G, const int32_t* xa, cons
 int mktfhe_gate_batch_mixed_dev(mktfhe_ctx* c, size_t G, const int32_t* gate_ids, const int32_t* xa, const int32_t* xb, const int32_t* ya,
                                 const int32_t* yb, const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob, void* stream) {
     if (!c) return MKTFHE_EINVAL;
+    if (!c->kids.empty()) return fail(c, MKTFHE_EINVAL, "device pointers belong to one GPU: use the per-device context (mktfhe_device_ctx)");
     if (G && (!gate_ids || !xa || !xb || !ya || !yb || !oa || !ob)) return fail(c, MKTFHE_EINVAL, "gate_batch_mixed: NULL buffer");
     CU_TRY(c, cudaSetDevice(c->device));
     // za/zb are read only by MKTFHE_GATE_AND3 gates; point them at x when absent so no gate dereferences NULL
@@ -484,7 +634,7 @@ int mktfhe_gate_batch_mixed_dev(mktfhe_ctx* c, size_t G, const int32_t* gate_ids
                              (cudaStream_t)stream, gate_ids);
 }
 
-int mktfhe_gate_batch_mixed(mktfhe_ctx* c, size_t G, const int32_t* gate_ids, const int32_t* xa, const int32_t* xb, const int32_t* ya,
+static int mktfhe_gate_batch_mixed_1(mktfhe_ctx* c, size_t G, const int32_t* gate_ids, const int32_t* xa, const int32_t* xb, const int32_t* ya,
                             const int32_t* yb, const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob) {
     if (!c) return MKTFHE_EINVAL;
     if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
@@ -514,7 +664,7 @@ int mktfhe_gate_batch_mixed(mktfhe_ctx* c, size_t G, const int32_t* gate_ids, co
     return MKTFHE_OK;
 }
 
-int mktfhe_bootstrap_batch(mktfhe_ctx* c, int64_t mu, size_t G, const int32_t* a_in, const int32_t* b_in, int32_t* a_out, int32_t* b_out) {
+static int mktfhe_bootstrap_batch_1(mktfhe_ctx* c, int64_t mu, size_t G, const int32_t* a_in, const int32_t* b_in, int32_t* a_out, int32_t* b_out) {
     if (!c) return MKTFHE_EINVAL;
     if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
     if (G == 0) return MKTFHE_OK;
@@ -533,7 +683,7 @@ int mktfhe_bootstrap_batch(mktfhe_ctx* c, int64_t mu, size_t G, const int32_t* a
     return MKTFHE_OK;
 }
 
-int mktfhe_blind_rotate_batch(mktfhe_ctx* c, int64_t mu, size_t G, const int32_t* a_in, const int32_t* b_in, int32_t* ext_out, int64_t* acc_out) {
+static int mktfhe_blind_rotate_batch_1(mktfhe_ctx* c, int64_t mu, size_t G, const int32_t* a_in, const int32_t* b_in, int32_t* ext_out, int64_t* acc_out) {
     if (!c) return MKTFHE_EINVAL;
     if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
     if (G == 0) return MKTFHE_OK;
@@ -554,7 +704,7 @@ int mktfhe_blind_rotate_batch(mktfhe_ctx* c, int64_t mu, size_t G, const int32_t
     return MKTFHE_OK;
 }
 
-int mktfhe_keyswitch_batch(mktfhe_ctx* c, size_t G, const int32_t* ext, int32_t* a_out, int32_t* b_out) {
+static int mktfhe_keyswitch_batch_1(mktfhe_ctx* c, size_t G, const int32_t* ext, int32_t* a_out, int32_t* b_out) {
     if (!c) return MKTFHE_EINVAL;
     if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
     if (G == 0) return MKTFHE_OK;
@@ -577,7 +727,7 @@ int mktfhe_keyswitch_batch(mktfhe_ctx* c, size_t G, const int32_t* ext, int32_t*
     return MKTFHE_OK;
 }
 
-int mktfhe_extprod_batch(mktfhe_ctx* c, size_t G, const int32_t* elem, const int64_t* acc_in, int64_t* acc_out) {
+static int mktfhe_extprod_batch_1(mktfhe_ctx* c, size_t G, const int32_t* elem, const int64_t* acc_in, int64_t* acc_out) {
     if (!c) return MKTFHE_EINVAL;
     if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
     if (G == 0) return MKTFHE_OK;
@@ -603,10 +753,18 @@ int mktfhe_extprod_batch(mktfhe_ctx* c, size_t G, const int32_t* elem, const int
     return MKTFHE_OK;
 }
 
-int mktfhe_negacyclic_mul_batch(mktfhe_ctx* c, size_t G, const int64_t* a, const int64_t* b, int64_t* out) {
+static int mktfhe_negacyclic_mul_batch_1(mktfhe_ctx* c, size_t G, const int64_t* a, const int64_t* b, int64_t* out) {
     if (!c) return MKTFHE_EINVAL;
     if (G == 0) return MKTFHE_OK;
     if (!a || !b || !out) return fail(c, MKTFHE_EINVAL, "negacyclic_mul_batch: NULL buffer");
+    {   // exactness of the CRT lift: N * max|a_i| * 2^63 must stay below M/4 (M ~ 2^84 at N = 1024, 2^112 at N = 2048)
+        const int64_t lim = c->prm.N == mk2k::N ? ((int64_t)1 << 25) : ((int64_t)1 << 8);
+        const size_t cnt = G * (size_t)c->prm.N;
+        for (size_t i = 0; i < cnt; i++)
+            if (a[i] > lim || a[i] < -lim)
+                return fail(c, MKTFHE_EINVAL, "negacyclic_mul_batch: |a[%zu]| = %lld exceeds 2^%d, the exact range of the small operand at N = %d",
+                            i, (long long)(a[i] < 0 ? -a[i] : a[i]), c->prm.N == mk2k::N ? 25 : 8, c->prm.N);
+    }
     CU_TRY(c, cudaSetDevice(c->device));
     const size_t bytes = G * (size_t)c->prm.N * 8;
     int rc;
@@ -624,16 +782,201 @@ int mktfhe_negacyclic_mul_batch(mktfhe_ctx* c, size_t G, const int64_t* a, const
     return MKTFHE_OK;
 }
 
-uint64_t mktfhe_launch_count(const mktfhe_ctx* c) { return c ? c->launches : 0; }
+// ---- public host-pointer entry points: single-device contexts run the body above, multi-device contexts shard [G] ------------
+#define MK_NOT_READY(c)                                                                       \
+    if (!(c)) return MKTFHE_EINVAL;                                                           \
+    if (!(c)->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)")
+
+int mktfhe_gate_batch(mktfhe_ctx* c, int gate, size_t G, const int32_t* xa, const int32_t* xb, const int32_t* ya, const int32_t* yb,
+                      const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob) {
+    if (!c) return MKTFHE_EINVAL;
+    if (c->kids.empty()) return mktfhe_gate_batch_1(c, gate, G, xa, xb, ya, yb, za, zb, oa, ob);
+    MK_NOT_READY(c);
+    if (G && (!xa || !xb || !ya || !yb || !oa || !ob)) return fail(c, MKTFHE_EINVAL, "gate_batch: NULL buffer");
+    const size_t kn = (size_t)c->prm.n * c->prm.k;
+    return for_each_shard(c, G, [=](mktfhe_ctx* r, size_t lo, size_t hi) {
+        return mktfhe_gate_batch_1(r, gate, hi - lo, xa + lo * kn, xb + lo, ya + lo * kn, yb + lo, za ? za + lo * kn : nullptr, zb ? zb + lo : nullptr,
+                                   oa + lo * kn, ob + lo);
+    });
+}
+
+int mktfhe_gate_batch_mixed(mktfhe_ctx* c, size_t G, const int32_t* gate_ids, const int32_t* xa, const int32_t* xb, const int32_t* ya,
+                            const int32_t* yb, const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob) {
+    if (!c) return MKTFHE_EINVAL;
+    if (c->kids.empty()) return mktfhe_gate_batch_mixed_1(c, G, gate_ids, xa, xb, ya, yb, za, zb, oa, ob);
+    MK_NOT_READY(c);
+    if (G && (!gate_ids || !xa || !xb || !ya || !yb || !oa || !ob)) return fail(c, MKTFHE_EINVAL, "gate_batch_mixed: NULL buffer");
+    const size_t kn = (size_t)c->prm.n * c->prm.k;
+    return for_each_shard(c, G, [=](mktfhe_ctx* r, size_t lo, size_t hi) {
+        return mktfhe_gate_batch_mixed_1(r, hi - lo, gate_ids + lo, xa + lo * kn, xb + lo, ya + lo * kn, yb + lo, za ? za + lo * kn : nullptr,
+                                         zb ? zb + lo : nullptr, oa + lo * kn, ob + lo);
+    });
+}
+
+int mktfhe_bootstrap_batch(mktfhe_ctx* c, int64_t mu, size_t G, const int32_t* a_in, const int32_t* b_in, int32_t* a_out, int32_t* b_out) {
+    if (!c) return MKTFHE_EINVAL;
+    if (c->kids.empty()) return mktfhe_bootstrap_batch_1(c, mu, G, a_in, b_in, a_out, b_out);
+    MK_NOT_READY(c);
+    if (G && (!a_in || !b_in || !a_out || !b_out)) return fail(c, MKTFHE_EINVAL, "bootstrap_batch: NULL buffer");
+    const size_t kn = (size_t)c->prm.n * c->prm.k;
+    return for_each_shard(c, G, [=](mktfhe_ctx* r, size_t lo, size_t hi) {
+        return mktfhe_bootstrap_batch_1(r, mu, hi - lo, a_in + lo * kn, b_in + lo, a_out + lo * kn, b_out + lo);
+    });
+}
+
+int mktfhe_blind_rotate_batch(mktfhe_ctx* c, int64_t mu, size_t G, const int32_t* a_in, const int32_t* b_in, int32_t* ext_out, int64_t* acc_out) {
+    if (!c) return MKTFHE_EINVAL;
+    if (c->kids.empty()) return mktfhe_blind_rotate_batch_1(c, mu, G, a_in, b_in, ext_out, acc_out);
+    MK_NOT_READY(c);
+    if (G && (!a_in || !b_in || !ext_out)) return fail(c, MKTFHE_EINVAL, "blind_rotate_batch: NULL buffer");
+    const size_t kn = (size_t)c->prm.n * c->prm.k, N = (size_t)c->prm.N;
+    return for_each_shard(c, G, [=](mktfhe_ctx* r, size_t lo, size_t hi) {
+        return mktfhe_blind_rotate_batch_1(r, mu, hi - lo, a_in + lo * kn, b_in + lo, ext_out + lo * (N + 1), acc_out ? acc_out + lo * 2 * N : nullptr);
+    });
+}
+
+int mktfhe_keyswitch_batch(mktfhe_ctx* c, size_t G, const int32_t* ext, int32_t* a_out, int32_t* b_out) {
+    if (!c) return MKTFHE_EINVAL;
+    if (c->kids.empty()) return mktfhe_keyswitch_batch_1(c, G, ext, a_out, b_out);
+    MK_NOT_READY(c);
+    if (G && (!ext || !a_out || !b_out)) return fail(c, MKTFHE_EINVAL, "keyswitch_batch: NULL buffer");
+    const size_t kn = (size_t)c->prm.n * c->prm.k, N = (size_t)c->prm.N;
+    return for_each_shard(c, G, [=](mktfhe_ctx* r, size_t lo, size_t hi) {
+        return mktfhe_keyswitch_batch_1(r, hi - lo, ext + lo * (N + 1), a_out + lo * kn, b_out + lo);
+    });
+}
+
+int mktfhe_extprod_batch(mktfhe_ctx* c, size_t G, const int32_t* elem, const int64_t* acc_in, int64_t* acc_out) {
+    if (!c) return MKTFHE_EINVAL;
+    if (c->kids.empty()) return mktfhe_extprod_batch_1(c, G, elem, acc_in, acc_out);
+    MK_NOT_READY(c);
+    if (G && (!elem || !acc_in || !acc_out)) return fail(c, MKTFHE_EINVAL, "extprod_batch: NULL buffer");
+    const size_t N = (size_t)c->prm.N;
+    return for_each_shard(c, G, [=](mktfhe_ctx* r, size_t lo, size_t hi) {
+        return mktfhe_extprod_batch_1(r, hi - lo, elem + lo, acc_in + lo * 2 * N, acc_out + lo * 2 * N);
+    });
+}
+
+int mktfhe_negacyclic_mul_batch(mktfhe_ctx* c, size_t G, const int64_t* a, const int64_t* b, int64_t* out) {
+    if (!c) return MKTFHE_EINVAL;
+    if (c->kids.empty()) return mktfhe_negacyclic_mul_batch_1(c, G, a, b, out);
+    if (G && (!a || !b || !out)) return fail(c, MKTFHE_EINVAL, "negacyclic_mul_batch: NULL buffer");
+    const size_t N = (size_t)c->prm.N;
+    return for_each_shard(c, G, [=](mktfhe_ctx* r, size_t lo, size_t hi) {
+        return mktfhe_negacyclic_mul_batch_1(r, hi - lo, a + lo * N, b + lo * N, out + lo * N);
+    });
+}
+
+// ---- multi-device lifetime -----------------------------------------------------------------------------------------------------
+int mktfhe_create_multi(const mktfhe_params* params, int n_devices, const int* devices, mktfhe_ctx** out) {
+    if (!out) return fail(nullptr, MKTFHE_EINVAL, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, MKTFHE_ECUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    if (n_devices == 0) n_devices = ndev;                       // 0 = every visible GPU
+    if (n_devices < 1 || n_devices > 64) return fail(nullptr, MKTFHE_EINVAL, "n_devices=%d out of range (1..64, or 0 for all)", n_devices);
+    std::vector<int> devs(n_devices);
+    for (int i = 0; i < n_devices; i++) devs[i] = devices ? devices[i] : i;
+    mktfhe_ctx* c = nullptr;
+    int rc = mktfhe_create(params, devs[0], &c);
+    if (rc) return rc;
+    for (int i = 1; i < n_devices; i++) {
+        mktfhe_ctx* k = nullptr;
+        rc = mktfhe_create(params, devs[i], &k);
+        if (rc) { mktfhe_destroy(c); return rc; }               // g_create_error holds the message
+        k->is_kid = true;
+        c->kids.push_back(k);
+    }
+    // peer access in both directions between every pair of distinct devices, where the hardware offers it (NVLink / NVSwitch):
+    // the key broadcast then moves GPU to GPU; without it cudaMemcpyPeerAsync stages through the host
+    for (int i = 0; i < n_devices; i++)
+        for (int j = 0; j < n_devices; j++) {
+            if (devs[i] == devs[j]) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devs[i], devs[j]) == cudaSuccess && can) {
+                cudaSetDevice(devs[i]);
+                cudaError_t pe = cudaDeviceEnablePeerAccess(devs[j], 0);
+                if (pe != cudaSuccess) cudaGetLastError();      // already enabled (by us or by the host framework): fine
+            }
+        }
+    cudaSetDevice(devs[0]);
+    *out = c;
+    return MKTFHE_OK;
+}
+
+int mktfhe_device_count(const mktfhe_ctx* c) { return c ? (int)n_replicas(c) : 0; }
+
+int mktfhe_device_ctx(mktfhe_ctx* c, int i, mktfhe_ctx** out, int* device) {
+    if (!c) return MKTFHE_EINVAL;
+    if (i < 0 || (size_t)i >= n_replicas(c)) return fail(c, MKTFHE_EINVAL, "device_ctx: replica %d out of range (%zu devices)", i, n_replicas(c));
+    if (out) *out = replica(c, i);
+    if (device) *device = replica(c, i)->device;
+    return MKTFHE_OK;
+}
+
+int mktfhe_shard_bounds(const mktfhe_ctx* c, size_t G, int i, size_t* lo, size_t* hi) {
+    if (!c || !lo || !hi || i < 0 || (size_t)i >= n_replicas(c)) return MKTFHE_EINVAL;
+    shard_bounds(G, n_replicas(c), (size_t)i, lo, hi);
+    return MKTFHE_OK;
+}
+
+int mktfhe_pin_host(void* p, size_t bytes) {
+    if (!p || !bytes) return MKTFHE_EINVAL;
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, MKTFHE_ECUDA, "cudaHostRegister: %s", cudaGetErrorString(e)); }
+    return MKTFHE_OK;
+}
+int mktfhe_unpin_host(void* p) {
+    if (!p) return MKTFHE_EINVAL;
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, MKTFHE_ECUDA, "cudaHostUnregister: %s", cudaGetErrorString(e)); }
+    return MKTFHE_OK;
+}
+
+#ifndef MK_BUILD_ID
+#define MK_BUILD_ID "unknown"
+#endif
+const char* mktfhe_build_id(void) { return MK_BUILD_ID; }
+
+int mktfhe_describe(const mktfhe_ctx* c, char* buf, size_t cap) {
+    if (!c || !buf || !cap) return MKTFHE_EINVAL;
+    std::string d = "{\"build_id\": \"" MK_BUILD_ID "\", \"devices\": [";
+    for (size_t r = 0; r < n_replicas(c); r++) d += (r ? ", " : "") + std::to_string(replica(const_cast<mktfhe_ctx*>(c), r)->device);
+    d += "], \"key_broadcast\": \"" + (c->kids.empty() ? std::string("none") : (c->bcast_how.empty() ? std::string("pending") : c->bcast_how)) + "\"";
+    d += ", \"keyswitch_fused\": " + std::string(c->last_fused ? "true" : "false");
+    d += ", \"gates_per_cta\": " + std::to_string(c->gpc) + ", \"sms\": " + std::to_string(c->num_sms);
+    d += ", \"bsk_bytes\": " + std::to_string(c->bsk_bytes) + ", \"ksk_bytes\": " + std::to_string(c->ksk_bytes) + "}";
+    snprintf(buf, cap, "%s", d.c_str());
+    return d.size() < cap ? MKTFHE_OK : MKTFHE_EINVAL;
+}
+
+uint64_t mktfhe_launch_count(const mktfhe_ctx* c) {
+    if (!c) return 0;
+    uint64_t n = c->launches;
+    for (const mktfhe_ctx* k : c->kids) n += k->launches;
+    return n;
+}
 
 int mktfhe_last_kernel_ms(mktfhe_ctx* c, float* blind_rotate_ms, float* keyswitch_ms) {
     if (!c) return MKTFHE_EINVAL;
-    if (!c->ev_valid) return fail(c, MKTFHE_ESTATE, "no batch has run yet");
-    CU_TRY(c, cudaSetDevice(c->device));
-    CU_TRY(c, cudaEventSynchronize(c->ev[3]));
     float br = 0.f, ks = 0.f;
-    CU_TRY(c, cudaEventElapsedTime(&br, c->ev[0], c->ev[1]));
-    CU_TRY(c, cudaEventElapsedTime(&ks, c->ev[2], c->ev[3]));
+    bool any = false;
+    for (size_t r = 0; r < n_replicas(c); r++) {   // multi-device: the slowest replica (they run concurrently)
+        mktfhe_ctx* d = replica(c, r);
+        if (!d->ev_valid) continue;
+        any = true;
+        CU_TRY(c, cudaSetDevice(d->device));
+        CU_TRY(c, cudaEventSynchronize(d->ev[3]));
+        float b1 = 0.f, k1 = 0.f;
+        CU_TRY(c, cudaEventElapsedTime(&b1, d->ev[0], d->ev[1]));
+        CU_TRY(c, cudaEventElapsedTime(&k1, d->ev[2], d->ev[3]));
+        br = b1 > br ? b1 : br;
+        ks = k1 > ks ? k1 : ks;
+    }
+    if (!any) return fail(c, MKTFHE_ESTATE, "no batch has run yet");
+    CU_TRY(c, cudaSetDevice(c->device));
     if (blind_rotate_ms) *blind_rotate_ms = br;
     if (keyswitch_ms) *keyswitch_ms = ks;
     return MKTFHE_OK;

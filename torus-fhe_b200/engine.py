@@ -1,10 +1,15 @@
-"""Engine: one GPU context with the parties' keys loaded, plus the multi-GPU plumbing.
+"""Engine: a GPU context with the parties' keys loaded, plus the multi-GPU plumbing.
 
-Multi-GPU model: one process per GPU (torchrun), every rank holds a
-full replica of the bootstrapping and key-switching keys, gate batches are sharded
-across ranks, and the only collective is the one-time key broadcast from rank 0
-(NCCL over NVLink on GPUs; `gloo` on CPU in the tests, which exercises the same
-host logic on plain byte buffers).
+Multi-GPU model: every GPU holds a full replica of the bootstrapping
+and key-switching keys, gate batches are sharded across GPUs, and the only exchange is
+the one-time key broadcast.  Two forms:
+  * inside the library (`Engine(params, devices=[0, 1, ...])` or `devices="all"` ->
+    `mktfhe_create_multi`): one process, one handle; the C ABI broadcasts the keys GPU
+    to GPU in `mktfhe_finalize_keys` and shards every host-pointer batch call.  This is
+    what a Julia caller of `mk_gate_nand_3gen(bk, ks, xs, ys)` gets;
+  * one process per GPU (torchrun): rank 0 loads, `broadcast_keys` moves the key
+    buffers with NCCL (`gloo` on CPU in the tests, which exercises the same host logic
+    on plain byte buffers), the host shards the batch with `shard_bounds`.
 """
 import os
 
@@ -17,14 +22,15 @@ class Engine:
     """Owns a `_cabi.Context`.  Keys come either from the host (`load_keys`) or, on
     non-root ranks, from rank 0 through `broadcast_keys`."""
 
-    def __init__(self, params, device=None):
+    def __init__(self, params, device=None, devices=None):
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
         self.params = params
-        self.device = device
         self.ctx = _cabi.Context(params.lwe_size, params.rlwe_polynomial_degree, params.max_parties,
                                  params.gsw_decomp_length, params.gsw_log2_base,
-                                 params.ks_decomp_length, params.ks_log2_base, device=device)
+                                 params.ks_decomp_length, params.ks_log2_base, device=device, devices=devices)
+        self.device = self.ctx.device          # first (or only) GPU
+        self.devices = list(self.ctx.devices)
         self.ready = False
 
     # bsk: per party int64 [n][4][l][N]; ksk: per party int32 [N][t][B-1][n+1]
@@ -59,6 +65,21 @@ class Engine:
             self.ctx.finalize_keys()
         self.ready = True
         return self
+
+    def ctx_on(self, device):
+        """The single-device context holding the keys on GPU `device` (for the *_dev calls, whose pointers live on one GPU):
+        the context itself for a one-GPU engine, the matching replica of a multi-device one."""
+        if len(self.devices) == 1:
+            if device != self.device:
+                raise ValueError(f"operands live on cuda:{device}, the engine holds its keys on cuda:{self.device}")
+            return self.ctx
+        if not hasattr(self, "_replicas"):
+            self._replicas = {}
+        if device not in self._replicas:
+            if device not in self.devices:
+                raise ValueError(f"operands live on cuda:{device}, the engine spans GPUs {self.devices}")
+            self._replicas[device] = self.ctx.replica(self.devices.index(device))
+        return self._replicas[device]
 
     def close(self):
         self.ctx.close()

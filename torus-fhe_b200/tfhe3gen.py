@@ -504,18 +504,40 @@ def _scheme_params_of(bk, ks):
                                  tg.decomp_length, tg.log2_base, 0.0, ksp.decomp_length, ksp.log2_base, 0.0, len(bk))
 
 
-def engine_for(bk, ks, device=None):
-    tag = (tuple(id(b) for b in bk), tuple(id(k) for k in ks))
+def default_devices():
+    """GPUs a new engine spans when the caller does not say: MKTFHE_B200_DEVICES = "all" | "0,1,2,3" | unset (one GPU: LOCAL_RANK or 0)."""
+    import os
+    v = os.environ.get("MKTFHE_B200_DEVICES", "")
+    if not v:
+        return None
+    return "all" if v == "all" else [int(x) for x in v.split(",")]
+
+
+def _same_keys(tag, bk, ks):
+    """The cache is keyed on the key OBJECTS (held by the tag, compared with `is`): ids alone can alias after garbage collection."""
+    tb, tk = tag
+    return len(tb) == len(bk) and len(tk) == len(ks) and all(a is b for a, b in zip(tb, bk)) and all(a is b for a, b in zip(tk, ks))
+
+
+def engine_for(bk, ks, device=None, devices=None):
+    """The engine holding (bk, ks), created on first use.  `devices` (a list of GPU ordinals or "all") makes it one context
+    spanning those GPUs (mktfhe_create_multi): keys broadcast inside the library, batched gate calls sharded over the GPUs."""
     cached = getattr(bk[0], "_engine", None)
-    if cached is not None and cached[0] == tag:
+    if cached is not None and _same_keys(cached[0], bk, ks):
         return cached[1]
     if bk[0].rlwe_params.is32:
         raise NotImplementedError("rlwe_is32 = true parameter sets are not part of the 3gen path (every 3gen set is Torus64)")
-    eng = Engine(_scheme_params_of(bk, ks), device=device)
+    eng = Engine(_scheme_params_of(bk, ks), device=device, devices=devices if devices is not None else default_devices())
     eng.load_keys([b.gsw_key for b in bk], [k.key for k in ks])
-    bk[0]._engine = ks[0]._engine = (tag, eng)
-    _tag_parts(bk, eng)
-    return eng
+    return attach_engine(bk, ks, eng)
+
+
+def release_engine(bk, ks):
+    """Frees the device key replicas held for (bk, ks) (the engine is otherwise kept alive by the key objects)."""
+    cached = getattr(bk[0], "_engine", None)
+    if cached is not None:
+        cached[1].close()
+        bk[0]._engine = ks[0]._engine = None
 
 
 def _tag_parts(bk, eng):
@@ -533,20 +555,20 @@ class RemoteKeys:
     arrays: the gate API finds the engine through it."""
 
     def __init__(self, eng):
-        self._engine = ((id(self),), eng)
+        self._engine = None
         self.tgsw_params, self.rlwe_params = tgsw_parameters(eng.params), rlwe_parameters(eng.params)
 
     @staticmethod
     def pair(eng):
         r = RemoteKeys(eng)
         bk, ks = [r] * eng.params.max_parties, [r] * eng.params.max_parties
-        r._engine = ((tuple(id(b) for b in bk), tuple(id(k) for k in ks)), eng)
+        r._engine = ((tuple(bk), tuple(ks)), eng)
         return bk, ks
 
 
 def attach_engine(bk, ks, eng):
     """Make `eng` (already holding these keys) the engine the gate API uses for (bk, ks)."""
-    bk[0]._engine = ks[0]._engine = ((tuple(id(b) for b in bk), tuple(id(k) for k in ks)), eng)
+    bk[0]._engine = ks[0]._engine = ((tuple(bk), tuple(ks)), eng)
     _tag_parts(bk, eng)
     return eng
 
@@ -561,14 +583,18 @@ def _gate_gpu(eng, gate, x, y, z):
     k, n = eng.params.max_parties, eng.params.lwe_size
     ops = [(t.a.reshape(-1, k, n).contiguous(), t.b.reshape(-1).contiguous()) for t in (x, y) + ((z,) if z is not None else ())]
     G = ops[0][1].numel()
+    dev = ops[0][0].device
+    if any(t.device != dev for op in ops for t in op):
+        raise ValueError("gate operands live on different devices")
+    ctx = eng.ctx_on(dev.index)                 # raises when the engine holds no key replica on the operands' GPU
     oa = torch.empty((G, k, n), dtype=torch.int32, device=ops[0][0].device)
     ob = torch.empty(G, dtype=torch.int32, device=ops[0][0].device)
     za, zb = (ops[2][0].data_ptr(), ops[2][1].data_ptr()) if z is not None else (0, 0)
     stream = torch.cuda.current_stream(ops[0][0].device).cuda_stream
     if not stream:                      # legacy default stream: the library then works on the context's own (non-blocking) stream, which
         torch.cuda.synchronize(ops[0][0].device)     # does not wait for the default stream -- the operands must be complete first
-    eng.ctx.gate_batch_dev(gate, G, ops[0][0].data_ptr(), ops[0][1].data_ptr(), ops[1][0].data_ptr(), ops[1][1].data_ptr(), za, zb,
-                           oa.data_ptr(), ob.data_ptr(), stream=stream)
+    ctx.gate_batch_dev(gate, G, ops[0][0].data_ptr(), ops[0][1].data_ptr(), ops[1][0].data_ptr(), ops[1][1].data_ptr(), za, zb,
+                       oa.data_ptr(), ob.data_ptr(), stream=stream)
     if not stream:                      # legacy default stream: the context's own stream did the work
         torch.cuda.synchronize(ops[0][0].device)
     shape = tuple(x.b.shape)
