@@ -147,6 +147,49 @@ def generate_keys(T, params, rng):
     return secret_keys, bk, ks
 
 
+def profile_evidence(T, parties, lib_path):
+    """Measured constants the roofline quotes, read from files under profiles/ (never literals): the IMAD-pipe peak and the HBM
+    key-stream rate from the micro-benchmarks, and -- only when the capture manifest belongs to THIS library's machine code and
+    parameter set -- the DRAM traffic and pipe-busy figures of the dominant kernel's `ncu --set full` capture."""
+    import hashlib
+    import re
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from kernel_id import kernel_id
+    prof = os.path.join(ROOT, "profiles")
+    ev = {"kernel_id": kernel_id(lib_path), "imad_peak": None, "key_stream": None, "capture": None, "capture_note": None}
+
+    def sha(path):
+        return hashlib.sha256(open(path, "rb").read()).hexdigest()[:16]
+    try:
+        f = os.path.join(prof, "pipe_ubench_r1.txt")
+        m = re.search(r"^IMAD \(lo\)\s+[\d.]+ ms\s+([\d.]+) T thread-ops/s\s+\(([\d.]+) lanes/clk/SM", open(f).read(), flags=re.M)
+        ev["imad_peak"] = {"value": float(m.group(1)) * 1e12, "lanes_per_clk_sm": float(m.group(2)), "source": "profiles/pipe_ubench_r1.txt", "sha256": sha(f)}
+    except Exception as e:
+        ev["imad_peak_note"] = f"profiles/pipe_ubench_r1.txt unreadable: {e}"
+    try:
+        f = os.path.join(prof, "key_stream_ubench_r1.txt")
+        m = re.search(r"x 1 CTAs x 12 warps.*?:\s+([\d.]+) GB/s", open(f).read())
+        ev["key_stream"] = {"value": float(m.group(1)), "source": "profiles/key_stream_ubench_r1.txt (the kernel's key access pattern over a 4 GiB buffer at "
+                            "the kernel's occupancy; in the product L2 serves the stream)", "sha256": sha(f)}
+    except Exception:
+        pass
+    f = os.path.join(prof, f"ncu_capture_{parties}party.json")
+    if not os.path.exists(f):
+        ev["capture_note"] = f"no ncu capture manifest for the {parties}-party set (profiles/ncu_capture_{parties}party.json)"
+    else:
+        man = json.load(open(f))
+        summ = os.path.join(ROOT, man["summary_file"])
+        if ev["kernel_id"] is None:
+            ev["capture_note"] = "cuobjdump unavailable: the library's kernel identity could not be checked against the capture"
+        elif man["kernel_id"] != ev["kernel_id"]:
+            ev["capture_note"] = f"capture {man['summary_file']} was taken from kernel id {man['kernel_id']}, this library is {ev['kernel_id']}: not quoted"
+        elif not os.path.exists(summ) or hashlib.sha256(open(summ, "rb").read()).hexdigest() != man["summary_sha256"]:
+            ev["capture_note"] = f"{man['summary_file']} is missing or does not match the manifest's sha256: not quoted"
+        else:
+            ev["capture"] = man
+    return ev
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -157,6 +200,13 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU baseline)")
+    # --abi-multi: ONE process drives args.gpus GPUs through one mktfhe_create_multi context (what a Julia host gets);
+    # default: one process per GPU (torchrun), NCCL key broadcast by the host side
+    ndev = args.gpus if args.abi_multi else 1
+    if args.abi_multi and world > 1:
+        raise SystemExit("bench.py: --abi-multi is a single-process mode (do not launch it under torchrun)")
+    if ndev > torch.cuda.device_count():
+        raise SystemExit(f"bench.py: --abi-multi --gpus {ndev} but {torch.cuda.device_count()} GPUs are visible")
     torch.cuda.set_device(local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
@@ -165,23 +215,25 @@ def run_ours(args):
     params = {2: T.mktfhe_parameters_2party_3gen, 3: T.mktfhe_parameters_3party_3gen, 4: T.mktfhe_parameters_4party_3gen,
               5: T.mktfhe_parameters_5party_3gen, 8: T.mktfhe_parameters_8party_3gen, 16: T.mktfhe_parameters_16party_3gen}[args.parties]
     G, k, n = args.gates, params.max_parties, params.lwe_size
-    eng = T.Engine(params, device=local)
+    devices = list(range(ndev)) if args.abi_multi else None
+    eng = T.Engine(params, device=local, devices=devices)
     rng = np.random.default_rng(KEY_SEED)
     secret_keys = None
     t_keys = time.perf_counter()
     if rank == 0:
         secret_keys, bk, ks = generate_keys(T, params, rng)
-        eng.load_keys([b.gsw_key for b in bk], [q.key for q in ks])
+        eng.load_keys([b.gsw_key for b in bk], [q.key for q in ks])      # multi-device context: includes the in-library broadcast
     if world > 1:
         eng.broadcast_keys(src=0)
     t_keys = time.perf_counter() - t_keys
     ctx = eng.ctx
+    GT = G * ndev                                     # gates this process handles per step (weak scaling: G per GPU)
 
     # synthetic random ciphertexts (timing is data-independent); the first 64 gates of every batch are valid encryptions
     # so rank 0 can check the decrypted truth table of exactly the batches it timed
     drng = np.random.default_rng(DATA_SEED + rank)
-    host = [torch.empty((G, k, n), dtype=torch.int32).pin_memory(), torch.empty(G, dtype=torch.int32).pin_memory(),
-            torch.empty((G, k, n), dtype=torch.int32).pin_memory(), torch.empty(G, dtype=torch.int32).pin_memory()]
+    host = [torch.empty((GT, k, n), dtype=torch.int32).pin_memory(), torch.empty(GT, dtype=torch.int32).pin_memory(),
+            torch.empty((GT, k, n), dtype=torch.int32).pin_memory(), torch.empty(GT, dtype=torch.int32).pin_memory()]
     for h in host:
         h.numpy()[...] = drng.integers(-2 ** 31, 2 ** 31, size=tuple(h.shape), dtype=np.int64).astype(np.int32)
     V = min(64, G)
@@ -189,26 +241,38 @@ def run_ours(args):
     if secret_keys is not None:
         ex, ey = T.mk_encrypt_3gen(drng, secret_keys, bits[0]), T.mk_encrypt_3gen(drng, secret_keys, bits[1])
         host[0].numpy()[:V], host[1].numpy()[:V], host[2].numpy()[:V], host[3].numpy()[:V] = ex.a, ex.b, ey.a, ey.b
-    dev = [h.cuda(non_blocking=False) for h in host]
-    out_a = torch.empty((G, k, n), dtype=torch.int32, device="cuda")
-    out_b = torch.empty(G, dtype=torch.int32, device="cuda")
-    host_oa, host_ob = torch.empty((G, k, n), dtype=torch.int32).pin_memory(), torch.empty(G, dtype=torch.int32).pin_memory()
-    stream = torch.cuda.Stream()          # kernels are launched on THIS stream; the CUDA events below are recorded on it
-    torch.cuda.set_stream(stream)
+    host_oa, host_ob = torch.empty((GT, k, n), dtype=torch.int32).pin_memory(), torch.empty(GT, dtype=torch.int32).pin_memory()
+    # per GPU of this process: the replica context, its slice of the inputs resident in HBM, outputs, a stream
+    reps = []
+    for i in range(ndev):
+        d = eng.devices[i] if args.abi_multi else local
+        lo, hi = ctx.shard_bounds(GT, i) if args.abi_multi else (0, G)
+        with torch.cuda.device(d):
+            st = torch.cuda.Stream(device=d)      # kernels are launched on THIS stream; the CUDA events below are recorded on it
+            reps.append({"dev": d, "ctx": ctx.replica(i) if ndev > 1 else ctx, "n": hi - lo, "stream": st,
+                         "in": [h[lo:hi].to(f"cuda:{d}") for h in host],
+                         "oa": torch.empty((hi - lo, k, n), dtype=torch.int32, device=f"cuda:{d}"),
+                         "ob": torch.empty(hi - lo, dtype=torch.int32, device=f"cuda:{d}")})
 
     def step_dev():
-        ctx.gate_batch_dev(T._cabi.GATE_NAND, G, dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), dev[3].data_ptr(), 0, 0,
-                           out_a.data_ptr(), out_b.data_ptr(), stream=stream.cuda_stream)
+        for r in reps:
+            i = r["in"]
+            r["ctx"].gate_batch_dev(T._cabi.GATE_NAND, r["n"], i[0].data_ptr(), i[1].data_ptr(), i[2].data_ptr(), i[3].data_ptr(), 0, 0,
+                                    r["oa"].data_ptr(), r["ob"].data_ptr(), stream=r["stream"].cuda_stream)
 
     def step_host():
         ctx.gate_batch(T._cabi.GATE_NAND, (host[0].numpy(), host[1].numpy()), (host[2].numpy(), host[3].numpy()),
                        out=(host_oa.numpy(), host_ob.numpy()))
 
+    def sync_all():
+        for r in reps:
+            torch.cuda.synchronize(r["dev"])
+
     def barrier():
-        torch.cuda.synchronize()
+        sync_all()
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        sync_all()
 
     def max_over_ranks(x):
         if world == 1:
@@ -225,17 +289,19 @@ def run_ours(args):
         sampler.start()
     # ---- timed region: device-resident inputs -------------------------------------------------------------------
     launches0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    br_ms = ks_ms = 0.0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in reps]
     barrier()
-    e0.record(stream)
+    for r, (e0, _) in zip(reps, ev):
+        e0.record(r["stream"])
     for _ in range(args.steps):
         step_dev()
-    e1.record(stream)
+    for r, (_, e1) in zip(reps, ev):
+        e1.record(r["stream"])
     barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms = max_over_ranks(max(e0.elapsed_time(e1) for e0, e1 in ev))      # slowest GPU of this process, then of all ranks
     launches = ctx.launch_count() - launches0
-    br_ms, ks_ms = ctx.last_kernel_ms()           # the last step's two kernels, CUDA events on the launching stream
+    br_ms, ks_ms = ctx.last_kernel_ms()           # the last step's two kernels (multi-device: slowest GPU), CUDA events on the launching stream
+    fused_ks = bool(reps[0]["ctx"].describe()["keyswitch_fused"])       # reported by the library, not inferred from a timing
     # ---- e2e: host-pointer C-ABI call, pinned host buffers, H2D and D2H inside the timed region --------------------
     step_host()
     barrier()
@@ -246,76 +312,88 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None
 
-    # latency of ONE bootstrap alone on the GPU (the reference's own protocol times single calls: perf_comp.jl:126)
-    lat_ms = None
+    # latency of ONE bootstrap alone on a GPU: the reference's own protocol times single calls, min / median of 100
+    # (measurements/test_suites/performance_comparison_test/perf_comp.jl:20,126-142)
+    lat = None
     if rank == 0:
-        one = [d[:1].contiguous() for d in dev]
-        for _ in range(2):
-            ctx.gate_batch_dev(T._cabi.GATE_NAND, 1, one[0].data_ptr(), one[1].data_ptr(), one[2].data_ptr(), one[3].data_ptr(), 0, 0,
-                               out_a.data_ptr(), out_b.data_ptr(), stream=stream.cuda_stream)
-        torch.cuda.synchronize()
-        lat_ms = sum(ctx.last_kernel_ms())
+        r = reps[0]
+        one = [d[:1].contiguous() for d in r["in"]]
+        samples = []
+        for it in range(args.latency_trials + 3):
+            r["ctx"].gate_batch_dev(T._cabi.GATE_NAND, 1, one[0].data_ptr(), one[1].data_ptr(), one[2].data_ptr(), one[3].data_ptr(), 0, 0,
+                                    r["oa"].data_ptr(), r["ob"].data_ptr(), stream=r["stream"].cuda_stream)
+            torch.cuda.synchronize(r["dev"])
+            if it >= 3:
+                samples.append(sum(r["ctx"].last_kernel_ms()))
+        lat = {"min": float(np.min(samples)), "median": float(np.median(samples)), "trials": len(samples)}
     ok = None
     if secret_keys is not None:
         got = T.mk_decrypt_3gen(secret_keys, T.MKLweSample(None, host_oa.numpy()[:V], host_ob.numpy()[:V]))
-        got_dev = T.mk_decrypt_3gen(secret_keys, T.MKLweSample(None, out_a[:V].cpu().numpy(), out_b[:V].cpu().numpy()))
+        got_dev = T.mk_decrypt_3gen(secret_keys, T.MKLweSample(None, reps[0]["oa"][:V].cpu().numpy(), reps[0]["ob"][:V].cpu().numpy()))
         ok = bool(np.array_equal(got, ~(bits[0] & bits[1])) and np.array_equal(got_dev, got))
 
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
         N, l = params.rlwe_polynomial_degree, params.gsw_decomp_length
-        bsk_1limb = k * n * 4 * l * N * 8                         # 68.2 MB per 2-party bootstrap (reference FFT key size)
-        bsk_stream, ksk_gather = ctx.algorithmic_bytes()          # what this build streams (three u32 residues per coefficient) / gathers per gate
+        big = N != 1024            # N = 2048 sets: no slot model / ncu capture manifest
+        evd = profile_evidence(T, k, T._cabi.LIB_PATH)
+        bsk_1limb = k * n * 4 * l * N * 8                         # 68.2 MB per 2-party bootstrap (the reference's transformed key size)
+        bsk_stream, ksk_gather = ctx.algorithmic_bytes()          # what this build streams (u32 residues per coefficient) / gathers per gate
         ct_io = 2 * (k * n + 1) * 4 + (N + 1) * 4
-        fused_ks = ks_ms <= 0.05                                  # the key switch ran as the epilogue of the blind-rotate kernel
-        per_gate = bsk_1limb + ct_io + (ksk_gather if fused_ks else 0)   # 68.2 MB key + 11.2 MB gathered ksk rows + ciphertext I/O
-        alg_bytes = G * per_gate
-        achieved = alg_bytes / (br_ms * 1e-3) / 1e9
+        per_gate = bsk_1limb + ct_io + (ksk_gather if fused_ks else 0)   # key + gathered ksk rows + ciphertext I/O
+        Gk = max(r["n"] for r in reps)                            # gates in the launch that br_ms timed (the slowest GPU's slice)
+        hbm_achieved = Gk * per_gate / (br_ms * 1e-3) / 1e9
         # algorithmic IMAD-pipe slots per gate of the three-prime RNS formulation, counting only work the
         # formulation cannot avoid: per blind-rotate step 6l forward NTTs of 4608 multiplying butterflies (the first stage of a digit
         # transform is a table lookup) and 6 inverse NTTs of 5120, 4 slots each (IMAD.HI is half rate); 12l x 1024 pointwise products
         # accumulated in 64 bits (IMAD.WIDE = 2 slots) + 6 x 1024 Montgomery reductions (3 slots); 2048 CRT lifts (17 slots)
         imad_slots = k * n * ((6 * l * 4608 + 6 * 5120) * 4 + 12 * l * 1024 * 2 + 6 * 1024 * 3 + 2 * 1024 * 17)
-        imad_peak = 18.26e12       # measured: tools/pipe_ubench.cu -> profiles/pipe_ubench_r1.txt (62.8 IMAD lanes/clk/SM)
-        ncu_traffic = {"bytes_in_captured_launch": 1.589e9, "gates_in_captured_launch": 2368, "waves_in_captured_launch": 8,
-                       "source": "profiles/ncu_r1_n_blind_rotate.txt (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture of a "
-                                 "2368-gate launch): one pass over bsk (102 MB) + ksk (90 MB) per wave of 296 gates, i.e. 0.67 MB per gate against "
-                                 "68 MB algorithmic; scaled here to this launch's gate count"}
-        traffic = ncu_traffic["bytes_in_captured_launch"] * G / ncu_traffic["gates_in_captured_launch"]
-        value = world * G * args.steps / (ms * 1e-3)
-        big = N != 1024            # N = 2048 sets: first functional kernels, no slot model / ncu capture yet
-        line = {"metric": METRIC.replace("2-party", f"{k}-party"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        cap, peak = evd["capture"], evd["imad_peak"]
+        traffic = cap["dram_bytes"] * Gk / cap["gates_in_launch"] if cap else None
+        imad = None
+        if not big and peak:
+            imad = {"achieved": Gk * imad_slots / (br_ms * 1e-3) / 1e12, "peak": peak["value"] / 1e12, "unit": "T IMAD-slots/s",
+                    "frac": Gk * imad_slots / (br_ms * 1e-3) / peak["value"]}
+        value = world * GT * args.steps / (ms * 1e-3)
+        hbm = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak, "peak_source": peak_src,
+               "algorithmic_bytes_per_gate": per_gate,
+               "algorithmic_bytes_breakdown": {"bsk_reference_transformed_size": bsk_1limb, "ksk_rows_gathered": ksk_gather if fused_ks else 0, "ciphertext_io": ct_io},
+               "streamed_bytes_per_gate_this_build": bsk_stream,
+               "note": "the contract's HBM figure over ALGORITHMIC bytes (SURVEY 8d); these bytes are served by L2 (see traffic), so HBM does not bind",
+               "key_stream_from_hbm_GBps": dict(evd["key_stream"], frac_of_peak=evd["key_stream"]["value"] / hbm_peak) if evd["key_stream"] else None}
+        roofline = {"kernel": "blind_rotate2k_kernel" if big else "blind_rotate_kernel", "kernel_id": evd["kernel_id"], "kernel_ms": br_ms,
+                    "gates_in_timed_launch": Gk, "keyswitch_ms": ks_ms, "keyswitch_fused_into_blind_rotate": fused_ks,
+                    "keyswitch_gather_GBps": None if fused_ks or ks_ms <= 0 else Gk * ksk_gather / (ks_ms * 1e-3) / 1e9,
+                    "kernel_share_of_step": br_ms / (ms / args.steps),
+                    "traffic": traffic, "traffic_source": ({"file": cap["summary_file"], "sha256": cap["summary_sha256"][:16], "kernel_id": cap["kernel_id"],
+                                                            "dram_bytes_in_captured_launch": cap["dram_bytes"], "gates_in_captured_launch": cap["gates_in_launch"],
+                                                            "l2_hit_rate": cap["l2_hit_rate"], "scaled": "x gates in this launch / gates in the captured launch"}
+                                                           if cap else evd["capture_note"]),
+                    "hbm": hbm}
+        if imad:          # primary bound: the integer multiply pipe; HBM figure kept beside it as the contract asks
+            roofline.update({"bound": "imad_pipe", "achieved": imad["achieved"], "peak": imad["peak"], "unit": imad["unit"], "frac": imad["frac"],
+                             "algorithmic_slots_per_gate": imad_slots,
+                             "peak_source": {k2: peak[k2] for k2 in ("source", "sha256", "lanes_per_clk_sm")},
+                             "ncu_fmaheavy_pipe_busy": cap["fmaheavy_pipe_busy"] if cap else None, "ncu_issue_active": cap["issue_active"] if cap else None,
+                             "ncu_source": cap["summary_file"] if cap else evd["capture_note"]})
+        else:
+            roofline.update({k2: hbm[k2] for k2 in ("bound", "achieved", "peak", "unit", "frac")})
+        line = {"metric": METRIC.replace("2-party", f"{k}-party"), "value": value, "unit": UNIT, "n_gpus": world * ndev, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "ms_per_bootstrap_amortized": ms / args.steps / G,
-                "ms_single_bootstrap_latency": lat_ms, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": ("u32 RNS (four 28-bit-prime NTTs + CRT, exact mod 2^64) / int32 LWE" if N != 1024 else "u32 RNS (three 28-bit-prime NTTs + CRT, exact mod 2^64) / int32 LWE"), "data": "synthetic",
+                "ms_single_bootstrap_latency": lat, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": ("u32 RNS (four 28-bit-prime NTTs + CRT, exact mod 2^64) / int32 LWE" if big else "u32 RNS (three 28-bit-prime NTTs + CRT, exact mod 2^64) / int32 LWE"), "data": "synthetic",
                 "config": {"workload": f"{k}-party NAND x{G} per GPU (mktfhe_parameters_{k}party_3gen: n={n} N={N} l={l} Bg=2^{params.gsw_log2_base} "
                                        f"t={params.ks_decomp_length} Bks=2^{params.ks_log2_base})",
-                           "gates_per_step_per_gpu": G, "parallelism": f"gate-sharded replicas x{world}",
+                           "gates_per_step_per_gpu": G,
+                           "parallelism": (f"one process, one C-ABI context spanning {ndev} GPUs (mktfhe_create_multi): gate-sharded replicas, key broadcast "
+                                           f"{ctx.describe()['key_broadcast']}" if args.abi_multi else f"gate-sharded replicas x{world} (one process per GPU)"),
                            "l2_policy": f"inputs ({2 * G * (k * n + 1) * 4 / 1e6:.0f} MB/step) + keys ({(bsk_stream + ctx.key_buffers()[1][1]) / 1e6:.0f} MB) exceed the 126 MB L2; no flush needed",
-                           "keys": "generated by the product host mirror (GPU exact products), broadcast over NCCL" if world > 1 else
-                                   "generated by the product host mirror (GPU exact products)", "key_setup_s": round(t_keys, 2)},
-                "e2e": {"value": world * G * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(2 * (G * k * n + G) * 4),
-                        "d2h_bytes_per_step": int((G * k * n + G) * 4)},
-                "gpu_launches": int(launches),
-                "roofline": {"kernel": "blind_rotate_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": achieved / hbm_peak, "traffic": None if big else traffic, "traffic_note": None if big else ncu_traffic, "peak_source": peak_src,
-                             "note": "contract roofline (HBM); the kernel is IMAD-pipe bound and streams the key from L2 (hit rate 98 %): see integer_bound",
-                             "algorithmic_bytes_per_gate": per_gate, "algorithmic_bytes_breakdown": {"bsk": bsk_1limb, "ksk_rows_gathered": ksk_gather if fused_ks else 0,
-                                                                                                       "ciphertext_io": ct_io},
-                             "streamed_bytes_per_gate_this_build": bsk_stream,
-                             "key_stream_from_hbm_GBps": {"value": 5793, "frac_of_peak": 5793 / hbm_peak, "source": "profiles/key_stream_ubench_r1.txt: the kernel's key access "
-                                                           "pattern over a 4 GiB buffer at the kernel's occupancy (in the product L2 serves the stream)"},
-                             "kernel_ms": br_ms, "keyswitch_ms": ks_ms, "keyswitch_gather_GBps": (G * ksk_gather / (ks_ms * 1e-3) / 1e9) if ks_ms > 0.05 else None,
-                             "keyswitch_fused_into_blind_rotate": ks_ms <= 0.05,
-                             "kernel_share_of_step": br_ms / (ms / args.steps),
-                             "integer_bound": None if big else {"bound": "imad_pipe", "algorithmic_slots_per_gate": imad_slots,
-                                               "achieved": G * imad_slots / (br_ms * 1e-3) / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-slots/s",
-                                               "frac": G * imad_slots / (br_ms * 1e-3) / imad_peak,
-                                               "ncu_fmaheavy_pipe_busy": 0.66, "ncu_issue_active": 0.57,
-                                               "ncu_source": "profiles/ncu_r1_n_blind_rotate.txt, ncu_r1_n_opmix.txt (executed fma-pipe slots incl. "
-                                               "address/move overhead: 15.1 k warp-slots per gate-step)"}},
-                "clocks": clocks, "decryptions_correct": ok}
-        if world == 1 and not args.no_cpu_baseline and args.parties == 2:
+                           "keys": "generated by the product host mirror (GPU exact products)" + (", broadcast over NCCL" if world > 1 else
+                                   ", broadcast inside mktfhe_finalize_keys" if ndev > 1 else ""), "key_setup_s": round(t_keys, 2)},
+                "e2e": {"value": world * GT * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(2 * (GT * k * n + GT) * 4),
+                        "d2h_bytes_per_step": int((GT * k * n + GT) * 4)},
+                "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "decryptions_correct": ok}
+        if world * ndev == 1 and not args.no_cpu_baseline and args.parties == 2:
             O, oks = oracle_keyset()
             cores = host_cores()
             cnt = max(cores, 8) * 4
@@ -489,6 +567,9 @@ def main():
     ap.add_argument("--parties", type=int, default=2, choices=[2, 3, 4, 5, 8, 16],
                     help="parameter set (BASELINE configs[2]: 4 and 8; 16 = the first N = 2048 set, one gate per SM: use --gates 148 or a multiple)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--abi-multi", action="store_true", help="one process, ONE C-ABI context spanning --gpus GPUs (mktfhe_create_multi) instead of one "
+                                                             "process per GPU under torchrun")
+    ap.add_argument("--latency-trials", type=int, default=100, help="single-bootstrap latency: min / median over this many calls")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="nand", choices=["nand", "adder", "less", "conv"],
                     help="nand = the headline metric; adder / less = BASELINE configs[3] (adder, comparator); conv = BASELINE configs[4]")

@@ -89,7 +89,8 @@ void mktfhe_destroy(mktfhe_ctx *ctx);
 /* GPUs a context spans (1 for mktfhe_create) */
 int mktfhe_device_count(const mktfhe_ctx *ctx);
 /* replica i of a multi-device context as a single-device context (i = 0: ctx itself) and its CUDA device ordinal, for the
- * *_dev entry points, which take pointers into one GPU; the replica is owned by ctx (do not destroy it). */
+ * *_dev entry points, which take pointers into ONE GPU: called on the spanning handle they address its first GPU (replica 0),
+ * the other GPUs are reached through their replicas.  A replica is owned by ctx (do not destroy it). */
 int mktfhe_device_ctx(mktfhe_ctx *ctx, int i, mktfhe_ctx **replica, int *device);
 /* the contiguous slice [lo, hi) of a batch of G that replica i processes in the host-pointer calls */
 int mktfhe_shard_bounds(const mktfhe_ctx *ctx, size_t G, int i, size_t *lo, size_t *hi);

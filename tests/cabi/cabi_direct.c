@@ -131,7 +131,6 @@ int main(int argc, char **argv) {
         ids[GM - 1] = 77;
         CHECK(mktfhe_gate_batch_mixed(mc, GM, ids, mxa, mxb, mya, myb, mza, mzb, moa, mob) == MKTFHE_EINVAL && strstr(mktfhe_last_error(mc), "device"),
               "a bad gate id in the last slice must surface with the device named: %s", mktfhe_last_error(mc));
-        CHECK(mktfhe_gate_batch_dev(mc, MKTFHE_GATE_NAND, 1, mxa, mxb, mya, myb, NULL, NULL, moa, mob, NULL) == MKTFHE_EINVAL, "_dev on a multi-device context");
         mktfhe_ctx *r1 = NULL; int d1 = -1;
         CHECK(mktfhe_device_ctx(mc, nd - 1, &r1, &d1) == MKTFHE_OK && r1 && d1 == devs[nd - 1], "device_ctx");
         char desc[512];

@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Identity of the hot kernels of a built libmktfhe_b200.so: sha256 over the SASS text (cuobjdump) of every blind_rotate kernel.
+Source edits that leave the machine code unchanged keep the id; bench.py compares it with the id recorded beside each ncu capture
+under profiles/ and refuses to quote a capture taken from other machine code.
+   python tools/kernel_id.py [path/to/libmktfhe_b200.so]"""
+import hashlib
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def kernel_id(lib=None, match="blind_rotate"):
+    lib = lib or os.path.join(ROOT, "torus-fhe_b200", "libmktfhe_b200.so")
+    try:
+        out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, timeout=300).stdout
+    except Exception:
+        return None
+    h, keep, n = hashlib.sha256(), False, 0
+    for line in out.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            keep = match in m.group(1)
+            if keep:
+                h.update(m.group(1).encode()); n += 1
+            continue
+        if keep:
+            m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(.*?);", line)
+            if m:
+                h.update(m.group(1).encode())
+    return h.hexdigest()[:16] if n else None
+
+
+if __name__ == "__main__":
+    print(kernel_id(sys.argv[1] if len(sys.argv) > 1 else None))

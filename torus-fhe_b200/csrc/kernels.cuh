@@ -42,11 +42,8 @@ constexpr int N = rns::N;
 #define MK_MAXNREG 168
 #endif
 #ifndef MK_S_UNROLL
-#define MK_S_UNROLL (MK_PEEL ? 4 : MK_WPG == 6 ? 1 : 2)           // unroll factor of the loop over digit polynomials
+#define MK_S_UNROLL (MK_WPG == 6 ? 1 : 2)           // unroll factor of the loop over digit polynomials
 #endif
-#ifndef MK_PEEL
-#define MK_PEEL 0           // 1 (with MK_S_UNROLL = l): the first digit pair DEFINES the 64-bit accumulators instead of adding to zeros, so
-#endif                      // they are not live (64 registers) during the first forward transform of a step
 #ifndef MK_ACC64
 #define MK_ACC64 1          // 1: the 2L products of a point accumulate in 64 bits, one Montgomery reduction; 0: one per pair
 #endif
@@ -69,9 +66,6 @@ constexpr int N = rns::N;
 #endif
 #ifndef MK_LOCKSTEP
 #define MK_LOCKSTEP 0       // n > 0: CTA-wide barrier every n steps to keep the gates on the same key element (measured: loses)
-#endif
-#ifndef MK_LAT2
-#define MK_LAT2 0           // experiment: throughput launch = two latency-split gates per CTA (l = 2 only)
 #endif
 #ifndef MK_STAGGER_NS
 #define MK_STAGGER_NS 0     // start odd gate slots this many ns late to interleave the IMAD-free phases (measured: loses)
@@ -421,10 +415,8 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
 #if MK_ACC64
         // all 2L products of a point accumulate in 64 bits (each < 2^60, 2L <= 8) and are Montgomery-reduced once
         u64 acc64[32];
-#if !MK_PEEL
 #pragma unroll
         for (int c = 0; c < 32; c++) acc64[c] = 0;
-#endif
 #else
         u32 accv[32];
 #pragma unroll
@@ -444,14 +436,7 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
 #pragma unroll
             for (int q4 = 0; q4 < 8; q4++) {
                 const uint4 ka = MK_KEY_LD(k_own + q4 * 32), kb = MK_KEY_LD(k_for + q4 * 32);
-#if MK_ACC64 && MK_PEEL
-                const u64 pr0 = (u64)x[4 * q4 + 0] * ka.x + (u64)ptile[(4 * q4 + 0) * 32 + lane] * kb.x;
-                const u64 pr1 = (u64)x[4 * q4 + 1] * ka.y + (u64)ptile[(4 * q4 + 1) * 32 + lane] * kb.y;
-                const u64 pr2 = (u64)x[4 * q4 + 2] * ka.z + (u64)ptile[(4 * q4 + 2) * 32 + lane] * kb.z;
-                const u64 pr3 = (u64)x[4 * q4 + 3] * ka.w + (u64)ptile[(4 * q4 + 3) * 32 + lane] * kb.w;
-                if (i == 0) { acc64[4 * q4 + 0] = pr0; acc64[4 * q4 + 1] = pr1; acc64[4 * q4 + 2] = pr2; acc64[4 * q4 + 3] = pr3; }
-                else { acc64[4 * q4 + 0] += pr0; acc64[4 * q4 + 1] += pr1; acc64[4 * q4 + 2] += pr2; acc64[4 * q4 + 3] += pr3; }
-#elif MK_ACC64
+#if MK_ACC64
                 acc64[4 * q4 + 0] += (u64)x[4 * q4 + 0] * ka.x + (u64)ptile[(4 * q4 + 0) * 32 + lane] * kb.x;
                 acc64[4 * q4 + 1] += (u64)x[4 * q4 + 1] * ka.y + (u64)ptile[(4 * q4 + 1) * 32 + lane] * kb.y;
                 acc64[4 * q4 + 2] += (u64)x[4 * q4 + 2] * ka.z + (u64)ptile[(4 * q4 + 2) * 32 + lane] * kb.z;
@@ -741,12 +726,6 @@ __global__ void __maxnreg__(MK_MAXNREG) blind_rotate_kernel(BlindRotateArgs p) {
 // latency launch: one gate per CTA, 6 l warps (168 registers at l = 2, 112 at l = 3, 80 at l = 4: a latency warp keeps no wide accumulators)
 template <int L>
 __global__ void __launch_bounds__(32 * lat_wpg(L), 1) blind_rotate_lat_kernel(BlindRotateArgs p) { blind_rotate_body<L, 1, lat_wpg(L)>(p); }
-
-#if MK_LAT2
-// experiment (profiles/ab_r2.txt): the latency split as a throughput shape -- two gates per CTA, 6 l warps each (24 warps at 80 registers, l = 2)
-template <int L>
-__global__ void __launch_bounds__(2 * 32 * lat_wpg(L), 1) blind_rotate_lat2_kernel(BlindRotateArgs p) { blind_rotate_body<L, 2, lat_wpg(L)>(p); }
-#endif
 
 // parity hook: acc_out[g] = ExtProd(acc_in[g], bsk[elem[g]])
 template <int L, int GPC>

@@ -59,6 +59,10 @@ struct mktfhe_ctx {
     // additional GPU; host-pointer batch calls shard [G] contiguously over all replicas, one host thread per replica
     std::vector<mktfhe_ctx*> kids;
     bool is_kid = false;
+    mktfhe_ctx* parent = nullptr;   // replicas 1.. point at the spanning context
+    uint64_t seq = 0;               // spanning context: number of bootstrap-like calls so far; ev_seq: the call that last recorded this replica's events
+    uint64_t ev_seq = 0;
+    bool in_shard_call = false;     // a sharded host-pointer call is in flight: its replicas all belong to call `seq`
     std::string bcast_how;       // how the keys reached the replicas ("p2p" / "nccl"), for mktfhe_describe
 };
 
@@ -191,17 +195,6 @@ void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G, 
     // (the partial last wave of the throughput grid cost 3 ms there, not a full wave), profiles/ab_r1.txt
     if (tail > (size_t)c->num_sms || ((!c->split_tail || c->prm.l != 2) && tail != G)) tail = 0;
     const size_t head = G - tail;
-#if MK_LAT2
-    if (head && c->prm.l == 2) {
-        mk::BlindRotateArgs h = a;
-        h.g0 = 0; h.G = (int)head;
-        const size_t sm2 = mk::TW_SMEM_BYTES + 2 * mk::gate_smem_bytes(2, mk::lat_wpg(2));
-        static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(mk::blind_rotate_lat2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2); attr_set = true; }
-        mk::blind_rotate_lat2_kernel<2><<<(unsigned)((head + 1) / 2), 2 * 32 * mk::lat_wpg(2), sm2, st>>>(h);
-        c->launches++;
-    } else
-#endif
     if (head) {
         mk::BlindRotateArgs h = a;
         h.g0 = 0; h.G = (int)head;
@@ -240,6 +233,11 @@ int run_bootstrap_dev(mktfhe_ctx* c, mk::GateLinear lin, int64_t mu, size_t G, c
         ext = (int32_t*)c->ext.p;
     }
     c->ev_valid = false;
+    {
+        mktfhe_ctx* root = c->parent ? c->parent : c;
+        if (!root->in_shard_call) root->seq++;
+        c->ev_seq = root->seq;
+    }
     CU_TRY(c, cudaEventRecord(c->ev[0], st));
     if (big) {
         // N = 2048: one gate per CTA (kernels2k.cuh); the key switch is the kernel's epilogue when its shape is covered
@@ -297,6 +295,8 @@ int for_each_shard(mktfhe_ctx* c, size_t G, F f) {
     std::vector<int> rc(R, MKTFHE_OK);
     std::vector<std::thread> th;
     th.reserve(R);
+    c->seq++;
+    c->in_shard_call = true;
     for (size_t r = 1; r < R; r++) {
         size_t lo, hi;
         shard_bounds(G, R, r, &lo, &hi);
@@ -311,6 +311,7 @@ int for_each_shard(mktfhe_ctx* c, size_t G, F f) {
     shard_bounds(G, R, 0, &lo, &hi);
     if (hi > lo) rc[0] = f(c, lo, hi);
     for (auto& t : th) t.join();
+    c->in_shard_call = false;
     for (size_t r = 0; r < R; r++)
         if (rc[r]) {
             if (r) c->err = "device " + std::to_string(replica(c, r)->device) + ": " + replica(c, r)->err;
@@ -570,7 +571,6 @@ int mktfhe_mark_keys_received(mktfhe_ctx* c) {
 int mktfhe_bootstrap_batch_dev(mktfhe_ctx* c, int64_t mu, size_t G, const int32_t* a_in, const int32_t* b_in, int32_t* a_out,
                                int32_t* b_out, void* stream) {
     if (!c) return MKTFHE_EINVAL;
-    if (!c->kids.empty()) return fail(c, MKTFHE_EINVAL, "device pointers belong to one GPU: use the per-device context (mktfhe_device_ctx)");
     if (G && (!a_in || !b_in || !a_out || !b_out)) return fail(c, MKTFHE_EINVAL, "bootstrap_batch: NULL buffer");
     CU_TRY(c, cudaSetDevice(c->device));
     return run_bootstrap_dev(c, {0, 1, 0, 0}, mu, G, a_in, b_in, nullptr, nullptr, nullptr, nullptr, a_out, b_out, nullptr, nullptr, true,
@@ -580,7 +580,6 @@ int mktfhe_bootstrap_batch_dev(mktfhe_ctx* c, int64_t mu, size_t G, const int32_
 int mktfhe_gate_batch_dev(mktfhe_ctx* c, int gate, size_t G, const int32_t* xa, const int32_t* xb, const int32_t* ya,
                           const int32_t* yb, const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob, void* stream) {
     if (!c) return MKTFHE_EINVAL;
-    if (!c->kids.empty()) return fail(c, MKTFHE_EINVAL, "device pointers belong to one GPU: use the per-device context (mktfhe_device_ctx)");
     bool ok;
     mk::GateLinear lin = gate_linear(gate, &ok);
     if (!ok) return fail(c, MKTFHE_EINVAL, "unknown gate id %d", gate);
@@ -626,7 +625,6 @@ static int mktfhe_gate_batch_1(mktfhe_ctx* c, int gate, size_t G, const int32_t*
 int mktfhe_gate_batch_mixed_dev(mktfhe_ctx* c, size_t G, const int32_t* gate_ids, const int32_t* xa, const int32_t* xb, const int32_t* ya,
                                 const int32_t* yb, const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob, void* stream) {
     if (!c) return MKTFHE_EINVAL;
-    if (!c->kids.empty()) return fail(c, MKTFHE_EINVAL, "device pointers belong to one GPU: use the per-device context (mktfhe_device_ctx)");
     if (G && (!gate_ids || !xa || !xb || !ya || !yb || !oa || !ob)) return fail(c, MKTFHE_EINVAL, "gate_batch_mixed: NULL buffer");
     CU_TRY(c, cudaSetDevice(c->device));
     // za/zb are read only by MKTFHE_GATE_AND3 gates; point them at x when absent so no gate dereferences NULL
@@ -887,6 +885,7 @@ int mktfhe_create_multi(const mktfhe_params* params, int n_devices, const int* d
         rc = mktfhe_create(params, devs[i], &k);
         if (rc) { mktfhe_destroy(c); return rc; }               // g_create_error holds the message
         k->is_kid = true;
+        k->parent = c;
         c->kids.push_back(k);
     }
     // peer access in both directions between every pair of distinct devices, where the hardware offers it (NVLink / NVSwitch):
@@ -963,9 +962,9 @@ int mktfhe_last_kernel_ms(mktfhe_ctx* c, float* blind_rotate_ms, float* keyswitc
     if (!c) return MKTFHE_EINVAL;
     float br = 0.f, ks = 0.f;
     bool any = false;
-    for (size_t r = 0; r < n_replicas(c); r++) {   // multi-device: the slowest replica (they run concurrently)
+    for (size_t r = 0; r < n_replicas(c); r++) {   // multi-device: the slowest of the replicas that took part in the most recent call
         mktfhe_ctx* d = replica(c, r);
-        if (!d->ev_valid) continue;
+        if (!d->ev_valid || (!c->kids.empty() && d->ev_seq != c->seq)) continue;
         any = true;
         CU_TRY(c, cudaSetDevice(d->device));
         CU_TRY(c, cudaEventSynchronize(d->ev[3]));

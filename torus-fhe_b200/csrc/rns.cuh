@@ -100,56 +100,20 @@ MK_HD u32 mont_mul2(u32 d1, u32 k1, u32 d2, u32 k2, u32 p, u32 pinv_neg) {
 // 31-entry table that `tw(e)` returns (uniform across the warp in the pass over the high index bits,
 // per-lane in the pass over the low index bits -- see ntt_rns.cuh).
 //
-// Butterflies of one forward stage issued in batches of MK_CT_BATCH with their three dependent multiplies grouped (all IMAD.HI, then
-// all q*p, then all y*w - q*p, then the adds): ptxas otherwise keeps the source order and pairs only two butterflies, leaving the
-// warp waiting on the IMAD.HI -> IMAD -> IMAD chain (ncu: `wait` is the top stall of the forward passes, profiles/ncu_r2_b_*).
-#ifndef MK_CT_BATCH
-#define MK_CT_BATCH 0
-#endif
-template <int K, class TW>
-MK_HD void ct_stage(u32 (&x)[32], TW tw, u32 p, u32 p2) {
-    constexpr int g = 16 >> K;
-#if MK_CT_BATCH
-    constexpr int B = MK_CT_BATCH;
-#pragma unroll
-    for (int j0 = 0; j0 < 16; j0 += B) {
-        u32 q[B], wl[B];
-#pragma unroll
-        for (int jj = 0; jj < B; jj++) {
-            const int j = j0 + jj, b = j / g, o = j % g;
-            const uint2_ w = tw((1 << K) - 1 + b);
-            wl[jj] = w.x;
-            q[jj] = mulhi32(x[2 * g * b + o + g], w.y);
-        }
-#pragma unroll
-        for (int jj = 0; jj < B; jj++) q[jj] = q[jj] * p;
-#pragma unroll
-        for (int jj = 0; jj < B; jj++) {
-            const int j = j0 + jj, b = j / g, o = j % g;
-            q[jj] = x[2 * g * b + o + g] * wl[jj] - q[jj];          // [0, 2p)
-        }
-#pragma unroll
-        for (int jj = 0; jj < B; jj++) {
-            const int j = j0 + jj, b = j / g, o = j % g;
-            const u32 X = x[2 * g * b + o];
-            x[2 * g * b + o] = alu_add(X, q[jj]);
-            x[2 * g * b + o + g] = X - q[jj] + p2;
-        }
-    }
-#else
-#pragma unroll
-    for (int b = 0; b < (1 << K); b++) {
-        const uint2_ w = tw((1 << K) - 1 + b);
-#pragma unroll
-        for (int j = 0; j < g; j++) ct_bfly<false>(x[2 * g * b + j], x[2 * g * b + j + g], w.x, w.y, p, p2);
-    }
-#endif
-}
 // ct32: inputs < B with B <= 4p; no reduction inside (the bound grows by 2p per stage); outputs < B + 10p <= 14p < 2^32.
 template <class TW>
 MK_HD void ct32(u32 (&x)[32], TW tw, u32 p) {
     const u32 p2 = keep_in_register(2 * p);
-    ct_stage<0>(x, tw, p, p2); ct_stage<1>(x, tw, p, p2); ct_stage<2>(x, tw, p, p2); ct_stage<3>(x, tw, p, p2); ct_stage<4>(x, tw, p, p2);
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const int g = 16 >> k;
+#pragma unroll
+        for (int b = 0; b < (1 << k); b++) {
+            const uint2_ w = tw((1 << k) - 1 + b);
+#pragma unroll
+            for (int j = 0; j < g; j++) ct_bfly<false>(x[2 * g * b + j], x[2 * g * b + j + g], w.x, w.y, p, p2);
+        }
+    }
 }
 // ct32 whose first stage is already half done: x[16..31] hold w0 * y (the stage-0 twiddle products, in [0, p)) instead of y.
 // Used for the gadget digits, whose 7-bit values make w0 * y a table lookup instead of a multiplication.
@@ -162,7 +126,16 @@ MK_HD void ct32_pre(u32 (&x)[32], TW tw, u32 p) {
         x[j] = alu_add(X, t);
         x[j + 16] = X - t + p2;
     }
-    ct_stage<1>(x, tw, p, p2); ct_stage<2>(x, tw, p, p2); ct_stage<3>(x, tw, p, p2); ct_stage<4>(x, tw, p, p2);
+#pragma unroll
+    for (int k = 1; k < 5; k++) {
+        const int g = 16 >> k;
+#pragma unroll
+        for (int b = 0; b < (1 << k); b++) {
+            const uint2_ w = tw((1 << k) - 1 + b);
+#pragma unroll
+            for (int j = 0; j < g; j++) ct_bfly<false>(x[2 * g * b + j], x[2 * g * b + j + g], w.x, w.y, p, p2);
+        }
+    }
 }
 // [0, 16p) -> [0, 4p): between the two passes of a forward transform
 MK_HD u32 reduce_to_4p(u32 v, u32 p4) {           // p4 = 4p (held in a register by the caller)
