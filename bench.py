@@ -412,6 +412,67 @@ def run_ours(args):
     return 0
 
 
+def run_single_key(args):
+    """SURVEY 8(f) rank 4, first slice: single-key TFHE (gates.jl:16-22 gate_nand on tfhe_parameters_128, api.jl:100-113) through the
+    same engine with one party.  One step = G NAND gates; value with inputs resident in HBM, e2e through the host mirror's gate_nand."""
+    import torch
+    import torus_fhe_b200 as T
+    T1 = T.tfhe1
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    torch.cuda.set_device(0)
+    rng = np.random.default_rng(KEY_SEED)
+    t0 = time.perf_counter()
+    sk, ck = T1.make_key_pair(rng, T1.tfhe_parameters_128())
+    eng = T1.engine_for(ck, device=0)
+    t_keys = time.perf_counter() - t0
+    G, n = args.gates, sk.params.lwe_size
+    bits = rng.integers(0, 2, (2, G)).astype(bool)
+    x, y = T1.encrypt(rng, sk, bits[0]), T1.encrypt(rng, sk, bits[1])
+    dev = [torch.from_numpy(np.ascontiguousarray(v)).cuda() for v in (x.a.reshape(G, 1, n), x.b, y.a.reshape(G, 1, n), y.b)]
+    oa, ob = torch.empty((G, 1, n), dtype=torch.int32, device="cuda"), torch.empty(G, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.Stream()
+    mu0, mu = int(T1.encode_message(1, 8)), int(T1.encode_message(1, 8)) << 32
+
+    def step_dev():
+        eng.ctx.affine_bootstrap_batch_dev(mu0, -1, -1, 0, mu, G, dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), dev[3].data_ptr(), 0, 0,
+                                           oa.data_ptr(), ob.data_ptr(), stream=stream.cuda_stream)
+    for _ in range(args.warmup):
+        step_dev()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0); sampler.start()
+    l0 = eng.ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = eng.ctx.launch_count() - l0
+    br_ms, ks_ms = eng.ctx.last_kernel_ms()
+    out = T1.gate_nand(ck, x, y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = T1.gate_nand(ck, x, y)
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    ok = bool(np.array_equal(T1.decrypt(sk, out), ~(bits[0] & bits[1])) and np.array_equal(out.b, ob.cpu().numpy()))
+    p = sk.params
+    print(json.dumps({"metric": "bootstrapped single-key TFHE NAND gates/sec (tfhe_parameters_128)", "value": G * args.steps / (ms * 1e-3), "unit": UNIT,
+                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "u32 RNS (three 28-bit-prime NTTs + CRT), Torus32 carried as v << 32 / int32 LWE", "data": "synthetic",
+                      "config": {"workload": f"single-key NAND x{G} (api.jl:100-113: n={p.lwe_size} N={p.rlwe_polynomial_degree} l={p.bs_decomp_length} "
+                                             f"Bg=2^{p.bs_log2_base} t={p.ks_decomp_length} Bks=2^{p.ks_log2_base}), the 3gen engine with one party",
+                                 "key_setup_s": round(t_keys, 2)},
+                      "e2e": {"value": G * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(2 * G * (n + 1) * 4), "d2h_bytes_per_step": int(G * (n + 1) * 4)},
+                      "gpu_launches": int(launches), "kernel_ms": {"blind_rotate": br_ms, "keyswitch": ks_ms,
+                                                                   "keyswitch_fused": bool(eng.ctx.describe()["keyswitch_fused"])},
+                      "clocks": clocks, "decryptions_correct": ok}))
+    eng.close()
+    return 0
+
+
 def run_circuit(args):
     """BASELINE configs[3]: WIDTH-bit ripple-carry adder (mk_add_3gen_v2, 3gen_mk_gates.jl:203-220) on I independent instances,
     one mixed-gate launch per dependency level (1 + 2*WIDTH levels, 5*WIDTH gates per instance)."""
@@ -571,8 +632,9 @@ def main():
                                                              "process per GPU under torchrun")
     ap.add_argument("--latency-trials", type=int, default=100, help="single-bootstrap latency: min / median over this many calls")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="nand", choices=["nand", "adder", "less", "conv"],
-                    help="nand = the headline metric; adder / less = BASELINE configs[3] (adder, comparator); conv = BASELINE configs[4]")
+    ap.add_argument("--workload", default="nand", choices=["nand", "adder", "less", "conv", "single"],
+                    help="nand = the headline metric; adder / less = BASELINE configs[3] (adder, comparator); conv = BASELINE configs[4]; "
+                         "single = single-key TFHE NAND (tfhe_parameters_128) through the same engine")
     ap.add_argument("--width", type=int, default=None, help="bits per encrypted integer (adder: 16, conv: 4)")
     ap.add_argument("--image", type=int, default=28, help="conv: input height = width")
     ap.add_argument("--instances", type=int, default=1024)
@@ -584,6 +646,8 @@ def main():
         sys.exit(run_circuit(args))
     if args.workload == "conv":
         sys.exit(run_conv(args))
+    if args.workload == "single":
+        sys.exit(run_single_key(args))
     sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))
 
 

@@ -139,6 +139,16 @@ int mktfhe_gate_batch_dev(mktfhe_ctx *ctx, int gate, size_t G, const int32_t *xa
                           const int32_t *ya, const int32_t *yb, const int32_t *za, const int32_t *zb,
                           int32_t *oa, int32_t *ob, void *stream);
 
+/* General form of the gates above and of the single-key gates (gates.jl:16-142: NAND, OR, AND, XOR, XNOR, NOR, ANDNY, ANDYN,
+ * ORNY, ORYN): temp = mu0 + cx*x + cy*y + cz*z (Int32 wrap-around, lwe.jl:62-76), then bootstrap(temp) with test-vector
+ * message mu (bootstrap.jl:97-100 / 3gen_mk_internals.jl:112-116).  y/z are read only when cy/cz != 0 (may be NULL). */
+int mktfhe_affine_bootstrap_batch(mktfhe_ctx *ctx, int32_t mu0, int32_t cx, int32_t cy, int32_t cz, int64_t mu, size_t G,
+                                  const int32_t *xa, const int32_t *xb, const int32_t *ya, const int32_t *yb,
+                                  const int32_t *za, const int32_t *zb, int32_t *oa, int32_t *ob);
+int mktfhe_affine_bootstrap_batch_dev(mktfhe_ctx *ctx, int32_t mu0, int32_t cx, int32_t cy, int32_t cz, int64_t mu, size_t G,
+                                      const int32_t *xa, const int32_t *xb, const int32_t *ya, const int32_t *yb,
+                                      const int32_t *za, const int32_t *zb, int32_t *oa, int32_t *ob, void *stream);
+
 /* One launch for a batch whose gates differ: gate_ids[g] in MKTFHE_GATE_* selects the prologue of gate g (a dependency
  * level of a circuit such as mk_add_3gen, 3gen_mk_gates.jl:183-220, mixes XOR/AND/OR gates).  za/zb may be NULL when
  * no gate is MKTFHE_GATE_AND3.  The _dev variant takes device pointers (gate_ids included) and does not validate ids:

@@ -1,0 +1,146 @@
+"""Single-key TFHE behind the 3gen engine (first slice): torus-fhe_b200/tfhe1.py.
+
+CPU tests: the numpy Torus32 restatement of the reference's single-key path (oracle/tfhe1_oracle.py) reproduces the reference's own
+test shape -- the decrypted truth table of its twelve gates (3-gen-mk-tfhe/test/runtests.jl:10-42) -- and the embedding the product
+uses (Torus32 values carried as v << 32 through the Torus64 3gen path, standard TGSW rows as the four 3gen parts) is exact: the 3gen
+exact oracle run on the embedded keys returns the single-key oracle's bits.
+GPU tests: the twelve gates through the product's host mirror, bit for bit against the single-key oracle on the same key bytes,
+and the reference's truth-table test on tfhe_parameters_128."""
+import numpy as np
+import pytest
+
+from oracle import tfhe1_oracle as O1
+
+PLAIN = {"NAND": lambda x, y: not (x and y), "OR": lambda x, y: x or y, "AND": lambda x, y: x and y, "XOR": lambda x, y: x != y,
+         "XNOR": lambda x, y: x == y, "NOR": lambda x, y: not (x or y), "ANDNY": lambda x, y: (not x) and y, "ANDYN": lambda x, y: x and not y,
+         "ORNY": lambda x, y: (not x) or y, "ORYN": lambda x, y: x or not y}
+
+
+def test_single_key_oracle_truth_tables_toy_ring():
+    """runtests.jl:10-42 on a toy ring (N = 128, n = 12): every gate, every input combination, decrypts to the plain gate."""
+    rng = np.random.default_rng(123)
+    n, N, l, bg, t, bb = 12, 128, 3, 7, 8, 2
+    s, z, bk, ksk = O1.keygen(rng, n, N, l, bg, t, bb, 2.0 ** -25, 2.0 ** -15)
+    prm = (l, bg, t, bb)
+    enc = lambda b: O1.encrypt(rng, s, b, 2.0 ** -15)
+    for name, plain in PLAIN.items():
+        for xb in (False, True):
+            for yb in (False, True):
+                assert O1.decrypt(s, O1.gate(name, bk, ksk, prm, enc(xb), enc(yb))) == plain(xb, yb), (name, xb, yb)
+    for xb in (False, True):
+        x = enc(xb)
+        assert O1.decrypt(s, O1.gate("NOT", bk, ksk, prm, x)) == (not xb)
+        for yb in (False, True):
+            for zb in (False, True):
+                assert O1.decrypt(s, O1.gate("MUX", bk, ksk, prm, x, enc(yb), enc(zb))) == (yb if xb else zb)
+
+
+def test_oracle_primitives_against_definitions():
+    rng = np.random.default_rng(5)
+    N = 64
+    a, b = rng.integers(-64, 64, N), rng.integers(-2 ** 31, 2 ** 31, N).astype(np.int32)
+    ref = np.zeros(N, object)
+    for i in range(N):
+        for j in range(N):
+            k, sgn = (i + j) % N, -1 if i + j >= N else 1
+            ref[k] += sgn * int(a[i]) * int(b[j])
+    assert np.array_equal(O1.negacyclic_mul(a, b), np.array([((int(v) + 2 ** 31) % 2 ** 32) - 2 ** 31 for v in ref], np.int32))
+    # decomposition recomposes to the input rounded DOWN to a multiple of 2^(32 - l*bgbit) = 2^11 (tgsw.jl:105-110: it floors)
+    p = rng.integers(-2 ** 31, 2 ** 31, N).astype(np.int32)
+    d = O1.decompose(p, 3, 7)
+    assert d.min() >= -64 and d.max() <= 63
+    rec = sum(d[q].astype(np.int64) << (32 - 7 * (q + 1)) for q in range(3))
+    err = (p.astype(np.int64) - rec + 2 ** 31) % 2 ** 32 - 2 ** 31
+    assert np.all((err >= 0) & (err < (1 << 11)))
+    # monomial: X^N = -1, X^(2N) = 1
+    assert np.array_equal(O1.mul_by_monomial(p, N), O1.wrap32(-p.astype(np.int64))) and np.array_equal(O1.mul_by_monomial(p, 2 * N), p)
+    assert np.array_equal(O1.mul_by_monomial(O1.mul_by_monomial(p, 5), -5), p)
+
+
+def _engine_parts(bk):
+    """The product's mapping of a standard TGSW key onto the engine's four parts, through its own class."""
+    import torus_fhe_b200.tfhe1 as T1
+    return T1.BootstrapKey(None, 0.0, None, None, None, samples=bk).engine_parts()
+
+
+def test_embedding_into_the_3gen_path_is_exact(oracle):
+    """Full ring (N = 1024), reduced LWE dimension: the exact 3gen oracle (Torus64, four parts) on the embedded key bytes gives the
+    single-key Torus32 oracle's bootstrap output bit for bit -- the claim tfhe1.py's module docstring makes, without a GPU."""
+    rng = np.random.default_rng(7)
+    n, N, l, bg, t, bb = 6, 1024, 3, 7, 8, 2
+    s, z, bk, ksk = O1.keygen(rng, n, N, l, bg, t, bb, 2.0 ** -25, 2.0 ** -15)
+    prm3 = dict(n=n, N=N, k=1, l=l, bgbit=bg, t=t, basebit=bb, sigma_lwe=2.0 ** -15, sigma_gsw=2.0 ** -25, sigma_ks=2.0 ** -15)
+    ks3 = oracle.KeySet(prm3, raw_bsk=_engine_parts(bk)[None], raw_ksk=ksk[None])
+    mu = O1.encode_message(1, 8)
+    for bit in (False, True):
+        x = O1.encrypt(rng, s, bit, 2.0 ** -15)
+        ra, rb = O1.bootstrap(bk, ksk, mu, x[0], x[1], l, bg, t, bb)
+        ga, gb = ks3.bootstrap_batch(oracle.EXACT_SCHOOLBOOK, mu << 32, x[0].reshape(1, 1, n), np.array([x[1]], np.int32), nthreads=1)
+        assert np.array_equal(ga.reshape(-1), ra) and int(gb[0]) == int(rb)
+        assert O1.decrypt(s, (ra, rb)) == bit
+
+
+@pytest.fixture(scope="module")
+def small_single_key():
+    """Key bytes from the single-key oracle's own generator (N = 1024, n = 16), loaded into the product through its classes."""
+    import torus_fhe_b200.tfhe1 as T1
+    rng = np.random.default_rng(11)
+    n, N, l, bg, t, bb = 16, 1024, 3, 7, 8, 2
+    s, z, bk, ksk = O1.keygen(rng, n, N, l, bg, t, bb, 2.0 ** -25, 2.0 ** -15)
+    params = T1.SchemeParameters(n, 2.0 ** -15, N, 1, True, l, bg, 2.0 ** -25, t, bb, 2.0 ** -15, 1)
+    sk = T1.SecretKey(None, params, key=s)
+    ck = T1.CloudKey.__new__(T1.CloudKey)
+    ck.params, ck._engine = params, None
+    ck.rlwe_key = T1.RLweKey(None, T1.rlwe_parameters(params), key=z)
+    ck.bootstrap_key = T1.BootstrapKey(None, 0.0, None, None, T1.tgsw_parameters(params), samples=bk)
+    ck.keyswitch_key = T1.KeyswitchKey.from_array(ksk, T1.keyswitch_parameters(params))
+    yield T1, rng, sk, ck, (s, bk, ksk, (l, bg, t, bb))
+    if ck._engine is not None:
+        ck._engine.close()
+
+
+@pytest.mark.gpu
+def test_single_key_gates_bit_exact_against_the_oracle(small_single_key):
+    T1, rng, sk, ck, (s, bk, ksk, prm) = small_single_key
+    bits = np.array([[a, b, c] for a in (0, 1) for b in (0, 1) for c in (0, 1)], bool)
+    x, y, z = (T1.encrypt(rng, sk, bits[:, i]) for i in range(3))
+    for name, (fn, nargs, plain) in T1.GATES.items():
+        args = (x, y, z)[:nargs]
+        out = fn(ck, *args)
+        assert out.a.shape == x.a.shape and out.b.shape == x.b.shape
+        for g in range(len(bits)):
+            ra, rb = O1.gate(name, bk, ksk, prm, *[(v.a[g], v.b[g]) for v in args])
+            assert np.array_equal(out.a[g], ra) and int(out.b[g]) == int(rb), (name, g)
+        assert np.array_equal(T1.decrypt(sk, out), plain(*[bits[:, i] for i in range(nargs)])), name
+    # bootstrap = keyswitch o bootstrap_wo_keyswitch (bootstrap.jl:97-100); scalar call = batch of one
+    mu = T1.encode_message(1, 8)
+    b1 = T1.bootstrap(ck, None, mu, x)
+    b2 = T1.keyswitch(ck, T1.bootstrap_wo_keyswitch(ck, mu, x))
+    assert np.array_equal(b1.a, b2.a) and np.array_equal(b1.b, b2.b) and np.array_equal(T1.decrypt(sk, b1), bits[:, 0])
+    one = T1.gate_nand(ck, x[3], y[3])
+    assert one.b.shape == () and T1.decrypt(sk, one) == (not (bits[3, 0] and bits[3, 1]))
+    assert T1.decrypt(sk, T1.gate_constant(ck, True)) is True
+
+
+@pytest.mark.gpu
+def test_reference_truth_table_test_on_tfhe_parameters_128():
+    """test/runtests.jl:28-59 ("gate" and "single party, custom parameters"): make_key_pair, then every gate on every input
+    combination, on tfhe_parameters_128 (keys generated by the product: exact key products on the GPU)."""
+    import torus_fhe_b200.tfhe1 as T1
+    rng = np.random.default_rng(123)
+    sk, ck = T1.make_key_pair(rng, T1.tfhe_parameters_128())
+    try:
+        bits = np.array([[a, b, c] for a in (0, 1) for b in (0, 1) for c in (0, 1)], bool)
+        x, y, z = (T1.encrypt(rng, sk, bits[:, i]) for i in range(3))
+        for name, (fn, nargs, plain) in T1.GATES.items():
+            out = fn(ck, *(x, y, z)[:nargs])
+            assert np.array_equal(T1.decrypt(sk, out), plain(*[bits[:, i] for i in range(nargs)])), name
+        # the 80-bit set needs 10-bit gadget digits: refused by the library, never silently mis-served
+        sk80 = T1.SecretKey(rng, T1.tfhe_parameters_80())
+        ck80 = T1.CloudKey.__new__(T1.CloudKey)
+        ck80.params, ck80._engine = sk80.params, None
+        import torus_fhe_b200 as T
+        with pytest.raises(T.MktfheError):
+            T1.engine_for(ck80)
+    finally:
+        ck._engine.close()

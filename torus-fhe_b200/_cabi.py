@@ -21,7 +21,7 @@ EXPORTS = (
     "mktfhe_device_count", "mktfhe_device_ctx", "mktfhe_shard_bounds", "mktfhe_pin_host", "mktfhe_unpin_host",
     "mktfhe_load_bsk", "mktfhe_load_ksk", "mktfhe_finalize_keys", "mktfhe_key_buffers", "mktfhe_mark_keys_received",
     "mktfhe_bootstrap_batch", "mktfhe_gate_batch", "mktfhe_bootstrap_batch_dev", "mktfhe_gate_batch_dev",
-    "mktfhe_gate_batch_mixed", "mktfhe_gate_batch_mixed_dev",
+    "mktfhe_gate_batch_mixed", "mktfhe_gate_batch_mixed_dev", "mktfhe_affine_bootstrap_batch", "mktfhe_affine_bootstrap_batch_dev",
     "mktfhe_extprod_batch", "mktfhe_blind_rotate_batch", "mktfhe_keyswitch_batch", "mktfhe_negacyclic_mul_batch",
     "mktfhe_launch_count", "mktfhe_last_kernel_ms", "mktfhe_algorithmic_bytes", "mktfhe_build_id", "mktfhe_describe",
 )
@@ -83,6 +83,8 @@ def lib():
         "mktfhe_gate_batch": (C.c_int, [vp, C.c_int, sz, vp, vp, vp, vp, vp, vp, vp, vp]),
         "mktfhe_bootstrap_batch_dev": (C.c_int, [vp, i64, sz, vp, vp, vp, vp, vp]),
         "mktfhe_gate_batch_dev": (C.c_int, [vp, C.c_int, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "mktfhe_affine_bootstrap_batch": (C.c_int, [vp, i32, i32, i32, i32, i64, sz, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "mktfhe_affine_bootstrap_batch_dev": (C.c_int, [vp, i32, i32, i32, i32, i64, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "mktfhe_gate_batch_mixed": (C.c_int, [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "mktfhe_gate_batch_mixed_dev": (C.c_int, [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "mktfhe_extprod_batch": (C.c_int, [vp, sz, vp, vp, vp]),
@@ -237,6 +239,23 @@ class Context:
         self._chk(lib().mktfhe_gate_batch(self.h, gate, G, _p(xa), _p(xb), _p(ya), _p(yb), _p(za), _p(zb), _p(oa), _p(ob)))
         return oa, ob
 
+    def affine_bootstrap_batch(self, mu0, cx, cy, cz, mu, x, y=None, z=None):
+        """bootstrap(mu0 + cx x + cy y + cz z) with test-vector message mu: the general form of every bootstrapped gate."""
+        xa, xb = self._ab(*x)
+        G = xb.size
+        ya = yb = za = zb = None
+        if y is not None:
+            ya, yb = self._ab(*y)
+        if z is not None:
+            za, zb = self._ab(*z)
+        if (cy and y is None) or (cz and z is None):
+            raise ValueError("a non-zero coefficient needs its operand")
+        oa, ob = np.empty((G, self.k, self.n), np.int32), np.empty(G, np.int32)
+        w = lambda v: int(np.int32(np.uint32(int(v) & 0xFFFFFFFF)))
+        self._chk(lib().mktfhe_affine_bootstrap_batch(self.h, w(mu0), w(cx), w(cy), w(cz), int(mu), G, _p(xa), _p(xb), _p(ya), _p(yb), _p(za), _p(zb),
+                                                      _p(oa), _p(ob)))
+        return oa, ob
+
     def gate_batch_mixed(self, gate_ids, x, y, z=None):
         """One launch for gates of different kinds: gate_ids[g] selects the prologue of gate g."""
         gate_ids = _c(gate_ids, np.int32).reshape(-1)
@@ -258,6 +277,11 @@ class Context:
 
     def gate_batch_dev(self, gate, G, xa, xb, ya, yb, za, zb, oa, ob, stream=0):
         self._chk(lib().mktfhe_gate_batch_dev(self.h, gate, G, xa, xb, ya, yb, za or None, zb or None, oa, ob, stream or None))
+
+    def affine_bootstrap_batch_dev(self, mu0, cx, cy, cz, mu, G, xa, xb, ya, yb, za, zb, oa, ob, stream=0):
+        w = lambda v: int(np.int32(np.uint32(int(v) & 0xFFFFFFFF)))
+        self._chk(lib().mktfhe_affine_bootstrap_batch_dev(self.h, w(mu0), w(cx), w(cy), w(cz), int(mu), G, xa, xb, ya or None, yb or None,
+                                                          za or None, zb or None, oa, ob, stream or None))
 
     def gate_batch_mixed_dev(self, G, gate_ids, xa, xb, ya, yb, za, zb, oa, ob, stream=0):
         self._chk(lib().mktfhe_gate_batch_mixed_dev(self.h, G, gate_ids, xa, xb, ya, yb, za or None, zb or None, oa, ob, stream or None))

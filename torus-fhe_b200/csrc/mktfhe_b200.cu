@@ -596,30 +596,37 @@ static int stage_in(mktfhe_ctx* c, DevBuf& b, const void* host, size_t bytes) {
     return MKTFHE_OK;
 }
 
-static int mktfhe_gate_batch_1(mktfhe_ctx* c, int gate, size_t G, const int32_t* xa, const int32_t* xb, const int32_t* ya, const int32_t* yb,
-                      const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob) {
-    if (!c) return MKTFHE_EINVAL;
-    bool ok;
-    mk::GateLinear lin = gate_linear(gate, &ok);
-    if (!ok) return fail(c, MKTFHE_EINVAL, "unknown gate id %d", gate);
+// host-pointer core of every "linear prologue + bootstrap" call: temp = mu0 + cx x + cy y + cz z, then mk_bootstrap_3gen(temp) with
+// test-vector message mu.  y / z are staged only when their coefficient is non-zero.
+static int affine_batch_1(mktfhe_ctx* c, mk::GateLinear lin, int64_t mu, size_t G, const int32_t* xa, const int32_t* xb, const int32_t* ya,
+                          const int32_t* yb, const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob, const char* what) {
     if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
     if (G == 0) return MKTFHE_OK;
-    if (!xa || !xb || !ya || !yb || !oa || !ob || (lin.cz && (!za || !zb))) return fail(c, MKTFHE_EINVAL, "gate_batch: NULL buffer");
+    if (!xa || !xb || !oa || !ob || (lin.cy && (!ya || !yb)) || (lin.cz && (!za || !zb))) return fail(c, MKTFHE_EINVAL, "%s: NULL buffer", what);
     CU_TRY(c, cudaSetDevice(c->device));
     const size_t kn = (size_t)c->prm.n * c->prm.k, abytes = G * kn * 4, bbytes = G * 4;
     int rc;
-    if ((rc = stage_in(c, c->in[0], xa, abytes)) || (rc = stage_in(c, c->in[1], xb, bbytes)) ||
-        (rc = stage_in(c, c->in[2], ya, abytes)) || (rc = stage_in(c, c->in[3], yb, bbytes)))
-        return rc;
+    if ((rc = stage_in(c, c->in[0], xa, abytes)) || (rc = stage_in(c, c->in[1], xb, bbytes))) return rc;
+    if (lin.cy && ((rc = stage_in(c, c->in[2], ya, abytes)) || (rc = stage_in(c, c->in[3], yb, bbytes)))) return rc;
     if (lin.cz && ((rc = stage_in(c, c->in[4], za, abytes)) || (rc = stage_in(c, c->in[5], zb, bbytes)))) return rc;
     if ((rc = reserve(c, c->oa, abytes)) || (rc = reserve(c, c->ob, bbytes))) return rc;
-    rc = run_bootstrap_dev(c, lin, (int64_t)1 << 61, G, (int32_t*)c->in[0].p, (int32_t*)c->in[1].p, (int32_t*)c->in[2].p, (int32_t*)c->in[3].p,
+    rc = run_bootstrap_dev(c, lin, mu, G, (int32_t*)c->in[0].p, (int32_t*)c->in[1].p, (int32_t*)c->in[2].p, (int32_t*)c->in[3].p,
                            (int32_t*)c->in[4].p, (int32_t*)c->in[5].p, (int32_t*)c->oa.p, (int32_t*)c->ob.p, nullptr, nullptr, true, nullptr);
     if (rc) return rc;
     CU_TRY(c, cudaMemcpyAsync(oa, c->oa.p, abytes, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaMemcpyAsync(ob, c->ob.p, bbytes, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     return MKTFHE_OK;
+}
+
+static int mktfhe_gate_batch_1(mktfhe_ctx* c, int gate, size_t G, const int32_t* xa, const int32_t* xb, const int32_t* ya, const int32_t* yb,
+                      const int32_t* za, const int32_t* zb, int32_t* oa, int32_t* ob) {
+    if (!c) return MKTFHE_EINVAL;
+    bool ok;
+    mk::GateLinear lin = gate_linear(gate, &ok);
+    if (!ok) return fail(c, MKTFHE_EINVAL, "unknown gate id %d", gate);
+    // output message encode_message64(1, 8) = 2^61 (rlwe_is32 == false, 3gen_mk_gates.jl:12)
+    return affine_batch_1(c, lin, (int64_t)1 << 61, G, xa, xb, ya, yb, za, zb, oa, ob, "gate_batch");
 }
 
 int mktfhe_gate_batch_mixed_dev(mktfhe_ctx* c, size_t G, const int32_t* gate_ids, const int32_t* xa, const int32_t* xb, const int32_t* ya,
@@ -796,6 +803,30 @@ int mktfhe_gate_batch(mktfhe_ctx* c, int gate, size_t G, const int32_t* xa, cons
         return mktfhe_gate_batch_1(r, gate, hi - lo, xa + lo * kn, xb + lo, ya + lo * kn, yb + lo, za ? za + lo * kn : nullptr, zb ? zb + lo : nullptr,
                                    oa + lo * kn, ob + lo);
     });
+}
+
+int mktfhe_affine_bootstrap_batch(mktfhe_ctx* c, int32_t mu0, int32_t cx, int32_t cy, int32_t cz, int64_t mu, size_t G, const int32_t* xa,
+                                  const int32_t* xb, const int32_t* ya, const int32_t* yb, const int32_t* za, const int32_t* zb, int32_t* oa,
+                                  int32_t* ob) {
+    if (!c) return MKTFHE_EINVAL;
+    const mk::GateLinear lin{mu0, cx, cy, cz};
+    if (c->kids.empty()) return affine_batch_1(c, lin, mu, G, xa, xb, ya, yb, za, zb, oa, ob, "affine_bootstrap_batch");
+    MK_NOT_READY(c);
+    if (G && (!xa || !xb || !oa || !ob)) return fail(c, MKTFHE_EINVAL, "affine_bootstrap_batch: NULL buffer");
+    const size_t kn = (size_t)c->prm.n * c->prm.k;
+    return for_each_shard(c, G, [=](mktfhe_ctx* r, size_t lo, size_t hi) {
+        return affine_batch_1(r, lin, mu, hi - lo, xa + lo * kn, xb + lo, ya ? ya + lo * kn : nullptr, yb ? yb + lo : nullptr,
+                              za ? za + lo * kn : nullptr, zb ? zb + lo : nullptr, oa + lo * kn, ob + lo, "affine_bootstrap_batch");
+    });
+}
+
+int mktfhe_affine_bootstrap_batch_dev(mktfhe_ctx* c, int32_t mu0, int32_t cx, int32_t cy, int32_t cz, int64_t mu, size_t G, const int32_t* xa,
+                                      const int32_t* xb, const int32_t* ya, const int32_t* yb, const int32_t* za, const int32_t* zb,
+                                      int32_t* oa, int32_t* ob, void* stream) {
+    if (!c) return MKTFHE_EINVAL;
+    if (G && (!xa || !xb || !oa || !ob || (cy && (!ya || !yb)) || (cz && (!za || !zb)))) return fail(c, MKTFHE_EINVAL, "affine_bootstrap_batch: NULL buffer");
+    CU_TRY(c, cudaSetDevice(c->device));
+    return run_bootstrap_dev(c, {mu0, cx, cy, cz}, mu, G, xa, xb, ya, yb, za, zb, oa, ob, nullptr, nullptr, true, (cudaStream_t)stream);
 }
 
 int mktfhe_gate_batch_mixed(mktfhe_ctx* c, size_t G, const int32_t* gate_ids, const int32_t* xa, const int32_t* xb, const int32_t* ya,
