@@ -147,16 +147,16 @@ def generate_keys(T, params, rng):
     return secret_keys, bk, ks
 
 
-def profile_evidence(T, parties, lib_path):
+def profile_evidence(T, parties, lib_path, N=1024, l=2):
     """Measured constants the roofline quotes, read from files under profiles/ (never literals): the IMAD-pipe peak and the HBM
     key-stream rate from the micro-benchmarks, and -- only when the capture manifest belongs to THIS library's machine code and
     parameter set -- the DRAM traffic and pipe-busy figures of the dominant kernel's `ncu --set full` capture."""
     import hashlib
     import re
     sys.path.insert(0, os.path.join(ROOT, "tools"))
-    from kernel_id import kernel_id
+    from kernel_id import hot_kernels, kernel_id
     prof = os.path.join(ROOT, "profiles")
-    ev = {"kernel_id": kernel_id(lib_path), "imad_peak": None, "key_stream": None, "capture": None, "capture_note": None}
+    ev = {"kernel_id": kernel_id(lib_path, hot_kernels(N, l)), "imad_peak": None, "key_stream": None, "capture": None, "capture_note": None}
 
     def sha(path):
         return hashlib.sha256(open(path, "rb").read()).hexdigest()[:16]
@@ -336,7 +336,7 @@ def run_ours(args):
         hbm_peak, peak_src = measured_peaks()
         N, l = params.rlwe_polynomial_degree, params.gsw_decomp_length
         big = N != 1024            # N = 2048 sets: no slot model / ncu capture manifest
-        evd = profile_evidence(T, k, T._cabi.LIB_PATH)
+        evd = profile_evidence(T, k, T._cabi.LIB_PATH, N, l)
         bsk_1limb = k * n * 4 * l * N * 8                         # 68.2 MB per 2-party bootstrap (the reference's transformed key size)
         bsk_stream, ksk_gather = ctx.algorithmic_bytes()          # what this build streams (u32 residues per coefficient) / gathers per gate
         ct_io = 2 * (k * n + 1) * 4 + (N + 1) * 4
@@ -470,6 +470,48 @@ def run_single_key(args):
                                                                    "keyswitch_fused": bool(eng.ctx.describe()["keyswitch_fused"])},
                       "clocks": clocks, "decryptions_correct": ok}))
     eng.close()
+    return 0
+
+
+def run_perf_comp(args):
+    """The reference's only published measurement protocol (measurements/test_suites/performance_comparison_test/perf_comp.jl:13-20, 107-142;
+    its plot is docs/speedup.png): k = 2, 4, 8, 16 parties on the 16-PARTY parameter set, 100 single calls of
+    mk_bootstrap_3gen(bk, ks, encode(1, 8), enc(true)), minimum and median of the per-call time.  Here: wall clock of the same call through
+    the host mirror (host buffers, H2D + kernel + D2H: what @elapsed sees) and the device time of its kernels beside it."""
+    import dataclasses
+    import torch
+    import torus_fhe_b200 as T
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    torch.cuda.set_device(0)
+    ref_s = {2: 0.23, 4: 0.53, 8: 1.06, 16: 2.1}      # read off docs/speedup.png (BASELINE.md): Julia, one CPU thread, hardware not stated
+    rows = []
+    for k in (2, 4, 8, 16):
+        params = dataclasses.replace(T.mktfhe_parameters_16party_3gen, max_parties=k)
+        rng = np.random.default_rng(KEY_SEED + k)
+        t0 = time.perf_counter()
+        secret_keys, bk, ks = generate_keys(T, params, rng)
+        eng = T.engine_for(bk, ks, device=0)
+        t_keys = time.perf_counter() - t0
+        mu = T.encode_message64(1, 8)
+        wall, devt, ok = [], [], True
+        for trial in range(args.latency_trials + 3):
+            x = T.mk_encrypt_3gen(rng, secret_keys, True)
+            t0 = time.perf_counter()
+            y = T.mk_bootstrap_3gen(bk, ks, mu, x)
+            dt = time.perf_counter() - t0
+            ok &= bool(T.mk_decrypt_3gen(secret_keys, y))
+            if trial >= 3:
+                wall.append(dt * 1e3); devt.append(sum(eng.ctx.last_kernel_ms()))
+        rows.append({"parties": k, "blind_rotate_steps": k * params.lwe_size, "wall_ms_min": float(np.min(wall)), "wall_ms_median": float(np.median(wall)),
+                     "device_ms_min": float(np.min(devt)), "device_ms_median": float(np.median(devt)), "trials": len(wall),
+                     "reference_julia_s": ref_s[k], "speedup_vs_reference_median": ref_s[k] * 1e3 / float(np.median(wall)),
+                     "key_setup_s": round(t_keys, 2), "decryptions_correct": ok})
+        T.release_engine(bk, ks)
+    print(json.dumps({"metric": "single mk_bootstrap_3gen latency on the 16-party parameter set, k = 2/4/8/16 parties (perf_comp.jl protocol)", "unit": "ms",
+                      "higher_is_better": False, "n_gpus": 1, "rows": rows,
+                      "config": {"workload": "mktfhe_parameters_16party_3gen (n=590 N=2048 l=1 Bg=2^26 t=4 Bks=2^3) with k parties, one bootstrap per call",
+                                 "reference_numbers": "docs/speedup.png: 0.23 / 0.53 / 1.06 / 2.1 s (Julia, one CPU thread; hardware not stated)"}}))
     return 0
 
 
@@ -632,7 +674,7 @@ def main():
                                                              "process per GPU under torchrun")
     ap.add_argument("--latency-trials", type=int, default=100, help="single-bootstrap latency: min / median over this many calls")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="nand", choices=["nand", "adder", "less", "conv", "single"],
+    ap.add_argument("--workload", default="nand", choices=["nand", "adder", "less", "conv", "single", "perf_comp"],
                     help="nand = the headline metric; adder / less = BASELINE configs[3] (adder, comparator); conv = BASELINE configs[4]; "
                          "single = single-key TFHE NAND (tfhe_parameters_128) through the same engine")
     ap.add_argument("--width", type=int, default=None, help="bits per encrypted integer (adder: 16, conv: 4)")
@@ -648,6 +690,8 @@ def main():
         sys.exit(run_conv(args))
     if args.workload == "single":
         sys.exit(run_single_key(args))
+    if args.workload == "perf_comp":
+        sys.exit(run_perf_comp(args))
     sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))
 
 

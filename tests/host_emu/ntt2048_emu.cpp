@@ -93,6 +93,11 @@ int main() {
             r[i] = (u32)(m < 0 ? m + T.c.p[i] : m) + (u32)(rnd() % 4) * T.c.p[i];
         }
         if (crt4_lift(r, T.c) != (u64)R) { fails++; printf("FAIL crt4\n"); }
+        {   // the quotient-corrected lift on y_i = R (M / p_i)^-1 mod p_i, in a lazy representative (+ 0..3 p_i)
+            u32 y[NP];
+            for (int i = 0; i < NP; i++) y[i] = rns::mulmod(r[i] % PRIMES[i], T.c.yscale[i], PRIMES[i]) + (u32)((it + i) & 3) * PRIMES[i];
+            if (crt4_lift_kappa(y, T.c) != (u64)R) { fails++; printf("FAIL crt4 kappa\n"); }
+        }
     }
     // exact negacyclic product: 2l = 2 polynomials of 26-bit signed digits against 64-bit keys (l = 1, Bg = 2^26), through the four primes
     for (int trial = 0; trial < 4 && !fails; trial++) {

@@ -376,5 +376,9 @@ def test_n2048_full_lwe_dimension_bit_exact(oracle):
         ra, rb = ks.gate_batch(oracle.EXACT_NTT, oracle.GATE_NAND, x, y)
         assert np.array_equal(oa, ra) and np.array_equal(ob, rb)
         assert np.array_equal(ks.decrypt(oa, ob), ~(bits[:, 0].astype(bool) & bits[:, 1].astype(bool)))
+        # and ONE gate of the same batch against the O(N^2) schoolbook definition itself at the full LWE dimension (1180 steps x 8
+        # products of degree 2048: about half a minute of CPU; the other back-end above covers the rest of the batch)
+        sa, sb = ks.gate_batch(oracle.EXACT_SCHOOLBOOK, oracle.GATE_NAND, (x[0][3:4], x[1][3:4]), (y[0][3:4], y[1][3:4]), nthreads=1)
+        assert np.array_equal(oa[3:4], sa) and np.array_equal(ob[3:4], sb)
     finally:
         eng.close()

@@ -12,7 +12,13 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def kernel_id(lib=None, match="blind_rotate"):
+def hot_kernels(N, l):
+    """Substrings (of mangled names) selecting the kernels that serve a parameter set: the N = 1024 throughput and latency kernels
+    of gadget length l, or the N = 2048 kernels."""
+    return ["N4mk2k"] if N == 2048 else [f"N2mk19blind_rotate_kernelILi{l}E", f"N2mk23blind_rotate_lat_kernelILi{l}E"]
+
+
+def kernel_id(lib=None, match=("blind_rotate",)):
     lib = lib or os.path.join(ROOT, "torus-fhe_b200", "libmktfhe_b200.so")
     try:
         out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, timeout=300).stdout
@@ -22,7 +28,7 @@ def kernel_id(lib=None, match="blind_rotate"):
     for line in out.splitlines():
         m = re.match(r"\s*Function : (\S+)", line)
         if m:
-            keep = match in m.group(1)
+            keep = any(x in m.group(1) for x in ([match] if isinstance(match, str) else match))
             if keep:
                 h.update(m.group(1).encode()); n += 1
             continue
@@ -34,4 +40,5 @@ def kernel_id(lib=None, match="blind_rotate"):
 
 
 if __name__ == "__main__":
-    print(kernel_id(sys.argv[1] if len(sys.argv) > 1 else None))
+    lib = sys.argv[1] if len(sys.argv) > 1 else None
+    print("all blind_rotate kernels:", kernel_id(lib), " N=1024 l=2:", kernel_id(lib, hot_kernels(1024, 2)), " N=2048:", kernel_id(lib, hot_kernels(2048, 1)))

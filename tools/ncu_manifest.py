@@ -11,13 +11,15 @@ import re
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from kernel_id import kernel_id  # noqa: E402
+from kernel_id import hot_kernels, kernel_id  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("summary")
 ap.add_argument("--parties", type=int, required=True)
 ap.add_argument("--gates", type=int, required=True, help="gates in the captured launch")
 ap.add_argument("--lib", default=None)
+ap.add_argument("--N", type=int, default=1024)
+ap.add_argument("--l", type=int, default=2)
 ap.add_argument("-o", "--out", required=True)
 a = ap.parse_args()
 text = open(a.summary).read()
@@ -33,7 +35,8 @@ def metric(name):
 
 man = {
     "kernel": re.search(r"^== (.*?)  grid", text, flags=re.M).group(1),
-    "kernel_id": kernel_id(a.lib),
+    "kernel_id": kernel_id(a.lib, hot_kernels(a.N, a.l)),
+    "kernel_id_covers": hot_kernels(a.N, a.l),
     "parties": a.parties,
     "gates_in_launch": a.gates,
     "gpu_time_ms": metric("gpu__time_duration.sum"),

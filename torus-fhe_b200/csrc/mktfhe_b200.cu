@@ -49,6 +49,7 @@ struct mktfhe_ctx {
     int num_sms = 0;
     bool split_tail = true;      // MKTFHE_B200_SPLIT_TAIL=0: no separate one-gate-per-CTA launch for the tail of a large batch (A/B)
     bool latency_kernel = true;  // MKTFHE_B200_LATENCY=0 turns the 12-warp small-batch launch off (A/B)
+    bool two_k16 = true;         // N = 2048: the sixteen-warp kernel (MKTFHE_B200_2K=8 selects the first, eight-warp kernel: A/B runs)
     bool fuse_ks = true;         // key switch as the epilogue of the blind-rotate kernel (MKTFHE_B200_FUSE_KS=0 disables: A/B runs)
     std::vector<char> bsk_loaded, ksk_loaded;
     bool ready = false;
@@ -143,6 +144,8 @@ int set_attrs(mktfhe_ctx* c) {
     if (c->prm.N == mk2k::N) {
         if (c->prm.l == 1) CU_TRY(c, cudaFuncSetAttribute(mk2k::blind_rotate2k_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk2k::smem_bytes(1)));
         else CU_TRY(c, cudaFuncSetAttribute(mk2k::blind_rotate2k_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk2k::smem_bytes(2)));
+        if (c->prm.l == 1) CU_TRY(c, cudaFuncSetAttribute(mk2k::blind_rotate2k16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk2k::smem_bytes16(1)));
+        else CU_TRY(c, cudaFuncSetAttribute(mk2k::blind_rotate2k16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk2k::smem_bytes16(2)));
         return MKTFHE_OK;
     }
     const int sm = (int)br_smem_bytes(c);
@@ -247,8 +250,13 @@ int run_bootstrap_dev(mktfhe_ctx* c, mk::GateLinear lin, int64_t mu, size_t G, c
         a.xa = xa; a.xb = xb; a.ya = ya; a.yb = yb; a.za = za; a.zb = zb;
         a.lin = lin; a.gate_ids = gate_ids; a.mu = mu; a.ext_out = ext; a.acc_out = acc_out;
         if (fuse) { a.ksk = c->d_ksk; a.ks_t = c->prm.t; a.ks_basebit = c->prm.basebit; a.oa = oa; a.ob = ob; }
-        if (c->prm.l == 1) mk2k::blind_rotate2k_kernel<1><<<(unsigned)G, mk2k::THREADS, mk2k::smem_bytes(1), st>>>(a);
-        else mk2k::blind_rotate2k_kernel<2><<<(unsigned)G, mk2k::THREADS, mk2k::smem_bytes(2), st>>>(a);
+        if (c->two_k16) {
+            if (c->prm.l == 1) mk2k::blind_rotate2k16_kernel<1><<<(unsigned)G, mk2k::THREADS16, mk2k::smem_bytes16(1), st>>>(a);
+            else mk2k::blind_rotate2k16_kernel<2><<<(unsigned)G, mk2k::THREADS16, mk2k::smem_bytes16(2), st>>>(a);
+        } else {
+            if (c->prm.l == 1) mk2k::blind_rotate2k_kernel<1><<<(unsigned)G, mk2k::THREADS, mk2k::smem_bytes(1), st>>>(a);
+            else mk2k::blind_rotate2k_kernel<2><<<(unsigned)G, mk2k::THREADS, mk2k::smem_bytes(2), st>>>(a);
+        }
         c->launches++;
     } else {
         mk::BlindRotateArgs a{};
@@ -457,6 +465,7 @@ int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
     if (const char* e = getenv("MKTFHE_B200_LATENCY")) c->latency_kernel = atoi(e) != 0;
     if (const char* e = getenv("MKTFHE_B200_SPLIT_TAIL")) c->split_tail = atoi(e) != 0;
     if (const char* e = getenv("MKTFHE_B200_FUSE_KS")) c->fuse_ks = atoi(e) != 0;
+    if (const char* e = getenv("MKTFHE_B200_2K")) c->two_k16 = atoi(e) != 8;
     const size_t ks_stride = mk::ks_row_stride(params->n);   // rows padded to 16 bytes on the device
     c->ksk_bytes = (size_t)params->k * params->N * params->t * B1 * ks_stride * sizeof(int32_t);
     CREATE_TRY(cudaMalloc(&c->d_bsk, c->bsk_bytes));

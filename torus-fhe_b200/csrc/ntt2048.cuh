@@ -77,6 +77,11 @@ struct Consts {
     u32 ginv[NP][NP], ginv_s[NP][NP];
     u64 pp[NP];              // pp[i] = p_0 * ... * p_{i-1} mod 2^64 (pp[0] = 1)
     u64 m_mod64;             // p_0 p_1 p_2 p_3 mod 2^64
+    // quotient-corrected lift (crt4_lift_kappa): the stored key carries the extra factor yscale[i] = (M / p_i)^-1 mod p_i
+    u32 yscale[NP];
+    u32 key_scale_k[NP];     // key_scale[i] * yscale[i] mod p_i
+    u64 cm[NP];              // (M / p_i) mod 2^64
+    u32 kf[NP];              // floor(2^59 / p_i): y * kf / 2^59 = y / p_i to 2^-29
 };
 
 constexpr int TILE_STRIDE = 33;
@@ -130,6 +135,40 @@ MK_HD u64 crt4_lift(const u32 (&r)[NP], const Consts& c) {
     for (int j = 1; j < NP; j++) R += c.pp[j] * v[j];
     if (v[NP - 1] > c.p[NP - 1] / 2) R -= c.m_mod64;                               // negative representative
     return R;
+}
+
+// The lift the N = 2048 kernels use (round 2).  Inputs are y_i = R * (M / p_i)^-1 mod p_i in ANY lazy representative below 2^30
+// (the factor rides in the stored key, Consts::key_scale_k).  R = sum_i y_i (M / p_i) - kappa M with kappa = round(sum_i y_i / p_i):
+// since |R| < M / 4 the sum is within 1/4 of an integer, and a 59-bit fixed-point estimate (error < 2^-27) rounds to it; a lazy
+// representative y_i + a p_i adds the integer a to the sum and a M to the first term, which cancel.  Everything is taken mod 2^64.
+// 4 IMAD.WIDE for kappa + 5 products of a 64-bit constant by a 32-bit value: ~23 fma-pipe slots against ~36 for Garner's four-prime
+// chain (six dependent Shoup products); the CRT phase was 14 % of the kernel's fma-pipe slots (profiles/ncu_r2_f_*).
+#ifndef MK2K_CRT_KAPPA
+#define MK2K_CRT_KAPPA 1
+#endif
+MK_HD u64 crt4_lift_kappa(const u32 (&y)[NP], const Consts& c) {
+    u64 frac = (u64)1 << 58;                                                       // rounding
+    u64 R = 0;
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        frac += (u64)y[i] * c.kf[i];                                               // < 4 * 2^30 * 2^32 + 2^58 < 2^64
+        R += c.cm[i] * (u64)y[i];
+    }
+    return R - (frac >> 59) * c.m_mod64;
+}
+MK_HD u64 lift4(const u32 (&r)[NP], const Consts& c) {
+#if MK2K_CRT_KAPPA
+    return crt4_lift_kappa(r, c);
+#else
+    return crt4_lift(r, c);
+#endif
+}
+MK_HD u32 stored_key_scale(const Consts& c, int i) {
+#if MK2K_CRT_KAPPA
+    return c.key_scale_k[i];
+#else
+    return c.key_scale[i];
+#endif
 }
 
 }  // namespace rns2k

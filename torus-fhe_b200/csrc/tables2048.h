@@ -53,6 +53,17 @@ struct HostTables {
         c.pp[0] = 1;
         for (int j = 1; j < NP; j++) c.pp[j] = c.pp[j - 1] * (u64)PRIMES[j - 1];   // wraps mod 2^64 from j = 3
         c.m_mod64 = c.pp[NP - 1] * (u64)PRIMES[NP - 1];
+        for (int i = 0; i < NP; i++) {
+            const u32 p = PRIMES[i];
+            u64 cm = 1;                    // M / p_i mod 2^64
+            u32 cmp = 1;                   // M / p_i mod p_i
+            for (int j = 0; j < NP; j++)
+                if (j != i) { cm *= (u64)PRIMES[j]; cmp = rns::mulmod(cmp, PRIMES[j] % p, p); }
+            c.cm[i] = cm;
+            c.yscale[i] = rns::invmod(cmp, p);
+            c.key_scale_k[i] = rns::mulmod(c.key_scale[i], c.yscale[i], p);
+            c.kf[i] = (u32)((((u64)1) << 59) / p);
+        }
     }
 };
 
