@@ -132,7 +132,7 @@ def run_reference(args):
     return 0
 
 
-def generate_keys(T, params, rng):
+def generate_keys(T, params, rng, ksk_on_device=True):
     """multikey_3gen.jl:15-30 through the product's own host mirror (exact key products run on the GPU)."""
     k = params.max_parties
     secret_keys = [T.SecretKey_3gen(rng, params) for _ in range(k)]
@@ -143,7 +143,8 @@ def generate_keys(T, params, rng):
     bk = [T.BootstrapKeyPart_3gen(rng, secret_keys[i].key, params.gsw_noise_stddev, crp, common, T.tgsw_parameters(params),
                                   T.rlwe_parameters(params), 1) for i in range(k)]
     bk = [T.TransformedBootstrapKeyPart_3gen(b) for b in bk]
-    ks = [T.KeyswitchKey(rng, params.ks_noise_stddev, T.keyswitch_parameters(params), secret_keys[i].key, rlwe_keys[i]) for i in range(k)]
+    mk_ks = T.KeyswitchKey.on_device if ksk_on_device else T.KeyswitchKey       # rows generated by the GPU (mktfhe_generate_ksk) or by numpy
+    ks = [mk_ks(rng, params.ks_noise_stddev, T.keyswitch_parameters(params), secret_keys[i].key, rlwe_keys[i]) for i in range(k)]
     return secret_keys, bk, ks
 
 
@@ -222,7 +223,7 @@ def run_ours(args):
     t_keys = time.perf_counter()
     if rank == 0:
         secret_keys, bk, ks = generate_keys(T, params, rng)
-        eng.load_keys([b.gsw_key for b in bk], [q.key for q in ks])      # multi-device context: includes the in-library broadcast
+        eng.load_keys([b.gsw_key for b in bk], [q.engine_part() for q in ks])      # multi-device context: includes the in-library broadcast
     if world > 1:
         eng.broadcast_keys(src=0)
     t_keys = time.perf_counter() - t_keys
@@ -601,7 +602,7 @@ def run_conv(args):
     if rank == 0:                                      # keys and encrypted data are made on rank 0 only
         rng = np.random.default_rng(KEY_SEED)
         secret_keys, bk, ks = generate_keys(T, params, rng)
-        eng.load_keys([b.gsw_key for b in bk], [q.key for q in ks])
+        eng.load_keys([b.gsw_key for b in bk], [q.engine_part() for q in ks])
         T.attach_engine(bk, ks, eng)
         inp, ker = rng.integers(-half, half, (H, H)), rng.integers(-half, half, (1, K, K))
         cin, cker = T.mk_int_encrypt_3gen(rng, secret_keys, inp, W), T.mk_int_encrypt_3gen(rng, secret_keys, ker, W)

@@ -111,6 +111,12 @@ int mktfhe_load_bsk(mktfhe_ctx *ctx, int party, const int64_t *polys);
 /* KeyswitchKey.key::Array{LweSample,3} of dims (base-1, t, N) (keyswitch.jl:7-42),
  * flattened as int32 [N][t][base-1][n+1] (a[0..n-1] then b), host. */
 int mktfhe_load_ksk(mktfhe_ctx *ctx, int party, const int32_t *rows);
+/* KeyswitchKey(rng, alpha, params, out_key, rlwe_key) (keyswitch.jl:14-41) generated ON the GPU, straight into the context's
+ * key-switching key of `party` (no 44 MB .. 140 MB per party built on the host and copied): lwe_key = the party's LWE secret,
+ * int32 [n]; rlwe_key = its RLWE secret polynomial, int64 [N] (extract_lwe_key, rlwe.jl:35-41); sigma = ks_noise_stddev; seed
+ * keys the counter-based generator (Philox4x32-10): row (i, j, h) = (a uniform, b = (z_i h) << (32 - j basebit) + e + <a, s>),
+ * e Gaussian and re-centred to zero mean over the key as :28-29.  The secrets are erased from device scratch before return. */
+int mktfhe_generate_ksk(mktfhe_ctx *ctx, int party, const int32_t *lwe_key, const int64_t *rlwe_key, double sigma, uint64_t seed);
 /* all parties loaded (or received through mktfhe_key_buffers) -> ready */
 int mktfhe_finalize_keys(mktfhe_ctx *ctx);
 /* device-resident key buffers, for a one-time NCCL broadcast from rank 0:

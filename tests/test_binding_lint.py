@@ -130,6 +130,8 @@ def ctypes_to_c(t):
     if t is C.c_char_p:
         return {"char*"}
     out = set()
+    if t is C.c_double:
+        return {"double"}
     for name, ct in (("int", C.c_int), ("int64_t", C.c_int64), ("uint64_t", C.c_uint64), ("size_t", C.c_size_t), ("int32_t", C.c_int32)):
         if C.sizeof(ct) == C.sizeof(t) and (ct(-1).value < 0) == (t(-1).value < 0):
             out.add(name)

@@ -173,3 +173,54 @@ def test_int_mul_on_ciphertexts(quiet_world):
     # where the reference's wiring coincides with a true product (b < 4: rows 3 and 4 are zero, and row `ctr` = row 3), check a * b
     m = b < 4
     assert np.array_equal(got[m], (a[m] * b[m]) & 15)
+
+
+def test_keyswitch_key_generated_on_the_device(oracle):
+    """mktfhe_generate_ksk (keyswitch.jl:14-41 on the GPU): every row, read back from the device key, is an LWE encryption under s of
+    (z_i h) << (32 - j basebit) (:35) with Gaussian noise of the requested deviation, re-centred to zero mean over the key (:28-29);
+    the uniform part looks uniform; two parties / two seeds give different rows; and gates through the generated key decrypt."""
+    import torch
+    import torus_fhe_b200 as T
+    rng = np.random.default_rng(0xB200_0D0E)
+    params = T.mktfhe_parameters_2party_3gen
+    n, N, t, bb = params.lwe_size, params.rlwe_polynomial_degree, params.ks_decomp_length, params.ks_log2_base
+    B1, k = (1 << bb) - 1, params.max_parties
+    sk = [T.SecretKey_3gen(rng, params) for _ in range(k)]
+    rk = [T.RLweKey(rng, T.rlwe_parameters(params), True) for _ in range(k)]
+    crp = T.CRP_3gen(rng, T.tgsw_parameters(params), T.rlwe_parameters(params), True)
+    pk = [T.PublicKey(rng, rk[i], params.gsw_noise_stddev, crp, T.tgsw_parameters(params), 1) for i in range(k)]
+    cpk = T.CommonPubKey_3gen(pk, params, k)
+    bk = [T.TransformedBootstrapKeyPart_3gen(T.BootstrapKeyPart_3gen(rng, sk[i].key, params.gsw_noise_stddev, crp, cpk,
+                                                                      T.tgsw_parameters(params), T.rlwe_parameters(params), 1)) for i in range(k)]
+    ks = [T.KeyswitchKey.on_device(rng, params.ks_noise_stddev, T.keyswitch_parameters(params), sk[i].key, rk[i]) for i in range(k)]
+    assert ks[0].key is None
+    eng = T.engine_for(bk, ks)
+    try:
+        _, ksk_t = eng.key_tensors()
+        stride = (n + 1 + 3) & ~3
+        rows = ksk_t.cpu().numpy().view(np.int32).reshape(k, N, t, B1, stride)
+        assert not np.array_equal(rows[0], rows[1])
+        for p in range(k):
+            s, z = sk[p].key.key.astype(np.int64), rk[p].key.astype(np.int64)
+            a, b = rows[p, ..., :n].astype(np.int64), rows[p, ..., n].astype(np.int64)
+            assert np.all(rows[p, ..., n + 1:] == 0)                                       # padding
+            h = np.arange(1, B1 + 1, dtype=np.int64)[None, None, :]
+            sh = (32 - np.arange(1, t + 1) * bb)[None, :, None]
+            msg = (z[:, None, None] * h) << sh
+            err = ((b - (a * s).sum(-1) - msg + 2 ** 31) % 2 ** 32 - 2 ** 31) / 2.0 ** 32  # phase - message, as a fraction of the torus
+            assert abs(err.mean()) < 2.0 ** -32 * 2                                        # re-centred (up to the truncation of dtot32)
+            assert 0.97 < err.std() / params.ks_noise_stddev < 1.03
+            u = rows[p, ::64, :, :, :n].astype(np.float64) / 2.0 ** 32                     # a sample of the uniform words
+            assert abs(u.mean()) < 2e-3 and abs(u.std() - 12 ** -0.5) < 2e-3
+            assert len(np.unique(rows[p, :8, :, :, :n])) > 0.999 * rows[p, :8, :, :, :n].size
+        bits = rng.integers(0, 2, (2, 64)).astype(bool)
+        x, y = T.mk_encrypt_3gen(rng, sk, bits[0]), T.mk_encrypt_3gen(rng, sk, bits[1])
+        assert np.array_equal(T.mk_decrypt_3gen(sk, T.mk_gate_nand_3gen(bk, ks, x, y)), ~(bits[0] & bits[1]))
+        assert np.array_equal(T.mk_decrypt_3gen(sk, T.mk_gate_xor_3gen(bk, ks, x, y)), bits[0] ^ bits[1])
+        # argument checks
+        with pytest.raises(T.MktfheError):
+            eng.ctx.generate_ksk(5, sk[0].key.key, rk[0].key, 1e-4, 1)
+        with pytest.raises(ValueError):
+            eng.ctx.generate_ksk(0, sk[0].key.key[:-1], rk[0].key, 1e-4, 1)
+    finally:
+        T.release_engine(bk, ks)

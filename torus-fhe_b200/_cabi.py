@@ -19,7 +19,7 @@ GATE_NAND, GATE_OR, GATE_AND, GATE_XOR, GATE_AND3 = 0, 1, 2, 3, 4
 EXPORTS = (
     "mktfhe_create", "mktfhe_create_multi", "mktfhe_destroy", "mktfhe_last_error",
     "mktfhe_device_count", "mktfhe_device_ctx", "mktfhe_shard_bounds", "mktfhe_pin_host", "mktfhe_unpin_host",
-    "mktfhe_load_bsk", "mktfhe_load_ksk", "mktfhe_finalize_keys", "mktfhe_key_buffers", "mktfhe_mark_keys_received",
+    "mktfhe_load_bsk", "mktfhe_load_ksk", "mktfhe_generate_ksk", "mktfhe_finalize_keys", "mktfhe_key_buffers", "mktfhe_mark_keys_received",
     "mktfhe_bootstrap_batch", "mktfhe_gate_batch", "mktfhe_bootstrap_batch_dev", "mktfhe_gate_batch_dev",
     "mktfhe_gate_batch_mixed", "mktfhe_gate_batch_mixed_dev", "mktfhe_affine_bootstrap_batch", "mktfhe_affine_bootstrap_batch_dev",
     "mktfhe_extprod_batch", "mktfhe_blind_rotate_batch", "mktfhe_keyswitch_batch", "mktfhe_negacyclic_mul_batch",
@@ -76,6 +76,7 @@ def lib():
         "mktfhe_last_error": (C.c_char_p, [vp]),
         "mktfhe_load_bsk": (C.c_int, [vp, C.c_int, vp]),
         "mktfhe_load_ksk": (C.c_int, [vp, C.c_int, vp]),
+        "mktfhe_generate_ksk": (C.c_int, [vp, C.c_int, vp, vp, C.c_double, C.c_uint64]),
         "mktfhe_finalize_keys": (C.c_int, [vp]),
         "mktfhe_key_buffers": (C.c_int, [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]),
         "mktfhe_mark_keys_received": (C.c_int, [vp]),
@@ -196,6 +197,13 @@ class Context:
         if rows.size != self.N * self.t * B1 * (self.n + 1):
             raise ValueError(f"ksk of party {party}: expected {(self.N, self.t, B1, self.n + 1)}, got {rows.shape}")
         self._chk(lib().mktfhe_load_ksk(self.h, party, _p(rows)))
+
+    def generate_ksk(self, party, lwe_key, rlwe_key, sigma, seed):
+        """keyswitch.jl:14-41 on the GPU, straight into the device key (mktfhe_generate_ksk)."""
+        s, z = _c(lwe_key, np.int32).reshape(-1), _c(rlwe_key, np.int64).reshape(-1)
+        if s.size != self.n or z.size != self.N:
+            raise ValueError(f"generate_ksk: expected an LWE key of {self.n} and an RLWE key of {self.N} coefficients")
+        self._chk(lib().mktfhe_generate_ksk(self.h, party, _p(s), _p(z), float(sigma), int(seed) & 0xFFFFFFFFFFFFFFFF))
 
     def finalize_keys(self):
         self._chk(lib().mktfhe_finalize_keys(self.h))

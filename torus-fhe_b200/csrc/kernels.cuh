@@ -852,4 +852,71 @@ __global__ void __launch_bounds__(KS_THREADS) keyswitch_kernel(int n, int k, int
     if (tid == n % KS_THREADS) ob[g] = (int32_t)((uint32_t)e[N] + bsum);   // thread owning column n
 }
 
+// ---- key generation on the device: the key-switching key (keyswitch.jl:14-41) -------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), counter-based: row and column of a key word are its counter, so the key is a pure function
+// of (seed, party) and no generator state is kept.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const u32 hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const u32 hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+// standard normal from two 32-bit words (Box-Muller, double precision)
+__device__ __forceinline__ double philox_normal(u32 a, u32 b) {
+    const double u1 = ((double)a + 1.0) * (1.0 / 4294967296.0), u2 = (double)b * (1.0 / 4294967296.0);
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+// pass 1: one Gaussian per row (row = (i * t + j) * B1 + h) and their sum, for the re-centring of keyswitch.jl:28-29
+__global__ void ksk_noise_kernel(double* __restrict__ noise, double* __restrict__ sum, size_t rows, double sigma, uint2 key) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double v = 0.0;
+    if (r < rows) {
+        const uint4 x = philox4x32(make_uint4((u32)r, (u32)(r >> 32), 0u, 0xE0150000u), key);
+        v = philox_normal(x.x, x.y) * sigma;
+        noise[r] = v;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sum, v);
+}
+// pass 2: one warp per row: a = n uniform words, b = message(i, j, h) + dtot32(noise - mean) + <a, s>  (keyswitch.jl:35-39, lwe.jl:47-53);
+// rows are written in the device layout of the fused key switch (padded to ks_row_stride(n) words)
+constexpr int KG_WARPS = 8;
+__global__ void __launch_bounds__(32 * KG_WARPS) ksk_generate_kernel(int32_t* __restrict__ rows_out, const double* __restrict__ noise,
+                                                                      const double* __restrict__ sum, const int32_t* __restrict__ s,
+                                                                      const int64_t* __restrict__ z, int n, int t, int basebit, size_t rows, uint2 key) {
+    const size_t r = (size_t)blockIdx.x * KG_WARPS + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31, B1 = (1 << basebit) - 1, stride = ks_row_stride(n);
+    const int h = (int)(r % B1) + 1, j = (int)((r / B1) % t) + 1;
+    const size_t i = r / ((size_t)B1 * t);
+    int32_t* row = rows_out + r * stride;
+    u32 dot = 0;
+    for (int c0 = 4 * lane; c0 < stride; c0 += 128) {
+        const uint4 x = philox4x32(make_uint4((u32)r, (u32)(r >> 32), (u32)(c0 >> 2), 0xA0000000u), key);
+        const u32 w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int c = c0 + q;
+            if (c < n) {
+                row[c] = (int32_t)w[q];
+                dot += w[q] * (u32)s[c];
+            } else if (c > n) {
+                row[c] = 0;                                    // padding
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane == 0) {
+        const double e = noise[r] - *sum / (double)rows;                                        // keyswitch.jl:29
+        const u32 msg = (u32)((int32_t)z[i] * h) << (32 - j * basebit);                           // :35 (Int32 wrap)
+        row[n] = (int32_t)(msg + (u32)__double2int_rz(e * 4294967296.0) + dot);                   // dtot32: trunc(Int32, d * 2^32)
+    }
+}
+
 }  // namespace mk

@@ -547,6 +547,36 @@ int mktfhe_load_ksk(mktfhe_ctx* c, int party, const int32_t* rows) {
     return MKTFHE_OK;
 }
 
+int mktfhe_generate_ksk(mktfhe_ctx* c, int party, const int32_t* lwe_key, const int64_t* rlwe_key, double sigma, uint64_t seed) {
+    if (!c) return MKTFHE_EINVAL;
+    if (party < 0 || party >= c->prm.k || !lwe_key || !rlwe_key) return fail(c, MKTFHE_EINVAL, "generate_ksk: bad party %d or NULL key", party);
+    if (!(sigma >= 0.0) || sigma > 0.25) return fail(c, MKTFHE_EINVAL, "generate_ksk: noise standard deviation %g out of range", sigma);
+    CU_TRY(c, cudaSetDevice(c->device));
+    const int n = c->prm.n, N = c->prm.N, t = c->prm.t, bb = c->prm.basebit, B1 = (1 << bb) - 1;
+    const size_t rows = (size_t)N * t * B1, per = c->ksk_bytes / c->prm.k;
+    // scratch: [rows] noise doubles, the sum, then the two secret vectors (erased below)
+    const size_t off_sum = rows * 8, off_s = off_sum + 8, off_z = (off_s + (size_t)n * 4 + 7) & ~(size_t)7, total = off_z + (size_t)N * 8;
+    int rc = reserve(c, c->raw, total);
+    if (rc) return rc;
+    char* base = (char*)c->raw.p;
+    CU_TRY(c, cudaMemsetAsync(base + off_sum, 0, 8, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(base + off_s, lwe_key, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(base + off_z, rlwe_key, (size_t)N * 8, cudaMemcpyHostToDevice, c->stream));
+    const uint2 key = make_uint2((uint32_t)seed ^ (uint32_t)(0x9E3779B9u * (uint32_t)(party + 1)), (uint32_t)(seed >> 32));
+    mk::ksk_noise_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, c->stream>>>((double*)base, (double*)(base + off_sum), rows, sigma, key);
+    CU_TRY(c, cudaGetLastError());
+    mk::ksk_generate_kernel<<<(unsigned)((rows + mk::KG_WARPS - 1) / mk::KG_WARPS), 32 * mk::KG_WARPS, 0, c->stream>>>(
+        (int32_t*)((char*)c->d_ksk + per * party), (const double*)base, (const double*)(base + off_sum), (const int32_t*)(base + off_s),
+        (const int64_t*)(base + off_z), n, t, bb, rows, key);
+    CU_TRY(c, cudaGetLastError());
+    c->launches += 2;
+    CU_TRY(c, cudaMemsetAsync(base + off_s, 0, total - off_s, c->stream));      // the secrets do not stay in device scratch
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->ksk_loaded[party] = 1;
+    c->ready = false;
+    return MKTFHE_OK;
+}
+
 int mktfhe_finalize_keys(mktfhe_ctx* c) {
     if (!c) return MKTFHE_EINVAL;
     for (int p = 0; p < c->prm.k; p++)

@@ -33,14 +33,17 @@ class Engine:
         self.devices = list(self.ctx.devices)
         self.ready = False
 
-    # bsk: per party int64 [n][4][l][N]; ksk: per party int32 [N][t][B-1][n+1]
+    # bsk: per party int64 [n][4][l][N]; ksk: per party int32 [N][t][B-1][n+1], or ("generate", lwe_key, rlwe_key, sigma, seed)
     def load_keys(self, bsk_parts, ksk_parts):
         k = self.params.max_parties
         if len(bsk_parts) != k or len(ksk_parts) != k:
             raise ValueError(f"expected keys of {k} parties, got {len(bsk_parts)} / {len(ksk_parts)}")
         for p in range(k):
             self.ctx.load_bsk(p, bsk_parts[p])
-            self.ctx.load_ksk(p, ksk_parts[p])
+            if isinstance(ksk_parts[p], tuple) and ksk_parts[p][0] == "generate":     # KeyswitchKey.on_device: rows made on the GPU
+                self.ctx.generate_ksk(p, *ksk_parts[p][1:])
+            else:
+                self.ctx.load_ksk(p, ksk_parts[p])
         self.ctx.finalize_keys()
         self.ready = True
         return self
