@@ -67,6 +67,9 @@ constexpr int N = rns::N;
 #ifndef MK_LOCKSTEP
 #define MK_LOCKSTEP 0       // n > 0: CTA-wide barrier every n steps to keep the gates on the same key element (measured: loses)
 #endif
+#ifndef MK_KEY_FIXED
+#define MK_KEY_FIXED 0
+#endif
 #ifndef MK_STAGGER_NS
 #define MK_STAGGER_NS 0     // start odd gate slots this many ns late to interleave the IMAD-free phases (measured: loses)
 #endif
@@ -699,7 +702,11 @@ __device__ __forceinline__ void blind_rotate_body(const BlindRotateArgs& p) {
         if (cta_full && (it % MK_LOCKSTEP) == 0) asm volatile("bar.sync 15, %0;" ::"r"(GPC * TPG) : "memory");
 #endif
         if (a == 0) continue;   // :69 (uniform across the gate)
+#if MK_KEY_FIXED     // diagnostic only (NOT exact): every step reads key element 0, which stays in L1 -- the upper bound of what any
+        extprod_step<L, true, W>(acc, dig, tiles, twB, p.bsk, a, p.bgbit, bar_id, pbar_id, gtid);            // key-staging scheme (TMA, smem) could gain
+#else
         extprod_step<L, true, W>(acc, dig, tiles, twB, p.bsk + (size_t)it * estride, a, p.bgbit, bar_id, pbar_id, gtid);
+#endif
     }
     if (p.acc_out) {
         int64_t* ao = p.acc_out + (size_t)g * 2 * N;

@@ -331,7 +331,8 @@ def _mul_context(N, device=0):
 
 
 def negacyclic_mul(small, big):
-    """Exact product mod (X^N + 1, 2^64) on the GPU; `small` has |coeff| < 2^15."""
+    """Exact product mod (X^N + 1, 2^64) on the GPU.  `small` must satisfy |coeff| <= 2^8 at N = 1024 (2^25 at N = 2048): beyond that
+    N * |small| * 2^63 leaves the exact range of the CRT lift, and the library rejects the call (MKTFHE_EINVAL)."""
     small, big = np.asarray(small, np.int64), np.asarray(big, np.int64)
     N = small.shape[-1]
     bshape = np.broadcast_shapes(small.shape, big.shape)
