@@ -67,6 +67,15 @@ constexpr int N = rns::N;
 #ifndef MK_LOCKSTEP
 #define MK_LOCKSTEP 0       // n > 0: CTA-wide barrier every n steps to keep the gates on the same key element (measured: loses)
 #endif
+#ifndef MK_ANTIPHASE
+#define MK_ANTIPHASE 0      // experiment (profiles/ab_r2.txt): the two gates of a CTA run half a step apart, held there by two CTA-wide barriers per
+#endif                      // step, so that one gate's decomposition / CRT overlaps the other's transforms; MK_AP_SPLIT picks the half-step boundary
+#ifndef MK_AP_SPLIT
+#define MK_AP_SPLIT 0       // 0: after the last forward transform; 1: between its two passes
+#endif
+#ifndef MK_PHASE_TRACE
+#define MK_PHASE_TRACE 0
+#endif
 #ifndef MK_KEY_FIXED
 #define MK_KEY_FIXED 0
 #endif
@@ -340,7 +349,7 @@ __device__ __forceinline__ void crt_phase_lat(u64* __restrict__ acc, const u32* 
 template <int L, bool MUX, int W = WPG>
 __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restrict__ dig, u32* __restrict__ tiles,
                                              const uint2_* __restrict__ twB, const u32* __restrict__ key, int a, int bgbit,
-                                             int bar_id, int pbar_id, int gtid) {
+                                             int bar_id, int pbar_id, int gtid, bool ap = false, int cta_threads = 0) {
     static_assert(W == 3 || W == 6 || (L >= 2 && W == lat_wpg(L)), "warps per gate: 3, 6, or 6 l (latency launch)");
     constexpr bool LAT = L >= 2 && W == lat_wpg(L);
     const int gw = gtid >> 5, lane = gtid & 31;
@@ -430,7 +439,25 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
             const int s_own = 2 * i + o, s_for = 2 * i + 1 - o;
             u32 x[32];
             load_digits(x, dig, lut, s_own, lane, bias);
+#if MK_ANTIPHASE && MK_AP_SPLIT == 1
+            {   // the forward transform written out, with the half-step boundary between its passes
+                const u32 p4f = rns::keep_in_register(4 * p);
+                rns::fwd_passA_pre(x, twAf, p);
+#pragma unroll
+                for (int r = 0; r < 32; r++) tile[r * rns::TILE_STRIDE + lane] = x[r];
+                __syncwarp();
+                if (ap && i == L - 1) asm volatile("bar.sync 15, %0;" ::"r"(cta_threads) : "memory");
+#pragma unroll
+                for (int c = 0; c < 32; c++) x[c] = rns::reduce_to_4p(tile[lane * rns::TILE_STRIDE + c], p4f);
+                __syncwarp();
+                rns::fwd_passB(x, twBf, p);
+            }
+#else
             warp_ntt_fwd_digits(x, tile, twAf, twBf, p, lane);
+#if MK_ANTIPHASE
+            if (ap && i == L - 1) asm volatile("bar.sync 15, %0;" ::"r"(cta_threads) : "memory");
+#endif
+#endif
 #pragma unroll
             for (int c = 0; c < 32; c++) tile[c * 32 + lane] = x[c];
             pair_barrier(pb);
@@ -689,6 +716,12 @@ __device__ __forceinline__ void blind_rotate_body(const BlindRotateArgs& p) {
 #if MK_LOCKSTEP
     const bool cta_full = (blockIdx.x + 1) * GPC <= p.G;      // every gate slot of this CTA is active
 #endif
+#if MK_ANTIPHASE
+    // both gate slots of the CTA active, two six-warp gates: run them half a step apart (gate 1 waits one barrier more at the start, gate 0
+    // one more at the end: 2 kn + 1 CTA-wide barriers each)
+    const bool ap = GPC == 2 && W == 6 && (blockIdx.x + 1) * GPC + p.g0 <= p.G;
+    if (ap && slot == 1) asm volatile("bar.sync 15, %0;" ::"r"(GPC * TPG) : "memory");
+#endif
     for (int it = 0; it < kn; it++) {
         const int a = mod_switch_2N((int32_t)((uint32_t)lin.cx * (uint32_t)rx + (uint32_t)lin.cy * (uint32_t)ry + (uint32_t)lin.cz * (uint32_t)rz));
         if (it + 1 < kn) {
@@ -701,17 +734,32 @@ __device__ __forceinline__ void blind_rotate_body(const BlindRotateArgs& p) {
         // out of phase costs 3 %)
         if (cta_full && (it % MK_LOCKSTEP) == 0) asm volatile("bar.sync 15, %0;" ::"r"(GPC * TPG) : "memory");
 #endif
+#if MK_ANTIPHASE
+        if (ap) asm volatile("bar.sync 15, %0;" ::"r"(GPC * TPG) : "memory");          // start of the first half-step
+        if (a == 0) { if (ap) asm volatile("bar.sync 15, %0;" ::"r"(GPC * TPG) : "memory"); continue; }
+#else
         if (a == 0) continue;   // :69 (uniform across the gate)
+#endif
+#if MK_PHASE_TRACE   // diagnostic: SM clock at the start of every step of every gate of CTA 0 and CTA 1, dumped through acc_out
+        if (p.acc_out && gtid == 0 && blockIdx.x < 2 && it < 2 * N) p.acc_out[(size_t)g * 2 * N + it] = (int64_t)clock64();
+#endif
 #if MK_KEY_FIXED     // diagnostic only (NOT exact): every step reads key element 0, which stays in L1 -- the upper bound of what any
         extprod_step<L, true, W>(acc, dig, tiles, twB, p.bsk, a, p.bgbit, bar_id, pbar_id, gtid);            // key-staging scheme (TMA, smem) could gain
+#elif MK_ANTIPHASE
+        extprod_step<L, true, W>(acc, dig, tiles, twB, p.bsk + (size_t)it * estride, a, p.bgbit, bar_id, pbar_id, gtid, ap, GPC * TPG);
 #else
         extprod_step<L, true, W>(acc, dig, tiles, twB, p.bsk + (size_t)it * estride, a, p.bgbit, bar_id, pbar_id, gtid);
 #endif
     }
+#if MK_ANTIPHASE
+    if (ap && slot == 0) asm volatile("bar.sync 15, %0;" ::"r"(GPC * TPG) : "memory");
+#endif
+#if !MK_PHASE_TRACE
     if (p.acc_out) {
         int64_t* ao = p.acc_out + (size_t)g * 2 * N;
         for (int i = gtid; i < 2 * N; i += TPG) ao[i] = (int64_t)acc[i];
     }
+#endif
     if (p.ksk) {   // fused extraction + key switch (the host only sets ksk when ks_fusable(n, t))
         if (p.ks_t == 3) fused_keyswitch<3, W>(acc, tiles, p, g, gtid, bar_id);
         else fused_keyswitch<5, W>(acc, tiles, p, g, gtid, bar_id);
