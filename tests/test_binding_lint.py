@@ -38,6 +38,7 @@ JULIA_TO_C = {
     "Cvoid": {"void"},
     "Csize_t": {"size_t"},
     "Int64": {"int64_t"},
+    "Int32": {"int32_t"},
     "UInt64": {"uint64_t"},
     "Ptr{Int32}": {"int32_t*"},
     "Ptr{Int64}": {"int64_t*"},
@@ -63,8 +64,8 @@ def split_top(s):
     return out
 
 
-def julia_ccalls():
-    text = open(os.path.join(ROOT, "julia", "TFHE_B200.jl")).read()
+def julia_ccalls(fname="TFHE_B200.jl"):
+    text = open(os.path.join(ROOT, "julia", fname)).read()
     text = "\n".join(line.split("#")[0] if not line.lstrip().startswith("#") else "" for line in text.splitlines())
     calls = []
     for m in re.finditer(r"ccall\(\(:(mktfhe_[a-z0-9_]+),\s*LIB\)\s*,", text):
@@ -102,6 +103,38 @@ def test_julia_ccalls_match_the_header():
     for must in ("mktfhe_create_multi", "mktfhe_device_count", "mktfhe_destroy", "mktfhe_last_error", "mktfhe_load_bsk", "mktfhe_load_ksk", "mktfhe_finalize_keys",
                  "mktfhe_bootstrap_batch", "mktfhe_gate_batch", "mktfhe_gate_batch_mixed", "mktfhe_blind_rotate_batch", "mktfhe_keyswitch_batch"):
         assert must in bound, must
+
+
+def test_single_key_julia_shim_matches_the_header():
+    """julia/TFHE1_B200.jl (single-key gate API over the same library): every ccall against the C declarations, the CParams
+    struct, balanced blocks, every exported name defined, and the same gate table as the Python twin / the oracle (gates.jl:16-142)."""
+    decls = c_declarations()
+    calls = julia_ccalls("TFHE1_B200.jl")
+    assert len(calls) >= 9
+    for name, ret, types, args in calls:
+        assert name in decls, name
+        cret, cparams = decls[name]
+        assert cret in JULIA_TO_C[ret], (name, ret, cret)
+        assert len(types) == len(cparams) == len(args), (name, types, cparams, args)
+        for jt, ct in zip(types, cparams):
+            assert ct in JULIA_TO_C[jt], f"{name}: Julia {jt} bound to C {ct}"
+    bound = {c[0] for c in calls}
+    for must in ("mktfhe_create_multi", "mktfhe_load_bsk", "mktfhe_load_ksk", "mktfhe_finalize_keys", "mktfhe_affine_bootstrap_batch",
+                 "mktfhe_blind_rotate_batch", "mktfhe_keyswitch_batch", "mktfhe_bootstrap_batch", "mktfhe_destroy"):
+        assert must in bound, must
+    raw = open(os.path.join(ROOT, "julia", "TFHE1_B200.jl")).read()
+    text = _julia_balance(raw)
+    body = re.search(r"struct CParams.*?\n(.*?)\nend", raw, flags=re.S).group(1)
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "mktfhe_b200.h")).read(), flags=re.S)
+    cfields = re.findall(r"int32_t\s+([A-Za-z_]+);", re.search(r"typedef struct \{(.*?)\} mktfhe_params;", header, flags=re.S).group(1))
+    assert re.findall(r"([A-Za-z_]+)::Int32", body) == cfields
+    exported = re.search(r"\nexport (.*?)\n\n", text + "\n\n", flags=re.S).group(1)
+    for name in re.findall(r"[A-Za-z_][A-Za-z_0-9!]*", exported):
+        assert re.search(rf"(function |struct |^|\(:){re.escape(name)}(?![A-Za-z_0-9!])", text, flags=re.M), f"exported {name} is not defined"
+    from oracle import tfhe1_oracle as O1
+    table = dict((m.group(1).upper(), tuple(int(v) for v in m.group(2, 3, 4, 5)))
+                 for m in re.finditer(r"\(:gate_([a-z]+), (-?\d+), (\d+), (-?\d+), (-?\d+)\)", raw))
+    assert table == O1.GATE_LINEAR
 
 
 def test_julia_cparams_struct_matches_mktfhe_params():

@@ -57,6 +57,36 @@ def test_oracle_primitives_against_definitions():
     assert np.array_equal(O1.mul_by_monomial(O1.mul_by_monomial(p, 5), -5), p)
 
 
+def test_host_mirror_names_parameters_and_linear_prologues():
+    """api.jl:76-113 parameter values; the twelve gates of gates.jl under their names; each gate's linear prologue in the product
+    equals the oracle's table (gates.jl:16-142); LweSample arithmetic wraps as Int32 (lwe.jl:62-76)."""
+    import inspect
+    import torus_fhe_b200.tfhe1 as T1
+    p = T1.tfhe_parameters_128()
+    assert (p.lwe_size, p.rlwe_polynomial_degree, p.rlwe_mask_size, p.bs_decomp_length, p.bs_log2_base, p.ks_decomp_length, p.ks_log2_base) == (630, 1024, 1, 3, 7, 8, 2)
+    assert p.lwe_noise_stddev == 1 / 2 ** 15 and p.bs_noise_stddev == 1 / 2 ** 25 and p.rlwe_is32
+    p = T1.tfhe_parameters_80()
+    assert (p.lwe_size, p.bs_decomp_length, p.bs_log2_base, p.ks_decomp_length, p.ks_log2_base) == (500, 2, 10, 8, 2)
+    assert set(T1.GATES) == {"NAND", "OR", "AND", "XOR", "XNOR", "NOT", "NOR", "ANDNY", "ANDYN", "ORNY", "ORYN", "MUX"}      # runtests.jl:10-23
+    for name in ("make_key_pair", "encrypt", "decrypt", "SecretKey", "CloudKey", "BootstrapKey", "bootstrap", "bootstrap_wo_keyswitch", "keyswitch",
+                 "gate_constant", "lwe_noiseless_trivial", "lwe_encrypt", "lwe_phase"):
+        assert hasattr(T1, name), name
+    # the (mu0, cx, cy) each gate hands to mktfhe_affine_bootstrap_batch, read from its source, against the oracle's table
+    for name, (m, space, cx, cy) in O1.GATE_LINEAR.items():
+        src = inspect.getsource(T1.GATES[name][0])
+        assert f"encode_message({m}, {space}), {cx}, {cy}, 0" in src, (name, src)
+    a = T1.LweSample(T1.LweParams(3), np.array([2 ** 31 - 1, -2 ** 31, 5], np.int32), np.int32(2 ** 31 - 1))
+    s2 = a + a
+    assert list(s2.a) == [-2, 0, 10] and int(s2.b) == -2 and list((-a).a[:1]) == [-(2 ** 31 - 1)] and list((a * 2).a) == [-2, 0, 10] and list((2 * a).a) == [-2, 0, 10]
+    assert int((a - a).b) == 0 and T1.lwe_noiseless_trivial(7, T1.LweParams(4), (2,)).a.shape == (2, 4)
+    # engine_parts: part order and the << 32 embedding
+    bk = np.arange(2 * 3 * 2 * 2 * 4, dtype=np.int32).reshape(2, 3, 2, 2, 4) - 40
+    parts = T1.BootstrapKey(None, 0.0, None, None, None, samples=bk).engine_parts()
+    assert parts.shape == (2, 4, 3, 4) and parts.dtype == np.int64
+    assert np.array_equal(parts[:, 0], bk[:, :, 1, 1].astype(np.int64) << 32) and np.array_equal(parts[:, 1], bk[:, :, 0, 1].astype(np.int64) << 32)
+    assert np.array_equal(parts[:, 2], bk[:, :, 0, 0].astype(np.int64) << 32) and np.array_equal(parts[:, 3], bk[:, :, 1, 0].astype(np.int64) << 32)
+
+
 def _engine_parts(bk):
     """The product's mapping of a standard TGSW key onto the engine's four parts, through its own class."""
     import torus_fhe_b200.tfhe1 as T1
