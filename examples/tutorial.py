@@ -43,7 +43,7 @@ def encrypted_minimum(ck, a, b):
 def main():
     rng = np.random.default_rng(123)
     t0 = time.perf_counter()
-    secret_key, cloud_key = T1.make_key_pair(rng)                  # tfhe_parameters_128 (the 80-bit set needs 10-bit gadget digits)
+    secret_key, cloud_key = T1.make_key_pair(rng)                  # the reference's default: tfhe_parameters_80
     T1.engine_for(cloud_key)
     print(f"key generation + upload: {time.perf_counter() - t0:.2f} s")
     pairs = 256

@@ -59,7 +59,8 @@ extern "C" {
 /* Integer part of SchemeParameters_3gen (api.jl:50-67); rlwe_mask_size = 1 and
  * rlwe_is32 = false as in every 3gen set (mk_api.jl:32-322).  Supported:
  *  - N = 1024 (2..8 parties, mk_api.jl:32-146): 1 <= l <= 4, bgbit <= 8, 2l*N*2^(bgbit-1)*2^63 < M/4 with M ~ 2^84 the
- *    product of the three NTT primes (so the CRT result is exact), n*k <= 8192;
+ *    product of the three NTT primes (so the CRT result is exact), n*k <= 8192; with MKTFHE_FLAG_TORUS32: l = 2 or 3,
+ *    bgbit <= 16, l*bgbit <= 32;
  *  - N = 2048 (16..256 parties, mk_api.jl:214-310): l = 1 or 2, bgbit <= 27, four NTT primes (M ~ 2^112), n*k <= 2^18;
  *  - t*basebit <= 31, basebit <= 16.
  * Rejected with MKTFHE_EINVAL: N = 4096 (512 parties). */
@@ -71,8 +72,16 @@ typedef struct {
     int32_t bgbit;    /* gsw_log2_base */
     int32_t t;        /* ks_decomp_length */
     int32_t basebit;  /* ks_log2_base */
-    int32_t reserved;
+    int32_t reserved; /* flags: 0, or MKTFHE_FLAG_TORUS32 */
 } mktfhe_params;
+
+/* Torus32 mode (N = 1024 only): for schemes whose ring elements are Torus32 (rlwe_is32 = true: the single-key sets of api.jl:76-113
+ * and the CCS multi-key sets) with a gadget base above 2^8.  The bootstrapping key is loaded UNSHIFTED -- int64 words holding the
+ * 32-bit signed Torus32 values -- gadget digits may have up to 16 bits (l * bgbit <= 32), accumulators, test-vector message and
+ * the parity hooks carry Torus32 values in the top half of their 64-bit words (v << 32), and each external product is added as
+ * R << 32.  Without the flag a Torus32 key can still be served through the default kernels as K << 32 when bgbit <= 8
+ * (torus-fhe_b200/tfhe1.py does that for tfhe_parameters_128: their table-driven first transform stage is faster). */
+#define MKTFHE_FLAG_TORUS32 1
 
 typedef struct mktfhe_ctx mktfhe_ctx;
 

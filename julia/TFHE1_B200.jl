@@ -6,7 +6,7 @@
 # explains the mapping (one party, Torus32 values carried as v << 32, a standard TGSW sample as the four 3gen parts).
 #
 # Usage inside the reference tree: `include("src/TFHE.jl"); include("TFHE1_B200.jl"); using .TFHE1_B200`, then
-#     secret_key, cloud_key = TFHE1_B200.make_key_pair(rng, params)     # params: a SchemeParameters with bs_log2_base <= 8
+#     secret_key, cloud_key = TFHE1_B200.make_key_pair(rng, params)     # params: tfhe_parameters_80 / tfhe_parameters_128 (N = 1024)
 #     TFHE1_B200.gate_nand(cloud_key, x, y)                             # x, y :: LweSample or Vector{LweSample} (one launch per vector)
 module TFHE1_B200
 
@@ -58,18 +58,22 @@ function CloudKey(rng::AbstractRNG, secret_key::SecretKey; devices::Vector{Cint}
     tp = tgsw_parameters(params)
     n, l, N = params.lwe_size, tp.decomp_length, params.rlwe_polynomial_degree
     parts = Array{Int64, 4}(undef, N, l, 4, n)
+    # gadget digits of up to 8 bits ride the default kernels (Torus32 values as v << 32); wider ones (tfhe_parameters_80: Bg = 2^10)
+    # use the library's Torus32 mode (include/mktfhe_b200.h, MKTFHE_FLAG_TORUS32): keys unshifted
+    t32 = tp.log2_base > 8
+    sh = t32 ? 0 : 32
     for j in 1:n
         s = tgsw_encrypt(rng, secret_key.key.key[j], params.bs_noise_stddev, rlwe_key, tp)     # TGswSample: samples[q, row], tgsw.jl:36-46
         for q in 1:l
             # part_1 body <- body digits, part_2 body <- mask digits, part_3 mask <- mask digits, part_4 mask <- body digits
-            parts[:, q, 1, j] = Int64.(s.samples[q, 2].a[2].coeffs) .<< 32
-            parts[:, q, 2, j] = Int64.(s.samples[q, 1].a[2].coeffs) .<< 32
-            parts[:, q, 3, j] = Int64.(s.samples[q, 1].a[1].coeffs) .<< 32
-            parts[:, q, 4, j] = Int64.(s.samples[q, 2].a[1].coeffs) .<< 32
+            parts[:, q, 1, j] = Int64.(s.samples[q, 2].a[2].coeffs) .<< sh
+            parts[:, q, 2, j] = Int64.(s.samples[q, 1].a[2].coeffs) .<< sh
+            parts[:, q, 3, j] = Int64.(s.samples[q, 1].a[1].coeffs) .<< sh
+            parts[:, q, 4, j] = Int64.(s.samples[q, 2].a[1].coeffs) .<< sh
         end
     end
     ks = KeyswitchKey(rng, params.ks_noise_stddev, keyswitch_parameters(params), secret_key.key, rlwe_key)
-    prm = CParams(n, N, 1, l, tp.log2_base, ks.params.decomp_length, ks.params.log2_base, 0)
+    prm = CParams(n, N, 1, l, tp.log2_base, ks.params.decomp_length, ks.params.log2_base, t32 ? 1 : 0)
     out = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:mktfhe_create_multi, LIB), Cint, (Ref{CParams}, Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), prm, length(devices),
                isempty(devices) ? Ptr{Cint}(C_NULL) : pointer(devices), out)

@@ -110,12 +110,15 @@ def test_embedding_into_the_3gen_path_is_exact(oracle):
         assert O1.decrypt(s, (ra, rb)) == bit
 
 
-@pytest.fixture(scope="module")
-def small_single_key():
-    """Key bytes from the single-key oracle's own generator (N = 1024, n = 16), loaded into the product through its classes."""
+@pytest.fixture(scope="module", params=[(3, 7), (2, 10), (3, 9)], ids=["l3_bg7_default_kernels", "l2_bg10_torus32_mode", "l3_bg9_torus32_mode"])
+def small_single_key(request):
+    """Key bytes from the single-key oracle's own generator (N = 1024, n = 16), loaded into the product through its classes: the gadget
+    shape of tfhe_parameters_128 (default kernels, keys << 32), of tfhe_parameters_80 (10-bit digits: the library's Torus32 mode) and
+    of the CCS 2-party set (l = 3, Bg = 2^9: Torus32 mode with three levels)."""
     import torus_fhe_b200.tfhe1 as T1
     rng = np.random.default_rng(11)
-    n, N, l, bg, t, bb = 16, 1024, 3, 7, 8, 2
+    l, bg = request.param
+    n, N, t, bb = 16, 1024, 8, 2
     s, z, bk, ksk = O1.keygen(rng, n, N, l, bg, t, bb, 2.0 ** -25, 2.0 ** -15)
     params = T1.SchemeParameters(n, 2.0 ** -15, N, 1, True, l, bg, 2.0 ** -25, t, bb, 2.0 ** -15, 1)
     sk = T1.SecretKey(None, params, key=s)
@@ -142,6 +145,16 @@ def test_single_key_gates_bit_exact_against_the_oracle(small_single_key):
             ra, rb = O1.gate(name, bk, ksk, prm, *[(v.a[g], v.b[g]) for v in args])
             assert np.array_equal(out.a[g], ra) and int(out.b[g]) == int(rb), (name, g)
         assert np.array_equal(T1.decrypt(sk, out), plain(*[bits[:, i] for i in range(nargs)])), name
+    # one external product alone (tgsw_extern_mul, tgsw.jl:143-147) through the parity hook: Torus32 accumulators ride in the top halves
+    eng = T1.engine_for(ck)
+    acc = rng.integers(-2 ** 31, 2 ** 31, (6, 2, 1024)).astype(np.int32)
+    acc[0], acc[1] = 0, -1
+    elem = np.array([0, 3, 7, 15, 1, 2], np.int32)
+    got = eng.ctx.extprod_batch(elem, acc.astype(np.int64) << 32)
+    assert np.all((got & 0xFFFFFFFF) == 0)
+    l, bgbit = prm[0], prm[1]
+    for g in range(6):
+        assert np.array_equal((got[g] >> 32).astype(np.int32), O1.tgsw_extern_mul(acc[g], bk[elem[g]], l, bgbit)), g
     # bootstrap = keyswitch o bootstrap_wo_keyswitch (bootstrap.jl:97-100); scalar call = batch of one
     mu = T1.encode_message(1, 8)
     b1 = T1.bootstrap(ck, None, mu, x)
@@ -165,12 +178,30 @@ def test_reference_truth_table_test_on_tfhe_parameters_128():
         for name, (fn, nargs, plain) in T1.GATES.items():
             out = fn(ck, *(x, y, z)[:nargs])
             assert np.array_equal(T1.decrypt(sk, out), plain(*[bits[:, i] for i in range(nargs)])), name
-        # the 80-bit set needs 10-bit gadget digits: refused by the library, never silently mis-served
-        sk80 = T1.SecretKey(rng, T1.tfhe_parameters_80())
-        ck80 = T1.CloudKey.__new__(T1.CloudKey)
-        ck80.params, ck80._engine = sk80.params, None
-        import torus_fhe_b200 as T
-        with pytest.raises(T.MktfheError):
-            T1.engine_for(ck80)
+    finally:
+        ck._engine.close()
+
+
+@pytest.mark.gpu
+def test_reference_gate_testcase_on_its_default_parameters():
+    """test/runtests.jl:28-42 ("gate"): `make_key_pair(rng)` with the DEFAULT parameters -- tfhe_parameters_80, Bg = 2^10 -- then every
+    gate on every input combination.  Runs in the library's Torus32 mode (10-bit gadget digits)."""
+    import torus_fhe_b200 as T
+    import torus_fhe_b200.tfhe1 as T1
+    rng = np.random.default_rng(123)
+    sk, ck = T1.make_key_pair(rng)
+    assert sk.params == T1.tfhe_parameters_80()
+    try:
+        eng = T1.engine_for(ck)
+        assert eng.ctx.flags == T._cabi.FLAG_TORUS32
+        bits = np.array([[a, b, c] for a in (0, 1) for b in (0, 1) for c in (0, 1)] * 4, bool)
+        x, y, z = (T1.encrypt(rng, sk, bits[:, i]) for i in range(3))
+        for name, (fn, nargs, plain) in T1.GATES.items():
+            out = fn(ck, *(x, y, z)[:nargs])
+            assert np.array_equal(T1.decrypt(sk, out), plain(*[bits[:, i] for i in range(nargs)])), name
+        # flag validation: Torus32 mode is an N = 1024, l = 2..3 mode; unknown flag bits are refused
+        for bad in ((500, 1024, 1, 4, 8, 8, 2, 1), (500, 1024, 1, 2, 17, 8, 2, 1), (500, 2048, 1, 1, 10, 8, 2, 1), (500, 1024, 1, 2, 10, 8, 2, 2)):
+            with pytest.raises(T.MktfheError):
+                T._cabi.Context(*bad[:7], flags=bad[7])
     finally:
         ck._engine.close()

@@ -33,7 +33,7 @@ def kernel_id(lib=None, match=("blind_rotate",)):
                 h.update(m.group(1).encode()); n += 1
             continue
         if keep:
-            m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(.*?);", line)
+            m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(.*?);", line)
             if m:
                 h.update(m.group(1).encode())
     return h.hexdigest()[:16] if n else None

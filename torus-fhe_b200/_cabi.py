@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("MKTFHE_B200_LIB") or os.path.join(_HERE, "libmktfhe_b
 
 OK, EINVAL, ECUDA, ESTATE, ENOMEM = 0, -1, -2, -3, -4
 GATE_NAND, GATE_OR, GATE_AND, GATE_XOR, GATE_AND3 = 0, 1, 2, 3, 4
+FLAG_TORUS32 = 1          # mktfhe_params.reserved: Torus32 mode (unshifted 32-bit keys, gadget digits of up to 16 bits)
 
 # every symbol include/mktfhe_b200.h declares
 EXPORTS = (
@@ -121,9 +122,10 @@ class Context:
     GPUs, or "all", behind one handle (mktfhe_create_multi): keys are broadcast inside finalize_keys and the host-pointer
     batch calls shard their batch over the GPUs."""
 
-    def __init__(self, n, N, k, l, bgbit, t, basebit, device=0, devices=None, _borrowed=None):
+    def __init__(self, n, N, k, l, bgbit, t, basebit, device=0, devices=None, _borrowed=None, flags=0):
         L = lib()
-        self.prm = CParams(n, N, k, l, bgbit, t, basebit, 0)
+        self.prm = CParams(n, N, k, l, bgbit, t, basebit, flags)
+        self.flags = flags
         self.n, self.N, self.k, self.l, self.bgbit, self.t, self.basebit = n, N, k, l, bgbit, t, basebit
         self._owned = _borrowed is None
         if _borrowed is not None:                       # a replica of a multi-device context (owned by its parent)
@@ -163,7 +165,7 @@ class Context:
         """Replica i as a single-device Context (borrowed: valid while this context lives) for the *_dev calls."""
         r, d = C.c_void_p(), C.c_int()
         self._chk(lib().mktfhe_device_ctx(self.h, i, C.byref(r), C.byref(d)))
-        return Context(self.n, self.N, self.k, self.l, self.bgbit, self.t, self.basebit, device=d.value, _borrowed=r.value)
+        return Context(self.n, self.N, self.k, self.l, self.bgbit, self.t, self.basebit, device=d.value, _borrowed=r.value, flags=self.flags)
 
     def shard_bounds(self, G, i):
         lo, hi = C.c_size_t(), C.c_size_t()

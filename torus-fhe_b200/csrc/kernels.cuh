@@ -120,16 +120,18 @@ __host__ __device__ inline size_t bsk_elem_words(int l) { return (size_t)rns::NP
 // row is read with 16-byte loads -- followed by one all-zero row
 __host__ __device__ constexpr int ks_row_stride(int n) { return (n + 1 + 3) & ~3; }
 // per gate: Torus64 accumulator, packed digits, one padded tile per warp
-__host__ __device__ constexpr size_t gate_smem_bytes(int l, int wpg = WPG) {
-    return (size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)wpg * rns::TILE_WORDS * 4;
+__host__ __device__ constexpr size_t gate_smem_bytes(int l, int wpg = WPG, bool wide = false) {   // wide: 16-bit digit fields (Torus32 mode)
+    return (size_t)2 * N * 8 + (size_t)2 * l * N * (wide ? 2 : 1) + (size_t)wpg * rns::TILE_WORDS * 4;
 }
 // gates per CTA: as many as fit in the 227 KB of shared memory beside the twiddle tables (at most MAX_GPC)
-__host__ __device__ constexpr int gpc_for(int l) {
+__host__ __device__ constexpr int gpc_for(int l, bool wide = false) {
     int g = MAX_GPC;
-    while (g > 1 && (size_t)TW_SMEM_BYTES + (size_t)g * gate_smem_bytes(l) > 227 * 1024) g--;
+    while (g > 1 && (size_t)TW_SMEM_BYTES + (size_t)g * gate_smem_bytes(l, WPG, wide) > 227 * 1024) g--;
     return g;
 }
-__host__ __device__ constexpr size_t cta_smem_bytes(int l) { return (size_t)TW_SMEM_BYTES + (size_t)gpc_for(l) * gate_smem_bytes(l); }
+__host__ __device__ constexpr size_t cta_smem_bytes(int l, bool wide = false) {
+    return (size_t)TW_SMEM_BYTES + (size_t)gpc_for(l, wide) * gate_smem_bytes(l, WPG, wide);
+}
 
 struct GateLinear {   // temp = mu0 + cx*x + cy*y + cz*z   (3gen_mk_gates.jl:8-74)
     int32_t mu0, cx, cy, cz;
@@ -240,21 +242,23 @@ __device__ __forceinline__ void warp_ntt_inv(u32 (&x)[32], u32* tile, const uint
 
 // Phase 1 of a step: rotate-subtract and gadget-decompose (tgsw.jl:112-138); digits biased to [0, Bg) and packed 4 per word
 // in the order the NTT warps read them (dig: [2L][8][32] words).
-template <int L, bool MUX, int W = WPG>
+template <int L, bool MUX, int W = WPG, bool WIDE = false>
 __device__ __forceinline__ void decompose_phase(const u64* __restrict__ acc, u32* __restrict__ dig, int a, int bgbit, int gtid) {
     u64 off = 0;
 #pragma unroll
     for (int q = 1; q <= L; q++) off += ((u64)1 << (64 - q * bgbit)) << (bgbit - 1);   // tgsw.jl:24-30
     const u32 dmask = (1u << bgbit) - 1;
-    for (int task = gtid; task < 512; task += 32 * W) {
-        const int c = task >> 8, rh = (task >> 5) & 7, ln = task & 31;
+    // byte fields: 4 coefficients per word, dig [2L][8][32]; WIDE (gadget digits of 9..16 bits): 2 per word, dig [2L][16][32]
+    constexpr int PER = WIDE ? 2 : 4, ROWS = 32 / PER, FIELD = 32 / PER;
+    for (int task = gtid; task < 2 * ROWS * 32; task += 32 * W) {
+        const int c = task / (ROWS * 32), rh = (task >> 5) % ROWS, ln = task & 31;
         const u64* poly = acc + c * N;
         u32 packed[L];
 #pragma unroll
         for (int q = 0; q < L; q++) packed[q] = 0;
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const int i = 32 * (4 * rh + b) + ln;
+        for (int b = 0; b < PER; b++) {
+            const int i = 32 * (PER * rh + b) + ln;
             u64 t;
             if (MUX) {
                 const int idx = (i - a) & (2 * N - 1);        // (X^a * p)[i] = +-p[(i - a) mod 2N]
@@ -266,11 +270,11 @@ __device__ __forceinline__ void decompose_phase(const u64* __restrict__ acc, u32
             }
             t += off;
 #pragma unroll
-            for (int q = 0; q < L; q++) packed[q] |= ((u32)(t >> (64 - (q + 1) * bgbit)) & dmask) << (8 * b);
+            for (int q = 0; q < L; q++) packed[q] |= ((u32)(t >> (64 - (q + 1) * bgbit)) & dmask) << (FIELD * b);
         }
         const int src = 1 - c;   // src 0 = body = acc[1]
 #pragma unroll
-        for (int q = 0; q < L; q++) dig[((src * L + q) * 8 + rh) * 32 + ln] = packed[q];
+        for (int q = 0; q < L; q++) dig[((src * L + q) * ROWS + rh) * 32 + ln] = packed[q];
     }
 }
 
@@ -288,6 +292,17 @@ __device__ __forceinline__ void load_digits(u32 (&x)[32], const u32* __restrict_
     }
 }
 
+// the same for 16-bit digit fields (Torus32 mode, gadget digits of up to 16 bits): all 32 coefficients as residues digit + (p - Bg/2);
+// no table stage -- the transform runs the plain first stage
+__device__ __forceinline__ void load_digits_wide(u32 (&x)[32], const u32* __restrict__ dig, int s, int lane, u32 bias) {
+#pragma unroll
+    for (int rh = 0; rh < 16; rh++) {
+        const u32 word = dig[(s * 16 + rh) * 32 + lane];
+        x[2 * rh] = rns::alu_add(word & 0xFFFFu, bias);
+        x[2 * rh + 1] = rns::alu_add(word >> 16, bias);
+    }
+}
+
 // One external product (tgsw_extern_mul_3gen, tgsw_3gen.jl:102-113) on the accumulator held in shared memory, by the TPG
 // threads of one gate.
 //   MUX = true : acc += ExtProd(X^a * acc - acc, key)   (mk_mux_rotate_3gen, 3gen_mk_internals.jl:59-62)
@@ -296,7 +311,7 @@ __device__ __forceinline__ void load_digits(u32 (&x)[32], const u32* __restrict_
 // Garner's lift of both output polynomials by all threads of the gate, added to (MUX) or stored in the accumulator.  The residues
 // of output oo sit in coefficient order at tiles + oo * out_stride (+ off1 / off2 words for primes 1 / 2).  The lift is one long dependent
 // chain per coefficient: CRT_ILP coefficients are interleaved per thread.
-template <bool MUX, int W, int CRT_ILP>
+template <bool MUX, int W, int CRT_ILP, int SHIFT = 0>
 __device__ __forceinline__ void crt_phase(u64* __restrict__ acc, const u32* __restrict__ tiles, int out_stride, int off1, int off2, int gtid) {
     constexpr int T = 32 * W, CRT_ROUNDS = (2 * N + T * CRT_ILP - 1) / (T * CRT_ILP);
 #pragma unroll 1
@@ -316,7 +331,7 @@ __device__ __forceinline__ void crt_phase(u64* __restrict__ acc, const u32* __re
         for (int j = 0; j < CRT_ILP; j++) {
             const int idx = gtid + (round * CRT_ILP + j) * T;
             const u64 R = rns::crt_lift(r0[j], r1[j], r2[j], c_rns.crt);
-            if (idx < 2 * N) acc[idx] = old[j] + R;
+            if (idx < 2 * N) acc[idx] = old[j] + (SHIFT ? R << SHIFT : R);      // Torus32 mode: the product of unshifted keys goes to the top half
         }
     }
 }
@@ -346,15 +361,16 @@ __device__ __forceinline__ void crt_phase_lat(u64* __restrict__ acc, const u32* 
     }
 }
 
-template <int L, bool MUX, int W = WPG>
+template <int L, bool MUX, int W = WPG, bool WIDE = false>
 __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restrict__ dig, u32* __restrict__ tiles,
                                              const uint2_* __restrict__ twB, const u32* __restrict__ key, int a, int bgbit,
                                              int bar_id, int pbar_id, int gtid, bool ap = false, int cta_threads = 0) {
     static_assert(W == 3 || W == 6 || (L >= 2 && W == lat_wpg(L)), "warps per gate: 3, 6, or 6 l (latency launch)");
     constexpr bool LAT = L >= 2 && W == lat_wpg(L);
+    static_assert(!WIDE || (W == 6 && !LAT), "16-bit digit fields (Torus32 mode) are served by the six-warp shape only");
     const int gw = gtid >> 5, lane = gtid & 31;
     const int w = LAT ? gw / (2 * L) : W == 6 ? gw >> 1 : gw;          // prime of this warp
-    decompose_phase<L, MUX, W>(acc, dig, a, bgbit, gtid);
+    decompose_phase<L, MUX, W, WIDE>(acc, dig, a, bgbit, gtid);
     gate_barrier<W>(bar_id);
     const u32 p = c_rns.p[w], pinv = c_rns.pinv_neg[w];
     const u32 p4 = rns::keep_in_register(4 * p);
@@ -438,6 +454,10 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
         for (int i = 0; i < L; i++) {
             const int s_own = 2 * i + o, s_for = 2 * i + 1 - o;
             u32 x[32];
+            if constexpr (WIDE) {
+                load_digits_wide(x, dig, s_own, lane, bias);
+                warp_ntt_fwd(x, tile, twAf, twBf, p, lane);
+            } else {
             load_digits(x, dig, lut, s_own, lane, bias);
 #if MK_ANTIPHASE && MK_AP_SPLIT == 1
             {   // the forward transform written out, with the half-step boundary between its passes
@@ -458,6 +478,7 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
             if (ap && i == L - 1) asm volatile("bar.sync 15, %0;" ::"r"(cta_threads) : "memory");
 #endif
 #endif
+            }
 #pragma unroll
             for (int c = 0; c < 32; c++) tile[c * 32 + lane] = x[c];
             pair_barrier(pb);
@@ -497,7 +518,7 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
 #pragma unroll
         for (int r = 0; r < 32; r++) tile[32 * r + lane] = x[r];   // residues in coefficient order
         gate_barrier<W>(bar_id);
-        crt_phase<MUX, W, MK_CRT_ILP>(acc, tiles, rns::TILE_WORDS, 2 * rns::TILE_WORDS, 4 * rns::TILE_WORDS, gtid);   // warp (w, o) = 2 w + o
+        crt_phase<MUX, W, MK_CRT_ILP, WIDE ? 32 : 0>(acc, tiles, rns::TILE_WORDS, 2 * rns::TILE_WORDS, 4 * rns::TILE_WORDS, gtid);   // warp (w, o) = 2 w + o
         gate_barrier<W>(bar_id);
     } else {
         // ---- phase 2 (3 warps): per prime, forward NTT of each digit polynomial and multiply-accumulate with the key
@@ -665,7 +686,7 @@ __device__ __forceinline__ void fused_keyswitch(const u64* __restrict__ acc, u32
 }
 
 // GPC gates per CTA, WPG warps per gate.  Accumulators resident in shared memory for all k*n steps.
-template <int L, int GPC, int W>
+template <int L, int GPC, int W, bool WIDE = false>
 __device__ __forceinline__ void blind_rotate_body(const BlindRotateArgs& p) {
     constexpr int TPG = 32 * W;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -677,10 +698,10 @@ __device__ __forceinline__ void blind_rotate_body(const BlindRotateArgs& p) {
     const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot, pbar_id = 1 + GPC + slot * rns::NP;
     const int g = p.g0 + blockIdx.x * GPC + slot;
     if (g >= p.G) return;   // no CTA-wide barrier below this line
-    unsigned char* base = smem_raw + TW_SMEM_BYTES + (size_t)slot * gate_smem_bytes(L, W);
+    unsigned char* base = smem_raw + TW_SMEM_BYTES + (size_t)slot * gate_smem_bytes(L, W, WIDE);
     u64* acc = reinterpret_cast<u64*>(base);
     u32* dig = reinterpret_cast<u32*>(base + 2 * N * 8);
-    u32* tiles = dig + 2 * L * (N / 4);
+    u32* tiles = dig + 2 * L * (N / (WIDE ? 2 : 4));
     const int kn = p.k * p.n;
     // gate prologue (3gen_mk_gates.jl) + mod switch (3gen_mk_internals.jl:102-103); every thread of the gate computes
     // the same rotation amounts from broadcast loads
@@ -748,7 +769,7 @@ __device__ __forceinline__ void blind_rotate_body(const BlindRotateArgs& p) {
 #elif MK_ANTIPHASE
         extprod_step<L, true, W>(acc, dig, tiles, twB, p.bsk + (size_t)it * estride, a, p.bgbit, bar_id, pbar_id, gtid, ap, GPC * TPG);
 #else
-        extprod_step<L, true, W>(acc, dig, tiles, twB, p.bsk + (size_t)it * estride, a, p.bgbit, bar_id, pbar_id, gtid);
+        extprod_step<L, true, W, WIDE>(acc, dig, tiles, twB, p.bsk + (size_t)it * estride, a, p.bgbit, bar_id, pbar_id, gtid);
 #endif
     }
 #if MK_ANTIPHASE
@@ -778,6 +799,13 @@ __device__ __forceinline__ void blind_rotate_body(const BlindRotateArgs& p) {
 template <int L, int GPC, int W = WPG>
 __global__ void __maxnreg__(MK_MAXNREG) blind_rotate_kernel(BlindRotateArgs p) { blind_rotate_body<L, GPC, W>(p); }
 
+// Torus32 mode (mktfhe_params.flags & MKTFHE_FLAG_TORUS32): gadget digits of up to 16 bits in 16-bit fields, keys loaded UNSHIFTED
+// (32-bit signed values) and every external product added as R << 32 -- the exact integer R then stays below 2^59 whatever the
+// gadget base, where the v << 32 embedding of the default kernels would leave the CRT range for Bg > 2^8.  Serves the reference's
+// tfhe_parameters_80 (Bg = 2^10, api.jl:76-91).  Separate entry points: the default kernels' machine code does not change.
+template <int L, int GPC>
+__global__ void __maxnreg__(MK_MAXNREG) blind_rotate_t32_kernel(BlindRotateArgs p) { blind_rotate_body<L, GPC, WPG, true>(p); }
+
 // latency launch: one gate per CTA, 6 l warps (168 registers at l = 2, 112 at l = 3, 80 at l = 4: a latency warp keeps no wide accumulators)
 template <int L>
 __global__ void __launch_bounds__(32 * lat_wpg(L), 1) blind_rotate_lat_kernel(BlindRotateArgs p) { blind_rotate_body<L, 1, lat_wpg(L)>(p); }
@@ -801,6 +829,27 @@ __global__ void __maxnreg__(MK_MAXNREG) extprod_kernel(int G, const u32* bsk, co
     for (int i = gtid; i < 2 * N; i += TPG) acc[i] = (u64)acc_in[(size_t)g * 2 * N + i];
     gate_barrier(bar_id);
     extprod_step<L, false>(acc, dig, tiles, twB, bsk + (size_t)elem[g] * bsk_elem_words(L), 0, bgbit, bar_id, pbar_id, gtid);
+    for (int i = gtid; i < 2 * N; i += TPG) acc_out[(size_t)g * 2 * N + i] = (int64_t)acc[i];
+}
+
+// the same in Torus32 mode: acc_in / acc_out hold Torus32 values in the TOP half of their words (v << 32)
+template <int L, int GPC>
+__global__ void __maxnreg__(MK_MAXNREG) extprod_t32_kernel(int G, const u32* bsk, const uint2_* twB_g, int bgbit, const int32_t* elem,
+                                                            const int64_t* acc_in, int64_t* acc_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2_* twB = reinterpret_cast<uint2_*>(smem_raw);
+    stage_twiddles(twB, twB_g);
+    __syncthreads();
+    const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot, pbar_id = 1 + GPC + slot * rns::NP;
+    const int g = blockIdx.x * GPC + slot;
+    if (g >= G) return;
+    unsigned char* base = smem_raw + TW_SMEM_BYTES + (size_t)slot * gate_smem_bytes(L, WPG, true);
+    u64* acc = reinterpret_cast<u64*>(base);
+    u32* dig = reinterpret_cast<u32*>(base + 2 * N * 8);
+    u32* tiles = dig + 2 * L * (N / 2);
+    for (int i = gtid; i < 2 * N; i += TPG) acc[i] = (u64)acc_in[(size_t)g * 2 * N + i];
+    gate_barrier(bar_id);
+    extprod_step<L, false, WPG, true>(acc, dig, tiles, twB, bsk + (size_t)elem[g] * bsk_elem_words(L), 0, bgbit, bar_id, pbar_id, gtid);
     for (int i = gtid; i < 2 * N; i += TPG) acc_out[(size_t)g * 2 * N + i] = (int64_t)acc[i];
 }
 

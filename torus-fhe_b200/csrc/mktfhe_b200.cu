@@ -49,6 +49,7 @@ struct mktfhe_ctx {
     int num_sms = 0;
     bool split_tail = true;      // MKTFHE_B200_SPLIT_TAIL=0: no separate one-gate-per-CTA launch for the tail of a large batch (A/B)
     bool latency_kernel = true;  // MKTFHE_B200_LATENCY=0 turns the 12-warp small-batch launch off (A/B)
+    bool t32 = false;            // Torus32 mode (MKTFHE_FLAG_TORUS32): blind_rotate_t32_kernel / extprod_t32_kernel
     bool two_k16 = true;         // N = 2048: the sixteen-warp kernel (MKTFHE_B200_2K=8 selects the first, eight-warp kernel: A/B runs)
     bool fuse_ks = true;         // key switch as the epilogue of the blind-rotate kernel (MKTFHE_B200_FUSE_KS=0 disables: A/B runs)
     std::vector<char> bsk_loaded, ksk_loaded;
@@ -102,6 +103,7 @@ int check_params(const mktfhe_params* p) {
     if (p->bgbit < 1 || p->bgbit > 30) return fail(nullptr, MKTFHE_EINVAL, "unsupported gsw_log2_base=%d", p->bgbit);
     if (p->basebit < 1 || p->basebit > 16) return fail(nullptr, MKTFHE_EINVAL, "unsupported ks_log2_base=%d (1..16)", p->basebit);
     if (p->N == mk2k::N) {
+        if (p->reserved) return fail(nullptr, MKTFHE_EINVAL, "flags are not defined for N=2048");
         // N = 2048 sets (mk_api.jl:214-310): l = 1 or 2 with a wide gadget base, four-prime exact product (kernels2k.cuh)
         if (p->l < 1 || p->l > 2) return fail(nullptr, MKTFHE_EINVAL, "N=2048 is supported with gsw_decomp_length l=1 or 2 (got %d)", p->l);
         if (p->bgbit < 1 || p->bgbit > 27) return fail(nullptr, MKTFHE_EINVAL, "N=2048: unsupported gsw_log2_base=%d (1..27)", p->bgbit);
@@ -113,6 +115,16 @@ int check_params(const mktfhe_params* p) {
         return MKTFHE_OK;
     }
     if (p->N != mk::N) return fail(nullptr, MKTFHE_EINVAL, "unsupported N=%d (1024 or 2048)", p->N);
+    if (p->reserved & ~MKTFHE_FLAG_TORUS32) return fail(nullptr, MKTFHE_EINVAL, "unknown flags 0x%x", p->reserved);
+    if (p->reserved & MKTFHE_FLAG_TORUS32) {
+        // Torus32 mode: unshifted 32-bit keys, 16-bit digit fields, products added as R << 32: |R| <= 2l * N * 2^(bgbit-1) * 2^31 < 2^59
+        if (p->l < 2 || p->l > 3) return fail(nullptr, MKTFHE_EINVAL, "Torus32 mode is built for gsw_decomp_length l=2 or 3 (got %d)", p->l);
+        if (p->bgbit < 1 || p->bgbit > 16 || p->l * p->bgbit > 32) return fail(nullptr, MKTFHE_EINVAL, "Torus32 mode: need bgbit <= 16 and l*bgbit <= 32");
+        if (p->k < 1 || p->n < 1 || (long long)p->n * p->k > 8192) return fail(nullptr, MKTFHE_EINVAL, "need 1 <= n*k <= 8192");
+        if (p->n + 1 > mk::KS_THREADS * mk::KS_MAXCOLS) return fail(nullptr, MKTFHE_EINVAL, "n too large for the key-switch kernel");
+        if (p->t < 1 || p->t * p->basebit > 31) return fail(nullptr, MKTFHE_EINVAL, "need t*basebit <= 31");
+        return MKTFHE_OK;
+    }
     if (p->l < 1 || p->l > 4) return fail(nullptr, MKTFHE_EINVAL, "unsupported gsw_decomp_length l=%d (1..4)", p->l);
     if (p->bgbit < 1 || p->l * p->bgbit > 32) return fail(nullptr, MKTFHE_EINVAL, "unsupported l*bgbit=%d (<=32)", p->l * p->bgbit);
     if ((1 << p->bgbit) > mk::LUT_BYTES_MAX)
@@ -129,7 +141,7 @@ int check_params(const mktfhe_params* p) {
 #ifndef MK_EXTRA_SMEM
 #define MK_EXTRA_SMEM 0     // diagnostic: unused shared memory to move the L1 carve-out
 #endif
-size_t br_smem_bytes(const mktfhe_ctx* c) { return mk::cta_smem_bytes(c->prm.l) + MK_EXTRA_SMEM; }
+size_t br_smem_bytes(const mktfhe_ctx* c) { return mk::cta_smem_bytes(c->prm.l, c->t32) + MK_EXTRA_SMEM; }
 
 // (L, GPC) instantiations: mk::gpc_for(l) gates per CTA
 #define MK_DISPATCH_L(c, KERNEL, ...)                                      \
@@ -149,6 +161,16 @@ int set_attrs(mktfhe_ctx* c) {
         return MKTFHE_OK;
     }
     const int sm = (int)br_smem_bytes(c);
+    if (c->t32) {
+        if (c->prm.l == 2) {
+            CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_t32_kernel<2, mk::gpc_for(2, true)>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+            CU_TRY(c, cudaFuncSetAttribute(mk::extprod_t32_kernel<2, mk::gpc_for(2, true)>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        } else {
+            CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_t32_kernel<3, mk::gpc_for(3, true)>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+            CU_TRY(c, cudaFuncSetAttribute(mk::extprod_t32_kernel<3, mk::gpc_for(3, true)>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        }
+        return MKTFHE_OK;
+    }
 #define SET_ATTR(L, GPC, dummy)                                                                                                    \
     CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));             \
     if (getenv("MKTFHE_B200_CARVEOUT"))                                                                                            \
@@ -192,6 +214,16 @@ void launch_one_gate_per_cta(mktfhe_ctx* c, mk::BlindRotateArgs a, size_t g0, si
 // leaves after its full waves -- of at most one gate per SM runs one gate per CTA instead, on the latency kernel (6 l warps per gate): at
 // l = 2 a gate alone on an SM finishes in 7.3 ms against 12.3 ms for two gates sharing it.  Bit-identical results.
 void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G, cudaStream_t st) {
+    if (c->t32) {   // Torus32 mode: one launch shape (two six-warp gates per CTA)
+        mk::BlindRotateArgs h = a;
+        h.g0 = 0; h.G = (int)G;
+        const size_t sm = br_smem_bytes(c);
+        const unsigned grid = (unsigned)((G + c->gpc - 1) / c->gpc);
+        if (c->prm.l == 2) mk::blind_rotate_t32_kernel<2, mk::gpc_for(2, true)><<<grid, c->gpc * mk::TPG, sm, st>>>(h);
+        else mk::blind_rotate_t32_kernel<3, mk::gpc_for(3, true)><<<grid, c->gpc * mk::TPG, sm, st>>>(h);
+        c->launches++;
+        return;
+    }
     const size_t wave = (size_t)c->gpc * (size_t)c->num_sms;
     size_t tail = c->gpc > 1 ? G % wave : 0;
     // the tail of a larger batch is split off only at l = 2, where it was measured to pay on two workloads; at l = 3 the split lost 1.2 %
@@ -460,7 +492,8 @@ int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
     const int B1 = (1 << params->basebit) - 1;
     const bool big = params->N == mk2k::N;
     c->bsk_bytes = (size_t)params->k * params->n * (big ? mk2k::bsk_elem_words(params->l) : mk::bsk_elem_words(params->l)) * sizeof(u32);
-    c->gpc = big ? 1 : mk::gpc_for(params->l);
+    c->t32 = !big && (params->reserved & MKTFHE_FLAG_TORUS32);
+    c->gpc = big ? 1 : mk::gpc_for(params->l, c->t32);
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
     if (const char* e = getenv("MKTFHE_B200_LATENCY")) c->latency_kernel = atoi(e) != 0;
     if (const char* e = getenv("MKTFHE_B200_SPLIT_TAIL")) c->split_tail = atoi(e) != 0;
@@ -785,11 +818,20 @@ static int mktfhe_extprod_batch_1(mktfhe_ctx* c, size_t G, const int32_t* elem, 
     if ((rc = stage_in(c, c->elem, elem, G * 4)) || (rc = stage_in(c, c->accin, acc_in, accbytes)) || (rc = reserve(c, c->accout, accbytes))) return rc;
     const size_t sm = br_smem_bytes(c);
     const unsigned grid = (unsigned)((G + c->gpc - 1) / c->gpc);
+    if (c->t32) {
+        if (c->prm.l == 2)
+            mk::extprod_t32_kernel<2, mk::gpc_for(2, true)><<<grid, c->gpc * mk::TPG, sm, c->stream>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, (const int32_t*)c->elem.p,
+                                                                                                       (const int64_t*)c->accin.p, (int64_t*)c->accout.p);
+        else
+            mk::extprod_t32_kernel<3, mk::gpc_for(3, true)><<<grid, c->gpc * mk::TPG, sm, c->stream>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, (const int32_t*)c->elem.p,
+                                                                                                       (const int64_t*)c->accin.p, (int64_t*)c->accout.p);
+    } else {
 #define LAUNCH_EP(L, GPC, dummy)                                                                                          \
     mk::extprod_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, c->stream>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, (const int32_t*)c->elem.p, \
                                                                        (const int64_t*)c->accin.p, (int64_t*)c->accout.p)
     MK_DISPATCH_L(c, LAUNCH_EP, 0)
 #undef LAUNCH_EP
+    }
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     CU_TRY(c, cudaMemcpyAsync(acc_out, c->accout.p, accbytes, cudaMemcpyDeviceToHost, c->stream));

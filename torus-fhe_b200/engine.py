@@ -22,13 +22,13 @@ class Engine:
     """Owns a `_cabi.Context`.  Keys come either from the host (`load_keys`) or, on
     non-root ranks, from rank 0 through `broadcast_keys`."""
 
-    def __init__(self, params, device=None, devices=None):
+    def __init__(self, params, device=None, devices=None, flags=0):
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
         self.params = params
         self.ctx = _cabi.Context(params.lwe_size, params.rlwe_polynomial_degree, params.max_parties,
                                  params.gsw_decomp_length, params.gsw_log2_base,
-                                 params.ks_decomp_length, params.ks_log2_base, device=device, devices=devices)
+                                 params.ks_decomp_length, params.ks_log2_base, device=device, devices=devices, flags=flags)
         self.device = self.ctx.device          # first (or only) GPU
         self.devices = list(self.ctx.devices)
         self.ready = False

@@ -16,8 +16,10 @@ How the scheme maps onto the engine (no new kernel):
 Every bootstrapped gate is one `mktfhe_affine_bootstrap_batch` call (linear prologue fused into the kernel); gate_mux follows
 gates.jl:166-177: two bootstraps without key switch, the OR in the extracted domain, one key switch.
 
-Supported: parameter sets with N = 1024, l*Bgbit <= 32, Bgbit <= 8 (tfhe_parameters_128: l = 3, Bg = 2^7).  tfhe_parameters_80 uses
-Bg = 2^10 (10-bit digits; the N = 1024 kernels pack digits in bytes): `mktfhe_create` rejects it (MKTFHE_EINVAL).  In the fork
+Supported: parameter sets with N = 1024 and l*Bgbit <= 32.  Bgbit <= 8 (tfhe_parameters_128: l = 3, Bg = 2^7) runs on the default
+kernels as described above.  tfhe_parameters_80 (l = 2, Bg = 2^10) has 10-bit digits and, embedded as v << 32, would leave the exact
+range of the three-prime CRT (2l N Bg/2 2^63 = 2^84): it runs in the library's Torus32 mode (MKTFHE_FLAG_TORUS32: 16-bit digit
+fields, keys loaded unshifted, every external product added as R << 32 -- kernels.cuh, blind_rotate_t32_kernel).  In the fork
 neither constructor runs as written (api.jl:76-113 pass 11 values to the 12-field struct after `rlwe_is32` was added, :50-67);
 here `rlwe_is32 = true` is filled in.  Names, arguments and behaviour follow the reference; samples may carry leading batch
 dimensions (a scalar call is a batch of one).
@@ -26,6 +28,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
+from . import _cabi
 from .engine import Engine
 from .tfhe3gen import (KeyswitchKey, KeyswitchParameters, LweKey, LweParams, RLweKey, RLweParams, SchemeParameters_3gen, TGswParams, dtot32,
                        encode_message, negacyclic_mul, rand_uniform_torus32)
@@ -49,7 +52,7 @@ class SchemeParameters:
 
 
 def tfhe_parameters_80(rlwe_mask_size=1):
-    """api.jl:76-91 (CGGI16, ~80 bits): Bg = 2^10 -- defined for completeness, not runnable on the N = 1024 kernels."""
+    """api.jl:76-91 (CGGI16, ~80 bits; the reference's default): Bg = 2^10, served by the library's Torus32 mode."""
     return SchemeParameters(500, 1 / 2 ** 15 * np.sqrt(2 / np.pi), 1024, rlwe_mask_size, True, 2, 10, 9e-9 * np.sqrt(2 / np.pi), 8, 2,
                             1 / 2 ** 15 * np.sqrt(2 / np.pi), 1)
 
@@ -161,9 +164,10 @@ class BootstrapKey:
             s[:, :, 1, 1, 0] += mg
         self.samples = s
 
-    def engine_parts(self):
-        """int64 [n][4][l][N] in the engine's part order, every Torus32 value carried as v << 32 (module docstring)."""
-        s = self.samples.astype(np.int64) << 32
+    def engine_parts(self, shift=32):
+        """int64 [n][4][l][N] in the engine's part order; every Torus32 value carried as v << 32 for the default kernels (module
+        docstring), or unshifted (shift = 0) for the library's Torus32 mode (MKTFHE_FLAG_TORUS32: gadget bases above 2^8)."""
+        s = self.samples.astype(np.int64) << shift
         return np.ascontiguousarray(np.stack([s[:, :, 1, 1], s[:, :, 0, 1], s[:, :, 0, 0], s[:, :, 1, 0]], axis=1))
 
 
@@ -178,10 +182,9 @@ class CloudKey:   # api.jl:212-228
 
 
 def make_key_pair(rng, params=None):
-    """api.jl:237-245.  The reference's default is tfhe_parameters_80, which these kernels do not serve (module docstring):
-    the default here is tfhe_parameters_128."""
+    """api.jl:237-245 (default parameters: tfhe_parameters_80, as in the reference)."""
     if params is None:
-        params = tfhe_parameters_128()
+        params = tfhe_parameters_80()
     sk = SecretKey(rng, params)
     return sk, CloudKey(rng, sk)
 
@@ -206,8 +209,11 @@ def engine_for(ck, device=None, devices=None):
             raise NotImplementedError("single-key sets are Torus32 with rlwe_mask_size = 1 (api.jl:76-113)")
         sp = SchemeParameters_3gen(p.lwe_size, p.lwe_noise_stddev, p.rlwe_polynomial_degree, 1, False, p.bs_decomp_length, p.bs_log2_base,
                                    p.bs_noise_stddev, p.ks_decomp_length, p.ks_log2_base, p.ks_noise_stddev, 1)
-        eng = Engine(sp, device=device, devices=devices)
-        eng.load_keys([ck.bootstrap_key.engine_parts()], [ck.keyswitch_key.key])
+        # gadget digits of up to 8 bits ride the default kernels (keys << 32, table-driven first transform stage); wider ones
+        # (tfhe_parameters_80: Bg = 2^10) need the library's Torus32 mode: unshifted keys, 16-bit digit fields
+        t32 = p.bs_log2_base > 8
+        eng = Engine(sp, device=device, devices=devices, flags=_cabi.FLAG_TORUS32 if t32 else 0)
+        eng.load_keys([ck.bootstrap_key.engine_parts(0 if t32 else 32)], [ck.keyswitch_key.key])
         ck._engine = eng
     return ck._engine
 
