@@ -180,6 +180,12 @@ int mktfhe_gate_batch_mixed_dev(mktfhe_ctx *ctx, size_t G, const int32_t *gate_i
  * G accumulators: acc = int64 [G][2][N] with [0] = mask (accum.a[1]) and
  * [1] = body (accum.a[2]); elem[g] = party*n + j. */
 int mktfhe_extprod_batch(mktfhe_ctx *ctx, size_t G, const int32_t *elem, const int64_t *acc_in, int64_t *acc_out);
+/* the same on device pointers (elem included), asynchronous on `stream`: the building block of the CCS scheme's hybrid product
+ * (UniProduct, mk_internals.jl:471-535), which torus-fhe_b200/tfhe_ccs.py composes from 2 (k+1) of these per blind-rotate step */
+int mktfhe_extprod_batch_dev(mktfhe_ctx *ctx, size_t G, const int32_t *elem, const int64_t *acc_in, int64_t *acc_out, void *stream);
+/* mk_keyswitch(ks, sample::MKLweSample) of the CCS scheme (mk_internals.jl:703-719): the extracted sample has one mask per party,
+ * ext_a = int32 [G][k][N], ext_b = int32 [G]; party p's mask goes through party p's key. */
+int mktfhe_mk_keyswitch_batch(mktfhe_ctx *ctx, size_t G, const int32_t *ext_a, const int32_t *ext_b, int32_t *a_out, int32_t *b_out);
 /* mk_bootstrap_wo_keyswitch_3gen (3gen_mk_internals.jl:99-109): returns the
  * extracted sample ext = int32 [G][N+1] (a'[0..N-1], b') and, if acc_out is not
  * NULL, the final accumulator int64 [G][2][N]. */

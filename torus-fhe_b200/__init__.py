@@ -9,6 +9,7 @@ Animesh005/Torus-FHE (3-gen-mk-tfhe/).  Import as `torus_fhe_b200` (the root shi
   interchange.py binary key / ciphertext files a Julia host can write (fixtures from the real reference)
   workloads.py the reference's VolumeMatching workload and the encrypted convolution layer on batched circuit instances
   tfhe1.py     single-key TFHE (api.jl, gates.jl, bootstrap.jl) through the same engine with one party (first slice)
+  tfhe_ccs.py  the CCS multi-key scheme (mk_gate_nand / mk_bootstrap) composed from batched external products of the same kernels
   csrc/        hand-written sm_100a kernels and the C ABI implementation
 """
 from . import _cabi
@@ -21,3 +22,4 @@ from .circuits import (gate_level, mk_int_add_3gen_gpu, mk_add_3gen, mk_add_3gen
 from .workloads import VolumeMatch, volume_match_plain, enc_conv2d, conv2d_plain, conv2d_gate_count, conv2d_output_shape
 from . import interchange
 from . import tfhe1
+from . import tfhe_ccs

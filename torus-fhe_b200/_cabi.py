@@ -23,7 +23,7 @@ EXPORTS = (
     "mktfhe_load_bsk", "mktfhe_load_ksk", "mktfhe_generate_ksk", "mktfhe_finalize_keys", "mktfhe_key_buffers", "mktfhe_mark_keys_received",
     "mktfhe_bootstrap_batch", "mktfhe_gate_batch", "mktfhe_bootstrap_batch_dev", "mktfhe_gate_batch_dev",
     "mktfhe_gate_batch_mixed", "mktfhe_gate_batch_mixed_dev", "mktfhe_affine_bootstrap_batch", "mktfhe_affine_bootstrap_batch_dev",
-    "mktfhe_extprod_batch", "mktfhe_blind_rotate_batch", "mktfhe_keyswitch_batch", "mktfhe_negacyclic_mul_batch",
+    "mktfhe_extprod_batch", "mktfhe_extprod_batch_dev", "mktfhe_mk_keyswitch_batch", "mktfhe_blind_rotate_batch", "mktfhe_keyswitch_batch", "mktfhe_negacyclic_mul_batch",
     "mktfhe_launch_count", "mktfhe_last_kernel_ms", "mktfhe_algorithmic_bytes", "mktfhe_build_id", "mktfhe_describe",
 )
 
@@ -90,6 +90,8 @@ def lib():
         "mktfhe_gate_batch_mixed": (C.c_int, [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "mktfhe_gate_batch_mixed_dev": (C.c_int, [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "mktfhe_extprod_batch": (C.c_int, [vp, sz, vp, vp, vp]),
+        "mktfhe_extprod_batch_dev": (C.c_int, [vp, sz, vp, vp, vp, vp]),
+        "mktfhe_mk_keyswitch_batch": (C.c_int, [vp, sz, vp, vp, vp, vp]),
         "mktfhe_blind_rotate_batch": (C.c_int, [vp, i64, sz, vp, vp, vp, vp]),
         "mktfhe_keyswitch_batch": (C.c_int, [vp, sz, vp, vp, vp]),
         "mktfhe_negacyclic_mul_batch": (C.c_int, [vp, sz, vp, vp, vp]),
@@ -306,6 +308,20 @@ class Context:
         out = np.empty((G, 2, self.N), np.int64)
         self._chk(lib().mktfhe_extprod_batch(self.h, G, _p(elem), _p(acc), _p(out)))
         return out
+
+    def extprod_batch_dev(self, G, elem, acc_in, acc_out, stream=0):
+        """Device pointers (ints): acc_out[g] = ExtProd(acc_in[g], element elem[g]); asynchronous on `stream`."""
+        self._chk(lib().mktfhe_extprod_batch_dev(self.h, G, elem, acc_in, acc_out, stream or None))
+
+    def mk_keyswitch_batch(self, ext_a, ext_b):
+        """CCS key switch: ext_a int32 [G][k][N] (one mask per party), ext_b int32 [G]."""
+        ext_a, ext_b = _c(ext_a, np.int32), _c(ext_b, np.int32).reshape(-1)
+        G = ext_b.size
+        if ext_a.size != G * self.k * self.N:
+            raise ValueError("ext_a must be int32 [G][k][N]")
+        oa, ob = np.empty((G, self.k, self.n), np.int32), np.empty(G, np.int32)
+        self._chk(lib().mktfhe_mk_keyswitch_batch(self.h, G, _p(ext_a), _p(ext_b), _p(oa), _p(ob)))
+        return oa, ob
 
     def blind_rotate_batch(self, mu, a, b, want_acc=False):
         a, b = self._ab(a, b)

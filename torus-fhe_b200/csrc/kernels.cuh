@@ -956,6 +956,51 @@ __global__ void __launch_bounds__(KS_THREADS) keyswitch_kernel(int n, int k, int
     if (tid == n % KS_THREADS) ob[g] = (int32_t)((uint32_t)e[N] + bsum);   // thread owning column n
 }
 
+// Multi-key key switch of the CCS scheme (mk_keyswitch, mk_internals.jl:703-719): the extracted sample carries ONE MASK PER PARTY
+// (ext_a [G][k][N]; the 3gen extraction has a single mask), party p's mask goes through party p's key: a_out[:, p] = keyswitch(ks[p],
+// (a[:, p], 0)).a, b_out = b + sum_p keyswitch(...).b.  Same row layout and thread mapping as keyswitch_kernel.
+__global__ void __launch_bounds__(KS_THREADS) mk_keyswitch_kernel(int n, int k, int t, int basebit, const int32_t* __restrict__ ksk,
+                                                                   const int32_t* __restrict__ ext_a, const int32_t* __restrict__ ext_b,
+                                                                   int32_t* __restrict__ oa, int32_t* __restrict__ ob) {
+    __shared__ uint32_t s_a[N];
+    const int g = blockIdx.x, tid = threadIdx.x;
+    const int B1 = (1 << basebit) - 1, row = n + 1, stride = ks_row_stride(n);
+    const uint32_t prec_offset = 1u << (32 - (1 + basebit * t));   // keyswitch.jl:58
+    const int ncols = (row + KS_THREADS - 1) / KS_THREADS;
+    uint32_t bsum = 0;
+    for (int p = 0; p < k; p++) {
+        __syncthreads();
+        const int32_t* e = ext_a + ((size_t)g * k + p) * N;
+        for (int i = tid; i < N; i += KS_THREADS) s_a[i] = (uint32_t)e[i] + prec_offset;
+        __syncthreads();
+        uint32_t acc[KS_MAXCOLS];
+#pragma unroll
+        for (int c = 0; c < KS_MAXCOLS; c++) acc[c] = 0;
+        const int32_t* rows = ksk + (size_t)p * N * t * B1 * stride;
+        for (int i = 0; i < N; i++) {
+            const uint32_t ai = s_a[i];
+            for (int j = 1; j <= t; j++) {
+                const uint32_t d = (ai >> (32 - j * basebit)) & (uint32_t)B1;
+                if (d != 0) {
+                    const int32_t* r = rows + (((size_t)i * t + (j - 1)) * B1 + (d - 1)) * stride;
+#pragma unroll
+                    for (int c = 0; c < KS_MAXCOLS; c++) {
+                        const int col = tid + c * KS_THREADS;
+                        if (c < ncols && col < row) acc[c] -= (uint32_t)__ldg(r + col);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < KS_MAXCOLS; c++) {
+            const int col = tid + c * KS_THREADS;
+            if (c < ncols && col < n) oa[((size_t)g * k + p) * n + col] = (int32_t)acc[c];
+            if (c < ncols && col == n) bsum += acc[c];
+        }
+    }
+    if (tid == n % KS_THREADS) ob[g] = (int32_t)((uint32_t)ext_b[g] + bsum);
+}
+
 // ---- key generation on the device: the key-switching key (keyswitch.jl:14-41) -------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11), counter-based: row and column of a key word are its counter, so the key is a pure function
 // of (seed, party) and no generator state is kept.

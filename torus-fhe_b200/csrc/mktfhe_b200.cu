@@ -967,6 +967,52 @@ int mktfhe_extprod_batch(mktfhe_ctx* c, size_t G, const int32_t* elem, const int
     });
 }
 
+int mktfhe_extprod_batch_dev(mktfhe_ctx* c, size_t G, const int32_t* elem, const int64_t* acc_in, int64_t* acc_out, void* stream) {
+    if (!c) return MKTFHE_EINVAL;
+    if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
+    if (G == 0) return MKTFHE_OK;
+    if (!elem || !acc_in || !acc_out) return fail(c, MKTFHE_EINVAL, "extprod_batch_dev: NULL buffer");
+    if (c->prm.N == mk2k::N) return fail(c, MKTFHE_EINVAL, "extprod_batch: the single-external-product hook exists for N=1024 only");
+    if (G > 0x7fffffffu) return fail(c, MKTFHE_EINVAL, "batch too large");
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const size_t sm = br_smem_bytes(c);
+    const unsigned grid = (unsigned)((G + c->gpc - 1) / c->gpc);
+    if (c->t32) {
+        if (c->prm.l == 2) mk::extprod_t32_kernel<2, mk::gpc_for(2, true)><<<grid, c->gpc * mk::TPG, sm, st>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, elem, acc_in, acc_out);
+        else mk::extprod_t32_kernel<3, mk::gpc_for(3, true)><<<grid, c->gpc * mk::TPG, sm, st>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, elem, acc_in, acc_out);
+    } else {
+#define LAUNCH_EPD(L, GPC, dummy) mk::extprod_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, st>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, elem, acc_in, acc_out)
+        MK_DISPATCH_L(c, LAUNCH_EPD, 0)
+#undef LAUNCH_EPD
+    }
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    return MKTFHE_OK;
+}
+
+int mktfhe_mk_keyswitch_batch(mktfhe_ctx* c, size_t G, const int32_t* ext_a, const int32_t* ext_b, int32_t* a_out, int32_t* b_out) {
+    if (!c) return MKTFHE_EINVAL;
+    if (!c->kids.empty()) return fail(c, MKTFHE_EINVAL, "mk_keyswitch_batch runs on a single-device context");
+    if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
+    if (G == 0) return MKTFHE_OK;
+    if (!ext_a || !ext_b || !a_out || !b_out) return fail(c, MKTFHE_EINVAL, "mk_keyswitch_batch: NULL buffer");
+    if (c->prm.N != mk::N) return fail(c, MKTFHE_EINVAL, "mk_keyswitch_batch exists for N=1024 only");
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t kn = (size_t)c->prm.n * c->prm.k, abytes = G * kn * 4, bbytes = G * 4, eabytes = G * (size_t)c->prm.k * c->prm.N * 4;
+    int rc;
+    if ((rc = stage_in(c, c->ext, ext_a, eabytes)) || (rc = stage_in(c, c->in[1], ext_b, bbytes)) || (rc = reserve(c, c->oa, abytes)) || (rc = reserve(c, c->ob, bbytes)))
+        return rc;
+    mk::mk_keyswitch_kernel<<<(unsigned)G, mk::KS_THREADS, 0, c->stream>>>(c->prm.n, c->prm.k, c->prm.t, c->prm.basebit, c->d_ksk, (const int32_t*)c->ext.p,
+                                                                           (const int32_t*)c->in[1].p, (int32_t*)c->oa.p, (int32_t*)c->ob.p);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(a_out, c->oa.p, abytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(b_out, c->ob.p, bbytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return MKTFHE_OK;
+}
+
 int mktfhe_negacyclic_mul_batch(mktfhe_ctx* c, size_t G, const int64_t* a, const int64_t* b, int64_t* out) {
     if (!c) return MKTFHE_EINVAL;
     if (c->kids.empty()) return mktfhe_negacyclic_mul_batch_1(c, G, a, b, out);
