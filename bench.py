@@ -475,6 +475,47 @@ def run_single_key(args):
     return 0
 
 
+def run_ccs(args):
+    """SURVEY 8(f) rank 4, second slice: the CCS multi-key scheme (mk_gate_nand, mk_gates.jl:7-13, on mktfhe_parameters_2party, mk_api.jl:4-10)
+    composed from batched external products of the same kernels (torus-fhe_b200/tfhe_ccs.py).  One step = G NAND gates from host buffers
+    to host buffers (the accumulators live in HBM during the blind rotation)."""
+    import torch
+    import torus_fhe_b200 as T
+    TC = T.tfhe_ccs
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    torch.cuda.set_device(0)
+    rng = np.random.default_rng(KEY_SEED)
+    params = TC.mktfhe_parameters_2party
+    t0 = time.perf_counter()
+    secret_keys = [TC.SecretKey(rng, params) for _ in range(2)]
+    shared_key = TC.SharedKey(rng, params)
+    ck = TC.MKCloudKey([TC.CloudKeyPart(rng, sk, shared_key) for sk in secret_keys], shared_key)
+    t_keys = time.perf_counter() - t0
+    G = args.gates
+    bits = rng.integers(0, 2, (2, G)).astype(bool)
+    x, y = TC.mk_encrypt(rng, secret_keys, bits[0]), TC.mk_encrypt(rng, secret_keys, bits[1])
+    TC.mk_gate_nand(ck, x[:64], y[:64])                          # warm-up
+    sampler = ClockSampler(0); sampler.start()
+    l0 = ck.products.ctx.launch_count() + ck.switch.ctx.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = TC.mk_gate_nand(ck, x, y)
+    dt = (time.perf_counter() - t0) / args.steps
+    launches = (ck.products.ctx.launch_count() + ck.switch.ctx.launch_count() - l0) // args.steps
+    clocks = sampler.stop()
+    ok = bool(np.array_equal(TC.mk_decrypt(secret_keys, out), ~(bits[0] & bits[1])))
+    print(json.dumps({"metric": "bootstrapped CCS 2-party MK NAND gates/sec (mktfhe_parameters_2party)", "value": G / dt, "unit": UNIT, "n_gpus": 1,
+                      "steps": args.steps, "ms_per_step": 1e3 * dt, "higher_is_better": True, "vs_baseline": None,
+                      "dtype": "u32 RNS (three 28-bit-prime NTTs + CRT), Torus32 mode (9-bit gadget digits) / int32 LWE", "data": "synthetic",
+                      "config": {"workload": f"CCS NAND x{G} (mk_api.jl:4-10: n={params.lwe_size} N=1024 l=3 Bg=2^9 t=8 Bks=2^2, 2 parties): per blind-rotate "
+                                             "step two launches of G x 3 external products + elementwise device ops; host buffers in and out",
+                                 "key_setup_s": round(t_keys, 2)},
+                      "gpu_launches": int(launches), "clocks": clocks, "decryptions_correct": ok}))
+    ck.close()
+    return 0
+
+
 def run_perf_comp(args):
     """The reference's only published measurement protocol (measurements/test_suites/performance_comparison_test/perf_comp.jl:13-20, 107-142;
     its plot is docs/speedup.png): k = 2, 4, 8, 16 parties on the 16-PARTY parameter set, 100 single calls of
@@ -676,7 +717,7 @@ def main():
                                                              "process per GPU under torchrun")
     ap.add_argument("--latency-trials", type=int, default=100, help="single-bootstrap latency: min / median over this many calls")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="nand", choices=["nand", "adder", "less", "conv", "single", "perf_comp"],
+    ap.add_argument("--workload", default="nand", choices=["nand", "adder", "less", "conv", "single", "perf_comp", "ccs"],
                     help="nand = the headline metric; adder / less = BASELINE configs[3] (adder, comparator); conv = BASELINE configs[4]; "
                          "single = single-key TFHE NAND (tfhe_parameters_128) through the same engine")
     ap.add_argument("--width", type=int, default=None, help="bits per encrypted integer (adder: 16, conv: 4)")
@@ -694,6 +735,8 @@ def main():
         sys.exit(run_single_key(args))
     if args.workload == "perf_comp":
         sys.exit(run_perf_comp(args))
+    if args.workload == "ccs":
+        sys.exit(run_ccs(args))
     sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))
 
 

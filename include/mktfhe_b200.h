@@ -183,6 +183,15 @@ int mktfhe_extprod_batch(mktfhe_ctx *ctx, size_t G, const int32_t *elem, const i
 /* the same on device pointers (elem included), asynchronous on `stream`: the building block of the CCS scheme's hybrid product
  * (UniProduct, mk_internals.jl:471-535), which torus-fhe_b200/tfhe_ccs.py composes from 2 (k+1) of these per blind-rotate step */
 int mktfhe_extprod_batch_dev(mktfhe_ctx *ctx, size_t G, const int32_t *elem, const int64_t *acc_in, int64_t *acc_out, void *stream);
+/* mk_bootstrap_wo_keyswitch of the CCS scheme (mk_internals.jl:793-850) on a batch, as a composition run entirely by the library: per
+ * blind-rotate step two launches of G (parties + 1) external products with the rotation / accumulation kernels between them;
+ * accumulators stay in HBM.  ctx: a Torus32-mode context whose parties * (parties + 2) "parties" hold the key elements of the hybrid
+ * product (UniProduct, :471-535) -- pseudo-party p (parties + 1) + i (i = 0: the b polynomial, i >= 1: a_i): part_1 = d[p][j],
+ * part_4 = -a or b_i; pseudo-party parties (parties + 1) + p: part_1 = f0[p][j], part_4 = f1[p][j]; part_2 = part_3 = 0
+ * (torus-fhe_b200/tfhe_ccs.py, build_elements).  mu: the Torus32 test-vector message.  a_in int32 [G][parties][n], b_in [G] ->
+ * the extracted sample with one mask per party, ext_a int32 [G][parties][N], ext_b [G]. */
+int mktfhe_ccs_blind_rotate_batch(mktfhe_ctx *ctx, int parties, int32_t mu, size_t G, const int32_t *a_in, const int32_t *b_in,
+                                  int32_t *ext_a, int32_t *ext_b);
 /* mk_keyswitch(ks, sample::MKLweSample) of the CCS scheme (mk_internals.jl:703-719): the extracted sample has one mask per party,
  * ext_a = int32 [G][k][N], ext_b = int32 [G]; party p's mask goes through party p's key. */
 int mktfhe_mk_keyswitch_batch(mktfhe_ctx *ctx, size_t G, const int32_t *ext_a, const int32_t *ext_b, int32_t *a_out, int32_t *b_out);

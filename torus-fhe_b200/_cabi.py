@@ -23,7 +23,7 @@ EXPORTS = (
     "mktfhe_load_bsk", "mktfhe_load_ksk", "mktfhe_generate_ksk", "mktfhe_finalize_keys", "mktfhe_key_buffers", "mktfhe_mark_keys_received",
     "mktfhe_bootstrap_batch", "mktfhe_gate_batch", "mktfhe_bootstrap_batch_dev", "mktfhe_gate_batch_dev",
     "mktfhe_gate_batch_mixed", "mktfhe_gate_batch_mixed_dev", "mktfhe_affine_bootstrap_batch", "mktfhe_affine_bootstrap_batch_dev",
-    "mktfhe_extprod_batch", "mktfhe_extprod_batch_dev", "mktfhe_mk_keyswitch_batch", "mktfhe_blind_rotate_batch", "mktfhe_keyswitch_batch", "mktfhe_negacyclic_mul_batch",
+    "mktfhe_extprod_batch", "mktfhe_extprod_batch_dev", "mktfhe_mk_keyswitch_batch", "mktfhe_ccs_blind_rotate_batch", "mktfhe_blind_rotate_batch", "mktfhe_keyswitch_batch", "mktfhe_negacyclic_mul_batch",
     "mktfhe_launch_count", "mktfhe_last_kernel_ms", "mktfhe_algorithmic_bytes", "mktfhe_build_id", "mktfhe_describe",
 )
 
@@ -92,6 +92,7 @@ def lib():
         "mktfhe_extprod_batch": (C.c_int, [vp, sz, vp, vp, vp]),
         "mktfhe_extprod_batch_dev": (C.c_int, [vp, sz, vp, vp, vp, vp]),
         "mktfhe_mk_keyswitch_batch": (C.c_int, [vp, sz, vp, vp, vp, vp]),
+        "mktfhe_ccs_blind_rotate_batch": (C.c_int, [vp, C.c_int, i32, sz, vp, vp, vp, vp]),
         "mktfhe_blind_rotate_batch": (C.c_int, [vp, i64, sz, vp, vp, vp, vp]),
         "mktfhe_keyswitch_batch": (C.c_int, [vp, sz, vp, vp, vp]),
         "mktfhe_negacyclic_mul_batch": (C.c_int, [vp, sz, vp, vp, vp]),
@@ -312,6 +313,17 @@ class Context:
     def extprod_batch_dev(self, G, elem, acc_in, acc_out, stream=0):
         """Device pointers (ints): acc_out[g] = ExtProd(acc_in[g], element elem[g]); asynchronous on `stream`."""
         self._chk(lib().mktfhe_extprod_batch_dev(self.h, G, elem, acc_in, acc_out, stream or None))
+
+    def ccs_blind_rotate_batch(self, parties, mu, a, b):
+        """CCS mk_bootstrap_wo_keyswitch on a batch (this context holds the hybrid product's key elements): a int32 [G][parties][n], b [G]
+        -> (ext_a int32 [G][parties][N], ext_b [G])."""
+        a, b = _c(a, np.int32), _c(b, np.int32).reshape(-1)
+        G = b.size
+        if a.size != G * parties * self.n:
+            raise ValueError("a must be int32 [G][parties][n]")
+        ea, eb = np.empty((G, parties, self.N), np.int32), np.empty(G, np.int32)
+        self._chk(lib().mktfhe_ccs_blind_rotate_batch(self.h, parties, int(np.int32(mu)), G, _p(a), _p(b), _p(ea), _p(eb)))
+        return ea, eb
 
     def mk_keyswitch_batch(self, ext_a, ext_b):
         """CCS key switch: ext_a int32 [G][k][N] (one mask per party), ext_b int32 [G]."""

@@ -1001,6 +1001,78 @@ __global__ void __launch_bounds__(KS_THREADS) mk_keyswitch_kernel(int n, int k, 
     if (tid == n % KS_THREADS) ob[g] = (int32_t)((uint32_t)ext_b[g] + bsum);
 }
 
+// ---- CCS multi-key blind rotation (mk_internals.jl:793-850) as a composition: the elementwise kernels around the two rounds of
+// G (k+1) external products per step (extprod_t32_kernel).  acc: u64 [G][k+1][N] = (b, a_1 .. a_k), Torus32 values in the top halves;
+// xin / xout: the external products' operands u64 [G (k+1)][2][N] ([0] = mask, [1] = body); elem: their key elements.
+constexpr int CCS_THREADS = 256;
+// acc = (X^-barb * testvect, 0, .., 0)   (mk_blind_rotate_and_extract :826-832)
+__global__ void __launch_bounds__(CCS_THREADS) ccs_init_kernel(u64* __restrict__ acc, const int32_t* __restrict__ b_in, int k, int64_t mu) {
+    const int g = blockIdx.x;
+    const int s = (-mod_switch_2N(b_in[g])) & (2 * N - 1);
+    u64* a = acc + (size_t)g * (k + 1) * N;
+    for (int i = threadIdx.x; i < (k + 1) * N; i += CCS_THREADS) {
+        const int c = i & (N - 1);
+        const int idx = (c - s) & (2 * N - 1);
+        a[i] = i < N ? ((idx & N) ? (u64)0 - (u64)mu : (u64)mu) : 0;
+    }
+}
+// round 1 operands of the step of key bit (party, j): body_i = X^a acc_i - acc_i with a = decode_message(a_in[g][party][j], 2N)
+// (mk_mux_rotate :793-800); element (party (k+1) + i) n + j
+__global__ void __launch_bounds__(CCS_THREADS) ccs_round1_kernel(const u64* __restrict__ acc, const int32_t* __restrict__ a_in, u64* __restrict__ xin,
+                                                                  int32_t* __restrict__ elem, int k, int n, int party, int j) {
+    const int g = blockIdx.x, i = blockIdx.y;
+    const int a = mod_switch_2N(a_in[((size_t)g * k + party) * n + j]);
+    const u64* p = acc + ((size_t)g * (k + 1) + i) * N;
+    u64* body = xin + (((size_t)g * (k + 1) + i) * 2 + 1) * N;
+    for (int c = threadIdx.x; c < N; c += CCS_THREADS) {
+        const int idx = (c - a) & (2 * N - 1);
+        u64 v = p[idx & (N - 1)];
+        if (idx & N) v = 0 - v;
+        body[c] = v - p[c];
+    }
+    if (threadIdx.x == 0) elem[g * (k + 1) + i] = (party * (k + 1) + i) * n + j;
+}
+// after round 1 (xout = (v_i, u_i)): acc_i += u_i; round 2 operands body_i = v_i; element (k (k+1) + party) n + j
+__global__ void __launch_bounds__(CCS_THREADS) ccs_round2_kernel(u64* __restrict__ acc, const u64* __restrict__ xout, u64* __restrict__ xin,
+                                                                  int32_t* __restrict__ elem, int k, int n, int party, int j) {
+    const int g = blockIdx.x, i = blockIdx.y;
+    const size_t e = (size_t)g * (k + 1) + i;
+    u64* p = acc + e * N;
+    for (int c = threadIdx.x; c < N; c += CCS_THREADS) {
+        p[c] += xout[(e * 2 + 1) * N + c];
+        xin[(e * 2 + 1) * N + c] = xout[(e * 2) * N + c];
+    }
+    if (threadIdx.x == 0) elem[e] = (k * (k + 1) + party) * n + j;
+}
+// after round 2 (xout = (w1_i, w0_i)): b += sum_i w0_i, a_party += sum_i w1_i   (UniProduct :529-531)
+__global__ void __launch_bounds__(CCS_THREADS) ccs_accumulate_kernel(u64* __restrict__ acc, const u64* __restrict__ xout, int k, int party) {
+    const int g = blockIdx.x;
+    u64* b = acc + (size_t)g * (k + 1) * N;
+    u64* ap = b + (size_t)(1 + party) * N;
+    for (int c = threadIdx.x; c < N; c += CCS_THREADS) {
+        u64 w0 = 0, w1 = 0;
+        for (int i = 0; i <= k; i++) {
+            const size_t e = (size_t)g * (k + 1) + i;
+            w1 += xout[(e * 2) * N + c];
+            w0 += xout[(e * 2 + 1) * N + c];
+        }
+        b[c] += w0;
+        ap[c] += w1;
+    }
+}
+// mk_rlwe_extract_sample (mk_internals.jl:145-154): per party a'_0 = a_0, a'_m = -a_{N-m}; b' = b_0 (Torus32 = top halves)
+__global__ void __launch_bounds__(CCS_THREADS) ccs_extract_kernel(const u64* __restrict__ acc, int32_t* __restrict__ ext_a, int32_t* __restrict__ ext_b, int k) {
+    const int g = blockIdx.x;
+    const u64* b = acc + (size_t)g * (k + 1) * N;
+    for (int i = threadIdx.x; i < k * N; i += CCS_THREADS) {
+        const int p = i / N, m = i & (N - 1);
+        const u64* a = b + (size_t)(1 + p) * N;
+        const u64 v = m == 0 ? a[0] : (u64)0 - a[N - m];
+        ext_a[((size_t)g * k + p) * N + m] = (int32_t)(v >> 32);
+    }
+    if (threadIdx.x == 0) ext_b[g] = (int32_t)(b[0] >> 32);
+}
+
 // ---- key generation on the device: the key-switching key (keyswitch.jl:14-41) -------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11), counter-based: row and column of a key word are its counter, so the key is a pure function
 // of (seed, party) and no generator state is kept.

@@ -991,6 +991,58 @@ int mktfhe_extprod_batch_dev(mktfhe_ctx* c, size_t G, const int32_t* elem, const
     return MKTFHE_OK;
 }
 
+int mktfhe_ccs_blind_rotate_batch(mktfhe_ctx* c, int parties, int32_t mu, size_t G, const int32_t* a_in, const int32_t* b_in, int32_t* ext_a,
+                                  int32_t* ext_b) {
+    if (!c) return MKTFHE_EINVAL;
+    if (!c->kids.empty()) return fail(c, MKTFHE_EINVAL, "ccs_blind_rotate_batch runs on a single-device context");
+    if (!c->ready) return fail(c, MKTFHE_ESTATE, "keys not finalized (mktfhe_finalize_keys)");
+    if (!c->t32) return fail(c, MKTFHE_EINVAL, "the CCS composition needs a Torus32-mode context (MKTFHE_FLAG_TORUS32)");
+    const int k = parties, n = c->prm.n, N = mk::N;
+    if (k < 1 || k * (k + 2) != c->prm.k)
+        return fail(c, MKTFHE_EINVAL, "a CCS context for %d parties holds %d pseudo-parties of key elements, this one has %d", k, k * (k + 2), c->prm.k);
+    if (G == 0) return MKTFHE_OK;
+    if (!a_in || !b_in || !ext_a || !ext_b) return fail(c, MKTFHE_EINVAL, "ccs_blind_rotate_batch: NULL buffer");
+    if (G * (size_t)(k + 1) > 0x7fffffffu) return fail(c, MKTFHE_EINVAL, "batch too large");
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t P = (size_t)G * (k + 1), abytes = G * (size_t)k * n * 4, xbytes = P * 2 * N * 8;
+    int rc;
+    if ((rc = stage_in(c, c->in[0], a_in, abytes)) || (rc = stage_in(c, c->in[1], b_in, G * 4)) || (rc = reserve(c, c->raw, P * N * 8)) ||
+        (rc = reserve(c, c->accin, xbytes)) || (rc = reserve(c, c->accout, xbytes)) || (rc = reserve(c, c->elem, P * 4)) ||
+        (rc = reserve(c, c->ext, G * (size_t)k * N * 4)) || (rc = reserve(c, c->ob, G * 4)))
+        return rc;
+    u64* acc = (u64*)c->raw.p;
+    u64 *xin = (u64*)c->accin.p, *xout = (u64*)c->accout.p;
+    int32_t* elem = (int32_t*)c->elem.p;
+    const int32_t* d_a = (const int32_t*)c->in[0].p;
+    cudaStream_t st = c->stream;
+    CU_TRY(c, cudaMemsetAsync(xin, 0, xbytes, st));                                   // the mask operands stay zero
+    mk::ccs_init_kernel<<<(unsigned)G, mk::CCS_THREADS, 0, st>>>(acc, (const int32_t*)c->in[1].p, k, (int64_t)mu << 32);
+    const size_t sm = br_smem_bytes(c);
+    const unsigned grid = (unsigned)((P + c->gpc - 1) / c->gpc);
+    const dim3 gi((unsigned)G, (unsigned)(k + 1));
+    auto products = [&]() {
+        if (c->prm.l == 2) mk::extprod_t32_kernel<2, mk::gpc_for(2, true)><<<grid, c->gpc * mk::TPG, sm, st>>>((int)P, c->d_bsk, c->d_twB, c->prm.bgbit, elem, (const int64_t*)xin, (int64_t*)xout);
+        else mk::extprod_t32_kernel<3, mk::gpc_for(3, true)><<<grid, c->gpc * mk::TPG, sm, st>>>((int)P, c->d_bsk, c->d_twB, c->prm.bgbit, elem, (const int64_t*)xin, (int64_t*)xout);
+    };
+    for (int party = 0; party < k; party++)                                           // mk_blind_rotate (mk_internals.jl:804-816): parties outer
+        for (int j = 0; j < n; j++) {
+            mk::ccs_round1_kernel<<<gi, mk::CCS_THREADS, 0, st>>>(acc, d_a, xin, elem, k, n, party, j);
+            products();
+            mk::ccs_round2_kernel<<<gi, mk::CCS_THREADS, 0, st>>>(acc, xout, xin, elem, k, n, party, j);
+            products();
+            mk::ccs_accumulate_kernel<<<(unsigned)G, mk::CCS_THREADS, 0, st>>>(acc, xout, k, party);
+            c->launches += 5;
+        }
+    CU_TRY(c, cudaGetLastError());
+    mk::ccs_extract_kernel<<<(unsigned)G, mk::CCS_THREADS, 0, st>>>(acc, (int32_t*)c->ext.p, (int32_t*)c->ob.p, k);
+    c->launches += 2;
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(ext_a, c->ext.p, G * (size_t)k * N * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(c, cudaMemcpyAsync(ext_b, c->ob.p, G * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(c, cudaStreamSynchronize(st));
+    return MKTFHE_OK;
+}
+
 int mktfhe_mk_keyswitch_batch(mktfhe_ctx* c, size_t G, const int32_t* ext_a, const int32_t* ext_b, int32_t* a_out, int32_t* b_out) {
     if (!c) return MKTFHE_EINVAL;
     if (!c->kids.empty()) return fail(c, MKTFHE_EINVAL, "mk_keyswitch_batch runs on a single-device context");

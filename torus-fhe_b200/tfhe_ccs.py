@@ -8,9 +8,9 @@ the polynomial as body, a zero mask, and a key element whose part_1 / part_4 hol
     round 1, polynomial i:  body' = <g^-1(acc_i), d>        = u_i      mask' = <g^-1(acc_i), b_i>  (i >= 1)  or  <g^-1(b), -a>  (i = 0)   = v_i
     round 2, polynomial i:  body' = <g^-1(v_i), f0>         = w0_i     mask' = <g^-1(v_i), f1>                                                = w1_i
     a_i += u_i,   a_party += sum_i w1_i,   b += u_0 + sum_i w0_i.
-So one blind-rotate step of a batch of G gates is two launches of G (k+1) external products (`mktfhe_extprod_batch_dev`, Torus32 mode:
-9-bit gadget digits) with the rotation, subtraction and accumulation between them as elementwise device operations; ciphertexts and
-accumulators stay in HBM for the whole blind rotation.  Extraction (mk_rlwe_extract_sample) gives one mask per party, which
+So one blind-rotate step of a batch of G gates is two launches of G (k+1) external products (Torus32 mode: 9-bit gadget digits) with
+small rotation / accumulation kernels between them -- all inside the library (`mktfhe_ccs_blind_rotate_batch`); accumulators stay in HBM
+for the whole blind rotation.  Extraction (mk_rlwe_extract_sample) gives one mask per party, which
 `mktfhe_mk_keyswitch_batch` switches with party p's key (mk_keyswitch, :703-719).  This is a composition, not a fused kernel: it is
 bit-exact and three orders of magnitude faster than the CPU path, but it leaves the factor a fused (k+1)-polynomial kernel would
 bring (half of each external product multiplies zeros) on the table -- DESIGN.md section 6/7.
@@ -147,56 +147,10 @@ def mk_decrypt(secret_keys, sample):
 
 
 def mk_bootstrap_wo_keyswitch(ck, mu, x):
-    """mk_internals.jl:839-850 on a batch: the extracted sample, one mask per party -- (ext_a int32 [G][k][N], ext_b int32 [G])."""
-    import torch
-    k, n, N = ck.k, ck.n, ck.N
-    dev = torch.device("cuda", ck.device)
-    xa, xb = x.a.reshape(-1, k, n), x.b.reshape(-1)
-    G = xb.size
-    sh = 32 - (int(2 * N).bit_length() - 1)
-    modsw = lambda v: ((v.astype(np.int64) + (1 << (sh - 1))).astype(np.uint32).view(np.int32) >> sh).astype(np.int64)     # decode_message(., 2N)
-    st = torch.cuda.Stream(dev)         # the library's launches and the elementwise device operations between them share this stream
-    with torch.cuda.device(dev), torch.cuda.stream(st):
-        bara = torch.from_numpy(modsw(xa)).to(dev)                                     # [G][k][n]
-        barb = torch.from_numpy(modsw(xb)).to(dev)
-        pos = torch.arange(N, device=dev, dtype=torch.int64)[None, :]
-
-        def rotate(acc, shift):                                                          # X^shift * acc, acc int64 [G][P][N], shift int64 [G]
-            idx = (pos - shift[:, None]) & (2 * N - 1)                                   # [G][N]
-            val = torch.gather(acc, 2, (idx & (N - 1))[:, None, :].expand(-1, acc.shape[1], -1))
-            return torch.where((idx >= N)[:, None, :], -val, val)
-
-        # acc = (b, a_1 .. a_k) = (X^-barb * testvect, 0 ..), Torus32 values in the top half of int64 words
-        acc = torch.zeros((G, k + 1, N), dtype=torch.int64, device=dev)
-        acc[:, 0] = rotate(torch.full((G, 1, N), int(np.int32(mu)) << 32, dtype=torch.int64, device=dev), -barb)[:, 0]
-        i_off = torch.arange(k + 1, device=dev, dtype=torch.int32)[None, :] * n          # element (pseudo-party q, j) = q n + j
-        buf_in = torch.zeros((G * (k + 1), 2, N), dtype=torch.int64, device=dev)           # [.., 0] = mask (stays zero), [.., 1] = body
-        buf_out = torch.empty_like(buf_in)
-        elem = torch.empty((G, k + 1), dtype=torch.int32, device=dev)
-        ctx = ck.products.ctx
-        for party in range(k):
-            for j in range(n):
-                a_g = bara[:, party, j]
-                temp = rotate(acc, a_g) - acc                                            # (X^a - 1) acc; zero where a = 0 (then nothing is added)
-                buf_in[:, 1] = temp.reshape(-1, N)
-                elem.copy_((party * (k + 1) * n + j + i_off).expand(G, -1))
-                ctx.extprod_batch_dev(G * (k + 1), elem.data_ptr(), buf_in.data_ptr(), buf_out.data_ptr(), stream=st.cuda_stream)
-                r1 = buf_out.reshape(G, k + 1, 2, N)
-                u = r1[:, :, 1].clone()                                                  # body' = <g^-1(acc_i), d>
-                buf_in[:, 1] = r1[:, :, 0].reshape(-1, N)                                # mask' = v_i
-                elem.fill_((k * (k + 1) + party) * n + j)
-                ctx.extprod_batch_dev(G * (k + 1), elem.data_ptr(), buf_in.data_ptr(), buf_out.data_ptr(), stream=st.cuda_stream)
-                r2 = buf_out.reshape(G, k + 1, 2, N)
-                acc += u
-                acc[:, 0] += r2[:, :, 1].sum(1)                                          # sum_i w0_i
-                acc[:, 1 + party] += r2[:, :, 0].sum(1)                                  # sum_i w1_i
-        # mk_rlwe_extract_sample (mk_internals.jl:145-154): per party a'_0 = a_0, a'_m = -a_{N-m}; b' = b_0
-        masks = acc[:, 1:]
-        ext_a = torch.cat([masks[:, :, :1], -masks[:, :, 1:].flip(-1)], dim=-1) >> 32
-        ext_b = acc[:, 0, 0] >> 32
-        out = ext_a.to(torch.int32).cpu().numpy(), ext_b.to(torch.int32).cpu().numpy()
-    st.synchronize()
-    return out
+    """mk_internals.jl:839-850 on a batch: the extracted sample, one mask per party -- (ext_a int32 [G][k][N], ext_b int32 [G]).
+    One library call (mktfhe_ccs_blind_rotate_batch): mod-switch, the k n steps of two rounds of G (k + 1) external products each with
+    the rotation / accumulation kernels between them, extraction; accumulators never leave HBM."""
+    return ck.products.ctx.ccs_blind_rotate_batch(ck.k, mu, x.a.reshape(-1, ck.k, ck.n), x.b.reshape(-1))
 
 
 def mk_keyswitch(ck, ext_a, ext_b):
