@@ -59,8 +59,8 @@ extern "C" {
 /* Integer part of SchemeParameters_3gen (api.jl:50-67); rlwe_mask_size = 1 and
  * rlwe_is32 = false as in every 3gen set (mk_api.jl:32-322).  Supported:
  *  - N = 1024 (2..8 parties, mk_api.jl:32-146): 1 <= l <= 4, bgbit <= 8, 2l*N*2^(bgbit-1)*2^63 < M/4 with M ~ 2^84 the
- *    product of the three NTT primes (so the CRT result is exact), n*k <= 8192; with MKTFHE_FLAG_TORUS32: l = 2 or 3,
- *    bgbit <= 16, l*bgbit <= 32;
+ *    product of the three NTT primes (so the CRT result is exact), n*k <= 8192; with MKTFHE_FLAG_TORUS32: l = 2..4,
+ *    bgbit <= 16, l*bgbit <= 32, n*k <= 32768;
  *  - N = 2048 (16..256 parties, mk_api.jl:214-310): l = 1 or 2, bgbit <= 27, four NTT primes (M ~ 2^112), n*k <= 2^18;
  *  - t*basebit <= 31, basebit <= 16.
  * Rejected with MKTFHE_EINVAL: N = 4096 (512 parties). */

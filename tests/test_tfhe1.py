@@ -199,8 +199,8 @@ def test_reference_gate_testcase_on_its_default_parameters():
         for name, (fn, nargs, plain) in T1.GATES.items():
             out = fn(ck, *(x, y, z)[:nargs])
             assert np.array_equal(T1.decrypt(sk, out), plain(*[bits[:, i] for i in range(nargs)])), name
-        # flag validation: Torus32 mode is an N = 1024, l = 2..3 mode; unknown flag bits are refused
-        for bad in ((500, 1024, 1, 4, 8, 8, 2, 1), (500, 1024, 1, 2, 17, 8, 2, 1), (500, 2048, 1, 1, 10, 8, 2, 1), (500, 1024, 1, 2, 10, 8, 2, 2)):
+        # flag validation: Torus32 mode is an N = 1024, l = 2..4 mode; unknown flag bits are refused
+        for bad in ((500, 1024, 1, 5, 6, 8, 2, 1), (500, 1024, 1, 2, 17, 8, 2, 1), (500, 2048, 1, 1, 10, 8, 2, 1), (500, 1024, 1, 2, 10, 8, 2, 2)):
             with pytest.raises(T.MktfheError):
                 T._cabi.Context(*bad[:7], flags=bad[7])
     finally:

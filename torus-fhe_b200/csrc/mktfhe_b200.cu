@@ -118,9 +118,10 @@ int check_params(const mktfhe_params* p) {
     if (p->reserved & ~MKTFHE_FLAG_TORUS32) return fail(nullptr, MKTFHE_EINVAL, "unknown flags 0x%x", p->reserved);
     if (p->reserved & MKTFHE_FLAG_TORUS32) {
         // Torus32 mode: unshifted 32-bit keys, 16-bit digit fields, products added as R << 32: |R| <= 2l * N * 2^(bgbit-1) * 2^31 < 2^59
-        if (p->l < 2 || p->l > 3) return fail(nullptr, MKTFHE_EINVAL, "Torus32 mode is built for gsw_decomp_length l=2 or 3 (got %d)", p->l);
+        if (p->l < 2 || p->l > 4) return fail(nullptr, MKTFHE_EINVAL, "Torus32 mode is built for gsw_decomp_length l=2..4 (got %d)", p->l);
         if (p->bgbit < 1 || p->bgbit > 16 || p->l * p->bgbit > 32) return fail(nullptr, MKTFHE_EINVAL, "Torus32 mode: need bgbit <= 16 and l*bgbit <= 32");
-        if (p->k < 1 || p->n < 1 || (long long)p->n * p->k > 8192) return fail(nullptr, MKTFHE_EINVAL, "need 1 <= n*k <= 8192");
+        // k may count the pseudo-parties of a CCS context (parties * (parties + 2) sets of n key elements): up to 2^15 elements
+        if (p->k < 1 || p->n < 1 || (long long)p->n * p->k > 32768) return fail(nullptr, MKTFHE_EINVAL, "need 1 <= n*k <= 32768");
         if (p->n + 1 > mk::KS_THREADS * mk::KS_MAXCOLS) return fail(nullptr, MKTFHE_EINVAL, "n too large for the key-switch kernel");
         if (p->t < 1 || p->t * p->basebit > 31) return fail(nullptr, MKTFHE_EINVAL, "need t*basebit <= 31");
         return MKTFHE_OK;
@@ -152,6 +153,14 @@ size_t br_smem_bytes(const mktfhe_ctx* c) { return mk::cta_smem_bytes(c->prm.l, 
     default: KERNEL(4, mk::gpc_for(4), __VA_ARGS__); break;                \
     }
 
+// Torus32-mode instantiations: l = 2, 3, 4
+#define MK_DISPATCH_T32(c, KERNEL, ...)                                          \
+    switch ((c)->prm.l) {                                                        \
+    case 2: KERNEL(2, mk::gpc_for(2, true), __VA_ARGS__); break;                 \
+    case 3: KERNEL(3, mk::gpc_for(3, true), __VA_ARGS__); break;                 \
+    default: KERNEL(4, mk::gpc_for(4, true), __VA_ARGS__); break;                \
+    }
+
 int set_attrs(mktfhe_ctx* c) {
     if (c->prm.N == mk2k::N) {
         if (c->prm.l == 1) CU_TRY(c, cudaFuncSetAttribute(mk2k::blind_rotate2k_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk2k::smem_bytes(1)));
@@ -162,13 +171,11 @@ int set_attrs(mktfhe_ctx* c) {
     }
     const int sm = (int)br_smem_bytes(c);
     if (c->t32) {
-        if (c->prm.l == 2) {
-            CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_t32_kernel<2, mk::gpc_for(2, true)>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-            CU_TRY(c, cudaFuncSetAttribute(mk::extprod_t32_kernel<2, mk::gpc_for(2, true)>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        } else {
-            CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_t32_kernel<3, mk::gpc_for(3, true)>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-            CU_TRY(c, cudaFuncSetAttribute(mk::extprod_t32_kernel<3, mk::gpc_for(3, true)>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        }
+#define SET_ATTR_T32(L, GPC, dummy)                                                                                                \
+    CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_t32_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));         \
+    CU_TRY(c, cudaFuncSetAttribute(mk::extprod_t32_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        MK_DISPATCH_T32(c, SET_ATTR_T32, 0)
+#undef SET_ATTR_T32
         return MKTFHE_OK;
     }
 #define SET_ATTR(L, GPC, dummy)                                                                                                    \
@@ -219,8 +226,9 @@ void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G, 
         h.g0 = 0; h.G = (int)G;
         const size_t sm = br_smem_bytes(c);
         const unsigned grid = (unsigned)((G + c->gpc - 1) / c->gpc);
-        if (c->prm.l == 2) mk::blind_rotate_t32_kernel<2, mk::gpc_for(2, true)><<<grid, c->gpc * mk::TPG, sm, st>>>(h);
-        else mk::blind_rotate_t32_kernel<3, mk::gpc_for(3, true)><<<grid, c->gpc * mk::TPG, sm, st>>>(h);
+#define LAUNCH_BR_T32(L, GPC, dummy) mk::blind_rotate_t32_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, st>>>(h)
+        MK_DISPATCH_T32(c, LAUNCH_BR_T32, 0)
+#undef LAUNCH_BR_T32
         c->launches++;
         return;
     }
@@ -819,12 +827,11 @@ static int mktfhe_extprod_batch_1(mktfhe_ctx* c, size_t G, const int32_t* elem, 
     const size_t sm = br_smem_bytes(c);
     const unsigned grid = (unsigned)((G + c->gpc - 1) / c->gpc);
     if (c->t32) {
-        if (c->prm.l == 2)
-            mk::extprod_t32_kernel<2, mk::gpc_for(2, true)><<<grid, c->gpc * mk::TPG, sm, c->stream>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, (const int32_t*)c->elem.p,
-                                                                                                       (const int64_t*)c->accin.p, (int64_t*)c->accout.p);
-        else
-            mk::extprod_t32_kernel<3, mk::gpc_for(3, true)><<<grid, c->gpc * mk::TPG, sm, c->stream>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, (const int32_t*)c->elem.p,
-                                                                                                       (const int64_t*)c->accin.p, (int64_t*)c->accout.p);
+#define LAUNCH_EP_T32(L, GPC, dummy)                                                                                                   \
+    mk::extprod_t32_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, c->stream>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, (const int32_t*)c->elem.p, \
+                                                                           (const int64_t*)c->accin.p, (int64_t*)c->accout.p)
+        MK_DISPATCH_T32(c, LAUNCH_EP_T32, 0)
+#undef LAUNCH_EP_T32
     } else {
 #define LAUNCH_EP(L, GPC, dummy)                                                                                          \
     mk::extprod_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, c->stream>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, (const int32_t*)c->elem.p, \
@@ -979,8 +986,9 @@ int mktfhe_extprod_batch_dev(mktfhe_ctx* c, size_t G, const int32_t* elem, const
     const size_t sm = br_smem_bytes(c);
     const unsigned grid = (unsigned)((G + c->gpc - 1) / c->gpc);
     if (c->t32) {
-        if (c->prm.l == 2) mk::extprod_t32_kernel<2, mk::gpc_for(2, true)><<<grid, c->gpc * mk::TPG, sm, st>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, elem, acc_in, acc_out);
-        else mk::extprod_t32_kernel<3, mk::gpc_for(3, true)><<<grid, c->gpc * mk::TPG, sm, st>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, elem, acc_in, acc_out);
+#define LAUNCH_EPD_T32(L, GPC, dummy) mk::extprod_t32_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, st>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, elem, acc_in, acc_out)
+        MK_DISPATCH_T32(c, LAUNCH_EPD_T32, 0)
+#undef LAUNCH_EPD_T32
     } else {
 #define LAUNCH_EPD(L, GPC, dummy) mk::extprod_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, st>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, elem, acc_in, acc_out)
         MK_DISPATCH_L(c, LAUNCH_EPD, 0)
@@ -1021,8 +1029,10 @@ int mktfhe_ccs_blind_rotate_batch(mktfhe_ctx* c, int parties, int32_t mu, size_t
     const unsigned grid = (unsigned)((P + c->gpc - 1) / c->gpc);
     const dim3 gi((unsigned)G, (unsigned)(k + 1));
     auto products = [&]() {
-        if (c->prm.l == 2) mk::extprod_t32_kernel<2, mk::gpc_for(2, true)><<<grid, c->gpc * mk::TPG, sm, st>>>((int)P, c->d_bsk, c->d_twB, c->prm.bgbit, elem, (const int64_t*)xin, (int64_t*)xout);
-        else mk::extprod_t32_kernel<3, mk::gpc_for(3, true)><<<grid, c->gpc * mk::TPG, sm, st>>>((int)P, c->d_bsk, c->d_twB, c->prm.bgbit, elem, (const int64_t*)xin, (int64_t*)xout);
+#define LAUNCH_CCS_T32(L, GPC, dummy) \
+    mk::extprod_t32_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, st>>>((int)P, c->d_bsk, c->d_twB, c->prm.bgbit, elem, (const int64_t*)xin, (int64_t*)xout)
+        MK_DISPATCH_T32(c, LAUNCH_CCS_T32, 0)
+#undef LAUNCH_CCS_T32
     };
     for (int party = 0; party < k; party++)                                           // mk_blind_rotate (mk_internals.jl:804-816): parties outer
         for (int j = 0; j < n; j++) {

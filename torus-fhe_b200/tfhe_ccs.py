@@ -15,8 +15,9 @@ for the whole blind rotation.  Extraction (mk_rlwe_extract_sample) gives one mas
 bit-exact and three orders of magnitude faster than the CPU path, but it leaves the factor a fused (k+1)-polynomial kernel would
 bring (half of each external product multiplies zeros) on the table -- DESIGN.md section 6/7.
 
-Names and arguments follow the reference; samples may carry a leading batch dimension.  Only `mktfhe_parameters_2party` (l = 3,
-Bg = 2^9) is served: the library's Torus32 mode is instantiated for l = 2, 3.
+Names and arguments follow the reference; samples may carry a leading batch dimension.  Served: `mktfhe_parameters_2party` (l = 3,
+Bg = 2^9) and `mktfhe_parameters_4party` (l = 4, Bg = 2^8); the 8- and 16-party CCS sets use l = 5 and 12, beyond the N = 1024 kernels'
+l <= 4.
 """
 import numpy as np
 
@@ -26,8 +27,9 @@ from .tfhe1 import SchemeParameters, keyswitch_parameters, lwe_parameters, rlwe_
 from .tfhe3gen import (KeyswitchKey, LweKey, LweParams, MKLweSample, RLweKey, SchemeParameters_3gen, dtot32, encode_message, mk_lwe_noiseless_trivial,
                        mk_lwe_phase, negacyclic_mul, rand_uniform_torus32)
 
-# mk_api.jl:4-10
+# mk_api.jl:4-10, 56-62
 mktfhe_parameters_2party = SchemeParameters(560, 3.05e-5, 1024, 1, True, 3, 9, 3.72e-9, 8, 2, 3.05e-5, 2)
+mktfhe_parameters_4party = SchemeParameters(560, 3.05e-5, 1024, 1, True, 4, 8, 3.72e-9, 8, 2, 3.05e-5, 4)
 
 
 class SecretKey:   # api.jl:176-184
