@@ -242,7 +242,7 @@ __device__ __forceinline__ void warp_ntt_inv(u32 (&x)[32], u32* tile, const uint
 
 // Phase 1 of a step: rotate-subtract and gadget-decompose (tgsw.jl:112-138); digits biased to [0, Bg) and packed 4 per word
 // in the order the NTT warps read them (dig: [2L][8][32] words).
-template <int L, bool MUX, int W = WPG, bool WIDE = false>
+template <int L, bool MUX, int W = WPG, bool WIDE = false, bool BODY = false>
 __device__ __forceinline__ void decompose_phase(const u64* __restrict__ acc, u32* __restrict__ dig, int a, int bgbit, int gtid) {
     u64 off = 0;
 #pragma unroll
@@ -250,8 +250,9 @@ __device__ __forceinline__ void decompose_phase(const u64* __restrict__ acc, u32
     const u32 dmask = (1u << bgbit) - 1;
     // byte fields: 4 coefficients per word, dig [2L][8][32]; WIDE (gadget digits of 9..16 bits): 2 per word, dig [2L][16][32]
     constexpr int PER = WIDE ? 2 : 4, ROWS = 32 / PER, FIELD = 32 / PER;
-    for (int task = gtid; task < 2 * ROWS * 32; task += 32 * W) {
-        const int c = task / (ROWS * 32), rh = (task >> 5) % ROWS, ln = task & 31;
+    // BODY: only the body polynomial (acc[1]) is decomposed -- the mask operand is known to be zero (CCS hybrid product)
+    for (int task = gtid; task < (BODY ? 1 : 2) * ROWS * 32; task += 32 * W) {
+        const int c = BODY ? 1 : task / (ROWS * 32), rh = (task >> 5) % ROWS, ln = task & 31;
         const u64* poly = acc + c * N;
         u32 packed[L];
 #pragma unroll
@@ -361,16 +362,17 @@ __device__ __forceinline__ void crt_phase_lat(u64* __restrict__ acc, const u32* 
     }
 }
 
-template <int L, bool MUX, int W = WPG, bool WIDE = false>
+template <int L, bool MUX, int W = WPG, bool WIDE = false, bool BODY = false>
 __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restrict__ dig, u32* __restrict__ tiles,
                                              const uint2_* __restrict__ twB, const u32* __restrict__ key, int a, int bgbit,
                                              int bar_id, int pbar_id, int gtid, bool ap = false, int cta_threads = 0) {
     static_assert(W == 3 || W == 6 || (L >= 2 && W == lat_wpg(L)), "warps per gate: 3, 6, or 6 l (latency launch)");
     constexpr bool LAT = L >= 2 && W == lat_wpg(L);
     static_assert(!WIDE || (W == 6 && !LAT), "16-bit digit fields (Torus32 mode) are served by the six-warp shape only");
+    static_assert(!BODY || WIDE, "the body-only product exists in Torus32 mode");
     const int gw = gtid >> 5, lane = gtid & 31;
     const int w = LAT ? gw / (2 * L) : W == 6 ? gw >> 1 : gw;          // prime of this warp
-    decompose_phase<L, MUX, W, WIDE>(acc, dig, a, bgbit, gtid);
+    decompose_phase<L, MUX, W, WIDE, BODY>(acc, dig, a, bgbit, gtid);
     gate_barrier<W>(bar_id);
     const u32 p = c_rns.p[w], pinv = c_rns.pinv_neg[w];
     const u32 p4 = rns::keep_in_register(4 * p);
@@ -450,13 +452,22 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
 #pragma unroll
         for (int c = 0; c < 32; c++) accv[c] = 0;
 #endif
+        // BODY (zero mask operand): only the L body digit polynomials s < L exist; the pairs (2i, 2i + 1) with 2i < L are processed and
+        // a warp whose own or partner's polynomial is s >= L skips that term (barriers are kept)
+        constexpr int PAIRS = BODY ? (L + 1) / 2 : L;
 #pragma unroll S_UNROLL
-        for (int i = 0; i < L; i++) {
+        for (int i = 0; i < PAIRS; i++) {
             const int s_own = 2 * i + o, s_for = 2 * i + 1 - o;
+            const bool have_own = !BODY || s_own < L;      // a missing polynomial is parked as zeros: its products vanish by themselves
             u32 x[32];
             if constexpr (WIDE) {
-                load_digits_wide(x, dig, s_own, lane, bias);
-                warp_ntt_fwd(x, tile, twAf, twBf, p, lane);
+                if (have_own) {
+                    load_digits_wide(x, dig, s_own, lane, bias);
+                    warp_ntt_fwd(x, tile, twAf, twBf, p, lane);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) x[c] = 0;
+                }
             } else {
             load_digits(x, dig, lut, s_own, lane, bias);
 #if MK_ANTIPHASE && MK_AP_SPLIT == 1
@@ -833,7 +844,8 @@ __global__ void __maxnreg__(MK_MAXNREG) extprod_kernel(int G, const u32* bsk, co
 }
 
 // the same in Torus32 mode: acc_in / acc_out hold Torus32 values in the TOP half of their words (v << 32)
-template <int L, int GPC>
+// BODY: the mask operand is zero and is neither read nor decomposed (the rounds of the CCS hybrid product)
+template <int L, int GPC, bool BODY = false>
 __global__ void __maxnreg__(MK_MAXNREG) extprod_t32_kernel(int G, const u32* bsk, const uint2_* twB_g, int bgbit, const int32_t* elem,
                                                             const int64_t* acc_in, int64_t* acc_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -847,9 +859,9 @@ __global__ void __maxnreg__(MK_MAXNREG) extprod_t32_kernel(int G, const u32* bsk
     u64* acc = reinterpret_cast<u64*>(base);
     u32* dig = reinterpret_cast<u32*>(base + 2 * N * 8);
     u32* tiles = dig + 2 * L * (N / 2);
-    for (int i = gtid; i < 2 * N; i += TPG) acc[i] = (u64)acc_in[(size_t)g * 2 * N + i];
+    for (int i = gtid + (BODY ? N : 0); i < 2 * N; i += TPG) acc[i] = (u64)acc_in[(size_t)g * 2 * N + i];
     gate_barrier(bar_id);
-    extprod_step<L, false, WPG, true>(acc, dig, tiles, twB, bsk + (size_t)elem[g] * bsk_elem_words(L), 0, bgbit, bar_id, pbar_id, gtid);
+    extprod_step<L, false, WPG, true, BODY>(acc, dig, tiles, twB, bsk + (size_t)elem[g] * bsk_elem_words(L), 0, bgbit, bar_id, pbar_id, gtid);
     for (int i = gtid; i < 2 * N; i += TPG) acc_out[(size_t)g * 2 * N + i] = (int64_t)acc[i];
 }
 

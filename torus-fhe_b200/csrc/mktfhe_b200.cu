@@ -173,7 +173,8 @@ int set_attrs(mktfhe_ctx* c) {
     if (c->t32) {
 #define SET_ATTR_T32(L, GPC, dummy)                                                                                                \
     CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_t32_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));         \
-    CU_TRY(c, cudaFuncSetAttribute(mk::extprod_t32_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    CU_TRY(c, cudaFuncSetAttribute(mk::extprod_t32_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));         \
+    CU_TRY(c, cudaFuncSetAttribute(mk::extprod_t32_kernel<L, GPC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         MK_DISPATCH_T32(c, SET_ATTR_T32, 0)
 #undef SET_ATTR_T32
         return MKTFHE_OK;
@@ -1030,7 +1031,7 @@ int mktfhe_ccs_blind_rotate_batch(mktfhe_ctx* c, int parties, int32_t mu, size_t
     const dim3 gi((unsigned)G, (unsigned)(k + 1));
     auto products = [&]() {
 #define LAUNCH_CCS_T32(L, GPC, dummy) \
-    mk::extprod_t32_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, st>>>((int)P, c->d_bsk, c->d_twB, c->prm.bgbit, elem, (const int64_t*)xin, (int64_t*)xout)
+    mk::extprod_t32_kernel<L, GPC, true><<<grid, GPC * mk::TPG, sm, st>>>((int)P, c->d_bsk, c->d_twB, c->prm.bgbit, elem, (const int64_t*)xin, (int64_t*)xout)
         MK_DISPATCH_T32(c, LAUNCH_CCS_T32, 0)
 #undef LAUNCH_CCS_T32
     };
