@@ -1,0 +1,453 @@
+// fft64.cuh -- the external product of the blind rotation on the FP64 pipe (N = 1024 parameter sets, byte-sized gadget digits).
+//
+// Same exact result as the three-prime NTT kernels of kernels.cuh (every product mod (X^N + 1, 2^64), bit for bit), computed the way
+// the reference computes it -- a folded complex FFT (3-gen-mk-tfhe/src/polynomials.jl:208-242) -- but made EXACT: the Torus64 key word
+// is split in three balanced limbs of 22 / 21 / 21 bits, so every limb product sum_s digit_s * limb_s is an integer below
+// 2 l N (Bg / 2) 2^21 <= 2^39, which a double-precision FFT of 512 complex points reproduces to within 2^-13 of an integer (measured
+// worst case, tools/fft_channel/proto.py; the rounding bound of the networks is 2^-8) -- rounding recovers it exactly and
+// R = r0 + (r1 << 22) + (r2 << 43) mod 2^64 is the wrap the reference's Int64 arithmetic performs (tgsw_3gen.jl:102-113).
+//
+// Why: per gate and step the NTT formulation needs 12 forward + 6 inverse 1024-point transforms at 4 IMAD-pipe slots per butterfly
+// (446 k slots); this one needs 4 forward + 6 inverse 512-point complex transforms at 6 DFMA-pipe slots per butterfly (about 212 k
+// slots), on a pipe of the same width (DFMA 62.5 lanes / clk / SM against IMAD 62.4, profiles/fp64_pipe_ubench_r2.txt), with no
+// modular corrections, no CRT, and the integer / load-store pipes left for the decomposition and the limb recombination.
+//
+// Transform networks (tools/fft_channel/proto.py is the numpy twin, tables_fft.h the table generator):
+//   forward  Cooley-Tukey, natural -> bit-reversed, on C[X] / (X^512 - i): the negacyclic twist is merged into the group twiddles, stage 0
+//            has the single twiddle exp(i pi / 4) and is formed straight from the digit bytes
+//   inverse  decimation in time, bit-reversed -> natural: pass B' has compile-time twiddles; the last stage and the untwist are done
+//            by the threads that round, recombine the limbs and update the accumulator
+// A warp holds a 512-point transform as 16 complex values per thread: position = h 256 + r 16 + l16 (lane = 16 h + l16, register r) in the
+// row layout, lane 16 + c (register c) in the column layout; one swizzled shared-memory transpose between the two.
+#pragma once
+#include <cuda_runtime.h>
+#include "kernels.cuh"
+#include "fft64_layout.h"
+
+namespace mkf {
+
+struct __align__(16) cpx { double x, y; };
+
+constexpr double INV_SQRT2 = 0.70710678118654752440;
+constexpr int WPG = 6, TPG = 32 * WPG;
+
+// per gate: Torus64 accumulator, packed digits (one byte per coefficient), 2l digit spectra, 6 limb-output buffers.
+// ALIAS (l >= 3): the limb-output buffers reuse the spectra (one more gate barrier per step).
+__host__ __device__ constexpr bool alias_for(int l) { return l >= 3; }
+__host__ __device__ constexpr int nbuf(int l) { return alias_for(l) ? (2 * l > 6 ? 2 * l : 6) : 2 * l + 6; }
+__host__ __device__ constexpr size_t gate_bytes(int l) { return (size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)nbuf(l) * M * 16; }
+__host__ __device__ constexpr int gpc_for(int l) {
+    int g = 2;
+    while (g > 1 && (size_t)TW_BYTES + (size_t)g * gate_bytes(l) > 227 * 1024) g--;
+    return g;
+}
+__host__ __device__ constexpr size_t cta_bytes(int l, int gpc) { return (size_t)TW_BYTES + (size_t)gpc * gate_bytes(l); }
+
+// (a, b) -> (a + w b, a - w b): 6 DFMA-pipe instructions
+__device__ __forceinline__ void ct(cpx& a, cpx& b, const cpx w) {
+    const double tr = fma(w.x, b.x, fma(-w.y, b.y, a.x));
+    const double ti = fma(w.x, b.y, fma(w.y, b.x, a.y));
+    b.x = fma(2.0, a.x, -tr);
+    b.y = fma(2.0, a.y, -ti);
+    a.x = tr;
+    a.y = ti;
+}
+// w = 1 and w = -i: 4 DADD
+__device__ __forceinline__ void ct_one(cpx& a, cpx& b) {
+    const double ar = a.x, ai = a.y;
+    a.x = ar + b.x; a.y = ai + b.y;
+    b.x = ar - b.x; b.y = ai - b.y;
+}
+__device__ __forceinline__ void ct_negi(cpx& a, cpx& b) {   // w b = -i b = (b.y, -b.x)
+    const double ar = a.x, ai = a.y, br = b.x, bi = b.y;
+    a.x = ar + bi; a.y = ai - br;
+    b.x = ar - bi; b.y = ai + br;
+}
+__device__ __forceinline__ cpx cmul(const cpx a, const cpx b) { return {fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x)}; }
+
+// exact small integer -> double without a conversion instruction: bits 0x43300000'u = 2^52 + u
+__device__ __forceinline__ double u2d(unsigned u, double magic) { return __hiloint2double(0x43300000, (int)u) - magic; }
+
+// stage 0 of the forward transform straight from the digit words: word j (j < 256) holds the biased digit bytes of coefficients
+// j, j + 256, j + 512, j + 768; a~[j] = d0 + i d2, a~[j + 256] = d1 + i d3; out = a~[j] +- exp(i pi / 4) a~[j + 256] (+ for h = 0)
+__device__ __forceinline__ void fwd_stage0_digits(cpx (&v)[16], const u32* __restrict__ dig_s, int lane, int half_bg) {
+    const int h = lane >> 4, l16 = lane & 15;
+    const double cs = h ? -INV_SQRT2 : INV_SQRT2;
+    const double two52 = 4503599627370496.0;
+    const double m0 = two52 + (double)half_bg, mP = two52 + 256.0, mQ = two52 + (double)(2 * half_bg);
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const u32 word = dig_s[16 * r + l16];
+        const u32 b0 = word & 0xffu, b1 = (word >> 8) & 0xffu, b2 = (word >> 16) & 0xffu, b3 = word >> 24;
+        const double x0 = u2d(b0, m0), y0 = u2d(b2, m0);
+        const double P = u2d(b1 - b3 + 256u, mP), Q = u2d(b1 + b3, mQ);      // x1 - y1, x1 + y1
+        v[r].x = fma(cs, P, x0);
+        v[r].y = fma(cs, Q, y0);
+    }
+}
+// the same from the four real coefficients (key transform): a0 = a[j], a1 = a[j + 256], a2 = a[j + 512], a3 = a[j + 768]
+__device__ __forceinline__ cpx fwd_stage0_real(double a0, double a1, double a2, double a3, int h) {
+    const double cs = h ? -INV_SQRT2 : INV_SQRT2;
+    return {fma(cs, a1 - a3, a0), fma(cs, a1 + a3, a2)};
+}
+
+// forward stages 1..4 in the row layout (register r = position bits 7..4)
+__device__ __forceinline__ void fwd_passA(cpx (&v)[16], const cpx* __restrict__ tw, int h) {
+    {
+        const cpx w = tw[TF_A + 0 + h];
+#pragma unroll
+        for (int r = 0; r < 8; r++) ct(v[r], v[r + 8], w);
+    }
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+        const cpx w = tw[TF_A + 2 + 2 * h + g];
+#pragma unroll
+        for (int r = 0; r < 4; r++) ct(v[8 * g + r], v[8 * g + r + 4], w);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const cpx w = tw[TF_A + 6 + 4 * h + g];
+#pragma unroll
+        for (int r = 0; r < 2; r++) ct(v[4 * g + r], v[4 * g + r + 2], w);
+    }
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+        const cpx w = tw[TF_A + 14 + 8 * h + g];
+        ct(v[2 * g], v[2 * g + 1], w);
+    }
+}
+// forward stages 5..8 in the column layout (register c = position bits 3..0), per-lane twiddles
+__device__ __forceinline__ void fwd_passB(cpx (&v)[16], const cpx* __restrict__ tw, int lane) {
+    {
+        const cpx w = tw[TF_B + lane];
+#pragma unroll
+        for (int c = 0; c < 8; c++) ct(v[c], v[c + 8], w);
+    }
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+        const cpx w = tw[TF_B + 32 + g * 32 + lane];
+#pragma unroll
+        for (int c = 0; c < 4; c++) ct(v[8 * g + c], v[8 * g + c + 4], w);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const cpx w = tw[TF_B + 96 + g * 32 + lane];
+#pragma unroll
+        for (int c = 0; c < 2; c++) ct(v[4 * g + c], v[4 * g + c + 2], w);
+    }
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+        const cpx w = tw[TF_B + 224 + g * 32 + lane];
+        ct(v[2 * g], v[2 * g + 1], w);
+    }
+}
+// inverse spans 1, 2, 4, 8 in the column layout: twiddle exp(-2 pi i (c mod sp) / (2 sp)), compile-time constants
+__device__ __forceinline__ void inv_passB(cpx (&v)[16]) {
+#pragma unroll
+    for (int c = 0; c < 16; c += 2) ct_one(v[c], v[c + 1]);
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) {
+        ct_one(v[c], v[c + 2]);
+        ct_negi(v[c + 1], v[c + 3]);
+    }
+#pragma unroll
+    for (int c = 0; c < 16; c += 8) {
+        ct_one(v[c], v[c + 4]);
+        ct(v[c + 1], v[c + 5], cpx{INV_SQRT2, -INV_SQRT2});
+        ct_negi(v[c + 2], v[c + 6]);
+        ct(v[c + 3], v[c + 7], cpx{-INV_SQRT2, -INV_SQRT2});
+    }
+    constexpr double C1 = 0.92387953251128675613, S1 = 0.38268343236508977173;   // cos, sin of pi / 8
+    ct_one(v[0], v[8]);
+    ct(v[1], v[9], cpx{C1, -S1});
+    ct(v[2], v[10], cpx{INV_SQRT2, -INV_SQRT2});
+    ct(v[3], v[11], cpx{S1, -C1});
+    ct_negi(v[4], v[12]);
+    ct(v[5], v[13], cpx{-S1, -C1});
+    ct(v[6], v[14], cpx{-INV_SQRT2, -INV_SQRT2});
+    ct(v[7], v[15], cpx{-C1, -S1});
+}
+// inverse spans 16, 32, 64, 128 in the row layout: twiddle exp(-2 pi i ((r mod rs) 16 + l16) / (32 rs))
+__device__ __forceinline__ void inv_passA(cpx (&v)[16], const cpx* __restrict__ tw, int l16) {
+#pragma unroll
+    for (int rs = 1; rs <= 8; rs *= 2) {
+#pragma unroll
+        for (int e = 0; e < rs; e++) {
+            const cpx w = tw[TI_A + 16 * (rs - 1) + e * 16 + l16];
+#pragma unroll
+            for (int r0 = 0; r0 < 16; r0 += 2 * rs) ct(v[r0 + e], v[r0 + e + rs], w);
+        }
+    }
+}
+// row layout -> column layout and back through a 512-entry buffer, XOR-swizzled so that both sides are conflict-free
+__device__ __forceinline__ void rows_to_cols(cpx (&v)[16], cpx* __restrict__ buf, int lane) {
+    const int h = lane >> 4, l16 = lane & 15;
+#pragma unroll
+    for (int r = 0; r < 16; r++) buf[h * 256 + r * 16 + (l16 ^ r)] = v[r];
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 16; c++) v[c] = buf[h * 256 + l16 * 16 + (c ^ l16)];
+    __syncwarp();
+}
+__device__ __forceinline__ void cols_to_rows(cpx (&v)[16], cpx* __restrict__ buf, int lane) {
+    const int h = lane >> 4, l16 = lane & 15;
+#pragma unroll
+    for (int c = 0; c < 16; c++) buf[h * 256 + l16 * 16 + (c ^ l16)] = v[c];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 16; r++) v[r] = buf[h * 256 + r * 16 + (l16 ^ r)];
+    __syncwarp();
+}
+
+__device__ __forceinline__ void stage_tables(cpx* tw_s, const cpx* __restrict__ tw_g) {
+    const double2* src = reinterpret_cast<const double2*>(tw_g);
+    double2* dst = reinterpret_cast<double2*>(tw_s);
+    for (int i = threadIdx.x; i < T_ENTRIES; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+// Phase 1 of a step: rotate-subtract and gadget-decompose (tgsw.jl:112-138); digits biased to [0, Bg), dig [2L][256] words, word j of
+// a polynomial = the bytes of coefficients j, j + 256, j + 512, j + 768
+template <int L, bool MUX>
+__device__ __forceinline__ void decompose(const u64* __restrict__ acc, u32* __restrict__ dig, int a, int bgbit, int gtid) {
+    u64 off = 0;
+#pragma unroll
+    for (int q = 1; q <= L; q++) off += ((u64)1 << (64 - q * bgbit)) << (bgbit - 1);   // tgsw.jl:24-30
+    const u32 dmask = (1u << bgbit) - 1;
+    for (int task = gtid; task < 512; task += TPG) {
+        const int c = task >> 8, j = task & 255;
+        const u64* poly = acc + c * N;
+        u32 packed[L];
+#pragma unroll
+        for (int q = 0; q < L; q++) packed[q] = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int i = j + 256 * b;
+            u64 t;
+            if (MUX) {
+                const int idx = (i - a) & (2 * N - 1);        // (X^a * p)[i] = +-p[(i - a) mod 2N]
+                u64 v = poly[idx & (N - 1)];
+                if (idx & N) v = 0 - v;
+                t = v - poly[i];
+            } else {
+                t = poly[i];
+            }
+            t += off;
+#pragma unroll
+            for (int q = 0; q < L; q++) packed[q] |= ((u32)(t >> (64 - (q + 1) * bgbit)) & dmask) << (8 * b);
+        }
+        const int src = 1 - c;   // src 0 = body = acc[1]
+#pragma unroll
+        for (int q = 0; q < L; q++) dig[(src * L + q) * 256 + j] = packed[q];
+    }
+}
+
+// One external product (tgsw_extern_mul_3gen, tgsw_3gen.jl:102-113) on the accumulator held in shared memory, by the 192 threads of a gate.
+//   MUX = true : acc += ExtProd(X^a * acc - acc, key)   (mk_mux_rotate_3gen, 3gen_mk_internals.jl:59-62)
+//   MUX = false: acc  = ExtProd(acc, key)
+// spec: 2L digit spectra [512]; ybuf: 6 limb-output buffers [512] (== spec when ALIAS); key: this element, FFT layout.
+template <int L, bool MUX>
+__device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restrict__ dig, cpx* __restrict__ spec, cpx* __restrict__ ybuf,
+                                             const cpx* __restrict__ tw, const cpx* __restrict__ key, int a, int bgbit, int bar_id, int gtid) {
+    constexpr bool ALIAS = alias_for(L);
+    const int gw = gtid >> 5, lane = gtid & 31;
+    decompose<L, MUX>(acc, dig, a, bgbit, gtid);
+    mk::gate_barrier<WPG>(bar_id);
+    // ---- forward transforms of the 2L digit polynomials
+#pragma unroll 1
+    for (int s = gw; s < 2 * L; s += WPG) {
+        cpx v[16];
+        fwd_stage0_digits(v, dig + s * 256, lane, 1 << (bgbit - 1));
+        fwd_passA(v, tw, lane >> 4);
+        rows_to_cols(v, ALIAS ? spec + s * M : ybuf + gw * M, lane);
+        fwd_passB(v, tw, lane);
+#pragma unroll
+        for (int c = 0; c < 16; c++) spec[s * M + c * 32 + lane] = v[c];
+    }
+    mk::gate_barrier<WPG>(bar_id);
+    // ---- warp (limb, out): multiply-accumulate over the 2L spectra, inverse transform up to the last stage
+    {
+        const int limb = gw >> 1, out = gw & 1;
+        cpx v[16];
+#pragma unroll
+        for (int c = 0; c < 16; c++) v[c] = cpx{0.0, 0.0};
+        const double2* kp = reinterpret_cast<const double2*>(key) + ((size_t)out * LIMBS + limb) * M + lane;   // [s][out][limb][512]
+#pragma unroll 1
+        for (int s = 0; s < 2 * L; s++) {
+            const double2* ks = kp + (size_t)s * (2 * LIMBS * M);
+            const cpx* xs = spec + s * M + lane;
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                const double2 k = __ldg(ks + c * 32);
+                const cpx x = xs[c * 32];
+                v[c].x = fma(x.x, k.x, fma(-x.y, k.y, v[c].x));
+                v[c].y = fma(x.x, k.y, fma(x.y, k.x, v[c].y));
+            }
+        }
+        if (ALIAS) mk::gate_barrier<WPG>(bar_id);            // every warp is done reading the spectra
+        inv_passB(v);
+        cols_to_rows(v, ybuf + gw * M, lane);
+        inv_passA(v, tw, lane & 15);
+        const int h = lane >> 4, l16 = lane & 15;
+#pragma unroll
+        for (int r = 0; r < 16; r++) ybuf[gw * M + h * 256 + r * 16 + l16] = v[r];
+    }
+    mk::gate_barrier<WPG>(bar_id);
+    // ---- last inverse stage, untwist, rounding, limb recombination, accumulator update: task (out, j) -> coefficients j + 256 b
+    {
+        const double MAGIC = 6755399441055744.0;             // 1.5 * 2^52: bits(r + MAGIC) - bits(MAGIC) = rint(r) for |r| < 2^51
+        const u64 MAGIC_BITS = 0x4338000000000000ull;
+        const u64 K = MAGIC_BITS + (MAGIC_BITS << LIMB_SHIFT1) + (MAGIC_BITS << LIMB_SHIFT2);
+        for (int task = gtid; task < 512; task += TPG) {
+            const int out = task >> 8, j = task & 255;
+            const cpx wj = tw[T_WJ + j], ut = tw[T_UT + j], ut2 = tw[T_UT2 + j];
+            u64 R[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int limb = 0; limb < LIMBS; limb++) {
+                const cpx* Y = ybuf + (limb * 2 + out) * M;
+                cpx lo = Y[j], hi = Y[j + 256];
+                ct(lo, hi, wj);
+                const cpx e = cmul(lo, ut), f = cmul(hi, ut2);
+                const int sh = limb == 0 ? 0 : limb == 1 ? LIMB_SHIFT1 : LIMB_SHIFT2;
+                R[0] += (u64)__double_as_longlong(e.x + MAGIC) << sh;     // coefficient j
+                R[1] += (u64)__double_as_longlong(f.x + MAGIC) << sh;     // j + 256
+                R[2] += (u64)__double_as_longlong(e.y + MAGIC) << sh;     // j + 512
+                R[3] += (u64)__double_as_longlong(f.y + MAGIC) << sh;     // j + 768
+            }
+            u64* ap = acc + out * N + j;
+#pragma unroll
+            for (int b = 0; b < 4; b++) ap[256 * b] = (MUX ? ap[256 * b] : 0) + (R[b] - K);
+        }
+    }
+    mk::gate_barrier<WPG>(bar_id);
+}
+
+// GPC gates per CTA, six warps per gate; prologue, k n steps, extraction and key switch as in mk::blind_rotate_body
+template <int L, int GPC>
+__device__ __forceinline__ void blind_rotate_body(const mk::BlindRotateArgs& p, const cpx* __restrict__ key_fft, const cpx* __restrict__ tw_g) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cpx* tw = reinterpret_cast<cpx*>(smem_raw);
+    stage_tables(tw, tw_g);
+    __syncthreads();
+    const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot;
+    const int g = p.g0 + blockIdx.x * GPC + slot;
+    if (g >= p.G) return;   // no CTA-wide barrier below this line
+    unsigned char* base = smem_raw + TW_BYTES + (size_t)slot * gate_bytes(L);
+    u64* acc = reinterpret_cast<u64*>(base);
+    u32* dig = reinterpret_cast<u32*>(base + 2 * N * 8);
+    cpx* spec = reinterpret_cast<cpx*>(base + 2 * N * 8 + 2 * L * N);
+    cpx* ybuf = alias_for(L) ? spec : spec + 2 * L * M;
+    const int kn = p.k * p.n;
+    const mk::GateLinear lin = p.gate_ids ? mk::gate_linear(__ldg(p.gate_ids + g)) : p.lin;
+    uint32_t tb = (uint32_t)lin.mu0 + (uint32_t)lin.cx * (uint32_t)__ldg(p.xb + g);
+    if (lin.cy) tb += (uint32_t)lin.cy * (uint32_t)__ldg(p.yb + g);
+    if (lin.cz) tb += (uint32_t)lin.cz * (uint32_t)__ldg(p.zb + g);
+    const int barb = mk::mod_switch_2N((int32_t)tb);
+    // acc = (0, X^{-barb} * testvect), testvect = mu * (1 + X + ... + X^{N-1})  (3gen_mk_internals.jl:88-92, rlwe.jl:113-119)
+    {
+        const int s = (-barb) & (2 * N - 1);
+        for (int i = gtid; i < N; i += TPG) {
+            const int idx = (i - s) & (2 * N - 1);
+            acc[i] = 0;
+            acc[N + i] = (idx & N) ? (u64)0 - (u64)p.mu : (u64)p.mu;
+        }
+    }
+    mk::gate_barrier<WPG>(bar_id);
+    const size_t estride = bsk_elem_cpx(L);
+    const size_t abase = (size_t)g * kn;
+    int32_t rx = __ldg(p.xa + abase), ry = lin.cy ? __ldg(p.ya + abase) : 0, rz = lin.cz ? __ldg(p.za + abase) : 0;
+    for (int it = 0; it < kn; it++) {
+        const int a = mk::mod_switch_2N((int32_t)((uint32_t)lin.cx * (uint32_t)rx + (uint32_t)lin.cy * (uint32_t)ry + (uint32_t)lin.cz * (uint32_t)rz));
+        if (it + 1 < kn) {
+            rx = __ldg(p.xa + abase + it + 1);
+            if (lin.cy) ry = __ldg(p.ya + abase + it + 1);
+            if (lin.cz) rz = __ldg(p.za + abase + it + 1);
+        }
+        if (a == 0) continue;   // 3gen_mk_internals.jl:69 (uniform across the gate)
+        extprod_step<L, true>(acc, dig, spec, ybuf, tw, key_fft + (size_t)it * estride, a, p.bgbit, bar_id, gtid);
+    }
+    if (p.acc_out) {
+        int64_t* ao = p.acc_out + (size_t)g * 2 * N;
+        for (int i = gtid; i < 2 * N; i += TPG) ao[i] = (int64_t)acc[i];
+    }
+    if (p.ksk) {   // fused extraction + key switch (the host only sets ksk when mk::ks_fusable(n, t)); scratch: the spectra
+        if (p.ks_t == 3) mk::fused_keyswitch<3, WPG>(acc, reinterpret_cast<u32*>(spec), p, g, gtid, bar_id);
+        else mk::fused_keyswitch<5, WPG>(acc, reinterpret_cast<u32*>(spec), p, g, gtid, bar_id);
+        return;
+    }
+    int32_t* ext = p.ext_out + (size_t)g * (N + 1);
+    for (int i = gtid; i < N; i += TPG) {
+        const u64 v = i == 0 ? acc[0] : (u64)0 - acc[N - i];
+        ext[i] = mk::t64tot32((int64_t)v);
+    }
+    if (gtid == 0) ext[N] = mk::t64tot32((int64_t)acc[N]);
+}
+
+#ifndef MKF_MAXNREG
+#define MKF_MAXNREG 168
+#endif
+template <int L, int GPC>
+__global__ void __maxnreg__(MKF_MAXNREG) blind_rotate_fft_kernel(mk::BlindRotateArgs p, const cpx* __restrict__ key_fft, const cpx* __restrict__ tw_g) {
+    blind_rotate_body<L, GPC>(p, key_fft, tw_g);
+}
+
+// parity hook: acc_out[g] = ExtProd(acc_in[g], key[elem[g]])
+template <int L, int GPC>
+__global__ void __maxnreg__(MKF_MAXNREG) extprod_fft_kernel(int G, const cpx* __restrict__ key_fft, const cpx* __restrict__ tw_g, int bgbit,
+                                                             const int32_t* __restrict__ elem, const int64_t* __restrict__ acc_in, int64_t* __restrict__ acc_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cpx* tw = reinterpret_cast<cpx*>(smem_raw);
+    stage_tables(tw, tw_g);
+    __syncthreads();
+    const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot;
+    const int g = blockIdx.x * GPC + slot;
+    if (g >= G) return;
+    unsigned char* base = smem_raw + TW_BYTES + (size_t)slot * gate_bytes(L);
+    u64* acc = reinterpret_cast<u64*>(base);
+    u32* dig = reinterpret_cast<u32*>(base + 2 * N * 8);
+    cpx* spec = reinterpret_cast<cpx*>(base + 2 * N * 8 + 2 * L * N);
+    cpx* ybuf = alias_for(L) ? spec : spec + 2 * L * M;
+    for (int i = gtid; i < 2 * N; i += TPG) acc[i] = (u64)acc_in[(size_t)g * 2 * N + i];
+    mk::gate_barrier<WPG>(bar_id);
+    extprod_step<L, false>(acc, dig, spec, ybuf, tw, key_fft + (size_t)elem[g] * bsk_elem_cpx(L), 0, bgbit, bar_id, gtid);
+    for (int i = gtid; i < 2 * N; i += TPG) acc_out[(size_t)g * 2 * N + i] = (int64_t)acc[i];
+}
+
+// One warp per (key polynomial, limb): raw int64 key -> spectrum of the limb, scaled by 1 / 512, in the FFT layout.
+// raw: [n][4 parts][l][N] int64 of one party; task = ((j*4 + part)*l + q)*3 + limb.
+constexpr int XF_WARPS = 4;
+__global__ void __launch_bounds__(XF_WARPS * 32) bsk_transform_fft_kernel(const int64_t* __restrict__ raw, cpx* __restrict__ bsk, int n, int l, int party,
+                                                                            const cpx* __restrict__ tw_g, int ntasks) {
+    __shared__ cpx bufs[XF_WARPS * M];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int task = blockIdx.x * XF_WARPS + warp;
+    if (task >= ntasks) return;
+    const int limb = task % LIMBS, pq = task / LIMBS;
+    const int q = pq % l, part = (pq / l) & 3, j = pq / (4 * l);
+    // part_1: body<-body, part_2: body<-mask, part_3: mask<-mask, part_4: mask<-body  (tgsw_3gen.jl:109-110)
+    const int out = part < 2 ? 1 : 0;
+    const int src = (part == 0 || part == 3) ? 0 : 1;
+    const int64_t* poly = raw + (size_t)pq * N;
+    const int h = lane >> 4, l16 = lane & 15;
+    auto limb_of = [&](int64_t k) -> double {
+        const int64_t l0 = ((k + (1ll << (LIMB_BITS0 - 1))) & ((1ll << LIMB_BITS0) - 1)) - (1ll << (LIMB_BITS0 - 1));
+        const int64_t k1 = (int64_t)((u64)k - (u64)l0) >> LIMB_BITS0;
+        const int64_t l1 = ((k1 + (1ll << (LIMB_BITS1 - 1))) & ((1ll << LIMB_BITS1) - 1)) - (1ll << (LIMB_BITS1 - 1));
+        const int64_t l2 = (k1 - l1) >> LIMB_BITS1;
+        return (double)(limb == 0 ? l0 : limb == 1 ? l1 : l2);
+    };
+    cpx v[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const int jj = 16 * r + l16;
+        v[r] = fwd_stage0_real(limb_of(poly[jj]), limb_of(poly[jj + 256]), limb_of(poly[jj + 512]), limb_of(poly[jj + 768]), h);
+    }
+    fwd_passA(v, tw_g, h);
+    rows_to_cols(v, bufs + warp * M, lane);
+    fwd_passB(v, tw_g, lane);
+    const size_t e = (size_t)party * n + j;
+    cpx* dst = bsk + e * bsk_elem_cpx(l) + (((size_t)(src * l + q) * 2 + out) * LIMBS + limb) * M;
+#pragma unroll
+    for (int c = 0; c < 16; c++) dst[c * 32 + lane] = cpx{v[c].x * (1.0 / M), v[c].y * (1.0 / M)};
+}
+
+}  // namespace mkf

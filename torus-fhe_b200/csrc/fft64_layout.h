@@ -1,0 +1,33 @@
+// fft64_layout.h -- constants of the FP64 FFT channel shared by the kernels (fft64.cuh) and the host table generator (tables_fft.h).
+#pragma once
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define MKF_HD __host__ __device__
+#else
+#define MKF_HD
+#endif
+
+namespace mkf {
+
+constexpr int N = 1024;        // ring degree (real negacyclic polynomials mod X^N + 1)
+constexpr int M = 512;         // complex points: C[X] / (X^M - i), a~[j] = a[j] + i a[j + M]
+constexpr int LIMBS = 3;       // a Torus64 key word = l0 + l1 2^22 + l2 2^43, balanced limbs of 22 / 21 / 21 bits
+constexpr int LIMB_BITS0 = 22, LIMB_BITS1 = 21;
+constexpr int LIMB_SHIFT1 = 22, LIMB_SHIFT2 = 43;
+
+// twiddle table, complex-double entries (staged in shared memory by the kernels)
+constexpr int TF_A = 0;                 // forward stages d = 1..4 (warp-half-uniform): TF_A + 2^d - 2 + g, g = group = pos >> (9 - d)
+constexpr int TF_B = 32;                // forward stages d = 5..8 (per lane): TF_B + 32 (2^(d-5) - 1) + sub 32 + lane, g = lane 2^(d-5) + sub
+constexpr int TI_A = TF_B + 480;        // inverse pass A', row span rs = 1, 2, 4, 8: TI_A + 16 (rs - 1) + (r mod rs) 16 + l16
+constexpr int T_WJ = TI_A + 240;        // last inverse stage: exp(-2 pi i j / 512), j < 256
+constexpr int T_UT = T_WJ + 256;        // untwist zeta^-j
+constexpr int T_UT2 = T_UT + 256;       // untwist zeta^-(j + 256)
+constexpr int T_ENTRIES = T_UT2 + 256;  // 1520 entries = 24 320 bytes
+constexpr int TW_BYTES = T_ENTRIES * 16;
+
+// bootstrapping key in the FFT layout: complex double [elem][s = src l + q][out 2][limb 3][512 points], point (c, lane) at c 32 + lane
+// (c = register index, lane = thread of the transform's output layout); values forward(fold(limb)) / 512
+MKF_HD inline constexpr size_t bsk_elem_cpx(int l) { return (size_t)2 * l * 2 * LIMBS * M; }
+
+}  // namespace mkf

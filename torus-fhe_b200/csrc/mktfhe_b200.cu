@@ -19,6 +19,8 @@
 #include "../../include/mktfhe_b200.h"
 #include "kernels.cuh"
 #include "kernels2k.cuh"
+#include "fft64.cuh"
+#include "tables_fft.h"
 #include "tables2048.h"
 #include "tables.h"
 
@@ -45,6 +47,12 @@ struct mktfhe_ctx {
     int32_t* d_ksk = nullptr;
     size_t ksk_bytes = 0;
     rns::uint2_* d_twB = nullptr;
+    // FP64 FFT channel (fft64.cuh; N = 1024, Torus64, byte digits): a second copy of the bootstrapping key as limb spectra, stored behind the
+    // NTT layout in the same allocation (d_bsk .. d_bsk + bsk_bytes covers both, so key broadcasts move both); serves the throughput launch
+    bool fft = false;
+    size_t bsk_ntt_bytes = 0;    // size of the NTT-layout part
+    mkf::cpx* d_bsk_fft = nullptr;
+    mkf::cpx* d_twF = nullptr;
     int gpc = 1;                 // gates per CTA of the blind-rotate / external-product kernels
     int num_sms = 0;
     bool split_tail = true;      // MKTFHE_B200_SPLIT_TAIL=0: no separate one-gate-per-CTA launch for the tail of a large batch (A/B)
@@ -161,6 +169,16 @@ size_t br_smem_bytes(const mktfhe_ctx* c) { return mk::cta_smem_bytes(c->prm.l, 
     default: KERNEL(4, mk::gpc_for(4, true), __VA_ARGS__); break;                \
     }
 
+// FFT-channel instantiations: mkf::gpc_for(l) gates per CTA
+#define MK_DISPATCH_FFT(c, KERNEL, ...)                                     \
+    switch ((c)->prm.l) {                                                   \
+    case 1: KERNEL(1, mkf::gpc_for(1), __VA_ARGS__); break;                 \
+    case 2: KERNEL(2, mkf::gpc_for(2), __VA_ARGS__); break;                 \
+    case 3: KERNEL(3, mkf::gpc_for(3), __VA_ARGS__); break;                 \
+    default: KERNEL(4, mkf::gpc_for(4), __VA_ARGS__); break;                \
+    }
+size_t fft_smem_bytes(const mktfhe_ctx* c) { return mkf::cta_bytes(c->prm.l, mkf::gpc_for(c->prm.l)); }
+
 int set_attrs(mktfhe_ctx* c) {
     if (c->prm.N == mk2k::N) {
         if (c->prm.l == 1) CU_TRY(c, cudaFuncSetAttribute(mk2k::blind_rotate2k_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk2k::smem_bytes(1)));
@@ -178,6 +196,14 @@ int set_attrs(mktfhe_ctx* c) {
         MK_DISPATCH_T32(c, SET_ATTR_T32, 0)
 #undef SET_ATTR_T32
         return MKTFHE_OK;
+    }
+    if (c->fft) {
+        const int smf = (int)fft_smem_bytes(c);
+#define SET_ATTR_FFT(L, GPC, dummy)                                                                                                \
+    CU_TRY(c, cudaFuncSetAttribute(mkf::blind_rotate_fft_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));       \
+    CU_TRY(c, cudaFuncSetAttribute(mkf::extprod_fft_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));
+        MK_DISPATCH_FFT(c, SET_ATTR_FFT, 0)
+#undef SET_ATTR_FFT
     }
 #define SET_ATTR(L, GPC, dummy)                                                                                                    \
     CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));             \
@@ -233,8 +259,9 @@ void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G, 
         c->launches++;
         return;
     }
-    const size_t wave = (size_t)c->gpc * (size_t)c->num_sms;
-    size_t tail = c->gpc > 1 ? G % wave : 0;
+    const int gpc = c->fft ? mkf::gpc_for(c->prm.l) : c->gpc;
+    const size_t wave = (size_t)gpc * (size_t)c->num_sms;
+    size_t tail = gpc > 1 ? G % wave : 0;
     // the tail of a larger batch is split off only at l = 2, where it was measured to pay on two workloads; at l = 3 the split lost 1.2 %
     // (the partial last wave of the throughput grid cost 3 ms there, not a full wave), profiles/ab_r1.txt
     if (tail > (size_t)c->num_sms || ((!c->split_tail || c->prm.l != 2) && tail != G)) tail = 0;
@@ -242,11 +269,18 @@ void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G, 
     if (head) {
         mk::BlindRotateArgs h = a;
         h.g0 = 0; h.G = (int)head;
-        const size_t sm = br_smem_bytes(c);
-        const unsigned grid = (unsigned)((head + c->gpc - 1) / c->gpc);
+        const unsigned grid = (unsigned)((head + gpc - 1) / gpc);
+        if (c->fft) {   // throughput launch on the FP64 FFT channel
+            const size_t smf = fft_smem_bytes(c);
+#define LAUNCH_BR_FFT(L, GPC, dummy) mkf::blind_rotate_fft_kernel<L, GPC><<<grid, GPC * mkf::TPG, smf, st>>>(h, c->d_bsk_fft, c->d_twF)
+            MK_DISPATCH_FFT(c, LAUNCH_BR_FFT, 0)
+#undef LAUNCH_BR_FFT
+        } else {
+            const size_t sm = br_smem_bytes(c);
 #define LAUNCH_BR(L, GPC, dummy) mk::blind_rotate_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, st>>>(h)
-        MK_DISPATCH_L(c, LAUNCH_BR, 0)
+            MK_DISPATCH_L(c, LAUNCH_BR, 0)
 #undef LAUNCH_BR
+        }
         c->launches++;
     }
     if (tail) launch_one_gate_per_cta(c, a, head, G, st);
@@ -502,6 +536,11 @@ int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
     const bool big = params->N == mk2k::N;
     c->bsk_bytes = (size_t)params->k * params->n * (big ? mk2k::bsk_elem_words(params->l) : mk::bsk_elem_words(params->l)) * sizeof(u32);
     c->t32 = !big && (params->reserved & MKTFHE_FLAG_TORUS32);
+    c->bsk_ntt_bytes = c->bsk_bytes;
+    // FP64 FFT channel: N = 1024, Torus64 keys, byte digits; exact while 2 l N (Bg / 2) 2^21 <= 2^40 (limb products recovered by rounding)
+    c->fft = !big && !c->t32 && std::log2((double)(2 * params->l) * params->N) + (params->bgbit - 1) + 21.0 <= 40.0;
+    if (const char* e = getenv("MKTFHE_B200_FFT")) c->fft = c->fft && atoi(e) != 0;
+    if (c->fft) c->bsk_bytes += (size_t)params->k * params->n * mkf::bsk_elem_cpx(params->l) * sizeof(mkf::cpx);
     c->gpc = big ? 1 : mk::gpc_for(params->l, c->t32);
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
     if (const char* e = getenv("MKTFHE_B200_LATENCY")) c->latency_kernel = atoi(e) != 0;
@@ -511,6 +550,12 @@ int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
     const size_t ks_stride = mk::ks_row_stride(params->n);   // rows padded to 16 bytes on the device
     c->ksk_bytes = (size_t)params->k * params->N * params->t * B1 * ks_stride * sizeof(int32_t);
     CREATE_TRY(cudaMalloc(&c->d_bsk, c->bsk_bytes));
+    if (c->fft) {
+        c->d_bsk_fft = reinterpret_cast<mkf::cpx*>(reinterpret_cast<char*>(c->d_bsk) + c->bsk_ntt_bytes);
+        mkf::HostTablesFFT TF;
+        CREATE_TRY(cudaMalloc(&c->d_twF, (size_t)mkf::TW_BYTES));
+        CREATE_TRY(cudaMemcpy(c->d_twF, TF.tw.data(), (size_t)mkf::TW_BYTES, cudaMemcpyHostToDevice));
+    }
     // the key-switching key is followed by one all-zero row (read by the fused key switch for zero digits)
     CREATE_TRY(cudaMalloc(&c->d_ksk, c->ksk_bytes + ks_stride * sizeof(int32_t)));
     CREATE_TRY(cudaMemset(c->d_ksk, 0, c->ksk_bytes + ks_stride * sizeof(int32_t)));
@@ -543,6 +588,7 @@ void mktfhe_destroy(mktfhe_ctx* c) {
     if (c->d_bsk) cudaFree(c->d_bsk);
     if (c->d_ksk) cudaFree(c->d_ksk);
     if (c->d_twB) cudaFree(c->d_twB);
+    if (c->d_twF) cudaFree(c->d_twF);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -567,6 +613,12 @@ int mktfhe_load_bsk(mktfhe_ctx* c, int party, const int64_t* polys) {
         const int ntasks = n * 4 * l * rns::NP;
         mk::bsk_transform_kernel<<<(ntasks + mk::XF_WARPS - 1) / mk::XF_WARPS, mk::XF_WARPS * 32, 0, c->stream>>>(
             (const int64_t*)c->raw.p, c->d_bsk, n, l, party, c->d_twB, ntasks);
+        if (c->fft) {
+            const int nt = n * 4 * l * mkf::LIMBS;
+            mkf::bsk_transform_fft_kernel<<<(nt + mkf::XF_WARPS - 1) / mkf::XF_WARPS, mkf::XF_WARPS * 32, 0, c->stream>>>(
+                (const int64_t*)c->raw.p, c->d_bsk_fft, n, l, party, c->d_twF, nt);
+            c->launches++;
+        }
     }
     c->launches++;
     CU_TRY(c, cudaGetLastError());
@@ -833,6 +885,15 @@ static int mktfhe_extprod_batch_1(mktfhe_ctx* c, size_t G, const int32_t* elem, 
                                                                            (const int64_t*)c->accin.p, (int64_t*)c->accout.p)
         MK_DISPATCH_T32(c, LAUNCH_EP_T32, 0)
 #undef LAUNCH_EP_T32
+    } else if (c->fft) {
+        const size_t smf = fft_smem_bytes(c);
+        const int gf = mkf::gpc_for(c->prm.l);
+        const unsigned gridf = (unsigned)((G + gf - 1) / gf);
+#define LAUNCH_EP_FFT(L, GPC, dummy)                                                                                                      \
+    mkf::extprod_fft_kernel<L, GPC><<<gridf, GPC * mkf::TPG, smf, c->stream>>>((int)G, c->d_bsk_fft, c->d_twF, c->prm.bgbit, (const int32_t*)c->elem.p, \
+                                                                                (const int64_t*)c->accin.p, (int64_t*)c->accout.p)
+        MK_DISPATCH_FFT(c, LAUNCH_EP_FFT, 0)
+#undef LAUNCH_EP_FFT
     } else {
 #define LAUNCH_EP(L, GPC, dummy)                                                                                          \
     mk::extprod_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, c->stream>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, (const int32_t*)c->elem.p, \
@@ -1166,6 +1227,7 @@ int mktfhe_describe(const mktfhe_ctx* c, char* buf, size_t cap) {
     for (size_t r = 0; r < n_replicas(c); r++) d += (r ? ", " : "") + std::to_string(replica(const_cast<mktfhe_ctx*>(c), r)->device);
     d += "], \"key_broadcast\": \"" + (c->kids.empty() ? std::string("none") : (c->bcast_how.empty() ? std::string("pending") : c->bcast_how)) + "\"";
     d += ", \"keyswitch_fused\": " + std::string(c->last_fused ? "true" : "false");
+    d += ", \"external_product\": \"" + std::string(c->fft ? "fft64" : "ntt_rns") + "\"";
     d += ", \"gates_per_cta\": " + std::to_string(c->gpc) + ", \"sms\": " + std::to_string(c->num_sms);
     d += ", \"bsk_bytes\": " + std::to_string(c->bsk_bytes) + ", \"ksk_bytes\": " + std::to_string(c->ksk_bytes) + "}";
     snprintf(buf, cap, "%s", d.c_str());
