@@ -13,6 +13,8 @@ BUSY = float(sys.argv[3]) if len(sys.argv) > 3 else None
 hdr = rows[1]
 body = [r for r in rows[2:] if len(r) >= len(hdr)]
 iS, iE, iSamp = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
+# binding math pipe: IMAD for the NTT kernels; "fp64" as 4th argument counts DFMA / DADD / DMUL instead (FFT-channel kernels)
+MATH = ("DFMA", "DADD", "DMUL") if len(sys.argv) > 4 and sys.argv[4] == "fp64" else ("IMAD", "UIMAD")
 stall_cols = [(i, h[6:]) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 
 
@@ -40,7 +42,7 @@ for (a, b, op, e) in segs:
     d = dict(samples=0, inst=0, fma=0, alu=0, lsu=0, stalls=collections.Counter())
     for r in body[a + 1:b + 1]:
         o = opcode(r[iS]); ex = int(r[iE] or 0); d["samples"] += int(r[iSamp] or 0); d["inst"] += ex
-        if o.startswith(("IMAD", "UIMAD")):
+        if o.startswith(MATH):
             d["fma"] += ex * (2 if o.startswith(("IMAD.HI", "IMAD.WIDE")) else 1)
         elif o.startswith(("LDS", "STS", "LDG", "STG")):
             d["lsu"] += ex
@@ -50,7 +52,7 @@ for (a, b, op, e) in segs:
             d["stalls"][name] += int(r[i] or 0)
     tot_f += d["fma"]
     out.append((a, b, op, e, d))
-allf = sum(int(r[iE] or 0) * (2 if opcode(r[iS]).startswith(("IMAD.HI", "IMAD.WIDE")) else 1) for r in body if opcode(r[iS]).startswith(("IMAD", "UIMAD")))
+allf = sum(int(r[iE] or 0) * (2 if opcode(r[iS]).startswith(("IMAD.HI", "IMAD.WIDE")) else 1) for r in body if opcode(r[iS]).startswith(MATH))
 print(f"samples {tot_s}; fma slots {allf / GS:.0f} per gate-step (main loop {tot_f / GS:.0f}); fmaheavy busy {BUSY} %")
 print(f"{'sass idx':>11s} {'ends with':22s} {'time%':>6s} {'inst/gs':>8s} {'fma/gs':>8s} {'alu/gs':>8s} {'lsu/gs':>7s} {'pipe%':>6s}  stalls")
 for (a, b, op, e, d) in out:

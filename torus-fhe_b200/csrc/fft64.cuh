@@ -116,28 +116,65 @@ __device__ __forceinline__ void fwd_passA(cpx (&v)[16], const cpx* __restrict__ 
         ct(v[2 * g], v[2 * g + 1], w);
     }
 }
-// forward stages 5..8 in the column layout (register c = position bits 3..0), per-lane twiddles
+// forward stages 5..8 in the column layout (register c = position bits 3..0), per-lane twiddles.
+// s(d, g), g = lane 2^(d-5) + sub, factors as s(d, lane 2^(d-5)) * exp(i pi rev(sub) / 2^(d-5)): one table load per stage (the sub = 0 entry)
+// and compile-time constants (MKF_TW_COMPUTE; 0 loads all 15 twiddles from the table) -- the load/store pipe, not the FP64 pipe, binds this kernel
+#ifndef MKF_TW_COMPUTE
+#define MKF_TW_COMPUTE 1
+#endif
+__device__ __forceinline__ cpx mul_i(const cpx a) { return {-a.y, a.x}; }
 __device__ __forceinline__ void fwd_passB(cpx (&v)[16], const cpx* __restrict__ tw, int lane) {
     {
         const cpx w = tw[TF_B + lane];
 #pragma unroll
         for (int c = 0; c < 8; c++) ct(v[c], v[c + 8], w);
     }
+#if MKF_TW_COMPUTE
+    // (computing all fourteen before the first use is what ptxas allocates best: interleaving them with the butterflies cost 4 %)
+    constexpr double C1 = 0.92387953251128675613, S1 = 0.38268343236508977173;   // cos, sin of pi / 8
+    cpx w6[2], w7[4], w8[8];
+    w6[0] = tw[TF_B + 32 + lane];
+    w6[1] = mul_i(w6[0]);
+    w7[0] = tw[TF_B + 96 + lane];
+    w7[1] = mul_i(w7[0]);                                    // rev2(1) = 2: exp(i pi / 2)
+    w7[2] = cmul(w7[0], cpx{INV_SQRT2, INV_SQRT2});          // rev2(2) = 1: exp(i pi / 4)
+    w7[3] = mul_i(w7[2]);                                    // rev2(3) = 3
+    w8[0] = tw[TF_B + 224 + lane];
+    w8[4] = cmul(w8[0], cpx{C1, S1});                        // rev3(4) = 1: exp(i pi / 8)
+    w8[2] = cmul(w8[0], cpx{INV_SQRT2, INV_SQRT2});          // rev3(2) = 2
+    w8[6] = cmul(w8[0], cpx{S1, C1});                        // rev3(6) = 3: exp(3 i pi / 8)
+    w8[1] = mul_i(w8[0]);                                    // rev3(1) = 4
+    w8[5] = mul_i(w8[4]);                                    // rev3(5) = 5
+    w8[3] = mul_i(w8[2]);                                    // rev3(3) = 6
+    w8[7] = mul_i(w8[6]);                                    // rev3(7) = 7
+#endif
 #pragma unroll
     for (int g = 0; g < 2; g++) {
+#if MKF_TW_COMPUTE
+        const cpx w = w6[g];
+#else
         const cpx w = tw[TF_B + 32 + g * 32 + lane];
+#endif
 #pragma unroll
         for (int c = 0; c < 4; c++) ct(v[8 * g + c], v[8 * g + c + 4], w);
     }
 #pragma unroll
     for (int g = 0; g < 4; g++) {
+#if MKF_TW_COMPUTE
+        const cpx w = w7[g];
+#else
         const cpx w = tw[TF_B + 96 + g * 32 + lane];
+#endif
 #pragma unroll
         for (int c = 0; c < 2; c++) ct(v[4 * g + c], v[4 * g + c + 2], w);
     }
 #pragma unroll
     for (int g = 0; g < 8; g++) {
+#if MKF_TW_COMPUTE
+        const cpx w = w8[g];
+#else
         const cpx w = tw[TF_B + 224 + g * 32 + lane];
+#endif
         ct(v[2 * g], v[2 * g + 1], w);
     }
 }
@@ -241,40 +278,130 @@ __device__ __forceinline__ void decompose(const u64* __restrict__ acc, u32* __re
     }
 }
 
-// One external product (tgsw_extern_mul_3gen, tgsw_3gen.jl:102-113) on the accumulator held in shared memory, by the 192 threads of a gate.
+// ---- phases of one external product (tgsw_extern_mul_3gen, tgsw_3gen.jl:102-113) on the accumulator held in shared memory -----------------
 //   MUX = true : acc += ExtProd(X^a * acc - acc, key)   (mk_mux_rotate_3gen, 3gen_mk_internals.jl:59-62)
 //   MUX = false: acc  = ExtProd(acc, key)
-// spec: 2L digit spectra [512]; ybuf: 6 limb-output buffers [512] (== spec when ALIAS); key: this element, FFT layout.
-template <int L, bool MUX>
-__device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restrict__ dig, cpx* __restrict__ spec, cpx* __restrict__ ybuf,
-                                             const cpx* __restrict__ tw, const cpx* __restrict__ key, int a, int bgbit, int bar_id, int gtid) {
-    constexpr bool ALIAS = alias_for(L);
-    const int gw = gtid >> 5, lane = gtid & 31;
-    decompose<L, MUX>(acc, dig, a, bgbit, gtid);
-    mk::gate_barrier<WPG>(bar_id);
-    // ---- forward transforms of the 2L digit polynomials
+// Per gate: spec = 2L digit spectra [512], ybuf = 6 limb-output buffers [512] (== spec when ALIAS), index lo = 2 limb + out.
+
+// forward transforms of the 2L digit polynomials by the warps gw = s, s + 6, ..; spectrum point (c, lane) at c 32 + lane
+template <int L>
+__device__ __forceinline__ void forward_phase(const u32* __restrict__ dig, cpx* __restrict__ spec, cpx* __restrict__ ybuf, const cpx* __restrict__ tw,
+                                              int bgbit, int gw, int lane) {
 #pragma unroll 1
     for (int s = gw; s < 2 * L; s += WPG) {
         cpx v[16];
         fwd_stage0_digits(v, dig + s * 256, lane, 1 << (bgbit - 1));
         fwd_passA(v, tw, lane >> 4);
-        rows_to_cols(v, ALIAS ? spec + s * M : ybuf + gw * M, lane);
+        rows_to_cols(v, alias_for(L) ? spec + s * M : ybuf + gw * M, lane);
         fwd_passB(v, tw, lane);
 #pragma unroll
         for (int c = 0; c < 16; c++) spec[s * M + c * 32 + lane] = v[c];
     }
+}
+// inverse transform of the 16 spectrum points of this thread up to the last stage; result in natural position order in buf
+__device__ __forceinline__ void inverse_to_buffer(cpx (&v)[16], cpx* __restrict__ buf, const cpx* __restrict__ tw, int lane) {
+    inv_passB(v);
+    cols_to_rows(v, buf, lane);
+    inv_passA(v, tw, lane & 15);
+    const int h = lane >> 4, l16 = lane & 15;
+#pragma unroll
+    for (int r = 0; r < 16; r++) buf[h * 256 + r * 16 + l16] = v[r];
+}
+// last inverse stage, untwist, rounding, limb recombination, accumulator update: task (out, j) -> coefficients j + 256 b
+template <bool MUX>
+__device__ __forceinline__ void recombine_phase(u64* __restrict__ acc, const cpx* __restrict__ ybuf, const cpx* __restrict__ tw, int gtid) {
+    const double MAGIC = 6755399441055744.0;             // 1.5 * 2^52: bits(r + MAGIC) - bits(MAGIC) = rint(r) for |r| < 2^51
+    const u64 MAGIC_BITS = 0x4338000000000000ull;
+    const u64 K = MAGIC_BITS + (MAGIC_BITS << LIMB_SHIFT1) + (MAGIC_BITS << LIMB_SHIFT2);
+    for (int task = gtid; task < 512; task += TPG) {
+        const int out = task >> 8, j = task & 255;
+        const cpx wj = tw[T_WJ + j], ut = tw[T_UT + j];
+#if !MKF_TW_COMPUTE
+        const cpx ut2 = tw[T_UT2 + j];
+#endif
+        u64 R[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int limb = 0; limb < LIMBS; limb++) {
+            const cpx* Y = ybuf + (limb * 2 + out) * M;
+            cpx lo = Y[j], hi = Y[j + 256];
+            ct(lo, hi, wj);
+#if MKF_TW_COMPUTE
+            const cpx e = cmul(lo, ut), g8 = cmul(hi, ut);      // zeta^-(j + 256) = zeta^-j exp(-i pi / 4)
+            const cpx f = {(g8.x + g8.y) * INV_SQRT2, (g8.y - g8.x) * INV_SQRT2};
+#else
+            const cpx e = cmul(lo, ut), f = cmul(hi, ut2);
+#endif
+            const int sh = limb == 0 ? 0 : limb == 1 ? LIMB_SHIFT1 : LIMB_SHIFT2;
+            R[0] += (u64)__double_as_longlong(e.x + MAGIC) << sh;     // coefficient j
+            R[1] += (u64)__double_as_longlong(f.x + MAGIC) << sh;     // j + 256
+            R[2] += (u64)__double_as_longlong(e.y + MAGIC) << sh;     // j + 512
+            R[3] += (u64)__double_as_longlong(f.y + MAGIC) << sh;     // j + 768
+        }
+        u64* ap = acc + out * N + j;
+#pragma unroll
+        for (int b = 0; b < 4; b++) ap[256 * b] = (MUX ? ap[256 * b] : 0) + (R[b] - K);
+    }
+}
+
+#ifndef MKF_KEY_PREFETCH
+#define MKF_KEY_PREFETCH 1
+#endif
+// smem pointers of one gate slot
+struct GateMem {
+    u64* acc;
+    u32* dig;
+    cpx *spec, *ybuf;
+};
+template <int L>
+__device__ __forceinline__ GateMem gate_mem(unsigned char* smem_raw, int slot) {
+    unsigned char* base = smem_raw + TW_BYTES + (size_t)slot * gate_bytes(L);
+    GateMem m;
+    m.acc = reinterpret_cast<u64*>(base);
+    m.dig = reinterpret_cast<u32*>(base + 2 * N * 8);
+    m.spec = reinterpret_cast<cpx*>(base + 2 * N * 8 + 2 * L * N);
+    m.ybuf = alias_for(L) ? m.spec : m.spec + 2 * L * M;
+    return m;
+}
+
+// One step of ONE gate by its 192 threads (every warp streams its own key polynomials: each key value is loaded once per gate and each
+// spectrum value six times per gate).
+template <int L, bool MUX>
+__device__ __forceinline__ void extprod_step(const GateMem& m, const cpx* __restrict__ tw, const cpx* __restrict__ key, int a, int bgbit, int bar_id,
+                                             int gtid) {
+    const int gw = gtid >> 5, lane = gtid & 31;
+    const int limb = gw >> 1, out = gw & 1;
+    const double2* kp = reinterpret_cast<const double2*>(key) + ((size_t)out * LIMBS + limb) * M + lane;   // [s][out][limb][512]
+    decompose<L, MUX>(m.acc, m.dig, a, bgbit, gtid);
     mk::gate_barrier<WPG>(bar_id);
-    // ---- warp (limb, out): multiply-accumulate over the 2L spectra, inverse transform up to the last stage
-    {
-        const int limb = gw >> 1, out = gw & 1;
+    forward_phase<L>(m.dig, m.spec, m.ybuf, tw, bgbit, gw, lane);
+    mk::gate_barrier<WPG>(bar_id);
+    {   // warp (limb, out): multiply-accumulate over the 2L spectra, inverse transform up to the last stage
         cpx v[16];
 #pragma unroll
         for (int c = 0; c < 16; c++) v[c] = cpx{0.0, 0.0};
-        const double2* kp = reinterpret_cast<const double2*>(key) + ((size_t)out * LIMBS + limb) * M + lane;   // [s][out][limb][512]
+#if MKF_KEY_PREFETCH
+        // every key register is refilled for the next digit polynomial as soon as it is consumed: the phase waits on L2 once per step, not 2l times
+        double2 kreg[16];
+#pragma unroll
+        for (int c = 0; c < 16; c++) kreg[c] = __ldg(kp + c * 32);
+#pragma unroll
+        for (int s = 0; s < 2 * L; s++) {
+            const double2* kn = kp + (size_t)(s + 1) * (2 * LIMBS * M);
+            const cpx* xs = m.spec + s * M + lane;
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                const double2 k = kreg[c];
+                if (s + 1 < 2 * L) kreg[c] = __ldg(kn + c * 32);
+                const cpx x = xs[c * 32];
+                v[c].x = fma(x.x, k.x, fma(-x.y, k.y, v[c].x));
+                v[c].y = fma(x.x, k.y, fma(x.y, k.x, v[c].y));
+            }
+        }
+#else
 #pragma unroll 1
         for (int s = 0; s < 2 * L; s++) {
             const double2* ks = kp + (size_t)s * (2 * LIMBS * M);
-            const cpx* xs = spec + s * M + lane;
+            const cpx* xs = m.spec + s * M + lane;
 #pragma unroll
             for (int c = 0; c < 16; c++) {
                 const double2 k = __ldg(ks + c * 32);
@@ -283,41 +410,12 @@ __device__ __forceinline__ void extprod_step(u64* __restrict__ acc, u32* __restr
                 v[c].y = fma(x.x, k.y, fma(x.y, k.x, v[c].y));
             }
         }
-        if (ALIAS) mk::gate_barrier<WPG>(bar_id);            // every warp is done reading the spectra
-        inv_passB(v);
-        cols_to_rows(v, ybuf + gw * M, lane);
-        inv_passA(v, tw, lane & 15);
-        const int h = lane >> 4, l16 = lane & 15;
-#pragma unroll
-        for (int r = 0; r < 16; r++) ybuf[gw * M + h * 256 + r * 16 + l16] = v[r];
+#endif
+        if (alias_for(L)) mk::gate_barrier<WPG>(bar_id);            // every warp is done reading the spectra
+        inverse_to_buffer(v, m.ybuf + gw * M, tw, lane);
     }
     mk::gate_barrier<WPG>(bar_id);
-    // ---- last inverse stage, untwist, rounding, limb recombination, accumulator update: task (out, j) -> coefficients j + 256 b
-    {
-        const double MAGIC = 6755399441055744.0;             // 1.5 * 2^52: bits(r + MAGIC) - bits(MAGIC) = rint(r) for |r| < 2^51
-        const u64 MAGIC_BITS = 0x4338000000000000ull;
-        const u64 K = MAGIC_BITS + (MAGIC_BITS << LIMB_SHIFT1) + (MAGIC_BITS << LIMB_SHIFT2);
-        for (int task = gtid; task < 512; task += TPG) {
-            const int out = task >> 8, j = task & 255;
-            const cpx wj = tw[T_WJ + j], ut = tw[T_UT + j], ut2 = tw[T_UT2 + j];
-            u64 R[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int limb = 0; limb < LIMBS; limb++) {
-                const cpx* Y = ybuf + (limb * 2 + out) * M;
-                cpx lo = Y[j], hi = Y[j + 256];
-                ct(lo, hi, wj);
-                const cpx e = cmul(lo, ut), f = cmul(hi, ut2);
-                const int sh = limb == 0 ? 0 : limb == 1 ? LIMB_SHIFT1 : LIMB_SHIFT2;
-                R[0] += (u64)__double_as_longlong(e.x + MAGIC) << sh;     // coefficient j
-                R[1] += (u64)__double_as_longlong(f.x + MAGIC) << sh;     // j + 256
-                R[2] += (u64)__double_as_longlong(e.y + MAGIC) << sh;     // j + 512
-                R[3] += (u64)__double_as_longlong(f.y + MAGIC) << sh;     // j + 768
-            }
-            u64* ap = acc + out * N + j;
-#pragma unroll
-            for (int b = 0; b < 4; b++) ap[256 * b] = (MUX ? ap[256 * b] : 0) + (R[b] - K);
-        }
-    }
+    recombine_phase<MUX>(m.acc, m.ybuf, tw, gtid);
     mk::gate_barrier<WPG>(bar_id);
 }
 
@@ -331,11 +429,8 @@ __device__ __forceinline__ void blind_rotate_body(const mk::BlindRotateArgs& p, 
     const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot;
     const int g = p.g0 + blockIdx.x * GPC + slot;
     if (g >= p.G) return;   // no CTA-wide barrier below this line
-    unsigned char* base = smem_raw + TW_BYTES + (size_t)slot * gate_bytes(L);
-    u64* acc = reinterpret_cast<u64*>(base);
-    u32* dig = reinterpret_cast<u32*>(base + 2 * N * 8);
-    cpx* spec = reinterpret_cast<cpx*>(base + 2 * N * 8 + 2 * L * N);
-    cpx* ybuf = alias_for(L) ? spec : spec + 2 * L * M;
+    const GateMem m = gate_mem<L>(smem_raw, slot);
+    u64* acc = m.acc;
     const int kn = p.k * p.n;
     const mk::GateLinear lin = p.gate_ids ? mk::gate_linear(__ldg(p.gate_ids + g)) : p.lin;
     uint32_t tb = (uint32_t)lin.mu0 + (uint32_t)lin.cx * (uint32_t)__ldg(p.xb + g);
@@ -363,15 +458,15 @@ __device__ __forceinline__ void blind_rotate_body(const mk::BlindRotateArgs& p, 
             if (lin.cz) rz = __ldg(p.za + abase + it + 1);
         }
         if (a == 0) continue;   // 3gen_mk_internals.jl:69 (uniform across the gate)
-        extprod_step<L, true>(acc, dig, spec, ybuf, tw, key_fft + (size_t)it * estride, a, p.bgbit, bar_id, gtid);
+        extprod_step<L, true>(m, tw, key_fft + (size_t)it * estride, a, p.bgbit, bar_id, gtid);
     }
     if (p.acc_out) {
         int64_t* ao = p.acc_out + (size_t)g * 2 * N;
         for (int i = gtid; i < 2 * N; i += TPG) ao[i] = (int64_t)acc[i];
     }
     if (p.ksk) {   // fused extraction + key switch (the host only sets ksk when mk::ks_fusable(n, t)); scratch: the spectra
-        if (p.ks_t == 3) mk::fused_keyswitch<3, WPG>(acc, reinterpret_cast<u32*>(spec), p, g, gtid, bar_id);
-        else mk::fused_keyswitch<5, WPG>(acc, reinterpret_cast<u32*>(spec), p, g, gtid, bar_id);
+        if (p.ks_t == 3) mk::fused_keyswitch<3, WPG>(acc, reinterpret_cast<u32*>(m.spec), p, g, gtid, bar_id);
+        else mk::fused_keyswitch<5, WPG>(acc, reinterpret_cast<u32*>(m.spec), p, g, gtid, bar_id);
         return;
     }
     int32_t* ext = p.ext_out + (size_t)g * (N + 1);
@@ -401,15 +496,11 @@ __global__ void __maxnreg__(MKF_MAXNREG) extprod_fft_kernel(int G, const cpx* __
     const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot;
     const int g = blockIdx.x * GPC + slot;
     if (g >= G) return;
-    unsigned char* base = smem_raw + TW_BYTES + (size_t)slot * gate_bytes(L);
-    u64* acc = reinterpret_cast<u64*>(base);
-    u32* dig = reinterpret_cast<u32*>(base + 2 * N * 8);
-    cpx* spec = reinterpret_cast<cpx*>(base + 2 * N * 8 + 2 * L * N);
-    cpx* ybuf = alias_for(L) ? spec : spec + 2 * L * M;
-    for (int i = gtid; i < 2 * N; i += TPG) acc[i] = (u64)acc_in[(size_t)g * 2 * N + i];
+    const GateMem m = gate_mem<L>(smem_raw, slot);
+    for (int i = gtid; i < 2 * N; i += TPG) m.acc[i] = (u64)acc_in[(size_t)g * 2 * N + i];
     mk::gate_barrier<WPG>(bar_id);
-    extprod_step<L, false>(acc, dig, spec, ybuf, tw, key_fft + (size_t)elem[g] * bsk_elem_cpx(L), 0, bgbit, bar_id, gtid);
-    for (int i = gtid; i < 2 * N; i += TPG) acc_out[(size_t)g * 2 * N + i] = (int64_t)acc[i];
+    extprod_step<L, false>(m, tw, key_fft + (size_t)elem[g] * bsk_elem_cpx(L), 0, bgbit, bar_id, gtid);
+    for (int i = gtid; i < 2 * N; i += TPG) acc_out[(size_t)g * 2 * N + i] = (int64_t)m.acc[i];
 }
 
 // One warp per (key polynomial, limb): raw int64 key -> spectrum of the limb, scaled by 1 / 512, in the FFT layout.
