@@ -3,6 +3,7 @@
 exact schoolbook product."""
 import os
 import subprocess
+import sys
 
 from conftest import ROOT
 
@@ -48,3 +49,20 @@ def test_f64_channel_prototype(tmp_path):
                            "-I", os.path.join(ROOT, "tools", "f64_channel"), os.path.join(ROOT, "tools", "f64_channel", "emu.cpp"), "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "f64_emu: OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_fft64_host_emulation(tmp_path):
+    """Arithmetic core of the FP64 FFT channel (fft64_core.cuh, tables_fft.h): the kernels' per-thread passes for 32 emulated lanes against the
+    definition of the transform and against the wrap-around integer external product (extreme operands included); the rounding margin
+    of the limb results is printed and bounded."""
+    exe = str(tmp_path / "fft64_emu")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "torus-fhe_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "host_emu", "fft64_emu.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "fft64_emu: OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_fft64_numpy_prototype():
+    """tools/fft_channel/proto.py: the same networks in numpy -- exact on random and extreme operands."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fft_channel", "proto.py")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "exact on 20 trials" in out.stdout, out.stdout + out.stderr

@@ -22,13 +22,10 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "kernels.cuh"
-#include "fft64_layout.h"
+#include "fft64_core.cuh"
 
 namespace mkf {
 
-struct __align__(16) cpx { double x, y; };
-
-constexpr double INV_SQRT2 = 0.70710678118654752440;
 constexpr int WPG = 6, TPG = 32 * WPG;
 
 // per gate: Torus64 accumulator, packed digits (one byte per coefficient), 2l digit spectra, 6 limb-output buffers.
@@ -43,196 +40,23 @@ __host__ __device__ constexpr int gpc_for(int l) {
 }
 __host__ __device__ constexpr size_t cta_bytes(int l, int gpc) { return (size_t)TW_BYTES + (size_t)gpc * gate_bytes(l); }
 
-// (a, b) -> (a + w b, a - w b): 6 DFMA-pipe instructions
-__device__ __forceinline__ void ct(cpx& a, cpx& b, const cpx w) {
-    const double tr = fma(w.x, b.x, fma(-w.y, b.y, a.x));
-    const double ti = fma(w.x, b.y, fma(w.y, b.x, a.y));
-    b.x = fma(2.0, a.x, -tr);
-    b.y = fma(2.0, a.y, -ti);
-    a.x = tr;
-    a.y = ti;
-}
-// w = 1 and w = -i: 4 DADD
-__device__ __forceinline__ void ct_one(cpx& a, cpx& b) {
-    const double ar = a.x, ai = a.y;
-    a.x = ar + b.x; a.y = ai + b.y;
-    b.x = ar - b.x; b.y = ai - b.y;
-}
-__device__ __forceinline__ void ct_negi(cpx& a, cpx& b) {   // w b = -i b = (b.y, -b.x)
-    const double ar = a.x, ai = a.y, br = b.x, bi = b.y;
-    a.x = ar + bi; a.y = ai - br;
-    b.x = ar - bi; b.y = ai + br;
-}
-__device__ __forceinline__ cpx cmul(const cpx a, const cpx b) { return {fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x)}; }
-
-// exact small integer -> double without a conversion instruction: bits 0x43300000'u = 2^52 + u
-__device__ __forceinline__ double u2d(unsigned u, double magic) { return __hiloint2double(0x43300000, (int)u) - magic; }
-
-// stage 0 of the forward transform straight from the digit words: word j (j < 256) holds the biased digit bytes of coefficients
-// j, j + 256, j + 512, j + 768; a~[j] = d0 + i d2, a~[j + 256] = d1 + i d3; out = a~[j] +- exp(i pi / 4) a~[j + 256] (+ for h = 0)
-__device__ __forceinline__ void fwd_stage0_digits(cpx (&v)[16], const u32* __restrict__ dig_s, int lane, int half_bg) {
-    const int h = lane >> 4, l16 = lane & 15;
-    const double cs = h ? -INV_SQRT2 : INV_SQRT2;
-    const double two52 = 4503599627370496.0;
-    const double m0 = two52 + (double)half_bg, mP = two52 + 256.0, mQ = two52 + (double)(2 * half_bg);
-#pragma unroll
-    for (int r = 0; r < 16; r++) {
-        const u32 word = dig_s[16 * r + l16];
-        const u32 b0 = word & 0xffu, b1 = (word >> 8) & 0xffu, b2 = (word >> 16) & 0xffu, b3 = word >> 24;
-        const double x0 = u2d(b0, m0), y0 = u2d(b2, m0);
-        const double P = u2d(b1 - b3 + 256u, mP), Q = u2d(b1 + b3, mQ);      // x1 - y1, x1 + y1
-        v[r].x = fma(cs, P, x0);
-        v[r].y = fma(cs, Q, y0);
-    }
-}
-// the same from the four real coefficients (key transform): a0 = a[j], a1 = a[j + 256], a2 = a[j + 512], a3 = a[j + 768]
-__device__ __forceinline__ cpx fwd_stage0_real(double a0, double a1, double a2, double a3, int h) {
-    const double cs = h ? -INV_SQRT2 : INV_SQRT2;
-    return {fma(cs, a1 - a3, a0), fma(cs, a1 + a3, a2)};
-}
-
-// forward stages 1..4 in the row layout (register r = position bits 7..4)
-__device__ __forceinline__ void fwd_passA(cpx (&v)[16], const cpx* __restrict__ tw, int h) {
-    {
-        const cpx w = tw[TF_A + 0 + h];
-#pragma unroll
-        for (int r = 0; r < 8; r++) ct(v[r], v[r + 8], w);
-    }
-#pragma unroll
-    for (int g = 0; g < 2; g++) {
-        const cpx w = tw[TF_A + 2 + 2 * h + g];
-#pragma unroll
-        for (int r = 0; r < 4; r++) ct(v[8 * g + r], v[8 * g + r + 4], w);
-    }
-#pragma unroll
-    for (int g = 0; g < 4; g++) {
-        const cpx w = tw[TF_A + 6 + 4 * h + g];
-#pragma unroll
-        for (int r = 0; r < 2; r++) ct(v[4 * g + r], v[4 * g + r + 2], w);
-    }
-#pragma unroll
-    for (int g = 0; g < 8; g++) {
-        const cpx w = tw[TF_A + 14 + 8 * h + g];
-        ct(v[2 * g], v[2 * g + 1], w);
-    }
-}
-// forward stages 5..8 in the column layout (register c = position bits 3..0), per-lane twiddles.
-// s(d, g), g = lane 2^(d-5) + sub, factors as s(d, lane 2^(d-5)) * exp(i pi rev(sub) / 2^(d-5)): one table load per stage (the sub = 0 entry)
-// and compile-time constants (MKF_TW_COMPUTE; 0 loads all 15 twiddles from the table) -- the load/store pipe, not the FP64 pipe, binds this kernel
-#ifndef MKF_TW_COMPUTE
-#define MKF_TW_COMPUTE 1
-#endif
-__device__ __forceinline__ cpx mul_i(const cpx a) { return {-a.y, a.x}; }
-__device__ __forceinline__ void fwd_passB(cpx (&v)[16], const cpx* __restrict__ tw, int lane) {
-    {
-        const cpx w = tw[TF_B + lane];
-#pragma unroll
-        for (int c = 0; c < 8; c++) ct(v[c], v[c + 8], w);
-    }
-#if MKF_TW_COMPUTE
-    // (computing all fourteen before the first use is what ptxas allocates best: interleaving them with the butterflies cost 4 %)
-    constexpr double C1 = 0.92387953251128675613, S1 = 0.38268343236508977173;   // cos, sin of pi / 8
-    cpx w6[2], w7[4], w8[8];
-    w6[0] = tw[TF_B + 32 + lane];
-    w6[1] = mul_i(w6[0]);
-    w7[0] = tw[TF_B + 96 + lane];
-    w7[1] = mul_i(w7[0]);                                    // rev2(1) = 2: exp(i pi / 2)
-    w7[2] = cmul(w7[0], cpx{INV_SQRT2, INV_SQRT2});          // rev2(2) = 1: exp(i pi / 4)
-    w7[3] = mul_i(w7[2]);                                    // rev2(3) = 3
-    w8[0] = tw[TF_B + 224 + lane];
-    w8[4] = cmul(w8[0], cpx{C1, S1});                        // rev3(4) = 1: exp(i pi / 8)
-    w8[2] = cmul(w8[0], cpx{INV_SQRT2, INV_SQRT2});          // rev3(2) = 2
-    w8[6] = cmul(w8[0], cpx{S1, C1});                        // rev3(6) = 3: exp(3 i pi / 8)
-    w8[1] = mul_i(w8[0]);                                    // rev3(1) = 4
-    w8[5] = mul_i(w8[4]);                                    // rev3(5) = 5
-    w8[3] = mul_i(w8[2]);                                    // rev3(3) = 6
-    w8[7] = mul_i(w8[6]);                                    // rev3(7) = 7
-#endif
-#pragma unroll
-    for (int g = 0; g < 2; g++) {
-#if MKF_TW_COMPUTE
-        const cpx w = w6[g];
-#else
-        const cpx w = tw[TF_B + 32 + g * 32 + lane];
-#endif
-#pragma unroll
-        for (int c = 0; c < 4; c++) ct(v[8 * g + c], v[8 * g + c + 4], w);
-    }
-#pragma unroll
-    for (int g = 0; g < 4; g++) {
-#if MKF_TW_COMPUTE
-        const cpx w = w7[g];
-#else
-        const cpx w = tw[TF_B + 96 + g * 32 + lane];
-#endif
-#pragma unroll
-        for (int c = 0; c < 2; c++) ct(v[4 * g + c], v[4 * g + c + 2], w);
-    }
-#pragma unroll
-    for (int g = 0; g < 8; g++) {
-#if MKF_TW_COMPUTE
-        const cpx w = w8[g];
-#else
-        const cpx w = tw[TF_B + 224 + g * 32 + lane];
-#endif
-        ct(v[2 * g], v[2 * g + 1], w);
-    }
-}
-// inverse spans 1, 2, 4, 8 in the column layout: twiddle exp(-2 pi i (c mod sp) / (2 sp)), compile-time constants
-__device__ __forceinline__ void inv_passB(cpx (&v)[16]) {
-#pragma unroll
-    for (int c = 0; c < 16; c += 2) ct_one(v[c], v[c + 1]);
-#pragma unroll
-    for (int c = 0; c < 16; c += 4) {
-        ct_one(v[c], v[c + 2]);
-        ct_negi(v[c + 1], v[c + 3]);
-    }
-#pragma unroll
-    for (int c = 0; c < 16; c += 8) {
-        ct_one(v[c], v[c + 4]);
-        ct(v[c + 1], v[c + 5], cpx{INV_SQRT2, -INV_SQRT2});
-        ct_negi(v[c + 2], v[c + 6]);
-        ct(v[c + 3], v[c + 7], cpx{-INV_SQRT2, -INV_SQRT2});
-    }
-    constexpr double C1 = 0.92387953251128675613, S1 = 0.38268343236508977173;   // cos, sin of pi / 8
-    ct_one(v[0], v[8]);
-    ct(v[1], v[9], cpx{C1, -S1});
-    ct(v[2], v[10], cpx{INV_SQRT2, -INV_SQRT2});
-    ct(v[3], v[11], cpx{S1, -C1});
-    ct_negi(v[4], v[12]);
-    ct(v[5], v[13], cpx{-S1, -C1});
-    ct(v[6], v[14], cpx{-INV_SQRT2, -INV_SQRT2});
-    ct(v[7], v[15], cpx{-C1, -S1});
-}
-// inverse spans 16, 32, 64, 128 in the row layout: twiddle exp(-2 pi i ((r mod rs) 16 + l16) / (32 rs))
-__device__ __forceinline__ void inv_passA(cpx (&v)[16], const cpx* __restrict__ tw, int l16) {
-#pragma unroll
-    for (int rs = 1; rs <= 8; rs *= 2) {
-#pragma unroll
-        for (int e = 0; e < rs; e++) {
-            const cpx w = tw[TI_A + 16 * (rs - 1) + e * 16 + l16];
-#pragma unroll
-            for (int r0 = 0; r0 < 16; r0 += 2 * rs) ct(v[r0 + e], v[r0 + e + rs], w);
-        }
-    }
-}
 // row layout -> column layout and back through a 512-entry buffer, XOR-swizzled so that both sides are conflict-free
 __device__ __forceinline__ void rows_to_cols(cpx (&v)[16], cpx* __restrict__ buf, int lane) {
     const int h = lane >> 4, l16 = lane & 15;
 #pragma unroll
-    for (int r = 0; r < 16; r++) buf[h * 256 + r * 16 + (l16 ^ r)] = v[r];
+    for (int r = 0; r < 16; r++) buf[transpose_slot(h, r, l16)] = v[r];
     __syncwarp();
 #pragma unroll
-    for (int c = 0; c < 16; c++) v[c] = buf[h * 256 + l16 * 16 + (c ^ l16)];
+    for (int c = 0; c < 16; c++) v[c] = buf[transpose_slot(h, l16, c)];
     __syncwarp();
 }
 __device__ __forceinline__ void cols_to_rows(cpx (&v)[16], cpx* __restrict__ buf, int lane) {
     const int h = lane >> 4, l16 = lane & 15;
 #pragma unroll
-    for (int c = 0; c < 16; c++) buf[h * 256 + l16 * 16 + (c ^ l16)] = v[c];
+    for (int c = 0; c < 16; c++) buf[transpose_slot(h, l16, c)] = v[c];
     __syncwarp();
 #pragma unroll
-    for (int r = 0; r < 16; r++) v[r] = buf[h * 256 + r * 16 + (l16 ^ r)];
+    for (int r = 0; r < 16; r++) v[r] = buf[transpose_slot(h, r, l16)];
     __syncwarp();
 }
 
@@ -310,36 +134,18 @@ __device__ __forceinline__ void inverse_to_buffer(cpx (&v)[16], cpx* __restrict_
 // last inverse stage, untwist, rounding, limb recombination, accumulator update: task (out, j) -> coefficients j + 256 b
 template <bool MUX>
 __device__ __forceinline__ void recombine_phase(u64* __restrict__ acc, const cpx* __restrict__ ybuf, const cpx* __restrict__ tw, int gtid) {
-    const double MAGIC = 6755399441055744.0;             // 1.5 * 2^52: bits(r + MAGIC) - bits(MAGIC) = rint(r) for |r| < 2^51
-    const u64 MAGIC_BITS = 0x4338000000000000ull;
-    const u64 K = MAGIC_BITS + (MAGIC_BITS << LIMB_SHIFT1) + (MAGIC_BITS << LIMB_SHIFT2);
     for (int task = gtid; task < 512; task += TPG) {
         const int out = task >> 8, j = task & 255;
         const cpx wj = tw[T_WJ + j], ut = tw[T_UT + j];
-#if !MKF_TW_COMPUTE
-        const cpx ut2 = tw[T_UT2 + j];
-#endif
-        u64 R[4] = {0, 0, 0, 0};
+        uint64_t R[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int limb = 0; limb < LIMBS; limb++) {
             const cpx* Y = ybuf + (limb * 2 + out) * M;
-            cpx lo = Y[j], hi = Y[j + 256];
-            ct(lo, hi, wj);
-#if MKF_TW_COMPUTE
-            const cpx e = cmul(lo, ut), g8 = cmul(hi, ut);      // zeta^-(j + 256) = zeta^-j exp(-i pi / 4)
-            const cpx f = {(g8.x + g8.y) * INV_SQRT2, (g8.y - g8.x) * INV_SQRT2};
-#else
-            const cpx e = cmul(lo, ut), f = cmul(hi, ut2);
-#endif
-            const int sh = limb == 0 ? 0 : limb == 1 ? LIMB_SHIFT1 : LIMB_SHIFT2;
-            R[0] += (u64)__double_as_longlong(e.x + MAGIC) << sh;     // coefficient j
-            R[1] += (u64)__double_as_longlong(f.x + MAGIC) << sh;     // j + 256
-            R[2] += (u64)__double_as_longlong(e.y + MAGIC) << sh;     // j + 512
-            R[3] += (u64)__double_as_longlong(f.y + MAGIC) << sh;     // j + 768
+            recombine_limb(R, Y[j], Y[j + 256], wj, ut, limb == 0 ? 0 : limb == 1 ? LIMB_SHIFT1 : LIMB_SHIFT2);
         }
         u64* ap = acc + out * N + j;
 #pragma unroll
-        for (int b = 0; b < 4; b++) ap[256 * b] = (MUX ? ap[256 * b] : 0) + (R[b] - K);
+        for (int b = 0; b < 4; b++) ap[256 * b] = (MUX ? ap[256 * b] : 0) + (R[b] - ROUND_K);
     }
 }
 
@@ -519,18 +325,11 @@ __global__ void __launch_bounds__(XF_WARPS * 32) bsk_transform_fft_kernel(const 
     const int src = (part == 0 || part == 3) ? 0 : 1;
     const int64_t* poly = raw + (size_t)pq * N;
     const int h = lane >> 4, l16 = lane & 15;
-    auto limb_of = [&](int64_t k) -> double {
-        const int64_t l0 = ((k + (1ll << (LIMB_BITS0 - 1))) & ((1ll << LIMB_BITS0) - 1)) - (1ll << (LIMB_BITS0 - 1));
-        const int64_t k1 = (int64_t)((u64)k - (u64)l0) >> LIMB_BITS0;
-        const int64_t l1 = ((k1 + (1ll << (LIMB_BITS1 - 1))) & ((1ll << LIMB_BITS1) - 1)) - (1ll << (LIMB_BITS1 - 1));
-        const int64_t l2 = (k1 - l1) >> LIMB_BITS1;
-        return (double)(limb == 0 ? l0 : limb == 1 ? l1 : l2);
-    };
     cpx v[16];
 #pragma unroll
     for (int r = 0; r < 16; r++) {
         const int jj = 16 * r + l16;
-        v[r] = fwd_stage0_real(limb_of(poly[jj]), limb_of(poly[jj + 256]), limb_of(poly[jj + 512]), limb_of(poly[jj + 768]), h);
+        v[r] = fwd_stage0_real(key_limb(poly[jj], limb), key_limb(poly[jj + 256], limb), key_limb(poly[jj + 512], limb), key_limb(poly[jj + 768], limb), h);
     }
     fwd_passA(v, tw_g, h);
     rows_to_cols(v, bufs + warp * M, lane);

@@ -47,10 +47,12 @@ struct mktfhe_ctx {
     int32_t* d_ksk = nullptr;
     size_t ksk_bytes = 0;
     rns::uint2_* d_twB = nullptr;
-    // FP64 FFT channel (fft64.cuh; N = 1024, Torus64, byte digits): a second copy of the bootstrapping key as limb spectra, stored behind the
-    // NTT layout in the same allocation (d_bsk .. d_bsk + bsk_bytes covers both, so key broadcasts move both); serves the throughput launch
+    // FP64 FFT channel (fft64.cuh; N = 1024, Torus64, byte digits; MKTFHE_B200_FFT=0 selects the three-prime NTT kernels instead: A/B runs):
+    // d_bsk then holds the bootstrapping key as limb spectra (d_bsk_fft == d_bsk) and every launch shape runs the FFT kernels
     bool fft = false;
-    size_t bsk_ntt_bytes = 0;    // size of the NTT-layout part
+    bool fft_small = true;       // batches (and tails) of at most one gate per SM: one six-warp FFT gate per CTA (MKTFHE_B200_FFT_SMALL=0: the
+                                 // NTT latency kernel -- needs the NTT key layout, so it then also keeps that copy, stored in front of the spectra)
+    size_t bsk_ntt_bytes = 0;    // size of the NTT-layout part of d_bsk (0 when every launch shape runs the FFT kernels)
     mkf::cpx* d_bsk_fft = nullptr;
     mkf::cpx* d_twF = nullptr;
     int gpc = 1;                 // gates per CTA of the blind-rotate / external-product kernels
@@ -204,6 +206,10 @@ int set_attrs(mktfhe_ctx* c) {
     CU_TRY(c, cudaFuncSetAttribute(mkf::extprod_fft_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));
         MK_DISPATCH_FFT(c, SET_ATTR_FFT, 0)
 #undef SET_ATTR_FFT
+        const int smf1 = (int)mkf::cta_bytes(c->prm.l, 1);
+#define SET_ATTR_FFT1(L, GPC, dummy) CU_TRY(c, cudaFuncSetAttribute(mkf::blind_rotate_fft_kernel<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf1));
+        MK_DISPATCH_FFT(c, SET_ATTR_FFT1, 0)
+#undef SET_ATTR_FFT1
     }
 #define SET_ATTR(L, GPC, dummy)                                                                                                    \
     CU_TRY(c, cudaFuncSetAttribute(mk::blind_rotate_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));             \
@@ -232,7 +238,12 @@ void launch_one_gate_per_cta(mktfhe_ctx* c, mk::BlindRotateArgs a, size_t g0, si
     const unsigned grid = (unsigned)(g1 - g0);
     const int l = c->prm.l;
     const size_t sml = mk::TW_SMEM_BYTES + mk::gate_smem_bytes(l, mk::lat_wpg(l));
-    if (l == 2 && c->latency_kernel) mk::blind_rotate_lat_kernel<2><<<grid, 32 * mk::lat_wpg(2), sml, st>>>(a);
+    if (c->fft && c->fft_small) {
+        const size_t smf1 = mkf::cta_bytes(l, 1);
+#define LAUNCH_BR_FFT1(L, GPC, dummy) mkf::blind_rotate_fft_kernel<L, 1><<<grid, mkf::TPG, smf1, st>>>(a, c->d_bsk_fft, c->d_twF)
+        MK_DISPATCH_FFT(c, LAUNCH_BR_FFT1, 0)
+#undef LAUNCH_BR_FFT1
+    } else if (l == 2 && c->latency_kernel) mk::blind_rotate_lat_kernel<2><<<grid, 32 * mk::lat_wpg(2), sml, st>>>(a);
     else if (l == 3 && c->latency_kernel) mk::blind_rotate_lat_kernel<3><<<grid, 32 * mk::lat_wpg(3), sml, st>>>(a);
     else if (l == 4 && c->latency_kernel) mk::blind_rotate_lat_kernel<4><<<grid, 32 * mk::lat_wpg(4), sml, st>>>(a);
     else {
@@ -540,6 +551,8 @@ int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
     // FP64 FFT channel: N = 1024, Torus64 keys, byte digits; exact while 2 l N (Bg / 2) 2^21 <= 2^40 (limb products recovered by rounding)
     c->fft = !big && !c->t32 && std::log2((double)(2 * params->l) * params->N) + (params->bgbit - 1) + 21.0 <= 40.0;
     if (const char* e = getenv("MKTFHE_B200_FFT")) c->fft = c->fft && atoi(e) != 0;
+    if (const char* e = getenv("MKTFHE_B200_FFT_SMALL")) c->fft_small = atoi(e) != 0;
+    if (c->fft && c->fft_small) c->bsk_ntt_bytes = c->bsk_bytes = 0;
     if (c->fft) c->bsk_bytes += (size_t)params->k * params->n * mkf::bsk_elem_cpx(params->l) * sizeof(mkf::cpx);
     c->gpc = big ? 1 : mk::gpc_for(params->l, c->t32);
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -611,8 +624,9 @@ int mktfhe_load_bsk(mktfhe_ctx* c, int party, const int64_t* polys) {
             (const int64_t*)c->raw.p, c->d_bsk, n, l, party, c->d_twB, ntasks);
     } else {
         const int ntasks = n * 4 * l * rns::NP;
-        mk::bsk_transform_kernel<<<(ntasks + mk::XF_WARPS - 1) / mk::XF_WARPS, mk::XF_WARPS * 32, 0, c->stream>>>(
-            (const int64_t*)c->raw.p, c->d_bsk, n, l, party, c->d_twB, ntasks);
+        if (c->bsk_ntt_bytes)
+            mk::bsk_transform_kernel<<<(ntasks + mk::XF_WARPS - 1) / mk::XF_WARPS, mk::XF_WARPS * 32, 0, c->stream>>>(
+                (const int64_t*)c->raw.p, c->d_bsk, n, l, party, c->d_twB, ntasks);
         if (c->fft) {
             const int nt = n * 4 * l * mkf::LIMBS;
             mkf::bsk_transform_fft_kernel<<<(nt + mkf::XF_WARPS - 1) / mkf::XF_WARPS, mkf::XF_WARPS * 32, 0, c->stream>>>(
@@ -1051,6 +1065,13 @@ int mktfhe_extprod_batch_dev(mktfhe_ctx* c, size_t G, const int32_t* elem, const
 #define LAUNCH_EPD_T32(L, GPC, dummy) mk::extprod_t32_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, st>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, elem, acc_in, acc_out)
         MK_DISPATCH_T32(c, LAUNCH_EPD_T32, 0)
 #undef LAUNCH_EPD_T32
+    } else if (c->fft) {
+        const size_t smf = fft_smem_bytes(c);
+        const int gf = mkf::gpc_for(c->prm.l);
+        const unsigned gridf = (unsigned)((G + gf - 1) / gf);
+#define LAUNCH_EPD_FFT(L, GPC, dummy) mkf::extprod_fft_kernel<L, GPC><<<gridf, GPC * mkf::TPG, smf, st>>>((int)G, c->d_bsk_fft, c->d_twF, c->prm.bgbit, elem, acc_in, acc_out)
+        MK_DISPATCH_FFT(c, LAUNCH_EPD_FFT, 0)
+#undef LAUNCH_EPD_FFT
     } else {
 #define LAUNCH_EPD(L, GPC, dummy) mk::extprod_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, st>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, elem, acc_in, acc_out)
         MK_DISPATCH_L(c, LAUNCH_EPD, 0)

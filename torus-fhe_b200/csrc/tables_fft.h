@@ -30,8 +30,7 @@ struct HostTablesFFT {
         for (int d = 1; d <= 4; d++)
             for (int g = 0; g < (1 << d); g++) put(TF_A + (1 << d) - 2 + g, fwd_ang(d, g));
         for (int d = 5; d <= 8; d++)
-            for (int sub = 0; sub < (1 << (d - 5)); sub++)
-                for (int lane = 0; lane < 32; lane++) put(TF_B + 32 * ((1 << (d - 5)) - 1) + sub * 32 + lane, fwd_ang(d, lane * (1 << (d - 5)) + sub));
+            for (int lane = 0; lane < 32; lane++) put(TF_B + 32 * (d - 5) + lane, fwd_ang(d, lane * (1 << (d - 5))));
         // inverse, decimation in time, bit-reversed -> natural: span sp, position twiddle exp(-2 pi i (pos mod sp) / (2 sp));
         // pass A' covers sp = 16 rs, rs = 1, 2, 4, 8, pos mod sp = (r mod rs) 16 + l16
         for (int rs = 1; rs <= 8; rs *= 2)
@@ -39,7 +38,6 @@ struct HostTablesFFT {
         for (int j = 0; j < 256; j++) {
             put(T_WJ + j, -2.0L * PI * (long double)j / 512.0L);        // last inverse stage (span 256)
             put(T_UT + j, -PI * (long double)j / 1024.0L);              // untwist zeta^-j, zeta = exp(i pi / N)
-            put(T_UT2 + j, -PI * (long double)(j + 256) / 1024.0L);     // zeta^-(j + 256)
         }
     }
 };
