@@ -12,10 +12,15 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def hot_kernels(N, l):
-    """Substrings (of mangled names) selecting the kernels that serve a parameter set: the N = 1024 throughput and latency kernels
-    of gadget length l, or the N = 2048 kernels."""
-    return ["N4mk2k"] if N == 2048 else [f"N2mk19blind_rotate_kernelILi{l}E", f"N2mk23blind_rotate_lat_kernelILi{l}E"]
+def hot_kernels(N, l, engine="ntt_rns"):
+    """Substrings (of mangled names) selecting the kernels that serve a parameter set: the N = 1024 kernels of gadget length l -- the FP64 FFT
+    channel (engine "fft64": both launch shapes are blind_rotate_fft_kernel<l, .>) or the three-prime NTT throughput and latency kernels --
+    or the N = 2048 kernels."""
+    if N == 2048:
+        return ["N4mk2k"]
+    if engine == "fft64":
+        return [f"N3mkf23blind_rotate_fft_kernelILi{l}E"]
+    return [f"N2mk19blind_rotate_kernelILi{l}E", f"N2mk23blind_rotate_lat_kernelILi{l}E"]
 
 
 def kernel_id(lib=None, match=("blind_rotate",)):
@@ -41,4 +46,5 @@ def kernel_id(lib=None, match=("blind_rotate",)):
 
 if __name__ == "__main__":
     lib = sys.argv[1] if len(sys.argv) > 1 else None
-    print("all blind_rotate kernels:", kernel_id(lib), " N=1024 l=2:", kernel_id(lib, hot_kernels(1024, 2)), " N=2048:", kernel_id(lib, hot_kernels(2048, 1)))
+    print("all blind_rotate kernels:", kernel_id(lib), " N=1024 l=2 fft64:", kernel_id(lib, hot_kernels(1024, 2, "fft64")),
+          " N=1024 l=2 ntt_rns:", kernel_id(lib, hot_kernels(1024, 2)), " N=2048:", kernel_id(lib, hot_kernels(2048, 1)))

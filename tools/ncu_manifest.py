@@ -20,6 +20,7 @@ ap.add_argument("--gates", type=int, required=True, help="gates in the captured 
 ap.add_argument("--lib", default=None)
 ap.add_argument("--N", type=int, default=1024)
 ap.add_argument("--l", type=int, default=2)
+ap.add_argument("--engine", default="ntt_rns", choices=["ntt_rns", "fft64"], help="which external-product kernels the capture is of")
 ap.add_argument("-o", "--out", required=True)
 a = ap.parse_args()
 text = open(a.summary).read()
@@ -35,13 +36,17 @@ def metric(name):
 
 man = {
     "kernel": re.search(r"^== (.*?)  grid", text, flags=re.M).group(1),
-    "kernel_id": kernel_id(a.lib, hot_kernels(a.N, a.l)),
-    "kernel_id_covers": hot_kernels(a.N, a.l),
+    "engine": a.engine,
+    "kernel_id": kernel_id(a.lib, hot_kernels(a.N, a.l, a.engine)),
+    "kernel_id_covers": hot_kernels(a.N, a.l, a.engine),
     "parties": a.parties,
     "gates_in_launch": a.gates,
     "gpu_time_ms": metric("gpu__time_duration.sum"),
     "dram_bytes": metric("dram__bytes_read.sum") + metric("dram__bytes_write.sum"),
     "fmaheavy_pipe_busy": metric("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed") / 100.0,
+    "fp64_pipe_busy": metric("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active") / 100.0 if a.engine == "fft64" else None,
+    "lsu_data_path_busy": metric("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed") / 100.0 if a.engine == "fft64" else None,
+    "l2_to_sm_bytes": metric("l1tex__m_xbar2l1tex_read_bytes.sum") if a.engine == "fft64" else None,
     "issue_active": metric("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100.0,
     "l2_hit_rate": metric("lts__t_sector_hit_rate.pct") / 100.0,
     "registers_per_thread": int(metric("launch__registers_per_thread")),

@@ -16,7 +16,10 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum ", "lts__t_bytes.sum.per_second",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum ", "smsp__average_warp_latency_per_inst_issued",
         "smsp__average_warps_issue_stalled", "sass__inst_executed_local", "sm__inst_executed_pipe_uniform", "sm__inst_executed_pipe_xu", "smsp__inst_executed_pipe_",
-        "l1tex__t_sector_hit_rate", "sm__inst_executed_pipe_adu", "sm__inst_executed_pipe_cbu", "sm__cycles_active.avg "]
+        "l1tex__t_sector_hit_rate", "sm__inst_executed_pipe_adu", "sm__inst_executed_pipe_cbu", "sm__cycles_active.avg ",
+        "sm__pipe_fp64_cycles_active.avg.pct", "sm__inst_executed_pipe_fp64.avg.pct", "l1tex__data_pipe_lsu_wavefronts.avg.pct", "l1tex__data_pipe_lsu_wavefronts.sum ",
+        "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum ", "l1tex__m_xbar2l1tex_read_bytes.sum ", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum"]
 out = []
 for r in rows[2:]:
     out.append(f"== {r[hdr.index('Kernel Name')]}  grid {r[hdr.index('Grid Size')]} block {r[hdr.index('Block Size')]}")

@@ -28,10 +28,10 @@ namespace mkf {
 
 constexpr int WPG = 6, TPG = 32 * WPG;
 
-// per gate: Torus64 accumulator, packed digits (one byte per coefficient), 2l digit spectra, 6 limb-output buffers.
-// ALIAS (l >= 3): the limb-output buffers reuse the spectra (one more gate barrier per step).
-__host__ __device__ constexpr bool alias_for(int l) { return l >= 3; }
-__host__ __device__ constexpr int nbuf(int l) { return alias_for(l) ? (2 * l > 6 ? 2 * l : 6) : 2 * l + 6; }
+// per gate: Torus64 accumulator, packed digits (one byte per coefficient), and max(2l, 6) buffers of 512 complex values: the 2l digit spectra
+// during the forward transforms and the multiply-accumulate, then (one gate barrier later) the 6 limb outputs.  Separate buffers for the
+// two roles would fit at l = 2 and save that barrier, but measured 0.9 % slower: the 64 KB they cost are worth more as L1 for the key stream.
+__host__ __device__ constexpr int nbuf(int l) { return 2 * l > 6 ? 2 * l : 6; }
 __host__ __device__ constexpr size_t gate_bytes(int l) { return (size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)nbuf(l) * M * 16; }
 __host__ __device__ constexpr int gpc_for(int l) {
     int g = 2;
@@ -105,18 +105,17 @@ __device__ __forceinline__ void decompose(const u64* __restrict__ acc, u32* __re
 // ---- phases of one external product (tgsw_extern_mul_3gen, tgsw_3gen.jl:102-113) on the accumulator held in shared memory -----------------
 //   MUX = true : acc += ExtProd(X^a * acc - acc, key)   (mk_mux_rotate_3gen, 3gen_mk_internals.jl:59-62)
 //   MUX = false: acc  = ExtProd(acc, key)
-// Per gate: spec = 2L digit spectra [512], ybuf = 6 limb-output buffers [512] (== spec when ALIAS), index lo = 2 limb + out.
+// Per gate: buf = max(2L, 6) buffers [512]: the 2L digit spectra, later the 6 limb outputs (index lo = 2 limb + out).
 
 // forward transforms of the 2L digit polynomials by the warps gw = s, s + 6, ..; spectrum point (c, lane) at c 32 + lane
 template <int L>
-__device__ __forceinline__ void forward_phase(const u32* __restrict__ dig, cpx* __restrict__ spec, cpx* __restrict__ ybuf, const cpx* __restrict__ tw,
-                                              int bgbit, int gw, int lane) {
+__device__ __forceinline__ void forward_phase(const u32* __restrict__ dig, cpx* __restrict__ spec, const cpx* __restrict__ tw, int bgbit, int gw, int lane) {
 #pragma unroll 1
     for (int s = gw; s < 2 * L; s += WPG) {
         cpx v[16];
         fwd_stage0_digits(v, dig + s * 256, lane, 1 << (bgbit - 1));
         fwd_passA(v, tw, lane >> 4);
-        rows_to_cols(v, alias_for(L) ? spec + s * M : ybuf + gw * M, lane);
+        rows_to_cols(v, spec + s * M, lane);
         fwd_passB(v, tw, lane);
 #pragma unroll
         for (int c = 0; c < 16; c++) spec[s * M + c * 32 + lane] = v[c];
@@ -149,14 +148,11 @@ __device__ __forceinline__ void recombine_phase(u64* __restrict__ acc, const cpx
     }
 }
 
-#ifndef MKF_KEY_PREFETCH
-#define MKF_KEY_PREFETCH 1
-#endif
 // smem pointers of one gate slot
 struct GateMem {
     u64* acc;
     u32* dig;
-    cpx *spec, *ybuf;
+    cpx* buf;      // max(2l, 6) x [512]: digit spectra, then limb outputs (index 2 limb + out)
 };
 template <int L>
 __device__ __forceinline__ GateMem gate_mem(unsigned char* smem_raw, int slot) {
@@ -164,8 +160,7 @@ __device__ __forceinline__ GateMem gate_mem(unsigned char* smem_raw, int slot) {
     GateMem m;
     m.acc = reinterpret_cast<u64*>(base);
     m.dig = reinterpret_cast<u32*>(base + 2 * N * 8);
-    m.spec = reinterpret_cast<cpx*>(base + 2 * N * 8 + 2 * L * N);
-    m.ybuf = alias_for(L) ? m.spec : m.spec + 2 * L * M;
+    m.buf = reinterpret_cast<cpx*>(base + 2 * N * 8 + 2 * L * N);
     return m;
 }
 
@@ -179,13 +174,12 @@ __device__ __forceinline__ void extprod_step(const GateMem& m, const cpx* __rest
     const double2* kp = reinterpret_cast<const double2*>(key) + ((size_t)out * LIMBS + limb) * M + lane;   // [s][out][limb][512]
     decompose<L, MUX>(m.acc, m.dig, a, bgbit, gtid);
     mk::gate_barrier<WPG>(bar_id);
-    forward_phase<L>(m.dig, m.spec, m.ybuf, tw, bgbit, gw, lane);
+    forward_phase<L>(m.dig, m.buf, tw, bgbit, gw, lane);
     mk::gate_barrier<WPG>(bar_id);
     {   // warp (limb, out): multiply-accumulate over the 2L spectra, inverse transform up to the last stage
         cpx v[16];
 #pragma unroll
         for (int c = 0; c < 16; c++) v[c] = cpx{0.0, 0.0};
-#if MKF_KEY_PREFETCH
         // every key register is refilled for the next digit polynomial as soon as it is consumed: the phase waits on L2 once per step, not 2l times
         double2 kreg[16];
 #pragma unroll
@@ -193,7 +187,7 @@ __device__ __forceinline__ void extprod_step(const GateMem& m, const cpx* __rest
 #pragma unroll
         for (int s = 0; s < 2 * L; s++) {
             const double2* kn = kp + (size_t)(s + 1) * (2 * LIMBS * M);
-            const cpx* xs = m.spec + s * M + lane;
+            const cpx* xs = m.buf + s * M + lane;
 #pragma unroll
             for (int c = 0; c < 16; c++) {
                 const double2 k = kreg[c];
@@ -203,25 +197,11 @@ __device__ __forceinline__ void extprod_step(const GateMem& m, const cpx* __rest
                 v[c].y = fma(x.x, k.y, fma(x.y, k.x, v[c].y));
             }
         }
-#else
-#pragma unroll 1
-        for (int s = 0; s < 2 * L; s++) {
-            const double2* ks = kp + (size_t)s * (2 * LIMBS * M);
-            const cpx* xs = m.spec + s * M + lane;
-#pragma unroll
-            for (int c = 0; c < 16; c++) {
-                const double2 k = __ldg(ks + c * 32);
-                const cpx x = xs[c * 32];
-                v[c].x = fma(x.x, k.x, fma(-x.y, k.y, v[c].x));
-                v[c].y = fma(x.x, k.y, fma(x.y, k.x, v[c].y));
-            }
-        }
-#endif
-        if (alias_for(L)) mk::gate_barrier<WPG>(bar_id);            // every warp is done reading the spectra
-        inverse_to_buffer(v, m.ybuf + gw * M, tw, lane);
+        mk::gate_barrier<WPG>(bar_id);                              // every warp is done reading the spectra: the buffers change roles
+        inverse_to_buffer(v, m.buf + gw * M, tw, lane);
     }
     mk::gate_barrier<WPG>(bar_id);
-    recombine_phase<MUX>(m.acc, m.ybuf, tw, gtid);
+    recombine_phase<MUX>(m.acc, m.buf, tw, gtid);
     mk::gate_barrier<WPG>(bar_id);
 }
 
@@ -271,8 +251,8 @@ __device__ __forceinline__ void blind_rotate_body(const mk::BlindRotateArgs& p, 
         for (int i = gtid; i < 2 * N; i += TPG) ao[i] = (int64_t)acc[i];
     }
     if (p.ksk) {   // fused extraction + key switch (the host only sets ksk when mk::ks_fusable(n, t)); scratch: the spectra
-        if (p.ks_t == 3) mk::fused_keyswitch<3, WPG>(acc, reinterpret_cast<u32*>(m.spec), p, g, gtid, bar_id);
-        else mk::fused_keyswitch<5, WPG>(acc, reinterpret_cast<u32*>(m.spec), p, g, gtid, bar_id);
+        if (p.ks_t == 3) mk::fused_keyswitch<3, WPG>(acc, reinterpret_cast<u32*>(m.buf), p, g, gtid, bar_id);
+        else mk::fused_keyswitch<5, WPG>(acc, reinterpret_cast<u32*>(m.buf), p, g, gtid, bar_id);
         return;
     }
     int32_t* ext = p.ext_out + (size_t)g * (N + 1);
