@@ -30,6 +30,12 @@
  *    All calls on one context share its scratch buffers and timing events, so
  *    they must be stream-ordered with each other (same stream, or ordered by
  *    events): two *_dev calls in flight on unordered streams race.
+ *  - arithmetic: every external product is exact mod (X^N + 1, 2^64).  Contexts with
+ *    N = 1024 and Torus64 keys compute it on the FP64 pipe (an exact three-limb
+ *    folded complex FFT, csrc/fft64.cuh); Torus32 mode and N = 2048 on three / four
+ *    28-bit NTT primes with a CRT lift.  Results are bit-identical either way;
+ *    MKTFHE_B200_FFT=0 in the environment of mktfhe_create selects the NTT kernels
+ *    (A/B runs), mktfhe_describe reports which engine a context runs.
  *  - ciphertext layout: MKLweSample (mk_internals.jl:23-37) `a::Array{Int32,2}`
  *    of shape (n, k), column-major == int32 [k][n] per sample; batches are
  *    int32 a[G][k][n], int32 b[G].
@@ -212,7 +218,8 @@ int mktfhe_negacyclic_mul_batch(mktfhe_ctx *ctx, size_t G, const int64_t *a, con
 /* hash of the kernel sources this library was built from (the ncu captures under profiles/ record the id they apply to) */
 const char *mktfhe_build_id(void);
 /* one-line JSON description of the context: build id, devices, how the keys were broadcast, whether the most recent
- * bootstrap ran the key switch as the blind-rotate kernel's epilogue, gates per CTA, key bytes */
+ * bootstrap ran the key switch as the blind-rotate kernel's epilogue, the external-product engine ("fft64" / "ntt_rns"),
+ * gates per CTA, key bytes */
 int mktfhe_describe(const mktfhe_ctx *ctx, char *buf, size_t cap);
 /* kernels launched by this context so far (all devices) */
 uint64_t mktfhe_launch_count(const mktfhe_ctx *ctx);
