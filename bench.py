@@ -461,6 +461,7 @@ def run_single_key(args):
     pname = "tfhe_parameters_80" if args.parties == 80 else "tfhe_parameters_128"      # --parties 80 selects the 80-bit set (Torus32 mode)
     sk, ck = T1.make_key_pair(rng, getattr(T1, pname)())
     eng = T1.engine_for(ck, device=0)
+    engine = eng.ctx.describe().get("external_product", "ntt_rns")
     t_keys = time.perf_counter() - t0
     G, n = args.gates, sk.params.lwe_size
     bits = rng.integers(0, 2, (2, G)).astype(bool)
@@ -497,7 +498,8 @@ def run_single_key(args):
     p = sk.params
     print(json.dumps({"metric": f"bootstrapped single-key TFHE NAND gates/sec ({pname})", "value": G * args.steps / (ms * 1e-3), "unit": UNIT,
                       "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                      "vs_baseline": None, "dtype": "u32 RNS (three 28-bit-prime NTTs + CRT), Torus32 carried as v << 32 / int32 LWE", "data": "synthetic",
+                      "vs_baseline": None, "dtype": ("f64 (three-limb folded FFT, rounded to the exact integers mod 2^64)" if engine == "fft64" else
+                                                     "u32 RNS (three 28-bit-prime NTTs + CRT)") + ", Torus32 carried as v << 32 / int32 LWE", "data": "synthetic",
                       "config": {"workload": f"single-key NAND x{G} (api.jl:76-113: n={p.lwe_size} N={p.rlwe_polynomial_degree} l={p.bs_decomp_length} "
                                              f"Bg=2^{p.bs_log2_base} t={p.ks_decomp_length} Bks=2^{p.ks_log2_base}), the 3gen engine with one party",
                                  "key_setup_s": round(t_keys, 2)},
