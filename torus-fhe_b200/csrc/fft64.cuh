@@ -132,19 +132,29 @@ __device__ __forceinline__ void inverse_to_buffer(cpx (&v)[16], cpx* __restrict_
 }
 // last inverse stage, untwist, rounding, limb recombination, accumulator update: task (out, j) -> coefficients j + 256 b
 template <bool MUX>
+__device__ __forceinline__ void recombine_task(u64* __restrict__ acc, const cpx* __restrict__ ybuf, const cpx wj, const cpx ut, int out, int j) {
+    uint64_t R[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int limb = 0; limb < LIMBS; limb++) {
+        const cpx* Y = ybuf + (limb * 2 + out) * M;
+        recombine_limb(R, Y[j], Y[j + 256], wj, ut, limb == 0 ? 0 : limb == 1 ? LIMB_SHIFT1 : LIMB_SHIFT2);
+    }
+    u64* ap = acc + out * N + j;
+#pragma unroll
+    for (int b = 0; b < 4; b++) ap[256 * b] = (MUX ? ap[256 * b] : 0) + (R[b] - ROUND_K);
+}
+// 512 tasks on 192 threads: thread t takes j = t for both outputs (one pair of twiddle loads), and the j = 192 .. 255 left over go to
+// threads 0 .. 127 as (j = 192 + t / 2, out = t & 1)
+template <bool MUX>
 __device__ __forceinline__ void recombine_phase(u64* __restrict__ acc, const cpx* __restrict__ ybuf, const cpx* __restrict__ tw, int gtid) {
-    for (int task = gtid; task < 512; task += TPG) {
-        const int out = task >> 8, j = task & 255;
-        const cpx wj = tw[T_WJ + j], ut = tw[T_UT + j];
-        uint64_t R[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int limb = 0; limb < LIMBS; limb++) {
-            const cpx* Y = ybuf + (limb * 2 + out) * M;
-            recombine_limb(R, Y[j], Y[j + 256], wj, ut, limb == 0 ? 0 : limb == 1 ? LIMB_SHIFT1 : LIMB_SHIFT2);
-        }
-        u64* ap = acc + out * N + j;
-#pragma unroll
-        for (int b = 0; b < 4; b++) ap[256 * b] = (MUX ? ap[256 * b] : 0) + (R[b] - ROUND_K);
+    {
+        const cpx wj = tw[T_WJ + gtid], ut = tw[T_UT + gtid];
+        recombine_task<MUX>(acc, ybuf, wj, ut, 0, gtid);
+        recombine_task<MUX>(acc, ybuf, wj, ut, 1, gtid);
+    }
+    if (gtid < 128) {
+        const int j = 192 + (gtid >> 1);
+        recombine_task<MUX>(acc, ybuf, tw[T_WJ + j], tw[T_UT + j], gtid & 1, j);
     }
 }
 

@@ -17,13 +17,15 @@ constexpr int LIMB_BITS0 = 22, LIMB_BITS1 = 21;
 constexpr int LIMB_SHIFT1 = 22, LIMB_SHIFT2 = 43;
 
 // twiddle table, complex-double entries (staged in shared memory by the kernels)
-constexpr int TF_A = 0;                 // forward stages d = 1..4 (warp-half-uniform): TF_A + 2^d - 2 + g, g = group = pos >> (9 - d)
+constexpr int TF_A = 0;                 // forward stages d = 1..4 (warp-half-uniform): TF_A + 2^d - 2 + g, g = group = pos >> (9 - d); the kernels load
+                                        // g = h 2^(d-1) and multiply by compile-time constants for the other groups of a half-warp
 constexpr int TF_B = 32;                // forward stages d = 5..8 (per lane): TF_B + 32 (d - 5) + lane = s(d, lane 2^(d-5)); the other groups of a
                                         // lane are this value times a compile-time constant (fft64_core.cuh, fwd_passB)
-constexpr int TI_A = TF_B + 128;        // inverse pass A', row span rs = 1, 2, 4, 8: TI_A + 16 (rs - 1) + (r mod rs) 16 + l16
-constexpr int T_WJ = TI_A + 240;        // last inverse stage: exp(-2 pi i j / 512), j < 256
+constexpr int TI_A = TF_B + 128;        // inverse pass A', row span rs = 2^t, t = 0..3: TI_A + 16 t + l16 = exp(-2 pi i l16 / (32 rs)); the factor
+                                        // exp(-2 pi i (r mod rs) / (2 rs)) of the other rows is a compile-time constant
+constexpr int T_WJ = TI_A + 64;        // last inverse stage: exp(-2 pi i j / 512), j < 256
 constexpr int T_UT = T_WJ + 256;        // untwist zeta^-j, j < 256 (zeta^-(j + 256) = zeta^-j exp(-i pi / 4))
-constexpr int T_ENTRIES = T_UT + 256;   // 912 entries = 14 592 bytes
+constexpr int T_ENTRIES = T_UT + 256;   // 736 entries = 11 776 bytes
 constexpr int TW_BYTES = T_ENTRIES * 16;
 
 // bootstrapping key in the FFT layout: complex double [elem][s = src l + q][out 2][limb 3][512 points], point (c, lane) at c 32 + lane

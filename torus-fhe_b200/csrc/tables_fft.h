@@ -32,9 +32,9 @@ struct HostTablesFFT {
         for (int d = 5; d <= 8; d++)
             for (int lane = 0; lane < 32; lane++) put(TF_B + 32 * (d - 5) + lane, fwd_ang(d, lane * (1 << (d - 5))));
         // inverse, decimation in time, bit-reversed -> natural: span sp, position twiddle exp(-2 pi i (pos mod sp) / (2 sp));
-        // pass A' covers sp = 16 rs, rs = 1, 2, 4, 8, pos mod sp = (r mod rs) 16 + l16
-        for (int rs = 1; rs <= 8; rs *= 2)
-            for (int e = 0; e < 16 * rs; e++) put(TI_A + 16 * (rs - 1) + e, -2.0L * PI * (long double)e / (long double)(32 * rs));
+        // pass A' covers sp = 16 rs, rs = 2^t, pos mod sp = (r mod rs) 16 + l16; the table holds the rows r mod rs = 0
+        for (int t = 0; t < 4; t++)
+            for (int e = 0; e < 16; e++) put(TI_A + 16 * t + e, -2.0L * PI * (long double)e / (long double)(32 << t));
         for (int j = 0; j < 256; j++) {
             put(T_WJ + j, -2.0L * PI * (long double)j / 512.0L);        // last inverse stage (span 256)
             put(T_UT + j, -PI * (long double)j / 1024.0L);              // untwist zeta^-j, zeta = exp(i pi / N)
