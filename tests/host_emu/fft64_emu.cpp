@@ -142,7 +142,7 @@ int main() {
         for (int j = 0; j < 256; j++) {
             uint64_t R[4] = {0, 0, 0, 0};
             for (int limb = 0; limb < LIMBS; limb++) {
-                recombine_limb(R, Y[limb][j], Y[limb][j + 256], TW[T_WJ + j], TW[T_UT + j], limb == 0 ? 0 : limb == 1 ? LIMB_SHIFT1 : LIMB_SHIFT2);
+                recombine_limb(R, Y[limb][j], Y[limb][j + 256], TW[T_WJ + j], TW[T_UT + j], limb_shift(LIMBS, limb));
                 // rounding margin of this limb: redo the last stage in plain arithmetic
                 cpx lo = Y[limb][j], hi = Y[limb][j + 256];
                 ct(lo, hi, TW[T_WJ + j]);
@@ -150,8 +150,8 @@ int main() {
                 worst_frac = std::fmax(worst_frac, std::fmax(std::fabs(e.x - std::nearbyint(e.x)), std::fabs(e.y - std::nearbyint(e.y))));
             }
             for (int b = 0; b < 4; b++)
-                CHECK(R[b] - ROUND_K == want[j + 256 * b], "trial %d coefficient %d: got %llx want %llx", trial, j + 256 * b,
-                      (unsigned long long)(R[b] - ROUND_K), (unsigned long long)want[j + 256 * b]);
+                CHECK(R[b] - round_k(LIMBS) == want[j + 256 * b], "trial %d coefficient %d: got %llx want %llx", trial, j + 256 * b,
+                      (unsigned long long)(R[b] - round_k(LIMBS)), (unsigned long long)want[j + 256 * b]);
             if (fails > 5) break;
         }
     }

@@ -31,14 +31,17 @@ constexpr int WPG = 6, TPG = 32 * WPG;
 // per gate: Torus64 accumulator, packed digits (one byte per coefficient), and max(2l, 6) buffers of 512 complex values: the 2l digit spectra
 // during the forward transforms and the multiply-accumulate, then (one gate barrier later) the 6 limb outputs.  Separate buffers for the
 // two roles would fit at l = 2 and save that barrier, but measured 0.9 % slower: the 64 KB they cost are worth more as L1 for the key stream.
-__host__ __device__ constexpr int nbuf(int l) { return 2 * l > 6 ? 2 * l : 6; }
-__host__ __device__ constexpr size_t gate_bytes(int l) { return (size_t)2 * N * 8 + (size_t)2 * l * N + (size_t)nbuf(l) * M * 16; }
-__host__ __device__ constexpr int gpc_for(int l) {
+// Torus32 mode (wide = true): 16-bit digit fields (2 bytes per coefficient) and two key limbs, i.e. max(2l, 4) buffers.
+__host__ __device__ constexpr int nbuf(int l, int nl = LIMBS) { return 2 * l > 2 * nl ? 2 * l : 2 * nl; }
+__host__ __device__ constexpr size_t gate_bytes(int l, bool wide = false) {
+    return (size_t)2 * N * 8 + (size_t)2 * l * N * (wide ? 2 : 1) + (size_t)nbuf(l, wide ? LIMBS_T32 : LIMBS) * M * 16;
+}
+__host__ __device__ constexpr int gpc_for(int l, bool wide = false) {
     int g = 2;
-    while (g > 1 && (size_t)TW_BYTES + (size_t)g * gate_bytes(l) > 227 * 1024) g--;
+    while (g > 1 && (size_t)TW_BYTES + (size_t)g * gate_bytes(l, wide) > 227 * 1024) g--;
     return g;
 }
-__host__ __device__ constexpr size_t cta_bytes(int l, int gpc) { return (size_t)TW_BYTES + (size_t)gpc * gate_bytes(l); }
+__host__ __device__ constexpr size_t cta_bytes(int l, int gpc, bool wide = false) { return (size_t)TW_BYTES + (size_t)gpc * gate_bytes(l, wide); }
 
 // row layout -> column layout and back through a 512-entry buffer, XOR-swizzled so that both sides are conflict-free
 __device__ __forceinline__ void rows_to_cols(cpx (&v)[16], cpx* __restrict__ buf, int lane) {
@@ -66,20 +69,23 @@ __device__ __forceinline__ void stage_tables(cpx* tw_s, const cpx* __restrict__ 
     for (int i = threadIdx.x; i < T_ENTRIES; i += blockDim.x) dst[i] = __ldg(src + i);
 }
 
-// Phase 1 of a step: rotate-subtract and gadget-decompose (tgsw.jl:112-138); digits biased to [0, Bg), dig [2L][256] words, word j of
-// a polynomial = the bytes of coefficients j, j + 256, j + 512, j + 768
-template <int L, bool MUX>
+// Phase 1 of a step: rotate-subtract and gadget-decompose (tgsw.jl:112-138); digits biased to [0, Bg).  Byte fields: dig [2L][256] words, word j of
+// a polynomial = the bytes of coefficients j, j + 256, j + 512, j + 768.  WIDE (16-bit fields): dig [2L][2][256] words, word (0, j) = coefficients
+// (j, j + 512), word (1, j) = (j + 256, j + 768).  BODY: the mask operand is zero; only the body polynomial acc[1] is decomposed (s < L).
+template <int L, bool MUX, bool WIDE = false, bool BODY = false>
 __device__ __forceinline__ void decompose(const u64* __restrict__ acc, u32* __restrict__ dig, int a, int bgbit, int gtid) {
     u64 off = 0;
 #pragma unroll
     for (int q = 1; q <= L; q++) off += ((u64)1 << (64 - q * bgbit)) << (bgbit - 1);   // tgsw.jl:24-30
     const u32 dmask = (1u << bgbit) - 1;
-    for (int task = gtid; task < 512; task += TPG) {
-        const int c = task >> 8, j = task & 255;
+    for (int task = gtid; task < (BODY ? 256 : 512); task += TPG) {
+        const int c = BODY ? 1 : task >> 8, j = task & 255;
         const u64* poly = acc + c * N;
-        u32 packed[L];
+        u32 packed[L], packed_b[WIDE ? L : 1];
 #pragma unroll
         for (int q = 0; q < L; q++) packed[q] = 0;
+#pragma unroll
+        for (int q = 0; q < (WIDE ? L : 1); q++) packed_b[q] = 0;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const int i = j + 256 * b;
@@ -94,11 +100,26 @@ __device__ __forceinline__ void decompose(const u64* __restrict__ acc, u32* __re
             }
             t += off;
 #pragma unroll
-            for (int q = 0; q < L; q++) packed[q] |= ((u32)(t >> (64 - (q + 1) * bgbit)) & dmask) << (8 * b);
+            for (int q = 0; q < L; q++) {
+                const u32 d = (u32)(t >> (64 - (q + 1) * bgbit)) & dmask;
+                if (WIDE) {
+                    if (b & 1) packed_b[q] |= d << (8 * (b - 1));     // b = 1 -> low field, b = 3 -> high field of word (1, j)
+                    else packed[q] |= d << (8 * b);                    // b = 0 -> low field, b = 2 -> high field of word (0, j)
+                } else {
+                    packed[q] |= d << (8 * b);
+                }
+            }
         }
         const int src = 1 - c;   // src 0 = body = acc[1]
 #pragma unroll
-        for (int q = 0; q < L; q++) dig[(src * L + q) * 256 + j] = packed[q];
+        for (int q = 0; q < L; q++) {
+            if (WIDE) {
+                dig[((src * L + q) * 2 + 0) * 256 + j] = packed[q];
+                dig[((src * L + q) * 2 + 1) * 256 + j] = packed_b[q];
+            } else {
+                dig[(src * L + q) * 256 + j] = packed[q];
+            }
+        }
     }
 }
 
@@ -108,12 +129,13 @@ __device__ __forceinline__ void decompose(const u64* __restrict__ acc, u32* __re
 // Per gate: buf = max(2L, 6) buffers [512]: the 2L digit spectra, later the 6 limb outputs (index lo = 2 limb + out).
 
 // forward transforms of the 2L digit polynomials by the warps gw = s, s + 6, ..; spectrum point (c, lane) at c 32 + lane
-template <int L>
+template <int NS, bool WIDE>
 __device__ __forceinline__ void forward_phase(const u32* __restrict__ dig, cpx* __restrict__ spec, const cpx* __restrict__ tw, int bgbit, int gw, int lane) {
 #pragma unroll 1
-    for (int s = gw; s < 2 * L; s += WPG) {
+    for (int s = gw; s < NS; s += WPG) {
         cpx v[16];
-        fwd_stage0_digits(v, dig + s * 256, lane, 1 << (bgbit - 1));
+        if (WIDE) fwd_stage0_digits_wide(v, dig + s * 512, dig + s * 512 + 256, lane, 1 << (bgbit - 1));
+        else fwd_stage0_digits(v, dig + s * 256, lane, 1 << (bgbit - 1));
         fwd_passA(v, tw, lane >> 4);
         rows_to_cols(v, spec + s * M, lane);
         fwd_passB(v, tw, lane);
@@ -130,31 +152,35 @@ __device__ __forceinline__ void inverse_to_buffer(cpx (&v)[16], cpx* __restrict_
 #pragma unroll
     for (int r = 0; r < 16; r++) buf[h * 256 + r * 16 + l16] = v[r];
 }
-// last inverse stage, untwist, rounding, limb recombination, accumulator update: task (out, j) -> coefficients j + 256 b
-template <bool MUX>
+// last inverse stage, untwist, rounding, limb recombination, accumulator update: task (out, j) -> coefficients j + 256 b.
+// NL = 2 (Torus32 mode): the exact product of the unshifted 32-bit keys is added as R << 32.
+template <bool MUX, int NL>
 __device__ __forceinline__ void recombine_task(u64* __restrict__ acc, const cpx* __restrict__ ybuf, const cpx wj, const cpx ut, int out, int j) {
     uint64_t R[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int limb = 0; limb < LIMBS; limb++) {
+    for (int limb = 0; limb < NL; limb++) {
         const cpx* Y = ybuf + (limb * 2 + out) * M;
-        recombine_limb(R, Y[j], Y[j + 256], wj, ut, limb == 0 ? 0 : limb == 1 ? LIMB_SHIFT1 : LIMB_SHIFT2);
+        recombine_limb(R, Y[j], Y[j + 256], wj, ut, limb_shift(NL, limb));
     }
     u64* ap = acc + out * N + j;
 #pragma unroll
-    for (int b = 0; b < 4; b++) ap[256 * b] = (MUX ? ap[256 * b] : 0) + (R[b] - ROUND_K);
+    for (int b = 0; b < 4; b++) {
+        const u64 r = R[b] - round_k(NL);
+        ap[256 * b] = (MUX ? ap[256 * b] : 0) + (NL == 2 ? r << 32 : r);
+    }
 }
 // 512 tasks on 192 threads: thread t takes j = t for both outputs (one pair of twiddle loads), and the j = 192 .. 255 left over go to
 // threads 0 .. 127 as (j = 192 + t / 2, out = t & 1)
-template <bool MUX>
+template <bool MUX, int NL>
 __device__ __forceinline__ void recombine_phase(u64* __restrict__ acc, const cpx* __restrict__ ybuf, const cpx* __restrict__ tw, int gtid) {
     {
         const cpx wj = tw[T_WJ + gtid], ut = tw[T_UT + gtid];
-        recombine_task<MUX>(acc, ybuf, wj, ut, 0, gtid);
-        recombine_task<MUX>(acc, ybuf, wj, ut, 1, gtid);
+        recombine_task<MUX, NL>(acc, ybuf, wj, ut, 0, gtid);
+        recombine_task<MUX, NL>(acc, ybuf, wj, ut, 1, gtid);
     }
     if (gtid < 128) {
         const int j = 192 + (gtid >> 1);
-        recombine_task<MUX>(acc, ybuf, tw[T_WJ + j], tw[T_UT + j], gtid & 1, j);
+        recombine_task<MUX, NL>(acc, ybuf, tw[T_WJ + j], tw[T_UT + j], gtid & 1, j);
     }
 }
 
@@ -164,59 +190,62 @@ struct GateMem {
     u32* dig;
     cpx* buf;      // max(2l, 6) x [512]: digit spectra, then limb outputs (index 2 limb + out)
 };
-template <int L>
+template <int L, bool WIDE = false>
 __device__ __forceinline__ GateMem gate_mem(unsigned char* smem_raw, int slot) {
-    unsigned char* base = smem_raw + TW_BYTES + (size_t)slot * gate_bytes(L);
+    unsigned char* base = smem_raw + TW_BYTES + (size_t)slot * gate_bytes(L, WIDE);
     GateMem m;
     m.acc = reinterpret_cast<u64*>(base);
     m.dig = reinterpret_cast<u32*>(base + 2 * N * 8);
-    m.buf = reinterpret_cast<cpx*>(base + 2 * N * 8 + 2 * L * N);
+    m.buf = reinterpret_cast<cpx*>(base + 2 * N * 8 + 2 * L * N * (WIDE ? 2 : 1));
     return m;
 }
 
 // One step of ONE gate by its 192 threads (every warp streams its own key polynomials: each key value is loaded once per gate and each
 // spectrum value six times per gate).
-template <int L, bool MUX>
+template <int L, bool MUX, int NL = LIMBS, bool WIDE = false, bool BODY = false>
 __device__ __forceinline__ void extprod_step(const GateMem& m, const cpx* __restrict__ tw, const cpx* __restrict__ key, int a, int bgbit, int bar_id,
                                              int gtid) {
+    constexpr int NS = BODY ? L : 2 * L;                            // digit polynomials (BODY: the body's only; they are s = 0 .. L-1)
     const int gw = gtid >> 5, lane = gtid & 31;
-    const int limb = gw >> 1, out = gw & 1;
-    const double2* kp = reinterpret_cast<const double2*>(key) + ((size_t)out * LIMBS + limb) * M + lane;   // [s][out][limb][512]
-    decompose<L, MUX>(m.acc, m.dig, a, bgbit, gtid);
+    const int limb = gw >> 1, out = gw & 1;                         // warps 0 .. 2 NL - 1 each own one limb output
+    const double2* kp = reinterpret_cast<const double2*>(key) + ((size_t)out * NL + limb) * M + lane;   // [s][out][limb][512]
+    decompose<L, MUX, WIDE, BODY>(m.acc, m.dig, a, bgbit, gtid);
     mk::gate_barrier<WPG>(bar_id);
-    forward_phase<L>(m.dig, m.buf, tw, bgbit, gw, lane);
+    forward_phase<NS, WIDE>(m.dig, m.buf, tw, bgbit, gw, lane);
     mk::gate_barrier<WPG>(bar_id);
-    {   // warp (limb, out): multiply-accumulate over the 2L spectra, inverse transform up to the last stage
+    {   // warp (limb, out): multiply-accumulate over the spectra, inverse transform up to the last stage
         cpx v[16];
+        if (NL == LIMBS || gw < 2 * NL) {
 #pragma unroll
-        for (int c = 0; c < 16; c++) v[c] = cpx{0.0, 0.0};
-        // every key register is refilled for the next digit polynomial as soon as it is consumed: the phase waits on L2 once per step, not 2l times
-        double2 kreg[16];
+            for (int c = 0; c < 16; c++) v[c] = cpx{0.0, 0.0};
+            // every key register is refilled for the next digit polynomial as soon as it is consumed: the phase waits on L2 once per step
+            double2 kreg[16];
 #pragma unroll
-        for (int c = 0; c < 16; c++) kreg[c] = __ldg(kp + c * 32);
+            for (int c = 0; c < 16; c++) kreg[c] = __ldg(kp + c * 32);
 #pragma unroll
-        for (int s = 0; s < 2 * L; s++) {
-            const double2* kn = kp + (size_t)(s + 1) * (2 * LIMBS * M);
-            const cpx* xs = m.buf + s * M + lane;
+            for (int s = 0; s < NS; s++) {
+                const double2* kn = kp + (size_t)(s + 1) * (2 * NL * M);
+                const cpx* xs = m.buf + s * M + lane;
 #pragma unroll
-            for (int c = 0; c < 16; c++) {
-                const double2 k = kreg[c];
-                if (s + 1 < 2 * L) kreg[c] = __ldg(kn + c * 32);
-                const cpx x = xs[c * 32];
-                v[c].x = fma(x.x, k.x, fma(-x.y, k.y, v[c].x));
-                v[c].y = fma(x.x, k.y, fma(x.y, k.x, v[c].y));
+                for (int c = 0; c < 16; c++) {
+                    const double2 k = kreg[c];
+                    if (s + 1 < NS) kreg[c] = __ldg(kn + c * 32);
+                    const cpx x = xs[c * 32];
+                    v[c].x = fma(x.x, k.x, fma(-x.y, k.y, v[c].x));
+                    v[c].y = fma(x.x, k.y, fma(x.y, k.x, v[c].y));
+                }
             }
         }
         mk::gate_barrier<WPG>(bar_id);                              // every warp is done reading the spectra: the buffers change roles
-        inverse_to_buffer(v, m.buf + gw * M, tw, lane);
+        if (NL == LIMBS || gw < 2 * NL) inverse_to_buffer(v, m.buf + gw * M, tw, lane);
     }
     mk::gate_barrier<WPG>(bar_id);
-    recombine_phase<MUX>(m.acc, m.buf, tw, gtid);
+    recombine_phase<MUX, NL>(m.acc, m.buf, tw, gtid);
     mk::gate_barrier<WPG>(bar_id);
 }
 
 // GPC gates per CTA, six warps per gate; prologue, k n steps, extraction and key switch as in mk::blind_rotate_body
-template <int L, int GPC>
+template <int L, int GPC, int NL = LIMBS, bool WIDE = false>
 __device__ __forceinline__ void blind_rotate_body(const mk::BlindRotateArgs& p, const cpx* __restrict__ key_fft, const cpx* __restrict__ tw_g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx* tw = reinterpret_cast<cpx*>(smem_raw);
@@ -225,7 +254,7 @@ __device__ __forceinline__ void blind_rotate_body(const mk::BlindRotateArgs& p, 
     const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot;
     const int g = p.g0 + blockIdx.x * GPC + slot;
     if (g >= p.G) return;   // no CTA-wide barrier below this line
-    const GateMem m = gate_mem<L>(smem_raw, slot);
+    const GateMem m = gate_mem<L, WIDE>(smem_raw, slot);
     u64* acc = m.acc;
     const int kn = p.k * p.n;
     const mk::GateLinear lin = p.gate_ids ? mk::gate_linear(__ldg(p.gate_ids + g)) : p.lin;
@@ -243,7 +272,7 @@ __device__ __forceinline__ void blind_rotate_body(const mk::BlindRotateArgs& p, 
         }
     }
     mk::gate_barrier<WPG>(bar_id);
-    const size_t estride = bsk_elem_cpx(L);
+    const size_t estride = bsk_elem_cpx(L, NL);
     const size_t abase = (size_t)g * kn;
     int32_t rx = __ldg(p.xa + abase), ry = lin.cy ? __ldg(p.ya + abase) : 0, rz = lin.cz ? __ldg(p.za + abase) : 0;
     for (int it = 0; it < kn; it++) {
@@ -254,7 +283,7 @@ __device__ __forceinline__ void blind_rotate_body(const mk::BlindRotateArgs& p, 
             if (lin.cz) rz = __ldg(p.za + abase + it + 1);
         }
         if (a == 0) continue;   // 3gen_mk_internals.jl:69 (uniform across the gate)
-        extprod_step<L, true>(m, tw, key_fft + (size_t)it * estride, a, p.bgbit, bar_id, gtid);
+        extprod_step<L, true, NL, WIDE>(m, tw, key_fft + (size_t)it * estride, a, p.bgbit, bar_id, gtid);
     }
     if (p.acc_out) {
         int64_t* ao = p.acc_out + (size_t)g * 2 * N;
@@ -280,11 +309,19 @@ template <int L, int GPC>
 __global__ void __maxnreg__(MKF_MAXNREG) blind_rotate_fft_kernel(mk::BlindRotateArgs p, const cpx* __restrict__ key_fft, const cpx* __restrict__ tw_g) {
     blind_rotate_body<L, GPC>(p, key_fft, tw_g);
 }
-
-// parity hook: acc_out[g] = ExtProd(acc_in[g], key[elem[g]])
+// Torus32 mode (mktfhe_params.flags & MKTFHE_FLAG_TORUS32): 16-bit digit fields, two 16-bit limbs of the unshifted 32-bit keys, products added
+// as R << 32.  Exact while 2 l N (Bg / 2) 2^15 <= 2^40; serves tfhe_parameters_80 (Bg = 2^10) and the gadget shapes of the CCS scheme.
 template <int L, int GPC>
+__global__ void __maxnreg__(MKF_MAXNREG) blind_rotate_fft_t32_kernel(mk::BlindRotateArgs p, const cpx* __restrict__ key_fft, const cpx* __restrict__ tw_g) {
+    blind_rotate_body<L, GPC, LIMBS_T32, true>(p, key_fft, tw_g);
+}
+
+// parity hook: acc_out[g] = ExtProd(acc_in[g], key[elem[g]]).  T32: Torus32 mode (values in the top halves of the words); BODY: the mask
+// operand is zero and neither read nor decomposed (the rounds of the CCS hybrid product)
+template <int L, int GPC, bool T32 = false, bool BODY = false>
 __global__ void __maxnreg__(MKF_MAXNREG) extprod_fft_kernel(int G, const cpx* __restrict__ key_fft, const cpx* __restrict__ tw_g, int bgbit,
                                                              const int32_t* __restrict__ elem, const int64_t* __restrict__ acc_in, int64_t* __restrict__ acc_out) {
+    constexpr int NL = T32 ? LIMBS_T32 : LIMBS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx* tw = reinterpret_cast<cpx*>(smem_raw);
     stage_tables(tw, tw_g);
@@ -292,23 +329,23 @@ __global__ void __maxnreg__(MKF_MAXNREG) extprod_fft_kernel(int G, const cpx* __
     const int slot = threadIdx.x / TPG, gtid = threadIdx.x - slot * TPG, bar_id = 1 + slot;
     const int g = blockIdx.x * GPC + slot;
     if (g >= G) return;
-    const GateMem m = gate_mem<L>(smem_raw, slot);
-    for (int i = gtid; i < 2 * N; i += TPG) m.acc[i] = (u64)acc_in[(size_t)g * 2 * N + i];
+    const GateMem m = gate_mem<L, T32>(smem_raw, slot);
+    for (int i = gtid + (BODY ? N : 0); i < 2 * N; i += TPG) m.acc[i] = (u64)acc_in[(size_t)g * 2 * N + i];
     mk::gate_barrier<WPG>(bar_id);
-    extprod_step<L, false>(m, tw, key_fft + (size_t)elem[g] * bsk_elem_cpx(L), 0, bgbit, bar_id, gtid);
+    extprod_step<L, false, NL, T32, BODY>(m, tw, key_fft + (size_t)elem[g] * bsk_elem_cpx(L, NL), 0, bgbit, bar_id, gtid);
     for (int i = gtid; i < 2 * N; i += TPG) acc_out[(size_t)g * 2 * N + i] = (int64_t)m.acc[i];
 }
 
 // One warp per (key polynomial, limb): raw int64 key -> spectrum of the limb, scaled by 1 / 512, in the FFT layout.
-// raw: [n][4 parts][l][N] int64 of one party; task = ((j*4 + part)*l + q)*3 + limb.
+// raw: [n][4 parts][l][N] int64 of one party; task = ((j*4 + part)*l + q)*nl + limb; nl = 3 (Torus64 words) or 2 (Torus32 mode: 32-bit values).
 constexpr int XF_WARPS = 4;
-__global__ void __launch_bounds__(XF_WARPS * 32) bsk_transform_fft_kernel(const int64_t* __restrict__ raw, cpx* __restrict__ bsk, int n, int l, int party,
+__global__ void __launch_bounds__(XF_WARPS * 32) bsk_transform_fft_kernel(const int64_t* __restrict__ raw, cpx* __restrict__ bsk, int n, int l, int nl, int party,
                                                                             const cpx* __restrict__ tw_g, int ntasks) {
     __shared__ cpx bufs[XF_WARPS * M];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int task = blockIdx.x * XF_WARPS + warp;
     if (task >= ntasks) return;
-    const int limb = task % LIMBS, pq = task / LIMBS;
+    const int limb = task % nl, pq = task / nl;
     const int q = pq % l, part = (pq / l) & 3, j = pq / (4 * l);
     // part_1: body<-body, part_2: body<-mask, part_3: mask<-mask, part_4: mask<-body  (tgsw_3gen.jl:109-110)
     const int out = part < 2 ? 1 : 0;
@@ -319,13 +356,13 @@ __global__ void __launch_bounds__(XF_WARPS * 32) bsk_transform_fft_kernel(const 
 #pragma unroll
     for (int r = 0; r < 16; r++) {
         const int jj = 16 * r + l16;
-        v[r] = fwd_stage0_real(key_limb(poly[jj], limb), key_limb(poly[jj + 256], limb), key_limb(poly[jj + 512], limb), key_limb(poly[jj + 768], limb), h);
+        v[r] = fwd_stage0_real(key_limb(poly[jj], limb, nl), key_limb(poly[jj + 256], limb, nl), key_limb(poly[jj + 512], limb, nl), key_limb(poly[jj + 768], limb, nl), h);
     }
     fwd_passA(v, tw_g, h);
     rows_to_cols(v, bufs + warp * M, lane);
     fwd_passB(v, tw_g, lane);
     const size_t e = (size_t)party * n + j;
-    cpx* dst = bsk + e * bsk_elem_cpx(l) + (((size_t)(src * l + q) * 2 + out) * LIMBS + limb) * M;
+    cpx* dst = bsk + e * bsk_elem_cpx(l, nl) + (((size_t)(src * l + q) * 2 + out) * nl + limb) * M;
 #pragma unroll
     for (int c = 0; c < 16; c++) dst[c * 32 + lane] = cpx{v[c].x * (1.0 / M), v[c].y * (1.0 / M)};
 }

@@ -72,6 +72,22 @@ MKF_FN void fwd_stage0_digits(cpx (&v)[16], const uint32_t* __restrict__ dig_s, 
         v[r].y = fma(cs, Q, y0);
     }
 }
+// the same from 16-bit digit fields (Torus32 mode, gadget digits of up to 13 bits): wa[j] = (coefficient j, j + 512), wb[j] = (j + 256, j + 768)
+MKF_FN void fwd_stage0_digits_wide(cpx (&v)[16], const uint32_t* __restrict__ wa, const uint32_t* __restrict__ wb, int lane, int half_bg) {
+    const int h = lane >> 4, l16 = lane & 15;
+    const double cs = h ? -INV_SQRT2 : INV_SQRT2;
+    const double two52 = 4503599627370496.0;
+    const double m0 = two52 + (double)half_bg, mP = two52 + 65536.0, mQ = two52 + (double)(2 * half_bg);
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const uint32_t a = wa[16 * r + l16], b = wb[16 * r + l16];
+        const uint32_t b0 = a & 0xffffu, b2 = a >> 16, b1 = b & 0xffffu, b3 = b >> 16;
+        const double x0 = u2d(b0, m0), y0 = u2d(b2, m0);
+        const double P = u2d(b1 - b3 + 65536u, mP), Q = u2d(b1 + b3, mQ);
+        v[r].x = fma(cs, P, x0);
+        v[r].y = fma(cs, Q, y0);
+    }
+}
 // the same from the four real coefficients (key transform): a0 = a[j], a1 = a[j + 256], a2 = a[j + 512], a3 = a[j + 768]
 MKF_FN cpx fwd_stage0_real(double a0, double a1, double a2, double a3, int h) {
     const double cs = h ? -INV_SQRT2 : INV_SQRT2;
@@ -242,8 +258,11 @@ MKF_FN uint64_t round_bits(double r) {
 #endif
 }
 // Last inverse stage (span 256), untwist and rounding of one limb for the point pair (j, j + 256): lo = Y[j], hi = Y[j + 256];
-// adds the limb's contribution (shifted bit patterns; the caller subtracts ROUND_K once) to R[b] = coefficient j + 256 b
-constexpr uint64_t ROUND_K = ROUND_MAGIC_BITS + (ROUND_MAGIC_BITS << LIMB_SHIFT1) + (ROUND_MAGIC_BITS << LIMB_SHIFT2);
+// adds the limb's contribution (shifted bit patterns; the caller subtracts round_k(nl) once) to R[b] = coefficient j + 256 b
+MKF_FN constexpr uint64_t round_k(int nl) {
+    return nl == 3 ? ROUND_MAGIC_BITS + (ROUND_MAGIC_BITS << limb_shift(3, 1)) + (ROUND_MAGIC_BITS << limb_shift(3, 2))
+                   : ROUND_MAGIC_BITS + (ROUND_MAGIC_BITS << limb_shift(2, 1));
+}
 MKF_FN void recombine_limb(uint64_t (&R)[4], cpx lo, cpx hi, const cpx wj, const cpx ut, int sh) {
     ct(lo, hi, wj);
     const cpx e = cmul(lo, ut), g8 = cmul(hi, ut);      // zeta^-(j + 256) = zeta^-j exp(-i pi / 4)
@@ -253,12 +272,19 @@ MKF_FN void recombine_limb(uint64_t (&R)[4], cpx lo, cpx hi, const cpx wj, const
     R[2] += round_bits(e.y) << sh;     // j + 512
     R[3] += round_bits(f.y) << sh;     // j + 768
 }
-// balanced limbs of a Torus64 key word: k = l0 + l1 2^22 + l2 2^43 (mod 2^64), |l0| <= 2^21, |l1|, |l2| <= 2^20
-MKF_FN double key_limb(int64_t k, int limb) {
-    const int64_t l0 = ((k + (1ll << (LIMB_BITS0 - 1))) & ((1ll << LIMB_BITS0) - 1)) - (1ll << (LIMB_BITS0 - 1));
-    const int64_t k1 = (int64_t)((uint64_t)k - (uint64_t)l0) >> LIMB_BITS0;
-    const int64_t l1 = ((k1 + (1ll << (LIMB_BITS1 - 1))) & ((1ll << LIMB_BITS1) - 1)) - (1ll << (LIMB_BITS1 - 1));
-    const int64_t l2 = (k1 - l1) >> LIMB_BITS1;
+// balanced limbs of a key word.  nl = 3 (Torus64): k = l0 + l1 2^22 + l2 2^43 (mod 2^64), |l0| <= 2^21, |l1|, |l2| <= 2^20;
+// nl = 2 (Torus32 mode, k holds a 32-bit value): k = l0 + l1 2^16 (mod 2^32), |l0|, |l1| <= 2^15
+MKF_FN double key_limb(int64_t k, int limb, int nl = LIMBS) {
+    if (nl == 2) {
+        const int32_t v = (int32_t)k;
+        const int32_t l0 = ((v + (1 << 15)) & 0xFFFF) - (1 << 15);
+        const int32_t l1 = (int32_t)((uint32_t)v - (uint32_t)l0) >> 16;
+        return (double)(limb == 0 ? l0 : l1);
+    }
+    const int64_t l0 = ((k + (1ll << 21)) & ((1ll << 22) - 1)) - (1ll << 21);
+    const int64_t k1 = (int64_t)((uint64_t)k - (uint64_t)l0) >> 22;
+    const int64_t l1 = ((k1 + (1ll << 20)) & ((1ll << 21) - 1)) - (1ll << 20);
+    const int64_t l2 = (k1 - l1) >> 21;
     return (double)(limb == 0 ? l0 : limb == 1 ? l1 : l2);
 }
 // slots of the swizzled transpose buffer: element (half h, row r, column c16) of a warp's 512 points

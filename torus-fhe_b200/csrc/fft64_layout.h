@@ -12,9 +12,10 @@ namespace mkf {
 
 constexpr int N = 1024;        // ring degree (real negacyclic polynomials mod X^N + 1)
 constexpr int M = 512;         // complex points: C[X] / (X^M - i), a~[j] = a[j] + i a[j + M]
-constexpr int LIMBS = 3;       // a Torus64 key word = l0 + l1 2^22 + l2 2^43, balanced limbs of 22 / 21 / 21 bits
-constexpr int LIMB_BITS0 = 22, LIMB_BITS1 = 21;
-constexpr int LIMB_SHIFT1 = 22, LIMB_SHIFT2 = 43;
+// key limbs: a Torus64 key word = l0 + l1 2^22 + l2 2^43 (three balanced limbs of 22 / 21 / 21 bits); a Torus32 key word (Torus32 mode:
+// unshifted 32-bit keys, products added as R << 32) = l0 + l1 2^16 (two balanced limbs of 16 bits)
+constexpr int LIMBS = 3, LIMBS_T32 = 2;
+MKF_HD inline constexpr int limb_shift(int nl, int limb) { return nl == 3 ? (limb == 0 ? 0 : limb == 1 ? 22 : 43) : 16 * limb; }
 
 // twiddle table, complex-double entries (staged in shared memory by the kernels)
 constexpr int TF_A = 0;                 // forward stages d = 1..4 (warp-half-uniform): TF_A + 2^d - 2 + g, g = group = pos >> (9 - d); the kernels load
@@ -28,8 +29,8 @@ constexpr int T_UT = T_WJ + 256;        // untwist zeta^-j, j < 256 (zeta^-(j + 
 constexpr int T_ENTRIES = T_UT + 256;   // 736 entries = 11 776 bytes
 constexpr int TW_BYTES = T_ENTRIES * 16;
 
-// bootstrapping key in the FFT layout: complex double [elem][s = src l + q][out 2][limb 3][512 points], point (c, lane) at c 32 + lane
+// bootstrapping key in the FFT layout: complex double [elem][s = src l + q][out 2][limb nl][512 points], point (c, lane) at c 32 + lane
 // (c = register index, lane = thread of the transform's output layout); values forward(fold(limb)) / 512
-MKF_HD inline constexpr size_t bsk_elem_cpx(int l) { return (size_t)2 * l * 2 * LIMBS * M; }
+MKF_HD inline constexpr size_t bsk_elem_cpx(int l, int nl = LIMBS) { return (size_t)2 * l * 2 * nl * M; }
 
 }  // namespace mkf

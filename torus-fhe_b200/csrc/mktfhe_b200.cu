@@ -179,7 +179,15 @@ size_t br_smem_bytes(const mktfhe_ctx* c) { return mk::cta_smem_bytes(c->prm.l, 
     case 3: KERNEL(3, mkf::gpc_for(3), __VA_ARGS__); break;                 \
     default: KERNEL(4, mkf::gpc_for(4), __VA_ARGS__); break;                \
     }
-size_t fft_smem_bytes(const mktfhe_ctx* c) { return mkf::cta_bytes(c->prm.l, mkf::gpc_for(c->prm.l)); }
+// Torus32-mode FFT instantiations: l = 2, 3, 4
+#define MK_DISPATCH_FFT_T32(c, KERNEL, ...)                                       \
+    switch ((c)->prm.l) {                                                         \
+    case 2: KERNEL(2, mkf::gpc_for(2, true), __VA_ARGS__); break;                 \
+    case 3: KERNEL(3, mkf::gpc_for(3, true), __VA_ARGS__); break;                 \
+    default: KERNEL(4, mkf::gpc_for(4, true), __VA_ARGS__); break;                \
+    }
+size_t fft_smem_bytes(const mktfhe_ctx* c) { return mkf::cta_bytes(c->prm.l, mkf::gpc_for(c->prm.l, c->t32), c->t32); }
+int fft_nl(const mktfhe_ctx* c) { return c->t32 ? mkf::LIMBS_T32 : mkf::LIMBS; }
 
 int set_attrs(mktfhe_ctx* c) {
     if (c->prm.N == mk2k::N) {
@@ -187,6 +195,17 @@ int set_attrs(mktfhe_ctx* c) {
         else CU_TRY(c, cudaFuncSetAttribute(mk2k::blind_rotate2k_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk2k::smem_bytes(2)));
         if (c->prm.l == 1) CU_TRY(c, cudaFuncSetAttribute(mk2k::blind_rotate2k16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk2k::smem_bytes16(1)));
         else CU_TRY(c, cudaFuncSetAttribute(mk2k::blind_rotate2k16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mk2k::smem_bytes16(2)));
+        return MKTFHE_OK;
+    }
+    if (c->fft && c->t32) {
+        const int smf = (int)fft_smem_bytes(c), smf1 = (int)mkf::cta_bytes(c->prm.l, 1, true);
+#define SET_ATTR_FFT_T32(L, GPC, dummy)                                                                                            \
+    CU_TRY(c, cudaFuncSetAttribute(mkf::blind_rotate_fft_t32_kernel<L, GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));   \
+    CU_TRY(c, cudaFuncSetAttribute(mkf::blind_rotate_fft_t32_kernel<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf1));    \
+    CU_TRY(c, cudaFuncSetAttribute(mkf::extprod_fft_kernel<L, GPC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));      \
+    CU_TRY(c, cudaFuncSetAttribute(mkf::extprod_fft_kernel<L, GPC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf));
+        MK_DISPATCH_FFT_T32(c, SET_ATTR_FFT_T32, 0)
+#undef SET_ATTR_FFT_T32
         return MKTFHE_OK;
     }
     const int sm = (int)br_smem_bytes(c);
@@ -259,7 +278,26 @@ void launch_one_gate_per_cta(mktfhe_ctx* c, mk::BlindRotateArgs a, size_t g0, si
 // leaves after its full waves -- of at most one gate per SM runs one gate per CTA instead, on the latency kernel (6 l warps per gate): at
 // l = 2 a gate alone on an SM finishes in 7.3 ms against 12.3 ms for two gates sharing it.  Bit-identical results.
 void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G, cudaStream_t st) {
-    if (c->t32) {   // Torus32 mode: one launch shape (two six-warp gates per CTA)
+    if (c->t32 && c->fft) {   // Torus32 mode on the FFT channel: two gates per CTA, or one for batches of at most one gate per SM
+        mk::BlindRotateArgs h = a;
+        h.g0 = 0; h.G = (int)G;
+        if (G <= (size_t)c->num_sms) {
+            const size_t smf1 = mkf::cta_bytes(c->prm.l, 1, true);
+#define LAUNCH_BR_FFT_T32_1(L, GPC, dummy) mkf::blind_rotate_fft_t32_kernel<L, 1><<<(unsigned)G, mkf::TPG, smf1, st>>>(h, c->d_bsk_fft, c->d_twF)
+            MK_DISPATCH_FFT_T32(c, LAUNCH_BR_FFT_T32_1, 0)
+#undef LAUNCH_BR_FFT_T32_1
+        } else {
+            const size_t smf = fft_smem_bytes(c);
+            const int gf = mkf::gpc_for(c->prm.l, true);
+            const unsigned gridf = (unsigned)((G + gf - 1) / gf);
+#define LAUNCH_BR_FFT_T32(L, GPC, dummy) mkf::blind_rotate_fft_t32_kernel<L, GPC><<<gridf, GPC * mkf::TPG, smf, st>>>(h, c->d_bsk_fft, c->d_twF)
+            MK_DISPATCH_FFT_T32(c, LAUNCH_BR_FFT_T32, 0)
+#undef LAUNCH_BR_FFT_T32
+        }
+        c->launches++;
+        return;
+    }
+    if (c->t32) {   // Torus32 mode, RNS kernels: one launch shape (two six-warp gates per CTA)
         mk::BlindRotateArgs h = a;
         h.g0 = 0; h.G = (int)G;
         const size_t sm = br_smem_bytes(c);
@@ -549,11 +587,12 @@ int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
     c->t32 = !big && (params->reserved & MKTFHE_FLAG_TORUS32);
     c->bsk_ntt_bytes = c->bsk_bytes;
     // FP64 FFT channel: N = 1024, Torus64 keys, byte digits; exact while 2 l N (Bg / 2) 2^21 <= 2^40 (limb products recovered by rounding)
-    c->fft = !big && !c->t32 && std::log2((double)(2 * params->l) * params->N) + (params->bgbit - 1) + 21.0 <= 40.0;
+    //                   Torus32 mode: two 16-bit limbs of the unshifted 32-bit keys, 2 l N (Bg / 2) 2^15 <= 2^40
+    c->fft = !big && std::log2((double)(2 * params->l) * params->N) + (params->bgbit - 1) + (c->t32 ? 15.0 : 21.0) <= 40.0;
     if (const char* e = getenv("MKTFHE_B200_FFT")) c->fft = c->fft && atoi(e) != 0;
     if (const char* e = getenv("MKTFHE_B200_FFT_SMALL")) c->fft_small = atoi(e) != 0;
-    if (c->fft && c->fft_small) c->bsk_ntt_bytes = c->bsk_bytes = 0;
-    if (c->fft) c->bsk_bytes += (size_t)params->k * params->n * mkf::bsk_elem_cpx(params->l) * sizeof(mkf::cpx);
+    if (c->fft && (c->fft_small || c->t32)) c->bsk_ntt_bytes = c->bsk_bytes = 0;
+    if (c->fft) c->bsk_bytes += (size_t)params->k * params->n * mkf::bsk_elem_cpx(params->l, fft_nl(c)) * sizeof(mkf::cpx);
     c->gpc = big ? 1 : mk::gpc_for(params->l, c->t32);
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
     if (const char* e = getenv("MKTFHE_B200_LATENCY")) c->latency_kernel = atoi(e) != 0;
@@ -628,9 +667,9 @@ int mktfhe_load_bsk(mktfhe_ctx* c, int party, const int64_t* polys) {
             mk::bsk_transform_kernel<<<(ntasks + mk::XF_WARPS - 1) / mk::XF_WARPS, mk::XF_WARPS * 32, 0, c->stream>>>(
                 (const int64_t*)c->raw.p, c->d_bsk, n, l, party, c->d_twB, ntasks);
         if (c->fft) {
-            const int nt = n * 4 * l * mkf::LIMBS;
+            const int nt = n * 4 * l * fft_nl(c);
             mkf::bsk_transform_fft_kernel<<<(nt + mkf::XF_WARPS - 1) / mkf::XF_WARPS, mkf::XF_WARPS * 32, 0, c->stream>>>(
-                (const int64_t*)c->raw.p, c->d_bsk_fft, n, l, party, c->d_twF, nt);
+                (const int64_t*)c->raw.p, c->d_bsk_fft, n, l, fft_nl(c), party, c->d_twF, nt);
             c->launches++;
         }
     }
@@ -893,7 +932,16 @@ static int mktfhe_extprod_batch_1(mktfhe_ctx* c, size_t G, const int32_t* elem, 
     if ((rc = stage_in(c, c->elem, elem, G * 4)) || (rc = stage_in(c, c->accin, acc_in, accbytes)) || (rc = reserve(c, c->accout, accbytes))) return rc;
     const size_t sm = br_smem_bytes(c);
     const unsigned grid = (unsigned)((G + c->gpc - 1) / c->gpc);
-    if (c->t32) {
+    if (c->t32 && c->fft) {
+        const size_t smf = fft_smem_bytes(c);
+        const int gf = mkf::gpc_for(c->prm.l, true);
+        const unsigned gridf = (unsigned)((G + gf - 1) / gf);
+#define LAUNCH_EP_FFT_T32(L, GPC, dummy)                                                                                                  \
+    mkf::extprod_fft_kernel<L, GPC, true><<<gridf, GPC * mkf::TPG, smf, c->stream>>>((int)G, c->d_bsk_fft, c->d_twF, c->prm.bgbit, (const int32_t*)c->elem.p, \
+                                                                                      (const int64_t*)c->accin.p, (int64_t*)c->accout.p)
+        MK_DISPATCH_FFT_T32(c, LAUNCH_EP_FFT_T32, 0)
+#undef LAUNCH_EP_FFT_T32
+    } else if (c->t32) {
 #define LAUNCH_EP_T32(L, GPC, dummy)                                                                                                   \
     mk::extprod_t32_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, c->stream>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, (const int32_t*)c->elem.p, \
                                                                            (const int64_t*)c->accin.p, (int64_t*)c->accout.p)
@@ -1061,7 +1109,15 @@ int mktfhe_extprod_batch_dev(mktfhe_ctx* c, size_t G, const int32_t* elem, const
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     const size_t sm = br_smem_bytes(c);
     const unsigned grid = (unsigned)((G + c->gpc - 1) / c->gpc);
-    if (c->t32) {
+    if (c->t32 && c->fft) {
+        const size_t smf = fft_smem_bytes(c);
+        const int gf = mkf::gpc_for(c->prm.l, true);
+        const unsigned gridf = (unsigned)((G + gf - 1) / gf);
+#define LAUNCH_EPD_FFT_T32(L, GPC, dummy) \
+    mkf::extprod_fft_kernel<L, GPC, true><<<gridf, GPC * mkf::TPG, smf, st>>>((int)G, c->d_bsk_fft, c->d_twF, c->prm.bgbit, elem, acc_in, acc_out)
+        MK_DISPATCH_FFT_T32(c, LAUNCH_EPD_FFT_T32, 0)
+#undef LAUNCH_EPD_FFT_T32
+    } else if (c->t32) {
 #define LAUNCH_EPD_T32(L, GPC, dummy) mk::extprod_t32_kernel<L, GPC><<<grid, GPC * mk::TPG, sm, st>>>((int)G, c->d_bsk, c->d_twB, c->prm.bgbit, elem, acc_in, acc_out)
         MK_DISPATCH_T32(c, LAUNCH_EPD_T32, 0)
 #undef LAUNCH_EPD_T32
@@ -1111,7 +1167,17 @@ int mktfhe_ccs_blind_rotate_batch(mktfhe_ctx* c, int parties, int32_t mu, size_t
     const size_t sm = br_smem_bytes(c);
     const unsigned grid = (unsigned)((P + c->gpc - 1) / c->gpc);
     const dim3 gi((unsigned)G, (unsigned)(k + 1));
+    const size_t smf = c->fft ? fft_smem_bytes(c) : 0;
+    const int gf = mkf::gpc_for(c->prm.l, true);
+    const unsigned gridf = (unsigned)((P + gf - 1) / gf);
     auto products = [&]() {
+        if (c->fft) {   // body-only Torus32 products on the FFT channel
+#define LAUNCH_CCS_FFT(L, GPC, dummy) \
+    mkf::extprod_fft_kernel<L, GPC, true, true><<<gridf, GPC * mkf::TPG, smf, st>>>((int)P, c->d_bsk_fft, c->d_twF, c->prm.bgbit, elem, (const int64_t*)xin, (int64_t*)xout)
+            MK_DISPATCH_FFT_T32(c, LAUNCH_CCS_FFT, 0)
+#undef LAUNCH_CCS_FFT
+            return;
+        }
 #define LAUNCH_CCS_T32(L, GPC, dummy) \
     mk::extprod_t32_kernel<L, GPC, true><<<grid, GPC * mk::TPG, sm, st>>>((int)P, c->d_bsk, c->d_twB, c->prm.bgbit, elem, (const int64_t*)xin, (int64_t*)xout)
         MK_DISPATCH_T32(c, LAUNCH_CCS_T32, 0)
