@@ -498,8 +498,8 @@ def run_single_key(args):
     p = sk.params
     print(json.dumps({"metric": f"bootstrapped single-key TFHE NAND gates/sec ({pname})", "value": G * args.steps / (ms * 1e-3), "unit": UNIT,
                       "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                      "vs_baseline": None, "dtype": ("f64 (three-limb folded FFT, rounded to the exact integers mod 2^64)" if engine == "fft64" else
-                                                     "u32 RNS (three 28-bit-prime NTTs + CRT)") + ", Torus32 carried as v << 32 / int32 LWE", "data": "synthetic",
+                      "vs_baseline": None, "dtype": (("f64 (two-limb folded FFT, Torus32 mode)" if args.parties == 80 else "f64 (three-limb folded FFT, Torus32 carried as v << 32)")
+                                                    if engine == "fft64" else "u32 RNS (three 28-bit-prime NTTs + CRT)") + " / int32 LWE", "data": "synthetic",
                       "config": {"workload": f"single-key NAND x{G} (api.jl:76-113: n={p.lwe_size} N={p.rlwe_polynomial_degree} l={p.bs_decomp_length} "
                                              f"Bg=2^{p.bs_log2_base} t={p.ks_decomp_length} Bks=2^{p.ks_log2_base}), the 3gen engine with one party",
                                  "key_setup_s": round(t_keys, 2)},
@@ -543,7 +543,8 @@ def run_ccs(args):
     ok = bool(np.array_equal(TC.mk_decrypt(secret_keys, out), ~(bits[0] & bits[1])))
     print(json.dumps({"metric": "bootstrapped CCS 2-party MK NAND gates/sec (mktfhe_parameters_2party)", "value": G / dt, "unit": UNIT, "n_gpus": 1,
                       "steps": args.steps, "ms_per_step": 1e3 * dt, "higher_is_better": True, "vs_baseline": None,
-                      "dtype": "u32 RNS (three 28-bit-prime NTTs + CRT), Torus32 mode (9-bit gadget digits) / int32 LWE", "data": "synthetic",
+                      "dtype": ("f64 (two-limb folded FFT, rounded to the exact integers mod 2^32)" if ck.products.ctx.describe().get("external_product") == "fft64"
+                                else "u32 RNS (three 28-bit-prime NTTs + CRT)") + ", Torus32 mode (9-bit gadget digits) / int32 LWE", "data": "synthetic",
                       "config": {"workload": f"CCS NAND x{G} (mk_api.jl:4-10: n={params.lwe_size} N=1024 l=3 Bg=2^9 t=8 Bks=2^2, 2 parties): per blind-rotate "
                                              "step two launches of G x 3 external products + elementwise device ops; host buffers in and out",
                                  "key_setup_s": round(t_keys, 2)},

@@ -31,9 +31,9 @@
  *    they must be stream-ordered with each other (same stream, or ordered by
  *    events): two *_dev calls in flight on unordered streams race.
  *  - arithmetic: every external product is exact mod (X^N + 1, 2^64).  Contexts with
- *    N = 1024 and Torus64 keys compute it on the FP64 pipe (an exact three-limb
- *    folded complex FFT, csrc/fft64.cuh); Torus32 mode and N = 2048 on three / four
- *    28-bit NTT primes with a CRT lift.  Results are bit-identical either way;
+ *    N = 1024 compute it on the FP64 pipe (an exact folded complex FFT with the
+ *    key word split in three limbs, two in Torus32 mode: csrc/fft64.cuh); N = 2048
+ *    on four 28-bit NTT primes with a CRT lift.  Results are bit-identical either way;
  *    MKTFHE_B200_FFT=0 in the environment of mktfhe_create selects the NTT kernels
  *    (A/B runs), mktfhe_describe reports which engine a context runs.
  *  - ciphertext layout: MKLweSample (mk_internals.jl:23-37) `a::Array{Int32,2}`

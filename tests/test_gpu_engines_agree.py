@@ -65,3 +65,41 @@ def test_engines_agree_other_gadget_shapes(oracle, rng, l, bgbit, k):
     prm = dict(n=40, N=1024, k=k, l=l, bgbit=bgbit, t=5, basebit=2, sigma_lwe=2.0 ** -20, sigma_gsw=2.0 ** -40, sigma_ks=2.0 ** -20)
     ks = oracle.KeySet(prm, seed=100 + l, nthreads=os.cpu_count() or 8)
     check_engines(ks, 300, rng, extprods=6)
+
+
+@pytest.mark.parametrize("l,bgbit", [(2, 10), (3, 9), (4, 8)])
+def test_engines_agree_torus32_mode(rng, l, bgbit):
+    """Torus32 mode (MKTFHE_FLAG_TORUS32: unshifted 32-bit keys, 16-bit digit fields, products added as R << 32) -- the gadget shapes of
+    tfhe_parameters_80 and of the CCS sets: external products and whole bootstraps of the FFT channel (two 16-bit key limbs) against the RNS
+    kernels on uniformly random key words (nothing of a real key's structure is needed for the two engines to have to agree)."""
+    import torus_fhe_b200 as T
+    n, N, k, t, bb = 24, 1024, 1, 8, 2
+    sp = T.SchemeParameters_3gen(n, 2.0 ** -15, N, 1, False, l, bgbit, 2.0 ** -25, t, bb, 2.0 ** -15, k)
+    bsk = rng.integers(-2 ** 31, 2 ** 31, size=(n, 4, l, N), dtype=np.int64)          # 32-bit values in int64 words
+    bsk[0, 0, 0, :8] = [2 ** 31 - 1, -2 ** 31, 0, -1, 1, 2 ** 15, -2 ** 15, 2 ** 15 - 1]
+    ksk = rng.integers(-2 ** 31, 2 ** 31, size=(N, t, (1 << bb) - 1, n + 1), dtype=np.int64).astype(np.int32)
+    engines = []
+    try:
+        for f in (1, 0):
+            os.environ["MKTFHE_B200_FFT"] = str(f)
+            try:
+                eng = T.Engine(sp, device=0, flags=T._cabi.FLAG_TORUS32)
+            finally:
+                os.environ.pop("MKTFHE_B200_FFT", None)
+            eng.load_keys([bsk], [ksk])
+            engines.append(eng)
+        fft, ntt = engines
+        assert fft.ctx.describe()["external_product"] == "fft64" and ntt.ctx.describe()["external_product"] == "ntt_rns"
+        acc = rng.integers(-2 ** 31, 2 ** 31, size=(16, 2, N), dtype=np.int64) << 32
+        acc[0], acc[1], acc[2] = 0, np.int64(-1) << 32, np.int64(-2 ** 31) << 32
+        elem = rng.integers(0, n, size=16).astype(np.int32)
+        assert np.array_equal(fft.ctx.extprod_batch(elem, acc), ntt.ctx.extprod_batch(elem, acc))
+        for G in (5, 300):          # one gate per CTA / two gates per CTA
+            xa = rng.integers(-2 ** 31, 2 ** 31, size=(G, k, n), dtype=np.int64).astype(np.int32)
+            xb = rng.integers(-2 ** 31, 2 ** 31, size=G, dtype=np.int64).astype(np.int32)
+            a1, b1 = fft.ctx.bootstrap_batch((1 << 29) << 32, xa, xb)
+            a2, b2 = ntt.ctx.bootstrap_batch((1 << 29) << 32, xa, xb)
+            assert np.array_equal(a1, a2) and np.array_equal(b1, b2), G
+    finally:
+        for e in engines:
+            e.close()
