@@ -1,4 +1,11 @@
-// fft64.cuh -- the external product of the blind rotation on the FP64 pipe (N = 1024 parameter sets, byte-sized gadget digits).
+// fft64.cuh -- the external product of the blind rotation on the FP64 pipe: every N = 1024 parameter set (Torus64 keys with byte-sized gadget
+// digits; Torus32 mode with digits of up to 13 bits).
+//
+//   blind_rotate_fft_kernel<L, GPC>       gate prologue + mod-switch + k n mux-rotate steps + extraction + fused key switch; two six-warp gates per
+//                                         CTA (throughput) or one (batches and tails of at most one gate per SM)
+//   blind_rotate_fft_t32_kernel<L, GPC>   the same in Torus32 mode (two 16-bit key limbs, 16-bit digit fields, products added as R << 32)
+//   extprod_fft_kernel<L, GPC, T32, BODY> one external product per gate slot (parity hook; BODY: the rounds of the CCS hybrid product)
+//   bsk_transform_fft_kernel              one-time: int64 key polynomials -> limb spectra in the streaming layout
 //
 // Same exact result as the three-prime NTT kernels of kernels.cuh (every product mod (X^N + 1, 2^64), bit for bit), computed the way
 // the reference computes it -- a folded complex FFT (3-gen-mk-tfhe/src/polynomials.jl:208-242) -- but made EXACT: the Torus64 key word
@@ -18,7 +25,10 @@
 //   inverse  decimation in time, bit-reversed -> natural: pass B' has compile-time twiddles; the last stage and the untwist are done
 //            by the threads that round, recombine the limbs and update the accumulator
 // A warp holds a 512-point transform as 16 complex values per thread: position = h 256 + r 16 + l16 (lane = 16 h + l16, register r) in the
-// row layout, lane 16 + c (register c) in the column layout; one swizzled shared-memory transpose between the two.
+// row layout, lane 16 + c (register c) in the column layout; one swizzled shared-memory transpose between the two.  Of the 15 twiddles a
+// pass needs per thread, one per stage is loaded and the rest are compile-time multiples of it (fft64_core.cuh).
+// The arithmetic core lives in fft64_core.cuh (__host__ __device__: tests/host_emu/fft64_emu.cpp runs it on the CPU); measured decisions are in
+// DESIGN.md section 4d and profiles/ab_r2.txt.
 #pragma once
 #include <cuda_runtime.h>
 #include "kernels.cuh"
