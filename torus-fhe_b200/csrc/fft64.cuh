@@ -11,7 +11,7 @@
 // the reference computes it -- a folded complex FFT (3-gen-mk-tfhe/src/polynomials.jl:208-242) -- but made EXACT: the Torus64 key word
 // is split in three balanced limbs of 22 / 21 / 21 bits, so every limb product sum_s digit_s * limb_s is an integer below
 // 2 l N (Bg / 2) 2^21 <= 2^39, which a double-precision FFT of 512 complex points reproduces to within 2^-13 of an integer (measured
-// worst case, tools/fft_channel/proto.py; the rounding bound of the networks is 2^-8) -- rounding recovers it exactly and
+// worst case, tools/fft_channel/proto.py; the norm-wise rounding bound of the three transforms is about 2^-7) -- rounding recovers it exactly and
 // R = r0 + (r1 << 22) + (r2 << 43) mod 2^64 is the wrap the reference's Int64 arithmetic performs (tgsw_3gen.jl:102-113).
 //
 // Why: per gate and step the NTT formulation needs 12 forward + 6 inverse 1024-point transforms at 4 IMAD-pipe slots per butterfly
