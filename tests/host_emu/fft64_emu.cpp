@@ -19,12 +19,13 @@ typedef std::vector<cpx> Buf;
 static std::vector<cpx> TW;
 
 // one warp: forward transform from the digit words (dig: 256 words) or from real coefficients; result in the spectrum layout [c 32 + lane]
-static Buf warp_forward(const uint32_t* dig, const double* real, int half_bg) {
+static Buf warp_forward(const uint32_t* dig, const double* real, int half_bg, bool wide = false) {
     cpx v[32][16];
     Buf buf(M), out(M);
     for (int lane = 0; lane < 32; lane++) {
         const int h = lane >> 4, l16 = lane & 15;
-        if (dig) fwd_stage0_digits(v[lane], dig, lane, half_bg);
+        if (dig && wide) fwd_stage0_digits_wide(v[lane], dig, dig + 256, lane, half_bg);
+        else if (dig) fwd_stage0_digits(v[lane], dig, lane, half_bg);
         else
             for (int r = 0; r < 16; r++) {
                 const int j = 16 * r + l16;
@@ -153,6 +154,60 @@ int main() {
                 CHECK(R[b] - round_k(LIMBS) == want[j + 256 * b], "trial %d coefficient %d: got %llx want %llx", trial, j + 256 * b,
                       (unsigned long long)(R[b] - round_k(LIMBS)), (unsigned long long)want[j + 256 * b]);
             if (fails > 5) break;
+        }
+    }
+    // ---- 3. Torus32 form: 16-bit digit fields (Bg = 2^10, l = 2), two 16-bit limbs of 32-bit key words, R mod 2^32
+    for (int trial = 0; trial < 8; trial++) {
+        const int L2 = 4, bg = 10, hb = 1 << (bg - 1);
+        std::vector<std::vector<uint32_t>> dig(L2, std::vector<uint32_t>(512));
+        std::vector<std::vector<int64_t>> d(L2, std::vector<int64_t>(N)), key(L2, std::vector<int64_t>(N));
+        for (int s = 0; s < L2; s++)
+            for (int i = 0; i < N; i++) {
+                uint32_t f;
+                int32_t kv;
+                if (trial == 0) { f = 0; kv = s & 1 ? INT32_MIN : INT32_MAX; }
+                else if (trial == 1) { f = rng() & 1 ? 2 * hb - 1 : 0; kv = (rng() & 1 ? 1 : -1) * 0x7FFF7FFF; }
+                else { f = rng() % (2 * hb); kv = (int32_t)rng(); }
+                d[s][i] = (int64_t)f - hb;
+                key[s][i] = kv;
+                const int b = i >> 8, j = i & 255;          // word (b & 1, j): field b >> 1
+                dig[s][(b & 1) * 256 + j] |= f << (16 * (b >> 1));
+            }
+        std::vector<uint32_t> want(N, 0);
+        for (int s = 0; s < L2; s++)
+            for (int i = 0; i < N; i++) {
+                if (!d[s][i]) continue;
+                for (int j = 0; j < N; j++) {
+                    const uint32_t p = (uint32_t)d[s][i] * (uint32_t)key[s][j];
+                    if (i + j < N) want[i + j] += p; else want[i + j - N] -= p;
+                }
+            }
+        std::vector<Buf> spec(L2);
+        for (int s = 0; s < L2; s++) spec[s] = warp_forward(dig[s].data(), nullptr, hb, true);
+        std::vector<Buf> Y(LIMBS_T32);
+        for (int limb = 0; limb < LIMBS_T32; limb++) {
+            Buf acc(M, cpx{0, 0});
+            for (int s = 0; s < L2; s++) {
+                std::vector<double> kl(N);
+                for (int i = 0; i < N; i++) kl[i] = key_limb(key[s][i], limb, LIMBS_T32);
+                Buf K = warp_forward(nullptr, kl.data(), 0);
+                for (int p = 0; p < M; p++) {
+                    const cpx k = {K[p].x * (1.0 / M), K[p].y * (1.0 / M)}, x = spec[s][p];
+                    acc[p].x = fma(x.x, k.x, fma(-x.y, k.y, acc[p].x));
+                    acc[p].y = fma(x.x, k.y, fma(x.y, k.x, acc[p].y));
+                }
+            }
+            Y[limb] = warp_inverse(acc);
+        }
+        for (int j = 0; j < 256 && fails <= 5; j++) {
+            uint64_t R[4] = {0, 0, 0, 0};
+            for (int limb = 0; limb < LIMBS_T32; limb++)
+                recombine_limb(R, Y[limb][j], Y[limb][j + 256], TW[T_WJ + j], TW[T_UT + j], limb_shift(LIMBS_T32, limb));
+            for (int b = 0; b < 4; b++) {
+                const uint64_t top = (R[b] - round_k(LIMBS_T32)) << 32;           // what the kernel adds to the accumulator
+                CHECK(top == ((uint64_t)want[j + 256 * b] << 32), "Torus32 trial %d coefficient %d: got %llx want %llx", trial, j + 256 * b,
+                      (unsigned long long)top, (unsigned long long)want[j + 256 * b] << 32);
+            }
         }
     }
     CHECK(worst_frac < 1.0 / 64, "a limb result is %g away from an integer", worst_frac);
