@@ -1,7 +1,7 @@
 // Host emulation of the FP64 FFT channel (torus-fhe_b200/csrc/fft64_core.cuh, tables_fft.h): the per-thread passes the CUDA kernels run,
 // executed for 32 emulated lanes with the kernels' own buffer slots, against (1) the definition of the transform -- evaluation at the
-// roots of X^512 - i -- and (2) the wrap-around integer external product sum_s digit_s * key_s mod (X^N + 1, 2^64), including operands at
-// the extremes of their ranges.  Prints the worst distance of a limb result to an integer (the margin of the rounding).
+// roots of X^512 - i -- and (2) the wrap-around integer external product sum_s digit_s * key_s mod (X^N + 1, 2^64), and mod 2^32 in the Torus32
+// form (16-bit digit fields, two key limbs), including operands at the extremes of their ranges.  Prints the worst distance of a limb result to an integer (the margin of the rounding).
 #include <cmath>
 #include <complex>
 #include <cstdint>
