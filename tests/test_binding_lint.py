@@ -137,6 +137,40 @@ def test_single_key_julia_shim_matches_the_header():
     assert table == O1.GATE_LINEAR
 
 
+def test_ccs_julia_shim_matches_the_header():
+    """julia/TFHE_CCS_B200.jl (the CCS multi-key gate API over the same library): every ccall against the C declarations, the CParams struct,
+    balanced blocks, every exported name defined, and the same pseudo-party numbering of the hybrid product's key elements as the Python
+    twin (tfhe_ccs.build_elements)."""
+    decls = c_declarations()
+    calls = julia_ccalls("TFHE_CCS_B200.jl")
+    assert len(calls) >= 10
+    for name, ret, types, args in calls:
+        assert name in decls, name
+        cret, cparams = decls[name]
+        assert cret in JULIA_TO_C[ret], (name, ret, cret)
+        assert len(types) == len(cparams) == len(args), (name, types, cparams, args)
+        for jt, ct in zip(types, cparams):
+            assert ct in JULIA_TO_C[jt], f"{name}: Julia {jt} bound to C {ct}"
+    bound = {c[0] for c in calls}
+    for must in ("mktfhe_create", "mktfhe_load_bsk", "mktfhe_load_ksk", "mktfhe_mark_keys_received", "mktfhe_finalize_keys",
+                 "mktfhe_ccs_blind_rotate_batch", "mktfhe_mk_keyswitch_batch", "mktfhe_destroy", "mktfhe_last_error"):
+        assert must in bound, must
+    raw = open(os.path.join(ROOT, "julia", "TFHE_CCS_B200.jl")).read()
+    text = _julia_balance(raw)
+    body = re.search(r"struct CParams.*?\n(.*?)\nend", raw, flags=re.S).group(1)
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "mktfhe_b200.h")).read(), flags=re.S)
+    cfields = re.findall(r"int32_t\s+([A-Za-z_]+);", re.search(r"typedef struct \{(.*?)\} mktfhe_params;", header, flags=re.S).group(1))
+    assert re.findall(r"([A-Za-z_]+)::Int32", body) == cfields
+    exported = re.search(r"\nexport (.*?)\n\n", text + "\n\n", flags=re.S).group(1)
+    for name in re.findall(r"[A-Za-z_][A-Za-z_0-9!]*", exported):
+        assert re.search(rf"(function |struct |^){re.escape(name)}(?![A-Za-z_0-9!])", text, flags=re.M), f"exported {name} is not defined"
+    # pseudo-party numbering: round 1 of polynomial i in party p's steps = p (k + 1) + i, round 2 = k (k + 1) + p (0-based), as in the twin
+    assert "(party - 1) * (k + 1) + i" in raw and "k * (k + 1) + party - 1" in raw
+    twin = open(os.path.join(ROOT, "torus-fhe_b200", "tfhe_ccs.py")).read()
+    assert "elems[pi * (k + 1) + i" in twin and "elems[k * (k + 1) + pi" in twin
+    assert re.search(r"MKTFHE_FLAG_TORUS32\s+1", header) and "FLAG_TORUS32 = Int32(1)" in raw
+
+
 def test_julia_cparams_struct_matches_mktfhe_params():
     text = open(os.path.join(ROOT, "julia", "TFHE_B200.jl")).read()
     body = re.search(r"struct CParams.*?\n(.*?)\nend", text, flags=re.S).group(1)
