@@ -57,6 +57,7 @@ struct mktfhe_ctx {
     mkf::cpx* d_twF = nullptr;
     int gpc = 1;                 // gates per CTA of the blind-rotate / external-product kernels
     int num_sms = 0;
+    bool split_tail_all = false; // MKTFHE_B200_SPLIT_TAIL=2: the tail launch at every l, not only l = 2
     bool split_tail = true;      // MKTFHE_B200_SPLIT_TAIL=0: no separate one-gate-per-CTA launch for the tail of a large batch (A/B)
     bool latency_kernel = true;  // MKTFHE_B200_LATENCY=0 turns the 12-warp small-batch launch off (A/B)
     bool t32 = false;            // Torus32 mode (MKTFHE_FLAG_TORUS32): blind_rotate_t32_kernel / extprod_t32_kernel
@@ -313,7 +314,8 @@ void launch_blind_rotate(mktfhe_ctx* c, const mk::BlindRotateArgs& a, size_t G, 
     size_t tail = gpc > 1 ? G % wave : 0;
     // the tail of a larger batch is split off only at l = 2, where it was measured to pay on two workloads; at l = 3 the split lost 1.2 %
     // (the partial last wave of the throughput grid cost 3 ms there, not a full wave), profiles/ab_r1.txt
-    if (tail > (size_t)c->num_sms || ((!c->split_tail || c->prm.l != 2) && tail != G)) tail = 0;
+    // (RNS kernels).  MKTFHE_B200_SPLIT_TAIL=2 splits at every l (A/B knob for the FFT kernels)
+    if (tail > (size_t)c->num_sms || ((!c->split_tail || (c->prm.l != 2 && !c->split_tail_all)) && tail != G)) tail = 0;
     const size_t head = G - tail;
     if (head) {
         mk::BlindRotateArgs h = a;
@@ -596,7 +598,7 @@ int mktfhe_create(const mktfhe_params* params, int device, mktfhe_ctx** out) {
     c->gpc = big ? 1 : mk::gpc_for(params->l, c->t32);
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
     if (const char* e = getenv("MKTFHE_B200_LATENCY")) c->latency_kernel = atoi(e) != 0;
-    if (const char* e = getenv("MKTFHE_B200_SPLIT_TAIL")) c->split_tail = atoi(e) != 0;
+    if (const char* e = getenv("MKTFHE_B200_SPLIT_TAIL")) { c->split_tail = atoi(e) != 0; c->split_tail_all = atoi(e) == 2; }
     if (const char* e = getenv("MKTFHE_B200_FUSE_KS")) c->fuse_ks = atoi(e) != 0;
     if (const char* e = getenv("MKTFHE_B200_2K")) c->two_k16 = atoi(e) != 8;
     const size_t ks_stride = mk::ks_row_stride(params->n);   // rows padded to 16 bytes on the device
